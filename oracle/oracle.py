@@ -1,0 +1,370 @@
+"""ctypes front end of the CPU ORACLE (test infrastructure, NOT product code).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may
+import this module.  It builds oracle/libsho_oracle.so on demand (g++ only) and exposes the
+restated reference functions with numpy arrays.  See oracle/sho_core.hpp for the parity status.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+c_dp = C.POINTER(C.c_double)
+c_i32p = C.POINTER(C.c_int32)
+c_i64p = C.POINTER(C.c_int64)
+c_u8p = C.POINTER(C.c_uint8)
+
+N_GEO = 12  # x y z area catchment_id radiation_slope_factor glacier lake reservoir forest routing_id routing_distance
+PTGSK_RESPONSES = ("avg_discharge", "charge_m3s", "snow_sca", "snow_swe", "snow_outflow", "glacier_melt", "ae_output", "pe_output")
+PTGSK_STATES = ("kirchner_discharge", "gs_albedo", "gs_lwc", "gs_surface_heat", "gs_alpha", "gs_sdc_melt_mean", "gs_acc_melt",
+                "gs_iso_pot_energy", "gs_temp_swe")
+HS_RESPONSES = PTGSK_RESPONSES + ("soil_outflow",)
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libsho_oracle.so")
+    srcs = [os.path.join(_HERE, f) for f in ("capi.cpp", "sho_core.hpp", "sho_pt_gs_k.hpp", "sho_hbv.hpp", "sho_region.hpp")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "libsho_oracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        L = _LIB
+        L.sho_last_error.restype = C.c_char_p
+        for name in ("sho_day_of_year", "sho_trim_year", "sho_calendar_time", "sho_catchment_index"):
+            getattr(L, name).restype = C.c_int64
+        for name in ("sho_gamma_p", "sho_gamma_quantile", "sho_pt_potential_evapotranspiration", "sho_ae_calculate_step",
+                     "sho_glacier_melt_step", "sho_gs_corr_lwc", "sho_gs_calc_q", "sho_hbv_soil_step", "sho_hbv_tank_step",
+                     "sho_hbv_ae_step", "sho_btk_prior_gradient", "sho_nash_sutcliffe", "sho_rmse", "sho_kling_gupta", "sho_abs_diff_sum"):
+            getattr(L, name).restype = C.c_double
+    return _LIB
+
+
+def _d(a):
+    return a.ctypes.data_as(c_dp)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _check(rc):
+    if rc != 0:
+        raise RuntimeError(lib().sho_last_error().decode())
+
+
+def hardware_concurrency():
+    return int(lib().sho_hardware_concurrency())
+
+
+# ---- calendar / special ---------------------------------------------------------------------
+def day_of_year(t_us):
+    return int(lib().sho_day_of_year(C.c_int64(int(t_us))))
+
+
+def trim_year(t_us):
+    return int(lib().sho_trim_year(C.c_int64(int(t_us))))
+
+
+def calendar_time(y, m, d):
+    return int(lib().sho_calendar_time(int(y), int(m), int(d)))
+
+
+def gamma_p(a, x):
+    return float(lib().sho_gamma_p(C.c_double(a), C.c_double(x)))
+
+
+def gamma_quantile(alpha, p):
+    return float(lib().sho_gamma_quantile(C.c_double(alpha), C.c_double(p)))
+
+
+# ---- method units ------------------------------------------------------------------------------
+def pt_potential_evapotranspiration(albedo, alpha, t, rad, rh):
+    return float(lib().sho_pt_potential_evapotranspiration(*(C.c_double(v) for v in (albedo, alpha, t, rad, rh))))
+
+
+def ae_calculate_step(water_level, pot, scale, snow_fraction):
+    return float(lib().sho_ae_calculate_step(*(C.c_double(v) for v in (water_level, pot, scale, snow_fraction))))
+
+
+def glacier_melt_step(dtf, t, sca_m2, glacier_m2):
+    return float(lib().sho_glacier_melt_step(*(C.c_double(v) for v in (dtf, t, sca_m2, glacier_m2))))
+
+
+def kirchner_step(q, p, e, dt_us=3600 * 10**6, c=(-2.439, 0.966, -0.10), abs_err=1e-7, rel_err=1e-8):
+    """-> (q_end, q_avg, n_accepted, n_rejected)"""
+    qq, qa = C.c_double(q), C.c_double(0.0)
+    na, nr = C.c_int(0), C.c_int(0)
+    _check(lib().sho_kirchner_step(C.c_double(c[0]), C.c_double(c[1]), C.c_double(c[2]), C.c_double(abs_err), C.c_double(rel_err),
+                                   C.c_int64(dt_us), C.byref(qq), C.byref(qa), C.c_double(p), C.c_double(e), C.byref(na), C.byref(nr)))
+    return qq.value, qa.value, na.value, nr.value
+
+
+GS_PARAM_DEFAULT = dict(winter_end_day_of_year=100, initial_bare_ground_fraction=0.04, snow_cv=0.4, tx=-0.5, wind_scale=2.0, wind_const=1.0,
+                        max_water=0.1, surface_magnitude=30.0, max_albedo=0.9, min_albedo=0.6, fast_albedo_decay_rate=5.0,
+                        slow_albedo_decay_rate=5.0, snowfall_reset_depth=5.0, glacier_albedo=0.4, calculate_iso_pot_energy=0.0,
+                        snow_cv_forest_factor=0.0, snow_cv_altitude_factor=0.0, n_winter_days=221)
+
+
+def gs_param(**kw):
+    d = dict(GS_PARAM_DEFAULT)
+    d.update(kw)
+    return _f64([float(d[k]) for k in GS_PARAM_DEFAULT])
+
+
+def gs_calc_snow_state(shape, scale, y0, lam, lwd, max_water_frac, temp_swe):
+    swe, sca = C.c_double(0), C.c_double(0)
+    lib().sho_gs_calc_snow_state(*(C.c_double(v) for v in (shape, scale, y0, lam, lwd, max_water_frac, temp_swe)), C.byref(swe), C.byref(sca))
+    return swe.value, sca.value
+
+
+def gs_corr_lwc(z1, a1, b1, z2, a2, b2):
+    n = C.c_int(0)
+    r = lib().sho_gs_corr_lwc(*(C.c_double(v) for v in (z1, a1, b1, z2, a2, b2)), C.byref(n))
+    return float(r), n.value
+
+
+def gs_calc_q(a, b, z):
+    return float(lib().sho_gs_calc_q(C.c_double(a), C.c_double(b), C.c_double(z)))
+
+
+def gs_reset_snow_pack(storage, **kw):
+    out = np.zeros(6)
+    p = gs_param(**kw)
+    lib().sho_gs_reset_snow_pack(_d(p), C.c_double(storage), _d(out))
+    return dict(zip(("sca", "lwc", "alpha", "sdc_melt_mean", "acc_melt", "temp_swe"), out))
+
+
+def gs_step(state8, t_us, dt_us, T, rad, prec_mm_h, wind_speed, rel_hum, forest_fraction=0.0, altitude=0.0, **kw):
+    """state8: albedo lwc surface_heat alpha sdc_melt_mean acc_melt iso_pot_energy temp_swe -> (state8', (sca, storage, outflow))"""
+    s = _f64(state8).copy()
+    r = np.zeros(3)
+    p = gs_param(**kw)
+    _check(lib().sho_gs_step(_d(p), _d(s), _d(r), C.c_int64(t_us), C.c_int64(dt_us),
+                             *(C.c_double(v) for v in (T, rad, prec_mm_h, wind_speed, rel_hum, forest_fraction, altitude))))
+    return s, r
+
+
+# ---- stack runs -----------------------------------------------------------------------------------
+def _ptrs(arrs):
+    P = (c_dp * len(arrs))()
+    for i, a in enumerate(arrs):
+        P[i] = _d(a) if a is not None else None
+    return P
+
+
+def ptgsk_run_cells(geo, params, forcing, state, t0_us, dt_us, n_axis=None, start_step=0, n_steps=0, pset_of_cell=None,
+                    collect_response=True, collect_state=False, collect_substeps=False, cell_mask=None, ncore=1):
+    """Reference-equivalent pt_gs_k run_cells on the CPU.
+
+    geo [n][12]; params [n_sets][31]; forcing dict of [T][n] arrays (temperature, precipitation, radiation, wind_speed, rel_hum);
+    state [n][9] (8 gamma_snow doubles + kirchner.q).  Returns dict(state=[n][9], <response>=[T][n], <state series>=[T+1][n]).
+    """
+    geo = _f64(geo)
+    n = geo.shape[0]
+    params = _f64(params).reshape(-1, 31)
+    f = [_f64(forcing[k]) for k in ("temperature", "precipitation", "radiation", "wind_speed", "rel_hum")]
+    T = f[0].shape[0] if n_axis is None else n_axis
+    st = _f64(state).reshape(n, 9).copy()
+    out = {}
+    resp = [np.full((T, n), np.nan) if collect_response else None for _ in PTGSK_RESPONSES]
+    sts = [np.full((T + 1, n), np.nan) if collect_state else None for _ in PTGSK_STATES]
+    sub = np.zeros((T, n)) if collect_substeps else None
+    ps = np.ascontiguousarray(pset_of_cell, dtype=np.int32) if pset_of_cell is not None else None
+    mask = np.ascontiguousarray(cell_mask, dtype=np.uint8) if cell_mask is not None else None
+    _check(lib().sho_ptgsk_run_cells(
+        C.c_int64(n), _d(geo), C.c_int64(params.shape[0]), _d(params), ps.ctypes.data_as(c_i32p) if ps is not None else None,
+        C.c_int64(t0_us), C.c_int64(dt_us), C.c_int64(T), C.c_int(start_step), C.c_int(n_steps),
+        _d(f[0]), _d(f[1]), _d(f[2]), _d(f[3]), _d(f[4]), C.c_int64(n), C.c_int64(1), _d(st),
+        _ptrs(resp) if collect_response else None, _ptrs(sts) if collect_state else None, _d(sub) if sub is not None else None,
+        C.c_int64(n), C.c_int64(1), mask.ctypes.data_as(c_u8p) if mask is not None else None, C.c_int(ncore)))
+    out["state"] = st
+    if collect_response:
+        out.update(dict(zip(PTGSK_RESPONSES, resp)))
+    if collect_state:
+        out.update(dict(zip(PTGSK_STATES, sts)))
+    if collect_substeps:
+        out["kirchner_substeps"] = sub
+    return out
+
+
+def _hs_run(fn, n_param, geo, params, forcing, state, t0_us, dt_us, start_step, n_steps, pset_of_cell, ncore):
+    geo = _f64(geo)
+    n = geo.shape[0]
+    params = _f64(params).reshape(-1, n_param)
+    f = [_f64(forcing[k]) for k in ("temperature", "precipitation", "radiation", "wind_speed", "rel_hum")]
+    T = f[0].shape[0]
+    st = _f64(state).copy()
+    n_state = st.shape[1]
+    resp = [np.full((T, n), np.nan) for _ in HS_RESPONSES]
+    ps = np.ascontiguousarray(pset_of_cell, dtype=np.int32) if pset_of_cell is not None else None
+    _check(fn(C.c_int64(n), _d(geo), C.c_int64(params.shape[0]), _d(params), C.c_int(n_param), ps.ctypes.data_as(c_i32p) if ps is not None else None,
+              C.c_int64(t0_us), C.c_int64(dt_us), C.c_int64(T), C.c_int(start_step), C.c_int(n_steps),
+              _d(f[0]), _d(f[1]), _d(f[2]), _d(f[3]), _d(f[4]), C.c_int64(n), C.c_int64(1), _d(st), C.c_int(n_state),
+              _ptrs(resp), C.c_int64(n), C.c_int64(1), C.c_int(ncore)))
+    out = dict(zip(HS_RESPONSES, resp))
+    out["state"] = st
+    return out
+
+
+def pthsk_run_cells(geo, params, forcing, state, t0_us, dt_us, start_step=0, n_steps=0, pset_of_cell=None, ncore=1):
+    """state [n][3+2*nb] = swe, sca, sp[nb], sw[nb], kirchner.q"""
+    return _hs_run(lib().sho_pthsk_run_cells, 18, geo, params, forcing, state, t0_us, dt_us, start_step, n_steps, pset_of_cell, ncore)
+
+
+def hbv_stack_run_cells(geo, params, forcing, state, t0_us, dt_us, start_step=0, n_steps=0, pset_of_cell=None, ncore=1):
+    """state [n][5+2*nb] = swe, sca, sp[nb], sw[nb], soil.sm, tank.uz, tank.lz"""
+    return _hs_run(lib().sho_hbv_stack_run_cells, 22, geo, params, forcing, state, t0_us, dt_us, start_step, n_steps, pset_of_cell, ncore)
+
+
+def hbv_snow_step(sp, sw, swe, sca, prec, temp, dt_us=3600 * 10**6, s=None, intervals=None, tx=0.0, cx=1.0, ts=0.0, lw=0.1, cfr=0.5):
+    n = len(sp)
+    s = _f64(s if s is not None else [1.0] * n)
+    iv = _f64(intervals if intervals is not None else np.linspace(0, 1, n))
+    sp, sw = _f64(sp).copy(), _f64(sw).copy()
+    cswe, csca, out = C.c_double(swe), C.c_double(sca), C.c_double(0)
+    par = _f64([tx, cx, ts, lw, cfr])
+    _check(lib().sho_hbv_snow_step(_d(s), _d(iv), C.c_int(n), _d(par), _d(sp), _d(sw), C.byref(cswe), C.byref(csca), C.c_int64(dt_us),
+                                   C.c_double(prec), C.c_double(temp), C.byref(out)))
+    return sp, sw, cswe.value, csca.value, out.value
+
+
+def hbv_soil_step(sm, insoil, act_evap, fc=300.0, beta=2.0):
+    s = C.c_double(sm)
+    out = lib().sho_hbv_soil_step(C.c_double(fc), C.c_double(beta), C.byref(s), C.c_double(insoil), C.c_double(act_evap))
+    return s.value, float(out)
+
+
+def hbv_tank_step(uz, lz, soil_outflow, uz1=25.0, kuz2=0.5, kuz1=0.3, perc=0.8, klz=0.02):
+    u, l = C.c_double(uz), C.c_double(lz)
+    par = _f64([uz1, kuz2, kuz1, perc, klz])
+    out = lib().sho_hbv_tank_step(_d(par), C.byref(u), C.byref(l), C.c_double(soil_outflow))
+    return u.value, l.value, float(out)
+
+
+def hbv_ae_step(sm, pot, lp, snow_fraction):
+    return float(lib().sho_hbv_ae_step(*(C.c_double(v) for v in (sm, pot, lp, snow_fraction))))
+
+
+# ---- interpolation -----------------------------------------------------------------------------------
+IDW_KINDS = dict(temperature=0, precipitation=1, radiation=2, wind_speed=3, rel_hum=4)
+
+
+def idw_par(max_members=10, max_distance=200000.0, distance_measure_factor=2.0, zscale=1.0, default_temp_gradient=-0.006,
+            gradient_by_equation=False, scale_factor=1.02):
+    return _f64([max_members, max_distance, distance_measure_factor, zscale, default_temp_gradient, float(gradient_by_equation), scale_factor])
+
+
+def idw_run(kind, src_xyz, src_values, dst_xyz, par, dst_slope=None, ncore=1):
+    """src_values [T][n_src] -> [T][n_dst]"""
+    src_xyz, dst_xyz, v = _f64(src_xyz), _f64(dst_xyz), _f64(src_values)
+    T, ns = v.shape
+    nd = dst_xyz.shape[0]
+    out = np.full((T, nd), np.nan)
+    sl = _f64(dst_slope) if dst_slope is not None else None
+    _check(lib().sho_idw_run(C.c_int(IDW_KINDS[kind]), C.c_int64(ns), _d(src_xyz), _d(v), C.c_int64(T), C.c_int64(nd), _d(dst_xyz),
+                             _d(sl) if sl is not None else None, _d(_f64(par)), _d(out), C.c_int64(nd), C.c_int64(1), C.c_int(ncore)))
+    return out
+
+
+def idw_neighbours(src_xyz, dst_xyz, par):
+    src_xyz, dst_xyz = _f64(src_xyz), _f64(dst_xyz)
+    nd, mm = dst_xyz.shape[0], int(par[0])
+    idx = np.full((nd, mm), -1, dtype=np.int32)
+    w = np.zeros((nd, mm))
+    cnt = np.zeros(nd, dtype=np.int32)
+    _check(lib().sho_idw_neighbours(C.c_int64(src_xyz.shape[0]), _d(src_xyz), C.c_int64(nd), _d(dst_xyz), _d(_f64(par)),
+                                    idx.ctypes.data_as(c_i32p), _d(w), cnt.ctypes.data_as(c_i32p)))
+    return idx, w, cnt
+
+
+def btk_par(gradient_sd=0.0025, sill=25.0, nug=0.5, range_=200000.0, zscale=20.0):
+    return _f64([gradient_sd, sill, nug, range_, zscale])
+
+
+def btk_run(src_xyz, src_values, dst_xyz, t0_us, dt_us, par=None):
+    src_xyz, dst_xyz, v = _f64(src_xyz), _f64(dst_xyz), _f64(src_values)
+    T, ns = v.shape
+    nd = dst_xyz.shape[0]
+    out = np.full((T, nd), np.nan)
+    _check(lib().sho_btk_run(C.c_int64(ns), _d(src_xyz), _d(v), C.c_int64(t0_us), C.c_int64(dt_us), C.c_int64(T), C.c_int64(nd), _d(dst_xyz),
+                             _d(par if par is not None else btk_par()), _d(out), C.c_int64(nd), C.c_int64(1)))
+    return out
+
+
+def btk_covariance(src_xyz, dst_xyz, par=None):
+    src_xyz, dst_xyz = _f64(src_xyz), _f64(dst_xyz)
+    ns, nd = src_xyz.shape[0], dst_xyz.shape[0]
+    K, k = np.zeros((ns, ns)), np.zeros((ns, nd))
+    _check(lib().sho_btk_covariance(C.c_int64(ns), _d(src_xyz), C.c_int64(nd), _d(dst_xyz), _d(par if par is not None else btk_par()), _d(K), _d(k)))
+    return K, k
+
+
+def btk_prior_gradient(t_us, dt_us):
+    return float(lib().sho_btk_prior_gradient(C.c_int64(t_us), C.c_int64(dt_us)))
+
+
+def average_accessor_same_axis(values, dt_us):
+    v = _f64(values).copy()
+    lib().sho_average_accessor_same_axis(_d(v), C.c_int64(v.size), C.c_int64(dt_us))
+    return v
+
+
+# ---- routing -----------------------------------------------------------------------------------------
+def make_uhg(n_steps, alpha, beta):
+    out = np.zeros(max(1, n_steps))
+    n = C.c_int(0)
+    _check(lib().sho_make_uhg(C.c_int(n_steps), C.c_double(alpha), C.c_double(beta), _d(out), C.byref(n)))
+    return out[: n.value].copy()
+
+
+def uhg_steps(distance, velocity, dt_us):
+    return int(lib().sho_uhg_steps(C.c_double(distance), C.c_double(velocity), C.c_int64(dt_us)))
+
+
+def river_flows(rivers, rid, cell_discharge, cell_rid, cell_distance, cell_uhg_par, dt_us):
+    """rivers [n][6] = id downstream_id distance velocity alpha beta; cell_discharge [T][n_cells] -> (local, upstream, output) each [T]"""
+    rivers, q = _f64(rivers).reshape(-1, 6), _f64(cell_discharge)
+    T, n = q.shape
+    out = np.zeros((3, T))
+    crid = np.ascontiguousarray(cell_rid, dtype=np.int64)
+    _check(lib().sho_river_flows(C.c_int64(rivers.shape[0]), _d(rivers), C.c_int64(rid), C.c_int64(n), _d(q), C.c_int64(n), C.c_int64(1),
+                                 crid.ctypes.data_as(c_i64p), _d(_f64(cell_distance)), _d(_f64(cell_uhg_par)), C.c_int64(T), C.c_int64(dt_us), _d(out)))
+    return out[0], out[1], out[2]
+
+
+# ---- goal functions -----------------------------------------------------------------------------------
+def nash_sutcliffe(o, m):
+    o, m = _f64(o), _f64(m)
+    return float(lib().sho_nash_sutcliffe(_d(o), _d(m), C.c_int64(o.size)))
+
+
+def rmse(o, m):
+    o, m = _f64(o), _f64(m)
+    return float(lib().sho_rmse(_d(o), _d(m), C.c_int64(o.size)))
+
+
+def kling_gupta(o, m, s_r=1.0, s_a=1.0, s_b=1.0):
+    o, m = _f64(o), _f64(m)
+    return float(lib().sho_kling_gupta(_d(o), _d(m), C.c_int64(o.size), C.c_double(s_r), C.c_double(s_a), C.c_double(s_b)))
+
+
+def abs_diff_sum(o, m):
+    o, m = _f64(o), _f64(m)
+    return float(lib().sho_abs_diff_sum(_d(o), _d(m), C.c_int64(o.size)))
+
+
+def catchment_index(cids):
+    cid = np.ascontiguousarray(cids, dtype=np.int64)
+    cix = np.zeros_like(cid)
+    m = np.zeros_like(cid)
+    n = lib().sho_catchment_index(C.c_int64(cid.size), cid.ctypes.data_as(c_i64p), cix.ctypes.data_as(c_i64p), m.ctypes.data_as(c_i64p))
+    return cix, m[:n].copy()

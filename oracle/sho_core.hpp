@@ -1,0 +1,669 @@
+// ============================================================================
+// oracle/sho_core.hpp -- CPU ORACLE (test infrastructure, NOT product code)
+//
+// A dependency-free C++17 restatement of the Shyft per-cell time-stepping hot
+// path (reference: magneano/shyft, VERSION 1675).  It exists only so that
+// tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+// reference leg have something to check and time the CUDA path against.
+// Nothing under shyft_b200/ may include, link or call it.
+//
+// Every function cites the reference file:line it follows (paths relative to
+// the reference root).  Third-party arithmetic that is not in the reference
+// tree (boost 1.68 odeint / math, pinned at
+// build_support/build_dependencies.sh:5-8) is restated from its published
+// algorithm; see the notes at each restatement.
+//
+// PARITY STATUS
+//  * pinned: everything except the incomplete-gamma branch of gamma_snow is
+//    checked against the reference's own known answers (tests/test_oracle_*).
+//  * "parity unpinned": boost::math::gamma_p / lgamma under
+//    policy<digits10<5>> / <digits10<10>> (core/gamma_snow.h:189-201) cannot
+//    be reproduced offline (precision-selected Lanczos tables are not
+//    available); the oracle evaluates them in full double precision.
+// ============================================================================
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <limits>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace sho {
+
+// ---------------------------------------------------------------------------
+// time: utctime = int64 microseconds since epoch  (core/utctime_utilities.h:28-34)
+// ---------------------------------------------------------------------------
+using utctime = int64_t;
+using utctimespan = int64_t;
+constexpr int64_t USEC = 1000000LL;
+constexpr utctimespan HOUR = 3600LL * USEC;
+constexpr utctimespan DAY = 86400LL * USEC;
+constexpr double nan_v = std::numeric_limits<double>::quiet_NaN();
+
+inline double to_seconds(utctimespan dt) { return double(dt) / double(USEC); }  // utctime_utilities.h:68
+inline utctimespan deltahours(int64_t h) { return h * HOUR; }
+
+struct fixed_dt {  // core/time_axis.h:74-115
+    utctime t = 0;
+    utctimespan dt = 0;
+    size_t n = 0;
+    size_t size() const { return n; }
+    utctime time(size_t i) const { return t + int64_t(i) * dt; }
+};
+
+namespace calendar {
+// Julian day arithmetic, core/utctime_utilities.h:342-365 (UTC only; the hot path
+// always uses the default UTC calendar, gamma_snow.h:47, bayesian_kriging.h:206)
+constexpr int64_t UnixDay = 2440588;
+constexpr int64_t UnixSecond = 86400LL * UnixDay;
+struct ymd { int year, month, day; };
+inline int64_t day_number(int year, int month, int day) {
+    int a = (14 - month) / 12;
+    int y = year + 4800 - a;
+    int m = month + 12 * a - 3;
+    return day + ((153 * m + 2) / 5) + 365LL * y + (y / 4) - (y / 100) + (y / 400) - 32045;
+}
+inline ymd from_day_number(int64_t dn) {
+    int64_t a = dn + 32044;
+    int64_t b = (4 * a + 3) / 146097;
+    int64_t c = a - ((146097 * b) / 4);
+    int64_t d = (4 * c + 3) / 1461;
+    int64_t e = c - (1461 * d) / 4;
+    int64_t m = (5 * e + 2) / 153;
+    ymd r;
+    r.day = int(e - ((153 * m + 2) / 5) + 1);
+    r.month = int(m + 3 - 12 * (m / 10));
+    r.year = int(100 * b + d - 4800 + (m / 10));
+    return r;
+}
+inline int64_t day_number(utctime t) { return (UnixSecond + t / USEC) / 86400; }
+inline utctime time(int y, int m, int d) { return (day_number(y, m, d) - UnixDay) * DAY; }
+// core/utctime_utilities.cpp:230-235
+inline size_t day_of_year(utctime t) {
+    int64_t jdn = day_number(t);
+    ymd x = from_day_number(jdn);
+    return size_t(1 + jdn - day_number(x.year, 1, 1));
+}
+// core/utctime_utilities.cpp:248-255 (deltaT == YEAR branch)
+inline utctime trim_year(utctime t) {
+    ymd x = from_day_number(day_number(t));
+    return time(x.year, 1, 1);
+}
+}  // namespace calendar
+
+// ---------------------------------------------------------------------------
+// unit conversion  (core/unit_conversion.h:6-15)
+// ---------------------------------------------------------------------------
+constexpr double mmh_to_m3s_scale_factor = 1 / (3600.0 * 1000.0);
+inline double mmh_to_m3s(double mmh, double area_m2) { return area_m2 * mmh * mmh_to_m3s_scale_factor; }
+inline double m3s_to_mmh(double m3s, double area_m2) { return m3s / (mmh_to_m3s_scale_factor * area_m2); }
+
+// ---------------------------------------------------------------------------
+// special functions restating boost 1.68 (third-party, absent from the tree)
+// ---------------------------------------------------------------------------
+namespace special {
+
+inline double lgamma_(double a) { return std::lgamma(a); }  // boost::math::lgamma, gamma_snow.h:199-201 (full double here)
+
+// common prefix x^a e^-x / Gamma(a); the same expression order gamma_snow.h:245,254 uses
+inline double gamma_prefix(double a, double x) { return std::exp(a * std::log(x) - x - lgamma_(a)); }
+
+// Regularised lower incomplete gamma P(a,x), a>0, x>=0.   Replaces boost::math::gamma_p
+// (gamma_snow.h:195-197).  Full-double evaluation: power series for x < a+1, modified-Lentz
+// continued fraction for Q otherwise (Abramowitz & Stegun 6.5.29 / 6.5.31).  "parity unpinned"
+// versus boost's reduced-precision policies, see header.
+inline double gamma_p(double a, double x) {
+    if (!(x > 0.0)) return 0.0;
+    if (std::isinf(x)) return 1.0;
+    const double eps = 1.0e-16;
+    const double pre = gamma_prefix(a, x);
+    if (x < a + 1.0) {
+        double ap = a, del = 1.0 / a, sum = del;
+        for (int n = 0; n < 2000; ++n) {
+            ap += 1.0;
+            del *= x / ap;
+            sum += del;
+            if (del < sum * eps) break;
+        }
+        return sum * pre;
+    }
+    const double tiny = 1.0e-300;
+    double b = x + 1.0 - a, c = 1.0 / tiny, d = 1.0 / b, h = d;
+    for (int i = 1; i < 2000; ++i) {
+        const double an = -double(i) * (double(i) - a);
+        b += 2.0;
+        d = an * d + b;
+        if (std::fabs(d) < tiny) d = tiny;
+        c = b + an / c;
+        if (std::fabs(c) < tiny) c = tiny;
+        d = 1.0 / d;
+        const double del = d * c;
+        h *= del;
+        if (std::fabs(del - 1.0) < eps) break;
+    }
+    return 1.0 - pre * h;
+}
+
+// boost::math::tools::brent_find_minima(f, min, max, bits, max_iter) -> x, restated literally
+// (call site gamma_snow.h:216-226, bits = 12, max_iter = 60).  The float literal for the golden
+// ratio and the tolerance 2^(1-bits) are boost's.  Pinned by test/gamma_snow_test.cpp:95-108.
+template <class F>
+inline double brent_find_minima(F f, double min, double max, int bits, int max_iter, int* n_eval = nullptr) {
+    bits = std::min(53 / 2, bits);
+    const double tolerance = std::ldexp(1.0, 1 - bits);
+    double x, w, v, u, delta, delta2, fu, fv, fw, fx, mid, fract1, fract2;
+    static const double golden = 0.3819660f;
+    x = w = v = max;
+    fw = fv = fx = f(x);
+    int evals = 1;
+    delta2 = delta = 0;
+    int count = max_iter;
+    do {
+        mid = (min + max) / 2;
+        fract1 = tolerance * std::fabs(x) + tolerance / 4;
+        fract2 = 2 * fract1;
+        if (std::fabs(x - mid) <= (fract2 - (max - min) / 2)) break;
+        if (std::fabs(delta2) > fract1) {
+            double r = (x - w) * (fx - fv);
+            double q = (x - v) * (fx - fw);
+            double p = (x - v) * q - (x - w) * r;
+            q = 2 * (q - r);
+            if (q > 0) p = -p;
+            q = std::fabs(q);
+            double td = delta2;
+            delta2 = delta;
+            if ((std::fabs(p) >= std::fabs(q * td / 2)) || (p <= q * (min - x)) || (p >= q * (max - x))) {
+                delta2 = (x >= mid) ? min - x : max - x;
+                delta = golden * delta2;
+            } else {
+                delta = p / q;
+                u = x + delta;
+                if (((u - min) < fract2) || ((max - u) < fract2)) delta = (mid - x) < 0 ? -std::fabs(fract1) : std::fabs(fract1);
+            }
+        } else {
+            delta2 = (x >= mid) ? min - x : max - x;
+            delta = golden * delta2;
+        }
+        u = (std::fabs(delta) >= fract1) ? (x + delta) : (delta > 0 ? (x + std::fabs(fract1)) : (x - std::fabs(fract1)));
+        fu = f(u);
+        ++evals;
+        if (fu <= fx) {
+            if (u >= x) min = x; else max = x;
+            v = w; w = x; x = u;
+            fv = fw; fw = fx; fx = fu;
+        } else {
+            if (u < x) min = u; else max = u;
+            if ((fu <= fw) || (w == x)) {
+                v = w; w = u; fv = fw; fw = fu;
+            } else if ((fu <= fv) || (v == x) || (v == w)) {
+                v = u; fv = fu;
+            }
+        }
+    } while (--count);
+    if (n_eval) *n_eval = evals;
+    return x;
+}
+}  // namespace special
+
+// ---------------------------------------------------------------------------
+// priestley_taylor  (core/priestley_taylor.h:29-116)
+// ---------------------------------------------------------------------------
+namespace priestley_taylor {
+struct parameter { double albedo = 0.2; double alpha = 1.26; };
+struct calculator {
+    double land_albedo, alpha;
+    calculator(double land_albedo, double alpha) : land_albedo(land_albedo), alpha(alpha) {}
+    // :75-86
+    double potential_evapotranspiration(double temperature, double global_radiation, double rhumidity) const {
+        static const double ck2[2] = {17.84362, 17.08085};
+        static const double ck3[2] = {245.425, 234.175};
+        const double ck1 = 0.610780, psycr = 0.066;
+        int i = temperature < 0 ? 0 : 1;
+        double ctt_inv = 1 / (ck3[i] + temperature);
+        double sat_pressure = ck1 * std::exp(ck2[i] * temperature * ctt_inv);
+        double delta = sat_pressure * ck2[i] * ck3[i] * ctt_inv * ctt_inv;
+        double vapour_pressure = sat_pressure * rhumidity;
+        double epot = alpha * delta * net_radiation(temperature, global_radiation, rhumidity, vapour_pressure) / (delta + psycr);
+        if (epot < 0.0) return 0.0;
+        return epot / (2500780 - 2361 * temperature);
+    }
+    // :98-103
+    double net_radiation(double temperature, double global_radiation, double rhumidity, double vapour_pressure) const {
+        const double bolz = 0.0000000567;
+        double k_temp = temperature + 273.15;
+        double e_atm = 1.24 * std::pow(10 * vapour_pressure / k_temp, 0.143) * (0.85 + 0.5 * rhumidity);
+        return bolz * std::pow(k_temp, 4) * (e_atm - 0.98) + global_radiation * (1.0 - land_albedo);
+    }
+};
+}  // namespace priestley_taylor
+
+// ---------------------------------------------------------------------------
+// actual_evapotranspiration  (core/actual_evapotranspiration.h:31-62)
+// ---------------------------------------------------------------------------
+namespace actual_evapotranspiration {
+struct parameter { double ae_scale_factor = 1.5; };
+inline double calc_pot_ratio(double water_level, double scale_factor) { return 1.0 - std::exp(-water_level * 3.0 / scale_factor); }
+inline double calculate_step(double water_level, double pot_evap, double scale_factor, double snow_fraction, utctimespan) {
+    return pot_evap * calc_pot_ratio(water_level, scale_factor) * (1.0 - snow_fraction);
+}
+}  // namespace actual_evapotranspiration
+
+// ---------------------------------------------------------------------------
+// glacier_melt (core/glacier_melt.h:27-52), precipitation_correction (:23-42)
+// ---------------------------------------------------------------------------
+namespace glacier_melt {
+struct parameter { double dtf = 6.0; double direct_response = 0.0; };
+inline double step(double dtf, double t, double snow_covered_area_m2, double glacier_area_m2) {
+    if (glacier_area_m2 <= snow_covered_area_m2 || t <= 0.0) return 0.0;
+    const double convert_m2_x_mm_d_to_m3_s = 0.001 / 86400.0;
+    return dtf * t * (glacier_area_m2 - snow_covered_area_m2) * convert_m2_x_mm_d_to_m3_s;
+}
+}  // namespace glacier_melt
+namespace precipitation_correction {
+struct parameter { double scale_factor = 1.0; };
+}
+
+// ---------------------------------------------------------------------------
+// kirchner  (core/kirchner.h:118-235) with boost::numeric::odeint
+//   make_dense_output(1e-7, 1e-8, runge_kutta_dopri5<double>()) restated.
+// Restated pieces of odeint 1.68 (all scalar state, value_type = time_type = double):
+//   runge_kutta_dopri5::do_step_impl (FSAL, with error estimate): stage sums are
+//     scale_sumN(1.0, dt*b_i1, dt*b_i2, ...) evaluated left to right;
+//   default_error_checker::error: |x_err| / (eps_abs + eps_rel*(a_x*|x_old| + a_dxdt*dt*|dxdt_old|)), a_x=a_dxdt=1;
+//   default_step_adjuster::decrease_step: dt *= max(0.9*err^(-1/(error_order-1)), 0.2), error_order = 4;
+//   default_step_adjuster::increase_step: if err<0.5: dt *= 0.9*max(5^-5, err)^(-1/stepper_order), order 5;
+//   dense_output_runge_kutta<..., explicit_controlled_stepper_fsal_tag>::initialize/do_step/calc_state
+//     (initialize discards the FSAL derivative; do_step loops try_step, throwing after 500 failures);
+//   runge_kutta_dopri5::calc_state: the Dormand-Prince continuous extension.
+// Pinned by shyft/tests/api/test_region_model_stacks.py:224-234,304 via tests/test_oracle_region_golden.py.
+// ---------------------------------------------------------------------------
+namespace kirchner {
+struct parameter { double c1 = -2.439; double c2 = 0.966; double c3 = -0.10; };
+struct step_stats { int accepted = 0; int rejected = 0; };
+
+struct calculator {
+    parameter param;
+    double eps_abs = 1.0e-7, eps_rel = 1.0e-8;
+    explicit calculator(const parameter& p) : param(p) {}
+    calculator(double abs_err, double rel_err, const parameter& p) : param(p), eps_abs(abs_err), eps_rel(rel_err) {}
+
+    double g(double ln_q) const { return std::exp(param.c1 + param.c2 * ln_q + param.c3 * ln_q * ln_q); }  // :186-188
+    double log_transform_f(double ln_q, double p, double e) const {                                        // :195-198
+        const double gln_q = g(ln_q);
+        return gln_q >= 1.e-30 ? gln_q * ((p - e) * std::exp(-ln_q) - 1.0) : 0.0;
+    }
+
+    // :213-235.  T0/T1 only enter through (T1-T0); times inside are hours.
+    void step(utctime T0, utctime T1, double& q, double& q_avg, double p, double e, step_stats* st = nullptr) const {
+        const double min_q = 0.00001;
+        if (q < min_q) q = min_q;
+        double x = std::log(q);
+        const double t0 = 0.0;
+        const double t1 = to_seconds(T1 - T0) / to_seconds(deltahours(1));
+        // dense_stepper.initialize(x, t0, t1 - t0)
+        double t = t0, dt = t1 - t0;
+        bool deriv_initialized = false;
+        double dxdt = 0.0;
+        // trapezoidal_average::initialize(q, t0)   (:34-39)
+        double area = 0.0, f_a = q, t_a = t0;
+        const double t_start = t0;
+
+        // Dormand-Prince tableau, written as odeint writes it (value_type(n)/value_type(d))
+        const double b21 = 1.0 / 5.0;
+        const double b31 = 3.0 / 40.0, b32 = 9.0 / 40.0;
+        const double b41 = 44.0 / 45.0, b42 = -56.0 / 15.0, b43 = 32.0 / 9.0;
+        const double b51 = 19372.0 / 6561.0, b52 = -25360.0 / 2187.0, b53 = 64448.0 / 6561.0, b54 = -212.0 / 729.0;
+        const double b61 = 9017.0 / 3168.0, b62 = -355.0 / 33.0, b63 = 46732.0 / 5247.0, b64 = 49.0 / 176.0, b65 = -5103.0 / 18656.0;
+        const double c1 = 35.0 / 384.0, c3 = 500.0 / 1113.0, c4 = 125.0 / 192.0, c5 = -2187.0 / 6784.0, c6 = 11.0 / 84.0;
+        const double dc1 = c1 - 5179.0 / 57600.0, dc3 = c3 - 7571.0 / 16695.0, dc4 = c4 - 393.0 / 640.0;
+        const double dc5 = c5 - (-92097.0 / 339200.0), dc6 = c6 - 187.0 / 2100.0, dc7 = -1.0 / 40.0;
+
+        double x_old = x, k1 = 0, k3 = 0, k4 = 0, k5 = 0, k6 = 0, k7 = 0, t_old = t;
+        while (t < t1) {  // :224
+            // ---- dense_output::do_step
+            if (!deriv_initialized) { dxdt = log_transform_f(x, p, e); deriv_initialized = true; }
+            t_old = t;
+            int fails = 0;
+            double x_new, dxdt_new;
+            for (;;) {
+                // ---- controlled_runge_kutta::try_step (fsal)
+                double xt = 1.0 * x + dt * b21 * dxdt;
+                const double k2 = log_transform_f(xt, p, e);
+                xt = 1.0 * x + dt * b31 * dxdt + dt * b32 * k2;
+                k3 = log_transform_f(xt, p, e);
+                xt = 1.0 * x + dt * b41 * dxdt + dt * b42 * k2 + dt * b43 * k3;
+                k4 = log_transform_f(xt, p, e);
+                xt = 1.0 * x + dt * b51 * dxdt + dt * b52 * k2 + dt * b53 * k3 + dt * b54 * k4;
+                k5 = log_transform_f(xt, p, e);
+                xt = 1.0 * x + dt * b61 * dxdt + dt * b62 * k2 + dt * b63 * k3 + dt * b64 * k4 + dt * b65 * k5;
+                k6 = log_transform_f(xt, p, e);
+                x_new = 1.0 * x + dt * c1 * dxdt + dt * c3 * k3 + dt * c4 * k4 + dt * c5 * k5 + dt * c6 * k6;
+                dxdt_new = log_transform_f(x_new, p, e);
+                const double x_err = dt * dc1 * dxdt + dt * dc3 * k3 + dt * dc4 * k4 + dt * dc5 * k5 + dt * dc6 * k6 + dt * dc7 * dxdt_new;
+                const double err = std::fabs(x_err) / (eps_abs + eps_rel * (1.0 * std::fabs(x) + (1.0 * dt) * std::fabs(dxdt)));
+                if (err > 1.0) {
+                    dt *= std::max(9.0 / 10.0 * std::pow(err, -1.0 / (4 - 1)), 1.0 / 5.0);
+                    if (st) st->rejected++;
+                    if (++fails >= 500) throw std::runtime_error("Max number of iterations exceeded (500). A new step size was not found.");
+                    continue;
+                }
+                t += dt;
+                if (err < 0.5) {
+                    const double e2 = std::max(std::pow(5.0, -5.0), err);
+                    dt *= 9.0 / 10.0 * std::pow(e2, -1.0 / 5);
+                }
+                if (st) st->accepted++;
+                break;
+            }
+            x_old = x; k1 = dxdt; k7 = dxdt_new;   // dense output keeps old state/deriv + stepper's k3..k6
+            x = x_new; dxdt = dxdt_new;            // toggle_current_state (FSAL)
+            if (t < t1) {                          // :228-229, trapezoidal_average::add (:46-50)
+                const double f = std::exp(x);
+                area += 0.5 * (f_a + f) * (t - t_a);
+                f_a = f; t_a = t;
+            }
+        }
+        // ---- dense_stepper.calc_state(t1, x_tmp): runge_kutta_dopri5::calc_state
+        {
+            const double b1 = c1, b3 = c3, b4 = c4, b5 = c5, b6 = c6;
+            const double dtl = t - t_old;
+            const double theta = (t1 - t_old) / dtl;
+            const double X1 = 5.0 * (2558722523.0 - 31403016.0 * theta) / 11282082432.0;
+            const double X3 = 100.0 * (882725551.0 - 15701508.0 * theta) / 32700410799.0;
+            const double X4 = 25.0 * (443332067.0 - 31403016.0 * theta) / 1880347072.0;
+            const double X5 = 32805.0 * (23143187.0 - 3489224.0 * theta) / 199316789632.0;
+            const double X6 = 55.0 * (29972135.0 - 7076736.0 * theta) / 822651844.0;
+            const double X7 = 10.0 * (7414447.0 - 829305.0 * theta) / 29380423.0;
+            const double theta_m_1 = theta - 1.0;
+            const double theta_sq = theta * theta;
+            const double A = theta_sq * (3.0 - 2.0 * theta);
+            const double B = theta_sq * theta_m_1;
+            const double C = theta_sq * theta_m_1 * theta_m_1;
+            const double D = theta * theta_m_1 * theta_m_1;
+            const double b1_theta = A * b1 - C * X1 + D;
+            const double b3_theta = A * b3 + C * X3;
+            const double b4_theta = A * b4 - C * X4;
+            const double b5_theta = A * b5 + C * X5;
+            const double b6_theta = A * b6 - C * X6;
+            const double b7_theta = B + C * X7;
+            x = 1.0 * x_old + dtl * b1_theta * k1 + dtl * b3_theta * k3 + dtl * b4_theta * k4 + dtl * b5_theta * k5 +
+                dtl * b6_theta * k6 + dtl * b7_theta * k7;
+        }
+        q = std::exp(x);                                   // :232
+        area += 0.5 * (f_a + q) * (t1 - t_a);              // :233 average_computer.add(q, t1)
+        t_a = t1;
+        q_avg = area / (t_a - t_start);                    // :52
+    }
+};
+}  // namespace kirchner
+
+// ---------------------------------------------------------------------------
+// gamma_snow  (core/gamma_snow.h:44-494)
+// ---------------------------------------------------------------------------
+namespace gamma_snow {
+static const double tol = 1.0e-10;
+
+struct parameter {  // :46-98
+    size_t winter_end_day_of_year = 100;
+    double initial_bare_ground_fraction = 0.04;
+    double snow_cv = 0.4;
+    double tx = -0.5;
+    double wind_scale = 2.0;
+    double wind_const = 1.0;
+    double max_water = 0.1;
+    double surface_magnitude = 30.0;
+    double max_albedo = 0.9;
+    double min_albedo = 0.6;
+    double fast_albedo_decay_rate = 5.0;
+    double slow_albedo_decay_rate = 5.0;
+    double snowfall_reset_depth = 5.0;
+    double glacier_albedo = 0.4;
+    bool calculate_iso_pot_energy = false;
+    double snow_cv_forest_factor = 0.0;
+    double snow_cv_altitude_factor = 0.0;
+    size_t n_winter_days = 221;
+    double effective_snow_cv(double forest_fraction, double altitude) const {  // :85-87
+        return snow_cv + forest_fraction * snow_cv_forest_factor + altitude * snow_cv_altitude_factor;
+    }
+    bool is_snow_season(utctime t) const {  // :89-93
+        utctime t_w_end = calendar::trim_year(t) + deltahours(int64_t(winter_end_day_of_year) * 24);
+        utctime start = t_w_end - deltahours(int64_t(n_winter_days) * 24);
+        return t >= start && t < t_w_end;
+    }
+    bool is_start_melt_season(utctime t, utctimespan) const { return calendar::day_of_year(t) == winter_end_day_of_year; }  // :95-97
+};
+
+struct state {  // :101-116
+    double albedo = 0.4, lwc = 0.1, surface_heat = 30000.0, alpha = 1.26, sdc_melt_mean = 0.0, acc_melt = 0.0,
+           iso_pot_energy = 0.0, temp_swe = 0.0;
+};
+struct response { double sca = 0.0, storage = 0.0, outflow = 0.0; };
+
+struct calculator {
+    const double melt_heat = 333660.0;
+    const double water_heat = 4180.0;
+    const double ice_heat = 2050.0;
+    const double sigma = 5.670373e-8;
+    const double BB0{0.98 * sigma * std::pow(273.15, 4)};
+
+    double gamma_p(double a, double b) const { return special::gamma_p(a, b); }  // :195-197
+    double lgamma(double a) const { return special::lgamma_(a); }                // :199-201
+
+    double calc_q(const double a, const double b, const double z) const {  // :209-212
+        return a * b * gamma_p(a + 1.0, z / b) + z * (1.0 - gamma_p(a, z / b));
+    }
+    double corr_lwc(const double z1, const double a1, const double b1, double /*z2*/, const double a2, const double b2,
+                    int* n_eval = nullptr) const {  // :214-227
+        double Q1 = calc_q(a1, b1, z1);
+        return special::brent_find_minima(
+            [Q1, a2, b2, this](double z) -> double { double f = this->calc_q(a2, b2, z) - Q1; return f * f; },
+            0.0, z1, 12, 60, n_eval);
+    }
+    void calc_snow_state(const double shape, const double scale, const double y0, const double lambda, const double lwd,
+                         const double max_water_frac, const double temp_swe, double& swe, double& sca) const {  // :230-260
+        double y = 0.0, y1 = 0.0;
+        const double m = shape * scale;
+        if (lambda <= 0.0) {
+            swe = m;
+            sca = 1.0 - y0;
+        } else if (lambda / scale > 1.3 * shape + 20.0) {
+            swe = sca = 0.0;
+            return;
+        } else {
+            const double x = lambda / scale;
+            y = gamma_p(shape, x);
+            y1 = y - std::exp(shape * std::log(x) - x - lgamma(shape)) / shape;
+            swe = m * (1.0 - y1) - lambda * (1 - y);
+            sca = (1.0 - y) * (1.0 - y0);
+        }
+        if (lwd > m) swe *= 1.0 + max_water_frac;
+        else if (lwd > 0.0) {
+            const double sat = lwd / max_water_frac;
+            const double x = sat / scale;
+            const double ssa = gamma_p(shape, x);
+            const double ssa1 = ssa - std::exp(shape * std::log(x) - x - lgamma(shape)) / shape;
+            const double liqwat = max_water_frac * (m * (ssa1 - y1) + sat * (1.0 - ssa) - lambda * (1.0 - y));
+            swe += liqwat;
+        }
+        swe += temp_swe;
+        swe *= 1.0 - y0;
+    }
+    void reset_snow_pack(double& sca, double& lwc, double& alpha, double& sdc_melt_mean, double& acc_melt, double& temp_swe,
+                         const double storage, const parameter& p) const {  // :262-274
+        if (storage > tol) {
+            sca = 1.0 - p.initial_bare_ground_fraction;
+            sdc_melt_mean = storage / sca;
+        } else {
+            sca = sdc_melt_mean = 0.0;
+        }
+        alpha = 1.0 / (p.snow_cv * p.snow_cv);
+        temp_swe = lwc = 0.0;
+        acc_melt = -1.0;
+    }
+
+    // :291-493
+    void step(state& s, response& r, utctime t, utctimespan dt, const parameter& p, const double T, const double rad,
+              const double prec_mm_h, const double wind_speed, const double rel_hum, const double forest_fraction,
+              const double altitude) const {
+        double sdc_melt_mean = s.sdc_melt_mean;
+        double acc_melt = s.acc_melt;
+        double iso_pot_energy = s.iso_pot_energy;
+        const double prec = prec_mm_h * double(dt) / double(HOUR);  // chrono: (double*duration)/duration
+
+        if (p.is_start_melt_season(t, dt)) acc_melt = iso_pot_energy = 0.0;
+
+        double snow, rain;
+        if (T < p.tx) { snow = prec; rain = 0.0; }
+        else { snow = 0.0; rain = prec; }
+        if (std::fabs(snow + rain - prec) > 1.0e-8) throw std::runtime_error("Mass balance violation!!!!");
+
+        if (snow < tol && sdc_melt_mean < tol && acc_melt < 0.0) {  // :313-322
+            s.albedo = p.max_albedo;
+            s.surface_heat = 0.0;
+            s.iso_pot_energy = 0.0;
+            r.sca = 0.0;
+            r.storage = 0.0;
+            r.outflow = prec_mm_h;
+            return;
+        }
+        double albedo = s.albedo, lwc = s.lwc, surface_heat = s.surface_heat, alpha = s.alpha, temp_swe = s.temp_swe;
+        double sca = 0.0, storage = 0.0, outflow = 0.0;
+
+        const double min_albedo = p.min_albedo;
+        const double max_albedo = p.max_albedo;
+        const double snow_cv = p.effective_snow_cv(forest_fraction, altitude);
+        const double albedo_range = max_albedo - min_albedo;
+        const double dt_in_days = to_seconds(dt) / to_seconds(DAY);
+        const double slow_albedo_decay_rate = 0.5 * albedo_range * dt_in_days / p.slow_albedo_decay_rate;
+        const double fast_albedo_decay_rate = std::pow(2.0, -dt_in_days / p.fast_albedo_decay_rate);
+
+        const double T_k = T + 273.15;
+        const double turb = p.wind_scale * wind_speed + p.wind_const;
+        double vapour_pressure = 33.864 * (std::pow(7.38e-3 * T + 0.8072, 8) - 1.9e-5 * std::fabs(1.8 * T + 48.0) + 1.316e-3) * rel_hum;
+        if (T < 0.0) vapour_pressure *= 1.0 + 9.72e-3 * T + 4.2e-5 * T * T;
+
+        if (snow > tol) albedo += snow * albedo_range / p.snowfall_reset_depth;
+        else {
+            if (T < 0.0) albedo -= slow_albedo_decay_rate;
+            else albedo = min_albedo + fast_albedo_decay_rate * (albedo - min_albedo);
+        }
+        albedo = std::max(std::min(albedo, max_albedo), min_albedo);
+
+        double effect = rad * (1.0 - albedo);
+        effect += 0.98 * sigma * std::pow(vapour_pressure / T_k, 6.87e-2) * std::pow(T_k, 4);
+
+        if (T > 0.0 && snow < tol) effect += rain * T * water_heat / to_seconds(dt);
+        if (T <= 0.0 && rain < tol) effect += snow * T * ice_heat / to_seconds(dt);
+
+        if (p.calculate_iso_pot_energy) {
+            double iso_effect = effect - BB0 + turb * (T + 1.7 * (vapour_pressure - 6.12));
+            iso_pot_energy += iso_effect * to_seconds(dt) / melt_heat;
+        }
+
+        double sst = std::min(0.0, 1.16 * T - 2.09);
+        if (sst > -tol) effect += turb * (T + 1.7 * (vapour_pressure - 6.12)) - BB0;
+        else
+            effect += turb * (T - sst + 1.7 * (vapour_pressure - 6.132 * std::exp(0.103 * T - 0.186))) -
+                      0.98 * sigma * std::pow(sst + 273.15, 4);
+
+        double delta_sh = -surface_heat;
+        surface_heat = p.surface_magnitude * ice_heat * sst * 0.5;
+        delta_sh += surface_heat;
+
+        double energy = effect * to_seconds(dt);
+        if (delta_sh > 0.0) energy -= delta_sh;
+
+        double potential_melt = std::max(0.0, energy / melt_heat);
+
+        double sdc_scale = sdc_melt_mean / alpha;
+        calc_snow_state(alpha, sdc_scale, p.initial_bare_ground_fraction, acc_melt, lwc, p.max_water, temp_swe, storage, sca);
+        double start_storage_value = storage;
+
+        if (acc_melt < 0.0) {  // :414-451
+            if (snow < tol) snow = 0.0;
+            else {
+                double alpha_prev = alpha;
+                double sdc_scale_prev = sdc_scale;
+                double sdc_snow = snow / (1.0 - p.initial_bare_ground_fraction);
+                alpha = (sdc_melt_mean * alpha + sdc_snow / (snow_cv * snow_cv)) / (sdc_snow + sdc_melt_mean);
+                sdc_melt_mean += sdc_snow;
+                sdc_scale = sdc_melt_mean / alpha;
+                if (lwc > 0.0 && sdc_snow > 0.01 * sdc_melt_mean) {
+                    double z1 = lwc / p.max_water;
+                    double z1_guess = z1 * (1.0 - sdc_snow / sdc_melt_mean);
+                    if (z1_guess < tol) z1_guess = z1 * 0.5;
+                    z1 = corr_lwc(z1, alpha_prev, sdc_scale_prev > 0.0 ? sdc_scale_prev : sdc_scale, z1_guess, alpha, sdc_scale);
+                    lwc = z1 * p.max_water;
+                    calc_snow_state(alpha, sdc_scale, p.initial_bare_ground_fraction, acc_melt, lwc, p.max_water, temp_swe, storage, sca);
+                }
+            }
+            lwc += rain;
+            if (sdc_melt_mean <= potential_melt) {
+                storage = 0.0;
+                reset_snow_pack(sca, lwc, alpha, sdc_melt_mean, acc_melt, temp_swe, storage, p);
+                sdc_scale = 0.0;
+            } else if (potential_melt > 0.0) {
+                sdc_melt_mean -= potential_melt;
+                lwc += potential_melt;
+                alpha = std::max(0.1, sdc_melt_mean / sdc_scale);
+                if (alpha > 1.0 / (snow_cv * snow_cv)) alpha = 1.0 / (snow_cv * snow_cv);
+                sdc_scale = sdc_melt_mean / alpha;
+            }
+        } else {  // :452-470
+            temp_swe += snow / (1.0 - p.initial_bare_ground_fraction);
+            if (temp_swe > 0.0) {
+                double melt = std::min(temp_swe, potential_melt);
+                temp_swe -= melt;
+                potential_melt -= melt;
+                lwc += melt;
+                if (temp_swe < tol) temp_swe = 0.0;
+            }
+            acc_melt += potential_melt;
+            lwc += rain + potential_melt;
+            if (!p.calculate_iso_pot_energy || p.is_snow_season(t)) {
+                if (storage < std::max(0.2, 2 * temp_swe) || storage < 0.2 * rain) {
+                    storage += snow;
+                    reset_snow_pack(sca, lwc, alpha, sdc_melt_mean, acc_melt, temp_swe, storage, p);
+                    sdc_scale = sdc_melt_mean / alpha;
+                }
+            }
+        }
+        calc_snow_state(alpha, sdc_scale, p.initial_bare_ground_fraction, acc_melt, lwc, p.max_water, temp_swe, storage, sca);
+
+        outflow = prec + start_storage_value - storage;
+        if (outflow < 0.0) outflow = 0.0;
+
+        s.albedo = albedo;
+        s.lwc = lwc;
+        s.surface_heat = surface_heat;
+        s.alpha = alpha;
+        s.sdc_melt_mean = sdc_melt_mean;
+        s.acc_melt = acc_melt;
+        s.iso_pot_energy = iso_pot_energy;
+        s.temp_swe = temp_swe;
+
+        r.sca = sca;
+        r.storage = storage;
+        r.outflow = outflow * double(HOUR) / double(dt);
+    }
+};
+}  // namespace gamma_snow
+
+// ---------------------------------------------------------------------------
+// geo_cell_data  (core/geo_cell_data.h:23-138) -- the subset the path reads
+// ---------------------------------------------------------------------------
+struct geo_cell {
+    double x = 0, y = 0, z = 0;
+    double area = 1000000.0;
+    int64_t catchment_id = -1;
+    double radiation_slope_factor = 0.9;
+    double glacier = 0, lake = 0, reservoir = 0, forest = 0;
+    int64_t routing_id = 0;
+    double routing_distance = 0.0;
+    size_t catchment_ix = 0;
+    double snow_storage() const { return 1.0 - lake - reservoir; }  // :59
+};
+
+}  // namespace sho
