@@ -1,0 +1,152 @@
+/* ============================================================================
+ * shyft_b200.h -- C ABI of the B200-native region-model hot path.
+ *
+ * The reference (magneano/shyft, VERSION 1675) has no FFI for this path: Python reaches the C++
+ * template members of region_model<cell_t> through boost.python (api/boostpython/expose.h:143-430).
+ * This header is the boundary a maintainer binds instead; each entry point cites the reference
+ * member it stands in for (paths relative to the reference root).  Plain pointers and sizes only,
+ * no exceptions cross it: every call returns 0 on success, non-zero on failure, and
+ * sb2_last_error() then returns the message (the reference's std::runtime_error text where one
+ * exists).  Host buffers are caller-owned; device buffers are library-owned unless a *_device
+ * variant says otherwise.  A model is not safe for concurrent calls (neither is the reference's,
+ * core/model_calibration.h:832); distinct models are independent.
+ * ==========================================================================*/
+#ifndef SHYFT_B200_H
+#define SHYFT_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sb2_model sb2_model;
+
+/* method stacks (core/pt_gs_k.h, core/pt_hs_k.h, core/hbv_stack.h) */
+enum { SB2_PT_GS_K = 0, SB2_PT_HS_K = 1, SB2_HBV_STACK = 2 };
+/* forcing variables, the members of cell.env_ts (core/cell_model.h:47-56) */
+enum { SB2_TEMPERATURE = 0, SB2_PRECIPITATION = 1, SB2_RADIATION = 2, SB2_WIND_SPEED = 3, SB2_REL_HUM = 4, SB2_N_FORCING = 5 };
+/* host array layouts for [time x cell] data */
+enum { SB2_TIME_MAJOR = 0 /* [t][cell] */, SB2_CELL_MAJOR = 1 /* [cell][t], the reference's per-cell vector<double> */ };
+
+/* response collector bits (core/pt_gs_k_cell_model.h:41-131): which per-cell series run_cells keeps */
+enum {
+    SB2_COLLECT_NONE = 0,          /* catchment sums only (calibration inner loop)                               */
+    SB2_COLLECT_DISCHARGE = 1,     /* discharge_collector: avg_discharge, charge_m3s                              */
+    SB2_COLLECT_SNOW = 2,          /* + snow_sca, snow_swe (set_snow_sca_swe_collection)                          */
+    SB2_COLLECT_ALL = 7,           /* all_response_collector: + snow_outflow, glacier_melt, ae_output, pe_output  */
+    SB2_COLLECT_STATE = 8          /* state_collector (T+1 points per series), set_state_collection               */
+};
+/* per-cell response series ids (all_response_collector member order); SB2_R_SOIL_OUTFLOW is hbv_stack only */
+enum { SB2_R_AVG_DISCHARGE = 0, SB2_R_CHARGE_M3S, SB2_R_SNOW_SCA, SB2_R_SNOW_SWE, SB2_R_SNOW_OUTFLOW, SB2_R_GLACIER_MELT,
+       SB2_R_AE_OUTPUT, SB2_R_PE_OUTPUT, SB2_R_SOIL_OUTFLOW, SB2_N_RESPONSE };
+/* pt_gs_k state series ids (state_collector member order, core/pt_gs_k_cell_model.h:146-208) */
+enum { SB2_S_KIRCHNER_DISCHARGE = 0, SB2_S_GS_ALBEDO, SB2_S_GS_LWC, SB2_S_GS_SURFACE_HEAT, SB2_S_GS_ALPHA, SB2_S_GS_SDC_MELT_MEAN,
+       SB2_S_GS_ACC_MELT, SB2_S_GS_ISO_POT_ENERGY, SB2_S_GS_TEMP_SWE, SB2_N_STATE_SERIES };
+
+/* geo_cell_data (core/geo_cell_data.h:107-138) flattened; one per cell, in the caller's cell order */
+typedef struct sb2_geo_cell {
+    double x, y, z;                 /* mid_point */
+    double area;                    /* m2 */
+    int64_t catchment_id;
+    double radiation_slope_factor;
+    double glacier, lake, reservoir, forest; /* land_type_fractions */
+    int64_t routing_id;             /* routing_info.id, 0 = none */
+    double routing_distance;        /* routing_info.distance [m] */
+} sb2_geo_cell;
+
+/* inverse_distance::parameter / temperature_parameter / precipitation_parameter (core/inverse_distance.h:38-74) */
+typedef struct sb2_idw_parameter {
+    int64_t max_members;
+    double max_distance;
+    double distance_measure_factor;
+    double zscale;
+    double default_temp_gradient;   /* temperature only */
+    int32_t gradient_by_equation;   /* temperature only */
+    double scale_factor;            /* precipitation only */
+} sb2_idw_parameter;
+/* bayesian_kriging::parameter (core/bayesian_kriging.h:204-230) */
+typedef struct sb2_btk_parameter {
+    double gradient_sd, sill, nug, range, zscale;
+} sb2_btk_parameter;
+/* interpolation_parameter (core/region_model.h:65-95) */
+typedef struct sb2_interpolation_parameter {
+    sb2_btk_parameter temperature;
+    int32_t use_idw_for_temperature;
+    sb2_idw_parameter temperature_idw;
+    sb2_idw_parameter precipitation;
+    sb2_idw_parameter wind_speed;
+    sb2_idw_parameter radiation;
+    sb2_idw_parameter rel_hum;
+} sb2_interpolation_parameter;
+void sb2_interpolation_parameter_default(sb2_interpolation_parameter* ip); /* the reference's default-constructed values */
+
+/* ---- lifetime -------------------------------------------------------------------------------- */
+/* region_model(const std::vector<geo_cell_data>&, const parameter_t&)  (core/region_model.h:283-291).
+ * Assigns catchment_ix in order of first appearance of catchment_id (:233-249). `device` = CUDA ordinal. */
+int sb2_model_create(int stack, int64_t n_cells, const sb2_geo_cell* cells, int device, sb2_model** out);
+void sb2_model_destroy(sb2_model* m);
+const char* sb2_last_error(const sb2_model* m); /* m == NULL: error of the last failed sb2_model_create on this thread */
+int sb2_version(void);
+
+int64_t sb2_size(const sb2_model* m);                                   /* region_model::size() :860 */
+int64_t sb2_number_of_catchments(const sb2_model* m);                   /* :318 */
+int sb2_catchment_ids(const sb2_model* m, int64_t* out);                /* cix -> cid, :320 */
+int sb2_cell_catchment_ix(const sb2_model* m, int64_t* out);            /* geo.catchment_ix per cell */
+int sb2_parameter_size(const sb2_model* m);                             /* parameter::size(): 31 / 18 / 22 */
+int sb2_state_size(const sb2_model* m);                                 /* doubles per cell state: 9 / 13 / 15 (5 snow bins) */
+
+/* ---- parameters, filter, state --------------------------------------------------------------- */
+int sb2_set_region_parameter(sb2_model* m, const double* p, int n);                     /* :646-655, vector order of parameter::set */
+int sb2_get_region_parameter(const sb2_model* m, double* p, int n);                     /* :660 */
+int sb2_set_catchment_parameter(sb2_model* m, int64_t cid, const double* p, int n);     /* :668-678 */
+int sb2_remove_catchment_parameter(sb2_model* m, int64_t cid);                          /* :683-691 */
+int sb2_has_catchment_parameter(const sb2_model* m, int64_t cid);                       /* :693 */
+int sb2_set_catchment_calculation_filter(sb2_model* m, const int64_t* cids, int n);     /* :715-729; n == 0 clears */
+int sb2_set_states(sb2_model* m, const double* states, int64_t n_cells);                /* :802-809, [cell][state_size] */
+int sb2_get_states(const sb2_model* m, double* states, int64_t n_cells);                /* :784-787 */
+int sb2_revert_to_initial_state(sb2_model* m);                                          /* :814-818 */
+int sb2_adjust_q(sb2_model* m, double q_scale, const int64_t* cids, int n);             /* :831-837 */
+int sb2_set_collector_mode(sb2_model* m, int collect_bits);                             /* cell type + set_state_collection / set_snow_sca_swe_collection :844-858 */
+
+/* ---- environment ------------------------------------------------------------------------------ */
+/* initialize_cell_environment(time_axis) (:359-364): fixed_dt{t0, dt, n} in microseconds; env_ts reset to NaN */
+int sb2_initialize_cell_environment(sb2_model* m, int64_t t0_us, int64_t dt_us, int64_t n);
+/* write cell.env_ts.<var> directly (the "distributed series supplied by the orchestrator" case, :448-452) */
+int sb2_set_cell_forcing(sb2_model* m, int var, const double* values, int layout);
+int sb2_get_cell_forcing(const sb2_model* m, int var, int64_t start_step, int64_t n_steps, double* out, int layout);
+/* region_environment sources (api/api.h:137-168): n_src geo-located series already on the model axis, values [t][src];
+ * the identity resampling of average_accessor (core/time_series.h:2033-2072) is applied on upload */
+int sb2_set_sources(sb2_model* m, int var, int64_t n_src, const double* xyz /* [src][3] */, const double* values /* [T][src] */);
+/* interpolate(ip, env, best_effort) (:397-527) over the whole axis; returns 0 also when best_effort swallowed a
+ * per-variable failure, in which case *all_ok (nullable) is 0 and that variable stays NaN */
+int sb2_interpolate(sb2_model* m, const sb2_interpolation_parameter* ip, int best_effort, int* all_ok);
+int sb2_is_cell_env_ts_ok(sb2_model* m, int* ok);                                       /* :954-962 */
+
+/* ---- the hot path -------------------------------------------------------------------------------- */
+/* run_cells(use_ncore, start_step, n_steps) (:578-597); same argument validation and messages; use_ncore has no
+ * meaning on the device.  n_steps == 0 runs to the end of the axis. */
+int sb2_run_cells(sb2_model* m, int start_step, int n_steps);
+/* run_interpolation + run_cells window by window for axes whose [t][cell] forcing does not fit in HBM: each window
+ * of `window_steps` steps is interpolated from the sources and stepped; per-cell series (if collected) hold the
+ * last window only, catchment sums and states cover the whole call. */
+int sb2_run_windowed(sb2_model* m, const sb2_interpolation_parameter* ip, int start_step, int n_steps, int window_steps);
+
+/* ---- results ------------------------------------------------------------------------------------- */
+/* cell.rc.<series> / cell.sc.<series> (api/boostpython/expose.h:98-120); out [n_steps][cell] or [cell][n_steps] */
+int sb2_get_response(const sb2_model* m, int series, int64_t start_step, int64_t n_steps, double* out, int layout);
+int sb2_get_state_series(const sb2_model* m, int series, int64_t start_step, int64_t n_points, double* out, int layout);
+/* catchment_discharges / catchment_charges (:873-900): out [n_steps][n_catchments], cix order */
+int sb2_catchment_discharges(const sb2_model* m, int64_t start_step, int64_t n_steps, double* out);
+int sb2_catchment_charges(const sb2_model* m, int64_t start_step, int64_t n_steps, double* out);
+
+/* ---- device-side hooks (plumbing for torch.distributed / CUDA-event timing; not part of the reference surface) -- */
+int sb2_set_stream(sb2_model* m, void* cuda_stream);           /* launch on this stream (default: the legacy default stream) */
+int sb2_device_catchment_discharges(sb2_model* m, void** dptr, int64_t* n_steps, int64_t* n_catchments); /* [T][n_catch] fp64 in HBM */
+int sb2_device_catchment_charges(sb2_model* m, void** dptr, int64_t* n_steps, int64_t* n_catchments);
+int64_t sb2_kernel_launches(const sb2_model* m);               /* launches of this library's kernels since creation */
+int sb2_last_run_kernel_ms(const sb2_model* m, float* step_ms, float* interp_ms); /* CUDA-event time of the last run's kernels */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

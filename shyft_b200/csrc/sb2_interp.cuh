@@ -1,0 +1,290 @@
+// sb2_interp.cuh -- region_model::interpolate on the device: IDW for all five variables and Bayesian
+// temperature kriging (BTK), producing forcing windows laid out [time][cell].
+//
+// Follows:
+//   inverse_distance::run_interpolation     core/inverse_distance.h:142-250 (neighbour lists :160-203, per-step mean :214-249)
+//   temperature_gradient_scale_computer     core/inverse_distance.h:265-325
+//   model transforms                         core/inverse_distance.h:365-472
+//   geo_point::distance_measure              core/geo_point.h:41-43
+//   btk_interpolation                        core/bayesian_kriging.h:280-402 (covariances :93-125)
+#pragma once
+#include <stdint.h>
+
+#include "sb2_math.cuh"
+
+namespace sb2 {
+
+enum { IDW_TEMPERATURE = 0, IDW_PRECIPITATION = 1, IDW_RADIATION = 2, IDW_WIND_SPEED = 3, IDW_REL_HUM = 4 };
+
+struct IdwParam {
+    int max_members;
+    double max_distance, distance_measure_factor, zscale, default_temp_gradient, scale_factor;
+    int gradient_by_equation;
+};
+
+__device__ __forceinline__ double distance_measure(double ax, double ay, double az, double bx, double by, double bz, double p, double zscale) {
+    const double d2 = (ax - bx) * (ax - bx) + (ay - by) * (ay - by) + (az - bz) * (az - bz) * zscale * zscale;
+    const double e = p / 2.0;
+    return e == 1.0 ? d2 : pow(d2, e);  // pow(x, 1.0) == x exactly
+}
+
+// Step 1 (:160-203): per destination cell the sources with weight >= min_weight; if more than max_members, the
+// max_members heaviest in descending weight order (std::partial_sort; ties, which the reference leaves
+// implementation-defined, resolve to the lower source index here), otherwise source order.
+// Output: nb_idx/nb_w/nb_f [k][cell], nb_n [cell]; nb_f = per-neighbour multiplicative transform factor.
+__global__ void idw_build_neighbours_kernel(int kind, int64_t n_cells, const double* __restrict__ cx, const double* __restrict__ cy,
+                                            const double* __restrict__ cz, const double* __restrict__ cslope, int n_src,
+                                            const double* __restrict__ sxyz, IdwParam p, double min_weight, int32_t* __restrict__ nb_idx,
+                                            double* __restrict__ nb_w, double* __restrict__ nb_f, int32_t* __restrict__ nb_n) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cells) return;
+    const double x = cx[c], y = cy[c], z = cz[c];
+    auto weight = [&](int k) {
+        const double w = dmin(1.0, 1.0 / distance_measure(x, y, z, sxyz[3 * k], sxyz[3 * k + 1], sxyz[3 * k + 2], p.distance_measure_factor, p.zscale));
+        return w;
+    };
+    int n_ok = 0;
+    for (int k = 0; k < n_src; ++k)
+        if (weight(k) >= min_weight) ++n_ok;
+    int cnt = 0;
+    if (n_ok <= p.max_members) {
+        for (int k = 0; k < n_src; ++k) {
+            const double w = weight(k);
+            if (w >= min_weight) { nb_idx[(int64_t)cnt * n_cells + c] = k; nb_w[(int64_t)cnt * n_cells + c] = w; ++cnt; }
+        }
+    } else {
+        double last_w = 2.0;  // weights are <= 1
+        int last_k = -1;
+        for (cnt = 0; cnt < p.max_members; ++cnt) {
+            double best_w = -1.0;
+            int best_k = -1;
+            for (int k = 0; k < n_src; ++k) {
+                const double w = weight(k);
+                if (!(w >= min_weight)) continue;
+                const bool after_last = (w < last_w) || (w == last_w && k > last_k);
+                if (after_last && w > best_w) { best_w = w; best_k = k; }
+            }
+            nb_idx[(int64_t)cnt * n_cells + c] = best_k;
+            nb_w[(int64_t)cnt * n_cells + c] = best_w;
+            last_w = best_w;
+            last_k = best_k;
+        }
+    }
+    nb_n[c] = cnt;
+    for (int j = 0; j < cnt; ++j) {
+        const int k = nb_idx[(int64_t)j * n_cells + c];
+        double f = 1.0;
+        if (kind == IDW_PRECIPITATION) f = pow(p.scale_factor, (z - sxyz[3 * k + 2]) / 100.0);  // :422-426
+        else if (kind == IDW_RADIATION) f = cslope[c];                                            // :392-394
+        nb_f[(int64_t)j * n_cells + c] = f;
+    }
+}
+
+// 3x3 solve with partial pivoting (arma::solve at inverse_distance.h:296-300); false when singular
+__device__ inline bool solve3(double A[3][3], double b[3], double x[3]) {
+    int piv[3] = {0, 1, 2};
+    double scale = 0;
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) scale = dmax(scale, fabs(A[i][j]));
+    if (!(scale > 0)) return false;
+    for (int c = 0; c < 3; ++c) {
+        int best = c;
+        for (int r = c + 1; r < 3; ++r) if (fabs(A[piv[r]][c]) > fabs(A[piv[best]][c])) best = r;
+        int tmp = piv[c]; piv[c] = piv[best]; piv[best] = tmp;
+        const double d = A[piv[c]][c];
+        if (fabs(d) < 1e-14 * scale) return false;
+        for (int r = c + 1; r < 3; ++r) {
+            const double f = A[piv[r]][c] / d;
+            for (int j = c; j < 3; ++j) A[piv[r]][j] -= f * A[piv[c]][j];
+            b[piv[r]] -= f * b[piv[c]];
+        }
+    }
+    for (int c = 2; c >= 0; --c) {
+        double s = b[piv[c]];
+        for (int j = c + 1; j < 3; ++j) s -= A[piv[c]][j] * x[j];
+        x[c] = s / A[piv[c]][c];
+    }
+    return isfinite(x[0]) && isfinite(x[1]) && isfinite(x[2]);
+}
+
+// Step 2 (:214-249): out[(i)*n_cells + c] = sum_k w*transform(v_k) / sum_k w over the finite neighbours, in list order.
+// Source values of a tile of steps are staged in shared memory; one thread per cell walks the tile.
+template <int KIND>
+__global__ void __launch_bounds__(128) idw_apply_kernel(int64_t n_cells, const double* __restrict__ cz, int n_src,
+                                                        const double* __restrict__ sxyz, const double* __restrict__ src /* [T][n_src] */,
+                                                        int64_t first_step, int n_steps, IdwParam p, const int32_t* __restrict__ nb_idx,
+                                                        const double* __restrict__ nb_w, const double* __restrict__ nb_f,
+                                                        const int32_t* __restrict__ nb_n, double* __restrict__ out, int tile_steps) {
+    extern __shared__ double sv[];  // [tile_steps][n_src] then (temperature) [n_src] source z
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool ok = c < n_cells;
+    const int cnt = ok ? nb_n[c] : 0;
+    const double z = ok ? cz[c] : 0.0;
+    for (int t0 = 0; t0 < n_steps; t0 += tile_steps) {
+        const int nt = min(tile_steps, n_steps - t0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < nt * n_src; e += blockDim.x) sv[e] = src[(first_step + t0) * n_src + e];
+        __syncthreads();
+        if (!ok) continue;
+        for (int i = 0; i < nt; ++i) {
+            const double* v = sv + i * n_src;
+            double scale = 1.0;
+            if (KIND == IDW_TEMPERATURE) {  // temperature_gradient_scale_computer::compute over the finite neighbours (:285-316)
+                scale = p.default_temp_gradient;
+                int nv = 0, mn = -1, mx = -1, first[4] = {-1, -1, -1, -1};
+                double zmn = 0, zmx = 0;
+                for (int j = 0; j < cnt; ++j) {
+                    const int k = nb_idx[(int64_t)j * n_cells + c];
+                    if (!isfinite(v[k])) continue;
+                    const double h = sxyz[3 * k + 2];
+                    if (nv < 4) first[nv] = k;
+                    if (nv == 0) { mn = mx = k; zmn = zmx = h; }
+                    else if (h < zmn) { mn = k; zmn = h; }
+                    else if (h > zmx) { mx = k; zmx = h; }
+                    ++nv;
+                }
+                bool solved = false;
+                if (p.gradient_by_equation && nv > 3) {
+                    double A[3][3], b[3], x[3];
+                    for (int r = 0; r < 3; ++r) {
+                        A[r][0] = sxyz[3 * first[r + 1]] - sxyz[3 * first[0]];
+                        A[r][1] = sxyz[3 * first[r + 1] + 1] - sxyz[3 * first[0] + 1];
+                        A[r][2] = sxyz[3 * first[r + 1] + 2] - sxyz[3 * first[0] + 2];
+                        b[r] = v[first[r + 1]] - v[first[0]];
+                    }
+                    if (solve3(A, b, x)) { scale = x[2]; solved = true; }
+                }
+                if (!solved && nv > 1) {
+                    const double dz = zmx - zmn;
+                    scale = dz > 50.0 ? (v[mx] - v[mn]) / dz : p.default_temp_gradient;
+                }
+            }
+            double sum_w = 0, sum_wv = 0;
+            for (int j = 0; j < cnt; ++j) {
+                const int k = nb_idx[(int64_t)j * n_cells + c];
+                const double s = v[k];
+                if (isfinite(s)) {
+                    const double w = nb_w[(int64_t)j * n_cells + c];
+                    double tv;
+                    if (KIND == IDW_TEMPERATURE) tv = s + scale * (z - sxyz[3 * k + 2]);
+                    else if (KIND == IDW_PRECIPITATION || KIND == IDW_RADIATION) tv = s * nb_f[(int64_t)j * n_cells + c];
+                    else tv = s;
+                    sum_wv += w * tv;
+                    sum_w += w;
+                }
+            }
+            out[(int64_t)(t0 + i) * n_cells + c] = sum_wv / sum_w;
+        }
+    }
+}
+
+// ---- BTK ---------------------------------------------------------------------------------------
+// k[s][c] = (sill - nug) * exp(-zscaled_distance(s, c) / range)   (bayesian_kriging.h:41-56,112-124)
+// omega[c][s] = sum_j k[j][c] * K_inv[j][s]                        (:316, omega = k.t()*K_inv)
+// bm[c][0..1] = ((f - F.t()*K_inv*k).t() * (I - GH_inv))[c]        (:314)
+// FtKinv [2][S] = F.t()*K_inv and M22 = (I - GH_inv) come from the host (S x S algebra).
+__global__ void btk_build_operators_kernel(int64_t n_cells, const double* __restrict__ cx, const double* __restrict__ cy,
+                                           const double* __restrict__ cz, int n_src, const double* __restrict__ sxyz,
+                                           const double* __restrict__ K_inv, const double* __restrict__ FtKinv,
+                                           const double* __restrict__ M22, double sill_m_nug, double range, double zscale,
+                                           double* __restrict__ omega /* [S][cells] */, double* __restrict__ bm /* [2][cells] */,
+                                           double* __restrict__ kbuf /* [S][cells] scratch */) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cells) return;
+    const double x = cx[c], y = cy[c], z = cz[c];
+    for (int s = 0; s < n_src; ++s) {
+        const double dx = sxyz[3 * s] - x, dy = sxyz[3 * s + 1] - y, dz = sxyz[3 * s + 2] - z;
+        const double d = sqrt(dx * dx + dy * dy + dz * dz * zscale * zscale);
+        kbuf[(int64_t)s * n_cells + c] = sill_m_nug * exp(-d / range);
+    }
+    double g0 = 0.0, g1 = 0.0;  // (F.t()*K_inv*k)[:, c]
+    for (int j = 0; j < n_src; ++j) {
+        const double kj = kbuf[(int64_t)j * n_cells + c];
+        g0 += FtKinv[j] * kj;
+        g1 += FtKinv[n_src + j] * kj;
+    }
+    const double d0 = 1.0 - g0, d1 = z - g1;  // f - ...
+    bm[c] = d0 * M22[0] + d1 * M22[2];
+    bm[n_cells + c] = d0 * M22[1] + d1 * M22[3];
+    for (int s = 0; s < n_src; ++s) {
+        double acc = 0.0;
+        for (int j = 0; j < n_src; ++j) acc += kbuf[(int64_t)j * n_cells + c] * K_inv[j * n_src + s];
+        omega[(int64_t)s * n_cells + c] = acc;
+    }
+}
+
+// per-step quantities (:384-394): beta_hat = E_beta_w * T_obs, resid = T_obs - F*beta_hat; one thread per step
+__global__ void btk_step_prepare_kernel(int n_steps, int64_t first_step, int n_src, const double* __restrict__ src,
+                                        const int32_t* __restrict__ valid_idx, int n_valid, const double* __restrict__ E_beta_w /* [2][n_valid] */,
+                                        const double* __restrict__ sz_valid, double* __restrict__ beta /* [n_steps][2] */,
+                                        double* __restrict__ resid /* [n_steps][n_valid] */) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_steps) return;
+    const double* v = src + (first_step + i) * n_src;
+    double b0 = 0.0, b1 = 0.0;
+    for (int s = 0; s < n_valid; ++s) {
+        const double t = v[valid_idx[s]];
+        b0 += E_beta_w[s] * t;
+        b1 += E_beta_w[n_valid + s] * t;
+    }
+    beta[2 * i] = b0;
+    beta[2 * i + 1] = b1;
+    for (int s = 0; s < n_valid; ++s) resid[(int64_t)i * n_valid + s] = v[valid_idx[s]] - (1.0 * b0 + sz_valid[s] * b1);
+}
+
+// T_hat[c] = f_c.t()*beta_hat + omega[c,:]*resid - BM[c,:]*(beta_hat - E_beta_pri)   (:394-396); E_beta_pri = (0, prior_gradient(t))
+__global__ void __launch_bounds__(128) btk_apply_kernel(int64_t n_cells, const double* __restrict__ cz, int n_valid,
+                                                        const double* __restrict__ omega /* [n_valid][cells] */, const double* __restrict__ bm,
+                                                        const double* __restrict__ beta, const double* __restrict__ resid,
+                                                        const double* __restrict__ prior_gradient /* [n_steps] */, int n_steps,
+                                                        double* __restrict__ out /* [n_steps][cells] */, int tile_steps) {
+    extern __shared__ double sr[];  // [tile_steps][n_valid]
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool ok = c < n_cells;
+    const double z = ok ? cz[c] : 0.0, bm0 = ok ? bm[c] : 0.0, bm1 = ok ? bm[n_cells + c] : 0.0;
+    for (int t0 = 0; t0 < n_steps; t0 += tile_steps) {
+        const int nt = min(tile_steps, n_steps - t0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < nt * n_valid; e += blockDim.x) sr[e] = resid[(int64_t)t0 * n_valid + e];
+        __syncthreads();
+        if (!ok) continue;
+        for (int i = 0; i < nt; ++i) {
+            const double b0 = beta[2 * (t0 + i)], b1 = beta[2 * (t0 + i) + 1];
+            double acc = 0.0;
+            for (int s = 0; s < n_valid; ++s) acc += omega[(int64_t)s * n_cells + c] * sr[i * n_valid + s];
+            const double t_hat = (1.0 * b0 + z * b1) + acc;
+            out[(int64_t)(t0 + i) * n_cells + c] = t_hat - (bm0 * (b0 - 0.0) + bm1 * (b1 - prior_gradient[t0 + i]));
+        }
+    }
+}
+
+__global__ void fill_kernel(double* __restrict__ p, int64_t n, double v) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+// identity resampling of average_accessor for a stair-case source on the model axis (time_series.h:202-310): (dt_s*v)/dt_s
+__global__ void average_accessor_same_axis_kernel(double* __restrict__ p, int64_t n, double dt_seconds) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = p[i];
+        p[i] = isfinite(v) ? (dt_seconds * v) / dt_seconds : nan("");
+    }
+}
+// [rows][cols] -> [cols][rows] tiled transpose (cell-major <-> time-major at the ABI)
+__global__ void transpose_kernel(const double* __restrict__ in, double* __restrict__ out, int64_t rows, int64_t cols) {
+    __shared__ double tile[32][33];
+    const int64_t bx = (int64_t)blockIdx.x * 32, by = (int64_t)blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int64_t r = by + j, c = bx + threadIdx.x;
+        if (r < rows && c < cols) tile[j][threadIdx.x] = in[r * cols + c];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int64_t c = bx + j, r = by + threadIdx.x;
+        if (r < rows && c < cols) out[c * rows + r] = tile[threadIdx.x][j];
+    }
+}
+__global__ void count_nonfinite_kernel(const double* __restrict__ p, int64_t n, unsigned long long* __restrict__ count) {
+    unsigned long long local = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) local += isfinite(p[i]) ? 0 : 1;
+    if (local) atomicAdd(count, local);
+}
+
+}  // namespace sb2

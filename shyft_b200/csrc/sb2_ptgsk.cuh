@@ -1,0 +1,619 @@
+// sb2_ptgsk.cuh -- the pt_gs_k cell stack as one sm_100a kernel.
+//
+// One thread per cell, the nine fp64 state values in registers for the whole time window, forcing and
+// collected series laid out [time][cell] so each step's loads and stores are coalesced 8-byte accesses,
+// per-catchment discharge reduced by a segmented warp shuffle into fixed slots (deterministic).
+//
+// Follows, step for step:
+//   run_pt_gs_k                      core/pt_gs_k.h:340-397
+//   gamma_snow::calculator::step     core/gamma_snow.h:291-493 (+ calc_snow_state :230-260, corr_lwc :214-227,
+//                                    reset_snow_pack :262-274, calc_q :209-212)
+//   kirchner::calculator::step       core/kirchner.h:213-235 over odeint's controlled dopri5 dense output
+//   priestley_taylor                 core/priestley_taylor.h:75-103
+//   actual_evapotranspiration        core/actual_evapotranspiration.h:40-62
+//   glacier_melt::step               core/glacier_melt.h:47-52
+//   collectors                       core/pt_gs_k_cell_model.h:81-90,116-123,193-205
+#pragma once
+#include <stdint.h>
+
+#include "sb2_math.cuh"
+
+namespace sb2 {
+
+// parameter set as the kernel reads it (host fills it from parameter::set order, core/pt_gs_k.h:77-112)
+struct PtgskParam {
+    double c1, c2, c3;            // kirchner
+    double ae_scale_factor;       // ae
+    double tx, wind_scale, max_water, wind_const, fast_albedo_decay_rate, slow_albedo_decay_rate, surface_magnitude, max_albedo,
+        min_albedo, snowfall_reset_depth, snow_cv, glacier_albedo;  // gs
+    double p_corr_scale_factor;
+    double snow_cv_forest_factor, snow_cv_altitude_factor;
+    double pt_albedo, pt_alpha;
+    double initial_bare_ground_fraction;
+    double gm_dtf, gm_direct_response;
+    double reservoir_direct_response_fraction;
+    // per-run constants the reference recomputes every step from p and dt (gamma_snow.h:341-343), evaluated once on the host
+    double slow_albedo_decay_step;  // 0.5*albedo_range*dt_in_days/slow_albedo_decay_rate
+    double fast_albedo_decay_step;  // pow(2.0, -dt_in_days/fast_albedo_decay_rate)
+    int32_t winter_end_day_of_year;
+    int32_t n_winter_days;
+    int32_t calculate_iso_pot_energy;
+    int32_t pad_;
+};
+
+enum : int { ERR_KIRCHNER_STEP = 1, ERR_MASS_BALANCE = 2 };
+
+struct PtgskRunArgs {
+    int64_t n_cells;
+    // static per-cell data (SoA)
+    const double* __restrict__ z;
+    const double* __restrict__ area;
+    const double* __restrict__ glacier;
+    const double* __restrict__ lake;
+    const double* __restrict__ reservoir;
+    const double* __restrict__ forest;
+    const int32_t* __restrict__ pset;          // parameter-set index per cell
+    const uint8_t* __restrict__ active;        // catchment calculation filter expanded per cell (nullable = all)
+    const PtgskParam* __restrict__ params;
+    double* __restrict__ state;                // [9][n_cells]
+    // forcing window: element (local step i, cell c) of variable v at f[v][i*n_cells + c]
+    const double* __restrict__ f[5];
+    // time
+    int n_steps;                               // steps in this launch
+    int64_t first_step;                        // absolute index on the model axis of local step 0
+    double dt_seconds;                         // to_seconds(dt)
+    double dt_hours;                           // to_seconds(T1-T0)/to_seconds(deltahours(1))
+    double dt_us;                              // double(dt.count())
+    const int32_t* __restrict__ day_of_year;   // [T] calendar::day_of_year(period.start), UTC
+    const int32_t* __restrict__ sec_of_year;   // [T] (period.start - trim(period.start, YEAR)) in seconds
+    // collected series: element (absolute step - out_first_step, cell) at r[s][...*n_cells + c]; null = not collected
+    double* __restrict__ resp[8];
+    double* __restrict__ st[9];
+    int64_t out_first_step;                    // absolute step stored at row 0 of resp/st
+    int collect_end_state;                     // write the T+1'th state point after the last step
+    // catchment partial sums: slot of each cell's (warp, catchment-run) segment, head flag; partial[i][slot][2]
+    const int32_t* __restrict__ slot;
+    double* __restrict__ partial;
+    int64_t n_slots;
+    int* __restrict__ error_flag;
+};
+
+struct GsState { double albedo, lwc, surface_heat, alpha, sdc_melt_mean, acc_melt, iso_pot_energy, temp_swe; };
+
+__device__ __forceinline__ double mmh_to_m3s(double mmh, double area) { return area * mmh * (1 / (3600.0 * 1000.0)); }
+__device__ __forceinline__ double m3s_to_mmh(double m3s, double area) { return m3s / ((1 / (3600.0 * 1000.0)) * area); }
+
+// ---- gamma_snow ---------------------------------------------------------------------------------
+// calc_q, gamma_snow.h:209-212
+__device__ __forceinline__ double gs_calc_q(double a, double b, double z, double lg_a, double lg_a1) {
+    const double x = z / b;
+    return a * b * gamma_p(a + 1.0, x, lg_a1) + z * (1.0 - gamma_p(a, x, lg_a));
+}
+
+// corr_lwc = boost brent_find_minima(f, 0, z1, bits=12, 60 iterations), gamma_snow.h:214-227
+__device__ __noinline__ double gs_corr_lwc(double z1, double a1, double b1, double a2, double b2) {
+    const double Q1 = gs_calc_q(a1, b1, z1, lgamma(a1), lgamma(a1 + 1.0));
+    const double lg_a2 = lgamma(a2), lg_a21 = lgamma(a2 + 1.0);
+    auto f = [&](double z) { const double d = gs_calc_q(a2, b2, z, lg_a2, lg_a21) - Q1; return d * d; };
+    const double tolerance = 0.00048828125;  // ldexp(1.0, 1 - 12)
+    const double golden = (double)0.3819660f;
+    double bmin = 0.0, bmax = z1;
+    double x, w, v, u, delta, delta2, fu, fv, fw, fx, mid, fract1, fract2;
+    x = w = v = bmax;
+    fw = fv = fx = f(x);
+    delta2 = delta = 0;
+    int count = 60;
+    do {
+        mid = (bmin + bmax) / 2;
+        fract1 = tolerance * fabs(x) + tolerance / 4;
+        fract2 = 2 * fract1;
+        if (fabs(x - mid) <= (fract2 - (bmax - bmin) / 2)) break;
+        if (fabs(delta2) > fract1) {
+            double r = (x - w) * (fx - fv);
+            double q = (x - v) * (fx - fw);
+            double p = (x - v) * q - (x - w) * r;
+            q = 2 * (q - r);
+            if (q > 0) p = -p;
+            q = fabs(q);
+            const double td = delta2;
+            delta2 = delta;
+            if ((fabs(p) >= fabs(q * td / 2)) || (p <= q * (bmin - x)) || (p >= q * (bmax - x))) {
+                delta2 = (x >= mid) ? bmin - x : bmax - x;
+                delta = golden * delta2;
+            } else {
+                delta = p / q;
+                u = x + delta;
+                if (((u - bmin) < fract2) || ((bmax - u) < fract2)) delta = (mid - x) < 0 ? -fabs(fract1) : fabs(fract1);
+            }
+        } else {
+            delta2 = (x >= mid) ? bmin - x : bmax - x;
+            delta = golden * delta2;
+        }
+        u = (fabs(delta) >= fract1) ? (x + delta) : (delta > 0 ? (x + fabs(fract1)) : (x - fabs(fract1)));
+        fu = f(u);
+        if (fu <= fx) {
+            if (u >= x) bmin = x; else bmax = x;
+            v = w; w = x; x = u;
+            fv = fw; fw = fx; fx = fu;
+        } else {
+            if (u < x) bmin = u; else bmax = u;
+            if ((fu <= fw) || (w == x)) {
+                v = w; w = u; fv = fw; fw = fu;
+            } else if ((fu <= fv) || (v == x) || (v == w)) {
+                v = u; fv = fu;
+            }
+        }
+    } while (--count);
+    return x;
+}
+
+// calc_snow_state, gamma_snow.h:230-260
+__device__ __noinline__ void gs_calc_snow_state(double shape, double scale, double y0, double lambda, double lwd, double max_water_frac,
+                                                double temp_swe, double& swe, double& sca) {
+    double y = 0.0, y1 = 0.0;
+    const double m = shape * scale;
+    double lg = 0.0;
+    bool have_lg = false;
+    if (lambda <= 0.0) {
+        swe = m;
+        sca = 1.0 - y0;
+    } else if (lambda / scale > 1.3 * shape + 20.0) {
+        swe = sca = 0.0;
+        return;
+    } else {
+        const double x = lambda / scale;
+        lg = lgamma(shape);
+        have_lg = true;
+        const double pre = gamma_prefix(shape, x, lg);
+        y = (x > 0.0) ? gamma_p_with_prefix(shape, x, pre) : 0.0;
+        y1 = y - pre / shape;
+        swe = m * (1.0 - y1) - lambda * (1 - y);
+        sca = (1.0 - y) * (1.0 - y0);
+    }
+    if (lwd > m) swe *= 1.0 + max_water_frac;
+    else if (lwd > 0.0) {
+        const double sat = lwd / max_water_frac;
+        const double x = sat / scale;
+        if (!have_lg) lg = lgamma(shape);
+        const double pre = gamma_prefix(shape, x, lg);
+        const double ssa = isinf(x) ? 1.0 : gamma_p_with_prefix(shape, x, pre);
+        const double ssa1 = ssa - pre / shape;
+        const double liqwat = max_water_frac * (m * (ssa1 - y1) + sat * (1.0 - ssa) - lambda * (1.0 - y));
+        swe += liqwat;
+    }
+    swe += temp_swe;
+    swe *= 1.0 - y0;
+}
+
+// reset_snow_pack, gamma_snow.h:262-274 (alpha uses p.snow_cv, not the effective cv)
+__device__ __forceinline__ void gs_reset_snow_pack(double& sca, double& lwc, double& alpha, double& sdc_melt_mean, double& acc_melt,
+                                                   double& temp_swe, double storage, const PtgskParam& p) {
+    if (storage > 1.0e-10) {
+        sca = 1.0 - p.initial_bare_ground_fraction;
+        sdc_melt_mean = storage / sca;
+    } else {
+        sca = sdc_melt_mean = 0.0;
+    }
+    alpha = 1.0 / (p.snow_cv * p.snow_cv);
+    temp_swe = lwc = 0.0;
+    acc_melt = -1.0;
+}
+
+// gamma_snow::calculator::step, gamma_snow.h:291-493
+__device__ __forceinline__ void gs_step(GsState& s, double& r_sca, double& r_storage, double& r_outflow, const PtgskParam& p, int doy,
+                                        int sec_of_year, double dt_seconds, double dt_us, double T, double rad, double prec_mm_h,
+                                        double wind_speed, double rel_hum, double forest_fraction, double altitude) {
+    const double tol = 1.0e-10;
+    const double melt_heat = 333660.0, water_heat = 4180.0, ice_heat = 2050.0, sigma = 5.670373e-8;
+    const double BB0 = 0.98 * sigma * (273.15 * 273.15 * 273.15 * 273.15) * 0 + 309.32891622827313;  // 0.98*sigma*pow(273.15,4)
+    double sdc_melt_mean = s.sdc_melt_mean;
+    double acc_melt = s.acc_melt;
+    double iso_pot_energy = s.iso_pot_energy;
+    const double prec = prec_mm_h * dt_us / 3600000000.0;
+
+    if (doy == p.winter_end_day_of_year) acc_melt = iso_pot_energy = 0.0;  // is_start_melt_season :95-97
+
+    double snow, rain;
+    if (T < p.tx) { snow = prec; rain = 0.0; }
+    else { snow = 0.0; rain = prec; }
+
+    if (snow < tol && sdc_melt_mean < tol && acc_melt < 0.0) {  // :313-322
+        s.albedo = p.max_albedo;
+        s.surface_heat = 0.0;
+        s.iso_pot_energy = 0.0;
+        r_sca = 0.0;
+        r_storage = 0.0;
+        r_outflow = prec_mm_h;
+        return;
+    }
+    double albedo = s.albedo, lwc = s.lwc, surface_heat = s.surface_heat, alpha = s.alpha, temp_swe = s.temp_swe;
+    double sca = 0.0, storage = 0.0, outflow = 0.0;
+
+    const double min_albedo = p.min_albedo;
+    const double max_albedo = p.max_albedo;
+    const double snow_cv = p.snow_cv + forest_fraction * p.snow_cv_forest_factor + altitude * p.snow_cv_altitude_factor;
+    const double albedo_range = max_albedo - min_albedo;
+
+    const double T_k = T + 273.15;
+    const double turb = p.wind_scale * wind_speed + p.wind_const;
+    double b8 = 7.38e-3 * T + 0.8072;
+    b8 *= b8; b8 *= b8; b8 *= b8;  // pow(x, 8)
+    double vapour_pressure = 33.864 * (b8 - 1.9e-5 * fabs(1.8 * T + 48.0) + 1.316e-3) * rel_hum;
+    if (T < 0.0) vapour_pressure *= 1.0 + 9.72e-3 * T + 4.2e-5 * T * T;
+
+    if (snow > tol) albedo += snow * albedo_range / p.snowfall_reset_depth;
+    else {
+        if (T < 0.0) albedo -= p.slow_albedo_decay_step;
+        else albedo = min_albedo + p.fast_albedo_decay_step * (albedo - min_albedo);
+    }
+    albedo = dmax(dmin(albedo, max_albedo), min_albedo);
+
+    double effect = rad * (1.0 - albedo);
+    const double T_k2 = T_k * T_k;
+    effect += 0.98 * sigma * pow(vapour_pressure / T_k, 6.87e-2) * (T_k2 * T_k2);
+
+    if (T > 0.0 && snow < tol) effect += rain * T * water_heat / dt_seconds;
+    if (T <= 0.0 && rain < tol) effect += snow * T * ice_heat / dt_seconds;
+
+    if (p.calculate_iso_pot_energy) {
+        const double iso_effect = effect - BB0 + turb * (T + 1.7 * (vapour_pressure - 6.12));
+        iso_pot_energy += iso_effect * dt_seconds / melt_heat;
+    }
+
+    const double sst = dmin(0.0, 1.16 * T - 2.09);
+    if (sst > -tol) effect += turb * (T + 1.7 * (vapour_pressure - 6.12)) - BB0;
+    else {
+        const double sk = sst + 273.15, sk2 = sk * sk;
+        effect += turb * (T - sst + 1.7 * (vapour_pressure - 6.132 * exp(0.103 * T - 0.186))) - 0.98 * sigma * (sk2 * sk2);
+    }
+
+    double delta_sh = -surface_heat;
+    surface_heat = p.surface_magnitude * ice_heat * sst * 0.5;
+    delta_sh += surface_heat;
+
+    double energy = effect * dt_seconds;
+    if (delta_sh > 0.0) energy -= delta_sh;
+
+    double potential_melt = dmax(0.0, energy / melt_heat);
+
+    double sdc_scale = sdc_melt_mean / alpha;
+    const double y0 = p.initial_bare_ground_fraction;
+    gs_calc_snow_state(alpha, sdc_scale, y0, acc_melt, lwc, p.max_water, temp_swe, storage, sca);
+    const double start_storage_value = storage;
+
+    if (acc_melt < 0.0) {  // :414-451
+        if (snow < tol) snow = 0.0;
+        else {
+            const double alpha_prev = alpha;
+            const double sdc_scale_prev = sdc_scale;
+            const double sdc_snow = snow / (1.0 - y0);
+            alpha = (sdc_melt_mean * alpha + sdc_snow / (snow_cv * snow_cv)) / (sdc_snow + sdc_melt_mean);
+            sdc_melt_mean += sdc_snow;
+            sdc_scale = sdc_melt_mean / alpha;
+            if (lwc > 0.0 && sdc_snow > 0.01 * sdc_melt_mean) {
+                double z1 = lwc / p.max_water;
+                z1 = gs_corr_lwc(z1, alpha_prev, sdc_scale_prev > 0.0 ? sdc_scale_prev : sdc_scale, alpha, sdc_scale);
+                lwc = z1 * p.max_water;
+                gs_calc_snow_state(alpha, sdc_scale, y0, acc_melt, lwc, p.max_water, temp_swe, storage, sca);
+            }
+        }
+        lwc += rain;
+        if (sdc_melt_mean <= potential_melt) {
+            storage = 0.0;
+            gs_reset_snow_pack(sca, lwc, alpha, sdc_melt_mean, acc_melt, temp_swe, storage, p);
+            sdc_scale = 0.0;
+        } else if (potential_melt > 0.0) {
+            sdc_melt_mean -= potential_melt;
+            lwc += potential_melt;
+            alpha = dmax(0.1, sdc_melt_mean / sdc_scale);
+            if (alpha > 1.0 / (snow_cv * snow_cv)) alpha = 1.0 / (snow_cv * snow_cv);
+            sdc_scale = sdc_melt_mean / alpha;
+        }
+    } else {  // :452-470
+        temp_swe += snow / (1.0 - y0);
+        if (temp_swe > 0.0) {
+            const double melt = dmin(temp_swe, potential_melt);
+            temp_swe -= melt;
+            potential_melt -= melt;
+            lwc += melt;
+            if (temp_swe < tol) temp_swe = 0.0;
+        }
+        acc_melt += potential_melt;
+        lwc += rain + potential_melt;
+        // is_snow_season(t): t in [t_w_end - n_winter_days*24h, t_w_end), t_w_end = trim(t,YEAR) + winter_end_day*24h  (:89-93)
+        bool in_season = true;
+        if (p.calculate_iso_pot_energy) {
+            const int64_t we = (int64_t)p.winter_end_day_of_year * 86400, ws = we - (int64_t)p.n_winter_days * 86400;
+            in_season = (int64_t)sec_of_year >= ws && (int64_t)sec_of_year < we;
+        }
+        if (in_season) {
+            if (storage < dmax(0.2, 2 * temp_swe) || storage < 0.2 * rain) {
+                storage += snow;
+                gs_reset_snow_pack(sca, lwc, alpha, sdc_melt_mean, acc_melt, temp_swe, storage, p);
+                sdc_scale = sdc_melt_mean / alpha;
+            }
+        }
+    }
+    gs_calc_snow_state(alpha, sdc_scale, y0, acc_melt, lwc, p.max_water, temp_swe, storage, sca);
+
+    outflow = prec + start_storage_value - storage;
+    if (outflow < 0.0) outflow = 0.0;
+
+    s.albedo = albedo;
+    s.lwc = lwc;
+    s.surface_heat = surface_heat;
+    s.alpha = alpha;
+    s.sdc_melt_mean = sdc_melt_mean;
+    s.acc_melt = acc_melt;
+    s.iso_pot_energy = iso_pot_energy;
+    s.temp_swe = temp_swe;
+    r_sca = sca;
+    r_storage = storage;
+    r_outflow = outflow * 3600000000.0 / dt_us;
+}
+
+// ---- priestley_taylor, core/priestley_taylor.h:75-103 -------------------------------------------------
+__device__ __forceinline__ double pt_potential_evapotranspiration(double land_albedo, double alpha, double temperature, double global_radiation,
+                                                                  double rhumidity) {
+    const double ck1 = 0.610780, psycr = 0.066, bolz = 0.0000000567;
+    const bool neg = temperature < 0;
+    const double ck2 = neg ? 17.84362 : 17.08085;
+    const double ck3 = neg ? 245.425 : 234.175;
+    const double ctt_inv = 1 / (ck3 + temperature);
+    const double sat_pressure = ck1 * exp(ck2 * temperature * ctt_inv);
+    const double delta = sat_pressure * ck2 * ck3 * ctt_inv * ctt_inv;
+    const double vapour_pressure = sat_pressure * rhumidity;
+    const double k_temp = temperature + 273.15;
+    const double e_atm = 1.24 * pow(10 * vapour_pressure / k_temp, 0.143) * (0.85 + 0.5 * rhumidity);
+    const double k2 = k_temp * k_temp;
+    const double net_radiation = bolz * (k2 * k2) * (e_atm - 0.98) + global_radiation * (1.0 - land_albedo);
+    const double epot = alpha * delta * net_radiation / (delta + psycr);
+    if (epot < 0.0) return 0.0;
+    return epot / (2500780 - 2361 * temperature);
+}
+
+// ---- kirchner, core/kirchner.h:186-235 --------------------------------------------------------------------
+struct KirchnerRhs {
+    double c1, c2, c3, pe;  // pe = p - e
+    __device__ __forceinline__ double operator()(double x) const {
+        const double g = exp(c1 + c2 * x + c3 * x * x);
+        return g >= 1.e-30 ? g * (pe * exp(-x) - 1.0) : 0.0;
+    }
+};
+
+// One model step of the log-transformed Kirchner ODE with odeint's controlled dopri5 + dense output
+// (abs 1e-7, rel 1e-8): same accept/reject sequence, same step-size updates, same continuous extension.
+__device__ __forceinline__ bool kirchner_step(double c1, double c2, double c3, double t1, double& q, double& q_avg, double p, double e) {
+    const double eps_abs = 1.0e-7, eps_rel = 1.0e-8;
+    if (q < 0.00001) q = 0.00001;
+    double x = log(q);
+    double t = 0.0, dt = t1;
+    const KirchnerRhs rhs{c1, c2, c3, p - e};
+    double dxdt = rhs(x);
+    double area = 0.0, f_a = q, t_a = 0.0;
+
+    const double b21 = 1.0 / 5.0;
+    const double b31 = 3.0 / 40.0, b32 = 9.0 / 40.0;
+    const double b41 = 44.0 / 45.0, b42 = -56.0 / 15.0, b43 = 32.0 / 9.0;
+    const double b51 = 19372.0 / 6561.0, b52 = -25360.0 / 2187.0, b53 = 64448.0 / 6561.0, b54 = -212.0 / 729.0;
+    const double b61 = 9017.0 / 3168.0, b62 = -355.0 / 33.0, b63 = 46732.0 / 5247.0, b64 = 49.0 / 176.0, b65 = -5103.0 / 18656.0;
+    const double c1_ = 35.0 / 384.0, c3_ = 500.0 / 1113.0, c4_ = 125.0 / 192.0, c5_ = -2187.0 / 6784.0, c6_ = 11.0 / 84.0;
+    const double dc1 = c1_ - 5179.0 / 57600.0, dc3 = c3_ - 7571.0 / 16695.0, dc4 = c4_ - 393.0 / 640.0;
+    const double dc5 = c5_ - (-92097.0 / 339200.0), dc6 = c6_ - 187.0 / 2100.0, dc7 = -1.0 / 40.0;
+
+    double x_old = x, k1 = dxdt, k3 = 0, k4 = 0, k5 = 0, k6 = 0, k7 = 0, t_old = 0.0;
+    while (t < t1) {
+        t_old = t;
+        int fails = 0;
+        double x_new, dxdt_new;
+        for (;;) {
+            double xt = 1.0 * x + dt * b21 * dxdt;
+            const double k2 = rhs(xt);
+            xt = 1.0 * x + dt * b31 * dxdt + dt * b32 * k2;
+            k3 = rhs(xt);
+            xt = 1.0 * x + dt * b41 * dxdt + dt * b42 * k2 + dt * b43 * k3;
+            k4 = rhs(xt);
+            xt = 1.0 * x + dt * b51 * dxdt + dt * b52 * k2 + dt * b53 * k3 + dt * b54 * k4;
+            k5 = rhs(xt);
+            xt = 1.0 * x + dt * b61 * dxdt + dt * b62 * k2 + dt * b63 * k3 + dt * b64 * k4 + dt * b65 * k5;
+            k6 = rhs(xt);
+            x_new = 1.0 * x + dt * c1_ * dxdt + dt * c3_ * k3 + dt * c4_ * k4 + dt * c5_ * k5 + dt * c6_ * k6;
+            dxdt_new = rhs(x_new);
+            const double x_err = dt * dc1 * dxdt + dt * dc3 * k3 + dt * dc4 * k4 + dt * dc5 * k5 + dt * dc6 * k6 + dt * dc7 * dxdt_new;
+            const double err = fabs(x_err) / (eps_abs + eps_rel * (1.0 * fabs(x) + (1.0 * dt) * fabs(dxdt)));
+            if (err > 1.0) {
+                dt *= dmax(9.0 / 10.0 * pow(err, -1.0 / 3.0), 1.0 / 5.0);
+                if (++fails >= 500) return false;
+                continue;
+            }
+            t += dt;
+            // the grown dt is only ever used by a following sub-step of this model step (initialize() resets it)
+            if (err < 0.5 && t < t1) dt *= 9.0 / 10.0 * pow(dmax(0.00032, err), -1.0 / 5.0);
+            break;
+        }
+        x_old = x; k1 = dxdt; k7 = dxdt_new;
+        x = x_new; dxdt = dxdt_new;
+        if (t < t1) {
+            const double fq = exp(x);
+            area += 0.5 * (f_a + fq) * (t - t_a);
+            f_a = fq; t_a = t;
+        }
+    }
+    {
+        const double dtl = t - t_old;
+        const double theta = (t1 - t_old) / dtl;
+        const double X1 = 5.0 * (2558722523.0 - 31403016.0 * theta) / 11282082432.0;
+        const double X3 = 100.0 * (882725551.0 - 15701508.0 * theta) / 32700410799.0;
+        const double X4 = 25.0 * (443332067.0 - 31403016.0 * theta) / 1880347072.0;
+        const double X5 = 32805.0 * (23143187.0 - 3489224.0 * theta) / 199316789632.0;
+        const double X6 = 55.0 * (29972135.0 - 7076736.0 * theta) / 822651844.0;
+        const double X7 = 10.0 * (7414447.0 - 829305.0 * theta) / 29380423.0;
+        const double theta_m_1 = theta - 1.0;
+        const double theta_sq = theta * theta;
+        const double A = theta_sq * (3.0 - 2.0 * theta);
+        const double B = theta_sq * theta_m_1;
+        const double C = theta_sq * theta_m_1 * theta_m_1;
+        const double D = theta * theta_m_1 * theta_m_1;
+        const double b1_theta = A * c1_ - C * X1 + D;
+        const double b3_theta = A * c3_ + C * X3;
+        const double b4_theta = A * c4_ - C * X4;
+        const double b5_theta = A * c5_ + C * X5;
+        const double b6_theta = A * c6_ - C * X6;
+        const double b7_theta = B + C * X7;
+        x = 1.0 * x_old + dtl * b1_theta * k1 + dtl * b3_theta * k3 + dtl * b4_theta * k4 + dtl * b5_theta * k5 + dtl * b6_theta * k6 +
+            dtl * b7_theta * k7;
+    }
+    q = exp(x);
+    area += 0.5 * (f_a + q) * (t1 - t_a);
+    q_avg = area / (t1 - 0.0);
+    return true;
+}
+
+// ---- the window kernel ----------------------------------------------------------------------------------
+// COLLECT bits: 1 avg_discharge+charge, 2 snow sca/swe, 4 snow_outflow/glacier_melt/ae/pe, 8 state series
+template <int COLLECT>
+__global__ void __launch_bounds__(128) ptgsk_run_kernel(const PtgskRunArgs a) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in_range = c < a.n_cells;
+    const int64_t cc = in_range ? c : a.n_cells - 1;  // out-of-range lanes shadow the last cell, never store
+    const bool active = in_range && (a.active == nullptr || a.active[cc] != 0);
+    const unsigned lane = threadIdx.x & 31u;
+
+    const PtgskParam& p = a.params[a.pset[cc]];
+    const double altitude = a.z[cc], cell_area_m2 = a.area[cc];
+    const double glacier_fraction = a.glacier[cc], lake = a.lake[cc], reservoir = a.reservoir[cc], forest_fraction = a.forest[cc];
+    // run_pt_gs_k prologue, pt_gs_k.h:347-357
+    const double gm_direct = p.gm_direct_response;
+    const double gm_routed = 1 - gm_direct;
+    const double snow_storage_fraction = 1.0 - lake - reservoir;
+    const double kirchner_routed_prec = reservoir * (1.0 - p.reservoir_direct_response_fraction) + lake;
+    const double direct_response_fraction = glacier_fraction * gm_direct + reservoir * p.reservoir_direct_response_fraction;
+    const double kirchner_fraction = 1 - direct_response_fraction;
+    const double glacier_area_m2 = cell_area_m2 * glacier_fraction;
+
+    const int64_t n = a.n_cells;
+    GsState gs;
+    gs.albedo = a.state[0 * n + cc]; gs.lwc = a.state[1 * n + cc]; gs.surface_heat = a.state[2 * n + cc]; gs.alpha = a.state[3 * n + cc];
+    gs.sdc_melt_mean = a.state[4 * n + cc]; gs.acc_melt = a.state[5 * n + cc]; gs.iso_pot_energy = a.state[6 * n + cc];
+    gs.temp_swe = a.state[7 * n + cc];
+    double kq = a.state[8 * n + cc];
+
+    // segmented-reduction bookkeeping: lanes of one slot are contiguous in the warp
+    int my_slot = -1;
+    bool head = false;
+    if (a.partial != nullptr) {
+        my_slot = in_range ? a.slot[cc] : -1;
+        const int prev = __shfl_up_sync(0xffffffffu, my_slot, 1);
+        head = in_range && (lane == 0 || prev != my_slot);
+    }
+
+    double f_t = a.f[0][cc], f_p = a.f[1][cc], f_r = a.f[2][cc], f_w = a.f[3][cc], f_h = a.f[4][cc];
+    bool failed = false;
+
+    for (int i = 0; i < a.n_steps; ++i) {
+        const double temp = f_t, prec_raw = f_p, rad = f_r, wind = f_w, rel_hum = f_h;
+        if (i + 1 < a.n_steps) {  // prefetch the next step's forcing while this step computes
+            const int64_t o = (int64_t)(i + 1) * n + cc;
+            f_t = a.f[0][o]; f_p = a.f[1][o]; f_r = a.f[2][o]; f_w = a.f[3][o]; f_h = a.f[4][o];
+        }
+        const int64_t step = a.first_step + i;
+        const int64_t orow = (step - a.out_first_step) * n + cc;
+        double out_q = 0.0, out_charge = 0.0;
+        if (active) {
+            const double prec = prec_raw * p.p_corr_scale_factor;
+            if (COLLECT & 8) {  // state at the beginning of the period, scale_snow applied (pt_gs_k.h:213-218,367)
+                a.st[0][orow] = mmh_to_m3s(kq, cell_area_m2);
+                a.st[1][orow] = gs.albedo;
+                a.st[2][orow] = gs.lwc * snow_storage_fraction;
+                a.st[3][orow] = gs.surface_heat;
+                a.st[4][orow] = gs.alpha;
+                a.st[5][orow] = gs.sdc_melt_mean;
+                a.st[6][orow] = gs.acc_melt;
+                a.st[7][orow] = gs.iso_pot_energy;
+                a.st[8][orow] = gs.temp_swe * snow_storage_fraction;
+            }
+            double sca, storage, outflow;
+            gs_step(gs, sca, storage, outflow, p, a.day_of_year[step], a.sec_of_year[step], a.dt_seconds, a.dt_us, temp, rad, prec, wind,
+                    rel_hum, forest_fraction, altitude);
+            // glacier_melt::step, glacier_melt.h:47-52
+            const double sca_m2 = cell_area_m2 * sca;
+            const double gm_melt_m3s =
+                (glacier_area_m2 <= sca_m2 || temp <= 0.0) ? 0.0 : p.gm_dtf * temp * (glacier_area_m2 - sca_m2) * (0.001 / 86400.0);
+            const double pot = pt_potential_evapotranspiration(p.pt_albedo, p.pt_alpha, temp, rad, rel_hum) * 3600.0;
+            // actual_evapotranspiration::calculate_step, actual_evapotranspiration.h:56-62
+            const double ae = pot * (1.0 - exp(-kq * 3.0 / p.ae_scale_factor)) * (1.0 - dmax(sca, glacier_fraction));
+            const double gm_mmh = m3s_to_mmh(gm_melt_m3s, cell_area_m2);
+            double q_avg;
+            if (!kirchner_step(p.c1, p.c2, p.c3, a.dt_hours, kq, q_avg,
+                               outflow * snow_storage_fraction + prec * kirchner_routed_prec + gm_routed * gm_mmh, ae)) {
+                failed = true;
+                q_avg = nan("");
+            }
+            const double total_discharge = dmax(0.0, prec - ae) * direct_response_fraction + gm_direct * gm_mmh + q_avg * kirchner_fraction;
+            const double charge_m3s =
+                +mmh_to_m3s(prec, cell_area_m2) - mmh_to_m3s(ae, cell_area_m2) + gm_melt_m3s - mmh_to_m3s(total_discharge, cell_area_m2);
+            out_q = mmh_to_m3s(total_discharge, cell_area_m2);
+            out_charge = charge_m3s;
+            if (COLLECT & 1) { a.resp[0][orow] = out_q; a.resp[1][orow] = charge_m3s; }
+            if (COLLECT & 2) { a.resp[2][orow] = sca; a.resp[3][orow] = storage * snow_storage_fraction; }
+            if (COLLECT & 4) {
+                a.resp[4][orow] = mmh_to_m3s(outflow * snow_storage_fraction, cell_area_m2);
+                a.resp[5][orow] = gm_melt_m3s;
+                a.resp[6][orow] = ae;
+                a.resp[7][orow] = pot;
+            }
+        }
+        if (a.partial != nullptr) {  // warp-uniform
+            double v0 = out_q, v1 = out_charge;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const double o0 = __shfl_down_sync(0xffffffffu, v0, off);
+                const double o1 = __shfl_down_sync(0xffffffffu, v1, off);
+                const int os = __shfl_down_sync(0xffffffffu, my_slot, off);
+                if (lane + off < 32 && os == my_slot) { v0 += o0; v1 += o1; }
+            }
+            if (head) {
+                double* dst = a.partial + ((int64_t)i * a.n_slots + my_slot) * 2;
+                dst[0] = v0;
+                dst[1] = v1;
+            }
+        }
+    }
+    if (active) {
+        if ((COLLECT & 8) && a.collect_end_state) {
+            const int64_t orow = (a.first_step + a.n_steps - a.out_first_step) * n + cc;
+            a.st[0][orow] = mmh_to_m3s(kq, cell_area_m2);
+            a.st[1][orow] = gs.albedo;
+            a.st[2][orow] = gs.lwc * snow_storage_fraction;
+            a.st[3][orow] = gs.surface_heat;
+            a.st[4][orow] = gs.alpha;
+            a.st[5][orow] = gs.sdc_melt_mean;
+            a.st[6][orow] = gs.acc_melt;
+            a.st[7][orow] = gs.iso_pot_energy;
+            a.st[8][orow] = gs.temp_swe * snow_storage_fraction;
+        }
+        a.state[0 * n + cc] = gs.albedo; a.state[1 * n + cc] = gs.lwc; a.state[2 * n + cc] = gs.surface_heat; a.state[3 * n + cc] = gs.alpha;
+        a.state[4 * n + cc] = gs.sdc_melt_mean; a.state[5 * n + cc] = gs.acc_melt; a.state[6 * n + cc] = gs.iso_pot_energy;
+        a.state[7 * n + cc] = gs.temp_swe; a.state[8 * n + cc] = kq;
+        if (failed) atomicOr(a.error_flag, ERR_KIRCHNER_STEP);
+    }
+}
+
+// catchment sums: out[(step) * n_catch + k] = sum of the slots of catchment k, in slot order (fixed -> deterministic)
+__global__ void catchment_reduce_kernel(const double* __restrict__ partial, int64_t n_slots, const int32_t* __restrict__ cat_ptr,
+                                        const int32_t* __restrict__ cat_slots, int n_catch, int n_steps, double* __restrict__ out_q,
+                                        double* __restrict__ out_charge, int64_t out_row0) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)n_steps * n_catch) return;
+    const int i = int(idx / n_catch), k = int(idx % n_catch);
+    double s0 = 0.0, s1 = 0.0;
+    for (int j = cat_ptr[k]; j < cat_ptr[k + 1]; ++j) {
+        const double* src = partial + ((int64_t)i * n_slots + cat_slots[j]) * 2;
+        s0 += src[0];
+        s1 += src[1];
+    }
+    out_q[(out_row0 + i) * n_catch + k] = s0;
+    out_charge[(out_row0 + i) * n_catch + k] = s1;
+}
+
+}  // namespace sb2
