@@ -39,7 +39,9 @@ enum {
 /* per-cell response series ids (all_response_collector member order); SB2_R_SOIL_OUTFLOW is hbv_stack only */
 enum { SB2_R_AVG_DISCHARGE = 0, SB2_R_CHARGE_M3S, SB2_R_SNOW_SCA, SB2_R_SNOW_SWE, SB2_R_SNOW_OUTFLOW, SB2_R_GLACIER_MELT,
        SB2_R_AE_OUTPUT, SB2_R_PE_OUTPUT, SB2_R_SOIL_OUTFLOW, SB2_N_RESPONSE };
-/* pt_gs_k state series ids (state_collector member order, core/pt_gs_k_cell_model.h:146-208) */
+/* pt_gs_k state series ids (state_collector member order, core/pt_gs_k_cell_model.h:146-208).
+ * pt_hs_k: 0 kirchner_discharge, 1 snow_sca, 2 snow_swe (core/pt_hs_k_cell_model.h:148-206);
+ * hbv_stack: 0 snow_swe, 1 snow_sca, 2 soil_moisture, 3 tank_uz, 4 tank_lz (core/hbv_stack_cell_model.h:148-213) */
 enum { SB2_S_KIRCHNER_DISCHARGE = 0, SB2_S_GS_ALBEDO, SB2_S_GS_LWC, SB2_S_GS_SURFACE_HEAT, SB2_S_GS_ALPHA, SB2_S_GS_SDC_MELT_MEAN,
        SB2_S_GS_ACC_MELT, SB2_S_GS_ISO_POT_ENERGY, SB2_S_GS_TEMP_SWE, SB2_N_STATE_SERIES };
 
@@ -99,11 +101,14 @@ int sb2_state_size(const sb2_model* m);                                 /* doubl
 int sb2_set_region_parameter(sb2_model* m, const double* p, int n);                     /* :646-655, vector order of parameter::set */
 int sb2_get_region_parameter(const sb2_model* m, double* p, int n);                     /* :660 */
 int sb2_set_catchment_parameter(sb2_model* m, int64_t cid, const double* p, int n);     /* :668-678 */
+int sb2_get_catchment_parameter(const sb2_model* m, int64_t cid, double* p, int n);     /* :702-708; the region parameter if no override */
 int sb2_remove_catchment_parameter(sb2_model* m, int64_t cid);                          /* :683-691 */
 int sb2_has_catchment_parameter(const sb2_model* m, int64_t cid);                       /* :693 */
 int sb2_set_catchment_calculation_filter(sb2_model* m, const int64_t* cids, int n);     /* :715-729; n == 0 clears */
 int sb2_set_states(sb2_model* m, const double* states, int64_t n_cells);                /* :802-809, [cell][state_size] */
 int sb2_get_states(const sb2_model* m, double* states, int64_t n_cells);                /* :784-787 */
+int sb2_set_initial_state(sb2_model* m, const double* states, int64_t n_cells);         /* the public member initial_state, :313 */
+int sb2_get_initial_state(const sb2_model* m, double* states, int64_t n_cells);
 int sb2_revert_to_initial_state(sb2_model* m);                                          /* :814-818 */
 int sb2_adjust_q(sb2_model* m, double q_scale, const int64_t* cids, int n);             /* :831-837 */
 int sb2_set_collector_mode(sb2_model* m, int collect_bits);                             /* cell type + set_state_collection / set_snow_sca_swe_collection :844-858 */
@@ -138,6 +143,15 @@ int sb2_get_state_series(const sb2_model* m, int series, int64_t start_step, int
 /* catchment_discharges / catchment_charges (:873-900): out [n_steps][n_catchments], cix order */
 int sb2_catchment_discharges(const sb2_model* m, int64_t start_step, int64_t n_steps, double* out);
 int sb2_catchment_charges(const sb2_model* m, int64_t start_step, int64_t n_steps, double* out);
+
+/* ---- routing (core/routing.h:145-383; region_model.h:909-949) -------------------------------------- */
+/* river_network: rivers [n][6] = id, downstream id (0 = none), downstream distance [m], uhg velocity, alpha, beta (routing.h:98-123).
+ * Validates ids and acyclicity like river_network::add / set_downstream_by_id (routing.h:160-250). */
+int sb2_set_river_network(sb2_model* m, int64_t n_rivers, const double* rivers);
+/* river_local_inflow_m3s / river_upstream_inflow_m3s / river_output_flow_m3s (region_model.h:926-949) of river `rid`
+ * over [start_step, start_step+n_steps); any output pointer may be NULL.  Needs avg_discharge collected over the axis. */
+int sb2_river_flows(sb2_model* m, int64_t rid, int64_t start_step, int64_t n_steps, double* local_inflow, double* upstream_inflow,
+                    double* output);
 
 /* ---- device-side hooks (plumbing for torch.distributed / CUDA-event timing; not part of the reference surface) -- */
 int sb2_set_stream(sb2_model* m, void* cuda_stream);           /* launch on this stream (default: the legacy default stream) */

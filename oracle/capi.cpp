@@ -247,12 +247,13 @@ int sho_idw_neighbours(int64_t n_src, const double* src_xyz, int64_t n_dst, cons
     }
     SHO_END
 }
-// btk_par: gradient_sd sill nug range zscale
+// btk_par: gradient_sd sill nug range zscale fixed_prior_gradient(NaN = the day-of-year sinusoid)
 int sho_btk_run(int64_t n_src, const double* src_xyz, const double* src_values, int64_t t0_us, int64_t dt_us, int64_t n_steps, int64_t n_dst,
                 const double* dst_xyz, const double* btk_par, double* out, int64_t o_tstride, int64_t o_cstride) {
     SHO_TRY
     btk::parameter p;
     p.gradient_sd = btk_par[0]; p.sill_value = btk_par[1]; p.nug_value = btk_par[2]; p.range_value = btk_par[3]; p.zscale_value = btk_par[4];
+    p.fixed_gradient = btk_par[5];
     fixed_dt ta{t0_us, dt_us, size_t(n_steps)};
     btk::btk_interpolation(make_points(n_src, src_xyz), src_values, ta, make_points(n_dst, dst_xyz), p, out, o_tstride, o_cstride);
     SHO_END

@@ -25,6 +25,15 @@ PTGSK_STATES = ("kirchner_discharge", "gs_albedo", "gs_lwc", "gs_surface_heat", 
 HS_RESPONSES = PTGSK_RESPONSES + ("soil_outflow",)
 
 
+GEO_COLS = ("x", "y", "z", "area", "catchment_id", "radiation_slope_factor", "glacier", "lake", "reservoir", "forest", "routing_id",
+            "routing_distance")
+
+
+def geo_matrix(geo_records):
+    """numpy record array with the fields of sb2_geo_cell -> the oracle's [n][12] double matrix"""
+    return np.stack([np.asarray(geo_records[c], dtype=np.float64) for c in GEO_COLS], axis=1)
+
+
 def build(force=False):
     so = os.path.join(_HERE, "libsho_oracle.so")
     srcs = [os.path.join(_HERE, f) for f in ("capi.cpp", "sho_core.hpp", "sho_pt_gs_k.hpp", "sho_hbv.hpp", "sho_region.hpp")]
@@ -286,8 +295,8 @@ def idw_neighbours(src_xyz, dst_xyz, par):
     return idx, w, cnt
 
 
-def btk_par(gradient_sd=0.0025, sill=25.0, nug=0.5, range_=200000.0, zscale=20.0):
-    return _f64([gradient_sd, sill, nug, range_, zscale])
+def btk_par(gradient_sd=0.0025, sill=25.0, nug=0.5, range_=200000.0, zscale=20.0, fixed_gradient=float("nan")):
+    return _f64([gradient_sd, sill, nug, range_, zscale, fixed_gradient])
 
 
 def btk_run(src_xyz, src_values, dst_xyz, t0_us, dt_us, par=None):

@@ -249,7 +249,9 @@ struct parameter {  // :204-230
     double nug_value = 0.5;
     double range_value = 200000.0;
     double zscale_value = 20.0;
+    double fixed_gradient = nan_v;  // test hook: the reference's test Parameter returns a constant prior gradient (test/bayesian_kriging_test.cpp:62-84)
     double temperature_gradient(utctime p_start, utctimespan p_span) const {  // :220-223
+        if (std::isfinite(fixed_gradient)) return fixed_gradient;
         const double doy = double(calendar::day_of_year(p_start + p_span / 2));
         return 1.18e-3 * std::sin(6.2831 / 365 * (doy + 79.0)) - 5.48e-3;
     }
@@ -350,7 +352,7 @@ inline void btk_interpolation(const std::vector<geo_point>& src, const double* s
 namespace routing {
 inline double gamma_pdf(double alpha, double x) {  // pdf of Gamma(shape alpha, scale 1)
     if (x < 0) return 0.0;
-    if (x == 0) return alpha == 1.0 ? 1.0 : (alpha > 1.0 ? 0.0 : std::numeric_limits<double>::infinity());
+    if (x == 0) return 0.0;  // boost 1.68 gamma.hpp pdf(): "if(x == 0) return 0;" for every shape
     return std::exp((alpha - 1.0) * std::log(x) - x - std::lgamma(alpha));
 }
 inline double gamma_quantile(double alpha, double pq) {  // inverse of P(alpha, x) by bracketed Newton on full-double P

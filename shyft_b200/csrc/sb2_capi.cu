@@ -1,0 +1,1170 @@
+// sb2_capi.cu -- the C ABI of include/shyft_b200.h over the sm_100a kernels.
+//
+// Mirrors the member surface of region_model<cell_t> (core/region_model.h:211-1049): construction and catchment
+// indexing (:233-249,283-291), parameters (:646-708), filter (:715-729), states (:784-837), interpolate (:397-527),
+// run_cells (:578-597), catchment_discharges/charges (:873-900).  Host code here only packs/unpacks structure-of-arrays
+// data, builds the small station-side operators and launches kernels; there is no CPU compute path.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/shyft_b200.h"
+#include "sb2_host.hpp"
+#include "sb2_interp.cuh"
+#include "sb2_ptgsk.cuh"
+#include "sb2_hbv.cuh"
+#include "sb2_routing.cuh"
+
+using namespace sb2;
+
+namespace {
+
+struct Error : std::runtime_error { using std::runtime_error::runtime_error; };
+
+#define CUDA_OK(expr)                                                                                              \
+    do {                                                                                                           \
+        cudaError_t e_ = (expr);                                                                                   \
+        if (e_ != cudaSuccess) throw Error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #expr);   \
+    } while (0)
+
+thread_local std::string g_create_error;
+
+template <class T>
+struct DevArray {  // library-owned device buffer
+    T* p = nullptr;
+    size_t n = 0;
+    DevArray() {}
+    DevArray(const DevArray&) = delete;
+    DevArray& operator=(const DevArray&) = delete;
+    ~DevArray() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void resize(size_t count) {
+        if (count == n) return;
+        release();
+        if (count) {
+            cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                throw Error("device allocation of " + std::to_string(count * sizeof(T)) + " bytes failed: " + cudaGetErrorString(e));
+            }
+        }
+        n = count;
+    }
+    void ensure(size_t count) { if (count > n) resize(count); }
+    void upload(const T* h, size_t count, cudaStream_t s) {
+        resize(count);
+        if (count) CUDA_OK(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    }
+    void upload(const std::vector<T>& h, cudaStream_t s) { upload(h.data(), h.size(), s); }
+};
+
+struct Source {  // one region_environment variable: geo-located series on the model axis (api/api.h:137-168)
+    int64_t n_src = 0;
+    std::vector<double> xyz;       // [src][3]
+    std::vector<double> h_values;  // [T][src], host copy (BTK validity bookkeeping, single-source copy)
+    DevArray<double> d_xyz, d_values;
+    bool has_nonfinite = false;
+};
+
+struct IdwPlan {  // neighbour lists of one variable (inverse_distance.h:160-203), [k][cell] on the device
+    bool valid = false;
+    IdwParam p{};
+    int64_t n_src = 0;
+    DevArray<int32_t> idx, cnt;
+    DevArray<double> w, f;
+};
+
+struct BtkOps {  // operators of one valid-station subset
+    std::vector<int> valid;
+    DevArray<double> omega, bm, E_beta_w, sz;
+    DevArray<int32_t> valid_idx;
+};
+
+const int kParamSize[3] = {31, 18, 22};
+const int kSnowBins = 5;
+const int kStateSize[3] = {9, 3 + 2 * kSnowBins, 5 + 2 * kSnowBins};
+
+inline int grid_for(int64_t n, int block) { return int((n + block - 1) / block); }
+
+}  // namespace
+
+struct sb2_model {
+    int stack = 0, device = 0;
+    cudaStream_t stream = 0;
+    std::string err;
+    int64_t n = 0;
+    std::vector<sb2_geo_cell> geo;
+    std::vector<int64_t> cix_of_cell, cix_to_cid;
+    std::map<int64_t, int64_t> cid_to_cix;
+    int n_param = 0, n_state = 0;
+    // parameters: region + per-catchment overrides (region_model.h:646-708)
+    std::vector<double> region_param;
+    std::map<int64_t, std::vector<double>> catch_param;
+    bool param_dirty = true;
+    std::vector<uint8_t> catchment_filter;  // by cix; empty = no filter
+    bool filter_dirty = true;
+    // static per-cell SoA
+    DevArray<double> d_x, d_y, d_z, d_area, d_glacier, d_lake, d_reservoir, d_forest, d_slope;
+    DevArray<int32_t> d_pset;
+    DevArray<uint8_t> d_active;
+    DevArray<PtgskParam> d_ptgsk_params;
+    DevArray<HbvParam> d_hbv_params;
+    // state [n_state][n] + the initial-state snapshot (region_model.h:313,593-594)
+    DevArray<double> d_state, d_initial_state;
+    bool has_initial = false;
+    // time axis
+    int64_t t0 = 0, dt = 0, T = 0;
+    DevArray<int32_t> d_doy, d_soy;
+    std::vector<double> h_prior_gradient;
+    DevArray<double> d_prior_gradient;
+    // forcing [rows][n] per variable; rows cover steps [forcing_first, forcing_first + forcing_rows)
+    DevArray<double> d_forcing[SB2_N_FORCING];
+    int64_t forcing_first = 0, forcing_rows = 0;
+    Source src[SB2_N_FORCING];
+    // interpolation plan cache
+    sb2_interpolation_parameter ip{};
+    bool ip_valid = false;
+    IdwPlan idw[SB2_N_FORCING];
+    std::vector<std::unique_ptr<BtkOps>> btk_cache;
+    DevArray<double> d_btk_kbuf, d_btk_beta, d_btk_resid;
+    // collected series
+    int collect_bits = SB2_COLLECT_DISCHARGE;
+    DevArray<double> d_resp[SB2_N_RESPONSE], d_st[SB2_N_STATE_SERIES];
+    int64_t out_first = 0, out_rows = 0;  // response rows cover [out_first, out_first + out_rows); state series one more
+    int64_t ran_first = 0, ran_steps = 0;
+    DevArray<double> d_cq, d_cc;  // catchment sums [T][n_catch]
+    // segmented catchment reduction
+    DevArray<int32_t> d_slot, d_cat_ptr, d_cat_slots;
+    int64_t n_slots = 0;
+    DevArray<double> d_partial;
+    int partial_steps = 0;
+    DevArray<int> d_error_flag;
+    // routing (core/routing.h)
+    std::vector<double> rivers;  // [n][6] id downstream distance velocity alpha beta
+    // bookkeeping
+    int64_t launches = 0;
+    float last_step_ms = 0.f, last_interp_ms = 0.f;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+
+    int64_t n_catch() const { return int64_t(cix_to_cid.size()); }
+    void use_device() const { CUDA_OK(cudaSetDevice(device)); }
+};
+
+namespace {
+
+template <class F>
+int guarded(sb2_model* m, F&& f) {
+    try {
+        if (!m) throw Error("null model");
+        m->use_device();
+        f();
+        return 0;
+    } catch (const std::exception& e) {
+        if (m) m->err = e.what();
+        return 1;
+    }
+}
+template <class F>
+int guarded_c(const sb2_model* m, F&& f) { return guarded(const_cast<sb2_model*>(m), f); }
+
+// ---- parameter tables ------------------------------------------------------------------------------------------
+// vector order of pt_gs_k::parameter::set (core/pt_gs_k.h:77-112)
+PtgskParam make_ptgsk_param(const double* v, int64_t dt_us) {
+    PtgskParam p{};
+    p.c1 = v[0]; p.c2 = v[1]; p.c3 = v[2];
+    p.ae_scale_factor = v[3];
+    p.tx = v[4]; p.wind_scale = v[5]; p.max_water = v[6]; p.wind_const = v[7];
+    p.fast_albedo_decay_rate = v[8]; p.slow_albedo_decay_rate = v[9]; p.surface_magnitude = v[10];
+    p.max_albedo = v[11]; p.min_albedo = v[12]; p.snowfall_reset_depth = v[13]; p.snow_cv = v[14]; p.glacier_albedo = v[15];
+    p.p_corr_scale_factor = v[16];
+    p.snow_cv_forest_factor = v[17]; p.snow_cv_altitude_factor = v[18];
+    p.pt_albedo = v[19]; p.pt_alpha = v[20];
+    p.initial_bare_ground_fraction = v[21];
+    p.winter_end_day_of_year = int32_t(size_t(v[22]));
+    p.calculate_iso_pot_energy = v[23] != 0.0 ? 1 : 0;
+    p.gm_dtf = v[24];
+    // v[25..27] routing velocity/alpha/beta: used by the routing kernels, not by the cell step
+    p.n_winter_days = int32_t(size_t(v[28]));
+    p.gm_direct_response = v[29];
+    p.reservoir_direct_response_fraction = v[30];
+    // gamma_snow.h:341-343, evaluated once per run instead of per step (same expressions, same libm)
+    const double dt_in_days = (double(dt_us) / 1e6) / 86400.0;
+    const double albedo_range = p.max_albedo - p.min_albedo;
+    p.slow_albedo_decay_step = 0.5 * albedo_range * dt_in_days / p.slow_albedo_decay_rate;
+    p.fast_albedo_decay_step = std::pow(2.0, -dt_in_days / p.fast_albedo_decay_rate);
+    return p;
+}
+std::vector<double> default_parameter(int stack) {
+    if (stack == SB2_PT_GS_K)  // pt_gs_k::parameter() defaults, vector order
+        return {-2.439, 0.966, -0.10, 1.5, -0.5, 2.0, 0.1, 1.0, 5.0, 5.0, 30.0, 0.9, 0.6, 5.0, 0.4, 0.4, 1.0, 0.0, 0.0, 0.2, 1.26,
+                0.04,   100.0, 0.0,  6.0, 1.0,  7.0, 0.0, 221.0, 0.0, 1.0};
+    if (stack == SB2_PT_HS_K)  // pt_hs_k::parameter::get order (core/pt_hs_k.h:108-131)
+        return {-2.439, 0.966, -0.10, 1.5, 0.1, 0.0, 1.0, 0.0, 0.5, 6.0, 1.0, 0.2, 1.26, 1.0, 7.0, 0.0, 0.0, 1.0};
+    // hbv_stack::parameter::get order (core/hbv_stack.h:127-155)
+    return {300.0, 2.0, 150.0, 25.0, 0.5, 0.3, 0.8, 0.02, 0.1, 0.0, 1.0, 0.0, 0.5, 1.0, 0.2, 1.26, 6.0, 1.0, 7.0, 0.0, 0.0, 1.0};
+}
+
+void sync_parameters(sb2_model* m) {
+    if (!m->param_dirty) return;
+    // set 0 = region parameter; one more set per catchment override (region_model.h:668-678)
+    std::vector<int32_t> pset(m->n, 0);
+    std::vector<const std::vector<double>*> sets{&m->region_param};
+    std::map<int64_t, int32_t> set_of_cid;
+    for (auto& kv : m->catch_param) { set_of_cid[kv.first] = int32_t(sets.size()); sets.push_back(&kv.second); }
+    for (int64_t i = 0; i < m->n; ++i) {
+        auto f = set_of_cid.find(m->geo[i].catchment_id);
+        if (f != set_of_cid.end()) pset[i] = f->second;
+    }
+    m->d_pset.upload(pset, m->stream);
+    if (m->stack == SB2_PT_GS_K) {
+        std::vector<PtgskParam> tab;
+        for (auto* s : sets) tab.push_back(make_ptgsk_param(s->data(), m->dt > 0 ? m->dt : 3600000000LL));
+        m->d_ptgsk_params.upload(tab, m->stream);
+    } else {
+        std::vector<HbvParam> tab;
+        for (auto* s : sets) tab.push_back(make_hbv_param(m->stack == SB2_HBV_STACK, s->data()));
+        m->d_hbv_params.upload(tab, m->stream);
+    }
+    CUDA_OK(cudaStreamSynchronize(m->stream));
+    m->param_dirty = false;
+}
+void sync_filter(sb2_model* m) {
+    if (!m->filter_dirty) return;
+    if (m->catchment_filter.empty()) m->d_active.release();
+    else {
+        std::vector<uint8_t> a(m->n);
+        for (int64_t i = 0; i < m->n; ++i) a[i] = m->catchment_filter[m->cix_of_cell[i]];
+        m->d_active.upload(a, m->stream);
+        CUDA_OK(cudaStreamSynchronize(m->stream));
+    }
+    m->filter_dirty = false;
+}
+
+// ---- catchment reduction layout: one slot per (warp, run of equal catchment_ix) -----------------------------
+void build_slots(sb2_model* m) {
+    std::vector<int32_t> slot(m->n);
+    std::vector<std::vector<int32_t>> by_cat(m->n_catch());
+    int32_t ns = 0;
+    for (int64_t i = 0; i < m->n; ++i) {
+        const bool head = (i % 32 == 0) || m->cix_of_cell[i] != m->cix_of_cell[i - 1];
+        if (head) { by_cat[m->cix_of_cell[i]].push_back(ns); ++ns; }
+        slot[i] = ns - 1;
+    }
+    m->n_slots = ns;
+    std::vector<int32_t> ptr(m->n_catch() + 1, 0), flat;
+    for (int64_t k = 0; k < m->n_catch(); ++k) {
+        for (auto s : by_cat[k]) flat.push_back(s);
+        ptr[k + 1] = int32_t(flat.size());
+    }
+    m->d_slot.upload(slot, m->stream);
+    m->d_cat_ptr.upload(ptr, m->stream);
+    m->d_cat_slots.upload(flat, m->stream);
+}
+
+void free_series(sb2_model* m) {
+    for (auto& b : m->d_resp) b.release();
+    for (auto& b : m->d_st) b.release();
+    m->out_rows = 0;
+}
+
+// rows needed for the per-cell series of this stack / collect mode
+bool wants_response(const sb2_model* m, int r) {
+    const int bits = m->collect_bits;
+    if (r <= SB2_R_CHARGE_M3S) return bits & 1;
+    if (r <= SB2_R_SNOW_SWE) return bits & 2;
+    if (r <= SB2_R_PE_OUTPUT) return bits & 4;
+    return (bits & 4) && m->stack == SB2_HBV_STACK;  // soil_outflow
+}
+int n_state_series(const sb2_model* m) { return m->stack == SB2_PT_GS_K ? 9 : (m->stack == SB2_PT_HS_K ? 3 : 5); }
+
+void ensure_series(sb2_model* m, int64_t first, int64_t rows) {
+    if (m->out_first != first || m->out_rows != rows) free_series(m);
+    for (int r = 0; r < SB2_N_RESPONSE; ++r) {
+        if (wants_response(m, r)) m->d_resp[r].ensure(size_t(rows) * m->n);
+        else m->d_resp[r].release();
+    }
+    for (int s = 0; s < SB2_N_STATE_SERIES; ++s) {
+        if ((m->collect_bits & SB2_COLLECT_STATE) && s < n_state_series(m)) m->d_st[s].ensure(size_t(rows + 1) * m->n);
+        else m->d_st[s].release();
+    }
+    m->out_first = first;
+    m->out_rows = rows;
+}
+
+void fill_nan(sb2_model* m, double* p, int64_t count) {
+    if (!count) return;
+    fill_kernel<<<std::min<int64_t>(grid_for(count, 256), 148 * 16), 256, 0, m->stream>>>(p, count, nan(""));
+    ++m->launches;
+}
+
+// ---- the cell step over [first, first+n_steps) with forcing/series windows already in place -------------------
+void launch_step_range(sb2_model* m, int64_t first, int64_t n_steps, bool collect_end_state) {
+    sync_parameters(m);
+    sync_filter(m);
+    const int64_t n = m->n;
+    const int block = 128;
+    const double dt_seconds = double(m->dt) / 1e6;
+    if (m->partial_steps == 0) {
+        // bound the scratch for the per-slot partial sums to ~256 MB
+        int64_t ps = std::max<int64_t>(1, std::min<int64_t>(1024, (256LL << 20) / std::max<int64_t>(1, m->n_slots * 16)));
+        m->partial_steps = int(ps);
+        m->d_partial.resize(size_t(ps) * m->n_slots * 2);
+    }
+    for (int64_t done = 0; done < n_steps; done += m->partial_steps) {
+        const int chunk = int(std::min<int64_t>(m->partial_steps, n_steps - done));
+        const int64_t s0 = first + done;
+        const bool last = done + chunk >= n_steps;
+        if (m->stack == SB2_PT_GS_K) {
+            PtgskRunArgs a{};
+            a.n_cells = n;
+            a.z = m->d_z.p; a.area = m->d_area.p; a.glacier = m->d_glacier.p; a.lake = m->d_lake.p; a.reservoir = m->d_reservoir.p;
+            a.forest = m->d_forest.p; a.pset = m->d_pset.p; a.active = m->d_active.p; a.params = m->d_ptgsk_params.p;
+            a.state = m->d_state.p;
+            for (int v = 0; v < 5; ++v) a.f[v] = m->d_forcing[v].p + (s0 - m->forcing_first) * n;
+            a.n_steps = chunk; a.first_step = s0;
+            a.dt_seconds = dt_seconds; a.dt_hours = dt_seconds / 3600.0; a.dt_us = double(m->dt);
+            a.bb0 = 0.98 * 5.670373e-8 * std::pow(273.15, 4);
+            a.day_of_year = m->d_doy.p; a.sec_of_year = m->d_soy.p;
+            for (int r = 0; r < 8; ++r) a.resp[r] = m->d_resp[r].p;
+            for (int s = 0; s < 9; ++s) a.st[s] = m->d_st[s].p;
+            a.out_first_step = m->out_first;
+            a.collect_end_state = (last && collect_end_state) ? 1 : 0;
+            a.slot = m->d_slot.p; a.partial = m->d_partial.p; a.n_slots = m->n_slots; a.error_flag = m->d_error_flag.p;
+            const int g = grid_for(n, block);
+            switch (m->collect_bits & 15) {
+#define SB2_CASE(B) case B: ptgsk_run_kernel<B><<<g, block, 0, m->stream>>>(a); break;
+                SB2_CASE(0) SB2_CASE(1) SB2_CASE(2) SB2_CASE(3) SB2_CASE(4) SB2_CASE(5) SB2_CASE(6) SB2_CASE(7)
+                SB2_CASE(8) SB2_CASE(9) SB2_CASE(10) SB2_CASE(11) SB2_CASE(12) SB2_CASE(13) SB2_CASE(14) SB2_CASE(15)
+#undef SB2_CASE
+            }
+        } else {
+            HbvRunArgs a{};
+            a.n_cells = n;
+            a.area = m->d_area.p; a.glacier = m->d_glacier.p; a.lake = m->d_lake.p; a.reservoir = m->d_reservoir.p;
+            a.pset = m->d_pset.p; a.active = m->d_active.p; a.params = m->d_hbv_params.p; a.state = m->d_state.p;
+            for (int v = 0; v < 5; ++v) a.f[v] = m->d_forcing[v].p + (s0 - m->forcing_first) * n;
+            a.n_steps = chunk; a.first_step = s0;
+            a.dt_seconds = dt_seconds; a.dt_hours = dt_seconds / 3600.0; a.dt_us = double(m->dt);
+            for (int r = 0; r < 9; ++r) a.resp[r] = m->d_resp[r].p;
+            for (int s = 0; s < 5; ++s) a.st[s] = m->d_st[s].p;
+            a.out_first_step = m->out_first;
+            a.collect_end_state = (last && collect_end_state) ? 1 : 0;
+            a.slot = m->d_slot.p; a.partial = m->d_partial.p; a.n_slots = m->n_slots; a.error_flag = m->d_error_flag.p;
+            a.collect = m->collect_bits & 15;
+            const int g = grid_for(n, block);
+            if (m->stack == SB2_PT_HS_K) hbv_run_kernel<false><<<g, block, 0, m->stream>>>(a);
+            else hbv_run_kernel<true><<<g, block, 0, m->stream>>>(a);
+        }
+        CUDA_OK(cudaGetLastError());
+        const int64_t total = int64_t(chunk) * m->n_catch();
+        catchment_reduce_kernel<<<grid_for(total, 256), 256, 0, m->stream>>>(m->d_partial.p, m->n_slots, m->d_cat_ptr.p, m->d_cat_slots.p,
+                                                                              int(m->n_catch()), chunk, m->d_cq.p, m->d_cc.p, s0);
+        CUDA_OK(cudaGetLastError());
+        m->launches += 2;
+    }
+}
+
+void check_device_errors(sb2_model* m) {
+    int flag = 0;
+    CUDA_OK(cudaMemcpyAsync(&flag, m->d_error_flag.p, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    CUDA_OK(cudaStreamSynchronize(m->stream));
+    if (flag) {
+        CUDA_OK(cudaMemsetAsync(m->d_error_flag.p, 0, sizeof(int), m->stream));
+        if (flag & ERR_KIRCHNER_STEP) throw Error("Max number of iterations exceeded (500). A new step size was not found.");
+        if (flag & ERR_MASS_BALANCE) throw Error("Mass balance violation!!!!");
+        if (flag & ERR_HBV_NEGATIVE_OUTFLOW) throw Error("hbv_snow: Negative outflow");
+        throw Error("device error flag " + std::to_string(flag));
+    }
+}
+
+// run_cells argument validation, messages as core/region_model.h:586-592
+void validate_run_args(const sb2_model* m, int start_step, int n_steps) {
+    if (!(m->T > 0)) throw Error("region_model::run with invalid time_axis invoked");
+    if (start_step < 0 || int64_t(start_step) + 1 > m->T) throw Error("region_model::run start_step must in range[0..n_steps-1>");
+    if (n_steps < 0) throw Error("region_model::run n_steps must be range[0..time-axis-steps]");
+    if (int64_t(start_step) + n_steps > m->T) throw Error("region_model::run start_step+n_steps must be within time-axis range");
+}
+void snapshot_initial_state_if_unset(sb2_model* m) {
+    if (m->has_initial) return;
+    m->d_initial_state.resize(m->d_state.n);
+    CUDA_OK(cudaMemcpyAsync(m->d_initial_state.p, m->d_state.p, m->d_state.n * sizeof(double), cudaMemcpyDeviceToDevice, m->stream));
+    m->has_initial = true;
+}
+
+// ---- interpolation ----------------------------------------------------------------------------------------------
+IdwParam to_idw(const sb2_idw_parameter& q) {
+    IdwParam p{};
+    p.max_members = int(q.max_members);
+    p.max_distance = q.max_distance;
+    p.distance_measure_factor = q.distance_measure_factor;
+    p.zscale = q.zscale;
+    p.default_temp_gradient = q.default_temp_gradient;
+    p.scale_factor = q.scale_factor;
+    p.gradient_by_equation = q.gradient_by_equation;
+    return p;
+}
+const sb2_idw_parameter& idw_parameter_of(const sb2_interpolation_parameter& ip, int var) {
+    switch (var) {
+        case SB2_TEMPERATURE: return ip.temperature_idw;
+        case SB2_PRECIPITATION: return ip.precipitation;
+        case SB2_RADIATION: return ip.radiation;
+        case SB2_WIND_SPEED: return ip.wind_speed;
+        default: return ip.rel_hum;
+    }
+}
+int idw_kind_of(int var) {
+    switch (var) {
+        case SB2_TEMPERATURE: return IDW_TEMPERATURE;
+        case SB2_PRECIPITATION: return IDW_PRECIPITATION;
+        case SB2_RADIATION: return IDW_RADIATION;
+        case SB2_WIND_SPEED: return IDW_WIND_SPEED;
+        default: return IDW_REL_HUM;
+    }
+}
+
+void build_idw_plan(sb2_model* m, int var) {
+    IdwPlan& pl = m->idw[var];
+    const Source& s = m->src[var];
+    pl.p = to_idw(idw_parameter_of(m->ip, var));
+    if (pl.p.max_members < 1) throw Error("inverse_distance: max_members must be >= 1");
+    pl.n_src = s.n_src;
+    const size_t k = size_t(std::min<int64_t>(pl.p.max_members, s.n_src));
+    pl.idx.resize(k * m->n); pl.w.resize(k * m->n); pl.f.resize(k * m->n); pl.cnt.resize(m->n);
+    // min_weight = 1/distance_measure(origin, (max_distance,0,0)) (inverse_distance.h:160-162)
+    const double d2 = pl.p.max_distance * pl.p.max_distance;
+    const double min_weight = 1.0 / std::pow(d2, pl.p.distance_measure_factor / 2.0);
+    idw_build_neighbours_kernel<<<grid_for(m->n, 128), 128, 0, m->stream>>>(idw_kind_of(var), m->n, m->d_x.p, m->d_y.p, m->d_z.p, m->d_slope.p,
+                                                                           int(s.n_src), s.d_xyz.p, pl.p, min_weight, pl.idx.p, pl.w.p, pl.f.p,
+                                                                           pl.cnt.p);
+    CUDA_OK(cudaGetLastError());
+    ++m->launches;
+    pl.valid = true;
+}
+
+int idw_tile_steps(int64_t n_src) {
+    const int64_t budget = 32 * 1024 / 8;  // 32 KB of source values per tile
+    return int(std::max<int64_t>(1, std::min<int64_t>(64, budget / std::max<int64_t>(1, n_src))));
+}
+
+void run_idw(sb2_model* m, int var, int64_t first, int64_t n_steps, double* out) {
+    IdwPlan& pl = m->idw[var];
+    if (!pl.valid) build_idw_plan(m, var);
+    const Source& s = m->src[var];
+    const int tile = idw_tile_steps(s.n_src);
+    const size_t smem = size_t(tile) * s.n_src * sizeof(double);
+    if (smem > 200 * 1024) throw Error("inverse_distance: too many sources for the shared-memory tile");
+    const int g = grid_for(m->n, 128);
+#define SB2_IDW(K)                                                                                                                  \
+    {                                                                                                                               \
+        if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(idw_apply_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); \
+        idw_apply_kernel<K><<<g, 128, smem, m->stream>>>(m->n, m->d_z.p, int(s.n_src), s.d_xyz.p, s.d_values.p, first, int(n_steps), pl.p, \
+                                                         pl.idx.p, pl.w.p, pl.f.p, pl.cnt.p, m->d_active.p, out, tile);               \
+    }
+    switch (idw_kind_of(var)) {
+        case IDW_TEMPERATURE: SB2_IDW(IDW_TEMPERATURE) break;
+        case IDW_PRECIPITATION: SB2_IDW(IDW_PRECIPITATION) break;
+        case IDW_RADIATION: SB2_IDW(IDW_RADIATION) break;
+        case IDW_WIND_SPEED: SB2_IDW(IDW_WIND_SPEED) break;
+        default: SB2_IDW(IDW_REL_HUM) break;
+    }
+#undef SB2_IDW
+    CUDA_OK(cudaGetLastError());
+    ++m->launches;
+}
+
+BtkOps* btk_ops_for(sb2_model* m, const std::vector<int>& valid, bool check_rank) {
+    for (auto& o : m->btk_cache)
+        if (o->valid == valid) return o.get();
+    if (m->btk_cache.size() >= 8) m->btk_cache.erase(m->btk_cache.begin() + 1);  // keep the full-set operators at slot 0
+    const Source& s = m->src[SB2_TEMPERATURE];
+    const sb2_btk_parameter& bp = m->ip.temperature;
+    host::BtkStationOps h = host::btk_station_ops(s.xyz, valid, bp.sill, bp.nug, bp.range, bp.zscale, bp.gradient_sd, check_rank);
+    auto o = std::make_unique<BtkOps>();
+    o->valid = valid;
+    const int nv = int(valid.size());
+    std::vector<double> sub_xyz(size_t(nv) * 3);
+    for (int i = 0; i < nv; ++i)
+        for (int c = 0; c < 3; ++c) sub_xyz[3 * i + c] = s.xyz[3 * valid[i] + c];
+    DevArray<double> d_sub_xyz, d_Kinv, d_FtKinv, d_M22;
+    d_sub_xyz.upload(sub_xyz, m->stream);
+    d_Kinv.upload(h.K_inv.a, m->stream);
+    d_FtKinv.upload(h.FtKinv.a, m->stream);
+    d_M22.upload(h.M22.a, m->stream);
+    o->E_beta_w.upload(h.E_beta_w.a, m->stream);
+    o->sz.upload(h.z, m->stream);
+    std::vector<int32_t> vi(valid.begin(), valid.end());
+    o->valid_idx.upload(vi, m->stream);
+    o->omega.resize(size_t(nv) * m->n);
+    o->bm.resize(size_t(2) * m->n);
+    m->d_btk_kbuf.ensure(size_t(nv) * m->n);
+    btk_build_operators_kernel<<<grid_for(m->n, 128), 128, 0, m->stream>>>(m->n, m->d_x.p, m->d_y.p, m->d_z.p, nv, d_sub_xyz.p, d_Kinv.p,
+                                                                          d_FtKinv.p, d_M22.p, bp.sill - bp.nug, bp.range, bp.zscale,
+                                                                          o->omega.p, o->bm.p, m->d_btk_kbuf.p);
+    CUDA_OK(cudaGetLastError());
+    ++m->launches;
+    CUDA_OK(cudaStreamSynchronize(m->stream));  // the temporaries above go out of scope
+    m->btk_cache.push_back(std::move(o));
+    return m->btk_cache.back().get();
+}
+
+void run_btk(sb2_model* m, int64_t first, int64_t n_steps, double* out) {
+    const Source& s = m->src[SB2_TEMPERATURE];
+    const int S = int(s.n_src);
+    std::vector<int> all(S);
+    for (int i = 0; i < S; ++i) all[i] = i;
+    BtkOps* full = btk_ops_for(m, all, true);  // built (and rank-checked) before the time loop, bayesian_kriging.h:300-316
+    // segments of constant valid-station set (:333-381)
+    int64_t i = 0;
+    while (i < n_steps) {
+        std::vector<int> valid;
+        if (!s.has_nonfinite) valid = all;
+        else {
+            const double* v = &s.h_values[size_t(first + i) * S];
+            for (int k = 0; k < S; ++k) if (std::isfinite(v[k])) valid.push_back(k);
+        }
+        if (valid.empty()) throw Error("bayesian kriging temperature: No valid sources for time period, giving up.");
+        int64_t j = i + 1;
+        if (!s.has_nonfinite) j = n_steps;
+        else
+            for (; j < n_steps; ++j) {
+                const double* v = &s.h_values[size_t(first + j) * S];
+                bool same = true;
+                size_t q = 0;
+                for (int k = 0; k < S && same; ++k) {
+                    const bool fin = std::isfinite(v[k]);
+                    const bool was = q < valid.size() && valid[q] == k;
+                    if (fin != was) same = false;
+                    if (was) ++q;
+                }
+                if (!same) break;
+            }
+        BtkOps* op = int(valid.size()) == S ? full : btk_ops_for(m, valid, false);
+        const int nv = int(valid.size());
+        const int64_t seg = j - i;
+        m->d_btk_beta.ensure(size_t(seg) * 2);
+        m->d_btk_resid.ensure(size_t(seg) * nv);
+        btk_step_prepare_kernel<<<grid_for(seg, 128), 128, 0, m->stream>>>(int(seg), first + i, S, s.d_values.p, op->valid_idx.p, nv,
+                                                                          op->E_beta_w.p, op->sz.p, m->d_btk_beta.p, m->d_btk_resid.p);
+        CUDA_OK(cudaGetLastError());
+        const int tile = idw_tile_steps(nv);
+        const size_t smem = size_t(tile) * nv * sizeof(double);
+        btk_apply_kernel<<<grid_for(m->n, 128), 128, smem, m->stream>>>(m->n, m->d_z.p, nv, op->omega.p, op->bm.p, m->d_btk_beta.p,
+                                                                       m->d_btk_resid.p, m->d_prior_gradient.p + first + i, int(seg),
+                                                                       m->d_active.p, out + i * m->n, tile);
+        CUDA_OK(cudaGetLastError());
+        m->launches += 2;
+        i = j;
+    }
+}
+
+// One variable over [first, first+n_steps) into out[(i)*n + c]; the case analysis of region_model.h:456-515
+void interpolate_variable(sb2_model* m, int var, int64_t first, int64_t n_steps, double* out) {
+    const Source& s = m->src[var];
+    if (s.n_src == 0) return;  // env.<var> == nullptr: the cell series keep their NaN fill
+    if (var == SB2_TEMPERATURE) {
+        if (s.n_src > 1) {
+            if (m->ip.use_idw_for_temperature) run_idw(m, var, first, n_steps, out);
+            else run_btk(m, first, n_steps, out);
+        } else {
+            broadcast_source_kernel<<<grid_for(m->n, 128), 128, 0, m->stream>>>(m->n, s.d_values.p + first, int(n_steps), m->d_active.p, out);
+            CUDA_OK(cudaGetLastError());
+            ++m->launches;
+        }
+    } else run_idw(m, var, first, n_steps, out);
+}
+
+bool interpolate_range(sb2_model* m, int64_t first, int64_t n_steps, int best_effort) {
+    sync_filter(m);
+    bool all_ok = true;
+    for (int var = 0; var < SB2_N_FORCING; ++var) {
+        try {
+            interpolate_variable(m, var, first, n_steps, m->d_forcing[var].p + (first - m->forcing_first) * m->n);
+        } catch (const std::exception&) {
+            if (!best_effort) throw;
+            all_ok = false;
+        }
+    }
+    return all_ok;
+}
+
+void set_interpolation_parameter(sb2_model* m, const sb2_interpolation_parameter* ip) {
+    if (!ip) throw Error("null interpolation parameter");
+    if (m->ip_valid && std::memcmp(&m->ip, ip, sizeof(*ip)) == 0) return;
+    m->ip = *ip;
+    m->ip_valid = true;
+    for (auto& pl : m->idw) pl.valid = false;
+    m->btk_cache.clear();
+}
+
+void ensure_forcing(sb2_model* m, int64_t first, int64_t rows, bool nan_fill) {
+    if (m->forcing_first == first && m->forcing_rows == rows && m->d_forcing[0].p) return;
+    for (auto& f : m->d_forcing) f.resize(size_t(rows) * m->n);
+    m->forcing_first = first;
+    m->forcing_rows = rows;
+    if (nan_fill)
+        for (auto& f : m->d_forcing) fill_nan(m, f.p, rows * m->n);
+}
+
+void copy_out_2d(sb2_model* m, const double* d_src /* [rows][n] */, int64_t rows, double* out, int layout) {
+    if (layout == SB2_TIME_MAJOR) {
+        CUDA_OK(cudaMemcpyAsync(out, d_src, size_t(rows) * m->n * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+    } else {
+        DevArray<double> tmp;
+        tmp.resize(size_t(rows) * m->n);
+        dim3 b(32, 8), g((unsigned)((m->n + 31) / 32), (unsigned)((rows + 31) / 32));
+        transpose_kernel<<<g, b, 0, m->stream>>>(d_src, tmp.p, rows, m->n);
+        CUDA_OK(cudaGetLastError());
+        ++m->launches;
+        CUDA_OK(cudaMemcpyAsync(out, tmp.p, size_t(rows) * m->n * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+        CUDA_OK(cudaStreamSynchronize(m->stream));
+        return;
+    }
+    CUDA_OK(cudaStreamSynchronize(m->stream));
+}
+
+void time_begin(sb2_model* m, int which) { CUDA_OK(cudaEventRecord(m->ev[which], m->stream)); }
+float time_end(sb2_model* m, int a, int b) {
+    CUDA_OK(cudaEventRecord(m->ev[b], m->stream));
+    CUDA_OK(cudaEventSynchronize(m->ev[b]));
+    float ms = 0.f;
+    CUDA_OK(cudaEventElapsedTime(&ms, m->ev[a], m->ev[b]));
+    return ms;
+}
+
+}  // namespace
+
+// ====================================================================================================================
+extern "C" {
+
+int sb2_version(void) { return 100; }
+
+void sb2_interpolation_parameter_default(sb2_interpolation_parameter* ip) {
+    if (!ip) return;
+    std::memset(ip, 0, sizeof(*ip));
+    ip->temperature = sb2_btk_parameter{0.0025, 25.0, 0.5, 200000.0, 20.0};  // bayesian_kriging.h:204-217
+    ip->use_idw_for_temperature = 0;
+    auto idw = [](int64_t mm) {
+        sb2_idw_parameter p{};
+        p.max_members = mm; p.max_distance = 200000.0; p.distance_measure_factor = 2.0; p.zscale = 1.0;
+        p.default_temp_gradient = -0.006; p.gradient_by_equation = 0; p.scale_factor = 1.02;
+        return p;
+    };
+    ip->temperature_idw = idw(20);  // inverse_distance.h:56-62
+    ip->precipitation = idw(20);    // :70-74
+    ip->wind_speed = idw(10);       // :38-48
+    ip->radiation = idw(10);
+    ip->rel_hum = idw(10);
+}
+
+int sb2_model_create(int stack, int64_t n_cells, const sb2_geo_cell* cells, int device, sb2_model** out) {
+    if (out) *out = nullptr;
+    std::unique_ptr<sb2_model> m;
+    try {
+        if (!out) throw Error("null output pointer");
+        if (stack < 0 || stack > 2) throw Error("unknown method stack");
+        if (n_cells <= 0 || !cells) throw Error("region_model needs at least one cell");
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0) {
+            cudaGetLastError();
+            throw Error(std::string("no CUDA device available (") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") +
+                        "); shyft_b200 has no CPU path");
+        }
+        if (device < 0 || device >= count) throw Error("CUDA device ordinal out of range");
+        m.reset(new sb2_model());
+        m->stack = stack; m->device = device; m->n = n_cells;
+        m->use_device();
+        m->geo.assign(cells, cells + n_cells);
+        m->n_param = kParamSize[stack]; m->n_state = kStateSize[stack];
+        // update_ix_to_id_mapping (region_model.h:233-249): cix in order of first appearance of the catchment id
+        m->cix_of_cell.resize(n_cells);
+        for (int64_t i = 0; i < n_cells; ++i) {
+            auto f = m->cid_to_cix.find(cells[i].catchment_id);
+            if (f == m->cid_to_cix.end()) {
+                m->cid_to_cix[cells[i].catchment_id] = int64_t(m->cix_to_cid.size());
+                m->cix_of_cell[i] = int64_t(m->cix_to_cid.size());
+                m->cix_to_cid.push_back(cells[i].catchment_id);
+            } else m->cix_of_cell[i] = f->second;
+        }
+        std::vector<double> col(n_cells);
+        auto up = [&](DevArray<double>& d, auto get) {
+            for (int64_t i = 0; i < n_cells; ++i) col[i] = get(cells[i]);
+            d.upload(col, m->stream);
+            CUDA_OK(cudaStreamSynchronize(m->stream));
+        };
+        up(m->d_x, [](const sb2_geo_cell& g) { return g.x; });
+        up(m->d_y, [](const sb2_geo_cell& g) { return g.y; });
+        up(m->d_z, [](const sb2_geo_cell& g) { return g.z; });
+        up(m->d_area, [](const sb2_geo_cell& g) { return g.area; });
+        up(m->d_glacier, [](const sb2_geo_cell& g) { return g.glacier; });
+        up(m->d_lake, [](const sb2_geo_cell& g) { return g.lake; });
+        up(m->d_reservoir, [](const sb2_geo_cell& g) { return g.reservoir; });
+        up(m->d_forest, [](const sb2_geo_cell& g) { return g.forest; });
+        up(m->d_slope, [](const sb2_geo_cell& g) { return g.radiation_slope_factor; });
+        m->region_param = default_parameter(stack);
+        // default-constructed cell states (pt_gs_k.h:204-226, pt_hs_k.h, hbv_stack.h)
+        std::vector<double> st0 = default_state(stack);
+        std::vector<double> soa(size_t(m->n_state) * n_cells);
+        for (int s = 0; s < m->n_state; ++s)
+            for (int64_t i = 0; i < n_cells; ++i) soa[size_t(s) * n_cells + i] = st0[s];
+        m->d_state.upload(soa, m->stream);
+        m->d_error_flag.resize(1);
+        CUDA_OK(cudaMemsetAsync(m->d_error_flag.p, 0, sizeof(int), m->stream));
+        build_slots(m.get());
+        for (auto& ev : m->ev) CUDA_OK(cudaEventCreate(&ev));
+        CUDA_OK(cudaStreamSynchronize(m->stream));
+        *out = m.release();
+        return 0;
+    } catch (const std::exception& e) {
+        g_create_error = e.what();
+        return 1;
+    }
+}
+
+void sb2_model_destroy(sb2_model* m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    cudaStreamSynchronize(m->stream);
+    for (auto& ev : m->ev) if (ev) cudaEventDestroy(ev);
+    delete m;
+}
+
+const char* sb2_last_error(const sb2_model* m) { return m ? m->err.c_str() : g_create_error.c_str(); }
+
+int64_t sb2_size(const sb2_model* m) { return m ? m->n : -1; }
+int64_t sb2_number_of_catchments(const sb2_model* m) { return m ? m->n_catch() : -1; }
+int sb2_catchment_ids(const sb2_model* m, int64_t* out) {
+    return guarded_c(m, [&] { std::copy(m->cix_to_cid.begin(), m->cix_to_cid.end(), out); });
+}
+int sb2_cell_catchment_ix(const sb2_model* m, int64_t* out) {
+    return guarded_c(m, [&] { std::copy(m->cix_of_cell.begin(), m->cix_of_cell.end(), out); });
+}
+int sb2_parameter_size(const sb2_model* m) { return m ? m->n_param : -1; }
+int sb2_state_size(const sb2_model* m) { return m ? m->n_state : -1; }
+
+// ---- parameters, filter, state -------------------------------------------------------------------------------------
+int sb2_set_region_parameter(sb2_model* m, const double* p, int n) {
+    return guarded(m, [&] {
+        if (n != m->n_param) throw Error("parameter vector size does not match parameter::size()");
+        m->region_param.assign(p, p + n);
+        m->param_dirty = true;
+    });
+}
+int sb2_get_region_parameter(const sb2_model* m, double* p, int n) {
+    return guarded_c(m, [&] {
+        if (n != m->n_param) throw Error("parameter vector size does not match parameter::size()");
+        std::copy(m->region_param.begin(), m->region_param.end(), p);
+    });
+}
+int sb2_set_catchment_parameter(sb2_model* m, int64_t cid, const double* p, int n) {
+    return guarded(m, [&] {
+        if (n != m->n_param) throw Error("parameter vector size does not match parameter::size()");
+        m->catch_param[cid].assign(p, p + n);
+        m->param_dirty = true;
+    });
+}
+int sb2_get_catchment_parameter(const sb2_model* m, int64_t cid, double* p, int n) {
+    return guarded_c(m, [&] {
+        if (n != m->n_param) throw Error("parameter vector size does not match parameter::size()");
+        auto f = m->catch_param.find(cid);
+        const std::vector<double>& v = f != m->catch_param.end() ? f->second : m->region_param;
+        std::copy(v.begin(), v.end(), p);
+    });
+}
+int sb2_remove_catchment_parameter(sb2_model* m, int64_t cid) {
+    return guarded(m, [&] {
+        if (m->catch_param.erase(cid)) m->param_dirty = true;
+    });
+}
+int sb2_has_catchment_parameter(const sb2_model* m, int64_t cid) { return m && m->catch_param.count(cid) ? 1 : 0; }
+
+int sb2_set_catchment_calculation_filter(sb2_model* m, const int64_t* cids, int n) {
+    return guarded(m, [&] {
+        if (n > 0) {
+            if (int64_t(n) > m->n_catch()) throw Error("set_catchment_calculation_filter: supplied list > available catchments");
+            for (int i = 0; i < n; ++i)
+                if (!m->cid_to_cix.count(cids[i])) throw Error("set_catchment_calculation_filter: no cells have supplied cid");
+            m->catchment_filter.assign(m->n_catch(), 0);
+            for (int i = 0; i < n; ++i) m->catchment_filter[m->cid_to_cix[cids[i]]] = 1;
+        } else m->catchment_filter.clear();
+        m->filter_dirty = true;
+    });
+}
+
+int sb2_set_states(sb2_model* m, const double* states, int64_t n_cells) {
+    return guarded(m, [&] {
+        if (n_cells != m->n) throw Error("Length of the state vector must equal number of cells");
+        std::vector<double> soa(size_t(m->n_state) * m->n);
+        for (int64_t i = 0; i < m->n; ++i)
+            for (int s = 0; s < m->n_state; ++s) soa[size_t(s) * m->n + i] = states[i * m->n_state + s];
+        m->d_state.upload(soa, m->stream);
+        CUDA_OK(cudaStreamSynchronize(m->stream));
+        if (!m->has_initial) {  // first set_states establishes the initial state (region_model.h:806-808)
+            m->d_initial_state.upload(soa, m->stream);
+            CUDA_OK(cudaStreamSynchronize(m->stream));
+            m->has_initial = true;
+        }
+    });
+}
+int sb2_get_states(const sb2_model* m, double* states, int64_t n_cells) {
+    return guarded_c(m, [&] {
+        if (n_cells != m->n) throw Error("Length of the state vector must equal number of cells");
+        std::vector<double> soa(size_t(m->n_state) * m->n);
+        CUDA_OK(cudaMemcpyAsync(soa.data(), m->d_state.p, soa.size() * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+        CUDA_OK(cudaStreamSynchronize(m->stream));
+        for (int64_t i = 0; i < m->n; ++i)
+            for (int s = 0; s < m->n_state; ++s) states[i * m->n_state + s] = soa[size_t(s) * m->n + i];
+    });
+}
+int sb2_set_initial_state(sb2_model* m, const double* states, int64_t n_cells) {
+    return guarded(m, [&] {
+        if (n_cells != m->n) throw Error("Length of the state vector must equal number of cells");
+        std::vector<double> soa(size_t(m->n_state) * m->n);
+        for (int64_t i = 0; i < m->n; ++i)
+            for (int s = 0; s < m->n_state; ++s) soa[size_t(s) * m->n + i] = states[i * m->n_state + s];
+        m->d_initial_state.upload(soa, m->stream);
+        CUDA_OK(cudaStreamSynchronize(m->stream));
+        m->has_initial = true;
+    });
+}
+int sb2_get_initial_state(const sb2_model* m, double* states, int64_t n_cells) {
+    return guarded_c(m, [&] {
+        if (n_cells != m->n) throw Error("Length of the state vector must equal number of cells");
+        if (!m->has_initial) throw Error("Initial state not yet established or set");
+        std::vector<double> soa(size_t(m->n_state) * m->n);
+        CUDA_OK(cudaMemcpyAsync(soa.data(), m->d_initial_state.p, soa.size() * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+        CUDA_OK(cudaStreamSynchronize(m->stream));
+        for (int64_t i = 0; i < m->n; ++i)
+            for (int s = 0; s < m->n_state; ++s) states[i * m->n_state + s] = soa[size_t(s) * m->n + i];
+    });
+}
+int sb2_revert_to_initial_state(sb2_model* m) {
+    return guarded(m, [&] {
+        if (!m->has_initial) throw Error("Initial state not yet established or set");
+        CUDA_OK(cudaMemcpyAsync(m->d_state.p, m->d_initial_state.p, m->d_state.n * sizeof(double), cudaMemcpyDeviceToDevice, m->stream));
+    });
+}
+int sb2_adjust_q(sb2_model* m, double q_scale, const int64_t* cids, int n) {
+    return guarded(m, [&] {
+        // state.adjust_q: kirchner.q *= q_scale (pt_gs_k.h:219-221, pt_hs_k.h:164); hbv_stack scales soil.sm, tank.uz, tank.lz (hbv_stack.h:182-185)
+        std::vector<uint8_t> sel(m->n, n == 0 ? 1 : 0);
+        for (int64_t i = 0; i < m->n && n > 0; ++i)
+            for (int k = 0; k < n; ++k)
+                if (m->geo[i].catchment_id == cids[k]) { sel[i] = 1; break; }
+        DevArray<uint8_t> d_sel;
+        d_sel.upload(sel, m->stream);
+        const int first = m->stack == SB2_HBV_STACK ? m->n_state - 3 : m->n_state - 1;
+        for (int s = first; s < m->n_state; ++s) {
+            scale_selected_kernel<<<grid_for(m->n, 256), 256, 0, m->stream>>>(m->d_state.p + size_t(s) * m->n, d_sel.p, m->n, q_scale);
+            ++m->launches;
+        }
+        CUDA_OK(cudaGetLastError());
+        CUDA_OK(cudaStreamSynchronize(m->stream));
+    });
+}
+int sb2_set_collector_mode(sb2_model* m, int collect_bits) {
+    return guarded(m, [&] {
+        if (collect_bits < 0 || collect_bits > 15) throw Error("collector mode out of range");
+        if (collect_bits != m->collect_bits) free_series(m);
+        m->collect_bits = collect_bits;
+    });
+}
+
+// ---- environment -----------------------------------------------------------------------------------------------------
+int sb2_initialize_cell_environment(sb2_model* m, int64_t t0_us, int64_t dt_us, int64_t n) {
+    return guarded(m, [&] {
+        if (dt_us <= 0 || n < 0) throw Error("initialize_cell_environment: invalid time axis");
+        const bool same_dt = dt_us == m->dt;
+        m->t0 = t0_us; m->dt = dt_us; m->T = n;
+        if (!same_dt) m->param_dirty = true;  // the albedo decay steps depend on dt
+        std::vector<int32_t> doy(n), soy(n);
+        m->h_prior_gradient.resize(n);
+        for (int64_t i = 0; i < n; ++i) {
+            const int64_t t = t0_us + i * dt_us;
+            doy[i] = host::day_of_year(t);
+            soy[i] = int32_t(host::seconds_of_year(t));
+            m->h_prior_gradient[i] = host::btk_prior_gradient(t, dt_us);
+        }
+        m->d_doy.upload(doy, m->stream);
+        m->d_soy.upload(soy, m->stream);
+        m->d_prior_gradient.upload(m->h_prior_gradient, m->stream);
+        m->d_cq.resize(size_t(n) * m->n_catch());
+        m->d_cc.resize(size_t(n) * m->n_catch());
+        if (n) {
+            CUDA_OK(cudaMemsetAsync(m->d_cq.p, 0, m->d_cq.n * sizeof(double), m->stream));
+            CUDA_OK(cudaMemsetAsync(m->d_cc.p, 0, m->d_cc.n * sizeof(double), m->stream));
+        }
+        // cell.env_ts is re-created NaN-filled on demand (cell_model.h:58-72); drop whatever was there
+        for (auto& f : m->d_forcing) f.release();
+        m->forcing_rows = 0; m->forcing_first = 0;
+        free_series(m);
+        m->ran_steps = 0;
+        CUDA_OK(cudaStreamSynchronize(m->stream));
+    });
+}
+
+int sb2_set_cell_forcing(sb2_model* m, int var, const double* values, int layout) {
+    return guarded(m, [&] {
+        if (var < 0 || var >= SB2_N_FORCING) throw Error("unknown forcing variable");
+        if (!(m->T > 0)) throw Error("initialize_cell_environment has not been called");
+        ensure_forcing(m, 0, m->T, true);
+        const size_t count = size_t(m->T) * m->n;
+        if (layout == SB2_TIME_MAJOR) {
+            CUDA_OK(cudaMemcpyAsync(m->d_forcing[var].p, values, count * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+        } else {
+            DevArray<double> tmp;
+            tmp.upload(values, count, m->stream);
+            dim3 b(32, 8), g((unsigned)((m->T + 31) / 32), (unsigned)((m->n + 31) / 32));
+            transpose_kernel<<<g, b, 0, m->stream>>>(tmp.p, m->d_forcing[var].p, m->n, m->T);
+            CUDA_OK(cudaGetLastError());
+            ++m->launches;
+            CUDA_OK(cudaStreamSynchronize(m->stream));
+        }
+        CUDA_OK(cudaStreamSynchronize(m->stream));
+    });
+}
+int sb2_get_cell_forcing(const sb2_model* cm, int var, int64_t start_step, int64_t n_steps, double* out, int layout) {
+    return guarded_c(cm, [&] {
+        sb2_model* m = const_cast<sb2_model*>(cm);
+        if (var < 0 || var >= SB2_N_FORCING) throw Error("unknown forcing variable");
+        if (!m->d_forcing[var].p) throw Error("cell environment not initialised");
+        if (start_step < m->forcing_first || start_step + n_steps > m->forcing_first + m->forcing_rows)
+            throw Error("requested steps are outside the resident forcing window");
+        copy_out_2d(m, m->d_forcing[var].p + (start_step - m->forcing_first) * m->n, n_steps, out, layout);
+    });
+}
+
+int sb2_set_sources(sb2_model* m, int var, int64_t n_src, const double* xyz, const double* values) {
+    return guarded(m, [&] {
+        if (var < 0 || var >= SB2_N_FORCING) throw Error("unknown forcing variable");
+        if (!(m->T > 0)) throw Error("initialize_cell_environment has not been called");
+        Source& s = m->src[var];
+        s.n_src = n_src;
+        m->idw[var].valid = false;
+        if (var == SB2_TEMPERATURE) m->btk_cache.clear();
+        if (n_src == 0) { s.xyz.clear(); s.h_values.clear(); s.d_xyz.release(); s.d_values.release(); return; }
+        s.xyz.assign(xyz, xyz + 3 * n_src);
+        s.d_xyz.upload(s.xyz, m->stream);
+        const size_t count = size_t(m->T) * n_src;
+        s.d_values.upload(values, count, m->stream);
+        // average_accessor of a stair-case source on the model axis (time_series.h:202-310,2033-2072)
+        average_accessor_same_axis_kernel<<<std::min<int64_t>(grid_for(count, 256), 148 * 16), 256, 0, m->stream>>>(s.d_values.p, int64_t(count),
+                                                                                                             double(m->dt) / 1e6);
+        CUDA_OK(cudaGetLastError());
+        ++m->launches;
+        s.has_nonfinite = false;
+        if (var == SB2_TEMPERATURE) {
+            s.h_values.assign(values, values + count);
+            for (size_t i = 0; i < count && !s.has_nonfinite; ++i) s.has_nonfinite = !std::isfinite(values[i]);
+        }
+        CUDA_OK(cudaStreamSynchronize(m->stream));
+    });
+}
+
+int sb2_interpolate(sb2_model* m, const sb2_interpolation_parameter* ip, int best_effort, int* all_ok) {
+    return guarded(m, [&] {
+        if (all_ok) *all_ok = 0;
+        if (!(m->T > 0)) throw Error("initialize_cell_environment has not been called");
+        set_interpolation_parameter(m, ip);
+        ensure_forcing(m, 0, m->T, true);
+        time_begin(m, 0);
+        const bool ok = interpolate_range(m, 0, m->T, best_effort);
+        m->last_interp_ms = time_end(m, 0, 1);
+        if (all_ok) *all_ok = ok ? 1 : 0;
+    });
+}
+
+int sb2_is_cell_env_ts_ok(sb2_model* m, int* ok) {
+    return guarded(m, [&] {
+        // region_model.h:954-962: every env_ts value of every calculated cell is finite
+        if (!m->d_forcing[0].p) { *ok = 0; return; }
+        sync_filter(m);
+        DevArray<unsigned long long> cnt;
+        cnt.resize(1);
+        CUDA_OK(cudaMemsetAsync(cnt.p, 0, sizeof(unsigned long long), m->stream));
+        for (auto& f : m->d_forcing) {
+            count_nonfinite_kernel<<<148 * 8, 256, 0, m->stream>>>(f.p, m->forcing_rows, m->n, m->d_active.p, cnt.p);
+            ++m->launches;
+        }
+        CUDA_OK(cudaGetLastError());
+        unsigned long long h = 0;
+        CUDA_OK(cudaMemcpyAsync(&h, cnt.p, sizeof(h), cudaMemcpyDeviceToHost, m->stream));
+        CUDA_OK(cudaStreamSynchronize(m->stream));
+        *ok = h == 0 ? 1 : 0;
+    });
+}
+
+// ---- the hot path ----------------------------------------------------------------------------------------------------
+int sb2_run_cells(sb2_model* m, int start_step, int n_steps) {
+    return guarded(m, [&] {
+        validate_run_args(m, start_step, n_steps);
+        if (!m->d_forcing[0].p || m->forcing_first != 0 || m->forcing_rows != m->T)
+            throw Error("run_cells: cell environment is not resident for the whole time axis (use interpolate / set_cell_forcing, or run_windowed)");
+        snapshot_initial_state_if_unset(m);
+        const int64_t first = n_steps > 0 ? start_step : 0;  // pt_gs_k.h:358-359: n_steps == 0 runs the whole axis
+        const int64_t count = n_steps > 0 ? n_steps : m->T;
+        const bool fresh = m->out_rows != m->T || m->out_first != 0;
+        ensure_series(m, 0, m->T);
+        // begin_run -> ts_init (cell_model.h:135-138,163-170): new series are NaN everywhere, existing ones NaN over the run range
+        for (int r = 0; r < SB2_N_RESPONSE; ++r)
+            if (m->d_resp[r].p) fill_nan(m, m->d_resp[r].p + (fresh ? 0 : first * m->n), (fresh ? m->T : count) * m->n);
+        for (int s = 0; s < SB2_N_STATE_SERIES; ++s)
+            if (m->d_st[s].p) fill_nan(m, m->d_st[s].p + (fresh ? 0 : first * m->n), (fresh ? m->T + 1 : count + 1) * m->n);
+        time_begin(m, 2);
+        launch_step_range(m, first, count, true);
+        m->last_step_ms = time_end(m, 2, 3);
+        m->ran_first = first; m->ran_steps = count;
+        check_device_errors(m);
+    });
+}
+
+int sb2_run_windowed(sb2_model* m, const sb2_interpolation_parameter* ip, int start_step, int n_steps, int window_steps) {
+    return guarded(m, [&] {
+        validate_run_args(m, start_step, n_steps);
+        if (window_steps <= 0) throw Error("run_windowed: window_steps must be positive");
+        set_interpolation_parameter(m, ip);
+        snapshot_initial_state_if_unset(m);
+        const int64_t first = n_steps > 0 ? start_step : 0;
+        const int64_t count = n_steps > 0 ? n_steps : m->T;
+        const int64_t W = std::min<int64_t>(window_steps, count);
+        float interp_ms = 0.f, step_ms = 0.f;
+        for (int64_t w0 = first; w0 < first + count; w0 += W) {
+            const int64_t wn = std::min<int64_t>(W, first + count - w0);
+            // the window buffers are reused: forcing rows [w0, w0+W), series rows likewise
+            if (m->forcing_rows != W || !m->d_forcing[0].p) {
+                for (auto& f : m->d_forcing) f.resize(size_t(W) * m->n);
+                m->forcing_rows = W;
+            }
+            m->forcing_first = w0;
+            for (int v = 0; v < SB2_N_FORCING; ++v)
+                if (m->src[v].n_src == 0) fill_nan(m, m->d_forcing[v].p, W * m->n);
+            time_begin(m, 0);
+            interpolate_range(m, w0, wn, 0);
+            CUDA_OK(cudaEventRecord(m->ev[1], m->stream));
+            if (m->out_rows != W) { free_series(m); }
+            ensure_series(m, w0, W);
+            m->out_first = w0;
+            CUDA_OK(cudaEventRecord(m->ev[2], m->stream));
+            launch_step_range(m, w0, wn, true);
+            CUDA_OK(cudaEventRecord(m->ev[3], m->stream));
+            CUDA_OK(cudaEventSynchronize(m->ev[3]));
+            float a = 0.f, b = 0.f;
+            CUDA_OK(cudaEventElapsedTime(&a, m->ev[0], m->ev[1]));
+            CUDA_OK(cudaEventElapsedTime(&b, m->ev[2], m->ev[3]));
+            interp_ms += a; step_ms += b;
+        }
+        m->last_interp_ms = interp_ms; m->last_step_ms = step_ms;
+        m->ran_first = first; m->ran_steps = count;
+        check_device_errors(m);
+    });
+}
+
+// ---- results -----------------------------------------------------------------------------------------------------------
+int sb2_get_response(const sb2_model* cm, int series, int64_t start_step, int64_t n_steps, double* out, int layout) {
+    return guarded_c(cm, [&] {
+        sb2_model* m = const_cast<sb2_model*>(cm);
+        if (series < 0 || series >= SB2_N_RESPONSE) throw Error("unknown response series");
+        if (!m->d_resp[series].p) throw Error("response series is not collected in the current collector mode");
+        if (start_step < m->out_first || start_step + n_steps > m->out_first + m->out_rows)
+            throw Error("requested steps are outside the resident series window");
+        copy_out_2d(m, m->d_resp[series].p + (start_step - m->out_first) * m->n, n_steps, out, layout);
+    });
+}
+int sb2_get_state_series(const sb2_model* cm, int series, int64_t start_step, int64_t n_points, double* out, int layout) {
+    return guarded_c(cm, [&] {
+        sb2_model* m = const_cast<sb2_model*>(cm);
+        if (series < 0 || series >= SB2_N_STATE_SERIES) throw Error("unknown state series");
+        if (!m->d_st[series].p) throw Error("state series is not collected in the current collector mode");
+        if (start_step < m->out_first || start_step + n_points > m->out_first + m->out_rows + 1)
+            throw Error("requested points are outside the resident series window");
+        copy_out_2d(m, m->d_st[series].p + (start_step - m->out_first) * m->n, n_points, out, layout);
+    });
+}
+static int catchment_copy(const sb2_model* cm, const DevArray<double>& d, int64_t start_step, int64_t n_steps, double* out) {
+    return guarded_c(cm, [&] {
+        sb2_model* m = const_cast<sb2_model*>(cm);
+        if (start_step < 0 || start_step + n_steps > m->T) throw Error("requested steps are outside the time axis");
+        CUDA_OK(cudaMemcpyAsync(out, d.p + start_step * m->n_catch(), size_t(n_steps) * m->n_catch() * sizeof(double), cudaMemcpyDeviceToHost,
+                                m->stream));
+        CUDA_OK(cudaStreamSynchronize(m->stream));
+    });
+}
+int sb2_catchment_discharges(const sb2_model* m, int64_t start_step, int64_t n_steps, double* out) {
+    return m ? catchment_copy(m, m->d_cq, start_step, n_steps, out) : 1;
+}
+int sb2_catchment_charges(const sb2_model* m, int64_t start_step, int64_t n_steps, double* out) {
+    return m ? catchment_copy(m, m->d_cc, start_step, n_steps, out) : 1;
+}
+
+// ---- routing (core/routing.h:326-383; region_model.h:909-949) ------------------------------------------------------------
+int sb2_set_river_network(sb2_model* m, int64_t n_rivers, const double* rivers) {
+    return guarded(m, [&] {
+        std::map<int64_t, int64_t> down;
+        for (int64_t i = 0; i < n_rivers; ++i) {
+            const int64_t id = int64_t(rivers[6 * i]);
+            if (id <= 0) throw Error("river id must be > 0");
+            if (down.count(id)) throw Error("river id already exists in the network");
+            down[id] = int64_t(rivers[6 * i + 1]);
+        }
+        for (auto& kv : down) {  // downstream must exist (or be 0) and the network must be acyclic (routing.h:215-250)
+            int64_t cur = kv.second;
+            size_t hops = 0;
+            while (cur > 0) {
+                auto f = down.find(cur);
+                if (f == down.end()) throw Error("river network: downstream river id not found");
+                cur = f->second;
+                if (++hops > down.size()) throw Error("river network: cycle detected");
+            }
+        }
+        m->rivers.assign(rivers, rivers + 6 * n_rivers);
+    });
+}
+
+int sb2_river_flows(sb2_model* m, int64_t rid, int64_t start_step, int64_t n_steps, double* local_inflow, double* upstream_inflow,
+                    double* output) {
+    return guarded(m, [&] {
+        if (!m->d_resp[SB2_R_AVG_DISCHARGE].p || m->out_first != 0 || m->out_rows != m->T)
+            throw Error("river flows need avg_discharge collected over the whole time axis (run_cells with a discharge collector)");
+        if (start_step < 0 || start_step + n_steps > m->T) throw Error("requested steps are outside the time axis");
+        // routing velocity/alpha/beta live in the cell's parameter set (pt_gs_k.h:102-104, pt_hs_k.h:81-83, hbv_stack.h:93-95)
+        const int off = m->stack == SB2_PT_GS_K ? 25 : (m->stack == SB2_PT_HS_K ? 13 : 17);
+        std::vector<double> cell_routing(size_t(m->n) * 5);
+        for (int64_t i = 0; i < m->n; ++i) {
+            auto f = m->catch_param.find(m->geo[i].catchment_id);
+            const std::vector<double>& p = f != m->catch_param.end() ? f->second : m->region_param;
+            double* cr = &cell_routing[5 * i];
+            cr[0] = double(m->geo[i].routing_id); cr[1] = m->geo[i].routing_distance;
+            cr[2] = p[off]; cr[3] = p[off + 1]; cr[4] = p[off + 2];
+        }
+        route_rivers(m->rivers, rid, cell_routing, m->n, m->T, m->dt, m->d_resp[SB2_R_AVG_DISCHARGE].p, m->stream, &m->launches, start_step,
+                     n_steps, local_inflow, upstream_inflow, output);
+    });
+}
+
+// ---- device-side hooks -----------------------------------------------------------------------------------------------------
+int sb2_set_stream(sb2_model* m, void* cuda_stream) {
+    return guarded(m, [&] {
+        CUDA_OK(cudaStreamSynchronize(m->stream));
+        m->stream = (cudaStream_t)cuda_stream;
+    });
+}
+int sb2_device_catchment_discharges(sb2_model* m, void** dptr, int64_t* n_steps, int64_t* n_catchments) {
+    return guarded(m, [&] { *dptr = m->d_cq.p; *n_steps = m->T; *n_catchments = m->n_catch(); });
+}
+int sb2_device_catchment_charges(sb2_model* m, void** dptr, int64_t* n_steps, int64_t* n_catchments) {
+    return guarded(m, [&] { *dptr = m->d_cc.p; *n_steps = m->T; *n_catchments = m->n_catch(); });
+}
+int64_t sb2_kernel_launches(const sb2_model* m) { return m ? m->launches : -1; }
+int sb2_last_run_kernel_ms(const sb2_model* m, float* step_ms, float* interp_ms) {
+    return guarded_c(m, [&] {
+        if (step_ms) *step_ms = m->last_step_ms;
+        if (interp_ms) *interp_ms = m->last_interp_ms;
+    });
+}
+
+}  // extern "C"

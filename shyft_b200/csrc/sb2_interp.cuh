@@ -23,7 +23,10 @@ struct IdwParam {
 };
 
 __device__ __forceinline__ double distance_measure(double ax, double ay, double az, double bx, double by, double bz, double p, double zscale) {
-    const double d2 = (ax - bx) * (ax - bx) + (ay - by) * (ay - by) + (az - bz) * (az - bz) * zscale * zscale;
+    // explicit round-to-nearest products and sums: never contracted to FMA, so weights (and with them the neighbour
+    // ordering) are bit-identical to the host arithmetic of the reference
+    const double dx = __dsub_rn(ax, bx), dy = __dsub_rn(ay, by), dz = __dsub_rn(az, bz);
+    const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(__dmul_rn(__dmul_rn(dz, dz), zscale), zscale));
     const double e = p / 2.0;
     return e == 1.0 ? d2 : pow(d2, e);  // pow(x, 1.0) == x exactly
 }
@@ -113,10 +116,11 @@ __global__ void __launch_bounds__(128) idw_apply_kernel(int64_t n_cells, const d
                                                         const double* __restrict__ sxyz, const double* __restrict__ src /* [T][n_src] */,
                                                         int64_t first_step, int n_steps, IdwParam p, const int32_t* __restrict__ nb_idx,
                                                         const double* __restrict__ nb_w, const double* __restrict__ nb_f,
-                                                        const int32_t* __restrict__ nb_n, double* __restrict__ out, int tile_steps) {
-    extern __shared__ double sv[];  // [tile_steps][n_src] then (temperature) [n_src] source z
+                                                        const int32_t* __restrict__ nb_n, const uint8_t* __restrict__ active,
+                                                        double* __restrict__ out, int tile_steps) {
+    extern __shared__ double sv[];  // [tile_steps][n_src]
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool ok = c < n_cells;
+    const bool ok = c < n_cells && (active == nullptr || active[c] != 0);  // cells outside the calculation filter keep their NaN fill (region_model.h:420-423)
     const int cnt = ok ? nb_n[c] : 0;
     const double z = ok ? cz[c] : 0.0;
     for (int t0 = 0; t0 < n_steps; t0 += tile_steps) {
@@ -236,10 +240,11 @@ __global__ void __launch_bounds__(128) btk_apply_kernel(int64_t n_cells, const d
                                                         const double* __restrict__ omega /* [n_valid][cells] */, const double* __restrict__ bm,
                                                         const double* __restrict__ beta, const double* __restrict__ resid,
                                                         const double* __restrict__ prior_gradient /* [n_steps] */, int n_steps,
-                                                        double* __restrict__ out /* [n_steps][cells] */, int tile_steps) {
+                                                        const uint8_t* __restrict__ active, double* __restrict__ out /* [n_steps][cells] */,
+                                                        int tile_steps) {
     extern __shared__ double sr[];  // [tile_steps][n_valid]
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool ok = c < n_cells;
+    const bool ok = c < n_cells && (active == nullptr || active[c] != 0);
     const double z = ok ? cz[c] : 0.0, bm0 = ok ? bm[c] : 0.0, bm1 = ok ? bm[n_cells + c] : 0.0;
     for (int t0 = 0; t0 < n_steps; t0 += tile_steps) {
         const int nt = min(tile_steps, n_steps - t0);
@@ -281,10 +286,28 @@ __global__ void transpose_kernel(const double* __restrict__ in, double* __restri
         if (r < rows && c < cols) out[c * rows + r] = tile[threadIdx.x][j];
     }
 }
-__global__ void count_nonfinite_kernel(const double* __restrict__ p, int64_t n, unsigned long long* __restrict__ count) {
+// non-finite values among the calculated cells of a [rows][n_cells] series (region_model.h:954-962)
+__global__ void count_nonfinite_kernel(const double* __restrict__ p, int64_t rows, int64_t n_cells, const uint8_t* __restrict__ active,
+                                       unsigned long long* __restrict__ count) {
     unsigned long long local = 0;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) local += isfinite(p[i]) ? 0 : 1;
+    const int64_t n = rows * n_cells;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (active != nullptr && active[i % n_cells] == 0) continue;
+        local += isfinite(p[i]) ? 0 : 1;
+    }
     if (local) atomicAdd(count, local);
+}
+// single temperature source: its resampled series copied to every calculated cell (region_model.h:470-481)
+__global__ void broadcast_source_kernel(int64_t n_cells, const double* __restrict__ src /* [n_steps] */, int n_steps,
+                                        const uint8_t* __restrict__ active, double* __restrict__ out) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cells || (active != nullptr && active[c] == 0)) return;
+    for (int i = 0; i < n_steps; ++i) out[(int64_t)i * n_cells + c] = src[i];
+}
+// state.adjust_q on the selected cells (region_model.h:831-837)
+__global__ void scale_selected_kernel(double* __restrict__ v, const uint8_t* __restrict__ sel, int64_t n, double scale) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && sel[i]) v[i] *= scale;
 }
 
 }  // namespace sb2

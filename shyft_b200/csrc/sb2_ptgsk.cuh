@@ -64,6 +64,7 @@ struct PtgskRunArgs {
     double dt_seconds;                         // to_seconds(dt)
     double dt_hours;                           // to_seconds(T1-T0)/to_seconds(deltahours(1))
     double dt_us;                              // double(dt.count())
+    double bb0;                                // 0.98*sigma*pow(273.15,4), gamma_snow.h:286 (host-evaluated)
     const int32_t* __restrict__ day_of_year;   // [T] calendar::day_of_year(period.start), UTC
     const int32_t* __restrict__ sec_of_year;   // [T] (period.start - trim(period.start, YEAR)) in seconds
     // collected series: element (absolute step - out_first_step, cell) at r[s][...*n_cells + c]; null = not collected
@@ -201,11 +202,10 @@ __device__ __forceinline__ void gs_reset_snow_pack(double& sca, double& lwc, dou
 
 // gamma_snow::calculator::step, gamma_snow.h:291-493
 __device__ __forceinline__ void gs_step(GsState& s, double& r_sca, double& r_storage, double& r_outflow, const PtgskParam& p, int doy,
-                                        int sec_of_year, double dt_seconds, double dt_us, double T, double rad, double prec_mm_h,
+                                        int sec_of_year, double dt_seconds, double dt_us, double BB0, double T, double rad, double prec_mm_h,
                                         double wind_speed, double rel_hum, double forest_fraction, double altitude) {
     const double tol = 1.0e-10;
     const double melt_heat = 333660.0, water_heat = 4180.0, ice_heat = 2050.0, sigma = 5.670373e-8;
-    const double BB0 = 0.98 * sigma * (273.15 * 273.15 * 273.15 * 273.15) * 0 + 309.32891622827313;  // 0.98*sigma*pow(273.15,4)
     double sdc_melt_mean = s.sdc_melt_mean;
     double acc_melt = s.acc_melt;
     double iso_pot_energy = s.iso_pot_energy;
@@ -533,7 +533,7 @@ __global__ void __launch_bounds__(128) ptgsk_run_kernel(const PtgskRunArgs a) {
                 a.st[8][orow] = gs.temp_swe * snow_storage_fraction;
             }
             double sca, storage, outflow;
-            gs_step(gs, sca, storage, outflow, p, a.day_of_year[step], a.sec_of_year[step], a.dt_seconds, a.dt_us, temp, rad, prec, wind,
+            gs_step(gs, sca, storage, outflow, p, a.day_of_year[step], a.sec_of_year[step], a.dt_seconds, a.dt_us, a.bb0, temp, rad, prec, wind,
                     rel_hum, forest_fraction, altitude);
             // glacier_melt::step, glacier_melt.h:47-52
             const double sca_m2 = cell_area_m2 * sca;

@@ -1,0 +1,77 @@
+"""GPU parity of the pt_hs_k and hbv_stack stacks and of river routing (BASELINE config 3 shape) through the C ABI."""
+import numpy as np
+import pytest
+
+from fixtures import FORCING, HBV_DEFAULT, PTHSK_DEFAULT, geo_matrix
+from parity import assert_parity
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sb():
+    import shyft_b200
+    return shyft_b200
+
+
+def _setup(sb, cls, par, stack, n=320, T=6000, S=16):
+    from shyft_b200 import synthetic
+    geo, ta, env = synthetic.make_region(n, T, S, config_index=2, cells_per_catchment=40, with_routing=True, start=1414800000)  # 2014-11-01
+    m = cls(geo, par)
+    m.run_interpolation(sb.InterpolationParameter(), ta, env)
+    st0 = synthetic.default_state(stack, n)
+    m.set_states(st0)
+    f = {k: m.cell_forcing(k) for k in FORCING}
+    return m, geo, ta, st0, f
+
+
+def test_pt_hs_k_parity(sb, oracle):
+    m, geo, ta, st0, f = _setup(sb, sb.PTHSKModel, PTHSK_DEFAULT, 1)
+    m.run_cells()
+    want = oracle.pthsk_run_cells(geo_matrix(geo), PTHSK_DEFAULT, f, st0, ta.start * 10**6, ta.delta_t * 10**6, ncore=8)
+    assert np.nanmax(want["snow_swe"]) > 5.0
+    for name in ("avg_discharge", "charge_m3s", "snow_sca", "snow_swe", "snow_outflow", "glacier_melt", "ae_output", "pe_output"):
+        assert_parity(m.response(name), want[name], "pt_hs_k " + name)
+    assert_parity(m.get_states(), want["state"], "pt_hs_k end state")
+
+
+def test_hbv_stack_parity(sb, oracle):
+    m, geo, ta, st0, f = _setup(sb, sb.HbvStackModel, HBV_DEFAULT, 2)
+    m.run_cells()
+    want = oracle.hbv_stack_run_cells(geo_matrix(geo), HBV_DEFAULT, f, st0, ta.start * 10**6, ta.delta_t * 10**6, ncore=8)
+    for name in ("avg_discharge", "charge_m3s", "snow_sca", "snow_swe", "snow_outflow", "glacier_melt", "ae_output", "pe_output", "soil_outflow"):
+        assert_parity(m.response(name), want[name], "hbv_stack " + name)
+    assert_parity(m.get_states(), want["state"], "hbv_stack end state")
+
+
+def test_hbv_chunked_equals_one_shot_and_state_series(sb):
+    m, geo, ta, st0, f = _setup(sb, sb.HbvStackModel, HBV_DEFAULT, 2, n=100, T=480)
+    m.set_state_collection(-1, True)
+    m.run_cells()
+    q, s = m.response("avg_discharge"), m.get_states()
+    sm = m.state_series("soil_moisture")
+    assert np.array_equal(sm[0], st0[:, 12]) and np.array_equal(sm[-1], s[:, 12])
+    m.revert_to_initial_state()
+    for k in range(4):
+        m.run_cells(0, 120 * k, 120)
+    assert np.array_equal(m.response("avg_discharge"), q) and np.array_equal(m.get_states(), s)
+
+
+def test_river_network_routing_parity(sb, oracle):
+    from shyft_b200 import synthetic
+    m, geo, ta, st0, f = _setup(sb, sb.PTHSKModel, PTHSK_DEFAULT, 1, n=320, T=1000)
+    m.run_cells()
+    rivers = synthetic.river_chain(m.number_of_catchments(), depth=4)
+    m.set_river_network(rivers)
+    gm = geo_matrix(geo)
+    q = m.response("avg_discharge")
+    uhg = np.tile(PTHSK_DEFAULT[13:16], (gm.shape[0], 1))
+    for rid in (1, 4, 8):
+        local, up, out = oracle.river_flows(rivers, rid, q, gm[:, 10].astype(np.int64), gm[:, 11], uhg, ta.delta_t * 10**6)
+        assert_parity(m.river_local_inflow_m3s(rid), local, f"river {rid} local inflow", rtol=1e-12)
+        assert_parity(m.river_upstream_inflow_m3s(rid), up, f"river {rid} upstream inflow", rtol=1e-12)
+        assert_parity(m.river_output_flow_m3s(rid), out, f"river {rid} output", rtol=1e-12)
+    with pytest.raises(RuntimeError, match="cycle"):
+        m.set_river_network([[1, 2, 100.0, 1.0, 7.0, 0.0], [2, 1, 100.0, 1.0, 7.0, 0.0]])
+    with pytest.raises(RuntimeError, match="not found"):
+        m.river_output_flow_m3s(999)

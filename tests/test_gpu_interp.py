@@ -1,0 +1,104 @@
+"""GPU parity of region_model::interpolate (IDW for five variables, Bayesian temperature kriging) through the C ABI."""
+import numpy as np
+import pytest
+
+from fixtures import FORCING, geo_matrix
+from parity import assert_parity
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sb():
+    import shyft_b200
+    return shyft_b200
+
+
+def _region(sb, n, T, S, **kw):
+    from shyft_b200 import synthetic
+    return synthetic.make_region(n, T, S, **kw)
+
+
+def test_idw_neighbour_lists_and_values_all_variables(sb, oracle):
+    n, T, S = 1500, 96, 64
+    geo, ta, env = _region(sb, n, T, S, config_index=11)
+    gm = geo_matrix(geo)
+    m = sb.PTGSKOptModel(geo)
+    ip = sb.InterpolationParameter(use_idw_for_temperature=1)
+    assert m.run_interpolation(ip, ta, env)
+    for name in FORCING:
+        xyz, vals = getattr(env, name)
+        mm = 20 if name in ("temperature", "precipitation") else 10
+        want = oracle.idw_run(name, xyz, oracle.average_accessor_same_axis(vals, 3600 * 10**6), gm[:, :3], oracle.idw_par(max_members=mm),
+                              dst_slope=gm[:, 5], ncore=4)
+        assert_parity(m.cell_forcing(name), want, "idw " + name, rtol=1e-12)
+
+
+def test_idw_with_missing_values_and_gradient_by_equation(sb, oracle):
+    n, T, S = 400, 200, 25
+    geo, ta, env = _region(sb, n, T, S, config_index=12, nan_fraction=0.05)
+    gm = geo_matrix(geo)
+    m = sb.PTGSKOptModel(geo)
+    ip = sb.InterpolationParameter(use_idw_for_temperature=1)
+    ip.temperature_idw.gradient_by_equation = 1
+    ip.temperature_idw.max_members = 6
+    ip.precipitation.max_members = 4
+    ip.precipitation.scale_factor = 1.05
+    ip.wind_speed.max_distance = 9000.0   # some cells end up with no station in reach -> 0/0 = NaN like the reference
+    ip.rel_hum.distance_measure_factor = 1.0
+    ip.radiation.zscale = 5.0
+    m.run_interpolation(ip, ta, env)
+    pars = dict(temperature=oracle.idw_par(max_members=6, gradient_by_equation=True), precipitation=oracle.idw_par(max_members=4, scale_factor=1.05),
+                wind_speed=oracle.idw_par(max_distance=9000.0), rel_hum=oracle.idw_par(distance_measure_factor=1.0), radiation=oracle.idw_par(zscale=5.0))
+    for name in FORCING:
+        xyz, vals = getattr(env, name)
+        want = oracle.idw_run(name, xyz, oracle.average_accessor_same_axis(vals, 3600 * 10**6), gm[:, :3], pars[name], dst_slope=gm[:, 5])
+        # the 3x3 gradient solve amplifies round-off by its condition number; everything else is a short weighted mean
+        assert_parity(m.cell_forcing(name), want, "idw+nan " + name, rtol=1e-9 if name == "temperature" else 1e-12)
+    assert not m.is_cell_env_ts_ok()
+
+
+def test_btk_full_and_reduced_station_sets(sb, oracle):
+    n, T, S = 900, 120, 36
+    geo, ta, env = _region(sb, n, T, S, config_index=13)
+    gm = geo_matrix(geo)
+    xyz, vals = env.temperature
+    vals = vals.copy()
+    vals[10:30, 3] = np.nan          # one station drops out for a while
+    vals[50:55, [0, 7, 20]] = np.nan  # three more later
+    env.temperature = (xyz, vals)
+    m = sb.PTGSKOptModel(geo)
+    ip = sb.InterpolationParameter()
+    assert m.run_interpolation(ip, ta, env)
+    want = oracle.btk_run(xyz, oracle.average_accessor_same_axis(vals, 3600 * 10**6), gm[:, :3], ta.start * 10**6, 3600 * 10**6)
+    assert_parity(m.cell_forcing("temperature"), want, "btk temperature", rtol=1e-9)
+
+
+def test_btk_all_stations_missing_is_an_error_unless_best_effort(sb):
+    n, T, S = 64, 24, 9
+    geo, ta, env = _region(sb, n, T, S, config_index=14)
+    xyz, vals = env.temperature
+    vals = vals.copy()
+    vals[5, :] = np.nan
+    env.temperature = (xyz, vals)
+    m = sb.PTGSKOptModel(geo)
+    ip = sb.InterpolationParameter()
+    assert m.run_interpolation(ip, ta, env, best_effort=True) is False          # swallowed, reported (region_model.h:517-526)
+    assert np.all(np.isfinite(m.cell_forcing("precipitation")))
+    with pytest.raises(RuntimeError, match="No valid sources for time period"):
+        m.run_interpolation(ip, ta, env, best_effort=False)
+
+
+def test_single_temperature_source_is_copied_and_missing_variable_stays_nan(sb):
+    n, T = 50, 48
+    geo, ta, env = _region(sb, n, T, 4, config_index=15)
+    xyz, vals = env.temperature
+    env.temperature = (xyz[:1], vals[:, :1])
+    env.wind_speed = None
+    m = sb.PTGSKOptModel(geo)
+    m.run_interpolation(sb.InterpolationParameter(), ta, env)
+    t = m.cell_forcing("temperature")
+    assert np.array_equal(t, np.repeat(vals[:, :1] * 3600.0 / 3600.0, n, axis=1))
+    assert np.all(np.isnan(m.cell_forcing("wind_speed")))
+    # cell-major readback is the transpose
+    assert np.array_equal(m.cell_forcing("temperature", layout=sb.capi.CELL_MAJOR), t.T)
