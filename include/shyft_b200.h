@@ -153,6 +153,12 @@ int sb2_set_river_network(sb2_model* m, int64_t n_rivers, const double* rivers);
 int sb2_river_flows(sb2_model* m, int64_t rid, int64_t start_step, int64_t n_steps, double* local_inflow, double* upstream_inflow,
                     double* output);
 
+/* ---- diagnostics ------------------------------------------------------------------------------------- */
+/* Evaluate one device function on n rows of inputs (unit tests in the style of test/gamma_snow_test.cpp, test/kirchner_test.cpp):
+ * fn 0 exp(x), 1 log(x), 2 pow(x,y), 3 lgamma(a), 4 gamma_p(a,x), 5 corr_lwc(z1,a1,b1,a2,b2), 6 calc_snow_state(shape,scale,y0,
+ * lambda,lwd,max_water_frac,temp_swe) -> swe,sca, 7 kirchner step(c1,c2,c3,dt_hours,q,p,e) -> q,q_avg,ok.  Errors: sb2_last_error(NULL). */
+int sb2_unit_eval(int device, int fn, int64_t n, const double* in, int n_in, double* out, int n_out);
+
 /* ---- device-side hooks (plumbing for torch.distributed / CUDA-event timing; not part of the reference surface) -- */
 int sb2_set_stream(sb2_model* m, void* cuda_stream);           /* launch on this stream (default: the legacy default stream) */
 int sb2_device_catchment_discharges(sb2_model* m, void** dptr, int64_t* n_steps, int64_t* n_catchments); /* [T][n_catch] fp64 in HBM */

@@ -6,6 +6,7 @@
 #include <chrono>
 #include <cstring>
 
+#include "sho_detmath.hpp"
 #include "sho_core.hpp"
 #include "sho_hbv.hpp"
 #include "sho_pt_gs_k.hpp"
@@ -45,6 +46,20 @@ int sho_hardware_concurrency() { return int(std::thread::hardware_concurrency())
 int64_t sho_day_of_year(int64_t t_us) { return int64_t(calendar::day_of_year(t_us)); }
 int64_t sho_trim_year(int64_t t_us) { return calendar::trim_year(t_us); }
 int64_t sho_calendar_time(int y, int m, int d) { return calendar::time(y, m, d); }
+
+// ---- deterministic elementary functions (sho_detmath.hpp), vectorised for the bit-exactness tests -------------
+void sho_dm_eval(int fn, int64_t n, const double* a, const double* b, double* out) {
+    for (int64_t i = 0; i < n; ++i) {
+        switch (fn) {
+            case 0: out[i] = dm::exp(a[i]); break;
+            case 1: out[i] = dm::log(a[i]); break;
+            case 2: out[i] = dm::pow(a[i], b[i]); break;
+            case 3: out[i] = dm::lgamma(a[i]); break;
+            case 4: out[i] = special::gamma_p(a[i], b[i]); break;
+            default: out[i] = nan_v;
+        }
+    }
+}
 
 // ---- special functions ----------------------------------------------------
 double sho_gamma_p(double a, double x) { return special::gamma_p(a, x); }

@@ -36,7 +36,7 @@ def geo_matrix(geo_records):
 
 def build(force=False):
     so = os.path.join(_HERE, "libsho_oracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("capi.cpp", "sho_core.hpp", "sho_pt_gs_k.hpp", "sho_hbv.hpp", "sho_region.hpp")]
+    srcs = [os.path.join(_HERE, f) for f in ("capi.cpp", "sho_detmath.hpp", "sho_core.hpp", "sho_pt_gs_k.hpp", "sho_hbv.hpp", "sho_region.hpp")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "libsho_oracle.so"], stdout=subprocess.DEVNULL)
     return so
@@ -72,6 +72,18 @@ def _check(rc):
 
 def hardware_concurrency():
     return int(lib().sho_hardware_concurrency())
+
+
+DM_FUNCTIONS = dict(exp=0, log=1, pow=2, lgamma=3, gamma_p=4)
+
+
+def dm_eval(fn, a, b=None):
+    """Deterministic elementary functions of oracle/sho_detmath.hpp (and gamma_p built on them), elementwise."""
+    a = _f64(a).ravel()
+    b = _f64(b).ravel() if b is not None else np.zeros_like(a)
+    out = np.zeros_like(a)
+    lib().sho_dm_eval(C.c_int(DM_FUNCTIONS[fn]), C.c_int64(a.size), _d(a), _d(b), _d(out))
+    return out
 
 
 # ---- calendar / special ---------------------------------------------------------------------

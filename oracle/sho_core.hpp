@@ -30,6 +30,8 @@
 #include <string>
 #include <vector>
 
+#include "sho_detmath.hpp"
+
 namespace sho {
 
 // ---------------------------------------------------------------------------
@@ -105,10 +107,10 @@ inline double m3s_to_mmh(double m3s, double area_m2) { return m3s / (mmh_to_m3s_
 // ---------------------------------------------------------------------------
 namespace special {
 
-inline double lgamma_(double a) { return std::lgamma(a); }  // boost::math::lgamma, gamma_snow.h:199-201 (full double here)
+inline double lgamma_(double a) { return dm::lgamma(a); }  // boost::math::lgamma, gamma_snow.h:199-201 (full double, deterministic: sho_detmath.hpp)
 
 // common prefix x^a e^-x / Gamma(a); the same expression order gamma_snow.h:245,254 uses
-inline double gamma_prefix(double a, double x) { return std::exp(a * std::log(x) - x - lgamma_(a)); }
+inline double gamma_prefix(double a, double x) { return dm::exp(a * dm::log(x) - x - lgamma_(a)); }
 
 // Regularised lower incomplete gamma P(a,x), a>0, x>=0.   Replaces boost::math::gamma_p
 // (gamma_snow.h:195-197).  Full-double evaluation: power series for x < a+1, modified-Lentz
@@ -222,7 +224,7 @@ struct calculator {
         const double ck1 = 0.610780, psycr = 0.066;
         int i = temperature < 0 ? 0 : 1;
         double ctt_inv = 1 / (ck3[i] + temperature);
-        double sat_pressure = ck1 * std::exp(ck2[i] * temperature * ctt_inv);
+        double sat_pressure = ck1 * dm::exp(ck2[i] * temperature * ctt_inv);
         double delta = sat_pressure * ck2[i] * ck3[i] * ctt_inv * ctt_inv;
         double vapour_pressure = sat_pressure * rhumidity;
         double epot = alpha * delta * net_radiation(temperature, global_radiation, rhumidity, vapour_pressure) / (delta + psycr);
@@ -233,8 +235,8 @@ struct calculator {
     double net_radiation(double temperature, double global_radiation, double rhumidity, double vapour_pressure) const {
         const double bolz = 0.0000000567;
         double k_temp = temperature + 273.15;
-        double e_atm = 1.24 * std::pow(10 * vapour_pressure / k_temp, 0.143) * (0.85 + 0.5 * rhumidity);
-        return bolz * std::pow(k_temp, 4) * (e_atm - 0.98) + global_radiation * (1.0 - land_albedo);
+        double e_atm = 1.24 * dm::pow(10 * vapour_pressure / k_temp, 0.143) * (0.85 + 0.5 * rhumidity);
+        return bolz * dm::pow4(k_temp) * (e_atm - 0.98) + global_radiation * (1.0 - land_albedo);
     }
 };
 }  // namespace priestley_taylor
@@ -244,7 +246,7 @@ struct calculator {
 // ---------------------------------------------------------------------------
 namespace actual_evapotranspiration {
 struct parameter { double ae_scale_factor = 1.5; };
-inline double calc_pot_ratio(double water_level, double scale_factor) { return 1.0 - std::exp(-water_level * 3.0 / scale_factor); }
+inline double calc_pot_ratio(double water_level, double scale_factor) { return 1.0 - dm::exp(-water_level * 3.0 / scale_factor); }
 inline double calculate_step(double water_level, double pot_evap, double scale_factor, double snow_fraction, utctimespan) {
     return pot_evap * calc_pot_ratio(water_level, scale_factor) * (1.0 - snow_fraction);
 }
@@ -289,17 +291,17 @@ struct calculator {
     explicit calculator(const parameter& p) : param(p) {}
     calculator(double abs_err, double rel_err, const parameter& p) : param(p), eps_abs(abs_err), eps_rel(rel_err) {}
 
-    double g(double ln_q) const { return std::exp(param.c1 + param.c2 * ln_q + param.c3 * ln_q * ln_q); }  // :186-188
+    double g(double ln_q) const { return dm::exp(param.c1 + param.c2 * ln_q + param.c3 * ln_q * ln_q); }  // :186-188
     double log_transform_f(double ln_q, double p, double e) const {                                        // :195-198
         const double gln_q = g(ln_q);
-        return gln_q >= 1.e-30 ? gln_q * ((p - e) * std::exp(-ln_q) - 1.0) : 0.0;
+        return gln_q >= 1.e-30 ? gln_q * ((p - e) * dm::exp(-ln_q) - 1.0) : 0.0;
     }
 
     // :213-235.  T0/T1 only enter through (T1-T0); times inside are hours.
     void step(utctime T0, utctime T1, double& q, double& q_avg, double p, double e, step_stats* st = nullptr) const {
         const double min_q = 0.00001;
         if (q < min_q) q = min_q;
-        double x = std::log(q);
+        double x = dm::log(q);
         const double t0 = 0.0;
         const double t1 = to_seconds(T1 - T0) / to_seconds(deltahours(1));
         // dense_stepper.initialize(x, t0, t1 - t0)
@@ -344,15 +346,15 @@ struct calculator {
                 const double x_err = dt * dc1 * dxdt + dt * dc3 * k3 + dt * dc4 * k4 + dt * dc5 * k5 + dt * dc6 * k6 + dt * dc7 * dxdt_new;
                 const double err = std::fabs(x_err) / (eps_abs + eps_rel * (1.0 * std::fabs(x) + (1.0 * dt) * std::fabs(dxdt)));
                 if (err > 1.0) {
-                    dt *= std::max(9.0 / 10.0 * std::pow(err, -1.0 / (4 - 1)), 1.0 / 5.0);
+                    dt *= std::max(9.0 / 10.0 * dm::pow(err, -1.0 / (4 - 1)), 1.0 / 5.0);
                     if (st) st->rejected++;
                     if (++fails >= 500) throw std::runtime_error("Max number of iterations exceeded (500). A new step size was not found.");
                     continue;
                 }
                 t += dt;
                 if (err < 0.5) {
-                    const double e2 = std::max(std::pow(5.0, -5.0), err);
-                    dt *= 9.0 / 10.0 * std::pow(e2, -1.0 / 5);
+                    const double e2 = std::max(0.00032, err);
+                    dt *= 9.0 / 10.0 * dm::pow(e2, -1.0 / 5);
                 }
                 if (st) st->accepted++;
                 break;
@@ -360,7 +362,7 @@ struct calculator {
             x_old = x; k1 = dxdt; k7 = dxdt_new;   // dense output keeps old state/deriv + stepper's k3..k6
             x = x_new; dxdt = dxdt_new;            // toggle_current_state (FSAL)
             if (t < t1) {                          // :228-229, trapezoidal_average::add (:46-50)
-                const double f = std::exp(x);
+                const double f = dm::exp(x);
                 area += 0.5 * (f_a + f) * (t - t_a);
                 f_a = f; t_a = t;
             }
@@ -391,7 +393,7 @@ struct calculator {
             x = 1.0 * x_old + dtl * b1_theta * k1 + dtl * b3_theta * k3 + dtl * b4_theta * k4 + dtl * b5_theta * k5 +
                 dtl * b6_theta * k6 + dtl * b7_theta * k7;
         }
-        q = std::exp(x);                                   // :232
+        q = dm::exp(x);                                   // :232
         area += 0.5 * (f_a + q) * (t1 - t_a);              // :233 average_computer.add(q, t1)
         t_a = t1;
         q_avg = area / (t_a - t_start);                    // :52
@@ -446,7 +448,7 @@ struct calculator {
     const double water_heat = 4180.0;
     const double ice_heat = 2050.0;
     const double sigma = 5.670373e-8;
-    const double BB0{0.98 * sigma * std::pow(273.15, 4)};
+    const double BB0{0.98 * sigma * dm::pow4(273.15)};
 
     double gamma_p(double a, double b) const { return special::gamma_p(a, b); }  // :195-197
     double lgamma(double a) const { return special::lgamma_(a); }                // :199-201
@@ -474,7 +476,7 @@ struct calculator {
         } else {
             const double x = lambda / scale;
             y = gamma_p(shape, x);
-            y1 = y - std::exp(shape * std::log(x) - x - lgamma(shape)) / shape;
+            y1 = y - dm::exp(shape * dm::log(x) - x - lgamma(shape)) / shape;
             swe = m * (1.0 - y1) - lambda * (1 - y);
             sca = (1.0 - y) * (1.0 - y0);
         }
@@ -483,7 +485,7 @@ struct calculator {
             const double sat = lwd / max_water_frac;
             const double x = sat / scale;
             const double ssa = gamma_p(shape, x);
-            const double ssa1 = ssa - std::exp(shape * std::log(x) - x - lgamma(shape)) / shape;
+            const double ssa1 = ssa - dm::exp(shape * dm::log(x) - x - lgamma(shape)) / shape;
             const double liqwat = max_water_frac * (m * (ssa1 - y1) + sat * (1.0 - ssa) - lambda * (1.0 - y));
             swe += liqwat;
         }
@@ -537,11 +539,11 @@ struct calculator {
         const double albedo_range = max_albedo - min_albedo;
         const double dt_in_days = to_seconds(dt) / to_seconds(DAY);
         const double slow_albedo_decay_rate = 0.5 * albedo_range * dt_in_days / p.slow_albedo_decay_rate;
-        const double fast_albedo_decay_rate = std::pow(2.0, -dt_in_days / p.fast_albedo_decay_rate);
+        const double fast_albedo_decay_rate = dm::pow(2.0, -dt_in_days / p.fast_albedo_decay_rate);
 
         const double T_k = T + 273.15;
         const double turb = p.wind_scale * wind_speed + p.wind_const;
-        double vapour_pressure = 33.864 * (std::pow(7.38e-3 * T + 0.8072, 8) - 1.9e-5 * std::fabs(1.8 * T + 48.0) + 1.316e-3) * rel_hum;
+        double vapour_pressure = 33.864 * (dm::pow8(7.38e-3 * T + 0.8072) - 1.9e-5 * std::fabs(1.8 * T + 48.0) + 1.316e-3) * rel_hum;
         if (T < 0.0) vapour_pressure *= 1.0 + 9.72e-3 * T + 4.2e-5 * T * T;
 
         if (snow > tol) albedo += snow * albedo_range / p.snowfall_reset_depth;
@@ -552,7 +554,7 @@ struct calculator {
         albedo = std::max(std::min(albedo, max_albedo), min_albedo);
 
         double effect = rad * (1.0 - albedo);
-        effect += 0.98 * sigma * std::pow(vapour_pressure / T_k, 6.87e-2) * std::pow(T_k, 4);
+        effect += 0.98 * sigma * dm::pow(vapour_pressure / T_k, 6.87e-2) * dm::pow4(T_k);
 
         if (T > 0.0 && snow < tol) effect += rain * T * water_heat / to_seconds(dt);
         if (T <= 0.0 && rain < tol) effect += snow * T * ice_heat / to_seconds(dt);
@@ -565,8 +567,8 @@ struct calculator {
         double sst = std::min(0.0, 1.16 * T - 2.09);
         if (sst > -tol) effect += turb * (T + 1.7 * (vapour_pressure - 6.12)) - BB0;
         else
-            effect += turb * (T - sst + 1.7 * (vapour_pressure - 6.132 * std::exp(0.103 * T - 0.186))) -
-                      0.98 * sigma * std::pow(sst + 273.15, 4);
+            effect += turb * (T - sst + 1.7 * (vapour_pressure - 6.132 * dm::exp(0.103 * T - 0.186))) -
+                      0.98 * sigma * dm::pow4(sst + 273.15);
 
         double delta_sh = -surface_heat;
         surface_heat = p.surface_magnitude * ice_heat * sst * 0.5;

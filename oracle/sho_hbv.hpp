@@ -202,7 +202,7 @@ struct calculator {
     explicit calculator(const parameter& p) : param(p) {}
     void step(state& s, response& r, utctime, utctime, double insoil, double act_evap) const {
         double temp = s.sm + insoil;
-        double outflow = insoil * std::pow(temp / param.fc, param.beta);
+        double outflow = insoil * dm::pow(temp / param.fc, param.beta);
         r.outflow = outflow > temp ? temp : outflow;
         s.sm = std::max(0.0, s.sm + insoil - r.outflow - act_evap);
     }

@@ -20,7 +20,7 @@ struct geo_point { double x = 0, y = 0, z = 0; };
 
 // core/geo_point.h:41-43
 inline double distance_measure(const geo_point& a, const geo_point& b, double p, double zscale) {
-    return std::pow((a.x - b.x) * (a.x - b.x) + (a.y - b.y) * (a.y - b.y) + (a.z - b.z) * (a.z - b.z) * zscale * zscale, p / 2.0);
+    return dm::pow((a.x - b.x) * (a.x - b.x) + (a.y - b.y) * (a.y - b.y) + (a.z - b.z) * (a.z - b.z) * zscale * zscale, p / 2.0);
 }
 // core/geo_point.h:49-51
 inline double zscaled_distance(const geo_point& a, const geo_point& b, double zscale) {
@@ -156,7 +156,7 @@ inline void run_interpolation(model_kind kind, const std::vector<geo_point>& src
                     double tv;
                     switch (kind) {
                         case TEMPERATURE: tv = sv + scale * (dst[j].z - src[sw.source].z); break;                       // :367-369
-                        case PRECIPITATION: tv = sv * std::pow(scale, (dst[j].z - src[sw.source].z) / 100.0); break;   // :422-426
+                        case PRECIPITATION: tv = sv * dm::pow(scale, (dst[j].z - src[sw.source].z) / 100.0); break;   // :422-426
                         case RADIATION: tv = sv * dst_slope_factor[j]; break;                                          // :392-394
                         default: tv = sv;
                     }
@@ -266,13 +266,13 @@ inline void build_covariance_matrices(const std::vector<geo_point>& src, const s
         K(i, i) = 1.0 * (p.sill_value - p.nug_value);  // K.eye; K.diag() *= zero_dist_cov
         for (size_t j = i + 1; j < n; ++j) {
             const double d = zscaled_distance(src[i], src[j], p.zscale_value);
-            K(i, j) = K(j, i) = (p.sill_value - p.nug_value) * std::exp(-d / p.range_value);
+            K(i, j) = K(j, i) = (p.sill_value - p.nug_value) * dm::exp(-d / p.range_value);
         }
     }
     k = la::mat(n, m);
     for (size_t i = 0; i < n; ++i)
         for (size_t j = 0; j < m; ++j)
-            k(i, j) = (p.sill_value - p.nug_value) * std::exp(-zscaled_distance(src[i], dst[j], p.zscale_value) / p.range_value);
+            k(i, j) = (p.sill_value - p.nug_value) * dm::exp(-zscaled_distance(src[i], dst[j], p.zscale_value) / p.range_value);
 }
 
 struct operators { la::mat F, E_beta_w, omega, GH_inv, BM; };
@@ -353,7 +353,7 @@ namespace routing {
 inline double gamma_pdf(double alpha, double x) {  // pdf of Gamma(shape alpha, scale 1)
     if (x < 0) return 0.0;
     if (x == 0) return 0.0;  // boost 1.68 gamma.hpp pdf(): "if(x == 0) return 0;" for every shape
-    return std::exp((alpha - 1.0) * std::log(x) - x - std::lgamma(alpha));
+    return dm::exp((alpha - 1.0) * dm::log(x) - x - dm::lgamma(alpha));
 }
 inline double gamma_quantile(double alpha, double pq) {  // inverse of P(alpha, x) by bracketed Newton on full-double P
     double lo = 0.0, hi = std::max(1.0, alpha);
@@ -449,8 +449,8 @@ inline double kling_gupta(const double* o, const double* m, size_t n, double s_r
     double a = qs / qo, b = us / uo;
     if (!std::isfinite(a)) a = 1.0;
     if (!std::isfinite(b)) b = 1.0;
-    double eds2 = (s_r != 0.0 ? std::pow(s_r * (r - 1), 2) : 0.0) + (s_a != 0.0 ? std::pow(s_a * (a - 1), 2) : 0.0) +
-                  (s_b != 0.0 ? std::pow(s_b * (b - 1), 2) : 0.0);
+    double eds2 = (s_r != 0.0 ? dm::pow(s_r * (r - 1), 2) : 0.0) + (s_a != 0.0 ? dm::pow(s_a * (a - 1), 2) : 0.0) +
+                  (s_b != 0.0 ? dm::pow(s_b * (b - 1), 2) : 0.0);
     return std::sqrt(eds2);
 }
 inline double abs_diff_sum(const double* o, const double* m, size_t n) {  // :2421-2431

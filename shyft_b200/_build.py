@@ -15,7 +15,7 @@ LIB = os.path.join(HERE, "libshyft_b200.so")
 # -fmad=false: the cell stacks follow the reference's operation order; contracting a*b+c into FMA changes the last bit
 # of intermediate results, which can flip the discrete decisions the reference's results are defined by (Kirchner
 # accept/reject, Brent branches, gamma_snow thresholds).  See DESIGN.md "FMA policy".
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false", "-Xcompiler", "-fPIC",
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false", "-Xcompiler", "-fPIC,-ffp-contract=off",
               "-cudart", "static"]
 
 

@@ -60,7 +60,7 @@ sb2_has_catchment_parameter sb2_set_catchment_calculation_filter sb2_set_states 
 sb2_get_initial_state sb2_revert_to_initial_state sb2_adjust_q sb2_set_collector_mode sb2_initialize_cell_environment
 sb2_set_cell_forcing sb2_get_cell_forcing sb2_set_sources sb2_interpolate sb2_is_cell_env_ts_ok sb2_run_cells sb2_run_windowed
 sb2_get_response sb2_get_state_series sb2_catchment_discharges sb2_catchment_charges sb2_set_river_network sb2_river_flows
-sb2_set_stream sb2_device_catchment_discharges sb2_device_catchment_charges sb2_kernel_launches sb2_last_run_kernel_ms""".split()
+sb2_unit_eval sb2_set_stream sb2_device_catchment_discharges sb2_device_catchment_charges sb2_kernel_launches sb2_last_run_kernel_ms""".split()
 
 _LIB = None
 
@@ -99,3 +99,18 @@ def dptr(a):
 
 def f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
+
+
+UNIT_FUNCTIONS = dict(exp=(0, 1, 1), log=(1, 1, 1), pow=(2, 2, 1), lgamma=(3, 1, 1), gamma_p=(4, 2, 1), corr_lwc=(5, 5, 1), calc_snow_state=(6, 7, 2),
+                      kirchner_step=(7, 7, 3))
+
+
+def unit_eval(fn, inputs, device=0):
+    """Evaluate one device function row-wise: inputs [n][n_in] -> [n][n_out] (sb2_unit_eval)."""
+    code, n_in, n_out = UNIT_FUNCTIONS[fn]
+    a = f64(inputs).reshape(-1, n_in)
+    out = np.zeros((a.shape[0], n_out))
+    rc = lib().sb2_unit_eval(C.c_int(device), C.c_int(code), C.c_int64(a.shape[0]), dptr(a), C.c_int(n_in), dptr(out), C.c_int(n_out))
+    if rc != 0:
+        raise RuntimeError(lib().sb2_last_error(None).decode())
+    return out

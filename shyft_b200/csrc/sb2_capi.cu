@@ -19,6 +19,7 @@
 #include "sb2_ptgsk.cuh"
 #include "sb2_hbv.cuh"
 #include "sb2_routing.cuh"
+#include "sb2_unit.cuh"
 
 using namespace sb2;
 
@@ -196,7 +197,7 @@ PtgskParam make_ptgsk_param(const double* v, int64_t dt_us) {
     const double dt_in_days = (double(dt_us) / 1e6) / 86400.0;
     const double albedo_range = p.max_albedo - p.min_albedo;
     p.slow_albedo_decay_step = 0.5 * albedo_range * dt_in_days / p.slow_albedo_decay_rate;
-    p.fast_albedo_decay_step = std::pow(2.0, -dt_in_days / p.fast_albedo_decay_rate);
+    p.fast_albedo_decay_step = sb_pow(2.0, -dt_in_days / p.fast_albedo_decay_rate);
     return p;
 }
 std::vector<double> default_parameter(int stack) {
@@ -283,7 +284,7 @@ bool wants_response(const sb2_model* m, int r) {
 int n_state_series(const sb2_model* m) { return m->stack == SB2_PT_GS_K ? 9 : (m->stack == SB2_PT_HS_K ? 3 : 5); }
 
 void ensure_series(sb2_model* m, int64_t first, int64_t rows) {
-    if (m->out_first != first || m->out_rows != rows) free_series(m);
+    if (m->out_rows != rows) free_series(m);  // a window buffer of the same size is reused as is
     for (int r = 0; r < SB2_N_RESPONSE; ++r) {
         if (wants_response(m, r)) m->d_resp[r].ensure(size_t(rows) * m->n);
         else m->d_resp[r].release();
@@ -328,7 +329,7 @@ void launch_step_range(sb2_model* m, int64_t first, int64_t n_steps, bool collec
             for (int v = 0; v < 5; ++v) a.f[v] = m->d_forcing[v].p + (s0 - m->forcing_first) * n;
             a.n_steps = chunk; a.first_step = s0;
             a.dt_seconds = dt_seconds; a.dt_hours = dt_seconds / 3600.0; a.dt_us = double(m->dt);
-            a.bb0 = 0.98 * 5.670373e-8 * std::pow(273.15, 4);
+            a.bb0 = 0.98 * 5.670373e-8 * sb_pow4(273.15);
             a.day_of_year = m->d_doy.p; a.sec_of_year = m->d_soy.p;
             for (int r = 0; r < 8; ++r) a.resp[r] = m->d_resp[r].p;
             for (int s = 0; s < 9; ++s) a.st[s] = m->d_st[s].p;
@@ -437,7 +438,7 @@ void build_idw_plan(sb2_model* m, int var) {
     pl.idx.resize(k * m->n); pl.w.resize(k * m->n); pl.f.resize(k * m->n); pl.cnt.resize(m->n);
     // min_weight = 1/distance_measure(origin, (max_distance,0,0)) (inverse_distance.h:160-162)
     const double d2 = pl.p.max_distance * pl.p.max_distance;
-    const double min_weight = 1.0 / std::pow(d2, pl.p.distance_measure_factor / 2.0);
+    const double min_weight = 1.0 / sb_pow(d2, pl.p.distance_measure_factor / 2.0);
     idw_build_neighbours_kernel<<<grid_for(m->n, 128), 128, 0, m->stream>>>(idw_kind_of(var), m->n, m->d_x.p, m->d_y.p, m->d_z.p, m->d_slope.p,
                                                                            int(s.n_src), s.d_xyz.p, pl.p, min_weight, pl.idx.p, pl.w.p, pl.f.p,
                                                                            pl.cnt.p);
@@ -1046,9 +1047,7 @@ int sb2_run_windowed(sb2_model* m, const sb2_interpolation_parameter* ip, int st
             time_begin(m, 0);
             interpolate_range(m, w0, wn, 0);
             CUDA_OK(cudaEventRecord(m->ev[1], m->stream));
-            if (m->out_rows != W) { free_series(m); }
             ensure_series(m, w0, W);
-            m->out_first = w0;
             CUDA_OK(cudaEventRecord(m->ev[2], m->stream));
             launch_step_range(m, w0, wn, true);
             CUDA_OK(cudaEventRecord(m->ev[3], m->stream));
@@ -1144,6 +1143,27 @@ int sb2_river_flows(sb2_model* m, int64_t rid, int64_t start_step, int64_t n_ste
         route_rivers(m->rivers, rid, cell_routing, m->n, m->T, m->dt, m->d_resp[SB2_R_AVG_DISCHARGE].p, m->stream, &m->launches, start_step,
                      n_steps, local_inflow, upstream_inflow, output);
     });
+}
+
+// ---- diagnostics ---------------------------------------------------------------------------------------------------------------
+int sb2_unit_eval(int device, int fn, int64_t n, const double* in, int n_in, double* out, int n_out) {
+    try {
+        static const int need_in[UNIT_N] = {1, 1, 2, 1, 2, 5, 7, 7}, need_out[UNIT_N] = {1, 1, 1, 1, 1, 1, 2, 3};
+        if (fn < 0 || fn >= UNIT_N) throw Error("unknown unit function");
+        if (n_in < need_in[fn] || n_out < need_out[fn]) throw Error("unit function: too few input or output columns");
+        CUDA_OK(cudaSetDevice(device));
+        DevArray<double> d_in, d_out;
+        d_in.upload(in, size_t(n) * n_in, 0);
+        d_out.resize(size_t(n) * n_out);
+        CUDA_OK(cudaMemsetAsync(d_out.p, 0, size_t(n) * n_out * sizeof(double), 0));
+        unit_eval_kernel<<<grid_for(n, 128), 128>>>(fn, n, d_in.p, n_in, d_out.p, n_out);
+        CUDA_OK(cudaGetLastError());
+        CUDA_OK(cudaMemcpy(out, d_out.p, size_t(n) * n_out * sizeof(double), cudaMemcpyDeviceToHost));
+        return 0;
+    } catch (const std::exception& e) {
+        g_create_error = e.what();
+        return 1;
+    }
 }
 
 // ---- device-side hooks -----------------------------------------------------------------------------------------------------

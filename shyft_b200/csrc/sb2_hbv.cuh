@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(128) hbv_run_kernel(const HbvRunArgs a) {
                 ae = (1.0 - snow_fraction) * (x0 < p.lp ? pot * (x0 / p.lp) : pot);  // hbv_actual_evapotranspiration.h:32-38
                 {  // hbv_soil::step, hbv_soil.h:59-64
                     const double t = x0 + snow_outflow;
-                    const double of = snow_outflow * pow(t / p.fc, p.beta);
+                    const double of = snow_outflow * sb_pow(t / p.fc, p.beta);
                     soil_outflow = of > t ? t : of;
                     x0 = dmax(0.0, x0 + snow_outflow - soil_outflow - ae);
                 }
@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(128) hbv_run_kernel(const HbvRunArgs a) {
                 }
                 total_discharge = dmax(0.0, prec - ae) * direct_response_fraction + gm_direct * gm_mmh + tank_outflow * land_fraction;
             } else {
-                ae = pot * (1.0 - exp(-x0 * 3.0 / p.ae_scale_factor)) * (1.0 - dmax(sca, glacier_fraction));
+                ae = pot * (1.0 - sb_exp(-x0 * 3.0 / p.ae_scale_factor)) * (1.0 - dmax(sca, glacier_fraction));
                 double q_avg;
                 if (!kirchner_step(p.c1, p.c2, p.c3, a.dt_hours, x0, q_avg,
                                    snow_outflow * snow_storage_fraction + prec * kirchner_routed_prec + gm_routed * gm_mmh, ae)) {

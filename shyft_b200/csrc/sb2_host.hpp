@@ -13,6 +13,8 @@
 #include <string>
 #include <vector>
 
+#include "sb2_math.cuh"
+
 namespace sb2 {
 namespace host {
 
@@ -133,7 +135,7 @@ inline BtkStationOps btk_station_ops(const std::vector<double>& sxyz, const std:
         for (size_t j = i + 1; j < n; ++j) {
             const double* b = &sxyz[3 * valid[j]];
             const double d = std::sqrt((a[0] - b[0]) * (a[0] - b[0]) + (a[1] - b[1]) * (a[1] - b[1]) + (a[2] - b[2]) * (a[2] - b[2]) * zscale * zscale);
-            K(i, j) = K(j, i) = c0 * std::exp(-d / range);
+            K(i, j) = K(j, i) = c0 * sb_exp(-d / range);
         }
     }
     BtkStationOps o;
@@ -166,7 +168,7 @@ inline double btk_prior_gradient(int64_t p_start_us, int64_t dt_us) {
 inline double gamma_p_full(double a, double x) {  // regularised lower incomplete gamma, full double
     if (!(x > 0.0)) return 0.0;
     if (std::isinf(x)) return 1.0;
-    const double pre = std::exp(a * std::log(x) - x - std::lgamma(a));
+    const double pre = sb_exp(a * sb_log(x) - x - sb_lgamma(a));
     if (x < a + 1.0) {
         double ap = a, del = 1.0 / a, sum = del;
         for (int n = 0; n < 2000; ++n) { ap += 1.0; del *= x / ap; sum += del; if (del < sum * 1.0e-16) break; }
@@ -189,7 +191,7 @@ inline double gamma_p_full(double a, double x) {  // regularised lower incomplet
 inline double gamma_pdf(double alpha, double x) {
     if (x < 0) return 0.0;
     if (x == 0) return 0.0;  // boost 1.68 gamma_distribution pdf returns 0 at x == 0 for every shape
-    return std::exp((alpha - 1.0) * std::log(x) - x - std::lgamma(alpha));
+    return sb_exp((alpha - 1.0) * sb_log(x) - x - sb_lgamma(alpha));
 }
 inline double gamma_quantile(double alpha, double pq) {  // bracketed Newton on P(alpha, x)
     double lo = 0.0, hi = std::max(1.0, alpha);

@@ -28,7 +28,7 @@ __device__ __forceinline__ double distance_measure(double ax, double ay, double 
     const double dx = __dsub_rn(ax, bx), dy = __dsub_rn(ay, by), dz = __dsub_rn(az, bz);
     const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(__dmul_rn(__dmul_rn(dz, dz), zscale), zscale));
     const double e = p / 2.0;
-    return e == 1.0 ? d2 : pow(d2, e);  // pow(x, 1.0) == x exactly
+    return sb_pow(d2, e);  // exact for e == 1 (the default distance_measure_factor 2)
 }
 
 // Step 1 (:160-203): per destination cell the sources with weight >= min_weight; if more than max_members, the
@@ -77,7 +77,7 @@ __global__ void idw_build_neighbours_kernel(int kind, int64_t n_cells, const dou
     for (int j = 0; j < cnt; ++j) {
         const int k = nb_idx[(int64_t)j * n_cells + c];
         double f = 1.0;
-        if (kind == IDW_PRECIPITATION) f = pow(p.scale_factor, (z - sxyz[3 * k + 2]) / 100.0);  // :422-426
+        if (kind == IDW_PRECIPITATION) f = sb_pow(p.scale_factor, (z - sxyz[3 * k + 2]) / 100.0);  // :422-426
         else if (kind == IDW_RADIATION) f = cslope[c];                                            // :392-394
         nb_f[(int64_t)j * n_cells + c] = f;
     }
@@ -198,7 +198,7 @@ __global__ void btk_build_operators_kernel(int64_t n_cells, const double* __rest
     for (int s = 0; s < n_src; ++s) {
         const double dx = sxyz[3 * s] - x, dy = sxyz[3 * s + 1] - y, dz = sxyz[3 * s + 2] - z;
         const double d = sqrt(dx * dx + dy * dy + dz * dz * zscale * zscale);
-        kbuf[(int64_t)s * n_cells + c] = sill_m_nug * exp(-d / range);
+        kbuf[(int64_t)s * n_cells + c] = sill_m_nug * sb_exp(-d / range);
     }
     double g0 = 0.0, g1 = 0.0;  // (F.t()*K_inv*k)[:, c]
     for (int j = 0; j < n_src; ++j) {

@@ -1,21 +1,133 @@
-// sb2_math.cuh -- fp64 device math used by the cell-stack kernels (sm_100a).
+// sb2_math.cuh -- fp64 math used by the cell-stack kernels (sm_100a) and by the host-side operator builds.
 //
-// The reference evaluates these through boost 1.68 (absent from its tree):
+// Deterministic elementary functions: exp, log, pow, lgamma written with IEEE-754 +,-,*,/ and sqrt only (no FMA
+// contraction: the library is built with -fmad=false; no CUDA libm), so that the device, the host part of this library
+// and any other conforming machine produce identical bits.  Why: gamma_snow's Brent search (core/gamma_snow.h:214-227)
+// amplifies last-bit differences between math libraries to 1e-4-level differences in liquid water content; a 1e-9 parity
+// statement is only meaningful over one fixed operation sequence (DESIGN.md "Deterministic math").  The sequence:
+//   exp(x)    k = floor(x/ln2 + 0.5), r = (x - k*ln2_hi) - k*ln2_lo, degree-13 Taylor polynomial (Horner), scaled by 2^k
+//   log(x)    x = 2^e*m, m in (sqrt(1/2), sqrt(2)], f = m-1, s = f/(2+f), f - f^2/2 + s*(f^2/2 + R(s^2)), R = atanh series to s^20
+//   pow(x,y)  exact for y = 0, 1, 2, 0.5; exp(y*log(x)) otherwise (x >= 0)
+//   lgamma(a) recurrence up to a >= 12, then the Stirling series to 1/a^13
+// The reference evaluates through libm and boost 1.68 (absent from its tree):
 //   gamma_p / lgamma      core/gamma_snow.h:195-201   (boost::math, reduced-precision policies)
 //   brent_find_minima     core/gamma_snow.h:216-226   (bits = 12, 60 iterations)
-// The kernels use full-double evaluations with a fixed operation order; tests/ checks them against
-// the CPU oracle, which states the same algorithms independently.
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#define SB2_HD __host__ __device__ __forceinline__
 
 namespace sb2 {
 
-__device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }  // std::max(a,b): (a < b) ? b : a
-__device__ __forceinline__ double dmin(double a, double b) { return b < a ? b : a; }  // std::min(a,b): (b < a) ? b : a
+SB2_HD double from_bits(unsigned long long u) {
+#ifdef __CUDA_ARCH__
+    return __longlong_as_double((long long)u);
+#else
+    double x; memcpy(&x, &u, 8); return x;
+#endif
+}
+SB2_HD unsigned long long bits_of(double x) {
+#ifdef __CUDA_ARCH__
+    return (unsigned long long)__double_as_longlong(x);
+#else
+    unsigned long long u; memcpy(&u, &x, 8); return u;
+#endif
+}
+SB2_HD double pow2i(int k) { return from_bits((unsigned long long)(k + 1023) << 52); }  // 2^k, -1022 <= k <= 1023
+SB2_HD double inf_() { return from_bits(0x7ff0000000000000ULL); }
+SB2_HD double nan_() { return from_bits(0x7ff8000000000000ULL); }
+
+SB2_HD double sb_exp(double x) {
+    if (x != x) return x;
+    if (x > 709.782712893384) return inf_();
+    if (x < -745.1332191019412) return 0.0;
+    const double kf = floor(x * 1.44269504088896338700e+00 + 0.5);
+    const double hi = x - kf * 6.93147180369123816490e-01;
+    const double lo = kf * 1.90821492927058770002e-10;
+    const double r = hi - lo;
+    double q = 1.0 / 6227020800.0;
+    q = q * r + 1.0 / 479001600.0;
+    q = q * r + 1.0 / 39916800.0;
+    q = q * r + 1.0 / 3628800.0;
+    q = q * r + 1.0 / 362880.0;
+    q = q * r + 1.0 / 40320.0;
+    q = q * r + 1.0 / 5040.0;
+    q = q * r + 1.0 / 720.0;
+    q = q * r + 1.0 / 120.0;
+    q = q * r + 1.0 / 24.0;
+    q = q * r + 1.0 / 6.0;
+    q = q * r + 0.5;
+    double p = 1.0 + (r + (r * r) * q);
+    int k = int(kf);
+    if (k > 1023) { p *= pow2i(1023); k -= 1023; }
+    if (k < -1022) { p *= pow2i(k + 1000); return p * pow2i(-1000); }
+    return p * pow2i(k);
+}
+
+SB2_HD double sb_log(double x) {
+    if (x != x || x < 0.0) return nan_();
+    if (x == 0.0) return -inf_();
+    if (x == inf_()) return x;
+    int e = 0;
+    if (x < 2.2250738585072014e-308) { x *= 18014398509481984.0; e = -54; }
+    const unsigned long long u = bits_of(x);
+    e += int((u >> 52) & 0x7ff) - 1023;
+    double m = from_bits((u & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL);
+    if (m > 1.4142135623730951) { m *= 0.5; e += 1; }
+    const double f = m - 1.0;
+    const double s = f / (2.0 + f);
+    const double z = s * s;
+    double R = 2.0 / 21.0;
+    R = R * z + 2.0 / 19.0;
+    R = R * z + 2.0 / 17.0;
+    R = R * z + 2.0 / 15.0;
+    R = R * z + 2.0 / 13.0;
+    R = R * z + 2.0 / 11.0;
+    R = R * z + 2.0 / 9.0;
+    R = R * z + 2.0 / 7.0;
+    R = R * z + 2.0 / 5.0;
+    R = R * z + 2.0 / 3.0;
+    R = R * z;
+    const double hfsq = 0.5 * f * f;
+    const double dk = double(e);
+    return dk * 6.93147180369123816490e-01 - ((hfsq - (s * (hfsq + R) + dk * 1.90821492927058770002e-10)) - f);
+}
+
+SB2_HD double sb_pow(double x, double y) {
+    if (y == 0.0) return 1.0;
+    if (y == 1.0) return x;
+    if (y == 2.0) return x * x;
+    if (y == 0.5) return sqrt(x);
+    if (x == 0.0) return y > 0.0 ? 0.0 : inf_();
+    return sb_exp(y * sb_log(x));
+}
+SB2_HD double sb_pow4(double x) { const double x2 = x * x; return x2 * x2; }
+SB2_HD double sb_pow8(double x) { double y = x * x; y = y * y; return y * y; }
+
+SB2_HD double sb_lgamma(double a) {
+    double prod = 1.0;
+    while (a < 12.0) { prod *= a; a += 1.0; }
+    const double ai = 1.0 / a, ai2 = ai * ai;
+    double s = 1.0 / 156.0;
+    s = 691.0 / 360360.0 - ai2 * s;
+    s = 1.0 / 1188.0 - ai2 * s;
+    s = 1.0 / 1680.0 - ai2 * s;
+    s = 1.0 / 1260.0 - ai2 * s;
+    s = 1.0 / 360.0 - ai2 * s;
+    s = 1.0 / 12.0 - ai2 * s;
+    s = ai * s;
+    return (((a - 0.5) * sb_log(a) - a) + 0.91893853320467274178) + s - sb_log(prod);
+}
+
+
+SB2_HD double dmax(double a, double b) { return (a < b) ? b : a; }  // std::max(a,b): (a < b) ? b : a
+SB2_HD double dmin(double a, double b) { return b < a ? b : a; }  // std::min(a,b): (b < a) ? b : a
 
 // x^a e^-x / Gamma(a), the prefix shared by P(a,x) and its a-derivative term (gamma_snow.h:245,254)
-__device__ __forceinline__ double gamma_prefix(double a, double x, double lgamma_a) { return exp(a * log(x) - x - lgamma_a); }
+__device__ __forceinline__ double gamma_prefix(double a, double x, double lgamma_a) { return sb_exp(a * sb_log(x) - x - lgamma_a); }
 
 // Regularised lower incomplete gamma P(a,x) given the prefix: series for x < a+1, Lentz continued fraction otherwise.
 __device__ __noinline__ double gamma_p_with_prefix(double a, double x, double pre) {
@@ -49,9 +161,9 @@ __device__ __noinline__ double gamma_p_with_prefix(double a, double x, double pr
 
 __device__ __forceinline__ double gamma_p(double a, double x, double lgamma_a) {
     if (!(x > 0.0)) return 0.0;
-    if (isinf(x)) return 1.0;
+    if (x == inf_()) return 1.0;
     return gamma_p_with_prefix(a, x, gamma_prefix(a, x, lgamma_a));
 }
-__device__ __forceinline__ double gamma_p(double a, double x) { return gamma_p(a, x, lgamma(a)); }
+__device__ __forceinline__ double gamma_p(double a, double x) { return gamma_p(a, x, sb_lgamma(a)); }
 
 }  // namespace sb2

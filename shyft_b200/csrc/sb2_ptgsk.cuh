@@ -93,8 +93,8 @@ __device__ __forceinline__ double gs_calc_q(double a, double b, double z, double
 
 // corr_lwc = boost brent_find_minima(f, 0, z1, bits=12, 60 iterations), gamma_snow.h:214-227
 __device__ __noinline__ double gs_corr_lwc(double z1, double a1, double b1, double a2, double b2) {
-    const double Q1 = gs_calc_q(a1, b1, z1, lgamma(a1), lgamma(a1 + 1.0));
-    const double lg_a2 = lgamma(a2), lg_a21 = lgamma(a2 + 1.0);
+    const double Q1 = gs_calc_q(a1, b1, z1, sb_lgamma(a1), sb_lgamma(a1 + 1.0));
+    const double lg_a2 = sb_lgamma(a2), lg_a21 = sb_lgamma(a2 + 1.0);
     auto f = [&](double z) { const double d = gs_calc_q(a2, b2, z, lg_a2, lg_a21) - Q1; return d * d; };
     const double tolerance = 0.00048828125;  // ldexp(1.0, 1 - 12)
     const double golden = (double)0.3819660f;
@@ -163,7 +163,7 @@ __device__ __noinline__ void gs_calc_snow_state(double shape, double scale, doub
         return;
     } else {
         const double x = lambda / scale;
-        lg = lgamma(shape);
+        lg = sb_lgamma(shape);
         have_lg = true;
         const double pre = gamma_prefix(shape, x, lg);
         y = (x > 0.0) ? gamma_p_with_prefix(shape, x, pre) : 0.0;
@@ -175,9 +175,9 @@ __device__ __noinline__ void gs_calc_snow_state(double shape, double scale, doub
     else if (lwd > 0.0) {
         const double sat = lwd / max_water_frac;
         const double x = sat / scale;
-        if (!have_lg) lg = lgamma(shape);
+        if (!have_lg) lg = sb_lgamma(shape);
         const double pre = gamma_prefix(shape, x, lg);
-        const double ssa = isinf(x) ? 1.0 : gamma_p_with_prefix(shape, x, pre);
+        const double ssa = (x == inf_()) ? 1.0 : gamma_p_with_prefix(shape, x, pre);
         const double ssa1 = ssa - pre / shape;
         const double liqwat = max_water_frac * (m * (ssa1 - y1) + sat * (1.0 - ssa) - lambda * (1.0 - y));
         swe += liqwat;
@@ -236,9 +236,7 @@ __device__ __forceinline__ void gs_step(GsState& s, double& r_sca, double& r_sto
 
     const double T_k = T + 273.15;
     const double turb = p.wind_scale * wind_speed + p.wind_const;
-    double b8 = 7.38e-3 * T + 0.8072;
-    b8 *= b8; b8 *= b8; b8 *= b8;  // pow(x, 8)
-    double vapour_pressure = 33.864 * (b8 - 1.9e-5 * fabs(1.8 * T + 48.0) + 1.316e-3) * rel_hum;
+    double vapour_pressure = 33.864 * (sb_pow8(7.38e-3 * T + 0.8072) - 1.9e-5 * fabs(1.8 * T + 48.0) + 1.316e-3) * rel_hum;
     if (T < 0.0) vapour_pressure *= 1.0 + 9.72e-3 * T + 4.2e-5 * T * T;
 
     if (snow > tol) albedo += snow * albedo_range / p.snowfall_reset_depth;
@@ -249,8 +247,7 @@ __device__ __forceinline__ void gs_step(GsState& s, double& r_sca, double& r_sto
     albedo = dmax(dmin(albedo, max_albedo), min_albedo);
 
     double effect = rad * (1.0 - albedo);
-    const double T_k2 = T_k * T_k;
-    effect += 0.98 * sigma * pow(vapour_pressure / T_k, 6.87e-2) * (T_k2 * T_k2);
+    effect += 0.98 * sigma * sb_pow(vapour_pressure / T_k, 6.87e-2) * sb_pow4(T_k);
 
     if (T > 0.0 && snow < tol) effect += rain * T * water_heat / dt_seconds;
     if (T <= 0.0 && rain < tol) effect += snow * T * ice_heat / dt_seconds;
@@ -263,8 +260,7 @@ __device__ __forceinline__ void gs_step(GsState& s, double& r_sca, double& r_sto
     const double sst = dmin(0.0, 1.16 * T - 2.09);
     if (sst > -tol) effect += turb * (T + 1.7 * (vapour_pressure - 6.12)) - BB0;
     else {
-        const double sk = sst + 273.15, sk2 = sk * sk;
-        effect += turb * (T - sst + 1.7 * (vapour_pressure - 6.132 * exp(0.103 * T - 0.186))) - 0.98 * sigma * (sk2 * sk2);
+        effect += turb * (T - sst + 1.7 * (vapour_pressure - 6.132 * sb_exp(0.103 * T - 0.186))) - 0.98 * sigma * sb_pow4(sst + 273.15);
     }
 
     double delta_sh = -surface_heat;
@@ -360,13 +356,12 @@ __device__ __forceinline__ double pt_potential_evapotranspiration(double land_al
     const double ck2 = neg ? 17.84362 : 17.08085;
     const double ck3 = neg ? 245.425 : 234.175;
     const double ctt_inv = 1 / (ck3 + temperature);
-    const double sat_pressure = ck1 * exp(ck2 * temperature * ctt_inv);
+    const double sat_pressure = ck1 * sb_exp(ck2 * temperature * ctt_inv);
     const double delta = sat_pressure * ck2 * ck3 * ctt_inv * ctt_inv;
     const double vapour_pressure = sat_pressure * rhumidity;
     const double k_temp = temperature + 273.15;
-    const double e_atm = 1.24 * pow(10 * vapour_pressure / k_temp, 0.143) * (0.85 + 0.5 * rhumidity);
-    const double k2 = k_temp * k_temp;
-    const double net_radiation = bolz * (k2 * k2) * (e_atm - 0.98) + global_radiation * (1.0 - land_albedo);
+    const double e_atm = 1.24 * sb_pow(10 * vapour_pressure / k_temp, 0.143) * (0.85 + 0.5 * rhumidity);
+    const double net_radiation = bolz * sb_pow4(k_temp) * (e_atm - 0.98) + global_radiation * (1.0 - land_albedo);
     const double epot = alpha * delta * net_radiation / (delta + psycr);
     if (epot < 0.0) return 0.0;
     return epot / (2500780 - 2361 * temperature);
@@ -376,8 +371,8 @@ __device__ __forceinline__ double pt_potential_evapotranspiration(double land_al
 struct KirchnerRhs {
     double c1, c2, c3, pe;  // pe = p - e
     __device__ __forceinline__ double operator()(double x) const {
-        const double g = exp(c1 + c2 * x + c3 * x * x);
-        return g >= 1.e-30 ? g * (pe * exp(-x) - 1.0) : 0.0;
+        const double g = sb_exp(c1 + c2 * x + c3 * x * x);
+        return g >= 1.e-30 ? g * (pe * sb_exp(-x) - 1.0) : 0.0;
     }
 };
 
@@ -386,7 +381,7 @@ struct KirchnerRhs {
 __device__ __forceinline__ bool kirchner_step(double c1, double c2, double c3, double t1, double& q, double& q_avg, double p, double e) {
     const double eps_abs = 1.0e-7, eps_rel = 1.0e-8;
     if (q < 0.00001) q = 0.00001;
-    double x = log(q);
+    double x = sb_log(q);
     double t = 0.0, dt = t1;
     const KirchnerRhs rhs{c1, c2, c3, p - e};
     double dxdt = rhs(x);
@@ -422,19 +417,19 @@ __device__ __forceinline__ bool kirchner_step(double c1, double c2, double c3, d
             const double x_err = dt * dc1 * dxdt + dt * dc3 * k3 + dt * dc4 * k4 + dt * dc5 * k5 + dt * dc6 * k6 + dt * dc7 * dxdt_new;
             const double err = fabs(x_err) / (eps_abs + eps_rel * (1.0 * fabs(x) + (1.0 * dt) * fabs(dxdt)));
             if (err > 1.0) {
-                dt *= dmax(9.0 / 10.0 * pow(err, -1.0 / 3.0), 1.0 / 5.0);
+                dt *= dmax(9.0 / 10.0 * sb_pow(err, -1.0 / (4 - 1)), 1.0 / 5.0);
                 if (++fails >= 500) return false;
                 continue;
             }
             t += dt;
             // the grown dt is only ever used by a following sub-step of this model step (initialize() resets it)
-            if (err < 0.5 && t < t1) dt *= 9.0 / 10.0 * pow(dmax(0.00032, err), -1.0 / 5.0);
+            if (err < 0.5 && t < t1) dt *= 9.0 / 10.0 * sb_pow(dmax(0.00032, err), -1.0 / 5);
             break;
         }
         x_old = x; k1 = dxdt; k7 = dxdt_new;
         x = x_new; dxdt = dxdt_new;
         if (t < t1) {
-            const double fq = exp(x);
+            const double fq = sb_exp(x);
             area += 0.5 * (f_a + fq) * (t - t_a);
             f_a = fq; t_a = t;
         }
@@ -463,7 +458,7 @@ __device__ __forceinline__ bool kirchner_step(double c1, double c2, double c3, d
         x = 1.0 * x_old + dtl * b1_theta * k1 + dtl * b3_theta * k3 + dtl * b4_theta * k4 + dtl * b5_theta * k5 + dtl * b6_theta * k6 +
             dtl * b7_theta * k7;
     }
-    q = exp(x);
+    q = sb_exp(x);
     area += 0.5 * (f_a + q) * (t1 - t_a);
     q_avg = area / (t1 - 0.0);
     return true;
@@ -541,7 +536,7 @@ __global__ void __launch_bounds__(128) ptgsk_run_kernel(const PtgskRunArgs a) {
                 (glacier_area_m2 <= sca_m2 || temp <= 0.0) ? 0.0 : p.gm_dtf * temp * (glacier_area_m2 - sca_m2) * (0.001 / 86400.0);
             const double pot = pt_potential_evapotranspiration(p.pt_albedo, p.pt_alpha, temp, rad, rel_hum) * 3600.0;
             // actual_evapotranspiration::calculate_step, actual_evapotranspiration.h:56-62
-            const double ae = pot * (1.0 - exp(-kq * 3.0 / p.ae_scale_factor)) * (1.0 - dmax(sca, glacier_fraction));
+            const double ae = pot * (1.0 - sb_exp(-kq * 3.0 / p.ae_scale_factor)) * (1.0 - dmax(sca, glacier_fraction));
             const double gm_mmh = m3s_to_mmh(gm_melt_m3s, cell_area_m2);
             double q_avg;
             if (!kirchner_step(p.c1, p.c2, p.c3, a.dt_hours, kq, q_avg,

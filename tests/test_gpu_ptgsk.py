@@ -155,6 +155,10 @@ def test_config1_slice_parity_through_a_winter(sb, oracle, collect):
         for name in sb.capi.STATE_SERIES_NAMES[sb.PT_GS_K]:
             assert_parity(m.state_series(name), want[name], name)
     assert_parity(m.get_states(), want["state"], "end state")
+    # one operation sequence on both machines (DESIGN.md "Deterministic math"): the per-cell results are in fact bit-identical
+    for name in names:
+        assert np.array_equal(m.response(name), want[name], equal_nan=True), name + " is within 1e-9 but not bit-identical"
+    assert np.array_equal(m.get_states(), want["state"])
     cix = m.cell_catchment_ix()
     cq = m.catchment_discharges()
     for k in range(m.number_of_catchments()):

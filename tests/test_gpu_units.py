@@ -1,0 +1,91 @@
+"""Device functions one at a time against the oracle (the reference unit-tests its methods the same way:
+test/gamma_snow_test.cpp, test/kirchner_test.cpp).  The deterministic math of shyft_b200/csrc/sb2_math.cuh and
+oracle/sho_detmath.hpp is one operation sequence written twice: results must be bit-identical."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from shyft_b200 import capi
+    return capi
+
+
+def _bits_equal(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.array_equal(a.view(np.uint64), b.view(np.uint64)) or np.array_equal(a[~np.isnan(a)], b[~np.isnan(b)]) and np.array_equal(np.isnan(a), np.isnan(b))
+
+
+def test_deterministic_math_is_bit_identical(capi, oracle):
+    rng = np.random.default_rng(42)
+    x = np.concatenate([rng.uniform(-745, 709, 200000), rng.uniform(-2, 2, 200000), [0.0, -0.0, 1e-300, 709.78, 710.0, -745.0, -746.0, np.nan, np.inf, -np.inf]])
+    assert _bits_equal(capi.unit_eval("exp", x)[:, 0], oracle.dm_eval("exp", x))
+    x = np.concatenate([np.exp(rng.uniform(-740, 709, 200000)), rng.uniform(0.5, 2.0, 200000), [0.0, 1.0, 5e-324, 1e-310, np.inf, -1.0, np.nan]])
+    assert _bits_equal(capi.unit_eval("log", x)[:, 0], oracle.dm_eval("log", x))
+    xy = np.stack([rng.uniform(0, 50, 200000), rng.uniform(-4, 4, 200000)], axis=1)
+    xy[:8] = [[0, 1.5], [0, -1.5], [2, 0], [3, 1], [3, 2], [9, 0.5], [1.02, 3.5], [5, -1.0 / 3]]
+    assert _bits_equal(capi.unit_eval("pow", xy)[:, 0], oracle.dm_eval("pow", xy[:, 0], xy[:, 1]))
+    a = rng.uniform(0.05, 60, 200000)
+    assert _bits_equal(capi.unit_eval("lgamma", a)[:, 0], oracle.dm_eval("lgamma", a))
+
+
+def test_gamma_p_is_bit_identical_and_accurate(capi, oracle):
+    sp = pytest.importorskip("scipy.special")
+    rng = np.random.default_rng(7)
+    a = rng.uniform(0.1, 8.0, 100000)
+    x = rng.uniform(0.0, 1.0, 100000) * (3 * a + 25)
+    got = capi.unit_eval("gamma_p", np.stack([a, x], axis=1))[:, 0]
+    assert _bits_equal(got, oracle.dm_eval("gamma_p", a, x))
+    ref = sp.gammainc(a, x)
+    assert np.max(np.abs(got - ref) / np.maximum(ref, 1e-300)) < 5e-13
+
+
+def test_corr_lwc_known_answer_and_bit_identity(capi, oracle):
+    z = capi.unit_eval("corr_lwc", [[4.0, 6.0, 1.0, 5.0, 2.0]])[0, 0]
+    assert abs(z - 3.8411) < 1e-4                      # test/gamma_snow_test.cpp:95-108
+    rng = np.random.default_rng(11)
+    n = 20000
+    a1 = rng.uniform(2.0, 6.25, n)
+    b1 = rng.uniform(0.05, 8.0, n)
+    z1 = rng.uniform(0.01, 1.0, n) * a1 * b1 * 2
+    a2 = np.minimum(6.25, a1 * rng.uniform(0.9, 1.2, n))
+    b2 = b1 * rng.uniform(1.0, 1.5, n)
+    got = capi.unit_eval("corr_lwc", np.stack([z1, a1, b1, a2, b2], axis=1))[:, 0]
+    want = np.array([oracle.gs_corr_lwc(z1[i], a1[i], b1[i], 0.0, a2[i], b2[i])[0] for i in range(n)])
+    assert _bits_equal(got, want)
+
+
+def test_calc_snow_state_known_answer_and_bit_identity(capi, oracle):
+    swe, sca = capi.unit_eval("calc_snow_state", [[6.25, 0.064, 0.04, 0.0, 0.0, 0.1, 0.0]])[0]
+    assert abs(swe - 0.384) < 1e-10 and abs(sca - 0.96) < 1e-10   # test/gamma_snow_test.cpp:76-93
+    rng = np.random.default_rng(13)
+    n = 20000
+    rows = np.stack([rng.uniform(0.1, 6.25, n), rng.uniform(0.0, 20.0, n), np.full(n, 0.04), rng.uniform(-1.0, 60.0, n),
+                     rng.uniform(0.0, 30.0, n) * (rng.random(n) < 0.7), np.full(n, 0.1), rng.uniform(0, 2, n) * (rng.random(n) < 0.3)], axis=1)
+    rows[:50, 1] = 0.0   # scale 0: lambda/scale = inf takes the bare-ground branch (gamma_snow.h:239-241)
+    got = capi.unit_eval("calc_snow_state", rows)
+    want = np.array([oracle.gs_calc_snow_state(*r) for r in rows])
+    assert _bits_equal(got, want)
+
+
+def test_kirchner_step_bit_identity_and_known_behaviour(capi, oracle):
+    rng = np.random.default_rng(17)
+    n = 20000
+    q = np.exp(rng.uniform(np.log(1e-6), np.log(60.0), n))
+    p = rng.exponential(2.0, n) * (rng.random(n) < 0.5)
+    e = rng.uniform(0, 0.3, n)
+    rows = np.stack([np.full(n, -2.439), np.full(n, 0.966), np.full(n, -0.10), np.full(n, 1.0), q, p, e], axis=1)
+    rows[: n // 4, 3] = 3.0    # 3-hour steps
+    rows[n // 4: n // 2, 3] = 24.0
+    got = capi.unit_eval("kirchner_step", rows)
+    assert np.all(got[:, 2] == 1.0)
+    want = np.array([oracle.kirchner_step(r[4], r[5], r[6], dt_us=int(r[3] * 3600 * 10**6))[:2] for r in rows])
+    assert _bits_equal(got[:, :2], want)
+    # P = 10, E = 0 from q = 1: q and q_avg converge to 10 (test/kirchner_test.cpp:40-54)
+    row = np.array([[-2.439, 0.966, -0.10, 1.0, 1.0, 10.0, 0.0]])
+    for _ in range(3000):
+        out = capi.unit_eval("kirchner_step", row)
+        row[0, 4] = out[0, 0]
+    assert abs(out[0, 0] - 10.0) < 1e-3 and abs(out[0, 1] - 10.0) < 1e-3
