@@ -6,7 +6,8 @@
 // amplifies such last-bit noise to 1e-4-level differences in liquid water content whenever its objective is flat
 // (measured on the B200: CUDA libm vs glibc gave 2.7 % of cell-steps off by more than 1e-9).  A 1e-9 parity
 // statement between two machines is therefore only meaningful if both evaluate the SAME operation sequence.
-// This header is that sequence, written with IEEE-754 +,-,*,/ and sqrt only (no FMA, no libm), so that any
+// This header is that sequence, written with IEEE-754 +,-,*,/, sqrt and explicit fma() only (no implicit contraction,
+// no libm), so that any
 // conforming machine -- the host CPU here, an sm_100a SM in shyft_b200/csrc/sb2_math.cuh -- produces identical
 // bits.  Accuracy (checked in tests/test_oracle_detmath.py against libm / scipy): exp, log < 1.5 ulp;
 // lgamma abs error < 1e-14 on (0.05, 200); pow(x,y) = exp(y*log(x)) except the exact cases y = 0, 0.5, 1, 2.
@@ -25,28 +26,27 @@ inline uint64_t bits_of(double x) { uint64_t u; std::memcpy(&u, &x, 8); return u
 inline double from_bits(uint64_t u) { double x; std::memcpy(&x, &u, 8); return x; }
 inline double pow2i(int k) { return from_bits(uint64_t(k + 1023) << 52); }  // 2^k, -1022 <= k <= 1023
 
-// exp(x): k = round(x/ln2), r = x - k*ln2 (two-part Cody-Waite), degree-13 Taylor polynomial in Horner form, scale by 2^k
+// exp(x): k = floor(x/ln2 + 1/2), r = x - k*ln2 (two fused steps), degree-13 Taylor polynomial by Estrin's scheme, scaled by 2^k
 inline double exp(double x) {
     if (x != x) return x;
     if (x > 709.782712893384) return std::numeric_limits<double>::infinity();
     if (x < -745.1332191019412) return 0.0;
-    const double kf = std::floor(x * 1.44269504088896338700e+00 + 0.5);
-    const double hi = x - kf * 6.93147180369123816490e-01;
-    const double lo = kf * 1.90821492927058770002e-10;
-    const double r = hi - lo;
-    double q = 1.0 / 6227020800.0;
-    q = q * r + 1.0 / 479001600.0;
-    q = q * r + 1.0 / 39916800.0;
-    q = q * r + 1.0 / 3628800.0;
-    q = q * r + 1.0 / 362880.0;
-    q = q * r + 1.0 / 40320.0;
-    q = q * r + 1.0 / 5040.0;
-    q = q * r + 1.0 / 720.0;
-    q = q * r + 1.0 / 120.0;
-    q = q * r + 1.0 / 24.0;
-    q = q * r + 1.0 / 6.0;
-    q = q * r + 0.5;
-    double p = 1.0 + (r + (r * r) * q);
+    const double kf = std::floor(std::fma(x, 1.44269504088896338700e+00, 0.5));
+    double r = std::fma(kf, -6.93147180369123816490e-01, x);
+    r = std::fma(kf, -1.90821492927058770002e-10, r);
+    const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
+    const double a0 = std::fma(1.0 / 6.0, r, 0.5);
+    const double a1 = std::fma(1.0 / 120.0, r, 1.0 / 24.0);
+    const double a2 = std::fma(1.0 / 5040.0, r, 1.0 / 720.0);
+    const double a3 = std::fma(1.0 / 362880.0, r, 1.0 / 40320.0);
+    const double a4 = std::fma(1.0 / 39916800.0, r, 1.0 / 3628800.0);
+    const double a5 = std::fma(1.0 / 6227020800.0, r, 1.0 / 479001600.0);
+    const double b0 = std::fma(a1, r2, a0);
+    const double b1 = std::fma(a3, r2, a2);
+    const double b2 = std::fma(a5, r2, a4);
+    const double d0 = std::fma(b1, r4, b0);
+    const double Q = std::fma(b2, r8, d0);
+    double p = 1.0 + std::fma(r2, Q, r);
     int k = int(kf);
     if (k > 1023) { p *= pow2i(1023); k -= 1023; }
     if (k < -1022) { p *= pow2i(k + 1000); return p * pow2i(-1000); }      // one rounding into the subnormal range
@@ -54,7 +54,7 @@ inline double exp(double x) {
 }
 
 // log(x): x = 2^e * m, m in (sqrt(1/2), sqrt(2)], f = m-1, s = f/(2+f), log(1+f) = f - f^2/2 + s*(f^2/2 + R(s^2)),
-// R(z) = sum_{k=1..10} 2/(2k+1) z^k  (the atanh series)
+// R(z) = z * sum_{k=0..9} 2/(2k+3) z^k  (the atanh series, Estrin's scheme)
 inline double log(double x) {
     if (x != x || x < 0.0) return std::numeric_limits<double>::quiet_NaN();
     if (x == 0.0) return -std::numeric_limits<double>::infinity();
@@ -67,21 +67,20 @@ inline double log(double x) {
     if (m > 1.4142135623730951) { m *= 0.5; e += 1; }
     const double f = m - 1.0;
     const double s = f / (2.0 + f);
-    const double z = s * s;
-    double R = 2.0 / 21.0;
-    R = R * z + 2.0 / 19.0;
-    R = R * z + 2.0 / 17.0;
-    R = R * z + 2.0 / 15.0;
-    R = R * z + 2.0 / 13.0;
-    R = R * z + 2.0 / 11.0;
-    R = R * z + 2.0 / 9.0;
-    R = R * z + 2.0 / 7.0;
-    R = R * z + 2.0 / 5.0;
-    R = R * z + 2.0 / 3.0;
-    R = R * z;
+    const double z = s * s, z2 = z * z, z4 = z2 * z2, z8 = z4 * z4;
+    const double t01 = std::fma(2.0 / 5.0, z, 2.0 / 3.0);
+    const double t23 = std::fma(2.0 / 9.0, z, 2.0 / 7.0);
+    const double t45 = std::fma(2.0 / 13.0, z, 2.0 / 11.0);
+    const double t67 = std::fma(2.0 / 17.0, z, 2.0 / 15.0);
+    const double t89 = std::fma(2.0 / 21.0, z, 2.0 / 19.0);
+    const double u0 = std::fma(t23, z2, t01);
+    const double u1 = std::fma(t67, z2, t45);
+    const double v0 = std::fma(u1, z4, u0);
+    const double R = z * std::fma(t89, z8, v0);
     const double hfsq = 0.5 * f * f;
     const double dk = double(e);
-    return dk * 6.93147180369123816490e-01 - ((hfsq - (s * (hfsq + R) + dk * 1.90821492927058770002e-10)) - f);
+    const double t = std::fma(s, hfsq + R, dk * 1.90821492927058770002e-10);
+    return std::fma(dk, 6.93147180369123816490e-01, f - (hfsq - t));
 }
 
 // pow(x, y) for x >= 0: exact for y = 0, 1, 2, 0.5; exp(y*log(x)) otherwise
@@ -102,12 +101,12 @@ inline double lgamma(double a) {
     while (a < 12.0) { prod *= a; a += 1.0; }
     const double ai = 1.0 / a, ai2 = ai * ai;
     double s = 1.0 / 156.0;
-    s = 691.0 / 360360.0 - ai2 * s;
-    s = 1.0 / 1188.0 - ai2 * s;
-    s = 1.0 / 1680.0 - ai2 * s;
-    s = 1.0 / 1260.0 - ai2 * s;
-    s = 1.0 / 360.0 - ai2 * s;
-    s = 1.0 / 12.0 - ai2 * s;
+    s = std::fma(-ai2, s, 691.0 / 360360.0);
+    s = std::fma(-ai2, s, 1.0 / 1188.0);
+    s = std::fma(-ai2, s, 1.0 / 1680.0);
+    s = std::fma(-ai2, s, 1.0 / 1260.0);
+    s = std::fma(-ai2, s, 1.0 / 360.0);
+    s = std::fma(-ai2, s, 1.0 / 12.0);
     s = ai * s;
     return (((a - 0.5) * dm::log(a) - a) + 0.91893853320467274178) + s - dm::log(prod);
 }

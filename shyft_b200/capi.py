@@ -74,7 +74,7 @@ def lib():
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = _build.LIB
+    path = os.environ.get("SB2_LIB") or _build.LIB   # SB2_LIB: a build variant produced by tools/ (tuning runs only)
     if not os.path.exists(path) or os.environ.get("SB2_REBUILD"):
         try:  # normally __graft_entry__.build() has produced the file and it travels with the tree
             _build.build_library(force=bool(os.environ.get("SB2_REBUILD")))

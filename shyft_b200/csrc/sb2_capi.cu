@@ -308,7 +308,7 @@ void launch_step_range(sb2_model* m, int64_t first, int64_t n_steps, bool collec
     sync_parameters(m);
     sync_filter(m);
     const int64_t n = m->n;
-    const int block = 128;
+    const int block = SB2_BLOCK;
     const double dt_seconds = double(m->dt) / 1e6;
     if (m->partial_steps == 0) {
         // bound the scratch for the per-slot partial sums to ~256 MB
@@ -457,14 +457,15 @@ void run_idw(sb2_model* m, int var, int64_t first, int64_t n_steps, double* out)
     if (!pl.valid) build_idw_plan(m, var);
     const Source& s = m->src[var];
     const int tile = idw_tile_steps(s.n_src);
-    const size_t smem = size_t(tile) * s.n_src * sizeof(double);
-    if (smem > 200 * 1024) throw Error("inverse_distance: too many sources for the shared-memory tile");
-    const int g = grid_for(m->n, 128);
-#define SB2_IDW(K)                                                                                                                  \
-    {                                                                                                                               \
+    const int max_k = int(std::max<int64_t>(1, std::min<int64_t>(pl.p.max_members, s.n_src)));
+    const size_t smem = size_t(tile) * s.n_src * sizeof(double) + size_t(max_k) * IDW_BLOCK * (2 * sizeof(double) + sizeof(int));
+    if (smem > 200 * 1024) throw Error("inverse_distance: too many sources / members for the shared-memory tiles");
+    const int g = grid_for(m->n, IDW_BLOCK);
+#define SB2_IDW(K)                                                                                                                   \
+    {                                                                                                                                \
         if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(idw_apply_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); \
-        idw_apply_kernel<K><<<g, 128, smem, m->stream>>>(m->n, m->d_z.p, int(s.n_src), s.d_xyz.p, s.d_values.p, first, int(n_steps), pl.p, \
-                                                         pl.idx.p, pl.w.p, pl.f.p, pl.cnt.p, m->d_active.p, out, tile);               \
+        idw_apply_kernel<K><<<g, IDW_BLOCK, smem, m->stream>>>(m->n, m->d_z.p, int(s.n_src), s.d_xyz.p, s.d_values.p, first, int(n_steps),  \
+                                                               pl.p, pl.idx.p, pl.w.p, pl.f.p, pl.cnt.p, m->d_active.p, out, tile, max_k);     \
     }
     switch (idw_kind_of(var)) {
         case IDW_TEMPERATURE: SB2_IDW(IDW_TEMPERATURE) break;
@@ -552,11 +553,22 @@ void run_btk(sb2_model* m, int64_t first, int64_t n_steps, double* out) {
         btk_step_prepare_kernel<<<grid_for(seg, 128), 128, 0, m->stream>>>(int(seg), first + i, S, s.d_values.p, op->valid_idx.p, nv,
                                                                           op->E_beta_w.p, op->sz.p, m->d_btk_beta.p, m->d_btk_resid.p);
         CUDA_OK(cudaGetLastError());
-        const int tile = idw_tile_steps(nv);
-        const size_t smem = size_t(tile) * nv * sizeof(double);
-        btk_apply_kernel<<<grid_for(m->n, 128), 128, smem, m->stream>>>(m->n, m->d_z.p, nv, op->omega.p, op->bm.p, m->d_btk_beta.p,
-                                                                       m->d_btk_resid.p, m->d_prior_gradient.p + first + i, int(seg),
-                                                                       m->d_active.p, out + i * m->n, tile);
+        double* o = out + i * m->n;
+        const double* pri = m->d_prior_gradient.p + first + i;
+#define SB2_BTK(KS, NT)                                                                                                            \
+    btk_apply_dmma_kernel<KS, NT><<<grid_for(m->n, 32 * NT), 128, 0, m->stream>>>(m->n, m->d_z.p, nv, op->omega.p, op->bm.p, m->d_btk_beta.p, \
+                                                                                  m->d_btk_resid.p, pri, int(seg), m->d_active.p, o)
+        if (nv <= 16) SB2_BTK(4, 4);
+        else if (nv <= 32) SB2_BTK(8, 4);
+        else if (nv <= 64) SB2_BTK(16, 2);
+        else if (nv <= 96) SB2_BTK(24, 1);
+        else {  // more stations than the register-resident operator tile holds: one thread per cell, operator rows streamed
+            const int tile = idw_tile_steps(nv);
+            const size_t smem = size_t(tile) * nv * sizeof(double);
+            btk_apply_kernel<<<grid_for(m->n, 128), 128, smem, m->stream>>>(m->n, m->d_z.p, nv, op->omega.p, op->bm.p, m->d_btk_beta.p,
+                                                                           m->d_btk_resid.p, pri, int(seg), m->d_active.p, o, tile);
+        }
+#undef SB2_BTK
         CUDA_OK(cudaGetLastError());
         m->launches += 2;
         i = j;

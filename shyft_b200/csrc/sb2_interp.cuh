@@ -79,6 +79,7 @@ __global__ void idw_build_neighbours_kernel(int kind, int64_t n_cells, const dou
         double f = 1.0;
         if (kind == IDW_PRECIPITATION) f = sb_pow(p.scale_factor, (z - sxyz[3 * k + 2]) / 100.0);  // :422-426
         else if (kind == IDW_RADIATION) f = cslope[c];                                            // :392-394
+        else if (kind == IDW_TEMPERATURE) f = sxyz[3 * k + 2];                                     // station height, read by the gradient (:285-316) and the transform (:367-369)
         nb_f[(int64_t)j * n_cells + c] = f;
     }
 }
@@ -110,23 +111,37 @@ __device__ inline bool solve3(double A[3][3], double b[3], double x[3]) {
 }
 
 // Step 2 (:214-249): out[(i)*n_cells + c] = sum_k w*transform(v_k) / sum_k w over the finite neighbours, in list order.
-// Source values of a tile of steps are staged in shared memory; one thread per cell walks the tile.
+// One thread per cell.  The block stages (a) its cells' neighbour lists -- index, weight and the per-neighbour constant
+// (precipitation/radiation factor, or the station height for temperature) -- once, laid out [j][thread] so the per-step
+// walk is conflict-free, and (b) the station values of a tile of steps; every step then runs out of shared memory.
+// dynamic smem: tile_steps*n_src doubles + max_k*IDW_BLOCK*(2 doubles + 1 int)
+constexpr int IDW_BLOCK = 128;
 template <int KIND>
-__global__ void __launch_bounds__(128) idw_apply_kernel(int64_t n_cells, const double* __restrict__ cz, int n_src,
-                                                        const double* __restrict__ sxyz, const double* __restrict__ src /* [T][n_src] */,
-                                                        int64_t first_step, int n_steps, IdwParam p, const int32_t* __restrict__ nb_idx,
-                                                        const double* __restrict__ nb_w, const double* __restrict__ nb_f,
-                                                        const int32_t* __restrict__ nb_n, const uint8_t* __restrict__ active,
-                                                        double* __restrict__ out, int tile_steps) {
-    extern __shared__ double sv[];  // [tile_steps][n_src]
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(IDW_BLOCK) idw_apply_kernel(int64_t n_cells, const double* __restrict__ cz, int n_src,
+                                                              const double* __restrict__ sxyz, const double* __restrict__ src /* [T][n_src] */,
+                                                              int64_t first_step, int n_steps, IdwParam p, const int32_t* __restrict__ nb_idx,
+                                                              const double* __restrict__ nb_w, const double* __restrict__ nb_f,
+                                                              const int32_t* __restrict__ nb_n, const uint8_t* __restrict__ active,
+                                                              double* __restrict__ out, int tile_steps, int max_k) {
+    extern __shared__ double smem[];
+    double* sv = smem;                                   // [tile_steps][n_src]
+    double* sw = sv + (size_t)tile_steps * n_src;        // [max_k][IDW_BLOCK]
+    double* sf = sw + (size_t)max_k * IDW_BLOCK;         // [max_k][IDW_BLOCK]
+    int* sk = (int*)(sf + (size_t)max_k * IDW_BLOCK);    // [max_k][IDW_BLOCK]
+    const int tid = threadIdx.x;
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + tid;
     const bool ok = c < n_cells && (active == nullptr || active[c] != 0);  // cells outside the calculation filter keep their NaN fill (region_model.h:420-423)
     const int cnt = ok ? nb_n[c] : 0;
     const double z = ok ? cz[c] : 0.0;
+    for (int j = 0; j < cnt; ++j) {
+        sk[j * IDW_BLOCK + tid] = nb_idx[(int64_t)j * n_cells + c];
+        sw[j * IDW_BLOCK + tid] = nb_w[(int64_t)j * n_cells + c];
+        sf[j * IDW_BLOCK + tid] = nb_f[(int64_t)j * n_cells + c];
+    }
     for (int t0 = 0; t0 < n_steps; t0 += tile_steps) {
         const int nt = min(tile_steps, n_steps - t0);
         __syncthreads();
-        for (int e = threadIdx.x; e < nt * n_src; e += blockDim.x) sv[e] = src[(first_step + t0) * n_src + e];
+        for (int e = tid; e < nt * n_src; e += blockDim.x) sv[e] = src[(first_step + t0) * n_src + e];
         __syncthreads();
         if (!ok) continue;
         for (int i = 0; i < nt; ++i) {
@@ -137,9 +152,9 @@ __global__ void __launch_bounds__(128) idw_apply_kernel(int64_t n_cells, const d
                 int nv = 0, mn = -1, mx = -1, first[4] = {-1, -1, -1, -1};
                 double zmn = 0, zmx = 0;
                 for (int j = 0; j < cnt; ++j) {
-                    const int k = nb_idx[(int64_t)j * n_cells + c];
+                    const int k = sk[j * IDW_BLOCK + tid];
                     if (!isfinite(v[k])) continue;
-                    const double h = sxyz[3 * k + 2];
+                    const double h = sf[j * IDW_BLOCK + tid];
                     if (nv < 4) first[nv] = k;
                     if (nv == 0) { mn = mx = k; zmn = zmx = h; }
                     else if (h < zmn) { mn = k; zmn = h; }
@@ -164,13 +179,12 @@ __global__ void __launch_bounds__(128) idw_apply_kernel(int64_t n_cells, const d
             }
             double sum_w = 0, sum_wv = 0;
             for (int j = 0; j < cnt; ++j) {
-                const int k = nb_idx[(int64_t)j * n_cells + c];
-                const double s = v[k];
+                const double s = v[sk[j * IDW_BLOCK + tid]];
                 if (isfinite(s)) {
-                    const double w = nb_w[(int64_t)j * n_cells + c];
+                    const double w = sw[j * IDW_BLOCK + tid];
                     double tv;
-                    if (KIND == IDW_TEMPERATURE) tv = s + scale * (z - sxyz[3 * k + 2]);
-                    else if (KIND == IDW_PRECIPITATION || KIND == IDW_RADIATION) tv = s * nb_f[(int64_t)j * n_cells + c];
+                    if (KIND == IDW_TEMPERATURE) tv = s + scale * (z - sf[j * IDW_BLOCK + tid]);
+                    else if (KIND == IDW_PRECIPITATION || KIND == IDW_RADIATION) tv = s * sf[j * IDW_BLOCK + tid];
                     else tv = s;
                     sum_wv += w * tv;
                     sum_w += w;
@@ -258,6 +272,96 @@ __global__ void __launch_bounds__(128) btk_apply_kernel(int64_t n_cells, const d
             for (int s = 0; s < n_valid; ++s) acc += omega[(int64_t)s * n_cells + c] * sr[i * n_valid + s];
             const double t_hat = (1.0 * b0 + z * b1) + acc;
             out[(int64_t)(t0 + i) * n_cells + c] = t_hat - (bm0 * (b0 - 0.0) + bm1 * (b1 - prior_gradient[t0 + i]));
+        }
+    }
+}
+
+// ---- BTK on the FP64 tensor cores ---------------------------------------------------------------------------
+// The per-step kriging term  sum_s omega[c][s] * resid[t][s]  is a dense (time x stations) x (stations x cells) contraction.
+// D[t][c] tiles of 8 steps x 8 cells are accumulated with mma.sync.m8n8k4.f64 (SASS DMMA): A = resid (row-major, staged per
+// block in shared memory, row stride padded to 4 mod 16 doubles so a half-warp's 4 rows x 4 columns hit 16 distinct 8-byte
+// banks), B = omega^T held in registers for the whole launch (it does not change over time), then the affine terms of
+// bayesian_kriging.h:394-396 are applied in the epilogue.  Each warp owns 8*NT consecutive cells; a quad of lanes stores 8
+// consecutive cells (64 B) per step.  KSTEPS*4 >= n_valid stations (zero padded).
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+template <int KSTEPS, int NT>
+__global__ void __launch_bounds__(128) btk_apply_dmma_kernel(int64_t n_cells, const double* __restrict__ cz, int n_valid,
+                                                             const double* __restrict__ omega /* [n_valid][cells] */, const double* __restrict__ bm,
+                                                             const double* __restrict__ beta /* [n_steps][2] */,
+                                                             const double* __restrict__ resid /* [n_steps][n_valid] */,
+                                                             const double* __restrict__ prior_gradient /* [n_steps] */, int n_steps,
+                                                             const uint8_t* __restrict__ active, double* __restrict__ out /* [n_steps][cells] */) {
+    constexpr int KP = KSTEPS * 4 + 4;  // padded row stride (doubles), == 4 mod 16
+    constexpr int BTK_TILE_STEPS = KSTEPS > 16 ? 32 : 64;  // steps of resid staged per block iteration (static smem <= 48 KB)
+    __shared__ double sr[BTK_TILE_STEPS * KP];
+    __shared__ double sbeta[BTK_TILE_STEPS * 2];
+    __shared__ double spri[BTK_TILE_STEPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, q = lane & 3;  // group (row of A / column of B), position in the quad
+    const int64_t cbase = ((int64_t)blockIdx.x * 4 + warp) * (8 * NT);
+    // B fragments: breg[nt][ks] = omega[cell cbase + nt*8 + g][station ks*4 + q]
+    double breg[NT][KSTEPS];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        const int64_t cell = cbase + nt * 8 + g;
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+            const int st = ks * 4 + q;
+            breg[nt][ks] = (cell < n_cells && st < n_valid) ? omega[(int64_t)st * n_cells + cell] : 0.0;
+        }
+    }
+    // epilogue constants of the two cells this lane stores per n-tile
+    double ez[NT][2], e0[NT][2], e1[NT][2];
+    bool eok[NT][2];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int64_t cell = cbase + nt * 8 + q * 2 + h;
+            const bool ok = cell < n_cells && (active == nullptr || active[cell] != 0);
+            eok[nt][h] = ok;
+            ez[nt][h] = ok ? cz[cell] : 0.0;
+            e0[nt][h] = ok ? bm[cell] : 0.0;
+            e1[nt][h] = ok ? bm[n_cells + cell] : 0.0;
+        }
+    for (int t0 = 0; t0 < n_steps; t0 += BTK_TILE_STEPS) {
+        const int nt_steps = min(BTK_TILE_STEPS, n_steps - t0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < BTK_TILE_STEPS * KP; e += blockDim.x) {
+            const int r = e / KP, k = e - r * KP;
+            sr[e] = (r < nt_steps && k < n_valid) ? resid[(int64_t)(t0 + r) * n_valid + k] : 0.0;
+        }
+        for (int e = threadIdx.x; e < BTK_TILE_STEPS; e += blockDim.x) {
+            const bool in = e < nt_steps;
+            sbeta[2 * e] = in ? beta[2 * (t0 + e)] : 0.0;
+            sbeta[2 * e + 1] = in ? beta[2 * (t0 + e) + 1] : 0.0;
+            spri[e] = in ? prior_gradient[t0 + e] : 0.0;
+        }
+        __syncthreads();
+        for (int m0 = 0; m0 < nt_steps; m0 += 8) {
+            double acc[NT][2];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < KSTEPS; ++ks) {
+                const double a = sr[(m0 + g) * KP + ks * 4 + q];
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) dmma_m8n8k4(acc[nt][0], acc[nt][1], a, breg[nt][ks]);
+            }
+            const int tl = m0 + g;  // this lane's row of D
+            if (tl < nt_steps) {
+                const double b0 = sbeta[2 * tl], b1 = sbeta[2 * tl + 1], pri = spri[tl];
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                        if (eok[nt][h]) {
+                            const double t_hat = (1.0 * b0 + ez[nt][h] * b1) + acc[nt][h];
+                            out[(int64_t)(t0 + tl) * n_cells + cbase + nt * 8 + q * 2 + h] = t_hat - (e0[nt][h] * (b0 - 0.0) + e1[nt][h] * (b1 - pri));
+                        }
+            }
         }
     }
 }

@@ -1,11 +1,11 @@
 // sb2_math.cuh -- fp64 math used by the cell-stack kernels (sm_100a) and by the host-side operator builds.
 //
-// Deterministic elementary functions: exp, log, pow, lgamma written with IEEE-754 +,-,*,/ and sqrt only (no FMA
-// contraction: the library is built with -fmad=false; no CUDA libm), so that the device, the host part of this library
+// Deterministic elementary functions: exp, log, pow, lgamma written with IEEE-754 +,-,*,/, sqrt and explicit fma() only (no
+// implicit contraction: the library is built with -fmad=false; no CUDA libm), so that the device, the host part of this library
 // and any other conforming machine produce identical bits.  Why: gamma_snow's Brent search (core/gamma_snow.h:214-227)
 // amplifies last-bit differences between math libraries to 1e-4-level differences in liquid water content; a 1e-9 parity
 // statement is only meaningful over one fixed operation sequence (DESIGN.md "Deterministic math").  The sequence:
-//   exp(x)    k = floor(x/ln2 + 0.5), r = (x - k*ln2_hi) - k*ln2_lo, degree-13 Taylor polynomial (Horner), scaled by 2^k
+//   exp(x)    k = floor(x/ln2 + 0.5), r = fma(k,-ln2_lo, fma(k,-ln2_hi,x)), degree-13 Taylor polynomial (Estrin, fma), scaled by 2^k
 //   log(x)    x = 2^e*m, m in (sqrt(1/2), sqrt(2)], f = m-1, s = f/(2+f), f - f^2/2 + s*(f^2/2 + R(s^2)), R = atanh series to s^20
 //   pow(x,y)  exact for y = 0, 1, 2, 0.5; exp(y*log(x)) otherwise (x >= 0)
 //   lgamma(a) recurrence up to a >= 12, then the Stirling series to 1/a^13
@@ -44,26 +44,25 @@ SB2_HD double sb_exp(double x) {
     if (x != x) return x;
     if (x > 709.782712893384) return inf_();
     if (x < -745.1332191019412) return 0.0;
-    const double kf = floor(x * 1.44269504088896338700e+00 + 0.5);
-    const double hi = x - kf * 6.93147180369123816490e-01;
-    const double lo = kf * 1.90821492927058770002e-10;
-    const double r = hi - lo;
-    double q = 1.0 / 6227020800.0;
-    q = q * r + 1.0 / 479001600.0;
-    q = q * r + 1.0 / 39916800.0;
-    q = q * r + 1.0 / 3628800.0;
-    q = q * r + 1.0 / 362880.0;
-    q = q * r + 1.0 / 40320.0;
-    q = q * r + 1.0 / 5040.0;
-    q = q * r + 1.0 / 720.0;
-    q = q * r + 1.0 / 120.0;
-    q = q * r + 1.0 / 24.0;
-    q = q * r + 1.0 / 6.0;
-    q = q * r + 0.5;
-    double p = 1.0 + (r + (r * r) * q);
+    const double kf = floor(fma(x, 1.44269504088896338700e+00, 0.5));
+    double r = fma(kf, -6.93147180369123816490e-01, x);
+    r = fma(kf, -1.90821492927058770002e-10, r);
+    const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
+    const double a0 = fma(1.0 / 6.0, r, 0.5);
+    const double a1 = fma(1.0 / 120.0, r, 1.0 / 24.0);
+    const double a2 = fma(1.0 / 5040.0, r, 1.0 / 720.0);
+    const double a3 = fma(1.0 / 362880.0, r, 1.0 / 40320.0);
+    const double a4 = fma(1.0 / 39916800.0, r, 1.0 / 3628800.0);
+    const double a5 = fma(1.0 / 6227020800.0, r, 1.0 / 479001600.0);
+    const double b0 = fma(a1, r2, a0);
+    const double b1 = fma(a3, r2, a2);
+    const double b2 = fma(a5, r2, a4);
+    const double d0 = fma(b1, r4, b0);
+    const double Q = fma(b2, r8, d0);
+    double p = 1.0 + fma(r2, Q, r);
     int k = int(kf);
     if (k > 1023) { p *= pow2i(1023); k -= 1023; }
-    if (k < -1022) { p *= pow2i(k + 1000); return p * pow2i(-1000); }
+    if (k < -1022) { p *= pow2i(k + 1000); return p * pow2i(-1000); }      // one rounding into the subnormal range
     return p * pow2i(k);
 }
 
@@ -72,28 +71,27 @@ SB2_HD double sb_log(double x) {
     if (x == 0.0) return -inf_();
     if (x == inf_()) return x;
     int e = 0;
-    if (x < 2.2250738585072014e-308) { x *= 18014398509481984.0; e = -54; }
+    if (x < 2.2250738585072014e-308) { x *= 18014398509481984.0; e = -54; }  // subnormal: scale by 2^54
     const unsigned long long u = bits_of(x);
     e += int((u >> 52) & 0x7ff) - 1023;
     double m = from_bits((u & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL);
     if (m > 1.4142135623730951) { m *= 0.5; e += 1; }
     const double f = m - 1.0;
     const double s = f / (2.0 + f);
-    const double z = s * s;
-    double R = 2.0 / 21.0;
-    R = R * z + 2.0 / 19.0;
-    R = R * z + 2.0 / 17.0;
-    R = R * z + 2.0 / 15.0;
-    R = R * z + 2.0 / 13.0;
-    R = R * z + 2.0 / 11.0;
-    R = R * z + 2.0 / 9.0;
-    R = R * z + 2.0 / 7.0;
-    R = R * z + 2.0 / 5.0;
-    R = R * z + 2.0 / 3.0;
-    R = R * z;
+    const double z = s * s, z2 = z * z, z4 = z2 * z2, z8 = z4 * z4;
+    const double t01 = fma(2.0 / 5.0, z, 2.0 / 3.0);
+    const double t23 = fma(2.0 / 9.0, z, 2.0 / 7.0);
+    const double t45 = fma(2.0 / 13.0, z, 2.0 / 11.0);
+    const double t67 = fma(2.0 / 17.0, z, 2.0 / 15.0);
+    const double t89 = fma(2.0 / 21.0, z, 2.0 / 19.0);
+    const double u0 = fma(t23, z2, t01);
+    const double u1 = fma(t67, z2, t45);
+    const double v0 = fma(u1, z4, u0);
+    const double R = z * fma(t89, z8, v0);
     const double hfsq = 0.5 * f * f;
     const double dk = double(e);
-    return dk * 6.93147180369123816490e-01 - ((hfsq - (s * (hfsq + R) + dk * 1.90821492927058770002e-10)) - f);
+    const double t = fma(s, hfsq + R, dk * 1.90821492927058770002e-10);
+    return fma(dk, 6.93147180369123816490e-01, f - (hfsq - t));
 }
 
 SB2_HD double sb_pow(double x, double y) {
@@ -112,12 +110,12 @@ SB2_HD double sb_lgamma(double a) {
     while (a < 12.0) { prod *= a; a += 1.0; }
     const double ai = 1.0 / a, ai2 = ai * ai;
     double s = 1.0 / 156.0;
-    s = 691.0 / 360360.0 - ai2 * s;
-    s = 1.0 / 1188.0 - ai2 * s;
-    s = 1.0 / 1680.0 - ai2 * s;
-    s = 1.0 / 1260.0 - ai2 * s;
-    s = 1.0 / 360.0 - ai2 * s;
-    s = 1.0 / 12.0 - ai2 * s;
+    s = fma(-ai2, s, 691.0 / 360360.0);
+    s = fma(-ai2, s, 1.0 / 1188.0);
+    s = fma(-ai2, s, 1.0 / 1680.0);
+    s = fma(-ai2, s, 1.0 / 1260.0);
+    s = fma(-ai2, s, 1.0 / 360.0);
+    s = fma(-ai2, s, 1.0 / 12.0);
     s = ai * s;
     return (((a - 0.5) * sb_log(a) - a) + 0.91893853320467274178) + s - sb_log(prod);
 }

@@ -80,6 +80,14 @@ struct PtgskRunArgs {
 };
 
 struct GsState { double albedo, lwc, surface_heat, alpha, sdc_melt_mean, acc_melt, iso_pot_energy, temp_swe; };
+// Exact memoisation across steps.  The snow state a step ends with (calc_snow_state at gamma_snow.h:472) is what the next
+// step starts by recomputing (:411) from the same five numbers; when their bits are unchanged the result is reused.
+struct GsCache {
+    double k_alpha, k_scale, k_acc, k_lwc, k_tswe;  // inputs of the memoised call (NaN = empty)
+    double storage, sca;                            // its outputs
+    double lg_key, lg_val;                          // lgamma(alpha)
+};
+__device__ __forceinline__ void gs_cache_clear(GsCache& c) { c.k_alpha = c.lg_key = nan_(); c.k_scale = c.k_acc = c.k_lwc = c.k_tswe = 0.0; c.storage = c.sca = c.lg_val = 0.0; }
 
 __device__ __forceinline__ double mmh_to_m3s(double mmh, double area) { return area * mmh * (1 / (3600.0 * 1000.0)); }
 __device__ __forceinline__ double m3s_to_mmh(double m3s, double area) { return m3s / ((1 / (3600.0 * 1000.0)) * area); }
@@ -149,8 +157,9 @@ __device__ __noinline__ double gs_corr_lwc(double z1, double a1, double b1, doub
 }
 
 // calc_snow_state, gamma_snow.h:230-260
+// `lg_key`/`lg_val` memoise lgamma(shape): the shape (alpha) changes on few steps, and equal bits in give equal bits out
 __device__ __noinline__ void gs_calc_snow_state(double shape, double scale, double y0, double lambda, double lwd, double max_water_frac,
-                                                double temp_swe, double& swe, double& sca) {
+                                                double temp_swe, double& swe, double& sca, double& lg_key, double& lg_val) {
     double y = 0.0, y1 = 0.0;
     const double m = shape * scale;
     double lg = 0.0;
@@ -163,7 +172,8 @@ __device__ __noinline__ void gs_calc_snow_state(double shape, double scale, doub
         return;
     } else {
         const double x = lambda / scale;
-        lg = sb_lgamma(shape);
+        if (shape != lg_key) { lg_key = shape; lg_val = sb_lgamma(shape); }
+        lg = lg_val;
         have_lg = true;
         const double pre = gamma_prefix(shape, x, lg);
         y = (x > 0.0) ? gamma_p_with_prefix(shape, x, pre) : 0.0;
@@ -175,7 +185,10 @@ __device__ __noinline__ void gs_calc_snow_state(double shape, double scale, doub
     else if (lwd > 0.0) {
         const double sat = lwd / max_water_frac;
         const double x = sat / scale;
-        if (!have_lg) lg = sb_lgamma(shape);
+        if (!have_lg) {
+            if (shape != lg_key) { lg_key = shape; lg_val = sb_lgamma(shape); }
+            lg = lg_val;
+        }
         const double pre = gamma_prefix(shape, x, lg);
         const double ssa = (x == inf_()) ? 1.0 : gamma_p_with_prefix(shape, x, pre);
         const double ssa1 = ssa - pre / shape;
@@ -201,7 +214,7 @@ __device__ __forceinline__ void gs_reset_snow_pack(double& sca, double& lwc, dou
 }
 
 // gamma_snow::calculator::step, gamma_snow.h:291-493
-__device__ __forceinline__ void gs_step(GsState& s, double& r_sca, double& r_storage, double& r_outflow, const PtgskParam& p, int doy,
+__device__ __forceinline__ void gs_step(GsState& s, GsCache& cache, double& r_sca, double& r_storage, double& r_outflow, const PtgskParam& p, int doy,
                                         int sec_of_year, double dt_seconds, double dt_us, double BB0, double T, double rad, double prec_mm_h,
                                         double wind_speed, double rel_hum, double forest_fraction, double altitude) {
     const double tol = 1.0e-10;
@@ -274,7 +287,11 @@ __device__ __forceinline__ void gs_step(GsState& s, double& r_sca, double& r_sto
 
     double sdc_scale = sdc_melt_mean / alpha;
     const double y0 = p.initial_bare_ground_fraction;
-    gs_calc_snow_state(alpha, sdc_scale, y0, acc_melt, lwc, p.max_water, temp_swe, storage, sca);
+    if (alpha == cache.k_alpha && sdc_scale == cache.k_scale && acc_melt == cache.k_acc && lwc == cache.k_lwc && temp_swe == cache.k_tswe) {
+        storage = cache.storage;
+        sca = cache.sca;
+    } else
+        gs_calc_snow_state(alpha, sdc_scale, y0, acc_melt, lwc, p.max_water, temp_swe, storage, sca, cache.lg_key, cache.lg_val);
     const double start_storage_value = storage;
 
     if (acc_melt < 0.0) {  // :414-451
@@ -290,7 +307,7 @@ __device__ __forceinline__ void gs_step(GsState& s, double& r_sca, double& r_sto
                 double z1 = lwc / p.max_water;
                 z1 = gs_corr_lwc(z1, alpha_prev, sdc_scale_prev > 0.0 ? sdc_scale_prev : sdc_scale, alpha, sdc_scale);
                 lwc = z1 * p.max_water;
-                gs_calc_snow_state(alpha, sdc_scale, y0, acc_melt, lwc, p.max_water, temp_swe, storage, sca);
+                gs_calc_snow_state(alpha, sdc_scale, y0, acc_melt, lwc, p.max_water, temp_swe, storage, sca, cache.lg_key, cache.lg_val);
             }
         }
         lwc += rain;
@@ -330,7 +347,9 @@ __device__ __forceinline__ void gs_step(GsState& s, double& r_sca, double& r_sto
             }
         }
     }
-    gs_calc_snow_state(alpha, sdc_scale, y0, acc_melt, lwc, p.max_water, temp_swe, storage, sca);
+    gs_calc_snow_state(alpha, sdc_scale, y0, acc_melt, lwc, p.max_water, temp_swe, storage, sca, cache.lg_key, cache.lg_val);
+    cache.k_alpha = alpha; cache.k_scale = sdc_scale; cache.k_acc = acc_melt; cache.k_lwc = lwc; cache.k_tswe = temp_swe;
+    cache.storage = storage; cache.sca = sca;
 
     outflow = prec + start_storage_value - storage;
     if (outflow < 0.0) outflow = 0.0;
@@ -466,8 +485,15 @@ __device__ __forceinline__ bool kirchner_step(double c1, double c2, double c3, d
 
 // ---- the window kernel ----------------------------------------------------------------------------------
 // COLLECT bits: 1 avg_discharge+charge, 2 snow sca/swe, 4 snow_outflow/glacier_melt/ae/pe, 8 state series
+#ifndef SB2_BLOCK
+#define SB2_BLOCK 32       // threads per block of the cell-step kernels: one warp per block balances the uneven per-cell work best (measured)
+#endif
+#ifndef SB2_MINBLOCKS
+#define SB2_MINBLOCKS 12   // resident blocks per SM the register allocation must allow (<= 168 registers per thread)
+#endif
+
 template <int COLLECT>
-__global__ void __launch_bounds__(128) ptgsk_run_kernel(const PtgskRunArgs a) {
+__global__ void __launch_bounds__(SB2_BLOCK, SB2_MINBLOCKS) ptgsk_run_kernel(const PtgskRunArgs a) {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool in_range = c < a.n_cells;
     const int64_t cc = in_range ? c : a.n_cells - 1;  // out-of-range lanes shadow the last cell, never store
@@ -492,6 +518,8 @@ __global__ void __launch_bounds__(128) ptgsk_run_kernel(const PtgskRunArgs a) {
     gs.sdc_melt_mean = a.state[4 * n + cc]; gs.acc_melt = a.state[5 * n + cc]; gs.iso_pot_energy = a.state[6 * n + cc];
     gs.temp_swe = a.state[7 * n + cc];
     double kq = a.state[8 * n + cc];
+    GsCache cache;
+    gs_cache_clear(cache);
 
     // segmented-reduction bookkeeping: lanes of one slot are contiguous in the warp
     int my_slot = -1;
@@ -528,7 +556,7 @@ __global__ void __launch_bounds__(128) ptgsk_run_kernel(const PtgskRunArgs a) {
                 a.st[8][orow] = gs.temp_swe * snow_storage_fraction;
             }
             double sca, storage, outflow;
-            gs_step(gs, sca, storage, outflow, p, a.day_of_year[step], a.sec_of_year[step], a.dt_seconds, a.dt_us, a.bb0, temp, rad, prec, wind,
+            gs_step(gs, cache, sca, storage, outflow, p, a.day_of_year[step], a.sec_of_year[step], a.dt_seconds, a.dt_us, a.bb0, temp, rad, prec, wind,
                     rel_hum, forest_fraction, altitude);
             // glacier_melt::step, glacier_melt.h:47-52
             const double sca_m2 = cell_area_m2 * sca;

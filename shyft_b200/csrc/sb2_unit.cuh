@@ -20,7 +20,11 @@ __global__ void unit_eval_kernel(int fn, int64_t n, const double* __restrict__ i
         case UNIT_LGAMMA: o[0] = sb_lgamma(a[0]); break;
         case UNIT_GAMMA_P: o[0] = gamma_p(a[0], a[1]); break;
         case UNIT_CORR_LWC: o[0] = gs_corr_lwc(a[0], a[1], a[2], a[3], a[4]); break;
-        case UNIT_CALC_SNOW_STATE: gs_calc_snow_state(a[0], a[1], a[2], a[3], a[4], a[5], a[6], o[0], o[1]); break;
+        case UNIT_CALC_SNOW_STATE: {
+            double lg_key = nan_(), lg_val = 0.0;
+            gs_calc_snow_state(a[0], a[1], a[2], a[3], a[4], a[5], a[6], o[0], o[1], lg_key, lg_val);
+            break;
+        }
         case UNIT_KIRCHNER_STEP: {
             double q = a[4], q_avg = 0.0;
             const bool ok = kirchner_step(a[0], a[1], a[2], a[3], q, q_avg, a[5], a[6]);

@@ -1,0 +1,15 @@
+"""Tuning helper: build variants of the CUDA library with different launch geometry (used with SB2_LIB=... bench.py)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from shyft_b200 import _build
+
+VARIANTS = {"b128": [], "b64m8": ["-DSB2_BLOCK=64", "-DSB2_MINBLOCKS=8"], "b64m10": ["-DSB2_BLOCK=64", "-DSB2_MINBLOCKS=10"],
+            "b32m16": ["-DSB2_BLOCK=32", "-DSB2_MINBLOCKS=16"], "b32m12": ["-DSB2_BLOCK=32", "-DSB2_MINBLOCKS=12"]}
+out_dir = os.path.join(_build.ROOT, "build")
+os.makedirs(out_dir, exist_ok=True)
+names = sys.argv[1:] or list(VARIANTS)
+for name in names:
+    _build.build_library(force=True, extra_flags=VARIANTS[name], output=os.path.join(out_dir, f"libshyft_b200_{name}.so"))
+    print("built", name)
