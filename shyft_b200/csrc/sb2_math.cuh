@@ -40,38 +40,96 @@ SB2_HD double pow2i(int k) { return from_bits((unsigned long long)(k + 1023) << 
 SB2_HD double inf_() { return from_bits(0x7ff0000000000000ULL); }
 SB2_HD double nan_() { return from_bits(0x7ff8000000000000ULL); }
 
-SB2_HD double sb_exp(double x) {
-    if (x != x) return x;
-    if (x > 709.782712893384) return inf_();
-    if (x < -745.1332191019412) return 0.0;
-    const double kf = floor(fma(x, 1.44269504088896338700e+00, 0.5));
-    double r = fma(kf, -6.93147180369123816490e-01, x);
-    r = fma(kf, -1.90821492927058770002e-10, r);
+// Polynomial coefficients.  On the device they live in constant memory so that every fma takes its coefficient as a
+// constant-bank operand (a 64-bit immediate costs two extra moves per use); the host reads the same initialisers.
+#define SB2_EXP_COEFFS {0.5, 1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0, 1.0 / 720.0, 1.0 / 5040.0, 1.0 / 40320.0, 1.0 / 362880.0, 1.0 / 3628800.0, \
+                        1.0 / 39916800.0, 1.0 / 479001600.0, 1.0 / 6227020800.0}
+#define SB2_LOG_COEFFS {2.0 / 3.0, 2.0 / 5.0, 2.0 / 7.0, 2.0 / 9.0, 2.0 / 11.0, 2.0 / 13.0, 2.0 / 15.0, 2.0 / 17.0, 2.0 / 19.0, 2.0 / 21.0}
+#define SB2_MISC_COEFFS {1.44269504088896338700e+00, -6.93147180369123816490e-01, -1.90821492927058770002e-10, 6.93147180369123816490e-01, \
+                         1.90821492927058770002e-10}
+__constant__ double kExpC_dev[12] = SB2_EXP_COEFFS;
+__constant__ double kLogC_dev[10] = SB2_LOG_COEFFS;
+__constant__ double kMiscC_dev[5] = SB2_MISC_COEFFS;
+static const double kExpC_host[12] = SB2_EXP_COEFFS;
+static const double kLogC_host[10] = SB2_LOG_COEFFS;
+static const double kMiscC_host[5] = SB2_MISC_COEFFS;
+#ifdef __CUDA_ARCH__
+#define SB2_EXPC(i) kExpC_dev[i]
+#define SB2_LOGC(i) kLogC_dev[i]
+#define SB2_MISC(i) kMiscC_dev[i]
+#else
+#define SB2_EXPC(i) kExpC_host[i]
+#define SB2_LOGC(i) kLogC_host[i]
+#define SB2_MISC(i) kMiscC_host[i]
+#endif
+
+// reduced argument and polynomial of exp: returns p = exp(r) for x = k*ln2 + r
+SB2_HD double sb_exp_core(double x, int& k) {
+    const double kf = floor(fma(x, SB2_MISC(0), 0.5));
+    double r = fma(kf, SB2_MISC(1), x);
+    r = fma(kf, SB2_MISC(2), r);
     const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
-    const double a0 = fma(1.0 / 6.0, r, 0.5);
-    const double a1 = fma(1.0 / 120.0, r, 1.0 / 24.0);
-    const double a2 = fma(1.0 / 5040.0, r, 1.0 / 720.0);
-    const double a3 = fma(1.0 / 362880.0, r, 1.0 / 40320.0);
-    const double a4 = fma(1.0 / 39916800.0, r, 1.0 / 3628800.0);
-    const double a5 = fma(1.0 / 6227020800.0, r, 1.0 / 479001600.0);
+    const double a0 = fma(SB2_EXPC(1), r, SB2_EXPC(0));
+    const double a1 = fma(SB2_EXPC(3), r, SB2_EXPC(2));
+    const double a2 = fma(SB2_EXPC(5), r, SB2_EXPC(4));
+    const double a3 = fma(SB2_EXPC(7), r, SB2_EXPC(6));
+    const double a4 = fma(SB2_EXPC(9), r, SB2_EXPC(8));
+    const double a5 = fma(SB2_EXPC(11), r, SB2_EXPC(10));
     const double b0 = fma(a1, r2, a0);
     const double b1 = fma(a3, r2, a2);
     const double b2 = fma(a5, r2, a4);
     const double d0 = fma(b1, r4, b0);
     const double Q = fma(b2, r8, d0);
-    double p = 1.0 + fma(r2, Q, r);
-    int k = int(kf);
+    k = int(kf);
+    return 1.0 + fma(r2, Q, r);
+}
+// the general path: NaN, overflow, underflow into the subnormal range
+#ifdef __CUDA_ARCH__
+__device__ __noinline__
+#else
+inline
+#endif
+double sb_exp_slow(double x) {
+    if (x != x) return x;
+    if (x > 709.782712893384) return inf_();
+    if (x < -745.1332191019412) return 0.0;
+    int k;
+    double p = sb_exp_core(x, k);
     if (k > 1023) { p *= pow2i(1023); k -= 1023; }
-    if (k < -1022) { p *= pow2i(k + 1000); return p * pow2i(-1000); }      // one rounding into the subnormal range
+    if (k < -1022) { p *= pow2i(k + 1000); return p * pow2i(-1000); }
     return p * pow2i(k);
 }
+SB2_HD double sb_exp_inl(double x) {
+    if (!(fabs(x) < 690.0)) return sb_exp_slow(x);
+    int k;
+    const double p = sb_exp_core(x, k);
+    // |k| <= 996 and p in (0.7, 1.5): p * 2^k is exact and normal, i.e. an add on the exponent field
+#ifdef __CUDA_ARCH__
+    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+#else
+    return p * pow2i(k);
+#endif
+}
 
-SB2_HD double sb_log(double x) {
+// Out-of-line copies for the device: the cell-step kernels call exp/log from some thirty places; one shared copy of each
+// keeps the step loop inside the instruction cache (inlined everywhere the pt_gs_k kernel was 136 KB of SASS and 22 % of
+// its issue slots stalled on instruction fetch).  SB2_MATH_INLINE=1 restores full inlining (tuning only).
+#ifndef SB2_MATH_INLINE
+#define SB2_MATH_INLINE 0
+#endif
+#if defined(__CUDA_ARCH__) && !SB2_MATH_INLINE
+#define SB2_MATH_FN __device__ __noinline__
+#else
+#define SB2_MATH_FN SB2_HD
+#endif
+SB2_MATH_FN double sb_exp(double x) { return sb_exp_inl(x); }
+
+SB2_MATH_FN double sb_log(double x) {
     if (x != x || x < 0.0) return nan_();
     if (x == 0.0) return -inf_();
     if (x == inf_()) return x;
     int e = 0;
-    if (x < 2.2250738585072014e-308) { x *= 18014398509481984.0; e = -54; }  // subnormal: scale by 2^54
+    if (x < 2.2250738585072014e-308) { x *= 18014398509481984.0; e = -54; }
     const unsigned long long u = bits_of(x);
     e += int((u >> 52) & 0x7ff) - 1023;
     double m = from_bits((u & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL);
@@ -79,19 +137,19 @@ SB2_HD double sb_log(double x) {
     const double f = m - 1.0;
     const double s = f / (2.0 + f);
     const double z = s * s, z2 = z * z, z4 = z2 * z2, z8 = z4 * z4;
-    const double t01 = fma(2.0 / 5.0, z, 2.0 / 3.0);
-    const double t23 = fma(2.0 / 9.0, z, 2.0 / 7.0);
-    const double t45 = fma(2.0 / 13.0, z, 2.0 / 11.0);
-    const double t67 = fma(2.0 / 17.0, z, 2.0 / 15.0);
-    const double t89 = fma(2.0 / 21.0, z, 2.0 / 19.0);
+    const double t01 = fma(SB2_LOGC(1), z, SB2_LOGC(0));
+    const double t23 = fma(SB2_LOGC(3), z, SB2_LOGC(2));
+    const double t45 = fma(SB2_LOGC(5), z, SB2_LOGC(4));
+    const double t67 = fma(SB2_LOGC(7), z, SB2_LOGC(6));
+    const double t89 = fma(SB2_LOGC(9), z, SB2_LOGC(8));
     const double u0 = fma(t23, z2, t01);
     const double u1 = fma(t67, z2, t45);
     const double v0 = fma(u1, z4, u0);
     const double R = z * fma(t89, z8, v0);
     const double hfsq = 0.5 * f * f;
     const double dk = double(e);
-    const double t = fma(s, hfsq + R, dk * 1.90821492927058770002e-10);
-    return fma(dk, 6.93147180369123816490e-01, f - (hfsq - t));
+    const double t = fma(s, hfsq + R, dk * SB2_MISC(4));
+    return fma(dk, SB2_MISC(3), f - (hfsq - t));
 }
 
 SB2_HD double sb_pow(double x, double y) {
@@ -105,7 +163,7 @@ SB2_HD double sb_pow(double x, double y) {
 SB2_HD double sb_pow4(double x) { const double x2 = x * x; return x2 * x2; }
 SB2_HD double sb_pow8(double x) { double y = x * x; y = y * y; return y * y; }
 
-SB2_HD double sb_lgamma(double a) {
+SB2_MATH_FN double sb_lgamma(double a) {
     double prod = 1.0;
     while (a < 12.0) { prod *= a; a += 1.0; }
     const double ai = 1.0 / a, ai2 = ai * ai;

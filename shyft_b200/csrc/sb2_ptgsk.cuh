@@ -387,12 +387,15 @@ __device__ __forceinline__ double pt_potential_evapotranspiration(double land_al
 }
 
 // ---- kirchner, core/kirchner.h:186-235 --------------------------------------------------------------------
+// the right-hand side d ln q / dt (kirchner.h:186-198); out of line so that the seven Runge-Kutta stages share one copy of
+// the two exponentials (the step loop then stays inside the instruction cache)
+__device__ __noinline__ double kirchner_rhs(double c1, double c2, double c3, double pe, double x) {
+    const double g = sb_exp_inl(c1 + c2 * x + c3 * x * x);  // the two exponentials interleave
+    return g >= 1.e-30 ? g * (pe * sb_exp_inl(-x) - 1.0) : 0.0;
+}
 struct KirchnerRhs {
     double c1, c2, c3, pe;  // pe = p - e
-    __device__ __forceinline__ double operator()(double x) const {
-        const double g = sb_exp(c1 + c2 * x + c3 * x * x);
-        return g >= 1.e-30 ? g * (pe * sb_exp(-x) - 1.0) : 0.0;
-    }
+    __device__ __forceinline__ double operator()(double x) const { return kirchner_rhs(c1, c2, c3, pe, x); }
 };
 
 // One model step of the log-transformed Kirchner ODE with odeint's controlled dopri5 + dense output
