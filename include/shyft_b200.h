@@ -153,6 +153,30 @@ int sb2_set_river_network(sb2_model* m, int64_t n_rivers, const double* rivers);
 int sb2_river_flows(sb2_model* m, int64_t rid, int64_t start_step, int64_t n_steps, double* local_inflow, double* upstream_inflow,
                     double* output);
 
+/* ---- calibration: the goal-function entry (core/model_calibration.h:404-900) -------------------------- */
+enum { SB2_GOAL_NASH_SUTCLIFFE = 0, SB2_GOAL_KLING_GUPTA = 1, SB2_GOAL_ABS_DIFF = 2, SB2_GOAL_RMSE = 3 };             /* target_spec_calc_type :217-222 */
+enum { SB2_TARGET_DISCHARGE = 0, SB2_TARGET_SNOW_COVERED_AREA = 1, SB2_TARGET_SNOW_WATER_EQUIVALENT = 2,
+       SB2_TARGET_ROUTED_DISCHARGE = 3, SB2_TARGET_CELL_CHARGE = 4 };                                                  /* target_property_type :225-231 */
+/* target_specification (:242-329).  The target series lives on its own fixed_dt axis, which must be aligned with the model
+ * axis (start on a model step, dt a whole multiple of the model dt, inside the model axis). */
+typedef struct sb2_target {
+    const double* values; int64_t t0_us, dt_us, n;
+    const int64_t* catchment_ids; int32_t n_catchments;
+    int64_t river_id;               /* ROUTED_DISCHARGE only */
+    double scale_factor;
+    int32_t calc_mode, property;
+    double s_r, s_a, s_b;           /* Kling-Gupta weights */
+} sb2_target;
+/* optimizer(model, targets, ...) + prepare_optimize (:517-552): stores the targets, switches snow collection on when a target
+ * needs it, sets the calculation filter to the union of the target catchments, snapshots the initial state if unset. */
+int sb2_set_targets(sb2_model* m, int n_targets, const sb2_target* targets);
+/* optimizer::calculate_goal_function(full parameter vector) (:691-699) = run() (:830-899): set the region parameter, reset the
+ * states, run_cells, evaluate every target, weighted mean. */
+int sb2_calculate_goal_function(sb2_model* m, const double* p, int n, double* goal);
+/* The same for n_sets parameter vectors P [n_sets][parameter_size] at once: the sets form an extra grid dimension of the cell
+ * step kernel and share the forcing reads (the reference evaluates one set at a time, dream_optimizer.cpp:62,201). */
+int sb2_calculate_goal_function_batch(sb2_model* m, int64_t n_sets, const double* P, double* goals);
+
 /* ---- diagnostics ------------------------------------------------------------------------------------- */
 /* Evaluate one device function on n rows of inputs (unit tests in the style of test/gamma_snow_test.cpp, test/kirchner_test.cpp):
  * fn 0 exp(x), 1 log(x), 2 pow(x,y), 3 lgamma(a), 4 gamma_p(a,x), 5 corr_lwc(z1,a1,b1,a2,b2), 6 calc_snow_state(shape,scale,y0,

@@ -334,6 +334,21 @@ int sho_river_flows(int64_t n_riv, const double* rivers, int64_t rid, int64_t n_
     SHO_END
 }
 
+// average_accessor of a stair-case series on an aligned coarser axis (core/time_series.h:202-310,2033-2072): target period i covers
+// source steps [first + i*k, first + (i+1)*k); area accumulates v*dt over the finite steps, tsum their length
+void sho_average_to_axis(const double* v, int64_t n_src, int64_t dt_us, int64_t first, int64_t k, int64_t n_out, double* out) {
+    for (int64_t i = 0; i < n_out; ++i) {
+        double area = 0.0;
+        utctimespan tsum = 0;
+        for (int64_t j = 0; j < k; ++j) {
+            const int64_t s = first + i * k + j;
+            if (s >= n_src) break;
+            if (std::isfinite(v[s])) { area += v[s] * to_seconds(dt_us); tsum += dt_us; }
+        }
+        out[i] = tsum > 0 ? area / to_seconds(tsum) : nan_v;
+    }
+}
+
 // ---- goal functions -----------------------------------------------------------
 double sho_nash_sutcliffe(const double* o, const double* m, int64_t n) { return goal::nash_sutcliffe(o, m, size_t(n)); }
 double sho_rmse(const double* o, const double* m, int64_t n) { return goal::rmse(o, m, size_t(n)); }

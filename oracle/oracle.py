@@ -362,6 +362,14 @@ def river_flows(rivers, rid, cell_discharge, cell_rid, cell_distance, cell_uhg_p
     return out[0], out[1], out[2]
 
 
+def average_to_axis(values, dt_us, first, k, n_out):
+    """True average of a stair-case series over aligned coarser periods (average_accessor semantics)."""
+    v = _f64(values)
+    out = np.zeros(n_out)
+    lib().sho_average_to_axis(_d(v), C.c_int64(v.size), C.c_int64(dt_us), C.c_int64(first), C.c_int64(k), C.c_int64(n_out), _d(out))
+    return out
+
+
 # ---- goal functions -----------------------------------------------------------------------------------
 def nash_sutcliffe(o, m):
     o, m = _f64(o), _f64(m)

@@ -8,3 +8,4 @@ from .capi import (COLLECT_ALL, COLLECT_DISCHARGE, COLLECT_NONE, COLLECT_SNOW, C
                    InterpolationParameter)
 from .region_model import (HbvStackModel, HbvStackOptModel, PTGSKModel, PTGSKOptModel, PTHSKModel, PTHSKOptModel, RegionEnvironment,  # noqa: F401
                            RegionModel, TimeAxis, geo_cell_data_vector)
+from .calibration import Optimizer, TargetSpecification  # noqa: F401,E402

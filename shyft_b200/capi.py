@@ -53,6 +53,13 @@ class InterpolationParameter(C.Structure):
             setattr(self, k, v)
 
 
+class Target(C.Structure):
+    """sb2_target: target_specification (core/model_calibration.h:242-329)"""
+    _fields_ = [("values", c_dp), ("t0_us", C.c_int64), ("dt_us", C.c_int64), ("n", C.c_int64), ("catchment_ids", c_i64p),
+                ("n_catchments", C.c_int32), ("river_id", C.c_int64), ("scale_factor", C.c_double), ("calc_mode", C.c_int32),
+                ("property", C.c_int32), ("s_r", C.c_double), ("s_a", C.c_double), ("s_b", C.c_double)]
+
+
 EXPORTS = """sb2_interpolation_parameter_default sb2_model_create sb2_model_destroy sb2_last_error sb2_version sb2_size
 sb2_number_of_catchments sb2_catchment_ids sb2_cell_catchment_ix sb2_parameter_size sb2_state_size sb2_set_region_parameter
 sb2_get_region_parameter sb2_set_catchment_parameter sb2_get_catchment_parameter sb2_remove_catchment_parameter
@@ -60,7 +67,7 @@ sb2_has_catchment_parameter sb2_set_catchment_calculation_filter sb2_set_states 
 sb2_get_initial_state sb2_revert_to_initial_state sb2_adjust_q sb2_set_collector_mode sb2_initialize_cell_environment
 sb2_set_cell_forcing sb2_get_cell_forcing sb2_set_sources sb2_interpolate sb2_is_cell_env_ts_ok sb2_run_cells sb2_run_windowed
 sb2_get_response sb2_get_state_series sb2_catchment_discharges sb2_catchment_charges sb2_set_river_network sb2_river_flows
-sb2_unit_eval sb2_set_stream sb2_device_catchment_discharges sb2_device_catchment_charges sb2_kernel_launches sb2_last_run_kernel_ms""".split()
+sb2_set_targets sb2_calculate_goal_function sb2_calculate_goal_function_batch sb2_unit_eval sb2_set_stream sb2_device_catchment_discharges sb2_device_catchment_charges sb2_kernel_launches sb2_last_run_kernel_ms""".split()
 
 _LIB = None
 

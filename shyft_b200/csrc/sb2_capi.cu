@@ -20,8 +20,12 @@
 #include "sb2_hbv.cuh"
 #include "sb2_routing.cuh"
 #include "sb2_unit.cuh"
+#include "sb2_goal.cuh"
 
 using namespace sb2;
+
+extern "C" int sb2_river_flows(sb2_model* m, int64_t rid, int64_t start_step, int64_t n_steps, double* local_inflow, double* upstream_inflow,
+                               double* output);
 
 namespace {
 
@@ -147,6 +151,20 @@ struct sb2_model {
     DevArray<int> d_error_flag;
     // routing (core/routing.h)
     std::vector<double> rivers;  // [n][6] id downstream distance velocity alpha beta
+    // calibration targets (core/model_calibration.h:242-329)
+    struct Target {
+        std::vector<double> obs;
+        int64_t t0 = 0, dt = 0;
+        std::vector<int64_t> cids;
+        int64_t river_id = 0;
+        double scale_factor = 1.0;
+        int calc_mode = 0, property = 0;
+        double s_r = 1.0, s_a = 1.0, s_b = 1.0;
+        DevArray<double> d_obs, d_series;
+        DevArray<int32_t> d_cix;
+    };
+    std::vector<std::unique_ptr<Target>> targets;
+    DevArray<int32_t> d_cell_ptr, d_cell_of_catch;  // cells grouped by catchment (area-weighted snow means)
     // bookkeeping
     int64_t launches = 0;
     float last_step_ms = 0.f, last_interp_ms = 0.f;
@@ -364,7 +382,7 @@ void launch_step_range(sb2_model* m, int64_t first, int64_t n_steps, bool collec
         CUDA_OK(cudaGetLastError());
         const int64_t total = int64_t(chunk) * m->n_catch();
         catchment_reduce_kernel<<<grid_for(total, 256), 256, 0, m->stream>>>(m->d_partial.p, m->n_slots, m->d_cat_ptr.p, m->d_cat_slots.p,
-                                                                              int(m->n_catch()), chunk, m->d_cq.p, m->d_cc.p, s0);
+                                                                              int(m->n_catch()), chunk, m->d_cq.p, m->d_cc.p, s0, 0, 0);
         CUDA_OK(cudaGetLastError());
         m->launches += 2;
     }
@@ -647,6 +665,154 @@ float time_end(sb2_model* m, int a, int b) {
     float ms = 0.f;
     CUDA_OK(cudaEventElapsedTime(&ms, m->ev[a], m->ev[b]));
     return ms;
+}
+
+// ---- calibration goal function (core/model_calibration.h:830-899) ---------------------------------------------------------
+void build_goal_targets(sb2_model* m, std::vector<GoalTarget>& gt, const double* cq, const double* cc, int64_t ens_stride) {
+    gt.clear();
+    for (auto& tp : m->targets) {
+        sb2_model::Target& t = *tp;
+        GoalTarget g{};
+        g.obs = t.d_obs.p;
+        g.first_step = (t.t0 - m->t0) / m->dt;
+        g.steps_per_period = int32_t(t.dt / m->dt);
+        g.n = int32_t(t.obs.size());
+        g.calc_mode = t.calc_mode;
+        g.s_r = t.s_r; g.s_a = t.s_a; g.s_b = t.s_b;
+        g.dt_seconds = double(m->dt) / 1e6;
+        if (t.property == SB2_TARGET_DISCHARGE || t.property == SB2_TARGET_CELL_CHARGE) {
+            g.series = t.property == SB2_TARGET_DISCHARGE ? cq : cc;
+            g.ens_stride = ens_stride;
+            g.n_col = int32_t(m->n_catch());
+            g.cix = t.d_cix.p;
+            g.n_cix = int32_t(t.cids.size());
+        } else {  // a per-target series [T][1] prepared by the caller
+            g.series = t.d_series.p;
+            g.ens_stride = 0;
+            g.n_col = 1;
+            g.cix = t.d_cix.p;  // holds a single 0
+            g.n_cix = 1;
+        }
+        gt.push_back(g);
+    }
+}
+
+// weighted mean over the targets with a finite partial value (:881-887)
+double combine_goal(const sb2_model* m, const double* partial) {
+    double goal = 0.0, scale_sum = 0.0;
+    for (size_t k = 0; k < m->targets.size(); ++k)
+        if (std::isfinite(partial[k])) { scale_sum += m->targets[k]->scale_factor; goal += m->targets[k]->scale_factor * partial[k]; }
+    return goal / scale_sum;
+}
+
+void prepare_snow_and_routed_targets(sb2_model* m) {
+    for (auto& tp : m->targets) {
+        sb2_model::Target& t = *tp;
+        if (t.property == SB2_TARGET_SNOW_COVERED_AREA || t.property == SB2_TARGET_SNOW_WATER_EQUIVALENT) {
+            const int r = t.property == SB2_TARGET_SNOW_COVERED_AREA ? SB2_R_SNOW_SCA : SB2_R_SNOW_SWE;
+            if (!m->d_resp[r].p || m->out_first != 0 || m->out_rows != m->T) throw Error(r == SB2_R_SNOW_SCA ? "resource collector doesn't have snow_sca" : "resource collector doesn't have snow_swe");
+            // area-weighted mean over all cells of the target's catchments (:765-790)
+            std::vector<int32_t> cells;
+            for (int64_t i = 0; i < m->n; ++i)
+                for (auto cid : t.cids)
+                    if (m->geo[i].catchment_id == cid) { cells.push_back(int32_t(i)); break; }
+            std::vector<int32_t> ptr{0, int32_t(cells.size())};
+            DevArray<int32_t> d_ptr, d_cells;
+            d_ptr.upload(ptr, m->stream);
+            d_cells.upload(cells, m->stream);
+            t.d_series.resize(size_t(m->T));
+            catchment_area_mean_kernel<<<grid_for(m->T, 256), 256, 0, m->stream>>>(m->d_resp[r].p, m->d_area.p, d_ptr.p, d_cells.p, 1, m->T, m->n,
+                                                                                  t.d_series.p);
+            CUDA_OK(cudaGetLastError());
+            ++m->launches;
+            CUDA_OK(cudaStreamSynchronize(m->stream));
+        } else if (t.property == SB2_TARGET_ROUTED_DISCHARGE) {
+            std::vector<double> out(size_t(m->T));
+            if (sb2_river_flows(m, t.river_id, 0, m->T, nullptr, nullptr, out.data()) != 0) throw Error(m->err);
+            t.d_series.upload(out, m->stream);
+            CUDA_OK(cudaStreamSynchronize(m->stream));
+        }
+    }
+}
+
+double evaluate_goal_single(sb2_model* m) {
+    prepare_snow_and_routed_targets(m);
+    std::vector<GoalTarget> gt;
+    build_goal_targets(m, gt, m->d_cq.p, m->d_cc.p, 0);
+    DevArray<GoalTarget> d_gt;
+    DevArray<double> d_out;
+    d_gt.upload(gt, m->stream);
+    d_out.resize(gt.size());
+    goal_kernel<<<dim3((unsigned)gt.size(), 1), 256, 0, m->stream>>>(d_gt.p, int(gt.size()), m->T, d_out.p);
+    CUDA_OK(cudaGetLastError());
+    ++m->launches;
+    std::vector<double> partial(gt.size());
+    CUDA_OK(cudaMemcpyAsync(partial.data(), d_out.p, partial.size() * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+    CUDA_OK(cudaStreamSynchronize(m->stream));
+    return combine_goal(m, partial.data());
+}
+
+// ensemble of region-parameter sets for pt_gs_k: member e = blockIdx.y steps its own copy of the state; the forcing reads are shared
+void goal_batch_ptgsk(sb2_model* m, int64_t n_sets, const double* P, double* goals) {
+    sync_parameters(m);
+    sync_filter(m);
+    const int64_t n = m->n, T = m->T, nc = m->n_catch();
+    const size_t state_sz = size_t(m->n_state) * n;
+    // members per pass from a ~12 GB budget: state + catchment series (discharge, charge)
+    const size_t per_member = state_sz * 8 + size_t(T) * nc * 16;
+    const int64_t E = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(n_sets, 65535), int64_t((12ULL << 30) / per_member)));
+    const int64_t ps = std::max<int64_t>(1, std::min<int64_t>(T, int64_t((1ULL << 30) / (size_t(E) * m->n_slots * 16))));
+    DevArray<double> d_state, d_partial, d_cq, d_cc, d_out;
+    DevArray<PtgskParam> d_par;
+    DevArray<GoalTarget> d_gt;
+    d_state.resize(size_t(E) * state_sz);
+    d_partial.resize(size_t(E) * ps * m->n_slots * 2);
+    d_cq.resize(size_t(E) * T * nc);
+    d_cc.resize(size_t(E) * T * nc);
+    d_out.resize(size_t(E) * m->targets.size());
+    std::vector<GoalTarget> gt;
+    build_goal_targets(m, gt, d_cq.p, d_cc.p, T * nc);
+    d_gt.upload(gt, m->stream);
+    const double dt_seconds = double(m->dt) / 1e6;
+    std::vector<double> partial(size_t(E) * gt.size());
+    for (int64_t e0 = 0; e0 < n_sets; e0 += E) {
+        const int64_t ne = std::min<int64_t>(E, n_sets - e0);
+        std::vector<PtgskParam> tab;
+        for (int64_t e = 0; e < ne; ++e) tab.push_back(make_ptgsk_param(P + (e0 + e) * m->n_param, m->dt));
+        d_par.upload(tab, m->stream);
+        for (int64_t e = 0; e < ne; ++e)  // reset_states(): every member starts from the initial state (:833)
+            CUDA_OK(cudaMemcpyAsync(d_state.p + e * state_sz, m->d_initial_state.p, state_sz * sizeof(double), cudaMemcpyDeviceToDevice, m->stream));
+        for (int64_t done = 0; done < T; done += ps) {
+            const int chunk = int(std::min<int64_t>(ps, T - done));
+            PtgskRunArgs a{};
+            a.n_cells = n;
+            a.z = m->d_z.p; a.area = m->d_area.p; a.glacier = m->d_glacier.p; a.lake = m->d_lake.p; a.reservoir = m->d_reservoir.p;
+            a.forest = m->d_forest.p; a.pset = m->d_pset.p; a.active = m->d_active.p; a.params = m->d_ptgsk_params.p;
+            a.state = d_state.p;
+            for (int v = 0; v < 5; ++v) a.f[v] = m->d_forcing[v].p + done * n;
+            a.n_steps = chunk; a.first_step = done;
+            a.dt_seconds = dt_seconds; a.dt_hours = dt_seconds / 3600.0; a.dt_us = double(m->dt);
+            a.bb0 = 0.98 * 5.670373e-8 * sb_pow4(273.15);
+            a.day_of_year = m->d_doy.p; a.sec_of_year = m->d_soy.p;
+            a.out_first_step = 0; a.collect_end_state = 0;
+            a.slot = m->d_slot.p; a.partial = d_partial.p; a.n_slots = m->n_slots; a.error_flag = m->d_error_flag.p;
+            a.ens_params = d_par.p; a.ens_state_stride = int64_t(state_sz); a.ens_partial_stride = ps * m->n_slots * 2;
+            ptgsk_run_kernel<0><<<dim3((unsigned)grid_for(n, SB2_BLOCK), (unsigned)ne), SB2_BLOCK, 0, m->stream>>>(a);
+            CUDA_OK(cudaGetLastError());
+            const int64_t total = int64_t(chunk) * nc;
+            catchment_reduce_kernel<<<dim3((unsigned)grid_for(total, 256), (unsigned)ne), 256, 0, m->stream>>>(
+                d_partial.p, m->n_slots, m->d_cat_ptr.p, m->d_cat_slots.p, int(nc), chunk, d_cq.p, d_cc.p, done, ps * m->n_slots * 2, T * nc);
+            CUDA_OK(cudaGetLastError());
+            m->launches += 2;
+        }
+        goal_kernel<<<dim3((unsigned)gt.size(), (unsigned)ne), 256, 0, m->stream>>>(d_gt.p, int(gt.size()), T, d_out.p);
+        CUDA_OK(cudaGetLastError());
+        ++m->launches;
+        CUDA_OK(cudaMemcpyAsync(partial.data(), d_out.p, size_t(ne) * gt.size() * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+        CUDA_OK(cudaStreamSynchronize(m->stream));
+        for (int64_t e = 0; e < ne; ++e) goals[e0 + e] = combine_goal(m, partial.data() + e * gt.size());
+    }
+    check_device_errors(m);
 }
 
 }  // namespace
@@ -1154,6 +1320,96 @@ int sb2_river_flows(sb2_model* m, int64_t rid, int64_t start_step, int64_t n_ste
         }
         route_rivers(m->rivers, rid, cell_routing, m->n, m->T, m->dt, m->d_resp[SB2_R_AVG_DISCHARGE].p, m->stream, &m->launches, start_step,
                      n_steps, local_inflow, upstream_inflow, output);
+    });
+}
+
+// ---- calibration (core/model_calibration.h) --------------------------------------------------------------------------------
+int sb2_set_targets(sb2_model* m, int n_targets, const sb2_target* targets) {
+    return guarded(m, [&] {
+        if (!(m->T > 0)) throw Error("initialize_cell_environment has not been called");
+        std::vector<std::unique_ptr<sb2_model::Target>> out;
+        std::vector<int64_t> filter;
+        bool need_snow = false;
+        for (int k = 0; k < n_targets; ++k) {
+            const sb2_target& s = targets[k];
+            auto t = std::make_unique<sb2_model::Target>();
+            if (s.n <= 0 || !s.values) throw Error("target_specification: empty target time-series");
+            if (s.calc_mode < 0 || s.calc_mode > 3 || s.property < 0 || s.property > 4) throw Error("target_specification: unknown calc_mode or property");
+            if (s.dt_us <= 0 || s.dt_us % m->dt != 0 || (s.t0_us - m->t0) % m->dt != 0 || s.t0_us < m->t0 ||
+                (s.t0_us - m->t0) / m->dt + int64_t(s.n) * (s.dt_us / m->dt) > m->T)
+                throw Error("target_specification: the target time-axis must be aligned with, and inside, the model time-axis");
+            if (s.property == SB2_TARGET_CELL_CHARGE && s.calc_mode == SB2_GOAL_ABS_DIFF)
+                throw Error("target_specification: ABS_DIFF on CELL_CHARGE (scaled variant) is not supported");
+            t->obs.assign(s.values, s.values + s.n);
+            t->t0 = s.t0_us; t->dt = s.dt_us;
+            t->cids.assign(s.catchment_ids, s.catchment_ids + s.n_catchments);
+            t->river_id = s.river_id; t->scale_factor = s.scale_factor; t->calc_mode = s.calc_mode; t->property = s.property;
+            t->s_r = s.s_r; t->s_a = s.s_a; t->s_b = s.s_b;
+            std::vector<int32_t> cix;
+            if (s.property == SB2_TARGET_ROUTED_DISCHARGE) {
+                cix.push_back(0);
+                // catchments feeding the river (and its upstreams) are calculated (model_calibration.h:536-539)
+                for (int64_t i = 0; i < m->n; ++i)
+                    if (m->geo[i].routing_id > 0) filter.push_back(m->geo[i].catchment_id);
+            } else {
+                if (s.n_catchments <= 0) throw Error("target_specification: no catchment ids");
+                for (auto cid : t->cids) {
+                    auto f = m->cid_to_cix.find(cid);
+                    if (f == m->cid_to_cix.end()) throw Error("target_specification: catchment id " + std::to_string(cid) + " not found");
+                    if (m->catch_param.count(cid)) throw Error("Cannot calibrate on local parameters.");
+                    cix.push_back(int32_t(f->second));
+                    filter.push_back(cid);
+                }
+                if (s.property == SB2_TARGET_SNOW_COVERED_AREA || s.property == SB2_TARGET_SNOW_WATER_EQUIVALENT) {
+                    need_snow = true;
+                    cix.assign(1, 0);
+                }
+            }
+            t->d_obs.upload(t->obs, m->stream);
+            t->d_cix.upload(cix, m->stream);
+            out.push_back(std::move(t));
+        }
+        CUDA_OK(cudaStreamSynchronize(m->stream));
+        m->targets = std::move(out);
+        // prepare_optimize (:517-552): snow collection on when a target asks for it, calculation filter = union of target catchments
+        if (need_snow && !(m->collect_bits & SB2_COLLECT_SNOW)) { free_series(m); m->collect_bits |= SB2_COLLECT_SNOW; }
+        std::sort(filter.begin(), filter.end());
+        filter.erase(std::unique(filter.begin(), filter.end()), filter.end());
+        if (!filter.empty()) {
+            m->catchment_filter.assign(m->n_catch(), 0);
+            for (auto cid : filter) m->catchment_filter[m->cid_to_cix[cid]] = 1;
+            m->filter_dirty = true;
+        }
+        snapshot_initial_state_if_unset(m);
+    });
+}
+
+int sb2_calculate_goal_function(sb2_model* m, const double* p, int n, double* goal) {
+    if (m && sb2_set_region_parameter(m, p, n) != 0) return 1;
+    if (m && sb2_revert_to_initial_state(m) != 0) return 1;
+    if (m && sb2_run_cells(m, 0, 0) != 0) return 1;
+    return guarded(m, [&] {
+        if (m->targets.empty()) throw Error("no target specification set");
+        *goal = evaluate_goal_single(m);
+    });
+}
+
+int sb2_calculate_goal_function_batch(sb2_model* m, int64_t n_sets, const double* P, double* goals) {
+    return guarded(m, [&] {
+        if (m->targets.empty()) throw Error("no target specification set");
+        if (n_sets <= 0) return;
+        bool device_batch = m->stack == SB2_PT_GS_K;
+        for (auto& t : m->targets)
+            if (t->property != SB2_TARGET_DISCHARGE && t->property != SB2_TARGET_CELL_CHARGE) device_batch = false;
+        if (device_batch) {
+            if (!m->has_initial) throw Error("Initial state not yet established or set");
+            if (!m->d_forcing[0].p || m->forcing_first != 0 || m->forcing_rows != m->T)
+                throw Error("run_cells: cell environment is not resident for the whole time axis (use interpolate / set_cell_forcing, or run_windowed)");
+            goal_batch_ptgsk(m, n_sets, P, goals);
+        } else {  // one member at a time through the single-evaluation entry
+            for (int64_t e = 0; e < n_sets; ++e)
+                if (sb2_calculate_goal_function(m, P + e * m->n_param, m->n_param, goals + e) != 0) throw Error(m->err);
+        }
     });
 }
 

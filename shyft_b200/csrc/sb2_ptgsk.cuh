@@ -77,6 +77,10 @@ struct PtgskRunArgs {
     double* __restrict__ partial;
     int64_t n_slots;
     int* __restrict__ error_flag;
+    // parameter-set ensemble (calibration): blockIdx.y = member; member e steps its own state / partial sums with the
+    // region parameter replaced by ens_params[e] (cells with a catchment override keep it, model_calibration.h:830-832)
+    const PtgskParam* __restrict__ ens_params;  // null = no ensemble
+    int64_t ens_state_stride, ens_partial_stride;
 };
 
 struct GsState { double albedo, lwc, surface_heat, alpha, sdc_melt_mean, acc_melt, iso_pot_energy, temp_swe; };
@@ -503,7 +507,10 @@ __global__ void __launch_bounds__(SB2_BLOCK, SB2_MINBLOCKS) ptgsk_run_kernel(con
     const bool active = in_range && (a.active == nullptr || a.active[cc] != 0);
     const unsigned lane = threadIdx.x & 31u;
 
-    const PtgskParam& p = a.params[a.pset[cc]];
+    const int ens = blockIdx.y;
+    const PtgskParam& p = (a.ens_params != nullptr && a.pset[cc] == 0) ? a.ens_params[ens] : a.params[a.pset[cc]];
+    double* __restrict__ state = a.state + (int64_t)ens * a.ens_state_stride;
+    double* __restrict__ partial = a.partial != nullptr ? a.partial + (int64_t)ens * a.ens_partial_stride : nullptr;
     const double altitude = a.z[cc], cell_area_m2 = a.area[cc];
     const double glacier_fraction = a.glacier[cc], lake = a.lake[cc], reservoir = a.reservoir[cc], forest_fraction = a.forest[cc];
     // run_pt_gs_k prologue, pt_gs_k.h:347-357
@@ -517,17 +524,17 @@ __global__ void __launch_bounds__(SB2_BLOCK, SB2_MINBLOCKS) ptgsk_run_kernel(con
 
     const int64_t n = a.n_cells;
     GsState gs;
-    gs.albedo = a.state[0 * n + cc]; gs.lwc = a.state[1 * n + cc]; gs.surface_heat = a.state[2 * n + cc]; gs.alpha = a.state[3 * n + cc];
-    gs.sdc_melt_mean = a.state[4 * n + cc]; gs.acc_melt = a.state[5 * n + cc]; gs.iso_pot_energy = a.state[6 * n + cc];
-    gs.temp_swe = a.state[7 * n + cc];
-    double kq = a.state[8 * n + cc];
+    gs.albedo = state[0 * n + cc]; gs.lwc = state[1 * n + cc]; gs.surface_heat = state[2 * n + cc]; gs.alpha = state[3 * n + cc];
+    gs.sdc_melt_mean = state[4 * n + cc]; gs.acc_melt = state[5 * n + cc]; gs.iso_pot_energy = state[6 * n + cc];
+    gs.temp_swe = state[7 * n + cc];
+    double kq = state[8 * n + cc];
     GsCache cache;
     gs_cache_clear(cache);
 
     // segmented-reduction bookkeeping: lanes of one slot are contiguous in the warp
     int my_slot = -1;
     bool head = false;
-    if (a.partial != nullptr) {
+    if (partial != nullptr) {
         my_slot = in_range ? a.slot[cc] : -1;
         const int prev = __shfl_up_sync(0xffffffffu, my_slot, 1);
         head = in_range && (lane == 0 || prev != my_slot);
@@ -589,7 +596,7 @@ __global__ void __launch_bounds__(SB2_BLOCK, SB2_MINBLOCKS) ptgsk_run_kernel(con
                 a.resp[7][orow] = pot;
             }
         }
-        if (a.partial != nullptr) {  // warp-uniform
+        if (partial != nullptr) {  // warp-uniform
             double v0 = out_q, v1 = out_charge;
 #pragma unroll
             for (int off = 1; off < 32; off <<= 1) {
@@ -599,7 +606,7 @@ __global__ void __launch_bounds__(SB2_BLOCK, SB2_MINBLOCKS) ptgsk_run_kernel(con
                 if (lane + off < 32 && os == my_slot) { v0 += o0; v1 += o1; }
             }
             if (head) {
-                double* dst = a.partial + ((int64_t)i * a.n_slots + my_slot) * 2;
+                double* dst = partial + ((int64_t)i * a.n_slots + my_slot) * 2;
                 dst[0] = v0;
                 dst[1] = v1;
             }
@@ -618,9 +625,9 @@ __global__ void __launch_bounds__(SB2_BLOCK, SB2_MINBLOCKS) ptgsk_run_kernel(con
             a.st[7][orow] = gs.iso_pot_energy;
             a.st[8][orow] = gs.temp_swe * snow_storage_fraction;
         }
-        a.state[0 * n + cc] = gs.albedo; a.state[1 * n + cc] = gs.lwc; a.state[2 * n + cc] = gs.surface_heat; a.state[3 * n + cc] = gs.alpha;
-        a.state[4 * n + cc] = gs.sdc_melt_mean; a.state[5 * n + cc] = gs.acc_melt; a.state[6 * n + cc] = gs.iso_pot_energy;
-        a.state[7 * n + cc] = gs.temp_swe; a.state[8 * n + cc] = kq;
+        state[0 * n + cc] = gs.albedo; state[1 * n + cc] = gs.lwc; state[2 * n + cc] = gs.surface_heat; state[3 * n + cc] = gs.alpha;
+        state[4 * n + cc] = gs.sdc_melt_mean; state[5 * n + cc] = gs.acc_melt; state[6 * n + cc] = gs.iso_pot_energy;
+        state[7 * n + cc] = gs.temp_swe; state[8 * n + cc] = kq;
         if (failed) atomicOr(a.error_flag, ERR_KIRCHNER_STEP);
     }
 }
@@ -628,9 +635,12 @@ __global__ void __launch_bounds__(SB2_BLOCK, SB2_MINBLOCKS) ptgsk_run_kernel(con
 // catchment sums: out[(step) * n_catch + k] = sum of the slots of catchment k, in slot order (fixed -> deterministic)
 __global__ void catchment_reduce_kernel(const double* __restrict__ partial, int64_t n_slots, const int32_t* __restrict__ cat_ptr,
                                         const int32_t* __restrict__ cat_slots, int n_catch, int n_steps, double* __restrict__ out_q,
-                                        double* __restrict__ out_charge, int64_t out_row0) {
+                                        double* __restrict__ out_charge, int64_t out_row0, int64_t ens_partial_stride, int64_t ens_out_stride) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)n_steps * n_catch) return;
+    partial += (int64_t)blockIdx.y * ens_partial_stride;  // blockIdx.y = ensemble member
+    out_q += (int64_t)blockIdx.y * ens_out_stride;
+    out_charge += (int64_t)blockIdx.y * ens_out_stride;
     const int i = int(idx / n_catch), k = int(idx % n_catch);
     double s0 = 0.0, s1 = 0.0;
     for (int j = cat_ptr[k]; j < cat_ptr[k + 1]; ++j) {

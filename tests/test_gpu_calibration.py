@@ -1,0 +1,113 @@
+"""GPU parity of the calibration goal-function entry (model_calibration.h:691-699, 830-899) and of its batched form
+(BASELINE config 5 shape: parameter-set ensemble x catchment x hourly steps, NSE goal)."""
+import numpy as np
+import pytest
+
+from fixtures import FORCING, PTGSK_DEFAULT, geo_matrix
+from parity import assert_parity
+
+pytestmark = pytest.mark.gpu
+DAY = 86400
+
+
+@pytest.fixture(scope="module")
+def sb():
+    import shyft_b200
+    return shyft_b200
+
+
+@pytest.fixture(scope="module")
+def setup(sb, oracle):
+    from shyft_b200 import synthetic
+    n, T, S = 240, 24 * 60, 9
+    geo, ta, env = synthetic.make_region(n, T, S, config_index=4, cells_per_catchment=80, start=1425168000)  # 2015-03-01: melt season
+    st0 = synthetic.default_state(0, n)
+    m = sb.PTGSKOptModel(geo, PTGSK_DEFAULT)
+    m.run_interpolation(sb.InterpolationParameter(), ta, env)
+    m.set_states(st0)
+    f = {k: m.cell_forcing(k) for k in FORCING}
+    gm = geo_matrix(geo)
+    # the "observed" series: the default-parameter run of catchments 1+2, daily means (twin experiment, test/calibration_test.cpp:337-559)
+    truth = oracle.ptgsk_run_cells(gm, PTGSK_DEFAULT, f, st0, ta.start * 10**6, 3600 * 10**6, ncore=8)
+    sel = np.isin(gm[:, 4], [1, 2])
+    obs_daily = oracle.average_to_axis(truth["avg_discharge"][:, sel].sum(axis=1), 3600 * 10**6, 0, 24, 60)
+    return m, geo, gm, ta, st0, f, obs_daily, sel
+
+
+def _oracle_goal(oracle, gm, ta, st0, f, p, sel, obs, mode):
+    run = oracle.ptgsk_run_cells(gm, p, f, st0, ta.start * 10**6, 3600 * 10**6, ncore=8)
+    sim = oracle.average_to_axis(run["avg_discharge"][:, sel].sum(axis=1), 3600 * 10**6, 0, 24, obs.size)
+    return {0: oracle.nash_sutcliffe, 1: oracle.kling_gupta, 2: oracle.abs_diff_sum, 3: oracle.rmse}[mode](obs, sim)
+
+
+def _perturbed(rng, k):
+    P = np.tile(PTGSK_DEFAULT, (k, 1))
+    P[:, 0] = rng.uniform(-3.0, -1.9, k)      # kirchner.c1
+    P[:, 1] = rng.uniform(0.8, 0.99, k)       # c2
+    P[:, 2] = rng.uniform(-0.15, -0.05, k)    # c3
+    P[:, 3] = rng.uniform(0.5, 2.5, k)        # ae scale
+    P[:, 4] = rng.uniform(-2.0, 2.0, k)       # tx
+    P[:, 5] = rng.uniform(1.0, 4.0, k)        # wind scale
+    P[:, 14] = rng.uniform(0.2, 0.8, k)       # snow cv
+    P[:, 16] = rng.uniform(0.8, 1.4, k)       # p_corr
+    return P
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+def test_goal_function_matches_the_reference_formulas(sb, oracle, setup, mode):
+    m, geo, gm, ta, st0, f, obs, sel = setup
+    opt = sb.Optimizer(m, [sb.TargetSpecification(obs, ta.start, DAY, [1, 2], 1.0, mode)])
+    assert opt.calculate_goal_function(PTGSK_DEFAULT) == pytest.approx(0.0, abs=1e-9)  # the twin reproduces itself
+    p = _perturbed(np.random.default_rng(mode), 1)[0]
+    got = opt.calculate_goal_function(p)
+    want = _oracle_goal(oracle, gm, ta, st0, f, p, sel, obs, mode)
+    assert got == pytest.approx(want, rel=1e-9)
+    # the calculation filter is the union of the target catchments (prepare_optimize, :517-552): catchment 3 is not stepped
+    assert np.all(m.catchment_discharges()[:, 2] == 0.0)
+
+
+def test_weighted_multi_target_goal_with_missing_observations(sb, oracle, setup):
+    m, geo, gm, ta, st0, f, obs, sel = setup
+    obs2 = obs.copy()
+    obs2[7:11] = np.nan
+    sel3 = gm[:, 4] == 3
+    truth3 = oracle.ptgsk_run_cells(gm, PTGSK_DEFAULT, f, st0, ta.start * 10**6, 3600 * 10**6, ncore=8)["avg_discharge"][:, sel3].sum(axis=1)
+    obs3 = oracle.average_to_axis(truth3, 3600 * 10**6, 24 * 10, 6, 100)  # 6-hourly target starting on day 10
+    targets = [sb.TargetSpecification(obs2, ta.start, DAY, [1, 2], 2.0, 0),
+               sb.TargetSpecification(obs3, ta.start + 10 * DAY, 6 * 3600, [3], 0.5, 1, s_r=1.0, s_a=0.5, s_b=2.0)]
+    opt = sb.Optimizer(m, targets)
+    p = _perturbed(np.random.default_rng(9), 1)[0]
+    got = opt.calculate_goal_function(p)
+    run = oracle.ptgsk_run_cells(gm, p, f, st0, ta.start * 10**6, 3600 * 10**6, ncore=8)["avg_discharge"]
+    g1 = oracle.nash_sutcliffe(obs2, oracle.average_to_axis(run[:, sel].sum(axis=1), 3600 * 10**6, 0, 24, 60))
+    g2 = oracle.kling_gupta(obs3, oracle.average_to_axis(run[:, sel3].sum(axis=1), 3600 * 10**6, 240, 6, 100), 1.0, 0.5, 2.0)
+    assert got == pytest.approx((2.0 * g1 + 0.5 * g2) / 2.5, rel=1e-9)
+    with pytest.raises(RuntimeError, match="aligned"):
+        sb.Optimizer(m, [sb.TargetSpecification(obs, ta.start + 1800, DAY, [1])])
+    with pytest.raises(RuntimeError, match="not found"):
+        sb.Optimizer(m, [sb.TargetSpecification(obs, ta.start, DAY, [77])])
+
+
+def test_batched_ensemble_equals_one_at_a_time(sb, oracle, setup):
+    m, geo, gm, ta, st0, f, obs, sel = setup
+    opt = sb.Optimizer(m, [sb.TargetSpecification(obs, ta.start, DAY, [1, 2], 1.0, 0)])
+    P = _perturbed(np.random.default_rng(21), 37)
+    batch = opt.calculate_goal_function_batch(P)
+    single = np.array([opt.calculate_goal_function(p) for p in P])
+    assert np.array_equal(batch, single)  # same kernels, same order of operations per member
+    for i in (0, 17, 36):
+        assert batch[i] == pytest.approx(_oracle_goal(oracle, gm, ta, st0, f, P[i], sel, obs, 0), rel=1e-9)
+    assert np.argmin(batch) == np.argmin(single)
+
+
+def test_snow_targets_use_area_weighted_catchment_means(sb, oracle, setup):
+    m, geo, gm, ta, st0, f, obs, sel = setup
+    truth = oracle.ptgsk_run_cells(gm, PTGSK_DEFAULT, f, st0, ta.start * 10**6, 3600 * 10**6, ncore=8)
+    area = gm[:, 3]
+    swe_obs = oracle.average_to_axis((truth["snow_swe"][:, sel] * area[sel]).sum(axis=1) / area[sel].sum(), 3600 * 10**6, 0, 24, 60)
+    opt = sb.Optimizer(m, [sb.TargetSpecification(swe_obs, ta.start, DAY, [1, 2], 1.0, 3, catchment_property=2)])
+    assert opt.calculate_goal_function(PTGSK_DEFAULT) == pytest.approx(0.0, abs=1e-9)
+    p = _perturbed(np.random.default_rng(5), 1)[0]
+    run = oracle.ptgsk_run_cells(gm, p, f, st0, ta.start * 10**6, 3600 * 10**6, ncore=8)
+    sim = oracle.average_to_axis((run["snow_swe"][:, sel] * area[sel]).sum(axis=1) / area[sel].sum(), 3600 * 10**6, 0, 24, 60)
+    assert opt.calculate_goal_function(p) == pytest.approx(oracle.rmse(swe_obs, sim), rel=1e-9)
