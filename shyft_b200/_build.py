@@ -59,7 +59,8 @@ def build_host_shim_test(force=False):
     out = os.path.join(ROOT, "tests", "cpp", "shim_selftest")
     if not os.path.exists(src):
         return None
-    deps = [src, os.path.join(ROOT, "include", "shyft_b200.h"), os.path.join(ROOT, "include", "shyft_b200", "region_model.hpp")]
+    deps = [src, os.path.join(ROOT, "include", "shyft_b200.h"), os.path.join(ROOT, "include", "shyft_b200", "region_model.hpp"), LIB]
     if force or _stale(out, deps):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "include"), "-o", out, src, "-ldl"])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "include"), "-o", out, src, "-L", HERE, "-lshyft_b200",
+                               "-Wl,-rpath," + HERE, "-Wl,-rpath,$ORIGIN/../../shyft_b200"])
     return out

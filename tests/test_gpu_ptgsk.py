@@ -269,3 +269,13 @@ def test_full_size_properties_config2_slice(sb):
     m.revert_to_initial_state()
     m.run_windowed(ip, window_steps=584)
     assert np.array_equal(m.catchment_discharges(), cq) and np.array_equal(m.get_states(), s1)
+
+
+def test_cpp_host_shim_selftest():
+    """include/shyft_b200/region_model.hpp (the C++ mirror of region_model<cell_t>) over the C ABI, reference literals."""
+    import subprocess
+    from shyft_b200 import _build
+    exe = _build.build_host_shim_test()
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "shim selftest ok" in r.stdout
