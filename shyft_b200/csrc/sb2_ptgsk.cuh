@@ -294,8 +294,11 @@ __device__ __forceinline__ void gs_step(GsState& s, GsCache& cache, double& r_sc
     if (alpha == cache.k_alpha && sdc_scale == cache.k_scale && acc_melt == cache.k_acc && lwc == cache.k_lwc && temp_swe == cache.k_tswe) {
         storage = cache.storage;
         sca = cache.sca;
-    } else
+    } else {
         gs_calc_snow_state(alpha, sdc_scale, y0, acc_melt, lwc, p.max_water, temp_swe, storage, sca, cache.lg_key, cache.lg_val);
+        cache.k_alpha = alpha; cache.k_scale = sdc_scale; cache.k_acc = acc_melt; cache.k_lwc = lwc; cache.k_tswe = temp_swe;
+        cache.storage = storage; cache.sca = sca;
+    }
     const double start_storage_value = storage;
 
     if (acc_melt < 0.0) {  // :414-451
@@ -351,9 +354,15 @@ __device__ __forceinline__ void gs_step(GsState& s, GsCache& cache, double& r_sc
             }
         }
     }
-    gs_calc_snow_state(alpha, sdc_scale, y0, acc_melt, lwc, p.max_water, temp_swe, storage, sca, cache.lg_key, cache.lg_val);
-    cache.k_alpha = alpha; cache.k_scale = sdc_scale; cache.k_acc = acc_melt; cache.k_lwc = lwc; cache.k_tswe = temp_swe;
-    cache.storage = storage; cache.sca = sca;
+    // (:472) in a cold dry spell nothing of the pack changed during the step: same five inputs, same result
+    if (alpha == cache.k_alpha && sdc_scale == cache.k_scale && acc_melt == cache.k_acc && lwc == cache.k_lwc && temp_swe == cache.k_tswe) {
+        storage = cache.storage;
+        sca = cache.sca;
+    } else {
+        gs_calc_snow_state(alpha, sdc_scale, y0, acc_melt, lwc, p.max_water, temp_swe, storage, sca, cache.lg_key, cache.lg_val);
+        cache.k_alpha = alpha; cache.k_scale = sdc_scale; cache.k_acc = acc_melt; cache.k_lwc = lwc; cache.k_tswe = temp_swe;
+        cache.storage = storage; cache.sca = sca;
+    }
 
     outflow = prec + start_storage_value - storage;
     if (outflow < 0.0) outflow = 0.0;
