@@ -86,12 +86,54 @@ struct PtgskRunArgs {
 struct GsState { double albedo, lwc, surface_heat, alpha, sdc_melt_mean, acc_melt, iso_pot_energy, temp_swe; };
 // Exact memoisation across steps.  The snow state a step ends with (calc_snow_state at gamma_snow.h:472) is what the next
 // step starts by recomputing (:411) from the same five numbers; when their bits are unchanged the result is reused.
+#ifndef SB2_CACHE_SMEM
+#define SB2_CACHE_SMEM 0  // 1 = keep the memo in shared memory ([field][thread]); measured no gain on B200 (513 vs 503 ms), registers it is
+#endif
+#ifndef SB2_BLOCK
+#define SB2_BLOCK 32       // threads per block of the cell-step kernels: one warp per block balances the uneven per-cell work best (measured)
+#endif
+#if SB2_CACHE_SMEM
+struct GsCache {
+    double* s;  // this thread's column of the block's [9][SB2_BLOCK] shared array
+    __device__ __forceinline__ double& f(int i) { return s[i * SB2_BLOCK]; }
+};
+#define SB2_CK_ALPHA(c) (c).f(0)
+#define SB2_CK_SCALE(c) (c).f(1)
+#define SB2_CK_ACC(c) (c).f(2)
+#define SB2_CK_LWC(c) (c).f(3)
+#define SB2_CK_TSWE(c) (c).f(4)
+#define SB2_CK_STORAGE(c) (c).f(5)
+#define SB2_CK_SCA(c) (c).f(6)
+#define SB2_CK_LGKEY(c) (c).f(7)
+#define SB2_CK_LGVAL(c) (c).f(8)
+#else
 struct GsCache {
     double k_alpha, k_scale, k_acc, k_lwc, k_tswe;  // inputs of the memoised call (NaN = empty)
     double storage, sca;                            // its outputs
     double lg_key, lg_val;                          // lgamma(alpha)
 };
-__device__ __forceinline__ void gs_cache_clear(GsCache& c) { c.k_alpha = c.lg_key = nan_(); c.k_scale = c.k_acc = c.k_lwc = c.k_tswe = 0.0; c.storage = c.sca = c.lg_val = 0.0; }
+#define SB2_CK_ALPHA(c) (c).k_alpha
+#define SB2_CK_SCALE(c) (c).k_scale
+#define SB2_CK_ACC(c) (c).k_acc
+#define SB2_CK_LWC(c) (c).k_lwc
+#define SB2_CK_TSWE(c) (c).k_tswe
+#define SB2_CK_STORAGE(c) (c).storage
+#define SB2_CK_SCA(c) (c).sca
+#define SB2_CK_LGKEY(c) (c).lg_key
+#define SB2_CK_LGVAL(c) (c).lg_val
+#endif
+__device__ __forceinline__ void gs_cache_clear(GsCache& c) {
+    SB2_CK_ALPHA(c) = nan_(); SB2_CK_LGKEY(c) = nan_();
+    SB2_CK_SCALE(c) = SB2_CK_ACC(c) = SB2_CK_LWC(c) = SB2_CK_TSWE(c) = 0.0;
+    SB2_CK_STORAGE(c) = SB2_CK_SCA(c) = SB2_CK_LGVAL(c) = 0.0;
+}
+__device__ __forceinline__ bool gs_cache_hit(GsCache& c, double alpha, double scale, double acc, double lwc, double tswe) {
+    return alpha == SB2_CK_ALPHA(c) && scale == SB2_CK_SCALE(c) && acc == SB2_CK_ACC(c) && lwc == SB2_CK_LWC(c) && tswe == SB2_CK_TSWE(c);
+}
+__device__ __forceinline__ void gs_cache_store(GsCache& c, double alpha, double scale, double acc, double lwc, double tswe, double storage, double sca) {
+    SB2_CK_ALPHA(c) = alpha; SB2_CK_SCALE(c) = scale; SB2_CK_ACC(c) = acc; SB2_CK_LWC(c) = lwc; SB2_CK_TSWE(c) = tswe;
+    SB2_CK_STORAGE(c) = storage; SB2_CK_SCA(c) = sca;
+}
 
 __device__ __forceinline__ double mmh_to_m3s(double mmh, double area) { return area * mmh * (1 / (3600.0 * 1000.0)); }
 __device__ __forceinline__ double m3s_to_mmh(double m3s, double area) { return m3s / ((1 / (3600.0 * 1000.0)) * area); }
@@ -291,13 +333,12 @@ __device__ __forceinline__ void gs_step(GsState& s, GsCache& cache, double& r_sc
 
     double sdc_scale = sdc_melt_mean / alpha;
     const double y0 = p.initial_bare_ground_fraction;
-    if (alpha == cache.k_alpha && sdc_scale == cache.k_scale && acc_melt == cache.k_acc && lwc == cache.k_lwc && temp_swe == cache.k_tswe) {
-        storage = cache.storage;
-        sca = cache.sca;
+    if (gs_cache_hit(cache, alpha, sdc_scale, acc_melt, lwc, temp_swe)) {
+        storage = SB2_CK_STORAGE(cache);
+        sca = SB2_CK_SCA(cache);
     } else {
-        gs_calc_snow_state(alpha, sdc_scale, y0, acc_melt, lwc, p.max_water, temp_swe, storage, sca, cache.lg_key, cache.lg_val);
-        cache.k_alpha = alpha; cache.k_scale = sdc_scale; cache.k_acc = acc_melt; cache.k_lwc = lwc; cache.k_tswe = temp_swe;
-        cache.storage = storage; cache.sca = sca;
+        gs_calc_snow_state(alpha, sdc_scale, y0, acc_melt, lwc, p.max_water, temp_swe, storage, sca, SB2_CK_LGKEY(cache), SB2_CK_LGVAL(cache));
+        gs_cache_store(cache, alpha, sdc_scale, acc_melt, lwc, temp_swe, storage, sca);
     }
     const double start_storage_value = storage;
 
@@ -314,7 +355,7 @@ __device__ __forceinline__ void gs_step(GsState& s, GsCache& cache, double& r_sc
                 double z1 = lwc / p.max_water;
                 z1 = gs_corr_lwc(z1, alpha_prev, sdc_scale_prev > 0.0 ? sdc_scale_prev : sdc_scale, alpha, sdc_scale);
                 lwc = z1 * p.max_water;
-                gs_calc_snow_state(alpha, sdc_scale, y0, acc_melt, lwc, p.max_water, temp_swe, storage, sca, cache.lg_key, cache.lg_val);
+                gs_calc_snow_state(alpha, sdc_scale, y0, acc_melt, lwc, p.max_water, temp_swe, storage, sca, SB2_CK_LGKEY(cache), SB2_CK_LGVAL(cache));
             }
         }
         lwc += rain;
@@ -355,13 +396,12 @@ __device__ __forceinline__ void gs_step(GsState& s, GsCache& cache, double& r_sc
         }
     }
     // (:472) in a cold dry spell nothing of the pack changed during the step: same five inputs, same result
-    if (alpha == cache.k_alpha && sdc_scale == cache.k_scale && acc_melt == cache.k_acc && lwc == cache.k_lwc && temp_swe == cache.k_tswe) {
-        storage = cache.storage;
-        sca = cache.sca;
+    if (gs_cache_hit(cache, alpha, sdc_scale, acc_melt, lwc, temp_swe)) {
+        storage = SB2_CK_STORAGE(cache);
+        sca = SB2_CK_SCA(cache);
     } else {
-        gs_calc_snow_state(alpha, sdc_scale, y0, acc_melt, lwc, p.max_water, temp_swe, storage, sca, cache.lg_key, cache.lg_val);
-        cache.k_alpha = alpha; cache.k_scale = sdc_scale; cache.k_acc = acc_melt; cache.k_lwc = lwc; cache.k_tswe = temp_swe;
-        cache.storage = storage; cache.sca = sca;
+        gs_calc_snow_state(alpha, sdc_scale, y0, acc_melt, lwc, p.max_water, temp_swe, storage, sca, SB2_CK_LGKEY(cache), SB2_CK_LGVAL(cache));
+        gs_cache_store(cache, alpha, sdc_scale, acc_melt, lwc, temp_swe, storage, sca);
     }
 
     outflow = prec + start_storage_value - storage;
@@ -501,9 +541,6 @@ __device__ __forceinline__ bool kirchner_step(double c1, double c2, double c3, d
 
 // ---- the window kernel ----------------------------------------------------------------------------------
 // COLLECT bits: 1 avg_discharge+charge, 2 snow sca/swe, 4 snow_outflow/glacier_melt/ae/pe, 8 state series
-#ifndef SB2_BLOCK
-#define SB2_BLOCK 32       // threads per block of the cell-step kernels: one warp per block balances the uneven per-cell work best (measured)
-#endif
 #ifndef SB2_MINBLOCKS
 #define SB2_MINBLOCKS 12   // resident blocks per SM the register allocation must allow (<= 168 registers per thread)
 #endif
@@ -537,7 +574,12 @@ __global__ void __launch_bounds__(SB2_BLOCK, SB2_MINBLOCKS) ptgsk_run_kernel(con
     gs.sdc_melt_mean = state[4 * n + cc]; gs.acc_melt = state[5 * n + cc]; gs.iso_pot_energy = state[6 * n + cc];
     gs.temp_swe = state[7 * n + cc];
     double kq = state[8 * n + cc];
+#if SB2_CACHE_SMEM
+    __shared__ double cache_s[9 * SB2_BLOCK];
+    GsCache cache{cache_s + threadIdx.x};
+#else
     GsCache cache;
+#endif
     gs_cache_clear(cache);
 
     // segmented-reduction bookkeeping: lanes of one slot are contiguous in the warp
