@@ -151,6 +151,11 @@ struct sb2_model {
     DevArray<int> d_error_flag;
     // routing (core/routing.h)
     std::vector<double> rivers;  // [n][6] id downstream distance velocity alpha beta
+    std::unique_ptr<RoutingPlan> route;      // built on first use, dropped when the network or the parameters change
+    DevArray<double> d_rlocal, d_rup, d_rout;  // [n_riv][T] local inflow / upstream inflow / routed output
+    bool rlocal_valid = false, rnet_valid = false;
+    DevArray<double> d_qhist;                // windowed runs: avg_discharge window preceded by the previous window's tail rows
+    int64_t qhist_rows = 0;
     // calibration targets (core/model_calibration.h:242-329)
     struct Target {
         std::vector<double> obs;
@@ -666,6 +671,23 @@ float time_end(sb2_model* m, int a, int b) {
     CUDA_OK(cudaEventElapsedTime(&ms, m->ev[a], m->ev[b]));
     return ms;
 }
+// ---- routing plan (core/routing.h:326-383) ---------------------------------------------------------------------------------
+void ensure_routing_plan(sb2_model* m) {
+    if (m->route) return;
+    if (m->rivers.empty()) throw Error("routing: the river network is empty");
+    // routing velocity/alpha/beta live in the cell's parameter set (pt_gs_k.h:102-104, pt_hs_k.h:81-83, hbv_stack.h:93-95)
+    const int off = m->stack == SB2_PT_GS_K ? 25 : (m->stack == SB2_PT_HS_K ? 13 : 17);
+    std::vector<double> cell_routing(size_t(m->n) * 5);
+    for (int64_t i = 0; i < m->n; ++i) {
+        auto f = m->catch_param.find(m->geo[i].catchment_id);
+        const std::vector<double>& p = f != m->catch_param.end() ? f->second : m->region_param;
+        double* cr = &cell_routing[5 * i];
+        cr[0] = double(m->geo[i].routing_id); cr[1] = m->geo[i].routing_distance;
+        cr[2] = p[off]; cr[3] = p[off + 1]; cr[4] = p[off + 2];
+    }
+    m->route = build_routing_plan(m->rivers, cell_routing, m->n, m->dt, m->stream);
+}
+
 
 // ---- calibration goal function (core/model_calibration.h:830-899) ---------------------------------------------------------
 void build_goal_targets(sb2_model* m, std::vector<GoalTarget>& gt, const double* cq, const double* cc, int64_t ens_stride) {
@@ -932,6 +954,7 @@ int sb2_set_region_parameter(sb2_model* m, const double* p, int n) {
         if (n != m->n_param) throw Error("parameter vector size does not match parameter::size()");
         m->region_param.assign(p, p + n);
         m->param_dirty = true;
+        m->route.reset();
     });
 }
 int sb2_get_region_parameter(const sb2_model* m, double* p, int n) {
@@ -945,6 +968,7 @@ int sb2_set_catchment_parameter(sb2_model* m, int64_t cid, const double* p, int 
         if (n != m->n_param) throw Error("parameter vector size does not match parameter::size()");
         m->catch_param[cid].assign(p, p + n);
         m->param_dirty = true;
+        m->route.reset();
     });
 }
 int sb2_get_catchment_parameter(const sb2_model* m, int64_t cid, double* p, int n) {
@@ -1198,6 +1222,7 @@ int sb2_run_cells(sb2_model* m, int start_step, int n_steps) {
         launch_step_range(m, first, count, true);
         m->last_step_ms = time_end(m, 2, 3);
         m->ran_first = first; m->ran_steps = count;
+        m->rlocal_valid = m->rnet_valid = false;
         check_device_errors(m);
     });
 }
@@ -1212,6 +1237,18 @@ int sb2_run_windowed(sb2_model* m, const sb2_interpolation_parameter* ip, int st
         const int64_t count = n_steps > 0 ? n_steps : m->T;
         const int64_t W = std::min<int64_t>(window_steps, count);
         float interp_ms = 0.f, step_ms = 0.f;
+        // routing over a windowed run: each window's cell discharge is convolved into the rivers' local inflow right away
+        // (the per-cell series of earlier windows are gone afterwards); the last cell_max_len-1 rows are carried over
+        const bool route = !m->rivers.empty() && (m->collect_bits & SB2_COLLECT_DISCHARGE) && first == 0 && count == m->T;
+        int64_t H = 0;
+        if (route) {
+            ensure_routing_plan(m);
+            H = m->route->cell_max_len - 1;
+            m->d_qhist.resize(size_t(H + W) * m->n);
+            CUDA_OK(cudaMemsetAsync(m->d_qhist.p, 0, size_t(H) * m->n * sizeof(double), m->stream));
+            m->d_rlocal.resize(size_t(m->route->n_riv) * m->T);
+        }
+        m->rlocal_valid = m->rnet_valid = false;
         for (int64_t w0 = first; w0 < first + count; w0 += W) {
             const int64_t wn = std::min<int64_t>(W, first + count - w0);
             // the window buffers are reused: forcing rows [w0, w0+W), series rows likewise
@@ -1228,6 +1265,14 @@ int sb2_run_windowed(sb2_model* m, const sb2_interpolation_parameter* ip, int st
             ensure_series(m, w0, W);
             CUDA_OK(cudaEventRecord(m->ev[2], m->stream));
             launch_step_range(m, w0, wn, true);
+            if (route) {
+                double* row0 = m->d_qhist.p + size_t(H) * m->n;
+                CUDA_OK(cudaMemcpyAsync(row0, m->d_resp[SB2_R_AVG_DISCHARGE].p, size_t(wn) * m->n * sizeof(double), cudaMemcpyDeviceToDevice, m->stream));
+                routing_local_inflow(*m->route, row0, m->n, wn, H, w0, m->T, m->d_rlocal.p, m->stream, &m->launches);
+                if (H > 0)  // the tail of this window becomes the history of the next (wn >= H for every window but possibly the last)
+                    CUDA_OK(cudaMemcpyAsync(m->d_qhist.p, m->d_qhist.p + size_t(wn) * m->n, size_t(H) * m->n * sizeof(double), cudaMemcpyDeviceToDevice,
+                                            m->stream));
+            }
             CUDA_OK(cudaEventRecord(m->ev[3], m->stream));
             CUDA_OK(cudaEventSynchronize(m->ev[3]));
             float a = 0.f, b = 0.f;
@@ -1237,6 +1282,7 @@ int sb2_run_windowed(sb2_model* m, const sb2_interpolation_parameter* ip, int st
         }
         m->last_interp_ms = interp_ms; m->last_step_ms = step_ms;
         m->ran_first = first; m->ran_steps = count;
+        if (route) m->rlocal_valid = true;
         check_device_errors(m);
     });
 }
@@ -1299,27 +1345,37 @@ int sb2_set_river_network(sb2_model* m, int64_t n_rivers, const double* rivers) 
             }
         }
         m->rivers.assign(rivers, rivers + 6 * n_rivers);
+        m->route.reset();
+        m->rlocal_valid = m->rnet_valid = false;
     });
 }
 
 int sb2_river_flows(sb2_model* m, int64_t rid, int64_t start_step, int64_t n_steps, double* local_inflow, double* upstream_inflow,
                     double* output) {
     return guarded(m, [&] {
-        if (!m->d_resp[SB2_R_AVG_DISCHARGE].p || m->out_first != 0 || m->out_rows != m->T)
-            throw Error("river flows need avg_discharge collected over the whole time axis (run_cells with a discharge collector)");
         if (start_step < 0 || start_step + n_steps > m->T) throw Error("requested steps are outside the time axis");
-        // routing velocity/alpha/beta live in the cell's parameter set (pt_gs_k.h:102-104, pt_hs_k.h:81-83, hbv_stack.h:93-95)
-        const int off = m->stack == SB2_PT_GS_K ? 25 : (m->stack == SB2_PT_HS_K ? 13 : 17);
-        std::vector<double> cell_routing(size_t(m->n) * 5);
-        for (int64_t i = 0; i < m->n; ++i) {
-            auto f = m->catch_param.find(m->geo[i].catchment_id);
-            const std::vector<double>& p = f != m->catch_param.end() ? f->second : m->region_param;
-            double* cr = &cell_routing[5 * i];
-            cr[0] = double(m->geo[i].routing_id); cr[1] = m->geo[i].routing_distance;
-            cr[2] = p[off]; cr[3] = p[off + 1]; cr[4] = p[off + 2];
+        ensure_routing_plan(m);
+        auto f = m->route->ix_of_rid.find(rid);
+        if (f == m->route->ix_of_rid.end()) throw Error("river network: river id " + std::to_string(rid) + " not found");
+        if (!m->rlocal_valid) {  // resident run: the whole avg_discharge series is in HBM
+            if (!m->d_resp[SB2_R_AVG_DISCHARGE].p || m->out_first != 0 || m->out_rows != m->T)
+                throw Error("river flows need avg_discharge over the whole time axis (run_cells with a discharge collector, or run_windowed with the river network set)");
+            m->d_rlocal.resize(size_t(m->route->n_riv) * m->T);
+            routing_local_inflow(*m->route, m->d_resp[SB2_R_AVG_DISCHARGE].p, m->n, m->T, 0, 0, m->T, m->d_rlocal.p, m->stream, &m->launches);
+            m->rlocal_valid = true;
+            m->rnet_valid = false;
         }
-        route_rivers(m->rivers, rid, cell_routing, m->n, m->T, m->dt, m->d_resp[SB2_R_AVG_DISCHARGE].p, m->stream, &m->launches, start_step,
-                     n_steps, local_inflow, upstream_inflow, output);
+        if (!m->rnet_valid) {
+            m->d_rup.resize(size_t(m->route->n_riv) * m->T);
+            m->d_rout.resize(size_t(m->route->n_riv) * m->T);
+            routing_network(*m->route, m->T, m->d_rlocal.p, m->d_rup.p, m->d_rout.p, m->stream, &m->launches);
+            m->rnet_valid = true;
+        }
+        const size_t off = size_t(f->second) * m->T + start_step, bytes = size_t(n_steps) * sizeof(double);
+        if (local_inflow) CUDA_OK(cudaMemcpyAsync(local_inflow, m->d_rlocal.p + off, bytes, cudaMemcpyDeviceToHost, m->stream));
+        if (upstream_inflow) CUDA_OK(cudaMemcpyAsync(upstream_inflow, m->d_rup.p + off, bytes, cudaMemcpyDeviceToHost, m->stream));
+        if (output) CUDA_OK(cudaMemcpyAsync(output, m->d_rout.p + off, bytes, cudaMemcpyDeviceToHost, m->stream));
+        CUDA_OK(cudaStreamSynchronize(m->stream));
     });
 }
 

@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <map>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <tuple>
@@ -22,10 +23,13 @@ namespace sb2 {
 constexpr int ROUTE_CELLS = 128;  // cells per chunk (= threads per block)
 constexpr int ROUTE_TT = 64;      // time steps per block
 
-// local_inflow[r][t] = sum over the river's cells (ascending cell order, 128 at a time) of sum_j w_c[j] * q_c[t-j]
+// local_inflow[r][g0 + t] = sum over the river's cells (ascending cell order, 128 at a time) of sum_j w_c[j] * q_c[t-j], t in [0, n_rows).
+// `q` points at row 0 of a [rows][n_cells] block that also has `hist` valid rows BEFORE row 0 (the tail of the previous
+// window); rows further back are before the start of the axis or not needed and read as zero (USE_ZERO, time_series.h:966-975).
 // grid (time tiles, rivers); dynamic smem: (ROUTE_TT + max_len - 1) * ROUTE_CELLS doubles
-__global__ void __launch_bounds__(ROUTE_CELLS) route_local_inflow_kernel(const double* __restrict__ q /* [T][n_cells] */, int64_t n_cells, int64_t T,
-                                                                         const int32_t* __restrict__ riv_ptr, const int32_t* __restrict__ riv_cells,
+__global__ void __launch_bounds__(ROUTE_CELLS) route_local_inflow_kernel(const double* __restrict__ q, int64_t n_cells, int64_t n_rows, int64_t hist,
+                                                                         int64_t g0, int64_t T, const int32_t* __restrict__ riv_ptr,
+                                                                         const int32_t* __restrict__ riv_cells,
                                                                          const int32_t* __restrict__ cell_uhg_id /* per gathered cell */,
                                                                          const int32_t* __restrict__ uhg_len, const double* __restrict__ uhg_w,
                                                                          int max_len, double* __restrict__ local /* [n_riv][T] */) {
@@ -33,20 +37,19 @@ __global__ void __launch_bounds__(ROUTE_CELLS) route_local_inflow_kernel(const d
     __shared__ double acc[ROUTE_TT];
     const int r = blockIdx.y;
     const int64_t t0 = (int64_t)blockIdx.x * ROUTE_TT;
-    const int nt = int(min((int64_t)ROUTE_TT, T - t0));
+    const int nt = int(min((int64_t)ROUTE_TT, n_rows - t0));
     const int rows = ROUTE_TT + max_len - 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x < ROUTE_TT) acc[threadIdx.x] = 0.0;
     for (int k0 = riv_ptr[r]; k0 < riv_ptr[r + 1]; k0 += ROUTE_CELLS) {
         const int nc = min(ROUTE_CELLS, riv_ptr[r + 1] - k0);
         __syncthreads();
-        // stage q rows [t0 - (max_len-1), t0 + ROUTE_TT) of this chunk's cells; rows before the axis start are zero (USE_ZERO)
         {
             const int c = threadIdx.x;
             const int64_t cell = c < nc ? riv_cells[k0 + c] : -1;
             for (int row = 0; row < rows; ++row) {
-                const int64_t t = t0 - (max_len - 1) + row;
-                sq[row * ROUTE_CELLS + c] = (cell >= 0 && t >= 0 && t < T) ? q[t * n_cells + cell] : 0.0;
+                const int64_t t = t0 - (max_len - 1) + row;  // row of the block, may be negative (history)
+                sq[row * ROUTE_CELLS + c] = (cell >= 0 && t >= -hist && t < n_rows && g0 + t >= 0) ? q[t * n_cells + cell] : 0.0;
             }
         }
         __syncthreads();
@@ -67,7 +70,7 @@ __global__ void __launch_bounds__(ROUTE_CELLS) route_local_inflow_kernel(const d
         }
     }
     __syncthreads();
-    if (threadIdx.x < nt) local[(int64_t)r * T + t0 + threadIdx.x] = acc[threadIdx.x];
+    if (threadIdx.x < nt) local[(int64_t)r * T + g0 + t0 + threadIdx.x] = acc[threadIdx.x];
 }
 
 // one network level: upstream[r][t] = sum of output[u][t] over upstream rivers u; output[r] = (local[r] + upstream[r]) (*) uhg_r
@@ -138,59 +141,66 @@ struct UhgTable {
 
 }  // namespace routing_host
 
-// cell_routing [n_cells][5] = routing id, distance, velocity, alpha, beta (velocity/alpha/beta from the cell's parameter set);
-// rivers [n][6] = id, downstream id, distance, velocity, alpha, beta.  Writes the three series of river `rid` for
-// [start_step, start_step + n_steps) to host memory (any of them may be null).
-inline void route_rivers(const std::vector<double>& rivers, int64_t rid, const std::vector<double>& cell_routing, int64_t n_cells, int64_t T,
-                         int64_t dt_us, const double* d_q, cudaStream_t stream, int64_t* launches, int64_t start_step, int64_t n_steps,
-                         double* local_inflow, double* upstream_inflow, double* output) {
+// Everything about a river network that does not depend on the simulated discharge: cells gathered per river, the
+// unit-hydrograph table, upstream lists and levels.  cell_routing [n_cells][5] = routing id, distance, velocity, alpha,
+// beta (velocity/alpha/beta from the cell's parameter set); rivers [n][6] = id, downstream id, distance, velocity, alpha, beta.
+struct RoutingPlan {
+    int n_riv = 0, max_len = 1, cell_max_len = 1, n_levels = 0;
+    std::map<int64_t, int> ix_of_rid;
+    std::vector<int> level_begin;
+    routing_host::DevBuf b_ptr, b_cells, b_cuhg, b_len, b_w, b_ruhg, b_upp, b_upi, b_lvl;
+    const int32_t *d_ptr = nullptr, *d_cells = nullptr, *d_cuhg = nullptr, *d_len = nullptr, *d_ruhg = nullptr, *d_upp = nullptr, *d_upi = nullptr,
+                  *d_order = nullptr;
+    const double* d_w = nullptr;
+};
+
+inline std::unique_ptr<RoutingPlan> build_routing_plan(const std::vector<double>& rivers, const std::vector<double>& cell_routing, int64_t n_cells,
+                                                       int64_t dt_us, cudaStream_t stream) {
     using namespace routing_host;
+    auto pl = std::make_unique<RoutingPlan>();
     const int n_riv = int(rivers.size() / 6);
     if (n_riv == 0) throw std::runtime_error("routing: the river network is empty");
-    std::map<int64_t, int> ix_of_rid;
-    for (int i = 0; i < n_riv; ++i) ix_of_rid[int64_t(rivers[6 * i])] = i;
-    if (!ix_of_rid.count(rid)) throw std::runtime_error("river network: river id " + std::to_string(rid) + " not found");
+    pl->n_riv = n_riv;
+    for (int i = 0; i < n_riv; ++i) pl->ix_of_rid[int64_t(rivers[6 * i])] = i;
     UhgTable tab;
-    // cells gathered per river, ascending cell order
     std::vector<std::vector<int32_t>> cells_of(n_riv);
     std::vector<int32_t> cell_uhg(n_cells, 0);
     for (int64_t c = 0; c < n_cells; ++c) {
         const int64_t id = int64_t(cell_routing[5 * c]);
         if (id <= 0) continue;
-        auto f = ix_of_rid.find(id);
-        if (f == ix_of_rid.end()) throw std::runtime_error("river network: river id " + std::to_string(id) + " not found");
+        auto f = pl->ix_of_rid.find(id);
+        if (f == pl->ix_of_rid.end()) throw std::runtime_error("river network: river id " + std::to_string(id) + " not found");
         cells_of[f->second].push_back(int32_t(c));
         cell_uhg[c] = tab.id_of(host::uhg_steps(cell_routing[5 * c + 1], cell_routing[5 * c + 2], dt_us), cell_routing[5 * c + 3],
                                 cell_routing[5 * c + 4]);
     }
+    for (auto& w : tab.w) pl->cell_max_len = std::max(pl->cell_max_len, int(w.size()));
     std::vector<int32_t> riv_ptr(n_riv + 1, 0), riv_cells, gathered_uhg, riv_uhg(n_riv);
     for (int r = 0; r < n_riv; ++r) {
         for (auto c : cells_of[r]) { riv_cells.push_back(c); gathered_uhg.push_back(cell_uhg[c]); }
         riv_ptr[r + 1] = int32_t(riv_cells.size());
         riv_uhg[r] = tab.id_of(host::uhg_steps(rivers[6 * r + 2], rivers[6 * r + 3], dt_us), rivers[6 * r + 4], rivers[6 * r + 5]);
     }
-    int max_len = 1;
-    for (auto& w : tab.w) max_len = std::max(max_len, int(w.size()));
-    const size_t smem_cells = size_t(ROUTE_TT + max_len - 1) * ROUTE_CELLS * sizeof(double);
-    if (smem_cells > 200 * 1024) throw std::runtime_error("routing: unit hydrograph too long for the shared-memory tile");
+    for (auto& w : tab.w) pl->max_len = std::max(pl->max_len, int(w.size()));
+    if (size_t(ROUTE_TT + pl->max_len - 1) * ROUTE_CELLS * sizeof(double) > 200 * 1024)
+        throw std::runtime_error("routing: unit hydrograph too long for the shared-memory tile");
     std::vector<int32_t> uhg_len(tab.w.size());
-    std::vector<double> uhg_w(tab.w.size() * max_len, 0.0);
+    std::vector<double> uhg_w(tab.w.size() * pl->max_len, 0.0);
     for (size_t i = 0; i < tab.w.size(); ++i) {
         uhg_len[i] = int32_t(tab.w[i].size());
-        std::copy(tab.w[i].begin(), tab.w[i].end(), uhg_w.begin() + i * max_len);
+        std::copy(tab.w[i].begin(), tab.w[i].end(), uhg_w.begin() + i * pl->max_len);
     }
     // upstream lists (ascending river id, routing.h:205-213) and levels (a river's level = 1 + max level of its upstreams)
     std::vector<std::vector<int32_t>> ups(n_riv);
-    for (auto& kv : ix_of_rid) {  // map order = ascending id
+    for (auto& kv : pl->ix_of_rid) {  // map order = ascending id
         const int64_t down = int64_t(rivers[6 * kv.second + 1]);
         if (down > 0) {
-            auto f = ix_of_rid.find(down);
-            if (f == ix_of_rid.end()) throw std::runtime_error("river network: downstream river id not found");
+            auto f = pl->ix_of_rid.find(down);
+            if (f == pl->ix_of_rid.end()) throw std::runtime_error("river network: downstream river id not found");
             ups[f->second].push_back(kv.second);
         }
     }
     std::vector<int> level(n_riv, -1);
-    int n_levels = 0;
     for (int pass = 0; pass <= n_riv; ++pass) {
         bool changed = false;
         for (int r = 0; r < n_riv; ++r) {
@@ -198,56 +208,56 @@ inline void route_rivers(const std::vector<double>& rivers, int64_t rid, const s
             int lv = 0;
             bool ready = true;
             for (auto u : ups[r]) { if (level[u] < 0) { ready = false; break; } lv = std::max(lv, level[u] + 1); }
-            if (ready) { level[r] = lv; n_levels = std::max(n_levels, lv + 1); changed = true; }
+            if (ready) { level[r] = lv; pl->n_levels = std::max(pl->n_levels, lv + 1); changed = true; }
         }
         if (!changed) break;
     }
     for (int r = 0; r < n_riv; ++r)
         if (level[r] < 0) throw std::runtime_error("river network: cycle detected");
-    std::vector<int32_t> up_ptr(n_riv + 1, 0), up_idx;
+    std::vector<int32_t> up_ptr(n_riv + 1, 0), up_idx, order;
     for (int r = 0; r < n_riv; ++r) { for (auto u : ups[r]) up_idx.push_back(u); up_ptr[r + 1] = int32_t(up_idx.size()); }
-
-    DevBuf b_ptr, b_cells, b_cuhg, b_len, b_w, b_ruhg, b_upp, b_upi, b_local, b_up, b_out, b_lvl;
-    const int32_t* d_ptr = b_ptr.upload(riv_ptr, stream);
-    const int32_t* d_cells = b_cells.upload(riv_cells, stream);
-    const int32_t* d_cuhg = b_cuhg.upload(gathered_uhg, stream);
-    const int32_t* d_len = b_len.upload(uhg_len, stream);
-    const double* d_w = b_w.upload(uhg_w, stream);
-    const int32_t* d_ruhg = b_ruhg.upload(riv_uhg, stream);
-    const int32_t* d_upp = b_upp.upload(up_ptr, stream);
-    const int32_t* d_upi = b_upi.upload(up_idx, stream);
-    double* d_local = b_local.alloc<double>(size_t(n_riv) * T);
-    double* d_up = b_up.alloc<double>(size_t(n_riv) * T);
-    double* d_out = b_out.alloc<double>(size_t(n_riv) * T);
-    cudaMemsetAsync(d_up, 0, size_t(n_riv) * T * sizeof(double), stream);
-
-    const unsigned tiles = unsigned((T + ROUTE_TT - 1) / ROUTE_TT);
-    if (smem_cells > 48 * 1024) cudaFuncSetAttribute(route_local_inflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_cells));
-    route_local_inflow_kernel<<<dim3(tiles, n_riv), ROUTE_CELLS, smem_cells, stream>>>(d_q, n_cells, T, d_ptr, d_cells, d_cuhg, d_len, d_w, max_len,
-                                                                                     d_local);
-    ++*launches;
-    std::vector<int32_t> order;
-    std::vector<int> level_begin(n_levels + 1, 0);
-    for (int lv = 0; lv < n_levels; ++lv) {
+    pl->level_begin.assign(pl->n_levels + 1, 0);
+    for (int lv = 0; lv < pl->n_levels; ++lv) {
         for (int r = 0; r < n_riv; ++r) if (level[r] == lv) order.push_back(r);
-        level_begin[lv + 1] = int(order.size());
+        pl->level_begin[lv + 1] = int(order.size());
     }
-    const int32_t* d_order = b_lvl.upload(order, stream);
-    const size_t smem_riv = size_t(ROUTE_TT + max_len - 1) * sizeof(double);
-    for (int lv = 0; lv < n_levels; ++lv) {
-        const int cnt = level_begin[lv + 1] - level_begin[lv];
-        route_river_level_kernel<<<dim3(tiles, cnt), ROUTE_TT, smem_riv, stream>>>(d_order + level_begin[lv], d_upp, d_upi, d_ruhg, d_len, d_w, max_len,
-                                                                                   T, d_local, d_up, d_out);
+    pl->d_ptr = pl->b_ptr.upload(riv_ptr, stream);
+    pl->d_cells = pl->b_cells.upload(riv_cells, stream);
+    pl->d_cuhg = pl->b_cuhg.upload(gathered_uhg, stream);
+    pl->d_len = pl->b_len.upload(uhg_len, stream);
+    pl->d_w = pl->b_w.upload(uhg_w, stream);
+    pl->d_ruhg = pl->b_ruhg.upload(riv_uhg, stream);
+    pl->d_upp = pl->b_upp.upload(up_ptr, stream);
+    pl->d_upi = pl->b_upi.upload(up_idx, stream);
+    pl->d_order = pl->b_lvl.upload(order, stream);
+    if (cudaStreamSynchronize(stream) != cudaSuccess) throw std::runtime_error("routing: upload failed");
+    return pl;
+}
+
+// cell -> river: the local inflow of every river over block rows [0, n_rows) = global steps [g0, g0 + n_rows)
+inline void routing_local_inflow(const RoutingPlan& pl, const double* d_q_row0, int64_t n_cells, int64_t n_rows, int64_t hist, int64_t g0, int64_t T,
+                                 double* d_local, cudaStream_t stream, int64_t* launches) {
+    const size_t smem = size_t(ROUTE_TT + pl.max_len - 1) * ROUTE_CELLS * sizeof(double);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(route_local_inflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    const unsigned tiles = unsigned((n_rows + ROUTE_TT - 1) / ROUTE_TT);
+    route_local_inflow_kernel<<<dim3(tiles, pl.n_riv), ROUTE_CELLS, smem, stream>>>(d_q_row0, n_cells, n_rows, hist, g0, T, pl.d_ptr, pl.d_cells, pl.d_cuhg,
+                                                                                  pl.d_len, pl.d_w, pl.max_len, d_local);
+    ++*launches;
+    if (cudaGetLastError() != cudaSuccess) throw std::runtime_error("routing: kernel launch failed");
+}
+
+// river network, leaves first: upstream inflow and routed output of every river over the whole axis
+inline void routing_network(const RoutingPlan& pl, int64_t T, const double* d_local, double* d_up, double* d_out, cudaStream_t stream, int64_t* launches) {
+    cudaMemsetAsync(d_up, 0, size_t(pl.n_riv) * T * sizeof(double), stream);
+    const unsigned tiles = unsigned((T + ROUTE_TT - 1) / ROUTE_TT);
+    const size_t smem = size_t(ROUTE_TT + pl.max_len - 1) * sizeof(double);
+    for (int lv = 0; lv < pl.n_levels; ++lv) {
+        const int cnt = pl.level_begin[lv + 1] - pl.level_begin[lv];
+        route_river_level_kernel<<<dim3(tiles, cnt), ROUTE_TT, smem, stream>>>(pl.d_order + pl.level_begin[lv], pl.d_upp, pl.d_upi, pl.d_ruhg, pl.d_len,
+                                                                              pl.d_w, pl.max_len, T, d_local, d_up, d_out);
         ++*launches;
     }
     if (cudaGetLastError() != cudaSuccess) throw std::runtime_error("routing: kernel launch failed");
-    const int r = ix_of_rid[rid];
-    const size_t bytes = size_t(n_steps) * sizeof(double);
-    if (local_inflow) cudaMemcpyAsync(local_inflow, d_local + size_t(r) * T + start_step, bytes, cudaMemcpyDeviceToHost, stream);
-    if (upstream_inflow) cudaMemcpyAsync(upstream_inflow, d_up + size_t(r) * T + start_step, bytes, cudaMemcpyDeviceToHost, stream);
-    if (output) cudaMemcpyAsync(output, d_out + size_t(r) * T + start_step, bytes, cudaMemcpyDeviceToHost, stream);
-    cudaError_t e = cudaStreamSynchronize(stream);
-    if (e != cudaSuccess) throw std::runtime_error(std::string("routing: ") + cudaGetErrorString(e));
 }
 
 }  // namespace sb2

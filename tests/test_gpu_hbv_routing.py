@@ -75,3 +75,30 @@ def test_river_network_routing_parity(sb, oracle):
         m.set_river_network([[1, 2, 100.0, 1.0, 7.0, 0.0], [2, 1, 100.0, 1.0, 7.0, 0.0]])
     with pytest.raises(RuntimeError, match="not found"):
         m.river_output_flow_m3s(999)
+
+
+@pytest.mark.parametrize("stack", ["pt_hs_k", "hbv_stack"])
+def test_windowed_run_with_routing_equals_resident_run(sb, stack):
+    """BASELINE config 3 shape: the axis does not fit in HBM at 400k cells, so rivers are fed window by window."""
+    from shyft_b200 import synthetic
+    cls, par, sid = (sb.PTHSKOptModel, PTHSK_DEFAULT, 1) if stack == "pt_hs_k" else (sb.HbvStackOptModel, HBV_DEFAULT, 2)
+    n, T, S = 640, 1500, 16
+    geo, ta, env = synthetic.make_region(n, T, S, config_index=2, cells_per_catchment=40, with_routing=True, start=1414800000)
+    rivers = synthetic.river_chain(n // 40, depth=8)
+    st0 = synthetic.default_state(sid, n)
+    ip = sb.InterpolationParameter()
+    a = cls(geo, par)
+    a.run_interpolation(ip, ta, env)
+    a.set_states(st0)
+    a.set_river_network(rivers)
+    a.run_cells()
+    b = cls(geo, par)
+    b.initialize_cell_environment(ta)
+    b.set_states(st0)
+    b.set_river_network(rivers)
+    b.run_windowed(ip, env=env, window_steps=333)
+    assert np.array_equal(a.catchment_discharges(), b.catchment_discharges())
+    for rid in (1, 5, 8, 16):
+        assert_parity(b.river_local_inflow_m3s(rid), a.river_local_inflow_m3s(rid), f"{stack} river {rid} local inflow (windowed)", rtol=1e-13)
+        assert_parity(b.river_output_flow_m3s(rid), a.river_output_flow_m3s(rid), f"{stack} river {rid} output (windowed)", rtol=1e-13)
+    assert a.river_output_flow_m3s(8).max() > a.river_local_inflow_m3s(8).max()  # the chain accumulates upstream flow
