@@ -182,6 +182,9 @@ int sb2_calculate_goal_function_batch(sb2_model* m, int64_t n_sets, const double
  * fn 0 exp(x), 1 log(x), 2 pow(x,y), 3 lgamma(a), 4 gamma_p(a,x), 5 corr_lwc(z1,a1,b1,a2,b2), 6 calc_snow_state(shape,scale,y0,
  * lambda,lwd,max_water_frac,temp_swe) -> swe,sca, 7 kirchner step(c1,c2,c3,dt_hours,q,p,e) -> q,q_avg,ok.  Errors: sb2_last_error(NULL). */
 int sb2_unit_eval(int device, int fn, int64_t n, const double* in, int n_in, double* out, int n_out);
+/* IDW with all station values finite runs as a dense tensor-core contraction (results within ~1e-15 of the per-neighbour
+ * weighted mean); on = 0 forces the per-neighbour kernel, which is bit-identical to the reference's operation order. */
+int sb2_set_idw_dense(sb2_model* m, int on);
 
 /* ---- device-side hooks (plumbing for torch.distributed / CUDA-event timing; not part of the reference surface) -- */
 int sb2_set_stream(sb2_model* m, void* cuda_stream);           /* launch on this stream (default: the legacy default stream) */

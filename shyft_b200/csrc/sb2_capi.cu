@@ -82,6 +82,8 @@ struct IdwPlan {  // neighbour lists of one variable (inverse_distance.h:160-203
     int64_t n_src = 0;
     DevArray<int32_t> idx, cnt;
     DevArray<double> w, f;
+    bool dense_valid = false;      // dense operator for the all-finite case (tensor-core path)
+    DevArray<double> dense, addc;  // [n_src][cells], [cells]
 };
 
 struct BtkOps {  // operators of one valid-station subset
@@ -138,6 +140,7 @@ struct sb2_model {
     std::vector<std::unique_ptr<BtkOps>> btk_cache;
     DevArray<double> d_btk_kbuf, d_btk_beta, d_btk_resid;
     // collected series
+    bool force_sparse_idw = false;  // diagnostics: run IDW through the per-neighbour kernel even when the dense operator applies
     int collect_bits = SB2_COLLECT_DISCHARGE;
     DevArray<double> d_resp[SB2_N_RESPONSE], d_st[SB2_N_STATE_SERIES];
     int64_t out_first = 0, out_rows = 0;  // response rows cover [out_first, out_first + out_rows); state series one more
@@ -468,6 +471,7 @@ void build_idw_plan(sb2_model* m, int var) {
     CUDA_OK(cudaGetLastError());
     ++m->launches;
     pl.valid = true;
+    pl.dense_valid = false;
 }
 
 int idw_tile_steps(int64_t n_src) {
@@ -479,6 +483,31 @@ void run_idw(sb2_model* m, int var, int64_t first, int64_t n_steps, double* out)
     IdwPlan& pl = m->idw[var];
     if (!pl.valid) build_idw_plan(m, var);
     const Source& s = m->src[var];
+    if (!s.has_nonfinite && !(var == SB2_TEMPERATURE && pl.p.gradient_by_equation) && s.n_src <= 96 && !m->force_sparse_idw) {
+        // every station value is finite: the weighted means are one dense contraction on the FP64 tensor cores
+        if (!pl.dense_valid) {
+            pl.dense.resize(size_t(s.n_src) * m->n);
+            pl.addc.resize(size_t(m->n));
+            idw_build_dense_kernel<<<grid_for(m->n, 128), 128, 0, m->stream>>>(idw_kind_of(var), m->n, int(s.n_src), m->d_z.p, pl.p.default_temp_gradient,
+                                                                              pl.idx.p, pl.w.p, pl.f.p, pl.cnt.p, pl.dense.p, pl.addc.p);
+            CUDA_OK(cudaGetLastError());
+            ++m->launches;
+            pl.dense_valid = true;
+        }
+        const int nv = int(s.n_src);
+        const double* v = s.d_values.p + first * s.n_src;
+#define SB2_DENSE(KS, NT)                                                                                                               \
+    dense_apply_dmma_kernel<KS, NT, 0><<<grid_for(m->n, 32 * NT), 128, 0, m->stream>>>(m->n, nullptr, nv, pl.dense.p, pl.addc.p, nullptr, v,    \
+                                                                                       s.n_src, nullptr, int(n_steps), m->d_active.p, out)
+        if (nv <= 16) SB2_DENSE(4, 4);
+        else if (nv <= 32) SB2_DENSE(8, 4);
+        else if (nv <= 64) SB2_DENSE(16, 2);
+        else SB2_DENSE(24, 1);
+#undef SB2_DENSE
+        CUDA_OK(cudaGetLastError());
+        ++m->launches;
+        return;
+    }
     const int tile = idw_tile_steps(s.n_src);
     const int max_k = int(std::max<int64_t>(1, std::min<int64_t>(pl.p.max_members, s.n_src)));
     const size_t smem = size_t(tile) * s.n_src * sizeof(double) + size_t(max_k) * IDW_BLOCK * (2 * sizeof(double) + sizeof(int));
@@ -578,9 +607,9 @@ void run_btk(sb2_model* m, int64_t first, int64_t n_steps, double* out) {
         CUDA_OK(cudaGetLastError());
         double* o = out + i * m->n;
         const double* pri = m->d_prior_gradient.p + first + i;
-#define SB2_BTK(KS, NT)                                                                                                            \
-    btk_apply_dmma_kernel<KS, NT><<<grid_for(m->n, 32 * NT), 128, 0, m->stream>>>(m->n, m->d_z.p, nv, op->omega.p, op->bm.p, m->d_btk_beta.p, \
-                                                                                  m->d_btk_resid.p, pri, int(seg), m->d_active.p, o)
+#define SB2_BTK(KS, NT)                                                                                                               \
+    dense_apply_dmma_kernel<KS, NT, 1><<<grid_for(m->n, 32 * NT), 128, 0, m->stream>>>(m->n, m->d_z.p, nv, op->omega.p, op->bm.p, m->d_btk_beta.p, \
+                                                                                       m->d_btk_resid.p, nv, pri, int(seg), m->d_active.p, o)
         if (nv <= 16) SB2_BTK(4, 4);
         else if (nv <= 32) SB2_BTK(8, 4);
         else if (nv <= 64) SB2_BTK(16, 2);
@@ -1161,10 +1190,8 @@ int sb2_set_sources(sb2_model* m, int var, int64_t n_src, const double* xyz, con
         CUDA_OK(cudaGetLastError());
         ++m->launches;
         s.has_nonfinite = false;
-        if (var == SB2_TEMPERATURE) {
-            s.h_values.assign(values, values + count);
-            for (size_t i = 0; i < count && !s.has_nonfinite; ++i) s.has_nonfinite = !std::isfinite(values[i]);
-        }
+        for (size_t i = 0; i < count && !s.has_nonfinite; ++i) s.has_nonfinite = !std::isfinite(values[i]);
+        if (var == SB2_TEMPERATURE) s.h_values.assign(values, values + count);
         CUDA_OK(cudaStreamSynchronize(m->stream));
     });
 }
@@ -1488,6 +1515,10 @@ int sb2_unit_eval(int device, int fn, int64_t n, const double* in, int n_in, dou
         g_create_error = e.what();
         return 1;
     }
+}
+
+int sb2_set_idw_dense(sb2_model* m, int on) {
+    return guarded(m, [&] { m->force_sparse_idw = on == 0; });
 }
 
 // ---- device-side hooks -----------------------------------------------------------------------------------------------------

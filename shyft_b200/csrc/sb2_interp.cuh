@@ -286,13 +286,18 @@ __global__ void __launch_bounds__(128) btk_apply_kernel(int64_t n_cells, const d
 __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
-template <int KSTEPS, int NT>
-__global__ void __launch_bounds__(128) btk_apply_dmma_kernel(int64_t n_cells, const double* __restrict__ cz, int n_valid,
-                                                             const double* __restrict__ omega /* [n_valid][cells] */, const double* __restrict__ bm,
-                                                             const double* __restrict__ beta /* [n_steps][2] */,
-                                                             const double* __restrict__ resid /* [n_steps][n_valid] */,
-                                                             const double* __restrict__ prior_gradient /* [n_steps] */, int n_steps,
-                                                             const uint8_t* __restrict__ active, double* __restrict__ out /* [n_steps][cells] */) {
+// MODE 1: Bayesian temperature kriging (A = resid, epilogue of bayesian_kriging.h:394-396).
+// MODE 0: inverse distance weighting with every station value finite: out[t][c] = sum_s W[c][s] * v[t][s] + addc[c], where the
+//         dense operator W (idw_build_dense_kernel) folds weights, normalisation, the per-neighbour factor and, for
+//         temperature, the min/max-height gradient (inverse_distance.h:304-315) into one matrix -- the "(cells x stations) x
+//         (stations x steps)" contraction of the interpolation step.  A = the station series themselves.
+template <int KSTEPS, int NT, int MODE>
+__global__ void __launch_bounds__(128) dense_apply_dmma_kernel(int64_t n_cells, const double* __restrict__ cz, int n_valid,
+                                                               const double* __restrict__ omega /* [n_valid][cells] */, const double* __restrict__ bm,
+                                                               const double* __restrict__ beta /* [n_steps][2] */,
+                                                               const double* __restrict__ resid /* [n_steps][row_stride] */, int64_t row_stride,
+                                                               const double* __restrict__ prior_gradient /* [n_steps] */, int n_steps,
+                                                               const uint8_t* __restrict__ active, double* __restrict__ out /* [n_steps][cells] */) {
     constexpr int KP = KSTEPS * 4 + 4;  // padded row stride (doubles), == 4 mod 16
     constexpr int BTK_TILE_STEPS = KSTEPS > 16 ? 32 : 64;  // steps of resid staged per block iteration (static smem <= 48 KB)
     __shared__ double sr[BTK_TILE_STEPS * KP];
@@ -322,23 +327,29 @@ __global__ void __launch_bounds__(128) btk_apply_dmma_kernel(int64_t n_cells, co
             const int64_t cell = cbase + nt * 8 + q * 2 + h;
             const bool ok = cell < n_cells && (active == nullptr || active[cell] != 0);
             eok[nt][h] = ok;
-            ez[nt][h] = ok ? cz[cell] : 0.0;
-            e0[nt][h] = ok ? bm[cell] : 0.0;
-            e1[nt][h] = ok ? bm[n_cells + cell] : 0.0;
+            if (MODE == 1) {
+                ez[nt][h] = ok ? cz[cell] : 0.0;
+                e0[nt][h] = ok ? bm[cell] : 0.0;
+                e1[nt][h] = ok ? bm[n_cells + cell] : 0.0;
+            } else {
+                ez[nt][h] = (ok && bm != nullptr) ? bm[cell] : 0.0;  // addc
+                e0[nt][h] = e1[nt][h] = 0.0;
+            }
         }
     for (int t0 = 0; t0 < n_steps; t0 += BTK_TILE_STEPS) {
         const int nt_steps = min(BTK_TILE_STEPS, n_steps - t0);
         __syncthreads();
         for (int e = threadIdx.x; e < BTK_TILE_STEPS * KP; e += blockDim.x) {
             const int r = e / KP, k = e - r * KP;
-            sr[e] = (r < nt_steps && k < n_valid) ? resid[(int64_t)(t0 + r) * n_valid + k] : 0.0;
+            sr[e] = (r < nt_steps && k < n_valid) ? resid[(int64_t)(t0 + r) * row_stride + k] : 0.0;
         }
-        for (int e = threadIdx.x; e < BTK_TILE_STEPS; e += blockDim.x) {
-            const bool in = e < nt_steps;
-            sbeta[2 * e] = in ? beta[2 * (t0 + e)] : 0.0;
-            sbeta[2 * e + 1] = in ? beta[2 * (t0 + e) + 1] : 0.0;
-            spri[e] = in ? prior_gradient[t0 + e] : 0.0;
-        }
+        if (MODE == 1)
+            for (int e = threadIdx.x; e < BTK_TILE_STEPS; e += blockDim.x) {
+                const bool in = e < nt_steps;
+                sbeta[2 * e] = in ? beta[2 * (t0 + e)] : 0.0;
+                sbeta[2 * e + 1] = in ? beta[2 * (t0 + e) + 1] : 0.0;
+                spri[e] = in ? prior_gradient[t0 + e] : 0.0;
+            }
         __syncthreads();
         for (int m0 = 0; m0 < nt_steps; m0 += 8) {
             double acc[NT][2];
@@ -352,17 +363,65 @@ __global__ void __launch_bounds__(128) btk_apply_dmma_kernel(int64_t n_cells, co
             }
             const int tl = m0 + g;  // this lane's row of D
             if (tl < nt_steps) {
-                const double b0 = sbeta[2 * tl], b1 = sbeta[2 * tl + 1], pri = spri[tl];
+                double b0 = 0.0, b1 = 0.0, pri = 0.0;
+                if (MODE == 1) { b0 = sbeta[2 * tl]; b1 = sbeta[2 * tl + 1]; pri = spri[tl]; }
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
                     for (int h = 0; h < 2; ++h)
                         if (eok[nt][h]) {
-                            const double t_hat = (1.0 * b0 + ez[nt][h] * b1) + acc[nt][h];
-                            out[(int64_t)(t0 + tl) * n_cells + cbase + nt * 8 + q * 2 + h] = t_hat - (e0[nt][h] * (b0 - 0.0) + e1[nt][h] * (b1 - pri));
+                            double v;
+                            if (MODE == 1) {
+                                const double t_hat = (1.0 * b0 + ez[nt][h] * b1) + acc[nt][h];
+                                v = t_hat - (e0[nt][h] * (b0 - 0.0) + e1[nt][h] * (b1 - pri));
+                            } else
+                                v = acc[nt][h] + ez[nt][h];
+                            out[(int64_t)(t0 + tl) * n_cells + cbase + nt * 8 + q * 2 + h] = v;
                         }
             }
         }
+    }
+}
+
+// Dense IDW operator of one variable from its neighbour lists, valid while every station value is finite:
+//   W[s][c] = w_cs * f_cs / sum_j w_cj  (f = precipitation / radiation factor, 1 otherwise)
+//   temperature: + (z_c - zbar_c) / dz * (delta_{s,hi} - delta_{s,lo}) when the neighbours span more than 50 m, else the
+//   constant default_gradient * (z_c - zbar_c) goes to addc[c]   (temperature_gradient_scale_computer, inverse_distance.h:304-315)
+__global__ void idw_build_dense_kernel(int kind, int64_t n_cells, int n_src, const double* __restrict__ cz, double default_gradient,
+                                       const int32_t* __restrict__ nb_idx, const double* __restrict__ nb_w, const double* __restrict__ nb_f,
+                                       const int32_t* __restrict__ nb_n, double* __restrict__ W /* [n_src][cells] */, double* __restrict__ addc) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cells) return;
+    for (int s = 0; s < n_src; ++s) W[(int64_t)s * n_cells + c] = 0.0;
+    const int cnt = nb_n[c];
+    addc[c] = 0.0;
+    if (cnt == 0) { W[c] = nan_(); return; }  // no station in reach: 0/0 in the reference
+    double sum_w = 0.0;
+    for (int j = 0; j < cnt; ++j) sum_w += nb_w[(int64_t)j * n_cells + c];
+    for (int j = 0; j < cnt; ++j) {
+        const int k = nb_idx[(int64_t)j * n_cells + c];
+        const double w = nb_w[(int64_t)j * n_cells + c];
+        const double f = (kind == IDW_PRECIPITATION || kind == IDW_RADIATION) ? nb_f[(int64_t)j * n_cells + c] : 1.0;
+        W[(int64_t)k * n_cells + c] += w * f / sum_w;
+    }
+    if (kind == IDW_TEMPERATURE) {
+        int mn = -1, mx = -1;
+        double zmn = 0, zmx = 0, zbar = 0.0;
+        for (int j = 0; j < cnt; ++j) {
+            const int k = nb_idx[(int64_t)j * n_cells + c];
+            const double h = nb_f[(int64_t)j * n_cells + c];  // station height
+            zbar += nb_w[(int64_t)j * n_cells + c] * h;
+            if (j == 0) { mn = mx = k; zmn = zmx = h; }
+            else if (h < zmn) { mn = k; zmn = h; }
+            else if (h > zmx) { mx = k; zmx = h; }
+        }
+        zbar /= sum_w;
+        const double dz = zmx - zmn, lever = cz[c] - zbar;
+        if (cnt > 1 && dz > 50.0) {
+            W[(int64_t)mx * n_cells + c] += lever / dz;
+            W[(int64_t)mn * n_cells + c] -= lever / dz;
+        } else
+            addc[c] = default_gradient * lever;
     }
 }
 

@@ -324,6 +324,10 @@ class RegionModel:
     def set_stream(self, cuda_stream_ptr):
         self._ck(self._L.sb2_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
 
+    def set_idw_dense(self, on):
+        """IDW as a dense tensor-core contraction when all station values are finite (default on); off = per-neighbour kernel."""
+        self._ck(self._L.sb2_set_idw_dense(self._h, C.c_int(1 if on else 0)))
+
     def kernel_launches(self):
         return int(self._L.sb2_kernel_launches(self._h))
 

@@ -102,3 +102,26 @@ def test_single_temperature_source_is_copied_and_missing_variable_stays_nan(sb):
     assert np.all(np.isnan(m.cell_forcing("wind_speed")))
     # cell-major readback is the transpose
     assert np.array_equal(m.cell_forcing("temperature", layout=sb.capi.CELL_MAJOR), t.T)
+
+
+def test_dense_tensor_core_idw_equals_per_neighbour_idw(sb):
+    """All station values finite: IDW runs as one dense DMMA contraction; it must agree with the per-neighbour kernel (which is
+    bit-identical to the reference's operation order) to round-off, including cells with no station in reach and both
+    temperature-gradient regimes (height span above / below 50 m)."""
+    n, T, S = 3000, 200, 40
+    geo, ta, env = _region(sb, n, T, S, config_index=16)
+    xyz = env.temperature[0].copy()
+    xyz[: S // 2, 2] = 500.0 + np.arange(S // 2) * 0.5   # a flat cluster: cells near it see < 50 m height span -> default gradient
+    env.temperature = (xyz, env.temperature[1])
+    ip = sb.InterpolationParameter(use_idw_for_temperature=1)
+    ip.temperature_idw.max_members = 5
+    ip.wind_speed.max_distance = 12000.0    # some cells have no wind station -> NaN in both paths
+    out = {}
+    for dense in (True, False):
+        m = sb.PTGSKOptModel(geo)
+        m.set_idw_dense(dense)
+        m.run_interpolation(ip, ta, env)
+        out[dense] = {k: m.cell_forcing(k) for k in FORCING}
+    assert np.isnan(out[False]["wind_speed"]).any() and not np.isnan(out[False]["wind_speed"]).all()
+    for k in FORCING:
+        assert_parity(out[True][k], out[False][k], "dense vs per-neighbour idw " + k, rtol=1e-13)
