@@ -41,6 +41,11 @@ extern "C" {
 
 const char* sho_last_error() { return g_err.c_str(); }
 int sho_hardware_concurrency() { return int(std::thread::hardware_concurrency()); }
+#ifdef SHO_COUNT
+void sho_counters(long long* out, int reset) {  // tools/cost_model.py
+    for (int i = 0; i < dm::C_N; ++i) { out[i] = dm::g_cnt.v[i]; if (reset) dm::g_cnt.v[i] = 0; }
+}
+#endif
 
 // ---- calendar -------------------------------------------------------------
 int64_t sho_day_of_year(int64_t t_us) { return int64_t(calendar::day_of_year(t_us)); }

@@ -113,39 +113,50 @@ inline double lgamma_(double a) { return dm::lgamma(a); }  // boost::math::lgamm
 inline double gamma_prefix(double a, double x) { return dm::exp(a * dm::log(x) - x - lgamma_(a)); }
 
 // Regularised lower incomplete gamma P(a,x), a>0, x>=0.   Replaces boost::math::gamma_p
-// (gamma_snow.h:195-197).  Full-double evaluation: power series for x < a+1, modified-Lentz
-// continued fraction for Q otherwise (Abramowitz & Stegun 6.5.29 / 6.5.31).  "parity unpinned"
-// versus boost's reduced-precision policies, see header.
+// (gamma_snow.h:195-197).  Full-double evaluation: power series for x < a+1 (Abramowitz & Stegun 6.5.29), continued
+// fraction for Q otherwise (6.5.31).  "parity unpinned" versus boost's reduced-precision policies, see header.
+// Both are evaluated WITHOUT a division per term (the B200 kernels evaluate the identical sequence, sb2_math.cuh):
+//   series    sum_{n>=0} x^n / (a (a+1) .. (a+n)) carried as the fraction P/Q:  Q *= a+n,  P = P (a+n) + x^n;  the term test
+//             "term < sum * 1e-16" reads  x^n < P * 1e-16;  one division P/Q at the end
+//   fraction  1/(b0 + a1/(b1 + a2/(b2 + ..))), b_i = x + 2i + 1 - a, a_i = -i (i - a), by the forward recurrence
+//             A_i = b_i A_{i-1} + a_i A_{i-2} (same for B), value B_i/A_i; converged when successive convergents agree to 1e-16
+//   P, Q, x^n (A, B) are rescaled by the exact factor 2^-500 whenever the high word of Q (|A|) exceeds that of 2^500.
 inline double gamma_p(double a, double x) {
     if (!(x > 0.0)) return 0.0;
     if (std::isinf(x)) return 1.0;
     const double eps = 1.0e-16;
+    const double small = 3.0549363634996047e-151;  // 2^-500
     const double pre = gamma_prefix(a, x);
     if (x < a + 1.0) {
-        double ap = a, del = 1.0 / a, sum = del;
+        double ap = a, P = 1.0, Q = a, xn = 1.0;
+        SHO_CNT(C_GSER_CALLS, 1);
         for (int n = 0; n < 2000; ++n) {
+            SHO_CNT(C_GSER_ITER, 1);
             ap += 1.0;
-            del *= x / ap;
-            sum += del;
-            if (del < sum * eps) break;
+            xn *= x;
+            Q *= ap;
+            P = std::fma(P, ap, xn);
+            if (xn < P * eps) break;
+            if (int32_t(dm::bits_of(Q) >> 32) > 0x5f300000) { Q *= small; P *= small; xn *= small; }  // high word of Q above that of 2^500
         }
-        return sum * pre;
+        return (P / Q) * pre;
     }
-    const double tiny = 1.0e-300;
-    double b = x + 1.0 - a, c = 1.0 / tiny, d = 1.0 / b, h = d;
+    double b = x + 1.0 - a;
+    double A1 = 1.0, B1 = 0.0, A = b, B = 1.0;  // convergents i-1 and i
+    SHO_CNT(C_GCF_CALLS, 1);
     for (int i = 1; i < 2000; ++i) {
-        const double an = -double(i) * (double(i) - a);
+        SHO_CNT(C_GCF_ITER, 1);
+        const double di = double(i);
+        const double an = -di * (di - a);
         b += 2.0;
-        d = an * d + b;
-        if (std::fabs(d) < tiny) d = tiny;
-        c = b + an / c;
-        if (std::fabs(c) < tiny) c = tiny;
-        d = 1.0 / d;
-        const double del = d * c;
-        h *= del;
-        if (std::fabs(del - 1.0) < eps) break;
+        const double An = std::fma(b, A, an * A1);
+        const double Bn = std::fma(b, B, an * B1);
+        A1 = A; B1 = B; A = An; B = Bn;
+        const double m1 = A * B1, m0 = A1 * B;
+        if (std::fabs(m1 - m0) < eps * std::fabs(m1)) break;
+        if (int32_t((dm::bits_of(A) >> 32) & 0x7fffffff) > 0x5f300000) { A *= small; B *= small; A1 *= small; B1 *= small; }
     }
-    return 1.0 - pre * h;
+    return 1.0 - pre * (B / A);
 }
 
 // boost::math::tools::brent_find_minima(f, min, max, bits, max_iter) -> x, restated literally
@@ -190,6 +201,7 @@ inline double brent_find_minima(F f, double min, double max, int bits, int max_i
         }
         u = (std::fabs(delta) >= fract1) ? (x + delta) : (delta > 0 ? (x + std::fabs(fract1)) : (x - std::fabs(fract1)));
         fu = f(u);
+        SHO_CNT(C_BRENT_EVAL, 1);
         ++evals;
         if (fu <= fx) {
             if (u >= x) min = x; else max = x;
@@ -345,7 +357,9 @@ struct calculator {
                 dxdt_new = log_transform_f(x_new, p, e);
                 const double x_err = dt * dc1 * dxdt + dt * dc3 * k3 + dt * dc4 * k4 + dt * dc5 * k5 + dt * dc6 * k6 + dt * dc7 * dxdt_new;
                 const double err = std::fabs(x_err) / (eps_abs + eps_rel * (1.0 * std::fabs(x) + (1.0 * dt) * std::fabs(dxdt)));
+                SHO_CNT(C_KIR_TRY, 1);
                 if (err > 1.0) {
+                    SHO_CNT(C_KIR_REJECT, 1);
                     dt *= std::max(9.0 / 10.0 * dm::pow(err, -1.0 / (4 - 1)), 1.0 / 5.0);
                     if (st) st->rejected++;
                     if (++fails >= 500) throw std::runtime_error("Max number of iterations exceeded (500). A new step size was not found.");
@@ -459,12 +473,14 @@ struct calculator {
     double corr_lwc(const double z1, const double a1, const double b1, double /*z2*/, const double a2, const double b2,
                     int* n_eval = nullptr) const {  // :214-227
         double Q1 = calc_q(a1, b1, z1);
+        SHO_CNT(C_BRENT_CALLS, 1);
         return special::brent_find_minima(
             [Q1, a2, b2, this](double z) -> double { double f = this->calc_q(a2, b2, z) - Q1; return f * f; },
             0.0, z1, 12, 60, n_eval);
     }
     void calc_snow_state(const double shape, const double scale, const double y0, const double lambda, const double lwd,
                          const double max_water_frac, const double temp_swe, double& swe, double& sca) const {  // :230-260
+        SHO_CNT(C_SNOW_STATE, 1);
         double y = 0.0, y1 = 0.0;
         const double m = shape * scale;
         if (lambda <= 0.0) {
@@ -509,6 +525,7 @@ struct calculator {
     void step(state& s, response& r, utctime t, utctimespan dt, const parameter& p, const double T, const double rad,
               const double prec_mm_h, const double wind_speed, const double rel_hum, const double forest_fraction,
               const double altitude) const {
+        SHO_CNT(C_CELL_STEPS, 1);
         double sdc_melt_mean = s.sdc_melt_mean;
         double acc_melt = s.acc_melt;
         double iso_pot_energy = s.iso_pot_energy;
@@ -534,6 +551,7 @@ struct calculator {
         double sca = 0.0, storage = 0.0, outflow = 0.0;
 
         const double min_albedo = p.min_albedo;
+        SHO_CNT(C_GS_ACTIVE, 1);
         const double max_albedo = p.max_albedo;
         const double snow_cv = p.effective_snow_cv(forest_fraction, altitude);
         const double albedo_range = max_albedo - min_albedo;

@@ -19,6 +19,19 @@
 #include <cstring>
 #include <limits>
 
+// Optional operation counters (tools/cost_model.py builds a second copy of the library with -DSHO_COUNT, single-threaded runs only).
+#ifdef SHO_COUNT
+namespace sho { namespace dm {
+struct counters_t { long long v[16]; };
+enum { C_EXP, C_LOG, C_LGAMMA, C_GSER_CALLS, C_GSER_ITER, C_GCF_CALLS, C_GCF_ITER, C_BRENT_CALLS, C_BRENT_EVAL, C_KIR_TRY, C_KIR_REJECT, C_SNOW_STATE,
+       C_GS_ACTIVE, C_CELL_STEPS, C_N };
+inline counters_t g_cnt{};
+} }
+#define SHO_CNT(i, n) (::sho::dm::g_cnt.v[::sho::dm::i] += (n))
+#else
+#define SHO_CNT(i, n) ((void)0)
+#endif
+
 namespace sho {
 namespace dm {
 
@@ -28,6 +41,7 @@ inline double pow2i(int k) { return from_bits(uint64_t(k + 1023) << 52); }  // 2
 
 // exp(x): k = floor(x/ln2 + 1/2), r = x - k*ln2 (two fused steps), degree-13 Taylor polynomial by Estrin's scheme, scaled by 2^k
 inline double exp(double x) {
+    SHO_CNT(C_EXP, 1);
     if (x != x) return x;
     if (x > 709.782712893384) return std::numeric_limits<double>::infinity();
     if (x < -745.1332191019412) return 0.0;
@@ -56,6 +70,7 @@ inline double exp(double x) {
 // log(x): x = 2^e * m, m in (sqrt(1/2), sqrt(2)], f = m-1, s = f/(2+f), log(1+f) = f - f^2/2 + s*(f^2/2 + R(s^2)),
 // R(z) = z * sum_{k=0..9} 2/(2k+3) z^k  (the atanh series, Estrin's scheme)
 inline double log(double x) {
+    SHO_CNT(C_LOG, 1);
     if (x != x || x < 0.0) return std::numeric_limits<double>::quiet_NaN();
     if (x == 0.0) return -std::numeric_limits<double>::infinity();
     if (x == std::numeric_limits<double>::infinity()) return x;
@@ -97,6 +112,7 @@ inline double pow8(double x) { double y = x * x; y = y * y; return y * y; }
 
 // lgamma(a), a > 0: shift a up to >= 12 by the recurrence, then the Stirling series
 inline double lgamma(double a) {
+    SHO_CNT(C_LGAMMA, 1);
     double prod = 1.0;
     while (a < 12.0) { prod *= a; a += 1.0; }
     const double ai = 1.0 / a, ai2 = ai * ai;

@@ -185,34 +185,39 @@ SB2_HD double dmin(double a, double b) { return b < a ? b : a; }  // std::min(a,
 // x^a e^-x / Gamma(a), the prefix shared by P(a,x) and its a-derivative term (gamma_snow.h:245,254)
 __device__ __forceinline__ double gamma_prefix(double a, double x, double lgamma_a) { return sb_exp(a * sb_log(x) - x - lgamma_a); }
 
-// Regularised lower incomplete gamma P(a,x) given the prefix: series for x < a+1, Lentz continued fraction otherwise.
+// Regularised lower incomplete gamma P(a,x) given the prefix: series for x < a+1, continued fraction for Q otherwise, both
+// without a division per term (an fp64 division is ~30 instructions; the series runs 10-40 terms per call and was the single
+// hottest loop of the pt_gs_k kernel).  The series is carried as the fraction P/Q (Q *= a+n, P = P (a+n) + x^n), the continued
+// fraction by the forward recurrence of its convergents A_i/B_i; exact 2^-500 rescaling keeps them in range.
 __device__ __noinline__ double gamma_p_with_prefix(double a, double x, double pre) {
     const double eps = 1.0e-16;
+    const double small = 3.0549363634996047e-151;  // 2^-500
     if (x < a + 1.0) {
-        double ap = a, del = 1.0 / a, sum = del;
+        double ap = a, P = 1.0, Q = a, xn = 1.0;
         for (int n = 0; n < 2000; ++n) {
             ap += 1.0;
-            del *= x / ap;
-            sum += del;
-            if (del < sum * eps) break;
+            xn *= x;
+            Q *= ap;
+            P = fma(P, ap, xn);
+            if (xn < P * eps) break;
+            if (__double2hiint(Q) > 0x5f300000) { Q *= small; P *= small; xn *= small; }  // Q > 2^500 (Q > 0: high word decides)
         }
-        return sum * pre;
+        return (P / Q) * pre;
     }
-    const double tiny = 1.0e-300;
-    double b = x + 1.0 - a, c = 1.0 / tiny, d = 1.0 / b, h = d;
+    double b = x + 1.0 - a;
+    double A1 = 1.0, B1 = 0.0, A = b, B = 1.0;
     for (int i = 1; i < 2000; ++i) {
-        const double an = -double(i) * (double(i) - a);
+        const double di = double(i);
+        const double an = -di * (di - a);
         b += 2.0;
-        d = an * d + b;
-        if (fabs(d) < tiny) d = tiny;
-        c = b + an / c;
-        if (fabs(c) < tiny) c = tiny;
-        d = 1.0 / d;
-        const double del = d * c;
-        h *= del;
-        if (fabs(del - 1.0) < eps) break;
+        const double An = fma(b, A, an * A1);
+        const double Bn = fma(b, B, an * B1);
+        A1 = A; B1 = B; A = An; B = Bn;
+        const double m1 = A * B1, m0 = A1 * B;
+        if (fabs(m1 - m0) < eps * fabs(m1)) break;
+        if ((__double2hiint(A) & 0x7fffffff) > 0x5f300000) { A *= small; B *= small; A1 *= small; B1 *= small; }  // |A| > 2^500
     }
-    return 1.0 - pre * h;
+    return 1.0 - pre * (B / A);
 }
 
 __device__ __forceinline__ double gamma_p(double a, double x, double lgamma_a) {

@@ -81,7 +81,11 @@ struct PtgskRunArgs {
     // region parameter replaced by ens_params[e] (cells with a catchment override keep it, model_calibration.h:830-832)
     const PtgskParam* __restrict__ ens_params;  // null = no ensemble
     int64_t ens_state_stride, ens_partial_stride;
+    // phase pipeline scratch, element (local step i, cell c) at scr[k][i*n_cells + c]:
+    // 0 potential evapotranspiration [mm/h], 1 long-wave addend, 2 turbulent addend, 3 snow outflow [mm/h], 4 snow covered area
+    double* __restrict__ scr[5];
 };
+enum : int { SCR_POT = 0, SCR_LW = 1, SCR_TADD = 2, SCR_OUTFLOW = 3, SCR_SCA = 4 };
 
 struct GsState { double albedo, lwc, surface_heat, alpha, sdc_melt_mean, acc_melt, iso_pot_energy, temp_swe; };
 // Exact memoisation across steps.  The snow state a step ends with (calc_snow_state at gamma_snow.h:472) is what the next
@@ -259,12 +263,31 @@ __device__ __forceinline__ void gs_reset_snow_pack(double& sca, double& lwc, dou
     acc_melt = -1.0;
 }
 
-// gamma_snow::calculator::step, gamma_snow.h:291-493
-__device__ __forceinline__ void gs_step(GsState& s, GsCache& cache, double& r_sca, double& r_storage, double& r_outflow, const PtgskParam& p, int doy,
-                                        int sec_of_year, double dt_seconds, double dt_us, double BB0, double T, double rad, double prec_mm_h,
-                                        double wind_speed, double rel_hum, double forest_fraction, double altitude) {
+// The addends of the energy balance that depend on the forcing (and parameters) only, gamma_snow.h:345-392: the long-wave term
+// and the turbulent / surface-emission term.  Evaluated per step inside the fused kernel, or for a whole window by
+// ptgsk_forcing_terms_kernel (no state involved); each is one addend of `effect`, so the sum keeps the reference's order.
+__device__ __forceinline__ double gs_vapour_pressure(double T, double rel_hum) {
+    double vapour_pressure = 33.864 * (sb_pow8(7.38e-3 * T + 0.8072) - 1.9e-5 * fabs(1.8 * T + 48.0) + 1.316e-3) * rel_hum;
+    if (T < 0.0) vapour_pressure *= 1.0 + 9.72e-3 * T + 4.2e-5 * T * T;
+    return vapour_pressure;
+}
+__device__ __forceinline__ void gs_energy_terms(const PtgskParam& p, double BB0, double T, double wind_speed, double rel_hum, double& lw, double& tadd) {
+    const double tol = 1.0e-10, sigma = 5.670373e-8;
+    const double T_k = T + 273.15;
+    const double turb = p.wind_scale * wind_speed + p.wind_const;
+    const double vapour_pressure = gs_vapour_pressure(T, rel_hum);
+    lw = 0.98 * sigma * sb_pow(vapour_pressure / T_k, 6.87e-2) * sb_pow4(T_k);
+    const double sst = dmin(0.0, 1.16 * T - 2.09);
+    if (sst > -tol) tadd = turb * (T + 1.7 * (vapour_pressure - 6.12)) - BB0;
+    else tadd = turb * (T - sst + 1.7 * (vapour_pressure - 6.132 * sb_exp(0.103 * T - 0.186))) - 0.98 * sigma * sb_pow4(sst + 273.15);
+}
+
+// gamma_snow::calculator::step, gamma_snow.h:291-493, given the two forcing-only addends (lw, tadd) of gs_energy_terms
+__device__ __forceinline__ void gs_step_core(GsState& s, GsCache& cache, double& r_sca, double& r_storage, double& r_outflow, const PtgskParam& p, int doy,
+                                             int sec_of_year, double dt_seconds, double dt_us, double BB0, double T, double rad, double prec_mm_h,
+                                             double lw, double tadd, double wind_speed, double rel_hum, double forest_fraction, double altitude) {
     const double tol = 1.0e-10;
-    const double melt_heat = 333660.0, water_heat = 4180.0, ice_heat = 2050.0, sigma = 5.670373e-8;
+    const double melt_heat = 333660.0, water_heat = 4180.0, ice_heat = 2050.0;
     double sdc_melt_mean = s.sdc_melt_mean;
     double acc_melt = s.acc_melt;
     double iso_pot_energy = s.iso_pot_energy;
@@ -293,11 +316,6 @@ __device__ __forceinline__ void gs_step(GsState& s, GsCache& cache, double& r_sc
     const double snow_cv = p.snow_cv + forest_fraction * p.snow_cv_forest_factor + altitude * p.snow_cv_altitude_factor;
     const double albedo_range = max_albedo - min_albedo;
 
-    const double T_k = T + 273.15;
-    const double turb = p.wind_scale * wind_speed + p.wind_const;
-    double vapour_pressure = 33.864 * (sb_pow8(7.38e-3 * T + 0.8072) - 1.9e-5 * fabs(1.8 * T + 48.0) + 1.316e-3) * rel_hum;
-    if (T < 0.0) vapour_pressure *= 1.0 + 9.72e-3 * T + 4.2e-5 * T * T;
-
     if (snow > tol) albedo += snow * albedo_range / p.snowfall_reset_depth;
     else {
         if (T < 0.0) albedo -= p.slow_albedo_decay_step;
@@ -306,21 +324,19 @@ __device__ __forceinline__ void gs_step(GsState& s, GsCache& cache, double& r_sc
     albedo = dmax(dmin(albedo, max_albedo), min_albedo);
 
     double effect = rad * (1.0 - albedo);
-    effect += 0.98 * sigma * sb_pow(vapour_pressure / T_k, 6.87e-2) * sb_pow4(T_k);
+    effect += lw;
 
     if (T > 0.0 && snow < tol) effect += rain * T * water_heat / dt_seconds;
     if (T <= 0.0 && rain < tol) effect += snow * T * ice_heat / dt_seconds;
 
     if (p.calculate_iso_pot_energy) {
-        const double iso_effect = effect - BB0 + turb * (T + 1.7 * (vapour_pressure - 6.12));
+        const double turb = p.wind_scale * wind_speed + p.wind_const;
+        const double iso_effect = effect - BB0 + turb * (T + 1.7 * (gs_vapour_pressure(T, rel_hum) - 6.12));
         iso_pot_energy += iso_effect * dt_seconds / melt_heat;
     }
 
     const double sst = dmin(0.0, 1.16 * T - 2.09);
-    if (sst > -tol) effect += turb * (T + 1.7 * (vapour_pressure - 6.12)) - BB0;
-    else {
-        effect += turb * (T - sst + 1.7 * (vapour_pressure - 6.132 * sb_exp(0.103 * T - 0.186))) - 0.98 * sigma * sb_pow4(sst + 273.15);
-    }
+    effect += tadd;
 
     double delta_sh = -surface_heat;
     surface_heat = p.surface_magnitude * ice_heat * sst * 0.5;
@@ -418,6 +434,19 @@ __device__ __forceinline__ void gs_step(GsState& s, GsCache& cache, double& r_sc
     r_sca = sca;
     r_storage = storage;
     r_outflow = outflow * 3600000000.0 / dt_us;
+}
+
+// the whole step (fused kernel): the early exit of :313-322 is taken before any transcendental is evaluated
+__device__ __forceinline__ void gs_step(GsState& s, GsCache& cache, double& r_sca, double& r_storage, double& r_outflow, const PtgskParam& p, int doy,
+                                        int sec_of_year, double dt_seconds, double dt_us, double BB0, double T, double rad, double prec_mm_h,
+                                        double wind_speed, double rel_hum, double forest_fraction, double altitude) {
+    double lw = 0.0, tadd = 0.0;
+    const double prec = prec_mm_h * dt_us / 3600000000.0;
+    const double acc = (doy == p.winter_end_day_of_year) ? 0.0 : s.acc_melt;
+    const bool bare = ((T < p.tx) ? prec : 0.0) < 1.0e-10 && s.sdc_melt_mean < 1.0e-10 && acc < 0.0;
+    if (!bare) gs_energy_terms(p, BB0, T, wind_speed, rel_hum, lw, tadd);
+    gs_step_core(s, cache, r_sca, r_storage, r_outflow, p, doy, sec_of_year, dt_seconds, dt_us, BB0, T, rad, prec_mm_h, lw, tadd, wind_speed, rel_hum,
+                 forest_fraction, altitude);
 }
 
 // ---- priestley_taylor, core/priestley_taylor.h:75-103 -------------------------------------------------
@@ -679,6 +708,215 @@ __global__ void __launch_bounds__(SB2_BLOCK, SB2_MINBLOCKS) ptgsk_run_kernel(con
         state[0 * n + cc] = gs.albedo; state[1 * n + cc] = gs.lwc; state[2 * n + cc] = gs.surface_heat; state[3 * n + cc] = gs.alpha;
         state[4 * n + cc] = gs.sdc_melt_mean; state[5 * n + cc] = gs.acc_melt; state[6 * n + cc] = gs.iso_pot_energy;
         state[7 * n + cc] = gs.temp_swe; state[8 * n + cc] = kq;
+        if (failed) atomicOr(a.error_flag, ERR_KIRCHNER_STEP);
+    }
+}
+
+// ---- the phase pipeline (the production path of run_cells) ----------------------------------------------------------
+// The stack of one step is a chain  forcing -> snow -> response  with no feedback from the Kirchner response into the snow
+// pack, so a window of steps is run as three kernels that hand [step][cell] arrays to each other:
+//   A  ptgsk_forcing_terms_kernel   stateless: Priestley-Taylor potential evapotranspiration and the two forcing-only addends of
+//                                   the snow energy balance, one thread per (cell, group of steps), full occupancy
+//   B  ptgsk_snow_kernel            gamma_snow over the window, eight state values in registers, data-dependent (snow / no snow,
+//                                   series lengths) -- its divergence no longer stalls the ODE solver
+//   C  ptgsk_response_kernel        glacier melt, actual evapotranspiration, Kirchner, discharge, catchment partial sums:
+//                                   uniform control flow, few registers, many resident warps
+// Same device functions, same operation order per cell as the fused kernel: results are bit-identical to it.  The extra HBM
+// traffic (five scratch arrays written and read once) is paid from a memory system that the fp64-bound stack leaves >90 % idle.
+#ifndef SB2_BLOCK_A
+#define SB2_BLOCK_A 128
+#endif
+#ifndef SB2_STEPS_A
+#define SB2_STEPS_A 8      // steps per thread of the forcing-terms kernel
+#endif
+#ifndef SB2_BLOCK_B
+#define SB2_BLOCK_B 32
+#endif
+#ifndef SB2_MINBLOCKS_B
+#define SB2_MINBLOCKS_B 16
+#endif
+#ifndef SB2_BLOCK_C
+#define SB2_BLOCK_C 64
+#endif
+#ifndef SB2_MINBLOCKS_C
+#define SB2_MINBLOCKS_C 10
+#endif
+
+__global__ void __launch_bounds__(SB2_BLOCK_A) ptgsk_forcing_terms_kernel(const PtgskRunArgs a) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.n_cells) return;
+    if (a.active != nullptr && a.active[c] == 0) return;
+    const PtgskParam& p = a.params[a.pset[c]];
+    const double pt_albedo = p.pt_albedo, pt_alpha = p.pt_alpha;
+    const int64_t n = a.n_cells;
+    const int i0 = blockIdx.y * SB2_STEPS_A;
+    const int i1 = min(i0 + SB2_STEPS_A, a.n_steps);
+#pragma unroll 2
+    for (int i = i0; i < i1; ++i) {
+        const int64_t o = (int64_t)i * n + c;
+        const double temp = a.f[0][o], rad = a.f[2][o], wind = a.f[3][o], rel_hum = a.f[4][o];
+        double lw, tadd;
+        gs_energy_terms(p, a.bb0, temp, wind, rel_hum, lw, tadd);
+        a.scr[SCR_POT][o] = pt_potential_evapotranspiration(pt_albedo, pt_alpha, temp, rad, rel_hum) * 3600.0;
+        a.scr[SCR_LW][o] = lw;
+        a.scr[SCR_TADD][o] = tadd;
+    }
+}
+
+// COLLECT bits used here: 2 snow sca/swe, 4 snow_outflow, 8 state series (the eight gamma_snow fields)
+template <int COLLECT>
+__global__ void __launch_bounds__(SB2_BLOCK_B, SB2_MINBLOCKS_B) ptgsk_snow_kernel(const PtgskRunArgs a) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.n_cells) return;
+    if (a.active != nullptr && a.active[c] == 0) return;
+    const PtgskParam& p = a.params[a.pset[c]];
+    const int64_t n = a.n_cells;
+    const double altitude = a.z[c], cell_area_m2 = a.area[c], forest_fraction = a.forest[c];
+    const double snow_storage_fraction = 1.0 - a.lake[c] - a.reservoir[c];
+    const bool iso = p.calculate_iso_pot_energy != 0;
+    double* __restrict__ state = a.state;
+    GsState gs;
+    gs.albedo = state[0 * n + c]; gs.lwc = state[1 * n + c]; gs.surface_heat = state[2 * n + c]; gs.alpha = state[3 * n + c];
+    gs.sdc_melt_mean = state[4 * n + c]; gs.acc_melt = state[5 * n + c]; gs.iso_pot_energy = state[6 * n + c];
+    gs.temp_swe = state[7 * n + c];
+    GsCache cache;
+    gs_cache_clear(cache);
+    double f_t = a.f[0][c], f_p = a.f[1][c], f_r = a.f[2][c], f_lw = a.scr[SCR_LW][c], f_ta = a.scr[SCR_TADD][c];
+    for (int i = 0; i < a.n_steps; ++i) {
+        const double temp = f_t, prec = f_p * p.p_corr_scale_factor, rad = f_r, lw = f_lw, tadd = f_ta;
+        const int64_t o = (int64_t)i * n + c;
+        if (i + 1 < a.n_steps) {
+            const int64_t o1 = o + n;
+            f_t = a.f[0][o1]; f_p = a.f[1][o1]; f_r = a.f[2][o1]; f_lw = a.scr[SCR_LW][o1]; f_ta = a.scr[SCR_TADD][o1];
+        }
+        const int64_t step = a.first_step + i;
+        const int64_t orow = (step - a.out_first_step) * n + c;
+        if (COLLECT & 8) {  // state at the beginning of the period, scale_snow applied (pt_gs_k.h:213-218,367)
+            a.st[1][orow] = gs.albedo;
+            a.st[2][orow] = gs.lwc * snow_storage_fraction;
+            a.st[3][orow] = gs.surface_heat;
+            a.st[4][orow] = gs.alpha;
+            a.st[5][orow] = gs.sdc_melt_mean;
+            a.st[6][orow] = gs.acc_melt;
+            a.st[7][orow] = gs.iso_pot_energy;
+            a.st[8][orow] = gs.temp_swe * snow_storage_fraction;
+        }
+        double wind = 0.0, rel_hum = 0.0;
+        if (iso) { wind = a.f[3][o]; rel_hum = a.f[4][o]; }
+        double sca, storage, outflow;
+        gs_step_core(gs, cache, sca, storage, outflow, p, a.day_of_year[step], a.sec_of_year[step], a.dt_seconds, a.dt_us, a.bb0, temp, rad, prec, lw,
+                     tadd, wind, rel_hum, forest_fraction, altitude);
+        a.scr[SCR_OUTFLOW][o] = outflow;
+        a.scr[SCR_SCA][o] = sca;
+        if (COLLECT & 2) { a.resp[2][orow] = sca; a.resp[3][orow] = storage * snow_storage_fraction; }
+        if (COLLECT & 4) a.resp[4][orow] = mmh_to_m3s(outflow * snow_storage_fraction, cell_area_m2);
+    }
+    if ((COLLECT & 8) && a.collect_end_state) {
+        const int64_t orow = (a.first_step + a.n_steps - a.out_first_step) * n + c;
+        a.st[1][orow] = gs.albedo;
+        a.st[2][orow] = gs.lwc * snow_storage_fraction;
+        a.st[3][orow] = gs.surface_heat;
+        a.st[4][orow] = gs.alpha;
+        a.st[5][orow] = gs.sdc_melt_mean;
+        a.st[6][orow] = gs.acc_melt;
+        a.st[7][orow] = gs.iso_pot_energy;
+        a.st[8][orow] = gs.temp_swe * snow_storage_fraction;
+    }
+    state[0 * n + c] = gs.albedo; state[1 * n + c] = gs.lwc; state[2 * n + c] = gs.surface_heat; state[3 * n + c] = gs.alpha;
+    state[4 * n + c] = gs.sdc_melt_mean; state[5 * n + c] = gs.acc_melt; state[6 * n + c] = gs.iso_pot_energy;
+    state[7 * n + c] = gs.temp_swe;
+}
+
+// COLLECT bits used here: 1 avg_discharge+charge, 4 glacier_melt/ae/pe, 8 state series (kirchner discharge)
+template <int COLLECT>
+__global__ void __launch_bounds__(SB2_BLOCK_C, SB2_MINBLOCKS_C) ptgsk_response_kernel(const PtgskRunArgs a) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in_range = c < a.n_cells;
+    const int64_t cc = in_range ? c : a.n_cells - 1;  // out-of-range lanes shadow the last cell, never store
+    const bool active = in_range && (a.active == nullptr || a.active[cc] != 0);
+    const unsigned lane = threadIdx.x & 31u;
+    const PtgskParam& p = a.params[a.pset[cc]];
+    const double cell_area_m2 = a.area[cc];
+    const double glacier_fraction = a.glacier[cc], lake = a.lake[cc], reservoir = a.reservoir[cc];
+    // run_pt_gs_k prologue, pt_gs_k.h:347-357
+    const double gm_direct = p.gm_direct_response;
+    const double gm_routed = 1 - gm_direct;
+    const double snow_storage_fraction = 1.0 - lake - reservoir;
+    const double kirchner_routed_prec = reservoir * (1.0 - p.reservoir_direct_response_fraction) + lake;
+    const double direct_response_fraction = glacier_fraction * gm_direct + reservoir * p.reservoir_direct_response_fraction;
+    const double kirchner_fraction = 1 - direct_response_fraction;
+    const double glacier_area_m2 = cell_area_m2 * glacier_fraction;
+    const double c1 = p.c1, c2 = p.c2, c3 = p.c3, ae_scale_factor = p.ae_scale_factor, gm_dtf = p.gm_dtf, p_corr = p.p_corr_scale_factor;
+    const int64_t n = a.n_cells;
+    double kq = a.state[8 * n + cc];
+
+    int my_slot = -1;
+    bool head = false;
+    if (a.partial != nullptr) {
+        my_slot = in_range ? a.slot[cc] : -1;
+        const int prev = __shfl_up_sync(0xffffffffu, my_slot, 1);
+        head = in_range && (lane == 0 || prev != my_slot);
+    }
+    double f_t = a.f[0][cc], f_p = a.f[1][cc], f_pot = a.scr[SCR_POT][cc], f_out = a.scr[SCR_OUTFLOW][cc], f_sca = a.scr[SCR_SCA][cc];
+    bool failed = false;
+    for (int i = 0; i < a.n_steps; ++i) {
+        const double temp = f_t, prec = f_p * p_corr, pot = f_pot, outflow = f_out, sca = f_sca;
+        if (i + 1 < a.n_steps) {
+            const int64_t o1 = (int64_t)(i + 1) * n + cc;
+            f_t = a.f[0][o1]; f_p = a.f[1][o1]; f_pot = a.scr[SCR_POT][o1]; f_out = a.scr[SCR_OUTFLOW][o1]; f_sca = a.scr[SCR_SCA][o1];
+        }
+        const int64_t step = a.first_step + i;
+        const int64_t orow = (step - a.out_first_step) * n + cc;
+        double out_q = 0.0, out_charge = 0.0;
+        if (active) {
+            if (COLLECT & 8) a.st[0][orow] = mmh_to_m3s(kq, cell_area_m2);
+            // glacier_melt::step, glacier_melt.h:47-52
+            const double sca_m2 = cell_area_m2 * sca;
+            const double gm_melt_m3s =
+                (glacier_area_m2 <= sca_m2 || temp <= 0.0) ? 0.0 : gm_dtf * temp * (glacier_area_m2 - sca_m2) * (0.001 / 86400.0);
+            // actual_evapotranspiration::calculate_step, actual_evapotranspiration.h:56-62
+            const double ae = pot * (1.0 - sb_exp(-kq * 3.0 / ae_scale_factor)) * (1.0 - dmax(sca, glacier_fraction));
+            const double gm_mmh = m3s_to_mmh(gm_melt_m3s, cell_area_m2);
+            double q_avg;
+            if (!kirchner_step(c1, c2, c3, a.dt_hours, kq, q_avg, outflow * snow_storage_fraction + prec * kirchner_routed_prec + gm_routed * gm_mmh,
+                               ae)) {
+                failed = true;
+                q_avg = nan("");
+            }
+            const double total_discharge = dmax(0.0, prec - ae) * direct_response_fraction + gm_direct * gm_mmh + q_avg * kirchner_fraction;
+            const double charge_m3s =
+                +mmh_to_m3s(prec, cell_area_m2) - mmh_to_m3s(ae, cell_area_m2) + gm_melt_m3s - mmh_to_m3s(total_discharge, cell_area_m2);
+            out_q = mmh_to_m3s(total_discharge, cell_area_m2);
+            out_charge = charge_m3s;
+            if (COLLECT & 1) { a.resp[0][orow] = out_q; a.resp[1][orow] = charge_m3s; }
+            if (COLLECT & 4) {
+                a.resp[5][orow] = gm_melt_m3s;
+                a.resp[6][orow] = ae;
+                a.resp[7][orow] = pot;
+            }
+        }
+        if (a.partial != nullptr) {  // warp-uniform
+            double v0 = out_q, v1 = out_charge;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const double o0 = __shfl_down_sync(0xffffffffu, v0, off);
+                const double o1 = __shfl_down_sync(0xffffffffu, v1, off);
+                const int os = __shfl_down_sync(0xffffffffu, my_slot, off);
+                if (lane + off < 32 && os == my_slot) { v0 += o0; v1 += o1; }
+            }
+            if (head) {
+                double* dst = a.partial + ((int64_t)i * a.n_slots + my_slot) * 2;
+                dst[0] = v0;
+                dst[1] = v1;
+            }
+        }
+    }
+    if (active) {
+        if ((COLLECT & 8) && a.collect_end_state) {
+            const int64_t orow = (a.first_step + a.n_steps - a.out_first_step) * n + cc;
+            a.st[0][orow] = mmh_to_m3s(kq, cell_area_m2);
+        }
+        a.state[8 * n + cc] = kq;
         if (failed) atomicOr(a.error_flag, ERR_KIRCHNER_STEP);
     }
 }
