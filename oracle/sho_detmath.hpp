@@ -39,29 +39,32 @@ inline uint64_t bits_of(double x) { uint64_t u; std::memcpy(&u, &x, 8); return u
 inline double from_bits(uint64_t u) { double x; std::memcpy(&x, &u, 8); return x; }
 inline double pow2i(int k) { return from_bits(uint64_t(k + 1023) << 52); }  // 2^k, -1022 <= k <= 1023
 
-// exp(x): k = floor(x/ln2 + 1/2), r = x - k*ln2 (two fused steps), degree-13 Taylor polynomial by Estrin's scheme, scaled by 2^k
+// exp(x): k = rint(x/ln2) by the magic-number add (t = x/ln2 + 1.5*2^52: low word of t = k), r = x - k*ln2 (two fused steps),
+// exp(r) = 1 + (r + r^2 Q(r)) with the degree-11 Taylor Q split into even and odd Horner chains in r^2, scaled by 2^k
 inline double exp(double x) {
     SHO_CNT(C_EXP, 1);
     if (x != x) return x;
     if (x > 709.782712893384) return std::numeric_limits<double>::infinity();
     if (x < -745.1332191019412) return 0.0;
-    const double kf = std::floor(std::fma(x, 1.44269504088896338700e+00, 0.5));
+    const double t = std::fma(x, 1.44269504088896338700e+00, 6755399441055744.0);
+    const double kf = t - 6755399441055744.0;
     double r = std::fma(kf, -6.93147180369123816490e-01, x);
     r = std::fma(kf, -1.90821492927058770002e-10, r);
-    const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
-    const double a0 = std::fma(1.0 / 6.0, r, 0.5);
-    const double a1 = std::fma(1.0 / 120.0, r, 1.0 / 24.0);
-    const double a2 = std::fma(1.0 / 5040.0, r, 1.0 / 720.0);
-    const double a3 = std::fma(1.0 / 362880.0, r, 1.0 / 40320.0);
-    const double a4 = std::fma(1.0 / 39916800.0, r, 1.0 / 3628800.0);
-    const double a5 = std::fma(1.0 / 6227020800.0, r, 1.0 / 479001600.0);
-    const double b0 = std::fma(a1, r2, a0);
-    const double b1 = std::fma(a3, r2, a2);
-    const double b2 = std::fma(a5, r2, a4);
-    const double d0 = std::fma(b1, r4, b0);
-    const double Q = std::fma(b2, r8, d0);
-    double p = 1.0 + std::fma(r2, Q, r);
-    int k = int(kf);
+    const double z = r * r;
+    double qe = 1.0 / 479001600.0, qo = 1.0 / 6227020800.0;
+    qe = std::fma(qe, z, 1.0 / 3628800.0);
+    qo = std::fma(qo, z, 1.0 / 39916800.0);
+    qe = std::fma(qe, z, 1.0 / 40320.0);
+    qo = std::fma(qo, z, 1.0 / 362880.0);
+    qe = std::fma(qe, z, 1.0 / 720.0);
+    qo = std::fma(qo, z, 1.0 / 5040.0);
+    qe = std::fma(qe, z, 1.0 / 24.0);
+    qo = std::fma(qo, z, 1.0 / 120.0);
+    qe = std::fma(qe, z, 0.5);
+    qo = std::fma(qo, z, 1.0 / 6.0);
+    const double Q = std::fma(r, qo, qe);
+    double p = 1.0 + std::fma(z, Q, r);
+    int k = int(uint32_t(bits_of(t) & 0xffffffffULL));
     if (k > 1023) { p *= pow2i(1023); k -= 1023; }
     if (k < -1022) { p *= pow2i(k + 1000); return p * pow2i(-1000); }      // one rounding into the subnormal range
     return p * pow2i(k);

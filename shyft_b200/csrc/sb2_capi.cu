@@ -150,6 +150,7 @@ struct sb2_model {
     DevArray<int32_t> d_slot, d_cat_ptr, d_cat_slots;
     int64_t n_slots = 0;
     DevArray<double> d_partial;
+    DevArray<double> d_scr[5];  // pt_gs_k phase pipeline scratch [partial_steps][n] (sb2_ptgsk.cuh)
     int partial_steps = 0;
     DevArray<int> d_error_flag;
     // routing (core/routing.h)
@@ -339,6 +340,8 @@ void launch_step_range(sb2_model* m, int64_t first, int64_t n_steps, bool collec
     if (m->partial_steps == 0) {
         // bound the scratch for the per-slot partial sums to ~256 MB
         int64_t ps = std::max<int64_t>(1, std::min<int64_t>(1024, (256LL << 20) / std::max<int64_t>(1, m->n_slots * 16)));
+        // pt_gs_k: the five scratch arrays of the phase pipeline are [ps][n] too; keep them within ~4 GB
+        if (m->stack == SB2_PT_GS_K) ps = std::max<int64_t>(16, std::min<int64_t>(ps, (4LL << 30) / (40 * std::max<int64_t>(1, n))));
         m->partial_steps = int(ps);
         m->d_partial.resize(size_t(ps) * m->n_slots * 2);
     }
@@ -362,13 +365,24 @@ void launch_step_range(sb2_model* m, int64_t first, int64_t n_steps, bool collec
             a.out_first_step = m->out_first;
             a.collect_end_state = (last && collect_end_state) ? 1 : 0;
             a.slot = m->d_slot.p; a.partial = m->d_partial.p; a.n_slots = m->n_slots; a.error_flag = m->d_error_flag.p;
-            const int g = grid_for(n, block);
-            switch (m->collect_bits & 15) {
-#define SB2_CASE(B) case B: ptgsk_run_kernel<B><<<g, block, 0, m->stream>>>(a); break;
-                SB2_CASE(0) SB2_CASE(1) SB2_CASE(2) SB2_CASE(3) SB2_CASE(4) SB2_CASE(5) SB2_CASE(6) SB2_CASE(7)
-                SB2_CASE(8) SB2_CASE(9) SB2_CASE(10) SB2_CASE(11) SB2_CASE(12) SB2_CASE(13) SB2_CASE(14) SB2_CASE(15)
+            // phase pipeline: forcing terms -> snow -> response (sb2_ptgsk.cuh), scratch [chunk][n] x 5
+            for (int k = 0; k < 5; ++k) {
+                m->d_scr[k].ensure(size_t(std::min<int64_t>(m->partial_steps, n_steps)) * n);
+                a.scr[k] = m->d_scr[k].p;
+            }
+            ptgsk_forcing_terms_kernel<<<dim3((unsigned)grid_for(n, SB2_BLOCK_A), (unsigned)grid_for(chunk, SB2_STEPS_A)), SB2_BLOCK_A, 0, m->stream>>>(a);
+            const int gb = grid_for(n, SB2_BLOCK_B), gc = grid_for(n, SB2_BLOCK_C);
+            switch (m->collect_bits & 14) {
+#define SB2_CASE(B) case B: ptgsk_snow_kernel<B><<<gb, SB2_BLOCK_B, 0, m->stream>>>(a); break;
+                SB2_CASE(0) SB2_CASE(2) SB2_CASE(4) SB2_CASE(6) SB2_CASE(8) SB2_CASE(10) SB2_CASE(12) SB2_CASE(14)
 #undef SB2_CASE
             }
+            switch (m->collect_bits & 13) {
+#define SB2_CASE(B) case B: ptgsk_response_kernel<B><<<gc, SB2_BLOCK_C, 0, m->stream>>>(a); break;
+                SB2_CASE(0) SB2_CASE(1) SB2_CASE(4) SB2_CASE(5) SB2_CASE(8) SB2_CASE(9) SB2_CASE(12) SB2_CASE(13)
+#undef SB2_CASE
+            }
+            m->launches += 2;
         } else {
             HbvRunArgs a{};
             a.n_cells = n;

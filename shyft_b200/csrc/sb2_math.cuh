@@ -5,7 +5,7 @@
 // and any other conforming machine produce identical bits.  Why: gamma_snow's Brent search (core/gamma_snow.h:214-227)
 // amplifies last-bit differences between math libraries to 1e-4-level differences in liquid water content; a 1e-9 parity
 // statement is only meaningful over one fixed operation sequence (DESIGN.md "Deterministic math").  The sequence:
-//   exp(x)    k = floor(x/ln2 + 0.5), r = fma(k,-ln2_lo, fma(k,-ln2_hi,x)), degree-13 Taylor polynomial (Estrin, fma), scaled by 2^k
+//   exp(x)    k = rint(x/ln2) (magic-number add), r = fma(k,-ln2_lo, fma(k,-ln2_hi,x)), degree-13 Taylor polynomial (even/odd Horner, fma), scaled by 2^k
 //   log(x)    x = 2^e*m, m in (sqrt(1/2), sqrt(2)], f = m-1, s = f/(2+f), f - f^2/2 + s*(f^2/2 + R(s^2)), R = atanh series to s^20
 //   pow(x,y)  exact for y = 0, 1, 2, 0.5; exp(y*log(x)) otherwise (x >= 0)
 //   lgamma(a) recurrence up to a >= 12, then the Stirling series to 1/a^13
@@ -63,25 +63,30 @@ static const double kMiscC_host[5] = SB2_MISC_COEFFS;
 #define SB2_MISC(i) kMiscC_host[i]
 #endif
 
-// reduced argument and polynomial of exp: returns p = exp(r) for x = k*ln2 + r
+// reduced argument and polynomial of exp: returns p = exp(r) for x = k*ln2 + r, |x| < 746
+//   k = round-to-nearest(x/ln2) by the magic-number add (t = x/ln2 + 1.5*2^52: the low word of t is k, t - 1.5*2^52 is k as a double)
+//   exp(r) = 1 + (r + r^2 Q(r)),  Q = Qe(r^2) + r Qo(r^2): two independent Horner chains, every fma takes ONE coefficient -- on sm_100a
+//   a constant operand of DFMA has to come from a uniform register, and one per instruction is what the ISA allows
 SB2_HD double sb_exp_core(double x, int& k) {
-    const double kf = floor(fma(x, SB2_MISC(0), 0.5));
+    const double t = fma(x, SB2_MISC(0), 6755399441055744.0);
+    const double kf = t - 6755399441055744.0;
     double r = fma(kf, SB2_MISC(1), x);
     r = fma(kf, SB2_MISC(2), r);
-    const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
-    const double a0 = fma(SB2_EXPC(1), r, SB2_EXPC(0));
-    const double a1 = fma(SB2_EXPC(3), r, SB2_EXPC(2));
-    const double a2 = fma(SB2_EXPC(5), r, SB2_EXPC(4));
-    const double a3 = fma(SB2_EXPC(7), r, SB2_EXPC(6));
-    const double a4 = fma(SB2_EXPC(9), r, SB2_EXPC(8));
-    const double a5 = fma(SB2_EXPC(11), r, SB2_EXPC(10));
-    const double b0 = fma(a1, r2, a0);
-    const double b1 = fma(a3, r2, a2);
-    const double b2 = fma(a5, r2, a4);
-    const double d0 = fma(b1, r4, b0);
-    const double Q = fma(b2, r8, d0);
-    k = int(kf);
-    return 1.0 + fma(r2, Q, r);
+    const double z = r * r;
+    double qe = SB2_EXPC(10), qo = SB2_EXPC(11);
+    qe = fma(qe, z, SB2_EXPC(8));
+    qo = fma(qo, z, SB2_EXPC(9));
+    qe = fma(qe, z, SB2_EXPC(6));
+    qo = fma(qo, z, SB2_EXPC(7));
+    qe = fma(qe, z, SB2_EXPC(4));
+    qo = fma(qo, z, SB2_EXPC(5));
+    qe = fma(qe, z, SB2_EXPC(2));
+    qo = fma(qo, z, SB2_EXPC(3));
+    qe = fma(qe, z, SB2_EXPC(0));
+    qo = fma(qo, z, SB2_EXPC(1));
+    const double Q = fma(r, qo, qe);
+    k = int(unsigned(bits_of(t) & 0xffffffffULL));
+    return 1.0 + fma(z, Q, r);
 }
 // the general path: NaN, overflow, underflow into the subnormal range
 #ifdef __CUDA_ARCH__
@@ -110,6 +115,19 @@ SB2_HD double sb_exp_inl(double x) {
     return p * pow2i(k);
 #endif
 }
+// The same value with the polynomial outside any branch: warp-synchronous callers (ptgsk_response_kernel) keep their control flow
+// uniform, so the compiler hoists the coefficients out of the loops; the general path patches the result of the rare lane.
+__device__ __forceinline__ double sb_exp_flat(double x) {
+#ifdef __CUDA_ARCH__
+    int k;
+    const double p = sb_exp_core(x, k);
+    double r = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+    if (!(fabs(x) < 690.0)) r = sb_exp_slow(x);
+    return r;
+#else
+    return sb_exp_inl(x);
+#endif
+}
 
 // Out-of-line copies for the device: the cell-step kernels call exp/log from some thirty places; one shared copy of each
 // keeps the step loop inside the instruction cache (inlined everywhere the pt_gs_k kernel was 136 KB of SASS and 22 % of
@@ -124,7 +142,7 @@ SB2_HD double sb_exp_inl(double x) {
 #endif
 SB2_MATH_FN double sb_exp(double x) { return sb_exp_inl(x); }
 
-SB2_MATH_FN double sb_log(double x) {
+SB2_HD double sb_log_inl(double x) {
     if (x != x || x < 0.0) return nan_();
     if (x == 0.0) return -inf_();
     if (x == inf_()) return x;
@@ -151,6 +169,7 @@ SB2_MATH_FN double sb_log(double x) {
     const double t = fma(s, hfsq + R, dk * SB2_MISC(4));
     return fma(dk, SB2_MISC(3), f - (hfsq - t));
 }
+SB2_MATH_FN double sb_log(double x) { return sb_log_inl(x); }
 
 SB2_HD double sb_pow(double x, double y) {
     if (y == 0.0) return 1.0;

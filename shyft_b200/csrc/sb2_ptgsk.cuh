@@ -475,19 +475,56 @@ __device__ __noinline__ double kirchner_rhs(double c1, double c2, double c3, dou
     const double g = sb_exp_inl(c1 + c2 * x + c3 * x * x);  // the two exponentials interleave
     return g >= 1.e-30 ? g * (pe * sb_exp_inl(-x) - 1.0) : 0.0;
 }
+// INL = true: the response kernel, whose whole step loop is ~1 000 instructions and stays inside the instruction cache when
+// every exp/log is expanded in place (no call / argument shuffling, coefficients in uniform registers)
+template <bool INL>
 struct KirchnerRhs {
     double c1, c2, c3, pe;  // pe = p - e
-    __device__ __forceinline__ double operator()(double x) const { return kirchner_rhs(c1, c2, c3, pe, x); }
+    __device__ __forceinline__ double operator()(double x) const {
+        if (INL) {
+            const double g = sb_exp_inl(c1 + c2 * x + c3 * x * x);
+            return g >= 1.e-30 ? g * (pe * sb_exp_inl(-x) - 1.0) : 0.0;
+        }
+        return kirchner_rhs(c1, c2, c3, pe, x);
+    }
 };
+
+// runge_kutta_dopri5::calc_state: the continuous extension at theta = (t1 - t_old)/dt_old (Appendix A.2 of SURVEY.md); only reached when a
+// model step took more than one sub-step, hence out of line
+__device__ __noinline__ double kirchner_calc_state(double x_old, double dtl, double theta, double k1, double k3, double k4, double k5, double k6,
+                                                   double k7) {
+    const double c1_ = 35.0 / 384.0, c3_ = 500.0 / 1113.0, c4_ = 125.0 / 192.0, c5_ = -2187.0 / 6784.0, c6_ = 11.0 / 84.0;
+    const double X1 = 5.0 * (2558722523.0 - 31403016.0 * theta) / 11282082432.0;
+    const double X3 = 100.0 * (882725551.0 - 15701508.0 * theta) / 32700410799.0;
+    const double X4 = 25.0 * (443332067.0 - 31403016.0 * theta) / 1880347072.0;
+    const double X5 = 32805.0 * (23143187.0 - 3489224.0 * theta) / 199316789632.0;
+    const double X6 = 55.0 * (29972135.0 - 7076736.0 * theta) / 822651844.0;
+    const double X7 = 10.0 * (7414447.0 - 829305.0 * theta) / 29380423.0;
+    const double theta_m_1 = theta - 1.0;
+    const double theta_sq = theta * theta;
+    const double A = theta_sq * (3.0 - 2.0 * theta);
+    const double B = theta_sq * theta_m_1;
+    const double C = theta_sq * theta_m_1 * theta_m_1;
+    const double D = theta * theta_m_1 * theta_m_1;
+    const double b1_theta = A * c1_ - C * X1 + D;
+    const double b3_theta = A * c3_ + C * X3;
+    const double b4_theta = A * c4_ - C * X4;
+    const double b5_theta = A * c5_ + C * X5;
+    const double b6_theta = A * c6_ - C * X6;
+    const double b7_theta = B + C * X7;
+    return 1.0 * x_old + dtl * b1_theta * k1 + dtl * b3_theta * k3 + dtl * b4_theta * k4 + dtl * b5_theta * k5 + dtl * b6_theta * k6 +
+           dtl * b7_theta * k7;
+}
 
 // One model step of the log-transformed Kirchner ODE with odeint's controlled dopri5 + dense output
 // (abs 1e-7, rel 1e-8): same accept/reject sequence, same step-size updates, same continuous extension.
+template <bool INL = false>
 __device__ __forceinline__ bool kirchner_step(double c1, double c2, double c3, double t1, double& q, double& q_avg, double p, double e) {
     const double eps_abs = 1.0e-7, eps_rel = 1.0e-8;
     if (q < 0.00001) q = 0.00001;
-    double x = sb_log(q);
+    double x = INL ? sb_log_inl(q) : sb_log(q);
     double t = 0.0, dt = t1;
-    const KirchnerRhs rhs{c1, c2, c3, p - e};
+    const KirchnerRhs<INL> rhs{c1, c2, c3, p - e};
     double dxdt = rhs(x);
     double area = 0.0, f_a = q, t_a = 0.0;
 
@@ -519,7 +556,14 @@ __device__ __forceinline__ bool kirchner_step(double c1, double c2, double c3, d
             x_new = 1.0 * x + dt * c1_ * dxdt + dt * c3_ * k3 + dt * c4_ * k4 + dt * c5_ * k5 + dt * c6_ * k6;
             dxdt_new = rhs(x_new);
             const double x_err = dt * dc1 * dxdt + dt * dc3 * k3 + dt * dc4 * k4 + dt * dc5 * k5 + dt * dc6 * k6 + dt * dc7 * dxdt_new;
-            const double err = fabs(x_err) / (eps_abs + eps_rel * (1.0 * fabs(x) + (1.0 * dt) * fabs(dxdt)));
+            const double err_num = fabs(x_err), err_den = eps_abs + eps_rel * (1.0 * fabs(x) + (1.0 * dt) * fabs(dxdt));
+            // err = err_num / err_den is compared with 1 (reject) and, only when another sub-step follows, sets the next dt.
+            // err_num < 0.75 err_den  =>  the rounded quotient is <= 1: accept without dividing when this sub-step reaches t1.
+            if (err_num < 0.75 * err_den && !(t + dt < t1)) {
+                t += dt;
+                break;
+            }
+            const double err = err_num / err_den;
             if (err > 1.0) {
                 dt *= dmax(9.0 / 10.0 * sb_pow(err, -1.0 / (4 - 1)), 1.0 / 5.0);
                 if (++fails >= 500) return false;
@@ -533,39 +577,123 @@ __device__ __forceinline__ bool kirchner_step(double c1, double c2, double c3, d
         x_old = x; k1 = dxdt; k7 = dxdt_new;
         x = x_new; dxdt = dxdt_new;
         if (t < t1) {
-            const double fq = sb_exp(x);
+            const double fq = INL ? sb_exp_inl(x) : sb_exp(x);
             area += 0.5 * (f_a + fq) * (t - t_a);
             f_a = fq; t_a = t;
         }
     }
-    {
-        const double dtl = t - t_old;
-        const double theta = (t1 - t_old) / dtl;
-        const double X1 = 5.0 * (2558722523.0 - 31403016.0 * theta) / 11282082432.0;
-        const double X3 = 100.0 * (882725551.0 - 15701508.0 * theta) / 32700410799.0;
-        const double X4 = 25.0 * (443332067.0 - 31403016.0 * theta) / 1880347072.0;
-        const double X5 = 32805.0 * (23143187.0 - 3489224.0 * theta) / 199316789632.0;
-        const double X6 = 55.0 * (29972135.0 - 7076736.0 * theta) / 822651844.0;
-        const double X7 = 10.0 * (7414447.0 - 829305.0 * theta) / 29380423.0;
-        const double theta_m_1 = theta - 1.0;
-        const double theta_sq = theta * theta;
-        const double A = theta_sq * (3.0 - 2.0 * theta);
-        const double B = theta_sq * theta_m_1;
-        const double C = theta_sq * theta_m_1 * theta_m_1;
-        const double D = theta * theta_m_1 * theta_m_1;
-        const double b1_theta = A * c1_ - C * X1 + D;
-        const double b3_theta = A * c3_ + C * X3;
-        const double b4_theta = A * c4_ - C * X4;
-        const double b5_theta = A * c5_ + C * X5;
-        const double b6_theta = A * c6_ - C * X6;
-        const double b7_theta = B + C * X7;
-        x = 1.0 * x_old + dtl * b1_theta * k1 + dtl * b3_theta * k3 + dtl * b4_theta * k4 + dtl * b5_theta * k5 + dtl * b6_theta * k6 +
-            dtl * b7_theta * k7;
-    }
-    q = sb_exp(x);
+    // One accepted sub-step of the whole model step (t_old = 0, t = t1; > 99.9 % of all steps): theta = 1 exactly, every b_i(theta)
+    // collapses to the tableau's b_i (A = 1, B = C = D = 0, all exact) and b7(theta) = 0, i.e. calc_state(t1) is x_new bit for bit.
+    if (!(t_old == 0.0 && t == t1 && fabs(k7) < inf_())) x = kirchner_calc_state(x_old, t - t_old, (t1 - t_old) / (t - t_old), k1, k3, k4, k5, k6, k7);
+    q = INL ? sb_exp_inl(x) : sb_exp(x);
     area += 0.5 * (f_a + q) * (t1 - t_a);
-    q_avg = area / (t1 - 0.0);
+    q_avg = (t1 == 1.0) ? area : area / (t1 - 0.0);  // x / 1.0 = x
     return true;
+}
+
+// Dormand-Prince tableau as odeint writes it (value_type(n)/value_type(d)); same expressions as in kirchner_step
+__constant__ double kDopri[27] = {
+    1.0 / 5.0,
+    3.0 / 40.0, 9.0 / 40.0,
+    44.0 / 45.0, -56.0 / 15.0, 32.0 / 9.0,
+    19372.0 / 6561.0, -25360.0 / 2187.0, 64448.0 / 6561.0, -212.0 / 729.0,
+    9017.0 / 3168.0, -355.0 / 33.0, 46732.0 / 5247.0, 49.0 / 176.0, -5103.0 / 18656.0,
+    35.0 / 384.0, 500.0 / 1113.0, 125.0 / 192.0, -2187.0 / 6784.0, 11.0 / 84.0,
+    35.0 / 384.0 - 5179.0 / 57600.0, 500.0 / 1113.0 - 7571.0 / 16695.0, 125.0 / 192.0 - 393.0 / 640.0,
+    -2187.0 / 6784.0 - (-92097.0 / 339200.0), 11.0 / 84.0 - 187.0 / 2100.0, -1.0 / 40.0,
+    1.e-30};  // [26]: the threshold of kirchner.h:197
+
+// The same step, warp-synchronous: all 32 lanes call it together and iterate until every lane has reached t1.  Each pass of the
+// loop is one try_step of every lane that is still running (finished lanes recompute their last try and discard it), so the
+// Runge-Kutta stages and their 14 exponentials sit in uniform control flow -- no per-lane loop, no call -- and each lane still
+// follows exactly the accept / reject sequence of kirchner_step above (bit-identical; tests/test_gpu_units.py).
+__device__ __forceinline__ double kirchner_rhs_flat(double c1, double c2, double c3, double pe, double x) {
+    // both exponentials through one range test, so that the two polynomials (four independent fma chains) interleave
+    const double a = c1 + c2 * x + c3 * x * x;
+    int ka, kx;
+    const double pa = sb_exp_core(a, ka), px = sb_exp_core(-x, kx);
+    double g = __hiloint2double(__double2hiint(pa) + (ka << 20), __double2loint(pa));
+    double ex = __hiloint2double(__double2hiint(px) + (kx << 20), __double2loint(px));
+    if (!(fabs(a) < 690.0 && fabs(x) < 690.0)) { g = sb_exp_slow(a); ex = sb_exp_slow(-x); }
+    const double h = g * (pe * ex - 1.0);
+    return g >= kDopri[26] ? h : 0.0;
+}
+__device__ __forceinline__ bool kirchner_step_warp(double c1, double c2, double c3, double t1, double& q, double& q_avg, double p, double e) {
+    const double eps_abs = 1.0e-7, eps_rel = 1.0e-8;
+    if (q < 0.00001) q = 0.00001;
+    double x = sb_log_inl(q);
+    double t = 0.0, dt = t1;
+    const double pe = p - e;
+    double dxdt = kirchner_rhs_flat(c1, c2, c3, pe, x);
+    double area = 0.0, f_a = q, t_a = 0.0;
+
+    // the tableau comes from constant memory (kDopri): a literal costs two uniform moves per use, a constant half a uniform load
+    const double b21 = kDopri[0];
+    const double b31 = kDopri[1], b32 = kDopri[2];
+    const double b41 = kDopri[3], b42 = kDopri[4], b43 = kDopri[5];
+    const double b51 = kDopri[6], b52 = kDopri[7], b53 = kDopri[8], b54 = kDopri[9];
+    const double b61 = kDopri[10], b62 = kDopri[11], b63 = kDopri[12], b64 = kDopri[13], b65 = kDopri[14];
+    const double c1_ = kDopri[15], c3_ = kDopri[16], c4_ = kDopri[17], c5_ = kDopri[18], c6_ = kDopri[19];
+    const double dc1 = kDopri[20], dc3 = kDopri[21], dc4 = kDopri[22], dc5 = kDopri[23], dc6 = kDopri[24], dc7 = kDopri[25];
+
+    int fails = 0;
+    bool failed = false;
+    bool running = t < t1;
+    while (__any_sync(0xffffffffu, running)) {
+        double xt = 1.0 * x + dt * b21 * dxdt;
+        const double k2 = kirchner_rhs_flat(c1, c2, c3, pe, xt);
+        xt = 1.0 * x + dt * b31 * dxdt + dt * b32 * k2;
+        const double k3 = kirchner_rhs_flat(c1, c2, c3, pe, xt);
+        xt = 1.0 * x + dt * b41 * dxdt + dt * b42 * k2 + dt * b43 * k3;
+        const double k4 = kirchner_rhs_flat(c1, c2, c3, pe, xt);
+        xt = 1.0 * x + dt * b51 * dxdt + dt * b52 * k2 + dt * b53 * k3 + dt * b54 * k4;
+        const double k5 = kirchner_rhs_flat(c1, c2, c3, pe, xt);
+        xt = 1.0 * x + dt * b61 * dxdt + dt * b62 * k2 + dt * b63 * k3 + dt * b64 * k4 + dt * b65 * k5;
+        const double k6 = kirchner_rhs_flat(c1, c2, c3, pe, xt);
+        const double x_new = 1.0 * x + dt * c1_ * dxdt + dt * c3_ * k3 + dt * c4_ * k4 + dt * c5_ * k5 + dt * c6_ * k6;
+        const double dxdt_new = kirchner_rhs_flat(c1, c2, c3, pe, x_new);
+        const double x_err = dt * dc1 * dxdt + dt * dc3 * k3 + dt * dc4 * k4 + dt * dc5 * k5 + dt * dc6 * k6 + dt * dc7 * dxdt_new;
+        const double err_num = fabs(x_err), err_den = eps_abs + eps_rel * (1.0 * fabs(x) + (1.0 * dt) * fabs(dxdt));
+        if (running) {
+            const double t_new = t + dt;
+            if (err_num < 0.75 * err_den && !(t_new < t1)) {
+                // accepted and at (or beyond) t1 without needing err itself, see kirchner_step
+                if (!(t == 0.0 && t_new == t1 && fabs(dxdt_new) < inf_()))
+                    x = kirchner_calc_state(x, t_new - t, (t1 - t) / (t_new - t), dxdt, k3, k4, k5, k6, dxdt_new);
+                else
+                    x = x_new;
+                running = false;
+            } else {
+                const double err = err_num / err_den;
+                if (err > 1.0) {
+                    dt *= dmax(9.0 / 10.0 * sb_pow(err, -1.0 / (4 - 1)), 1.0 / 5.0);
+                    if (++fails >= 500) { failed = true; running = false; }
+                } else {
+                    fails = 0;
+                    if (t_new < t1) {
+                        if (err < 0.5) dt *= 9.0 / 10.0 * sb_pow(dmax(0.00032, err), -1.0 / 5);
+                        t = t_new;
+                        x = x_new;
+                        dxdt = dxdt_new;
+                        const double fq = sb_exp(x);
+                        area += 0.5 * (f_a + fq) * (t - t_a);
+                        f_a = fq;
+                        t_a = t;
+                    } else {
+                        if (!(t == 0.0 && t_new == t1 && fabs(dxdt_new) < inf_()))
+                            x = kirchner_calc_state(x, t_new - t, (t1 - t) / (t_new - t), dxdt, k3, k4, k5, k6, dxdt_new);
+                        else
+                            x = x_new;
+                        running = false;
+                    }
+                }
+            }
+        }
+    }
+    q = sb_exp_flat(x);
+    area += 0.5 * (f_a + q) * (t1 - t_a);
+    q_avg = (t1 == 1.0) ? area : area / (t1 - 0.0);  // x / 1.0 = x
+    return !failed;
 }
 
 // ---- the window kernel ----------------------------------------------------------------------------------
@@ -736,10 +864,10 @@ __global__ void __launch_bounds__(SB2_BLOCK, SB2_MINBLOCKS) ptgsk_run_kernel(con
 #define SB2_MINBLOCKS_B 16
 #endif
 #ifndef SB2_BLOCK_C
-#define SB2_BLOCK_C 64
+#define SB2_BLOCK_C 32
 #endif
 #ifndef SB2_MINBLOCKS_C
-#define SB2_MINBLOCKS_C 10
+#define SB2_MINBLOCKS_C 16
 #endif
 
 __global__ void __launch_bounds__(SB2_BLOCK_A) ptgsk_forcing_terms_kernel(const PtgskRunArgs a) {
@@ -868,31 +996,34 @@ __global__ void __launch_bounds__(SB2_BLOCK_C, SB2_MINBLOCKS_C) ptgsk_response_k
         const int64_t step = a.first_step + i;
         const int64_t orow = (step - a.out_first_step) * n + cc;
         double out_q = 0.0, out_charge = 0.0;
-        if (active) {
-            if (COLLECT & 8) a.st[0][orow] = mmh_to_m3s(kq, cell_area_m2);
+        {   // every lane steps (the Kirchner solver is warp-synchronous); lanes without an active cell run on benign inputs, store nothing
+            if ((COLLECT & 8) && active) a.st[0][orow] = mmh_to_m3s(kq, cell_area_m2);
             // glacier_melt::step, glacier_melt.h:47-52
             const double sca_m2 = cell_area_m2 * sca;
             const double gm_melt_m3s =
                 (glacier_area_m2 <= sca_m2 || temp <= 0.0) ? 0.0 : gm_dtf * temp * (glacier_area_m2 - sca_m2) * (0.001 / 86400.0);
             // actual_evapotranspiration::calculate_step, actual_evapotranspiration.h:56-62
-            const double ae = pot * (1.0 - sb_exp(-kq * 3.0 / ae_scale_factor)) * (1.0 - dmax(sca, glacier_fraction));
-            const double gm_mmh = m3s_to_mmh(gm_melt_m3s, cell_area_m2);
-            double q_avg;
-            if (!kirchner_step(c1, c2, c3, a.dt_hours, kq, q_avg, outflow * snow_storage_fraction + prec * kirchner_routed_prec + gm_routed * gm_mmh,
-                               ae)) {
+            const double ae = pot * (1.0 - sb_exp_flat(-kq * 3.0 / ae_scale_factor)) * (1.0 - dmax(sca, glacier_fraction));
+            const double gm_mmh = gm_melt_m3s == 0.0 ? 0.0 : m3s_to_mmh(gm_melt_m3s, cell_area_m2);  // +0 / positive = +0
+            double q_avg, kq_new = active ? kq : 1.0;
+            const double k_in = outflow * snow_storage_fraction + prec * kirchner_routed_prec + gm_routed * gm_mmh;
+            if (!kirchner_step_warp(c1, c2, c3, a.dt_hours, kq_new, q_avg, active ? k_in : 0.0, active ? ae : 0.0)) {
                 failed = true;
                 q_avg = nan("");
             }
             const double total_discharge = dmax(0.0, prec - ae) * direct_response_fraction + gm_direct * gm_mmh + q_avg * kirchner_fraction;
             const double charge_m3s =
                 +mmh_to_m3s(prec, cell_area_m2) - mmh_to_m3s(ae, cell_area_m2) + gm_melt_m3s - mmh_to_m3s(total_discharge, cell_area_m2);
-            out_q = mmh_to_m3s(total_discharge, cell_area_m2);
-            out_charge = charge_m3s;
-            if (COLLECT & 1) { a.resp[0][orow] = out_q; a.resp[1][orow] = charge_m3s; }
-            if (COLLECT & 4) {
-                a.resp[5][orow] = gm_melt_m3s;
-                a.resp[6][orow] = ae;
-                a.resp[7][orow] = pot;
+            if (active) {
+                kq = kq_new;
+                out_q = mmh_to_m3s(total_discharge, cell_area_m2);
+                out_charge = charge_m3s;
+                if (COLLECT & 1) { a.resp[0][orow] = out_q; a.resp[1][orow] = charge_m3s; }
+                if (COLLECT & 4) {
+                    a.resp[5][orow] = gm_melt_m3s;
+                    a.resp[6][orow] = ae;
+                    a.resp[7][orow] = pot;
+                }
             }
         }
         if (a.partial != nullptr) {  // warp-uniform
