@@ -120,6 +120,7 @@ inline double gamma_prefix(double a, double x) { return dm::exp(a * dm::log(x) -
 //             "term < sum * 1e-16" reads  x^n < P * 1e-16;  one division P/Q at the end
 //   fraction  1/(b0 + a1/(b1 + a2/(b2 + ..))), b_i = x + 2i + 1 - a, a_i = -i (i - a), by the forward recurrence
 //             A_i = b_i A_{i-1} + a_i A_{i-2} (same for B), value B_i/A_i; converged when successive convergents agree to 1e-16
+//   Terms are taken four (convergents two) at a time, with the tests after each group: short dependent chains, one branch per group.
 //   P, Q, x^n (A, B) are rescaled by the exact factor 2^-500 whenever the high word of Q (|A|) exceeds that of 2^500.
 inline double gamma_p(double a, double x) {
     if (!(x > 0.0)) return 0.0;
@@ -128,30 +129,38 @@ inline double gamma_p(double a, double x) {
     const double small = 3.0549363634996047e-151;  // 2^-500
     const double pre = gamma_prefix(a, x);
     if (x < a + 1.0) {
+        // terms are added four at a time; the term test and the range test follow each group of four
         double ap = a, P = 1.0, Q = a, xn = 1.0;
         SHO_CNT(C_GSER_CALLS, 1);
-        for (int n = 0; n < 2000; ++n) {
-            SHO_CNT(C_GSER_ITER, 1);
-            ap += 1.0;
-            xn *= x;
-            Q *= ap;
-            P = std::fma(P, ap, xn);
+        for (int n = 0; n < 500; ++n) {
+            SHO_CNT(C_GSER_ITER, 4);
+            for (int k = 0; k < 4; ++k) {
+                ap += 1.0;
+                xn *= x;
+                Q *= ap;
+                P = std::fma(P, ap, xn);
+            }
             if (xn < P * eps) break;
             if (int32_t(dm::bits_of(Q) >> 32) > 0x5f300000) { Q *= small; P *= small; xn *= small; }  // high word of Q above that of 2^500
         }
         return (P / Q) * pre;
     }
-    double b = x + 1.0 - a;
+    // two convergents per pass; the convergence test compares the last two, the range test follows it
+    double b = x + 1.0 - a, di = 0.0;
     double A1 = 1.0, B1 = 0.0, A = b, B = 1.0;  // convergents i-1 and i
     SHO_CNT(C_GCF_CALLS, 1);
-    for (int i = 1; i < 2000; ++i) {
-        SHO_CNT(C_GCF_ITER, 1);
-        const double di = double(i);
-        const double an = -di * (di - a);
+    for (int i = 0; i < 1000; ++i) {
+        SHO_CNT(C_GCF_ITER, 2);
+        di += 1.0;
+        double an = -di * (di - a);
         b += 2.0;
-        const double An = std::fma(b, A, an * A1);
-        const double Bn = std::fma(b, B, an * B1);
-        A1 = A; B1 = B; A = An; B = Bn;
+        A1 = std::fma(b, A, an * A1);   // convergent 2i+1 overwrites 2i-1
+        B1 = std::fma(b, B, an * B1);
+        di += 1.0;
+        an = -di * (di - a);
+        b += 2.0;
+        A = std::fma(b, A1, an * A);    // convergent 2i+2 overwrites 2i
+        B = std::fma(b, B1, an * B);
         const double m1 = A * B1, m0 = A1 * B;
         if (std::fabs(m1 - m0) < eps * std::fabs(m1)) break;
         if (int32_t((dm::bits_of(A) >> 32) & 0x7fffffff) > 0x5f300000) { A *= small; B *= small; A1 *= small; B1 *= small; }

@@ -71,7 +71,7 @@ inline double exp(double x) {
 }
 
 // log(x): x = 2^e * m, m in (sqrt(1/2), sqrt(2)], f = m-1, s = f/(2+f), log(1+f) = f - f^2/2 + s*(f^2/2 + R(s^2)),
-// R(z) = z * sum_{k=0..9} 2/(2k+3) z^k  (the atanh series, Estrin's scheme)
+// R(z) = z * sum_{k=0..9} 2/(2k+3) z^k  (the atanh series; even and odd Horner chains in z^2)
 inline double log(double x) {
     SHO_CNT(C_LOG, 1);
     if (x != x || x < 0.0) return std::numeric_limits<double>::quiet_NaN();
@@ -85,16 +85,17 @@ inline double log(double x) {
     if (m > 1.4142135623730951) { m *= 0.5; e += 1; }
     const double f = m - 1.0;
     const double s = f / (2.0 + f);
-    const double z = s * s, z2 = z * z, z4 = z2 * z2, z8 = z4 * z4;
-    const double t01 = std::fma(2.0 / 5.0, z, 2.0 / 3.0);
-    const double t23 = std::fma(2.0 / 9.0, z, 2.0 / 7.0);
-    const double t45 = std::fma(2.0 / 13.0, z, 2.0 / 11.0);
-    const double t67 = std::fma(2.0 / 17.0, z, 2.0 / 15.0);
-    const double t89 = std::fma(2.0 / 21.0, z, 2.0 / 19.0);
-    const double u0 = std::fma(t23, z2, t01);
-    const double u1 = std::fma(t67, z2, t45);
-    const double v0 = std::fma(u1, z4, u0);
-    const double R = z * std::fma(t89, z8, v0);
+    const double z = s * s, w = z * z;
+    double re = 2.0 / 19.0, ro = 2.0 / 21.0;
+    re = std::fma(re, w, 2.0 / 15.0);
+    ro = std::fma(ro, w, 2.0 / 17.0);
+    re = std::fma(re, w, 2.0 / 11.0);
+    ro = std::fma(ro, w, 2.0 / 13.0);
+    re = std::fma(re, w, 2.0 / 7.0);
+    ro = std::fma(ro, w, 2.0 / 9.0);
+    re = std::fma(re, w, 2.0 / 3.0);
+    ro = std::fma(ro, w, 2.0 / 5.0);
+    const double R = z * std::fma(z, ro, re);
     const double hfsq = 0.5 * f * f;
     const double dk = double(e);
     const double t = std::fma(s, hfsq + R, dk * 1.90821492927058770002e-10);

@@ -6,7 +6,7 @@
 // amplifies last-bit differences between math libraries to 1e-4-level differences in liquid water content; a 1e-9 parity
 // statement is only meaningful over one fixed operation sequence (DESIGN.md "Deterministic math").  The sequence:
 //   exp(x)    k = rint(x/ln2) (magic-number add), r = fma(k,-ln2_lo, fma(k,-ln2_hi,x)), degree-13 Taylor polynomial (even/odd Horner, fma), scaled by 2^k
-//   log(x)    x = 2^e*m, m in (sqrt(1/2), sqrt(2)], f = m-1, s = f/(2+f), f - f^2/2 + s*(f^2/2 + R(s^2)), R = atanh series to s^20
+//   log(x)    x = 2^e*m, m in (sqrt(1/2), sqrt(2)], f = m-1, s = f/(2+f), f - f^2/2 + s*(f^2/2 + R(s^2)), R = atanh series to s^20 (even/odd Horner)
 //   pow(x,y)  exact for y = 0, 1, 2, 0.5; exp(y*log(x)) otherwise (x >= 0)
 //   lgamma(a) recurrence up to a >= 12, then the Stirling series to 1/a^13
 // The reference evaluates through libm and boost 1.68 (absent from its tree):
@@ -154,22 +154,63 @@ SB2_HD double sb_log_inl(double x) {
     if (m > 1.4142135623730951) { m *= 0.5; e += 1; }
     const double f = m - 1.0;
     const double s = f / (2.0 + f);
-    const double z = s * s, z2 = z * z, z4 = z2 * z2, z8 = z4 * z4;
-    const double t01 = fma(SB2_LOGC(1), z, SB2_LOGC(0));
-    const double t23 = fma(SB2_LOGC(3), z, SB2_LOGC(2));
-    const double t45 = fma(SB2_LOGC(5), z, SB2_LOGC(4));
-    const double t67 = fma(SB2_LOGC(7), z, SB2_LOGC(6));
-    const double t89 = fma(SB2_LOGC(9), z, SB2_LOGC(8));
-    const double u0 = fma(t23, z2, t01);
-    const double u1 = fma(t67, z2, t45);
-    const double v0 = fma(u1, z4, u0);
-    const double R = z * fma(t89, z8, v0);
+    const double z = s * s, w = z * z;
+    double re = SB2_LOGC(8), ro = SB2_LOGC(9);  // even / odd Horner chains in w = z^2: one coefficient per fma (see sb_exp_core)
+    re = fma(re, w, SB2_LOGC(6));
+    ro = fma(ro, w, SB2_LOGC(7));
+    re = fma(re, w, SB2_LOGC(4));
+    ro = fma(ro, w, SB2_LOGC(5));
+    re = fma(re, w, SB2_LOGC(2));
+    ro = fma(ro, w, SB2_LOGC(3));
+    re = fma(re, w, SB2_LOGC(0));
+    ro = fma(ro, w, SB2_LOGC(1));
+    const double R = z * fma(z, ro, re);
     const double hfsq = 0.5 * f * f;
     const double dk = double(e);
     const double t = fma(s, hfsq + R, dk * SB2_MISC(4));
     return fma(dk, SB2_MISC(3), f - (hfsq - t));
 }
 SB2_MATH_FN double sb_log(double x) { return sb_log_inl(x); }
+// the same value without early returns (special operands patched by selects at the end), for code that must stay branch-free
+__device__ __forceinline__ double sb_log_flat(double x0) {
+    const bool sub = x0 < 2.2250738585072014e-308;
+    const double x = sub ? x0 * 18014398509481984.0 : x0;
+    const unsigned long long u = bits_of(x);
+    int e = int((u >> 52) & 0x7ff) - 1023 + (sub ? -54 : 0);
+    double m = from_bits((u & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL);
+    const bool hi = m > 1.4142135623730951;
+    m = hi ? m * 0.5 : m;
+    e += hi ? 1 : 0;
+    const double f = m - 1.0;
+    const double s = f / (2.0 + f);
+    const double z = s * s, w = z * z;
+    double re = SB2_LOGC(8), ro = SB2_LOGC(9);  // even / odd Horner chains in w = z^2: one coefficient per fma (see sb_exp_core)
+    re = fma(re, w, SB2_LOGC(6));
+    ro = fma(ro, w, SB2_LOGC(7));
+    re = fma(re, w, SB2_LOGC(4));
+    ro = fma(ro, w, SB2_LOGC(5));
+    re = fma(re, w, SB2_LOGC(2));
+    ro = fma(ro, w, SB2_LOGC(3));
+    re = fma(re, w, SB2_LOGC(0));
+    ro = fma(ro, w, SB2_LOGC(1));
+    const double R = z * fma(z, ro, re);
+    const double hfsq = 0.5 * f * f;
+    const double dk = double(e);
+    const double t = fma(s, hfsq + R, dk * SB2_MISC(4));
+    double r = fma(dk, SB2_MISC(3), f - (hfsq - t));
+    if (x0 == inf_()) r = x0;
+    if (x0 == 0.0) r = -inf_();
+    if (x0 != x0 || x0 < 0.0) r = nan_();
+    return r;
+}
+__device__ __forceinline__ double sb_pow_flat(double x, double y) {  // y is a literal at every call site: the exact cases fold away
+    if (y == 0.0) return 1.0;
+    if (y == 1.0) return x;
+    if (y == 2.0) return x * x;
+    if (y == 0.5) return sqrt(x);
+    const double r = sb_exp_flat(y * sb_log_flat(x));
+    return x == 0.0 ? (y > 0.0 ? 0.0 : inf_()) : r;
+}
 
 SB2_HD double sb_pow(double x, double y) {
     if (y == 0.0) return 1.0;
@@ -208,36 +249,45 @@ __device__ __forceinline__ double gamma_prefix(double a, double x, double lgamma
 // without a division per term (an fp64 division is ~30 instructions; the series runs 10-40 terms per call and was the single
 // hottest loop of the pt_gs_k kernel).  The series is carried as the fraction P/Q (Q *= a+n, P = P (a+n) + x^n), the continued
 // fraction by the forward recurrence of its convergents A_i/B_i; exact 2^-500 rescaling keeps them in range.
-__device__ __noinline__ double gamma_p_with_prefix(double a, double x, double pre) {
+// Terms are taken four (convergents two) at a time with the tests after each group: short dependent chains, one branch per group.
+__device__ __forceinline__ double gamma_p_with_prefix_inl(double a, double x, double pre) {
     const double eps = 1.0e-16;
     const double small = 3.0549363634996047e-151;  // 2^-500
     if (x < a + 1.0) {
         double ap = a, P = 1.0, Q = a, xn = 1.0;
-        for (int n = 0; n < 2000; ++n) {
-            ap += 1.0;
-            xn *= x;
-            Q *= ap;
-            P = fma(P, ap, xn);
+        for (int n = 0; n < 500; ++n) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                ap += 1.0;
+                xn *= x;
+                Q *= ap;
+                P = fma(P, ap, xn);
+            }
             if (xn < P * eps) break;
             if (__double2hiint(Q) > 0x5f300000) { Q *= small; P *= small; xn *= small; }  // Q > 2^500 (Q > 0: high word decides)
         }
         return (P / Q) * pre;
     }
-    double b = x + 1.0 - a;
+    double b = x + 1.0 - a, di = 0.0;
     double A1 = 1.0, B1 = 0.0, A = b, B = 1.0;
-    for (int i = 1; i < 2000; ++i) {
-        const double di = double(i);
-        const double an = -di * (di - a);
+    for (int i = 0; i < 1000; ++i) {
+        di += 1.0;
+        double an = -di * (di - a);
         b += 2.0;
-        const double An = fma(b, A, an * A1);
-        const double Bn = fma(b, B, an * B1);
-        A1 = A; B1 = B; A = An; B = Bn;
+        A1 = fma(b, A, an * A1);
+        B1 = fma(b, B, an * B1);
+        di += 1.0;
+        an = -di * (di - a);
+        b += 2.0;
+        A = fma(b, A1, an * A);
+        B = fma(b, B1, an * B);
         const double m1 = A * B1, m0 = A1 * B;
         if (fabs(m1 - m0) < eps * fabs(m1)) break;
         if ((__double2hiint(A) & 0x7fffffff) > 0x5f300000) { A *= small; B *= small; A1 *= small; B1 *= small; }  // |A| > 2^500
     }
     return 1.0 - pre * (B / A);
 }
+__device__ __noinline__ double gamma_p_with_prefix(double a, double x, double pre) { return gamma_p_with_prefix_inl(a, x, pre); }
 
 __device__ __forceinline__ double gamma_p(double a, double x, double lgamma_a) {
     if (!(x > 0.0)) return 0.0;

@@ -208,8 +208,10 @@ __device__ __noinline__ double gs_corr_lwc(double z1, double a1, double b1, doub
 
 // calc_snow_state, gamma_snow.h:230-260
 // `lg_key`/`lg_val` memoise lgamma(shape): the shape (alpha) changes on few steps, and equal bits in give equal bits out
-__device__ __noinline__ void gs_calc_snow_state(double shape, double scale, double y0, double lambda, double lwd, double max_water_frac,
-                                                double temp_swe, double& swe, double& sca, double& lg_key, double& lg_val) {
+// FLAT = true: exp / log / the incomplete gamma expanded in place without calls (the snow kernel's two hot call sites)
+template <bool FLAT>
+__device__ __forceinline__ void gs_calc_snow_state_impl(double shape, double scale, double y0, double lambda, double lwd, double max_water_frac,
+                                                        double temp_swe, double& swe, double& sca, double& lg_key, double& lg_val) {
     double y = 0.0, y1 = 0.0;
     const double m = shape * scale;
     double lg = 0.0;
@@ -225,8 +227,8 @@ __device__ __noinline__ void gs_calc_snow_state(double shape, double scale, doub
         if (shape != lg_key) { lg_key = shape; lg_val = sb_lgamma(shape); }
         lg = lg_val;
         have_lg = true;
-        const double pre = gamma_prefix(shape, x, lg);
-        y = (x > 0.0) ? gamma_p_with_prefix(shape, x, pre) : 0.0;
+        const double pre = FLAT ? sb_exp_flat(shape * sb_log_flat(x) - x - lg) : gamma_prefix(shape, x, lg);
+        y = (x > 0.0) ? (FLAT ? gamma_p_with_prefix_inl(shape, x, pre) : gamma_p_with_prefix(shape, x, pre)) : 0.0;
         y1 = y - pre / shape;
         swe = m * (1.0 - y1) - lambda * (1 - y);
         sca = (1.0 - y) * (1.0 - y0);
@@ -239,14 +241,19 @@ __device__ __noinline__ void gs_calc_snow_state(double shape, double scale, doub
             if (shape != lg_key) { lg_key = shape; lg_val = sb_lgamma(shape); }
             lg = lg_val;
         }
-        const double pre = gamma_prefix(shape, x, lg);
-        const double ssa = (x == inf_()) ? 1.0 : gamma_p_with_prefix(shape, x, pre);
+        const double pre = FLAT ? sb_exp_flat(shape * sb_log_flat(x) - x - lg) : gamma_prefix(shape, x, lg);
+        const double ssa = (x == inf_()) ? 1.0 : (FLAT ? gamma_p_with_prefix_inl(shape, x, pre) : gamma_p_with_prefix(shape, x, pre));
         const double ssa1 = ssa - pre / shape;
         const double liqwat = max_water_frac * (m * (ssa1 - y1) + sat * (1.0 - ssa) - lambda * (1.0 - y));
         swe += liqwat;
     }
     swe += temp_swe;
     swe *= 1.0 - y0;
+}
+
+__device__ __noinline__ void gs_calc_snow_state(double shape, double scale, double y0, double lambda, double lwd, double max_water_frac,
+                                                double temp_swe, double& swe, double& sca, double& lg_key, double& lg_val) {
+    gs_calc_snow_state_impl<false>(shape, scale, y0, lambda, lwd, max_water_frac, temp_swe, swe, sca, lg_key, lg_val);
 }
 
 // reset_snow_pack, gamma_snow.h:262-274 (alpha uses p.snow_cv, not the effective cv)
@@ -271,18 +278,20 @@ __device__ __forceinline__ double gs_vapour_pressure(double T, double rel_hum) {
     if (T < 0.0) vapour_pressure *= 1.0 + 9.72e-3 * T + 4.2e-5 * T * T;
     return vapour_pressure;
 }
+template <bool FLAT = false>
 __device__ __forceinline__ void gs_energy_terms(const PtgskParam& p, double BB0, double T, double wind_speed, double rel_hum, double& lw, double& tadd) {
     const double tol = 1.0e-10, sigma = 5.670373e-8;
     const double T_k = T + 273.15;
     const double turb = p.wind_scale * wind_speed + p.wind_const;
     const double vapour_pressure = gs_vapour_pressure(T, rel_hum);
-    lw = 0.98 * sigma * sb_pow(vapour_pressure / T_k, 6.87e-2) * sb_pow4(T_k);
+    lw = 0.98 * sigma * (FLAT ? sb_pow_flat(vapour_pressure / T_k, 6.87e-2) : sb_pow(vapour_pressure / T_k, 6.87e-2)) * sb_pow4(T_k);
     const double sst = dmin(0.0, 1.16 * T - 2.09);
     if (sst > -tol) tadd = turb * (T + 1.7 * (vapour_pressure - 6.12)) - BB0;
-    else tadd = turb * (T - sst + 1.7 * (vapour_pressure - 6.132 * sb_exp(0.103 * T - 0.186))) - 0.98 * sigma * sb_pow4(sst + 273.15);
+    else tadd = turb * (T - sst + 1.7 * (vapour_pressure - 6.132 * (FLAT ? sb_exp_flat(0.103 * T - 0.186) : sb_exp(0.103 * T - 0.186)))) - 0.98 * sigma * sb_pow4(sst + 273.15);
 }
 
 // gamma_snow::calculator::step, gamma_snow.h:291-493, given the two forcing-only addends (lw, tadd) of gs_energy_terms
+template <bool FLAT = false>
 __device__ __forceinline__ void gs_step_core(GsState& s, GsCache& cache, double& r_sca, double& r_storage, double& r_outflow, const PtgskParam& p, int doy,
                                              int sec_of_year, double dt_seconds, double dt_us, double BB0, double T, double rad, double prec_mm_h,
                                              double lw, double tadd, double wind_speed, double rel_hum, double forest_fraction, double altitude) {
@@ -353,7 +362,8 @@ __device__ __forceinline__ void gs_step_core(GsState& s, GsCache& cache, double&
         storage = SB2_CK_STORAGE(cache);
         sca = SB2_CK_SCA(cache);
     } else {
-        gs_calc_snow_state(alpha, sdc_scale, y0, acc_melt, lwc, p.max_water, temp_swe, storage, sca, SB2_CK_LGKEY(cache), SB2_CK_LGVAL(cache));
+        if (FLAT) gs_calc_snow_state_impl<true>(alpha, sdc_scale, y0, acc_melt, lwc, p.max_water, temp_swe, storage, sca, SB2_CK_LGKEY(cache), SB2_CK_LGVAL(cache));
+        else gs_calc_snow_state(alpha, sdc_scale, y0, acc_melt, lwc, p.max_water, temp_swe, storage, sca, SB2_CK_LGKEY(cache), SB2_CK_LGVAL(cache));
         gs_cache_store(cache, alpha, sdc_scale, acc_melt, lwc, temp_swe, storage, sca);
     }
     const double start_storage_value = storage;
@@ -416,7 +426,8 @@ __device__ __forceinline__ void gs_step_core(GsState& s, GsCache& cache, double&
         storage = SB2_CK_STORAGE(cache);
         sca = SB2_CK_SCA(cache);
     } else {
-        gs_calc_snow_state(alpha, sdc_scale, y0, acc_melt, lwc, p.max_water, temp_swe, storage, sca, SB2_CK_LGKEY(cache), SB2_CK_LGVAL(cache));
+        if (FLAT) gs_calc_snow_state_impl<true>(alpha, sdc_scale, y0, acc_melt, lwc, p.max_water, temp_swe, storage, sca, SB2_CK_LGKEY(cache), SB2_CK_LGVAL(cache));
+        else gs_calc_snow_state(alpha, sdc_scale, y0, acc_melt, lwc, p.max_water, temp_swe, storage, sca, SB2_CK_LGKEY(cache), SB2_CK_LGVAL(cache));
         gs_cache_store(cache, alpha, sdc_scale, acc_melt, lwc, temp_swe, storage, sca);
     }
 
@@ -450,6 +461,7 @@ __device__ __forceinline__ void gs_step(GsState& s, GsCache& cache, double& r_sc
 }
 
 // ---- priestley_taylor, core/priestley_taylor.h:75-103 -------------------------------------------------
+template <bool FLAT = false>
 __device__ __forceinline__ double pt_potential_evapotranspiration(double land_albedo, double alpha, double temperature, double global_radiation,
                                                                   double rhumidity) {
     const double ck1 = 0.610780, psycr = 0.066, bolz = 0.0000000567;
@@ -457,11 +469,11 @@ __device__ __forceinline__ double pt_potential_evapotranspiration(double land_al
     const double ck2 = neg ? 17.84362 : 17.08085;
     const double ck3 = neg ? 245.425 : 234.175;
     const double ctt_inv = 1 / (ck3 + temperature);
-    const double sat_pressure = ck1 * sb_exp(ck2 * temperature * ctt_inv);
+    const double sat_pressure = ck1 * (FLAT ? sb_exp_flat(ck2 * temperature * ctt_inv) : sb_exp(ck2 * temperature * ctt_inv));
     const double delta = sat_pressure * ck2 * ck3 * ctt_inv * ctt_inv;
     const double vapour_pressure = sat_pressure * rhumidity;
     const double k_temp = temperature + 273.15;
-    const double e_atm = 1.24 * sb_pow(10 * vapour_pressure / k_temp, 0.143) * (0.85 + 0.5 * rhumidity);
+    const double e_atm = 1.24 * (FLAT ? sb_pow_flat(10 * vapour_pressure / k_temp, 0.143) : sb_pow(10 * vapour_pressure / k_temp, 0.143)) * (0.85 + 0.5 * rhumidity);
     const double net_radiation = bolz * sb_pow4(k_temp) * (e_atm - 0.98) + global_radiation * (1.0 - land_albedo);
     const double epot = alpha * delta * net_radiation / (delta + psycr);
     if (epot < 0.0) return 0.0;
@@ -884,8 +896,8 @@ __global__ void __launch_bounds__(SB2_BLOCK_A) ptgsk_forcing_terms_kernel(const 
         const int64_t o = (int64_t)i * n + c;
         const double temp = a.f[0][o], rad = a.f[2][o], wind = a.f[3][o], rel_hum = a.f[4][o];
         double lw, tadd;
-        gs_energy_terms(p, a.bb0, temp, wind, rel_hum, lw, tadd);
-        a.scr[SCR_POT][o] = pt_potential_evapotranspiration(pt_albedo, pt_alpha, temp, rad, rel_hum) * 3600.0;
+        gs_energy_terms<true>(p, a.bb0, temp, wind, rel_hum, lw, tadd);
+        a.scr[SCR_POT][o] = pt_potential_evapotranspiration<true>(pt_albedo, pt_alpha, temp, rad, rel_hum) * 3600.0;
         a.scr[SCR_LW][o] = lw;
         a.scr[SCR_TADD][o] = tadd;
     }
@@ -932,8 +944,8 @@ __global__ void __launch_bounds__(SB2_BLOCK_B, SB2_MINBLOCKS_B) ptgsk_snow_kerne
         double wind = 0.0, rel_hum = 0.0;
         if (iso) { wind = a.f[3][o]; rel_hum = a.f[4][o]; }
         double sca, storage, outflow;
-        gs_step_core(gs, cache, sca, storage, outflow, p, a.day_of_year[step], a.sec_of_year[step], a.dt_seconds, a.dt_us, a.bb0, temp, rad, prec, lw,
-                     tadd, wind, rel_hum, forest_fraction, altitude);
+        gs_step_core<true>(gs, cache, sca, storage, outflow, p, a.day_of_year[step], a.sec_of_year[step], a.dt_seconds, a.dt_us, a.bb0, temp, rad, prec,
+                           lw, tadd, wind, rel_hum, forest_fraction, altitude);
         a.scr[SCR_OUTFLOW][o] = outflow;
         a.scr[SCR_SCA][o] = sca;
         if (COLLECT & 2) { a.resp[2][orow] = sca; a.resp[3][orow] = storage * snow_storage_fraction; }
