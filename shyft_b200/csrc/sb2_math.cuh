@@ -289,6 +289,81 @@ __device__ __forceinline__ double gamma_p_with_prefix_inl(double a, double x, do
 }
 __device__ __noinline__ double gamma_p_with_prefix(double a, double x, double pre) { return gamma_p_with_prefix_inl(a, x, pre); }
 
+// Two incomplete gamma values of the same shape at once: P(a, x1) and P(a, x2), each evaluated exactly as by
+// gamma_p_with_prefix_inl (same terms, same tests, same rescaling), but in ONE series loop and ONE continued-fraction loop that
+// advance both problems together.  The terms a+n and their product Q depend on the shape only and are shared; a problem that has
+// converged has its result latched and is carried along idle.  A warp then runs max(n1, n2) passes instead of n1 + n2, with two
+// independent dependency chains per lane.
+__device__ __forceinline__ void gamma_p_pair_inl(double a, double x1, bool need1, double pre1, double x2, bool need2, double pre2, double& P1,
+                                                 double& P2) {
+    const double eps = 1.0e-16;
+    const double small = 3.0549363634996047e-151;  // 2^-500
+    const bool s1 = need1 && x1 < a + 1.0, s2 = need2 && x2 < a + 1.0;
+    const bool c1 = need1 && !s1, c2 = need2 && !s2;
+    if (s1 || s2) {
+        double ap = a, Q = a, Pa = 1.0, xa = 1.0, Pb = 1.0, xb = 1.0;
+        double Pa_f = 1.0, Qa_f = a, Pb_f = 1.0, Qb_f = a;
+        bool ra = s1, rb = s2;
+        for (int n = 0; n < 500; ++n) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                ap += 1.0;
+                xa *= x1;
+                xb *= x2;
+                Q *= ap;
+                Pa = fma(Pa, ap, xa);
+                Pb = fma(Pb, ap, xb);
+            }
+            if (ra) { Pa_f = Pa; Qa_f = Q; ra = !(xa < Pa * eps); }
+            if (rb) { Pb_f = Pb; Qb_f = Q; rb = !(xb < Pb * eps); }
+            if (!(ra || rb)) break;
+            if (__double2hiint(Q) > 0x5f300000) { Q *= small; Pa *= small; xa *= small; Pb *= small; xb *= small; }
+        }
+        if (s1) P1 = (Pa_f / Qa_f) * pre1;
+        if (s2) P2 = (Pb_f / Qb_f) * pre2;
+    }
+    if (c1 || c2) {
+        double ba = x1 + 1.0 - a, bb = x2 + 1.0 - a, di = 0.0;
+        double A1a = 1.0, B1a = 0.0, Aa = ba, Ba = 1.0;
+        double A1b = 1.0, B1b = 0.0, Ab = bb, Bb = 1.0;
+        double Aa_f = Aa, Ba_f = Ba, Ab_f = Ab, Bb_f = Bb;
+        bool ra = c1, rb = c2;
+        for (int i = 0; i < 1000; ++i) {
+            di += 1.0;
+            double an = -di * (di - a);
+            ba += 2.0;
+            bb += 2.0;
+            A1a = fma(ba, Aa, an * A1a);
+            B1a = fma(ba, Ba, an * B1a);
+            A1b = fma(bb, Ab, an * A1b);
+            B1b = fma(bb, Bb, an * B1b);
+            di += 1.0;
+            an = -di * (di - a);
+            ba += 2.0;
+            bb += 2.0;
+            Aa = fma(ba, A1a, an * Aa);
+            Ba = fma(ba, B1a, an * Ba);
+            Ab = fma(bb, A1b, an * Ab);
+            Bb = fma(bb, B1b, an * Bb);
+            if (ra) {
+                const double m1 = Aa * B1a, m0 = A1a * Ba;
+                Aa_f = Aa; Ba_f = Ba;
+                ra = !(fabs(m1 - m0) < eps * fabs(m1));
+            }
+            if (rb) {
+                const double m1 = Ab * B1b, m0 = A1b * Bb;
+                Ab_f = Ab; Bb_f = Bb;
+                rb = !(fabs(m1 - m0) < eps * fabs(m1));
+            }
+            if (!(ra || rb)) break;
+            if ((__double2hiint(Aa) & 0x7fffffff) > 0x5f300000) { Aa *= small; Ba *= small; A1a *= small; B1a *= small; }
+            if ((__double2hiint(Ab) & 0x7fffffff) > 0x5f300000) { Ab *= small; Bb *= small; A1b *= small; B1b *= small; }
+        }
+        if (c1) P1 = 1.0 - pre1 * (Ba_f / Aa_f);
+        if (c2) P2 = 1.0 - pre2 * (Bb_f / Ab_f);
+    }
+}
+
 __device__ __forceinline__ double gamma_p(double a, double x, double lgamma_a) {
     if (!(x > 0.0)) return 0.0;
     if (x == inf_()) return 1.0;

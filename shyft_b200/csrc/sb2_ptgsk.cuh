@@ -208,8 +208,6 @@ __device__ __noinline__ double gs_corr_lwc(double z1, double a1, double b1, doub
 
 // calc_snow_state, gamma_snow.h:230-260
 // `lg_key`/`lg_val` memoise lgamma(shape): the shape (alpha) changes on few steps, and equal bits in give equal bits out
-// FLAT = true: exp / log / the incomplete gamma expanded in place without calls (the snow kernel's two hot call sites)
-template <bool FLAT>
 __device__ __forceinline__ void gs_calc_snow_state_impl(double shape, double scale, double y0, double lambda, double lwd, double max_water_frac,
                                                         double temp_swe, double& swe, double& sca, double& lg_key, double& lg_val) {
     double y = 0.0, y1 = 0.0;
@@ -227,8 +225,8 @@ __device__ __forceinline__ void gs_calc_snow_state_impl(double shape, double sca
         if (shape != lg_key) { lg_key = shape; lg_val = sb_lgamma(shape); }
         lg = lg_val;
         have_lg = true;
-        const double pre = FLAT ? sb_exp_flat(shape * sb_log_flat(x) - x - lg) : gamma_prefix(shape, x, lg);
-        y = (x > 0.0) ? (FLAT ? gamma_p_with_prefix_inl(shape, x, pre) : gamma_p_with_prefix(shape, x, pre)) : 0.0;
+        const double pre = gamma_prefix(shape, x, lg);
+        y = (x > 0.0) ? gamma_p_with_prefix(shape, x, pre) : 0.0;
         y1 = y - pre / shape;
         swe = m * (1.0 - y1) - lambda * (1 - y);
         sca = (1.0 - y) * (1.0 - y0);
@@ -241,9 +239,64 @@ __device__ __forceinline__ void gs_calc_snow_state_impl(double shape, double sca
             if (shape != lg_key) { lg_key = shape; lg_val = sb_lgamma(shape); }
             lg = lg_val;
         }
-        const double pre = FLAT ? sb_exp_flat(shape * sb_log_flat(x) - x - lg) : gamma_prefix(shape, x, lg);
-        const double ssa = (x == inf_()) ? 1.0 : (FLAT ? gamma_p_with_prefix_inl(shape, x, pre) : gamma_p_with_prefix(shape, x, pre));
+        const double pre = gamma_prefix(shape, x, lg);
+        const double ssa = (x == inf_()) ? 1.0 : gamma_p_with_prefix(shape, x, pre);
         const double ssa1 = ssa - pre / shape;
+        const double liqwat = max_water_frac * (m * (ssa1 - y1) + sat * (1.0 - ssa) - lambda * (1.0 - y));
+        swe += liqwat;
+    }
+    swe += temp_swe;
+    swe *= 1.0 - y0;
+}
+
+// The same function for the snow kernel's hot call site (end of step): exp / log / the incomplete gamma expanded in place, and both
+// evaluations (snow-free fraction at lambda, saturated fraction at lwd / max_water_frac) advanced together by gamma_p_pair_inl.
+__device__ __forceinline__ void gs_calc_snow_state_hot(double shape, double scale, double y0, double lambda, double lwd, double max_water_frac,
+                                                       double temp_swe, double& swe, double& sca, double& lg_key, double& lg_val) {
+    const double m = shape * scale;
+    const bool need1 = !(lambda <= 0.0);
+    double x1 = 0.0, x2 = 0.0, sat = 0.0;
+    if (need1) {
+        x1 = lambda / scale;
+        if (x1 > 1.3 * shape + 20.0) {
+            swe = sca = 0.0;
+            return;
+        }
+    }
+    const bool need2 = !(lwd > m) && lwd > 0.0;
+    if (need2) {
+        sat = lwd / max_water_frac;
+        x2 = sat / scale;
+    }
+    double lg = 0.0;
+    if (need1 || need2) {
+        if (shape != lg_key) { lg_key = shape; lg_val = sb_lgamma(shape); }
+        lg = lg_val;
+    }
+    double pre1 = 0.0, P1 = 0.0, pre2 = 0.0, P2 = 0.0;
+    if (need1 || need2) {
+        // both prefixes x^a e^-x / Gamma(a) side by side (two independent exp/log chains), then both incomplete gammas in one pair of loops
+        pre1 = sb_exp_flat(shape * sb_log_flat(x1) - x1 - lg);
+        pre2 = sb_exp_flat(shape * sb_log_flat(x2) - x2 - lg);
+        const bool g1 = need1 && x1 > 0.0;                  // !(x1 > 0): P1 = 0 (x1 = inf has returned above)
+        const bool g2 = need2 && !(x2 == inf_());           // x2 = inf: P2 = 1
+        if (need2 && !g2) P2 = 1.0;
+        gamma_p_pair_inl(shape, x1, g1, pre1, x2, g2, pre2, P1, P2);
+    }
+    double y = 0.0, y1 = 0.0;
+    if (need1) {
+        y = P1;
+        y1 = y - pre1 / shape;
+        swe = m * (1.0 - y1) - lambda * (1 - y);
+        sca = (1.0 - y) * (1.0 - y0);
+    } else {
+        swe = m;
+        sca = 1.0 - y0;
+    }
+    if (lwd > m) swe *= 1.0 + max_water_frac;
+    else if (need2) {
+        const double ssa = P2;
+        const double ssa1 = ssa - pre2 / shape;
         const double liqwat = max_water_frac * (m * (ssa1 - y1) + sat * (1.0 - ssa) - lambda * (1.0 - y));
         swe += liqwat;
     }
@@ -253,7 +306,7 @@ __device__ __forceinline__ void gs_calc_snow_state_impl(double shape, double sca
 
 __device__ __noinline__ void gs_calc_snow_state(double shape, double scale, double y0, double lambda, double lwd, double max_water_frac,
                                                 double temp_swe, double& swe, double& sca, double& lg_key, double& lg_val) {
-    gs_calc_snow_state_impl<false>(shape, scale, y0, lambda, lwd, max_water_frac, temp_swe, swe, sca, lg_key, lg_val);
+    gs_calc_snow_state_impl(shape, scale, y0, lambda, lwd, max_water_frac, temp_swe, swe, sca, lg_key, lg_val);
 }
 
 // reset_snow_pack, gamma_snow.h:262-274 (alpha uses p.snow_cv, not the effective cv)
@@ -362,8 +415,7 @@ __device__ __forceinline__ void gs_step_core(GsState& s, GsCache& cache, double&
         storage = SB2_CK_STORAGE(cache);
         sca = SB2_CK_SCA(cache);
     } else {
-        if (FLAT) gs_calc_snow_state_impl<true>(alpha, sdc_scale, y0, acc_melt, lwc, p.max_water, temp_swe, storage, sca, SB2_CK_LGKEY(cache), SB2_CK_LGVAL(cache));
-        else gs_calc_snow_state(alpha, sdc_scale, y0, acc_melt, lwc, p.max_water, temp_swe, storage, sca, SB2_CK_LGKEY(cache), SB2_CK_LGVAL(cache));
+        gs_calc_snow_state(alpha, sdc_scale, y0, acc_melt, lwc, p.max_water, temp_swe, storage, sca, SB2_CK_LGKEY(cache), SB2_CK_LGVAL(cache));  // cold: memo hit
         gs_cache_store(cache, alpha, sdc_scale, acc_melt, lwc, temp_swe, storage, sca);
     }
     const double start_storage_value = storage;
@@ -426,7 +478,7 @@ __device__ __forceinline__ void gs_step_core(GsState& s, GsCache& cache, double&
         storage = SB2_CK_STORAGE(cache);
         sca = SB2_CK_SCA(cache);
     } else {
-        if (FLAT) gs_calc_snow_state_impl<true>(alpha, sdc_scale, y0, acc_melt, lwc, p.max_water, temp_swe, storage, sca, SB2_CK_LGKEY(cache), SB2_CK_LGVAL(cache));
+        if (FLAT) gs_calc_snow_state_hot(alpha, sdc_scale, y0, acc_melt, lwc, p.max_water, temp_swe, storage, sca, SB2_CK_LGKEY(cache), SB2_CK_LGVAL(cache));
         else gs_calc_snow_state(alpha, sdc_scale, y0, acc_melt, lwc, p.max_water, temp_swe, storage, sca, SB2_CK_LGKEY(cache), SB2_CK_LGVAL(cache));
         gs_cache_store(cache, alpha, sdc_scale, acc_melt, lwc, temp_swe, storage, sca);
     }
@@ -852,6 +904,13 @@ __global__ void __launch_bounds__(SB2_BLOCK, SB2_MINBLOCKS) ptgsk_run_kernel(con
     }
 }
 
+// L1 prefetch of a [step][cell] element a few steps ahead: the step kernels consume one 8-byte value per array and step, so the
+// register prefetch (one step ahead) leaves the DRAM latency exposed whenever a step is short (snow-free cells, single-try steps)
+__device__ __forceinline__ void prefetch_l1(const double* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#ifndef SB2_PREFETCH_AHEAD
+#define SB2_PREFETCH_AHEAD 4
+#endif
+
 // ---- the phase pipeline (the production path of run_cells) ----------------------------------------------------------
 // The stack of one step is a chain  forcing -> snow -> response  with no feedback from the Kirchner response into the snow
 // pack, so a window of steps is run as three kernels that hand [step][cell] arrays to each other:
@@ -929,6 +988,10 @@ __global__ void __launch_bounds__(SB2_BLOCK_B, SB2_MINBLOCKS_B) ptgsk_snow_kerne
             const int64_t o1 = o + n;
             f_t = a.f[0][o1]; f_p = a.f[1][o1]; f_r = a.f[2][o1]; f_lw = a.scr[SCR_LW][o1]; f_ta = a.scr[SCR_TADD][o1];
         }
+        if (SB2_PREFETCH_AHEAD > 1 && i + SB2_PREFETCH_AHEAD < a.n_steps) {
+            const int64_t o2 = o + SB2_PREFETCH_AHEAD * n;
+            prefetch_l1(a.f[0] + o2); prefetch_l1(a.f[1] + o2); prefetch_l1(a.f[2] + o2); prefetch_l1(a.scr[SCR_LW] + o2); prefetch_l1(a.scr[SCR_TADD] + o2);
+        }
         const int64_t step = a.first_step + i;
         const int64_t orow = (step - a.out_first_step) * n + c;
         if (COLLECT & 8) {  // state at the beginning of the period, scale_snow applied (pt_gs_k.h:213-218,367)
@@ -1004,6 +1067,11 @@ __global__ void __launch_bounds__(SB2_BLOCK_C, SB2_MINBLOCKS_C) ptgsk_response_k
         if (i + 1 < a.n_steps) {
             const int64_t o1 = (int64_t)(i + 1) * n + cc;
             f_t = a.f[0][o1]; f_p = a.f[1][o1]; f_pot = a.scr[SCR_POT][o1]; f_out = a.scr[SCR_OUTFLOW][o1]; f_sca = a.scr[SCR_SCA][o1];
+        }
+        if (SB2_PREFETCH_AHEAD > 1 && i + SB2_PREFETCH_AHEAD < a.n_steps) {
+            const int64_t o2 = (int64_t)(i + SB2_PREFETCH_AHEAD) * n + cc;
+            prefetch_l1(a.f[0] + o2); prefetch_l1(a.f[1] + o2); prefetch_l1(a.scr[SCR_POT] + o2); prefetch_l1(a.scr[SCR_OUTFLOW] + o2);
+            prefetch_l1(a.scr[SCR_SCA] + o2);
         }
         const int64_t step = a.first_step + i;
         const int64_t orow = (step - a.out_first_step) * n + cc;
