@@ -42,6 +42,7 @@ extern "C" {
 const char* sho_last_error() { return g_err.c_str(); }
 int sho_hardware_concurrency() { return int(std::thread::hardware_concurrency()); }
 #ifdef SHO_COUNT
+void sho_cost_buffer(unsigned char* buf) { dm::g_cost_cursor = buf; }
 void sho_counters(long long* out, int reset) {  // tools/cost_model.py
     for (int i = 0; i < dm::C_N; ++i) { out[i] = dm::g_cnt.v[i]; if (reset) dm::g_cnt.v[i] = 0; }
 }

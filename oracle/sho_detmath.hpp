@@ -26,6 +26,7 @@ struct counters_t { long long v[16]; };
 enum { C_EXP, C_LOG, C_LGAMMA, C_GSER_CALLS, C_GSER_ITER, C_GCF_CALLS, C_GCF_ITER, C_BRENT_CALLS, C_BRENT_EVAL, C_KIR_TRY, C_KIR_REJECT, C_SNOW_STATE,
        C_GS_ACTIVE, C_CELL_STEPS, C_N };
 inline counters_t g_cnt{};
+inline unsigned char* g_cost_cursor = nullptr;  // tools/cost_model.py: 4 bytes per cell-step {series terms, fraction convergents, exp+log, brent evals} of gamma_snow
 } }
 #define SHO_CNT(i, n) (::sho::dm::g_cnt.v[::sho::dm::i] += (n))
 #else

@@ -139,8 +139,19 @@ inline void run_pt_gs_k(const geo_cell& geo, const parameter& parameter, const f
         double prec = f.prec[int64_t(i) * f.stride] * parameter.p_corr.scale_factor;  // precipitation_correction.h:39-41
         collect_state(i);
 
+#ifdef SHO_COUNT
+        const dm::counters_t cnt0 = dm::g_cnt;
+#endif
         gs.step(st.gs, response.gs, p_start, timespan, parameter.gs, temp, rad, prec, f.wind_speed[int64_t(i) * f.stride], rel_hum,
                 forest_fraction, altitude);
+#ifdef SHO_COUNT
+        if (dm::g_cost_cursor) {
+            auto d = [&](int k) { const long long v = dm::g_cnt.v[k] - cnt0.v[k]; return (unsigned char)(v > 255 ? 255 : v); };
+            dm::g_cost_cursor[0] = d(dm::C_GSER_ITER); dm::g_cost_cursor[1] = d(dm::C_GCF_ITER);
+            dm::g_cost_cursor[2] = (unsigned char)(d(dm::C_EXP) + d(dm::C_LOG)); dm::g_cost_cursor[3] = d(dm::C_BRENT_EVAL);
+            dm::g_cost_cursor += 4;
+        }
+#endif
         response.gm_melt_m3s = glacier_melt::step(parameter.gm.dtf, temp, cell_area_m2 * response.gs.sca, glacier_area_m2);
         response.pt_pot_evapotranspiration = pt.potential_evapotranspiration(temp, rad, rel_hum) * to_seconds(HOUR);
         response.ae = actual_evapotranspiration::calculate_step(st.kirchner_q, response.pt_pot_evapotranspiration,

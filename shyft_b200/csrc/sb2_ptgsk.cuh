@@ -249,54 +249,52 @@ __device__ __forceinline__ void gs_calc_snow_state_impl(double shape, double sca
     swe *= 1.0 - y0;
 }
 
-// The same function for the snow kernel's hot call site (end of step): exp / log / the incomplete gamma expanded in place, and both
-// evaluations (snow-free fraction at lambda, saturated fraction at lwd / max_water_frac) advanced together by gamma_p_pair_inl.
-__device__ __forceinline__ void gs_calc_snow_state_hot(double shape, double scale, double y0, double lambda, double lwd, double max_water_frac,
+// The same function for the snow kernel's hot call site (end of step): exp / log / the incomplete gamma expanded in place (no calls
+// inside, coefficients in uniform registers), itself out of line so that its registers do not weigh on the step loop.  Measured
+// alternatives (profiles/README.md): expanded in the step loop (-3 %), one shared copy of prefix + incomplete gamma in a two-pass
+// loop (-8 %), both evaluations advanced together in one pair of loops (gamma_p_pair_inl, -15 %: on most steps only one is needed).
+#ifndef SB2_SNOW_HOT_NOINLINE
+#define SB2_SNOW_HOT_NOINLINE 1
+#endif
+#if SB2_SNOW_HOT_NOINLINE
+__device__ __noinline__
+#else
+__device__ __forceinline__
+#endif
+void gs_calc_snow_state_hot(double shape, double scale, double y0, double lambda, double lwd, double max_water_frac,
                                                        double temp_swe, double& swe, double& sca, double& lg_key, double& lg_val) {
-    const double m = shape * scale;
-    const bool need1 = !(lambda <= 0.0);
-    double x1 = 0.0, x2 = 0.0, sat = 0.0;
-    if (need1) {
-        x1 = lambda / scale;
-        if (x1 > 1.3 * shape + 20.0) {
-            swe = sca = 0.0;
-            return;
-        }
-    }
-    const bool need2 = !(lwd > m) && lwd > 0.0;
-    if (need2) {
-        sat = lwd / max_water_frac;
-        x2 = sat / scale;
-    }
-    double lg = 0.0;
-    if (need1 || need2) {
-        if (shape != lg_key) { lg_key = shape; lg_val = sb_lgamma(shape); }
-        lg = lg_val;
-    }
-    double pre1 = 0.0, P1 = 0.0, pre2 = 0.0, P2 = 0.0;
-    if (need1 || need2) {
-        // both prefixes x^a e^-x / Gamma(a) side by side (two independent exp/log chains), then both incomplete gammas in one pair of loops
-        pre1 = sb_exp_flat(shape * sb_log_flat(x1) - x1 - lg);
-        pre2 = sb_exp_flat(shape * sb_log_flat(x2) - x2 - lg);
-        const bool g1 = need1 && x1 > 0.0;                  // !(x1 > 0): P1 = 0 (x1 = inf has returned above)
-        const bool g2 = need2 && !(x2 == inf_());           // x2 = inf: P2 = 1
-        if (need2 && !g2) P2 = 1.0;
-        gamma_p_pair_inl(shape, x1, g1, pre1, x2, g2, pre2, P1, P2);
-    }
     double y = 0.0, y1 = 0.0;
-    if (need1) {
-        y = P1;
-        y1 = y - pre1 / shape;
-        swe = m * (1.0 - y1) - lambda * (1 - y);
-        sca = (1.0 - y) * (1.0 - y0);
-    } else {
+    const double m = shape * scale;
+    double lg = 0.0;
+    bool have_lg = false;
+    if (lambda <= 0.0) {
         swe = m;
         sca = 1.0 - y0;
+    } else if (lambda / scale > 1.3 * shape + 20.0) {
+        swe = sca = 0.0;
+        return;
+    } else {
+        const double x = lambda / scale;
+        if (shape != lg_key) { lg_key = shape; lg_val = sb_lgamma(shape); }
+        lg = lg_val;
+        have_lg = true;
+        const double pre = sb_exp_flat(shape * sb_log_flat(x) - x - lg);
+        y = (x > 0.0) ? gamma_p_with_prefix_inl(shape, x, pre) : 0.0;
+        y1 = y - pre / shape;
+        swe = m * (1.0 - y1) - lambda * (1 - y);
+        sca = (1.0 - y) * (1.0 - y0);
     }
     if (lwd > m) swe *= 1.0 + max_water_frac;
-    else if (need2) {
-        const double ssa = P2;
-        const double ssa1 = ssa - pre2 / shape;
+    else if (lwd > 0.0) {
+        const double sat = lwd / max_water_frac;
+        const double x = sat / scale;
+        if (!have_lg) {
+            if (shape != lg_key) { lg_key = shape; lg_val = sb_lgamma(shape); }
+            lg = lg_val;
+        }
+        const double pre = sb_exp_flat(shape * sb_log_flat(x) - x - lg);
+        const double ssa = (x == inf_()) ? 1.0 : gamma_p_with_prefix_inl(shape, x, pre);
+        const double ssa1 = ssa - pre / shape;
         const double liqwat = max_water_frac * (m * (ssa1 - y1) + sat * (1.0 - ssa) - lambda * (1.0 - y));
         swe += liqwat;
     }
@@ -932,7 +930,7 @@ __device__ __forceinline__ void prefetch_l1(const double* p) { asm volatile("pre
 #define SB2_BLOCK_B 32
 #endif
 #ifndef SB2_MINBLOCKS_B
-#define SB2_MINBLOCKS_B 16
+#define SB2_MINBLOCKS_B 12
 #endif
 #ifndef SB2_BLOCK_C
 #define SB2_BLOCK_C 32

@@ -5,7 +5,8 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from shyft_b200 import _build
 
-VARIANTS = {"pf0": ["-DSB2_PREFETCH_AHEAD=0"], "pf2": ["-DSB2_PREFETCH_AHEAD=2"], "pf8": ["-DSB2_PREFETCH_AHEAD=8"],
+VARIANTS = {"snowfn": ["-DSB2_SNOW_HOT_NOINLINE=1"], "snowfn12": ["-DSB2_SNOW_HOT_NOINLINE=1", "-DSB2_MINBLOCKS_B=12"], "snowfn20": ["-DSB2_SNOW_HOT_NOINLINE=1", "-DSB2_MINBLOCKS_B=20"],
+            "pf0": ["-DSB2_PREFETCH_AHEAD=0"], "pf2": ["-DSB2_PREFETCH_AHEAD=2"], "pf8": ["-DSB2_PREFETCH_AHEAD=8"],
             "pB32x12": ["-DSB2_MINBLOCKS_B=12"], "pB32x20": ["-DSB2_MINBLOCKS_B=20"], "pB64x8": ["-DSB2_BLOCK_B=64", "-DSB2_MINBLOCKS_B=8"],
             "pC64x8": ["-DSB2_BLOCK_C=64", "-DSB2_MINBLOCKS_C=8"], "pC32x20": ["-DSB2_BLOCK_C=32", "-DSB2_MINBLOCKS_C=20"], "pC32x12": ["-DSB2_BLOCK_C=32", "-DSB2_MINBLOCKS_C=12"], "pC64x6": ["-DSB2_BLOCK_C=64", "-DSB2_MINBLOCKS_C=6"], "pC32x24": ["-DSB2_BLOCK_C=32", "-DSB2_MINBLOCKS_C=24"], "pC128x4": ["-DSB2_BLOCK_C=128", "-DSB2_MINBLOCKS_C=4"], "pC32x16": ["-DSB2_BLOCK_C=32", "-DSB2_MINBLOCKS_C=16"],
             "nosmemcache": ["-DSB2_CACHE_SMEM=0"], "inl": ["-DSB2_MATH_INLINE=1"], "b128": ["-DSB2_BLOCK=128", "-DSB2_MINBLOCKS=1"], "b64m8": ["-DSB2_BLOCK=64", "-DSB2_MINBLOCKS=8"], "b64m10": ["-DSB2_BLOCK=64", "-DSB2_MINBLOCKS=10"],
