@@ -370,6 +370,7 @@ void launch_step_range(sb2_model* m, int64_t first, int64_t n_steps, bool collec
                 m->d_scr[k].ensure(size_t(std::min<int64_t>(m->partial_steps, n_steps)) * n);
                 a.scr[k] = m->d_scr[k].p;
             }
+            a.ens_scr_stride = 0;
             ptgsk_forcing_terms_kernel<<<dim3((unsigned)grid_for(n, SB2_BLOCK_A), (unsigned)grid_for(chunk, SB2_STEPS_A)), SB2_BLOCK_A, 0, m->stream>>>(a);
             const int gb = grid_for(n, SB2_BLOCK_B), gc = grid_for(n, SB2_BLOCK_C);
             switch (m->collect_bits & 14) {
@@ -817,7 +818,7 @@ double evaluate_goal_single(sb2_model* m) {
     return combine_goal(m, partial.data());
 }
 
-// ensemble of region-parameter sets for pt_gs_k: member e = blockIdx.y steps its own copy of the state; the forcing reads are shared
+// ensemble of region-parameter sets for pt_gs_k: member e = one grid layer of the phase pipeline, stepping its own copy of the state
 void goal_batch_ptgsk(sb2_model* m, int64_t n_sets, const double* P, double* goals) {
     sync_parameters(m);
     sync_filter(m);
@@ -826,8 +827,11 @@ void goal_batch_ptgsk(sb2_model* m, int64_t n_sets, const double* P, double* goa
     // members per pass from a ~12 GB budget: state + catchment series (discharge, charge)
     const size_t per_member = state_sz * 8 + size_t(T) * nc * 16;
     const int64_t E = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(n_sets, 65535), int64_t((12ULL << 30) / per_member)));
-    const int64_t ps = std::max<int64_t>(1, std::min<int64_t>(T, int64_t((1ULL << 30) / (size_t(E) * m->n_slots * 16))));
-    DevArray<double> d_state, d_partial, d_cq, d_cc, d_out;
+    // steps per pass: ~1 GB of per-slot partial sums and ~4 GB of phase-pipeline scratch (five [E][ps][n] arrays)
+    const int64_t ps = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(T, int64_t((1ULL << 30) / (size_t(E) * m->n_slots * 16))),
+                                                               std::max<int64_t>(8, int64_t((4ULL << 30) / (size_t(E) * n * 40)))));
+    DevArray<double> d_state, d_partial, d_cq, d_cc, d_out, d_scr[5];
+    for (auto& b : d_scr) b.resize(size_t(E) * ps * n);
     DevArray<PtgskParam> d_par;
     DevArray<GoalTarget> d_gt;
     d_state.resize(size_t(E) * state_sz);
@@ -862,7 +866,14 @@ void goal_batch_ptgsk(sb2_model* m, int64_t n_sets, const double* P, double* goa
             a.out_first_step = 0; a.collect_end_state = 0;
             a.slot = m->d_slot.p; a.partial = d_partial.p; a.n_slots = m->n_slots; a.error_flag = m->d_error_flag.p;
             a.ens_params = d_par.p; a.ens_state_stride = int64_t(state_sz); a.ens_partial_stride = ps * m->n_slots * 2;
-            ptgsk_run_kernel<0><<<dim3((unsigned)grid_for(n, SB2_BLOCK), (unsigned)ne), SB2_BLOCK, 0, m->stream>>>(a);
+            for (int k = 0; k < 5; ++k) a.scr[k] = d_scr[k].p;
+            a.ens_scr_stride = ps * n;
+            // the same phase pipeline as run_cells, one grid layer per member
+            ptgsk_forcing_terms_kernel<<<dim3((unsigned)grid_for(n, SB2_BLOCK_A), (unsigned)grid_for(chunk, SB2_STEPS_A), (unsigned)ne), SB2_BLOCK_A, 0,
+                                         m->stream>>>(a);
+            ptgsk_snow_kernel<0><<<dim3((unsigned)grid_for(n, SB2_BLOCK_B), (unsigned)ne), SB2_BLOCK_B, 0, m->stream>>>(a);
+            ptgsk_response_kernel<0><<<dim3((unsigned)grid_for(n, SB2_BLOCK_C), (unsigned)ne), SB2_BLOCK_C, 0, m->stream>>>(a);
+            m->launches += 2;
             CUDA_OK(cudaGetLastError());
             const int64_t total = int64_t(chunk) * nc;
             catchment_reduce_kernel<<<dim3((unsigned)grid_for(total, 256), (unsigned)ne), 256, 0, m->stream>>>(
@@ -1513,7 +1524,7 @@ int sb2_calculate_goal_function_batch(sb2_model* m, int64_t n_sets, const double
 // ---- diagnostics ---------------------------------------------------------------------------------------------------------------
 int sb2_unit_eval(int device, int fn, int64_t n, const double* in, int n_in, double* out, int n_out) {
     try {
-        static const int need_in[UNIT_N] = {1, 1, 2, 1, 2, 5, 7, 7}, need_out[UNIT_N] = {1, 1, 1, 1, 1, 1, 2, 3};
+        static const int need_in[UNIT_N] = {1, 1, 2, 1, 2, 5, 7, 7, 1, 1, 2, 7, 7, 3}, need_out[UNIT_N] = {1, 1, 1, 1, 1, 1, 2, 3, 1, 1, 1, 2, 3, 2};
         if (fn < 0 || fn >= UNIT_N) throw Error("unknown unit function");
         if (n_in < need_in[fn] || n_out < need_out[fn]) throw Error("unit function: too few input or output columns");
         CUDA_OK(cudaSetDevice(device));

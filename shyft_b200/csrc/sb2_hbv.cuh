@@ -279,18 +279,18 @@ __global__ void __launch_bounds__(128) hbv_run_kernel(const HbvRunArgs a) {
         const int64_t step = a.first_step + i;
         const int64_t orow = (step - a.out_first_step) * n + cc;
         double out_q = 0.0, out_charge = 0.0;
+        // pt_hs_k: the Kirchner solver is warp-synchronous (kirchner_step_warp), so the step is split around it: every lane calls it,
+        // lanes without an active cell on benign inputs
+        double prec = 0.0, snow_outflow = 0.0, gm_melt_m3s = 0.0, pot = 0.0, gm_mmh = 0.0, ae = 0.0, total_discharge = 0.0, soil_outflow = 0.0;
         if (active) {
             const double temp = a.f[0][o], rad = a.f[2][o], rel_hum = a.f[4][o];
-            const double prec = a.f[1][o] * p.p_corr_scale_factor;
+            prec = a.f[1][o] * p.p_corr_scale_factor;
             if (a.collect & 8) collect_state(orow);
-            double snow_outflow;
             if (!hbv_snow_step(sp, sw, swe, sca, snow_outflow, p, a.dt_seconds, prec, temp)) failed_snow = true;
             const double sca_m2 = cell_area_m2 * sca;
-            const double gm_melt_m3s =
-                (glacier_area_m2 <= sca_m2 || temp <= 0.0) ? 0.0 : p.gm_dtf * temp * (glacier_area_m2 - sca_m2) * (0.001 / 86400.0);
-            const double pot = pt_potential_evapotranspiration(p.pt_albedo, p.pt_alpha, temp, rad, rel_hum) * 3600.0;
-            const double gm_mmh = m3s_to_mmh(gm_melt_m3s, cell_area_m2);
-            double ae, total_discharge, soil_outflow = 0.0;
+            gm_melt_m3s = (glacier_area_m2 <= sca_m2 || temp <= 0.0) ? 0.0 : p.gm_dtf * temp * (glacier_area_m2 - sca_m2) * (0.001 / 86400.0);
+            pot = pt_potential_evapotranspiration<true>(p.pt_albedo, p.pt_alpha, temp, rad, rel_hum) * 3600.0;
+            gm_mmh = gm_melt_m3s == 0.0 ? 0.0 : m3s_to_mmh(gm_melt_m3s, cell_area_m2);  // +0 / positive = +0
             if (HBV_STACK) {
                 const double snow_fraction = dmax(sca, glacier_fraction);
                 ae = (1.0 - snow_fraction) * (x0 < p.lp ? pot * (x0 / p.lp) : pot);  // hbv_actual_evapotranspiration.h:32-38
@@ -313,15 +313,22 @@ __global__ void __launch_bounds__(128) hbv_run_kernel(const HbvRunArgs a) {
                 }
                 total_discharge = dmax(0.0, prec - ae) * direct_response_fraction + gm_direct * gm_mmh + tank_outflow * land_fraction;
             } else {
-                ae = pot * (1.0 - sb_exp(-x0 * 3.0 / p.ae_scale_factor)) * (1.0 - dmax(sca, glacier_fraction));
-                double q_avg;
-                if (!kirchner_step(p.c1, p.c2, p.c3, a.dt_hours, x0, q_avg,
-                                   snow_outflow * snow_storage_fraction + prec * kirchner_routed_prec + gm_routed * gm_mmh, ae)) {
-                    failed_k = true;
-                    q_avg = nan("");
-                }
+                ae = pot * (1.0 - sb_exp_flat(-x0 * 3.0 / p.ae_scale_factor)) * (1.0 - dmax(sca, glacier_fraction));
+            }
+        }
+        if (!HBV_STACK) {
+            double q_avg, kq_new = active ? x0 : 1.0;
+            const double k_in = snow_outflow * snow_storage_fraction + prec * kirchner_routed_prec + gm_routed * gm_mmh;
+            if (!kirchner_step_warp(p.c1, p.c2, p.c3, a.dt_hours, kq_new, q_avg, active ? k_in : 0.0, active ? ae : 0.0)) {
+                failed_k = true;
+                q_avg = nan("");
+            }
+            if (active) {
+                x0 = kq_new;
                 total_discharge = dmax(0.0, prec - ae) * direct_response_fraction + gm_direct * gm_mmh + q_avg * land_fraction;
             }
+        }
+        if (active) {
             const double charge_m3s =
                 +mmh_to_m3s(prec, cell_area_m2) - mmh_to_m3s(ae, cell_area_m2) + gm_melt_m3s - mmh_to_m3s(total_discharge, cell_area_m2);
             out_q = mmh_to_m3s(total_discharge, cell_area_m2);

@@ -1,7 +1,8 @@
-// sb2_ptgsk.cuh -- the pt_gs_k cell stack as one sm_100a kernel.
+// sb2_ptgsk.cuh -- the pt_gs_k cell stack on sm_100a: a three-kernel phase pipeline per time window
+// (forcing terms -> gamma_snow -> response, see "the phase pipeline" below).
 //
-// One thread per cell, the nine fp64 state values in registers for the whole time window, forcing and
-// collected series laid out [time][cell] so each step's loads and stores are coalesced 8-byte accesses,
+// One thread per cell in the two stateful kernels, the fp64 state values in registers for the whole time window, forcing,
+// scratch and collected series laid out [time][cell] so each step's loads and stores are coalesced 8-byte accesses,
 // per-catchment discharge reduced by a segmented warp shuffle into fixed slots (deterministic).
 //
 // Follows, step for step:
@@ -84,33 +85,16 @@ struct PtgskRunArgs {
     // phase pipeline scratch, element (local step i, cell c) at scr[k][i*n_cells + c]:
     // 0 potential evapotranspiration [mm/h], 1 long-wave addend, 2 turbulent addend, 3 snow outflow [mm/h], 4 snow covered area
     double* __restrict__ scr[5];
+    int64_t ens_scr_stride;  // elements between two members' scratch arrays
 };
 enum : int { SCR_POT = 0, SCR_LW = 1, SCR_TADD = 2, SCR_OUTFLOW = 3, SCR_SCA = 4 };
 
 struct GsState { double albedo, lwc, surface_heat, alpha, sdc_melt_mean, acc_melt, iso_pot_energy, temp_swe; };
 // Exact memoisation across steps.  The snow state a step ends with (calc_snow_state at gamma_snow.h:472) is what the next
 // step starts by recomputing (:411) from the same five numbers; when their bits are unchanged the result is reused.
-#ifndef SB2_CACHE_SMEM
-#define SB2_CACHE_SMEM 0  // 1 = keep the memo in shared memory ([field][thread]); measured no gain on B200 (513 vs 503 ms), registers it is
-#endif
 #ifndef SB2_BLOCK
-#define SB2_BLOCK 32       // threads per block of the cell-step kernels: one warp per block balances the uneven per-cell work best (measured)
+#define SB2_BLOCK 32       // threads per block of the hbv step kernel (sb2_hbv.cuh)
 #endif
-#if SB2_CACHE_SMEM
-struct GsCache {
-    double* s;  // this thread's column of the block's [9][SB2_BLOCK] shared array
-    __device__ __forceinline__ double& f(int i) { return s[i * SB2_BLOCK]; }
-};
-#define SB2_CK_ALPHA(c) (c).f(0)
-#define SB2_CK_SCALE(c) (c).f(1)
-#define SB2_CK_ACC(c) (c).f(2)
-#define SB2_CK_LWC(c) (c).f(3)
-#define SB2_CK_TSWE(c) (c).f(4)
-#define SB2_CK_STORAGE(c) (c).f(5)
-#define SB2_CK_SCA(c) (c).f(6)
-#define SB2_CK_LGKEY(c) (c).f(7)
-#define SB2_CK_LGVAL(c) (c).f(8)
-#else
 struct GsCache {
     double k_alpha, k_scale, k_acc, k_lwc, k_tswe;  // inputs of the memoised call (NaN = empty)
     double storage, sca;                            // its outputs
@@ -125,7 +109,6 @@ struct GsCache {
 #define SB2_CK_SCA(c) (c).sca
 #define SB2_CK_LGKEY(c) (c).lg_key
 #define SB2_CK_LGVAL(c) (c).lg_val
-#endif
 __device__ __forceinline__ void gs_cache_clear(GsCache& c) {
     SB2_CK_ALPHA(c) = nan_(); SB2_CK_LGKEY(c) = nan_();
     SB2_CK_SCALE(c) = SB2_CK_ACC(c) = SB2_CK_LWC(c) = SB2_CK_TSWE(c) = 0.0;
@@ -497,19 +480,6 @@ __device__ __forceinline__ void gs_step_core(GsState& s, GsCache& cache, double&
     r_outflow = outflow * 3600000000.0 / dt_us;
 }
 
-// the whole step (fused kernel): the early exit of :313-322 is taken before any transcendental is evaluated
-__device__ __forceinline__ void gs_step(GsState& s, GsCache& cache, double& r_sca, double& r_storage, double& r_outflow, const PtgskParam& p, int doy,
-                                        int sec_of_year, double dt_seconds, double dt_us, double BB0, double T, double rad, double prec_mm_h,
-                                        double wind_speed, double rel_hum, double forest_fraction, double altitude) {
-    double lw = 0.0, tadd = 0.0;
-    const double prec = prec_mm_h * dt_us / 3600000000.0;
-    const double acc = (doy == p.winter_end_day_of_year) ? 0.0 : s.acc_melt;
-    const bool bare = ((T < p.tx) ? prec : 0.0) < 1.0e-10 && s.sdc_melt_mean < 1.0e-10 && acc < 0.0;
-    if (!bare) gs_energy_terms(p, BB0, T, wind_speed, rel_hum, lw, tadd);
-    gs_step_core(s, cache, r_sca, r_storage, r_outflow, p, doy, sec_of_year, dt_seconds, dt_us, BB0, T, rad, prec_mm_h, lw, tadd, wind_speed, rel_hum,
-                 forest_fraction, altitude);
-}
-
 // ---- priestley_taylor, core/priestley_taylor.h:75-103 -------------------------------------------------
 template <bool FLAT = false>
 __device__ __forceinline__ double pt_potential_evapotranspiration(double land_albedo, double alpha, double temperature, double global_radiation,
@@ -758,150 +728,6 @@ __device__ __forceinline__ bool kirchner_step_warp(double c1, double c2, double 
     return !failed;
 }
 
-// ---- the window kernel ----------------------------------------------------------------------------------
-// COLLECT bits: 1 avg_discharge+charge, 2 snow sca/swe, 4 snow_outflow/glacier_melt/ae/pe, 8 state series
-#ifndef SB2_MINBLOCKS
-#define SB2_MINBLOCKS 12   // resident blocks per SM the register allocation must allow (<= 168 registers per thread)
-#endif
-
-template <int COLLECT>
-__global__ void __launch_bounds__(SB2_BLOCK, SB2_MINBLOCKS) ptgsk_run_kernel(const PtgskRunArgs a) {
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool in_range = c < a.n_cells;
-    const int64_t cc = in_range ? c : a.n_cells - 1;  // out-of-range lanes shadow the last cell, never store
-    const bool active = in_range && (a.active == nullptr || a.active[cc] != 0);
-    const unsigned lane = threadIdx.x & 31u;
-
-    const int ens = blockIdx.y;
-    const PtgskParam& p = (a.ens_params != nullptr && a.pset[cc] == 0) ? a.ens_params[ens] : a.params[a.pset[cc]];
-    double* __restrict__ state = a.state + (int64_t)ens * a.ens_state_stride;
-    double* __restrict__ partial = a.partial != nullptr ? a.partial + (int64_t)ens * a.ens_partial_stride : nullptr;
-    const double altitude = a.z[cc], cell_area_m2 = a.area[cc];
-    const double glacier_fraction = a.glacier[cc], lake = a.lake[cc], reservoir = a.reservoir[cc], forest_fraction = a.forest[cc];
-    // run_pt_gs_k prologue, pt_gs_k.h:347-357
-    const double gm_direct = p.gm_direct_response;
-    const double gm_routed = 1 - gm_direct;
-    const double snow_storage_fraction = 1.0 - lake - reservoir;
-    const double kirchner_routed_prec = reservoir * (1.0 - p.reservoir_direct_response_fraction) + lake;
-    const double direct_response_fraction = glacier_fraction * gm_direct + reservoir * p.reservoir_direct_response_fraction;
-    const double kirchner_fraction = 1 - direct_response_fraction;
-    const double glacier_area_m2 = cell_area_m2 * glacier_fraction;
-
-    const int64_t n = a.n_cells;
-    GsState gs;
-    gs.albedo = state[0 * n + cc]; gs.lwc = state[1 * n + cc]; gs.surface_heat = state[2 * n + cc]; gs.alpha = state[3 * n + cc];
-    gs.sdc_melt_mean = state[4 * n + cc]; gs.acc_melt = state[5 * n + cc]; gs.iso_pot_energy = state[6 * n + cc];
-    gs.temp_swe = state[7 * n + cc];
-    double kq = state[8 * n + cc];
-#if SB2_CACHE_SMEM
-    __shared__ double cache_s[9 * SB2_BLOCK];
-    GsCache cache{cache_s + threadIdx.x};
-#else
-    GsCache cache;
-#endif
-    gs_cache_clear(cache);
-
-    // segmented-reduction bookkeeping: lanes of one slot are contiguous in the warp
-    int my_slot = -1;
-    bool head = false;
-    if (partial != nullptr) {
-        my_slot = in_range ? a.slot[cc] : -1;
-        const int prev = __shfl_up_sync(0xffffffffu, my_slot, 1);
-        head = in_range && (lane == 0 || prev != my_slot);
-    }
-
-    double f_t = a.f[0][cc], f_p = a.f[1][cc], f_r = a.f[2][cc], f_w = a.f[3][cc], f_h = a.f[4][cc];
-    bool failed = false;
-
-    for (int i = 0; i < a.n_steps; ++i) {
-        const double temp = f_t, prec_raw = f_p, rad = f_r, wind = f_w, rel_hum = f_h;
-        if (i + 1 < a.n_steps) {  // prefetch the next step's forcing while this step computes
-            const int64_t o = (int64_t)(i + 1) * n + cc;
-            f_t = a.f[0][o]; f_p = a.f[1][o]; f_r = a.f[2][o]; f_w = a.f[3][o]; f_h = a.f[4][o];
-        }
-        const int64_t step = a.first_step + i;
-        const int64_t orow = (step - a.out_first_step) * n + cc;
-        double out_q = 0.0, out_charge = 0.0;
-        if (active) {
-            const double prec = prec_raw * p.p_corr_scale_factor;
-            if (COLLECT & 8) {  // state at the beginning of the period, scale_snow applied (pt_gs_k.h:213-218,367)
-                a.st[0][orow] = mmh_to_m3s(kq, cell_area_m2);
-                a.st[1][orow] = gs.albedo;
-                a.st[2][orow] = gs.lwc * snow_storage_fraction;
-                a.st[3][orow] = gs.surface_heat;
-                a.st[4][orow] = gs.alpha;
-                a.st[5][orow] = gs.sdc_melt_mean;
-                a.st[6][orow] = gs.acc_melt;
-                a.st[7][orow] = gs.iso_pot_energy;
-                a.st[8][orow] = gs.temp_swe * snow_storage_fraction;
-            }
-            double sca, storage, outflow;
-            gs_step(gs, cache, sca, storage, outflow, p, a.day_of_year[step], a.sec_of_year[step], a.dt_seconds, a.dt_us, a.bb0, temp, rad, prec, wind,
-                    rel_hum, forest_fraction, altitude);
-            // glacier_melt::step, glacier_melt.h:47-52
-            const double sca_m2 = cell_area_m2 * sca;
-            const double gm_melt_m3s =
-                (glacier_area_m2 <= sca_m2 || temp <= 0.0) ? 0.0 : p.gm_dtf * temp * (glacier_area_m2 - sca_m2) * (0.001 / 86400.0);
-            const double pot = pt_potential_evapotranspiration(p.pt_albedo, p.pt_alpha, temp, rad, rel_hum) * 3600.0;
-            // actual_evapotranspiration::calculate_step, actual_evapotranspiration.h:56-62
-            const double ae = pot * (1.0 - sb_exp(-kq * 3.0 / p.ae_scale_factor)) * (1.0 - dmax(sca, glacier_fraction));
-            const double gm_mmh = m3s_to_mmh(gm_melt_m3s, cell_area_m2);
-            double q_avg;
-            if (!kirchner_step(p.c1, p.c2, p.c3, a.dt_hours, kq, q_avg,
-                               outflow * snow_storage_fraction + prec * kirchner_routed_prec + gm_routed * gm_mmh, ae)) {
-                failed = true;
-                q_avg = nan("");
-            }
-            const double total_discharge = dmax(0.0, prec - ae) * direct_response_fraction + gm_direct * gm_mmh + q_avg * kirchner_fraction;
-            const double charge_m3s =
-                +mmh_to_m3s(prec, cell_area_m2) - mmh_to_m3s(ae, cell_area_m2) + gm_melt_m3s - mmh_to_m3s(total_discharge, cell_area_m2);
-            out_q = mmh_to_m3s(total_discharge, cell_area_m2);
-            out_charge = charge_m3s;
-            if (COLLECT & 1) { a.resp[0][orow] = out_q; a.resp[1][orow] = charge_m3s; }
-            if (COLLECT & 2) { a.resp[2][orow] = sca; a.resp[3][orow] = storage * snow_storage_fraction; }
-            if (COLLECT & 4) {
-                a.resp[4][orow] = mmh_to_m3s(outflow * snow_storage_fraction, cell_area_m2);
-                a.resp[5][orow] = gm_melt_m3s;
-                a.resp[6][orow] = ae;
-                a.resp[7][orow] = pot;
-            }
-        }
-        if (partial != nullptr) {  // warp-uniform
-            double v0 = out_q, v1 = out_charge;
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const double o0 = __shfl_down_sync(0xffffffffu, v0, off);
-                const double o1 = __shfl_down_sync(0xffffffffu, v1, off);
-                const int os = __shfl_down_sync(0xffffffffu, my_slot, off);
-                if (lane + off < 32 && os == my_slot) { v0 += o0; v1 += o1; }
-            }
-            if (head) {
-                double* dst = partial + ((int64_t)i * a.n_slots + my_slot) * 2;
-                dst[0] = v0;
-                dst[1] = v1;
-            }
-        }
-    }
-    if (active) {
-        if ((COLLECT & 8) && a.collect_end_state) {
-            const int64_t orow = (a.first_step + a.n_steps - a.out_first_step) * n + cc;
-            a.st[0][orow] = mmh_to_m3s(kq, cell_area_m2);
-            a.st[1][orow] = gs.albedo;
-            a.st[2][orow] = gs.lwc * snow_storage_fraction;
-            a.st[3][orow] = gs.surface_heat;
-            a.st[4][orow] = gs.alpha;
-            a.st[5][orow] = gs.sdc_melt_mean;
-            a.st[6][orow] = gs.acc_melt;
-            a.st[7][orow] = gs.iso_pot_energy;
-            a.st[8][orow] = gs.temp_swe * snow_storage_fraction;
-        }
-        state[0 * n + cc] = gs.albedo; state[1 * n + cc] = gs.lwc; state[2 * n + cc] = gs.surface_heat; state[3 * n + cc] = gs.alpha;
-        state[4 * n + cc] = gs.sdc_melt_mean; state[5 * n + cc] = gs.acc_melt; state[6 * n + cc] = gs.iso_pot_energy;
-        state[7 * n + cc] = gs.temp_swe; state[8 * n + cc] = kq;
-        if (failed) atomicOr(a.error_flag, ERR_KIRCHNER_STEP);
-    }
-}
-
 // L1 prefetch of a [step][cell] element a few steps ahead: the step kernels consume one 8-byte value per array and step, so the
 // register prefetch (one step ahead) leaves the DRAM latency exposed whenever a step is short (snow-free cells, single-try steps)
 __device__ __forceinline__ void prefetch_l1(const double* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
@@ -943,9 +769,13 @@ __global__ void __launch_bounds__(SB2_BLOCK_A) ptgsk_forcing_terms_kernel(const 
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= a.n_cells) return;
     if (a.active != nullptr && a.active[c] == 0) return;
-    const PtgskParam& p = a.params[a.pset[c]];
+    const int ens = blockIdx.z;  // parameter-set ensemble member (calibration), as in ptgsk_run_kernel
+    const PtgskParam& p = (a.ens_params != nullptr && a.pset[c] == 0) ? a.ens_params[ens] : a.params[a.pset[c]];
     const double pt_albedo = p.pt_albedo, pt_alpha = p.pt_alpha;
     const int64_t n = a.n_cells;
+    double* __restrict__ s_pot = a.scr[SCR_POT] + (int64_t)ens * a.ens_scr_stride;
+    double* __restrict__ s_lw = a.scr[SCR_LW] + (int64_t)ens * a.ens_scr_stride;
+    double* __restrict__ s_tadd = a.scr[SCR_TADD] + (int64_t)ens * a.ens_scr_stride;
     const int i0 = blockIdx.y * SB2_STEPS_A;
     const int i1 = min(i0 + SB2_STEPS_A, a.n_steps);
 #pragma unroll 2
@@ -954,9 +784,9 @@ __global__ void __launch_bounds__(SB2_BLOCK_A) ptgsk_forcing_terms_kernel(const 
         const double temp = a.f[0][o], rad = a.f[2][o], wind = a.f[3][o], rel_hum = a.f[4][o];
         double lw, tadd;
         gs_energy_terms<true>(p, a.bb0, temp, wind, rel_hum, lw, tadd);
-        a.scr[SCR_POT][o] = pt_potential_evapotranspiration<true>(pt_albedo, pt_alpha, temp, rad, rel_hum) * 3600.0;
-        a.scr[SCR_LW][o] = lw;
-        a.scr[SCR_TADD][o] = tadd;
+        s_pot[o] = pt_potential_evapotranspiration<true>(pt_albedo, pt_alpha, temp, rad, rel_hum) * 3600.0;
+        s_lw[o] = lw;
+        s_tadd[o] = tadd;
     }
 }
 
@@ -966,29 +796,34 @@ __global__ void __launch_bounds__(SB2_BLOCK_B, SB2_MINBLOCKS_B) ptgsk_snow_kerne
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= a.n_cells) return;
     if (a.active != nullptr && a.active[c] == 0) return;
-    const PtgskParam& p = a.params[a.pset[c]];
+    const int ens = blockIdx.y;
+    const PtgskParam& p = (a.ens_params != nullptr && a.pset[c] == 0) ? a.ens_params[ens] : a.params[a.pset[c]];
     const int64_t n = a.n_cells;
+    const double* __restrict__ s_lw = a.scr[SCR_LW] + (int64_t)ens * a.ens_scr_stride;
+    const double* __restrict__ s_tadd = a.scr[SCR_TADD] + (int64_t)ens * a.ens_scr_stride;
+    double* __restrict__ s_outflow = a.scr[SCR_OUTFLOW] + (int64_t)ens * a.ens_scr_stride;
+    double* __restrict__ s_sca = a.scr[SCR_SCA] + (int64_t)ens * a.ens_scr_stride;
     const double altitude = a.z[c], cell_area_m2 = a.area[c], forest_fraction = a.forest[c];
     const double snow_storage_fraction = 1.0 - a.lake[c] - a.reservoir[c];
     const bool iso = p.calculate_iso_pot_energy != 0;
-    double* __restrict__ state = a.state;
+    double* __restrict__ state = a.state + (int64_t)ens * a.ens_state_stride;
     GsState gs;
     gs.albedo = state[0 * n + c]; gs.lwc = state[1 * n + c]; gs.surface_heat = state[2 * n + c]; gs.alpha = state[3 * n + c];
     gs.sdc_melt_mean = state[4 * n + c]; gs.acc_melt = state[5 * n + c]; gs.iso_pot_energy = state[6 * n + c];
     gs.temp_swe = state[7 * n + c];
     GsCache cache;
     gs_cache_clear(cache);
-    double f_t = a.f[0][c], f_p = a.f[1][c], f_r = a.f[2][c], f_lw = a.scr[SCR_LW][c], f_ta = a.scr[SCR_TADD][c];
+    double f_t = a.f[0][c], f_p = a.f[1][c], f_r = a.f[2][c], f_lw = s_lw[c], f_ta = s_tadd[c];
     for (int i = 0; i < a.n_steps; ++i) {
         const double temp = f_t, prec = f_p * p.p_corr_scale_factor, rad = f_r, lw = f_lw, tadd = f_ta;
         const int64_t o = (int64_t)i * n + c;
         if (i + 1 < a.n_steps) {
             const int64_t o1 = o + n;
-            f_t = a.f[0][o1]; f_p = a.f[1][o1]; f_r = a.f[2][o1]; f_lw = a.scr[SCR_LW][o1]; f_ta = a.scr[SCR_TADD][o1];
+            f_t = a.f[0][o1]; f_p = a.f[1][o1]; f_r = a.f[2][o1]; f_lw = s_lw[o1]; f_ta = s_tadd[o1];
         }
         if (SB2_PREFETCH_AHEAD > 1 && i + SB2_PREFETCH_AHEAD < a.n_steps) {
             const int64_t o2 = o + SB2_PREFETCH_AHEAD * n;
-            prefetch_l1(a.f[0] + o2); prefetch_l1(a.f[1] + o2); prefetch_l1(a.f[2] + o2); prefetch_l1(a.scr[SCR_LW] + o2); prefetch_l1(a.scr[SCR_TADD] + o2);
+            prefetch_l1(a.f[0] + o2); prefetch_l1(a.f[1] + o2); prefetch_l1(a.f[2] + o2); prefetch_l1(s_lw + o2); prefetch_l1(s_tadd + o2);
         }
         const int64_t step = a.first_step + i;
         const int64_t orow = (step - a.out_first_step) * n + c;
@@ -1007,8 +842,8 @@ __global__ void __launch_bounds__(SB2_BLOCK_B, SB2_MINBLOCKS_B) ptgsk_snow_kerne
         double sca, storage, outflow;
         gs_step_core<true>(gs, cache, sca, storage, outflow, p, a.day_of_year[step], a.sec_of_year[step], a.dt_seconds, a.dt_us, a.bb0, temp, rad, prec,
                            lw, tadd, wind, rel_hum, forest_fraction, altitude);
-        a.scr[SCR_OUTFLOW][o] = outflow;
-        a.scr[SCR_SCA][o] = sca;
+        s_outflow[o] = outflow;
+        s_sca[o] = sca;
         if (COLLECT & 2) { a.resp[2][orow] = sca; a.resp[3][orow] = storage * snow_storage_fraction; }
         if (COLLECT & 4) a.resp[4][orow] = mmh_to_m3s(outflow * snow_storage_fraction, cell_area_m2);
     }
@@ -1036,7 +871,13 @@ __global__ void __launch_bounds__(SB2_BLOCK_C, SB2_MINBLOCKS_C) ptgsk_response_k
     const int64_t cc = in_range ? c : a.n_cells - 1;  // out-of-range lanes shadow the last cell, never store
     const bool active = in_range && (a.active == nullptr || a.active[cc] != 0);
     const unsigned lane = threadIdx.x & 31u;
-    const PtgskParam& p = a.params[a.pset[cc]];
+    const int ens = blockIdx.y;
+    const PtgskParam& p = (a.ens_params != nullptr && a.pset[cc] == 0) ? a.ens_params[ens] : a.params[a.pset[cc]];
+    double* __restrict__ state = a.state + (int64_t)ens * a.ens_state_stride;
+    double* __restrict__ partial = a.partial != nullptr ? a.partial + (int64_t)ens * a.ens_partial_stride : nullptr;
+    const double* __restrict__ s_pot = a.scr[SCR_POT] + (int64_t)ens * a.ens_scr_stride;
+    const double* __restrict__ s_outflow = a.scr[SCR_OUTFLOW] + (int64_t)ens * a.ens_scr_stride;
+    const double* __restrict__ s_sca = a.scr[SCR_SCA] + (int64_t)ens * a.ens_scr_stride;
     const double cell_area_m2 = a.area[cc];
     const double glacier_fraction = a.glacier[cc], lake = a.lake[cc], reservoir = a.reservoir[cc];
     // run_pt_gs_k prologue, pt_gs_k.h:347-357
@@ -1049,27 +890,27 @@ __global__ void __launch_bounds__(SB2_BLOCK_C, SB2_MINBLOCKS_C) ptgsk_response_k
     const double glacier_area_m2 = cell_area_m2 * glacier_fraction;
     const double c1 = p.c1, c2 = p.c2, c3 = p.c3, ae_scale_factor = p.ae_scale_factor, gm_dtf = p.gm_dtf, p_corr = p.p_corr_scale_factor;
     const int64_t n = a.n_cells;
-    double kq = a.state[8 * n + cc];
+    double kq = state[8 * n + cc];
 
     int my_slot = -1;
     bool head = false;
-    if (a.partial != nullptr) {
+    if (partial != nullptr) {
         my_slot = in_range ? a.slot[cc] : -1;
         const int prev = __shfl_up_sync(0xffffffffu, my_slot, 1);
         head = in_range && (lane == 0 || prev != my_slot);
     }
-    double f_t = a.f[0][cc], f_p = a.f[1][cc], f_pot = a.scr[SCR_POT][cc], f_out = a.scr[SCR_OUTFLOW][cc], f_sca = a.scr[SCR_SCA][cc];
+    double f_t = a.f[0][cc], f_p = a.f[1][cc], f_pot = s_pot[cc], f_out = s_outflow[cc], f_sca = s_sca[cc];
     bool failed = false;
     for (int i = 0; i < a.n_steps; ++i) {
         const double temp = f_t, prec = f_p * p_corr, pot = f_pot, outflow = f_out, sca = f_sca;
         if (i + 1 < a.n_steps) {
             const int64_t o1 = (int64_t)(i + 1) * n + cc;
-            f_t = a.f[0][o1]; f_p = a.f[1][o1]; f_pot = a.scr[SCR_POT][o1]; f_out = a.scr[SCR_OUTFLOW][o1]; f_sca = a.scr[SCR_SCA][o1];
+            f_t = a.f[0][o1]; f_p = a.f[1][o1]; f_pot = s_pot[o1]; f_out = s_outflow[o1]; f_sca = s_sca[o1];
         }
         if (SB2_PREFETCH_AHEAD > 1 && i + SB2_PREFETCH_AHEAD < a.n_steps) {
             const int64_t o2 = (int64_t)(i + SB2_PREFETCH_AHEAD) * n + cc;
-            prefetch_l1(a.f[0] + o2); prefetch_l1(a.f[1] + o2); prefetch_l1(a.scr[SCR_POT] + o2); prefetch_l1(a.scr[SCR_OUTFLOW] + o2);
-            prefetch_l1(a.scr[SCR_SCA] + o2);
+            prefetch_l1(a.f[0] + o2); prefetch_l1(a.f[1] + o2); prefetch_l1(s_pot + o2); prefetch_l1(s_outflow + o2);
+            prefetch_l1(s_sca + o2);
         }
         const int64_t step = a.first_step + i;
         const int64_t orow = (step - a.out_first_step) * n + cc;
@@ -1104,7 +945,7 @@ __global__ void __launch_bounds__(SB2_BLOCK_C, SB2_MINBLOCKS_C) ptgsk_response_k
                 }
             }
         }
-        if (a.partial != nullptr) {  // warp-uniform
+        if (partial != nullptr) {  // warp-uniform
             double v0 = out_q, v1 = out_charge;
 #pragma unroll
             for (int off = 1; off < 32; off <<= 1) {
@@ -1114,7 +955,7 @@ __global__ void __launch_bounds__(SB2_BLOCK_C, SB2_MINBLOCKS_C) ptgsk_response_k
                 if (lane + off < 32 && os == my_slot) { v0 += o0; v1 += o1; }
             }
             if (head) {
-                double* dst = a.partial + ((int64_t)i * a.n_slots + my_slot) * 2;
+                double* dst = partial + ((int64_t)i * a.n_slots + my_slot) * 2;
                 dst[0] = v0;
                 dst[1] = v1;
             }
@@ -1125,7 +966,7 @@ __global__ void __launch_bounds__(SB2_BLOCK_C, SB2_MINBLOCKS_C) ptgsk_response_k
             const int64_t orow = (a.first_step + a.n_steps - a.out_first_step) * n + cc;
             a.st[0][orow] = mmh_to_m3s(kq, cell_area_m2);
         }
-        a.state[8 * n + cc] = kq;
+        state[8 * n + cc] = kq;
         if (failed) atomicOr(a.error_flag, ERR_KIRCHNER_STEP);
     }
 }

@@ -6,13 +6,17 @@
 
 namespace sb2 {
 
-enum { UNIT_EXP = 0, UNIT_LOG, UNIT_POW, UNIT_LGAMMA, UNIT_GAMMA_P, UNIT_CORR_LWC, UNIT_CALC_SNOW_STATE, UNIT_KIRCHNER_STEP, UNIT_N };
+enum { UNIT_EXP = 0, UNIT_LOG, UNIT_POW, UNIT_LGAMMA, UNIT_GAMMA_P, UNIT_CORR_LWC, UNIT_CALC_SNOW_STATE, UNIT_KIRCHNER_STEP,
+       // the forms the production kernels use: branch-free exp/log/pow, the in-place snow state, the warp-synchronous Kirchner step
+       UNIT_EXP_FLAT, UNIT_LOG_FLAT, UNIT_POW_FLAT, UNIT_CALC_SNOW_STATE_HOT, UNIT_KIRCHNER_STEP_WARP, UNIT_GAMMA_P_PAIR, UNIT_N };
 
 __global__ void unit_eval_kernel(int fn, int64_t n, const double* __restrict__ in, int n_in, double* __restrict__ out, int n_out) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in_range = i0 < n;
+    const int64_t i = in_range ? i0 : n - 1;  // lanes past the end shadow the last element (warp-synchronous functions need all 32 lanes)
     const double* a = in + i * n_in;
-    double* o = out + i * n_out;
+    double ob[4] = {0.0, 0.0, 0.0, 0.0};
+    double* o = ob;
     switch (fn) {
         case UNIT_EXP: o[0] = sb_exp(a[0]); break;
         case UNIT_LOG: o[0] = sb_log(a[0]); break;
@@ -31,8 +35,32 @@ __global__ void unit_eval_kernel(int fn, int64_t n, const double* __restrict__ i
             o[0] = q; o[1] = q_avg; o[2] = ok ? 1.0 : 0.0;
             break;
         }
+        case UNIT_EXP_FLAT: o[0] = sb_exp_flat(a[0]); break;
+        case UNIT_LOG_FLAT: o[0] = sb_log_flat(a[0]); break;
+        case UNIT_POW_FLAT: o[0] = sb_pow_flat(a[0], a[1]); break;
+        case UNIT_CALC_SNOW_STATE_HOT: {
+            double lg_key = nan_(), lg_val = 0.0;
+            gs_calc_snow_state_hot(a[0], a[1], a[2], a[3], a[4], a[5], a[6], o[0], o[1], lg_key, lg_val);
+            break;
+        }
+        case UNIT_KIRCHNER_STEP_WARP: {
+            double q = a[4], q_avg = 0.0;
+            const bool ok = kirchner_step_warp(a[0], a[1], a[2], a[3], q, q_avg, a[5], a[6]);
+            o[0] = q; o[1] = q_avg; o[2] = ok ? 1.0 : 0.0;
+            break;
+        }
+        case UNIT_GAMMA_P_PAIR: {  // in: a, x1, x2 -> P(a,x1), P(a,x2) advanced together
+            const double lg = sb_lgamma(a[0]);
+            const double pre1 = sb_exp_flat(a[0] * sb_log_flat(a[1]) - a[1] - lg), pre2 = sb_exp_flat(a[0] * sb_log_flat(a[2]) - a[2] - lg);
+            double P1 = 0.0, P2 = 0.0;
+            gamma_p_pair_inl(a[0], a[1], a[1] > 0.0, pre1, a[2], a[2] > 0.0, pre2, P1, P2);
+            o[0] = P1; o[1] = P2;
+            break;
+        }
         default: break;
     }
+    if (in_range)
+        for (int k = 0; k < n_out && k < 4; ++k) out[i * n_out + k] = ob[k];
 }
 
 }  // namespace sb2

@@ -31,6 +31,18 @@ def test_deterministic_math_is_bit_identical(capi, oracle):
     assert _bits_equal(capi.unit_eval("lgamma", a)[:, 0], oracle.dm_eval("lgamma", a))
 
 
+def test_branch_free_forms_are_bit_identical(capi, oracle):
+    """sb_exp_flat / sb_log_flat / sb_pow_flat (what the production kernels expand in place) against the same oracle functions."""
+    rng = np.random.default_rng(43)
+    x = np.concatenate([rng.uniform(-745, 709, 200000), rng.uniform(-2, 2, 200000), [0.0, -0.0, 1e-300, 689.9, 690.0, 709.78, 710.0, -745.0, -746.0, np.nan, np.inf, -np.inf]])
+    assert _bits_equal(capi.unit_eval("exp_flat", x)[:, 0], oracle.dm_eval("exp", x))
+    x = np.concatenate([np.exp(rng.uniform(-740, 709, 200000)), rng.uniform(0.5, 2.0, 200000), [0.0, 1.0, 5e-324, 1e-310, np.inf, -1.0, np.nan]])
+    assert _bits_equal(capi.unit_eval("log_flat", x)[:, 0], oracle.dm_eval("log", x))
+    xy = np.stack([rng.uniform(0, 50, 200000), rng.uniform(-4, 4, 200000)], axis=1)
+    xy[:8] = [[0, 1.5], [0, -1.5], [2, 0], [3, 1], [3, 2], [9, 0.5], [1.02, 3.5], [5, -1.0 / 3]]
+    assert _bits_equal(capi.unit_eval("pow_flat", xy)[:, 0], oracle.dm_eval("pow", xy[:, 0], xy[:, 1]))
+
+
 def test_gamma_p_is_bit_identical_and_accurate(capi, oracle):
     sp = pytest.importorskip("scipy.special")
     rng = np.random.default_rng(7)
@@ -40,6 +52,11 @@ def test_gamma_p_is_bit_identical_and_accurate(capi, oracle):
     assert _bits_equal(got, oracle.dm_eval("gamma_p", a, x))
     ref = sp.gammainc(a, x)
     assert np.max(np.abs(got - ref) / np.maximum(ref, 1e-300)) < 5e-13
+    # two arguments of one shape advanced together (gamma_p_pair_inl): each equals its own evaluation
+    x2 = rng.uniform(0.0, 1.0, 100000) * (3 * a + 25)
+    pair = capi.unit_eval("gamma_p_pair", np.stack([a, x, x2], axis=1))
+    assert _bits_equal(pair[:, 0], got)
+    assert _bits_equal(pair[:, 1], oracle.dm_eval("gamma_p", a, x2))
 
 
 def test_corr_lwc_known_answer_and_bit_identity(capi, oracle):
@@ -68,6 +85,7 @@ def test_calc_snow_state_known_answer_and_bit_identity(capi, oracle):
     got = capi.unit_eval("calc_snow_state", rows)
     want = np.array([oracle.gs_calc_snow_state(*r) for r in rows])
     assert _bits_equal(got, want)
+    assert _bits_equal(capi.unit_eval("calc_snow_state_hot", rows), want)   # the snow kernel's in-place form
 
 
 def test_kirchner_step_bit_identity_and_known_behaviour(capi, oracle):
@@ -83,6 +101,11 @@ def test_kirchner_step_bit_identity_and_known_behaviour(capi, oracle):
     assert np.all(got[:, 2] == 1.0)
     want = np.array([oracle.kirchner_step(r[4], r[5], r[6], dt_us=int(r[3] * 3600 * 10**6))[:2] for r in rows])
     assert _bits_equal(got[:, :2], want)
+    # the warp-synchronous solver of the production kernels: lanes with 1..n sub-steps share a warp, n not a multiple of 32
+    rows_w = rows[: n - 7]
+    got_w = capi.unit_eval("kirchner_step_warp", rows_w)
+    assert np.all(got_w[:, 2] == 1.0)
+    assert _bits_equal(got_w[:, :2], want[: n - 7])
     # P = 10, E = 0 from q = 1: q and q_avg converge to 10 (test/kirchner_test.cpp:40-54)
     row = np.array([[-2.439, 0.966, -0.10, 1.0, 1.0, 10.0, 0.0]])
     for _ in range(3000):
