@@ -84,6 +84,8 @@ struct IdwPlan {  // neighbour lists of one variable (inverse_distance.h:160-203
     DevArray<double> w, f;
     bool dense_valid = false;      // dense operator for the all-finite case (tensor-core path)
     DevArray<double> dense, addc;  // [n_src][cells], [cells]
+    DevArray<int32_t> ulist;       // station compaction of the dense apply kernel: [tiles][k_slots] union lists ...
+    DevArray<uint8_t> ukc;         // ... and k-steps in use per tile (idw_union_plan_kernel)
 };
 
 struct BtkOps {  // operators of one valid-station subset
@@ -507,13 +509,29 @@ void run_idw(sb2_model* m, int var, int64_t first, int64_t n_steps, double* out)
                                                                               pl.idx.p, pl.w.p, pl.f.p, pl.cnt.p, pl.dense.p, pl.addc.p);
             CUDA_OK(cudaGetLastError());
             ++m->launches;
+            // station compaction lists per tile of the apply kernel (tile shape as dispatched below)
+            const int nvp = int(s.n_src);
+            const int ks = nvp <= 16 ? 4 : (nvp <= 32 ? 8 : (nvp <= 64 ? 16 : 24)), ntile = nvp <= 32 ? 4 : (nvp <= 64 ? 2 : 1);
+            const int64_t n_tiles = grid_for(m->n, 32 * ntile) * 4;  // the apply grid covers whole blocks of four tiles
+            pl.ulist.resize(size_t(n_tiles) * ks * 4);
+            pl.ukc.resize(size_t(n_tiles));
+            CUDA_OK(cudaMemsetAsync(pl.ukc.p, 0, size_t(n_tiles), m->stream));
+            idw_union_plan_kernel<<<grid_for(n_tiles * 32, 128), 128, 0, m->stream>>>(m->n, nvp, pl.dense.p, 8 * ntile, ks * 4, pl.ulist.p, pl.ukc.p);
+            CUDA_OK(cudaGetLastError());
+            ++m->launches;
             pl.dense_valid = true;
         }
         const int nv = int(s.n_src);
         const double* v = s.d_values.p + first * s.n_src;
-#define SB2_DENSE(KS, NT)                                                                                                               \
-    dense_apply_dmma_kernel<KS, NT, 0><<<grid_for(m->n, 32 * NT), 128, 0, m->stream>>>(m->n, nullptr, nv, pl.dense.p, pl.addc.p, nullptr, v,    \
-                                                                                       s.n_src, nullptr, int(n_steps), m->d_active.p, out)
+        const int use_tma = (nv % 2 == 0 && (reinterpret_cast<uintptr_t>(v) & 15) == 0) ? 1 : 0;
+#define SB2_DENSE(KS, NT)                                                                                                                 \
+    do {                                                                                                                                  \
+        const int smem = 2 * (KS > 16 ? 32 : 64) * (KS * 4 + 4) * int(sizeof(double));                                                    \
+        auto kern = dense_apply_dmma_kernel<KS, NT, 0, true>;                                                                             \
+        CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                                           \
+        kern<<<grid_for(m->n, 32 * NT), 128, smem, m->stream>>>(m->n, nullptr, nv, pl.dense.p, pl.addc.p, nullptr, v, s.n_src, nullptr,   \
+                                                                int(n_steps), m->d_active.p, out, pl.ulist.p, pl.ukc.p, use_tma);         \
+    } while (0)
         if (nv <= 16) SB2_DENSE(4, 4);
         else if (nv <= 32) SB2_DENSE(8, 4);
         else if (nv <= 64) SB2_DENSE(16, 2);
@@ -622,9 +640,16 @@ void run_btk(sb2_model* m, int64_t first, int64_t n_steps, double* out) {
         CUDA_OK(cudaGetLastError());
         double* o = out + i * m->n;
         const double* pri = m->d_prior_gradient.p + first + i;
-#define SB2_BTK(KS, NT)                                                                                                               \
-    dense_apply_dmma_kernel<KS, NT, 1><<<grid_for(m->n, 32 * NT), 128, 0, m->stream>>>(m->n, m->d_z.p, nv, op->omega.p, op->bm.p, m->d_btk_beta.p, \
-                                                                                       m->d_btk_resid.p, nv, pri, int(seg), m->d_active.p, o)
+        const int use_tma = (nv % 2 == 0 && (reinterpret_cast<uintptr_t>(m->d_btk_resid.p) & 15) == 0) ? 1 : 0;
+#define SB2_BTK(KS, NT)                                                                                                                   \
+    do {                                                                                                                                  \
+        const int smem = 2 * (KS > 16 ? 32 : 64) * (KS * 4 + 4) * int(sizeof(double));                                                    \
+        auto kern = dense_apply_dmma_kernel<KS, NT, 1, false>;                                                                            \
+        CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                                           \
+        kern<<<grid_for(m->n, 32 * NT), 128, smem, m->stream>>>(m->n, m->d_z.p, nv, op->omega.p, op->bm.p, m->d_btk_beta.p,               \
+                                                                m->d_btk_resid.p, nv, pri, int(seg), m->d_active.p, o, nullptr, nullptr,  \
+                                                                use_tma);                                                                 \
+    } while (0)
         if (nv <= 16) SB2_BTK(4, 4);
         else if (nv <= 32) SB2_BTK(8, 4);
         else if (nv <= 64) SB2_BTK(16, 2);

@@ -291,29 +291,63 @@ __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, do
 //         dense operator W (idw_build_dense_kernel) folds weights, normalisation, the per-neighbour factor and, for
 //         temperature, the min/max-height gradient (inverse_distance.h:304-315) into one matrix -- the "(cells x stations) x
 //         (stations x steps)" contraction of the interpolation step.  A = the station series themselves.
-template <int KSTEPS, int NT, int MODE>
+// Staging: the rows of A for a tile of steps are contiguous in global memory (n_valid doubles each); warp 0 issues one TMA bulk copy
+// (cp.async.bulk, global -> shared, completion counted on an mbarrier) per row into the padded tile, two tiles in flight (double
+// buffer), so the copy of tile i+1 overlaps the DMMAs of tile i.  (Before: a load -> store loop between two __syncthreads took
+// half of the kernel's stall samples, profiles/README.md.)  use_tma = 0 keeps the plain loop for rows that are not 16-byte multiples.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (int spins = 0; !done; ++spins) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (spins > (1 << 24)) __trap();  // a copy that never lands must not hang the device
+    }
+}
+
+template <int KSTEPS, int NT, int MODE, bool COMPACT>
 __global__ void __launch_bounds__(128) dense_apply_dmma_kernel(int64_t n_cells, const double* __restrict__ cz, int n_valid,
                                                                const double* __restrict__ omega /* [n_valid][cells] */, const double* __restrict__ bm,
                                                                const double* __restrict__ beta /* [n_steps][2] */,
                                                                const double* __restrict__ resid /* [n_steps][row_stride] */, int64_t row_stride,
                                                                const double* __restrict__ prior_gradient /* [n_steps] */, int n_steps,
-                                                               const uint8_t* __restrict__ active, double* __restrict__ out /* [n_steps][cells] */) {
+                                                               const uint8_t* __restrict__ active, double* __restrict__ out /* [n_steps][cells] */,
+                                                               const int32_t* __restrict__ ulist, const uint8_t* __restrict__ ukc, int use_tma) {
     constexpr int KP = KSTEPS * 4 + 4;  // padded row stride (doubles), == 4 mod 16
-    constexpr int BTK_TILE_STEPS = KSTEPS > 16 ? 32 : 64;  // steps of resid staged per block iteration (static smem <= 48 KB)
-    __shared__ double sr[BTK_TILE_STEPS * KP];
-    __shared__ double sbeta[BTK_TILE_STEPS * 2];
-    __shared__ double spri[BTK_TILE_STEPS];
+    constexpr int TILE = KSTEPS > 16 ? 32 : 64;  // steps of A staged per buffer
+    extern __shared__ __align__(16) double sr_dyn[];  // two buffers of TILE * KP doubles
+    __shared__ double sbeta[2][TILE * 2];
+    __shared__ double spri[2][TILE];
+    __shared__ __align__(8) unsigned long long bar[2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, q = lane & 3;  // group (row of A / column of B), position in the quad
-    const int64_t cbase = ((int64_t)blockIdx.x * 4 + warp) * (8 * NT);
-    // B fragments: breg[nt][ks] = omega[cell cbase + nt*8 + g][station ks*4 + q]
+    const int64_t tile = (int64_t)blockIdx.x * 4 + warp;
+    const int64_t cbase = tile * (8 * NT);
+    // Station compaction (COMPACT, inverse distance): a tile of 8*NT neighbouring cells draws on a dozen of the stations, so the
+    // contraction runs over the tile's union list only (ulist: station of k-slot ks*4+q, padded with the index of a zero column;
+    // ukc: k-steps in use) -- the zero weights of a 64-station operator are 3 k-steps out of 4.  Otherwise the slots are the stations.
+    int ul[KSTEPS];
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ++ks) ul[ks] = COMPACT ? ulist[tile * (KSTEPS * 4) + ks * 4 + q] : ks * 4 + q;
+    const int kc = COMPACT ? ukc[tile] : KSTEPS;
+    // B fragments: breg[nt][ks] = omega[cell cbase + nt*8 + g][station of slot ks*4 + q]
     double breg[NT][KSTEPS];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
         const int64_t cell = cbase + nt * 8 + g;
 #pragma unroll
         for (int ks = 0; ks < KSTEPS; ++ks) {
-            const int st = ks * 4 + q;
+            const int st = ul[ks];
             breg[nt][ks] = (cell < n_cells && st < n_valid) ? omega[(int64_t)st * n_cells + cell] : 0.0;
         }
     }
@@ -336,50 +370,83 @@ __global__ void __launch_bounds__(128) dense_apply_dmma_kernel(int64_t n_cells, 
                 e0[nt][h] = e1[nt][h] = 0.0;
             }
         }
-    for (int t0 = 0; t0 < n_steps; t0 += BTK_TILE_STEPS) {
-        const int nt_steps = min(BTK_TILE_STEPS, n_steps - t0);
-        __syncthreads();
-        for (int e = threadIdx.x; e < BTK_TILE_STEPS * KP; e += blockDim.x) {
-            const int r = e / KP, k = e - r * KP;
-            sr[e] = (r < nt_steps && k < n_valid) ? resid[(int64_t)(t0 + r) * row_stride + k] : 0.0;
+    // both buffers zeroed once: the pad columns (and unused stations) stay zero for the whole launch
+    for (int e = threadIdx.x; e < 2 * TILE * KP; e += blockDim.x) sr_dyn[e] = 0.0;
+    if (threadIdx.x == 0 && use_tma) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes above before the async-proxy copies below
+    __syncthreads();
+    const int n_tiles = (n_steps + TILE - 1) / TILE;
+    const bool vec_ok = (n_cells % 2 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);  // rows of out start 16-byte aligned
+    auto stage = [&](int it) {
+        const int buf = it & 1, t0 = it * TILE;
+        const int nt_steps = min(TILE, n_steps - t0);
+        double* dst = sr_dyn + buf * TILE * KP;
+        if (use_tma) {
+            if (warp == 0) {
+                if (lane == 0) mbar_arrive_expect_tx(&bar[buf], (uint32_t)(nt_steps * n_valid * 8));
+                __syncwarp();
+                for (int r = lane; r < nt_steps; r += 32)
+                    bulk_copy_g2s(dst + r * KP, resid + (int64_t)(t0 + r) * row_stride, (uint32_t)(n_valid * 8), &bar[buf]);
+            }
+        } else {
+            for (int e = threadIdx.x; e < TILE * n_valid; e += blockDim.x) {
+                const int r = e / n_valid, k = e - r * n_valid;
+                dst[r * KP + k] = r < nt_steps ? resid[(int64_t)(t0 + r) * row_stride + k] : 0.0;
+            }
         }
         if (MODE == 1)
-            for (int e = threadIdx.x; e < BTK_TILE_STEPS; e += blockDim.x) {
+            for (int e = threadIdx.x; e < TILE; e += blockDim.x) {
                 const bool in = e < nt_steps;
-                sbeta[2 * e] = in ? beta[2 * (t0 + e)] : 0.0;
-                sbeta[2 * e + 1] = in ? beta[2 * (t0 + e) + 1] : 0.0;
-                spri[e] = in ? prior_gradient[t0 + e] : 0.0;
+                sbeta[buf][2 * e] = in ? beta[2 * (t0 + e)] : 0.0;
+                sbeta[buf][2 * e + 1] = in ? beta[2 * (t0 + e) + 1] : 0.0;
+                spri[buf][e] = in ? prior_gradient[t0 + e] : 0.0;
             }
+    };
+    stage(0);
+    for (int it = 0; it < n_tiles; ++it) {
+        const int buf = it & 1, t0 = it * TILE;
+        const int nt_steps = min(TILE, n_steps - t0);
+        if (it + 1 < n_tiles) stage(it + 1);  // the other buffer: every warp left it at the barrier that closed iteration it-1
+        if (use_tma) mbar_wait(&bar[buf], (uint32_t)((it >> 1) & 1));
         __syncthreads();
+        const double* sr = sr_dyn + buf * TILE * KP;
         for (int m0 = 0; m0 < nt_steps; m0 += 8) {
             double acc[NT][2];
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
 #pragma unroll
             for (int ks = 0; ks < KSTEPS; ++ks) {
-                const double a = sr[(m0 + g) * KP + ks * 4 + q];
+                if (!COMPACT || ks < kc) {  // warp-uniform
+                    const double a = sr[(m0 + g) * KP + ul[ks]];
 #pragma unroll
-                for (int nt = 0; nt < NT; ++nt) dmma_m8n8k4(acc[nt][0], acc[nt][1], a, breg[nt][ks]);
+                    for (int nt = 0; nt < NT; ++nt) dmma_m8n8k4(acc[nt][0], acc[nt][1], a, breg[nt][ks]);
+                }
             }
             const int tl = m0 + g;  // this lane's row of D
             if (tl < nt_steps) {
                 double b0 = 0.0, b1 = 0.0, pri = 0.0;
-                if (MODE == 1) { b0 = sbeta[2 * tl]; b1 = sbeta[2 * tl + 1]; pri = spri[tl]; }
+                if (MODE == 1) { b0 = sbeta[buf][2 * tl]; b1 = sbeta[buf][2 * tl + 1]; pri = spri[buf][tl]; }
 #pragma unroll
-                for (int nt = 0; nt < NT; ++nt)
+                for (int nt = 0; nt < NT; ++nt) {
+                    double v[2];
 #pragma unroll
-                    for (int h = 0; h < 2; ++h)
-                        if (eok[nt][h]) {
-                            double v;
-                            if (MODE == 1) {
-                                const double t_hat = (1.0 * b0 + ez[nt][h] * b1) + acc[nt][h];
-                                v = t_hat - (e0[nt][h] * (b0 - 0.0) + e1[nt][h] * (b1 - pri));
-                            } else
-                                v = acc[nt][h] + ez[nt][h];
-                            out[(int64_t)(t0 + tl) * n_cells + cbase + nt * 8 + q * 2 + h] = v;
-                        }
+                    for (int h = 0; h < 2; ++h) {
+                        if (MODE == 1) {
+                            const double t_hat = (1.0 * b0 + ez[nt][h] * b1) + acc[nt][h];
+                            v[h] = t_hat - (e0[nt][h] * (b0 - 0.0) + e1[nt][h] * (b1 - pri));
+                        } else
+                            v[h] = acc[nt][h] + ez[nt][h];
+                    }
+                    double* dst = out + (int64_t)(t0 + tl) * n_cells + cbase + nt * 8 + q * 2;
+                    if (eok[nt][0] && eok[nt][1] && vec_ok) *reinterpret_cast<double2*>(dst) = make_double2(v[0], v[1]);  // the lane's two cells: 16 B
+                    else {
+                        if (eok[nt][0]) dst[0] = v[0];
+                        if (eok[nt][1]) dst[1] = v[1];
+                    }
+                }
             }
         }
+        __syncthreads();  // every warp is done with this buffer before it is refilled
     }
 }
 
@@ -423,6 +490,28 @@ __global__ void idw_build_dense_kernel(int kind, int64_t n_cells, int n_src, con
         } else
             addc[c] = default_gradient * lever;
     }
+}
+
+// Union lists for the station compaction of dense_apply_dmma_kernel<KSTEPS, NT, 0>: one warp per tile of 8*NT cells collects, in
+// station order, the stations with a non-zero weight for any cell of the tile.
+__global__ void idw_union_plan_kernel(int64_t n_cells, int n_src, const double* __restrict__ W /* [n_src][cells] */, int cells_per_tile,
+                                      int k_slots, int32_t* __restrict__ ulist /* [tiles][k_slots] */, uint8_t* __restrict__ ukc) {
+    const int64_t tile = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int64_t n_tiles = (n_cells + cells_per_tile - 1) / cells_per_tile;
+    if (tile >= n_tiles) return;  // whole warps leave together
+    const int64_t cell = tile * cells_per_tile + lane;
+    const bool mine = lane < cells_per_tile && cell < n_cells;
+    int count = 0;
+    for (int s = 0; s < n_src; ++s) {
+        const bool nz = mine && W[(int64_t)s * n_cells + cell] != 0.0;  // NaN (no station in reach) counts as a weight
+        if (__any_sync(0xffffffffu, nz)) {
+            if (lane == 0) ulist[tile * k_slots + count] = s;
+            ++count;
+        }
+    }
+    for (int k = count + lane; k < k_slots; k += 32) ulist[tile * k_slots + k] = k_slots;  // a zero-filled pad column of the staged tile
+    if (lane == 0) ukc[tile] = (uint8_t)((count + 3) / 4);
 }
 
 __global__ void fill_kernel(double* __restrict__ p, int64_t n, double v) {
