@@ -758,6 +758,9 @@ __device__ __forceinline__ void prefetch_l1(const double* p) { asm volatile("pre
 #ifndef SB2_MINBLOCKS_B
 #define SB2_MINBLOCKS_B 12
 #endif
+#ifndef SB2_RESP_SMEM_CONST
+#define SB2_RESP_SMEM_CONST 1
+#endif
 #ifndef SB2_BLOCK_C
 #define SB2_BLOCK_C 32
 #endif
@@ -878,6 +881,43 @@ __global__ void __launch_bounds__(SB2_BLOCK_C, SB2_MINBLOCKS_C) ptgsk_response_k
     const double* __restrict__ s_pot = a.scr[SCR_POT] + (int64_t)ens * a.ens_scr_stride;
     const double* __restrict__ s_outflow = a.scr[SCR_OUTFLOW] + (int64_t)ens * a.ens_scr_stride;
     const double* __restrict__ s_sca = a.scr[SCR_SCA] + (int64_t)ens * a.ens_scr_stride;
+    // Per-cell constants of the step (run_pt_gs_k prologue, pt_gs_k.h:347-357) live in shared memory, one column per thread: each is
+    // read once or twice per step, and twelve doubles less in registers is one more resident warp per scheduler for the ODE solver.
+#if SB2_RESP_SMEM_CONST
+    __shared__ double cst[12][SB2_BLOCK_C];
+#define SB2_CST(k) (((volatile double*)cst[k])[threadIdx.x])
+    {
+        const double area = a.area[cc], gf = a.glacier[cc], lake = a.lake[cc], reservoir = a.reservoir[cc];
+        const double gmd = p.gm_direct_response;
+        const double drf = gf * gmd + reservoir * p.reservoir_direct_response_fraction;
+        cst[0][threadIdx.x] = area;
+        cst[1][threadIdx.x] = gf;
+        cst[2][threadIdx.x] = gmd;
+        cst[3][threadIdx.x] = 1 - gmd;
+        cst[4][threadIdx.x] = 1.0 - lake - reservoir;
+        cst[5][threadIdx.x] = reservoir * (1.0 - p.reservoir_direct_response_fraction) + lake;
+        cst[6][threadIdx.x] = drf;
+        cst[7][threadIdx.x] = 1 - drf;
+        cst[8][threadIdx.x] = area * gf;
+        cst[9][threadIdx.x] = p.ae_scale_factor;
+        cst[10][threadIdx.x] = p.gm_dtf;
+        cst[11][threadIdx.x] = p.p_corr_scale_factor;
+    }
+    __syncwarp();
+#define cell_area_m2 SB2_CST(0)
+#define glacier_fraction SB2_CST(1)
+#define gm_direct SB2_CST(2)
+#define gm_routed SB2_CST(3)
+#define snow_storage_fraction SB2_CST(4)
+#define kirchner_routed_prec SB2_CST(5)
+#define direct_response_fraction SB2_CST(6)
+#define kirchner_fraction SB2_CST(7)
+#define glacier_area_m2 SB2_CST(8)
+#define ae_scale_factor SB2_CST(9)
+#define gm_dtf SB2_CST(10)
+#define p_corr SB2_CST(11)
+    const double c1 = p.c1, c2 = p.c2, c3 = p.c3;
+#else
     const double cell_area_m2 = a.area[cc];
     const double glacier_fraction = a.glacier[cc], lake = a.lake[cc], reservoir = a.reservoir[cc];
     // run_pt_gs_k prologue, pt_gs_k.h:347-357
@@ -889,6 +929,7 @@ __global__ void __launch_bounds__(SB2_BLOCK_C, SB2_MINBLOCKS_C) ptgsk_response_k
     const double kirchner_fraction = 1 - direct_response_fraction;
     const double glacier_area_m2 = cell_area_m2 * glacier_fraction;
     const double c1 = p.c1, c2 = p.c2, c3 = p.c3, ae_scale_factor = p.ae_scale_factor, gm_dtf = p.gm_dtf, p_corr = p.p_corr_scale_factor;
+#endif
     const int64_t n = a.n_cells;
     double kq = state[8 * n + cc];
 
@@ -970,6 +1011,21 @@ __global__ void __launch_bounds__(SB2_BLOCK_C, SB2_MINBLOCKS_C) ptgsk_response_k
         if (failed) atomicOr(a.error_flag, ERR_KIRCHNER_STEP);
     }
 }
+#if SB2_RESP_SMEM_CONST
+#undef cell_area_m2
+#undef glacier_fraction
+#undef gm_direct
+#undef gm_routed
+#undef snow_storage_fraction
+#undef kirchner_routed_prec
+#undef direct_response_fraction
+#undef kirchner_fraction
+#undef glacier_area_m2
+#undef ae_scale_factor
+#undef gm_dtf
+#undef p_corr
+#undef SB2_CST
+#endif
 
 // catchment sums: out[(step) * n_catch + k] = sum of the slots of catchment k, in slot order (fixed -> deterministic)
 __global__ void catchment_reduce_kernel(const double* __restrict__ partial, int64_t n_slots, const int32_t* __restrict__ cat_ptr,
