@@ -31,6 +31,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 BYTES_PER_CELL_STEP = 56  # 5 forcings read + avg_discharge, charge_m3s written
+TRAFFIC_PER_CELL_STEP = 168.0  # ncu dram__bytes_read+write of the three kernels / cell-steps of the captured window (8.60 GB / 51.2 M)
 PTGSK_DEFAULT = [-2.439, 0.966, -0.10, 1.5, -0.5, 2.0, 0.1, 1.0, 5.0, 5.0, 30.0, 0.9, 0.6, 5.0, 0.4, 0.4, 1.0, 0.0, 0.0, 0.2, 1.26, 0.04, 100.0, 0.0,
                  6.0, 1.0, 7.0, 0.0, 221.0, 0.0, 1.0]
 
@@ -156,6 +157,11 @@ def cpu_baseline(args, geo_local, ta, env, target_seconds):
             "sample": f"{n} cells (evenly spread over the shard) x first {T} steps, oracle run_cells with {cores} threads, best of 2 ({el:.2f} s)"}
 
 
+def workload_name(args, n, T):
+    return (f"pt_gs_k {n} cells/GPU x {T} hourly steps ({args.years:g} y), BTK temperature + IDW precipitation/radiation/wind/rel_hum, "
+            f"{args.stations} stations, discharge collector, windows of {args.window} steps")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -175,7 +181,9 @@ def run_reference(args):
         "impl": "reference", "metric": "cell-timesteps/sec (pt_gs_k run_cells)", "value": v, "unit": "cell-timesteps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * args.cells * n_steps / v, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"pt_gs_k {args.cells} cells x {n_steps} hourly steps, BTK temperature + IDW", "note": "ms_per_step extrapolated from the sample"},
+        "config": {"workload": workload_name(args, args.cells, n_steps), "cells_per_gpu": args.cells, "n_steps": n_steps,
+                   "note": "the CPU oracle's run_cells (interpolated forcing resident in host memory) on a bounded sample of the same cells; "
+                           "ms_per_step extrapolated from the sample to the whole workload"},
         "cpu_baseline": {"value": v, "unit": "cell-timesteps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "cell-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
@@ -303,18 +311,26 @@ def main():
             "metric": "cell-timesteps/sec (pt_gs_k run_cells)", "value": value, "unit": "cell-timesteps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"pt_gs_k {n} cells/GPU x {T} hourly steps ({args.years:g} y), BTK temperature + IDW precipitation/radiation/wind/rel_hum, "
-                                   f"{args.stations} stations, discharge collector, windows of {args.window} steps",
+            "config": {"workload": workload_name(args, n, T),
                        "cells_per_gpu": n, "n_steps": T, "window_steps": args.window,
                        "l2": "inputs larger than L2: every window streams %.0f MB of forcing + series per pass" % (n * args.window * 56 / 1e6),
                        "interp_ms_per_step": statistics.mean(interp_ms_acc), "step_kernel_ms_per_step": k_ms},
             "e2e": {"value": cell_steps / float(e2e_s.item()), "unit": "cell-timesteps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "kernel": "ptgsk_run_kernel<1>", "launches_per_step": n_windows, "avg_launch_ms": k_ms / n_windows,
+            # run_cells of one window = the three kernels of the phase pipeline, launched back to back; "achieved" divides the
+            # ALGORITHMIC bytes (56 B per cell-step) by their summed CUDA-event time.  "traffic" is the DRAM
+            # traffic ncu measures for one 512-step window of 100 000 cells (profiles/ncu_pipeline_r01_f_winter_window.txt: 3 x the
+            # algorithmic bytes, because the phases hand five scratch arrays to each other through HBM -- the stack is fp64-bound).
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": TRAFFIC_PER_CELL_STEP * n * min(args.window, T),
+                         "kernel": "run_cells window = ptgsk_forcing_terms_kernel + ptgsk_snow_kernel<0> + ptgsk_response_kernel<1>",
+                         "launches_per_step": n_windows, "avg_launch_ms": k_ms / n_windows,
                          "algorithmic_bytes_per_launch": BYTES_PER_CELL_STEP * n * min(args.window, T), "peak_source": peak_src,
-                         "note": "fp64-compute bound, not HBM bound: see DESIGN.md (H3) and profiles/"},
+                         "binding_roof": {"pipe": "fp64", "pipe_active_pct_ncu": {"forcing_terms": 70.2, "snow": 37.6, "response": 58.7},
+                                          "source": "profiles/ncu_pipeline_r01_f_winter_window.txt (sm__pipe_fp64_cycles_active, winter window)"},
+                         "note": "fp64-compute bound, not HBM bound: 16-25 exp/log, an adaptive ODE step and incomplete gamma functions "
+                                 "per cell-step against 56 bytes (DESIGN.md section 3, SURVEY H3)"},
         }
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(args, geo, ta, env, args.cpu_seconds)

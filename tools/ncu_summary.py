@@ -19,6 +19,8 @@ with open(out, "w") as f:
     f.write(f"# ncu --set full --clock-control none summary of {rep.split('/')[-1]} (one column per captured launch)\n")
     for i, h in enumerate(hdr):
         if any(h == k or h.startswith(k) for k in KEYS) and "peak_sustained_elapsed.per" not in h:
+            if all(r[i] in ("0", "0.000000", "") for r in rows[2:]):
+                continue  # a pipe this kernel does not touch
             f.write(f"{h} [{units[i]}]: " + " | ".join(r[i] for r in rows[2:]) + "\n")
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
     srows = list(csv.reader(io.StringIO(src)))
