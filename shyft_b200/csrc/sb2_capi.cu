@@ -153,6 +153,7 @@ struct sb2_model {
     int64_t n_slots = 0;
     DevArray<double> d_partial;
     DevArray<double> d_scr[5];  // pt_gs_k phase pipeline scratch [partial_steps][n] (sb2_ptgsk.cuh)
+    DevArray<int> d_tickets;    // response kernel time split: [0] ticket counter, [1..] finished slices per cell group
     int partial_steps = 0;
     DevArray<int> d_error_flag;
     // routing (core/routing.h)
@@ -332,6 +333,11 @@ void fill_nan(sb2_model* m, double* p, int64_t count) {
     ++m->launches;
 }
 
+// Time split of the snow / response kernels (sb2_ptgsk.cuh): worth it while a launch of whole-window blocks is only a few waves of
+// the ~2 000 one-warp blocks a B200 holds of these kernels (100 000 cells = 3 125 blocks = 1.2-1.8 waves); with many waves the tail
+// is small and the split only costs (ensembles: 6.8 -> 4.9 G cell-steps/s when split).
+bool use_time_split(int64_t blocks_per_launch) { return blocks_per_launch < 16000; }
+
 // ---- the cell step over [first, first+n_steps) with forcing/series windows already in place -------------------
 void launch_step_range(sb2_model* m, int64_t first, int64_t n_steps, bool collect_end_state) {
     sync_parameters(m);
@@ -375,13 +381,20 @@ void launch_step_range(sb2_model* m, int64_t first, int64_t n_steps, bool collec
             a.ens_scr_stride = 0;
             ptgsk_forcing_terms_kernel<<<dim3((unsigned)grid_for(n, SB2_BLOCK_A), (unsigned)grid_for(chunk, SB2_STEPS_A)), SB2_BLOCK_A, 0, m->stream>>>(a);
             const int gb = grid_for(n, SB2_BLOCK_B), gc = grid_for(n, SB2_BLOCK_C);
+            // snow and response kernels in slices of SB2_UNIT_STEPS steps handed out by ticket (see the kernels); counters zeroed per launch
+            const bool split = use_time_split(gb);
+            const int n_slices = split ? grid_for(chunk, SB2_UNIT_STEPS) : 1;
+            m->d_tickets.ensure(size_t(1 + std::max(gb, gc)));
+            a.unit_steps = split ? SB2_UNIT_STEPS : 0; a.tickets = m->d_tickets.p; a.progress = m->d_tickets.p + 1;
+            CUDA_OK(cudaMemsetAsync(m->d_tickets.p, 0, size_t(1 + gb) * sizeof(int), m->stream));
             switch (m->collect_bits & 14) {
-#define SB2_CASE(B) case B: ptgsk_snow_kernel<B><<<gb, SB2_BLOCK_B, 0, m->stream>>>(a); break;
+#define SB2_CASE(B) case B: ptgsk_snow_kernel<B><<<gb * n_slices, SB2_BLOCK_B, 0, m->stream>>>(a); break;
                 SB2_CASE(0) SB2_CASE(2) SB2_CASE(4) SB2_CASE(6) SB2_CASE(8) SB2_CASE(10) SB2_CASE(12) SB2_CASE(14)
 #undef SB2_CASE
             }
+            CUDA_OK(cudaMemsetAsync(m->d_tickets.p, 0, size_t(1 + gc) * sizeof(int), m->stream));
             switch (m->collect_bits & 13) {
-#define SB2_CASE(B) case B: ptgsk_response_kernel<B><<<gc, SB2_BLOCK_C, 0, m->stream>>>(a); break;
+#define SB2_CASE(B) case B: ptgsk_response_kernel<B><<<gc * n_slices, SB2_BLOCK_C, 0, m->stream>>>(a); break;
                 SB2_CASE(0) SB2_CASE(1) SB2_CASE(4) SB2_CASE(5) SB2_CASE(8) SB2_CASE(9) SB2_CASE(12) SB2_CASE(13)
 #undef SB2_CASE
             }
@@ -857,6 +870,8 @@ void goal_batch_ptgsk(sb2_model* m, int64_t n_sets, const double* P, double* goa
                                                                std::max<int64_t>(8, int64_t((4ULL << 30) / (size_t(E) * n * 40)))));
     DevArray<double> d_state, d_partial, d_cq, d_cc, d_out, d_scr[5];
     for (auto& b : d_scr) b.resize(size_t(E) * ps * n);
+    DevArray<int> d_tickets;  // [E] ticket counters, then [E][cell groups] finished slices (response kernel time split)
+    d_tickets.resize(size_t(E) * (1 + std::max(grid_for(n, SB2_BLOCK_B), grid_for(n, SB2_BLOCK_C))));
     DevArray<PtgskParam> d_par;
     DevArray<GoalTarget> d_gt;
     d_state.resize(size_t(E) * state_sz);
@@ -896,8 +911,16 @@ void goal_batch_ptgsk(sb2_model* m, int64_t n_sets, const double* P, double* goa
             // the same phase pipeline as run_cells, one grid layer per member
             ptgsk_forcing_terms_kernel<<<dim3((unsigned)grid_for(n, SB2_BLOCK_A), (unsigned)grid_for(chunk, SB2_STEPS_A), (unsigned)ne), SB2_BLOCK_A, 0,
                                          m->stream>>>(a);
-            ptgsk_snow_kernel<0><<<dim3((unsigned)grid_for(n, SB2_BLOCK_B), (unsigned)ne), SB2_BLOCK_B, 0, m->stream>>>(a);
-            ptgsk_response_kernel<0><<<dim3((unsigned)grid_for(n, SB2_BLOCK_C), (unsigned)ne), SB2_BLOCK_C, 0, m->stream>>>(a);
+            {
+                const int gb = grid_for(n, SB2_BLOCK_B), gc = grid_for(n, SB2_BLOCK_C);
+                const bool split = use_time_split(int64_t(gb) * ne);
+                const int n_slices = split ? grid_for(chunk, SB2_UNIT_STEPS) : 1;
+                a.unit_steps = split ? SB2_UNIT_STEPS : 0; a.tickets = d_tickets.p; a.progress = d_tickets.p + E;
+                CUDA_OK(cudaMemsetAsync(d_tickets.p, 0, d_tickets.n * sizeof(int), m->stream));
+                ptgsk_snow_kernel<0><<<dim3((unsigned)(gb * n_slices), (unsigned)ne), SB2_BLOCK_B, 0, m->stream>>>(a);
+                CUDA_OK(cudaMemsetAsync(d_tickets.p, 0, d_tickets.n * sizeof(int), m->stream));
+                ptgsk_response_kernel<0><<<dim3((unsigned)(gc * n_slices), (unsigned)ne), SB2_BLOCK_C, 0, m->stream>>>(a);
+            }
             m->launches += 2;
             CUDA_OK(cudaGetLastError());
             const int64_t total = int64_t(chunk) * nc;
@@ -1549,7 +1572,7 @@ int sb2_calculate_goal_function_batch(sb2_model* m, int64_t n_sets, const double
 // ---- diagnostics ---------------------------------------------------------------------------------------------------------------
 int sb2_unit_eval(int device, int fn, int64_t n, const double* in, int n_in, double* out, int n_out) {
     try {
-        static const int need_in[UNIT_N] = {1, 1, 2, 1, 2, 5, 7, 7, 1, 1, 2, 7, 7, 3}, need_out[UNIT_N] = {1, 1, 1, 1, 1, 1, 2, 3, 1, 1, 1, 2, 3, 2};
+        static const int need_in[UNIT_N] = {1, 1, 2, 1, 2, 5, 7, 7, 1, 1, 2, 7, 7, 4}, need_out[UNIT_N] = {1, 1, 1, 1, 1, 1, 2, 3, 1, 1, 1, 2, 3, 2};
         if (fn < 0 || fn >= UNIT_N) throw Error("unknown unit function");
         if (n_in < need_in[fn] || n_out < need_out[fn]) throw Error("unit function: too few input or output columns");
         CUDA_OK(cudaSetDevice(device));

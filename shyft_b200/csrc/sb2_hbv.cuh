@@ -129,7 +129,7 @@ __device__ __forceinline__ bool hbv_snow_step(double (&sp)[HBV_NB], double (&sw)
     else { snow = 0.0; rain = prec; }
     swe += snow + sca * rain;
     if (swe < 0.1) {
-        outflow = total_water / dt_hours;
+        outflow = div_pos(total_water, dt_hours);
 #pragma unroll
         for (int i = 0; i < HBV_NB; ++i) sp[i] = sw[i] = 0.0;
         s_swe = 0.0;
@@ -224,7 +224,7 @@ __device__ __forceinline__ bool hbv_snow_step(double (&sp)[HBV_NB], double (&sw)
         if (total_water - swe < -1.0e-6) ok = false;
         else swe = total_water;
     }
-    outflow = (total_water - swe) / dt_hours;
+    outflow = div_pos(total_water - swe, dt_hours);
     s_swe = swe;
     s_sca = sca;
     return ok;

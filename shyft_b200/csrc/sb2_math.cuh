@@ -239,6 +239,10 @@ SB2_MATH_FN double sb_lgamma(double a) {
 }
 
 
+// num / den for den > 0 where num is often exactly zero (no precipitation, no outflow, ...): +-0 / den = +-0 exactly, and a zero
+// numerator sends CUDA's division through its ~90-instruction general path (ncu: three such calls per step of the snow kernel)
+__device__ __forceinline__ double div_pos(double num, double den) { return num == 0.0 ? num : num / den; }
+
 SB2_HD double dmax(double a, double b) { return (a < b) ? b : a; }  // std::max(a,b): (a < b) ? b : a
 SB2_HD double dmin(double a, double b) { return b < a ? b : a; }  // std::min(a,b): (b < a) ? b : a
 
@@ -289,62 +293,67 @@ __device__ __forceinline__ double gamma_p_with_prefix_inl(double a, double x, do
 }
 __device__ __noinline__ double gamma_p_with_prefix(double a, double x, double pre) { return gamma_p_with_prefix_inl(a, x, pre); }
 
-// Two incomplete gamma values of the same shape at once: P(a, x1) and P(a, x2), each evaluated exactly as by
-// gamma_p_with_prefix_inl (same terms, same tests, same rescaling), but in ONE series loop and ONE continued-fraction loop that
-// advance both problems together.  The terms a+n and their product Q depend on the shape only and are shared; a problem that has
-// converged has its result latched and is carried along idle.  A warp then runs max(n1, n2) passes instead of n1 + n2, with two
-// independent dependency chains per lane.
-__device__ __forceinline__ void gamma_p_pair_inl(double a, double x1, bool need1, double pre1, double x2, bool need2, double pre2, double& P1,
-                                                 double& P2) {
+// Two incomplete gamma values at once: P(a1, x1) and P(a2, x2), each evaluated exactly as by gamma_p_with_prefix_inl (same terms,
+// same tests, same rescaling), but in ONE series loop and ONE continued-fraction loop that advance both problems together: two
+// independent dependency chains per lane and max(n1, n2) instead of n1 + n2 passes.  A problem that has converged has its result
+// latched and is carried along idle.  Used where both values are always needed: calc_q of the Brent search (shapes a+1 and a at
+// the same x, gamma_snow.h:209-212).
+__device__ __forceinline__ void gamma_p_pair_inl(double a1, double x1, bool need1, double pre1, double a2, double x2, bool need2, double pre2,
+                                                 double& P1, double& P2) {
     const double eps = 1.0e-16;
     const double small = 3.0549363634996047e-151;  // 2^-500
-    const bool s1 = need1 && x1 < a + 1.0, s2 = need2 && x2 < a + 1.0;
+    const bool s1 = need1 && x1 < a1 + 1.0, s2 = need2 && x2 < a2 + 1.0;
     const bool c1 = need1 && !s1, c2 = need2 && !s2;
     if (s1 || s2) {
-        double ap = a, Q = a, Pa = 1.0, xa = 1.0, Pb = 1.0, xb = 1.0;
-        double Pa_f = 1.0, Qa_f = a, Pb_f = 1.0, Qb_f = a;
+        double apa = a1, Qa = a1, Pa = 1.0, xa = 1.0;
+        double apb = a2, Qb = a2, Pb = 1.0, xb = 1.0;
+        double Pa_f = 1.0, Qa_f = a1, Pb_f = 1.0, Qb_f = a2;
         bool ra = s1, rb = s2;
         for (int n = 0; n < 500; ++n) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                ap += 1.0;
+                apa += 1.0;
+                apb += 1.0;
                 xa *= x1;
                 xb *= x2;
-                Q *= ap;
-                Pa = fma(Pa, ap, xa);
-                Pb = fma(Pb, ap, xb);
+                Qa *= apa;
+                Qb *= apb;
+                Pa = fma(Pa, apa, xa);
+                Pb = fma(Pb, apb, xb);
             }
-            if (ra) { Pa_f = Pa; Qa_f = Q; ra = !(xa < Pa * eps); }
-            if (rb) { Pb_f = Pb; Qb_f = Q; rb = !(xb < Pb * eps); }
+            if (ra) { Pa_f = Pa; Qa_f = Qa; ra = !(xa < Pa * eps); }
+            if (rb) { Pb_f = Pb; Qb_f = Qb; rb = !(xb < Pb * eps); }
             if (!(ra || rb)) break;
-            if (__double2hiint(Q) > 0x5f300000) { Q *= small; Pa *= small; xa *= small; Pb *= small; xb *= small; }
+            if (__double2hiint(Qa) > 0x5f300000) { Qa *= small; Pa *= small; xa *= small; }
+            if (__double2hiint(Qb) > 0x5f300000) { Qb *= small; Pb *= small; xb *= small; }
         }
         if (s1) P1 = (Pa_f / Qa_f) * pre1;
         if (s2) P2 = (Pb_f / Qb_f) * pre2;
     }
     if (c1 || c2) {
-        double ba = x1 + 1.0 - a, bb = x2 + 1.0 - a, di = 0.0;
+        double ba = x1 + 1.0 - a1, bb = x2 + 1.0 - a2, di = 0.0;
         double A1a = 1.0, B1a = 0.0, Aa = ba, Ba = 1.0;
         double A1b = 1.0, B1b = 0.0, Ab = bb, Bb = 1.0;
         double Aa_f = Aa, Ba_f = Ba, Ab_f = Ab, Bb_f = Bb;
         bool ra = c1, rb = c2;
         for (int i = 0; i < 1000; ++i) {
             di += 1.0;
-            double an = -di * (di - a);
+            double ana = -di * (di - a1), anb = -di * (di - a2);
             ba += 2.0;
             bb += 2.0;
-            A1a = fma(ba, Aa, an * A1a);
-            B1a = fma(ba, Ba, an * B1a);
-            A1b = fma(bb, Ab, an * A1b);
-            B1b = fma(bb, Bb, an * B1b);
+            A1a = fma(ba, Aa, ana * A1a);
+            B1a = fma(ba, Ba, ana * B1a);
+            A1b = fma(bb, Ab, anb * A1b);
+            B1b = fma(bb, Bb, anb * B1b);
             di += 1.0;
-            an = -di * (di - a);
+            ana = -di * (di - a1);
+            anb = -di * (di - a2);
             ba += 2.0;
             bb += 2.0;
-            Aa = fma(ba, A1a, an * Aa);
-            Ba = fma(ba, B1a, an * Ba);
-            Ab = fma(bb, A1b, an * Ab);
-            Bb = fma(bb, B1b, an * Bb);
+            Aa = fma(ba, A1a, ana * Aa);
+            Ba = fma(ba, B1a, ana * Ba);
+            Ab = fma(bb, A1b, anb * Ab);
+            Bb = fma(bb, B1b, anb * Bb);
             if (ra) {
                 const double m1 = Aa * B1a, m0 = A1a * Ba;
                 Aa_f = Aa; Ba_f = Ba;

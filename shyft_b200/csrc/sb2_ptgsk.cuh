@@ -86,6 +86,11 @@ struct PtgskRunArgs {
     // 0 potential evapotranspiration [mm/h], 1 long-wave addend, 2 turbulent addend, 3 snow outflow [mm/h], 4 snow covered area
     double* __restrict__ scr[5];
     int64_t ens_scr_stride;  // elements between two members' scratch arrays
+    // response kernel time split (see ptgsk_response_kernel): steps per work unit (0 = one unit per cell group), ticket counter per
+    // ensemble member, finished units per (member, cell group)
+    int unit_steps;
+    int* __restrict__ tickets;
+    int* __restrict__ progress;
 };
 enum : int { SCR_POT = 0, SCR_LW = 1, SCR_TADD = 2, SCR_OUTFLOW = 3, SCR_SCA = 4 };
 
@@ -136,7 +141,32 @@ __device__ __forceinline__ double gs_calc_q(double a, double b, double z, double
 __device__ __noinline__ double gs_corr_lwc(double z1, double a1, double b1, double a2, double b2) {
     const double Q1 = gs_calc_q(a1, b1, z1, sb_lgamma(a1), sb_lgamma(a1 + 1.0));
     const double lg_a2 = sb_lgamma(a2), lg_a21 = sb_lgamma(a2 + 1.0);
-    auto f = [&](double z) { const double d = gs_calc_q(a2, b2, z, lg_a2, lg_a21) - Q1; return d * d; };
+    // the objective (calc_q(a2, b2, z) - Q1)^2, ~8 evaluations per search and two incomplete gammas each: log(x) is evaluated once for
+    // both prefixes (same argument, same value), the two exp interleave, and P(a2+1, x), P(a2, x) advance together (gamma_p_pair_inl)
+#ifndef SB2_BRENT_VARIANT
+#define SB2_BRENT_VARIANT 0
+#endif
+    auto f = [&](double z) {
+#if SB2_BRENT_VARIANT == 0
+        const double d = gs_calc_q(a2, b2, z, lg_a2, lg_a21) - Q1;
+#else
+        const double x = z / b2;
+        double p1 = 0.0, p0 = 0.0;  // P(a2+1, x), P(a2, x); gamma_p(): 0 unless x > 0, 1 at x = inf
+        if (x == inf_()) p1 = p0 = 1.0;
+        else if (x > 0.0) {
+            const double lx = sb_log_flat(x);
+            const double pre1 = sb_exp_flat((a2 + 1.0) * lx - x - lg_a21), pre0 = sb_exp_flat(a2 * lx - x - lg_a2);
+#if SB2_BRENT_VARIANT == 1
+            p1 = gamma_p_with_prefix(a2 + 1.0, x, pre1);
+            p0 = gamma_p_with_prefix(a2, x, pre0);
+#else
+            gamma_p_pair_inl(a2 + 1.0, x, true, pre1, a2, x, true, pre0, p1, p0);
+#endif
+        }
+        const double d = (a2 * b2 * p1 + z * (1.0 - p0)) - Q1;
+#endif
+        return d * d;
+    };
     const double tolerance = 0.00048828125;  // ldexp(1.0, 1 - 12)
     const double golden = (double)0.3819660f;
     double bmin = 0.0, bmax = z1;
@@ -334,7 +364,7 @@ __device__ __forceinline__ void gs_step_core(GsState& s, GsCache& cache, double&
     double sdc_melt_mean = s.sdc_melt_mean;
     double acc_melt = s.acc_melt;
     double iso_pot_energy = s.iso_pot_energy;
-    const double prec = prec_mm_h * dt_us / 3600000000.0;
+    const double prec = div_pos(prec_mm_h * dt_us, 3600000000.0);
 
     if (doy == p.winter_end_day_of_year) acc_melt = iso_pot_energy = 0.0;  // is_start_melt_season :95-97
 
@@ -369,8 +399,8 @@ __device__ __forceinline__ void gs_step_core(GsState& s, GsCache& cache, double&
     double effect = rad * (1.0 - albedo);
     effect += lw;
 
-    if (T > 0.0 && snow < tol) effect += rain * T * water_heat / dt_seconds;
-    if (T <= 0.0 && rain < tol) effect += snow * T * ice_heat / dt_seconds;
+    if (T > 0.0 && snow < tol) effect += div_pos(rain * T * water_heat, dt_seconds);
+    if (T <= 0.0 && rain < tol) effect += div_pos(snow * T * ice_heat, dt_seconds);
 
     if (p.calculate_iso_pot_energy) {
         const double turb = p.wind_scale * wind_speed + p.wind_const;
@@ -430,7 +460,7 @@ __device__ __forceinline__ void gs_step_core(GsState& s, GsCache& cache, double&
             sdc_scale = sdc_melt_mean / alpha;
         }
     } else {  // :452-470
-        temp_swe += snow / (1.0 - y0);
+        temp_swe += div_pos(snow, 1.0 - y0);  // y0 < 1
         if (temp_swe > 0.0) {
             const double melt = dmin(temp_swe, potential_melt);
             temp_swe -= melt;
@@ -477,7 +507,7 @@ __device__ __forceinline__ void gs_step_core(GsState& s, GsCache& cache, double&
     s.temp_swe = temp_swe;
     r_sca = sca;
     r_storage = storage;
-    r_outflow = outflow * 3600000000.0 / dt_us;
+    r_outflow = div_pos(outflow * 3600000000.0, dt_us);
 }
 
 // ---- priestley_taylor, core/priestley_taylor.h:75-103 -------------------------------------------------
@@ -758,6 +788,9 @@ __device__ __forceinline__ void prefetch_l1(const double* p) { asm volatile("pre
 #ifndef SB2_MINBLOCKS_B
 #define SB2_MINBLOCKS_B 12
 #endif
+#ifndef SB2_UNIT_STEPS
+#define SB2_UNIT_STEPS 64    // steps per work unit of the response kernel (time split)
+#endif
 #ifndef SB2_RESP_SMEM_CONST
 #define SB2_RESP_SMEM_CONST 1
 #endif
@@ -796,10 +829,31 @@ __global__ void __launch_bounds__(SB2_BLOCK_A) ptgsk_forcing_terms_kernel(const 
 // COLLECT bits used here: 2 snow sca/swe, 4 snow_outflow, 8 state series (the eight gamma_snow fields)
 template <int COLLECT>
 __global__ void __launch_bounds__(SB2_BLOCK_B, SB2_MINBLOCKS_B) ptgsk_snow_kernel(const PtgskRunArgs a) {
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= a.n_cells) return;
-    if (a.active != nullptr && a.active[c] == 0) return;
     const int ens = blockIdx.y;
+    // time split by ticket, as in ptgsk_response_kernel (1.76 waves of whole-window blocks otherwise); the memo starts empty in
+    // every slice, which costs one snow-state evaluation per cell and slice
+    int64_t group = blockIdx.x;
+    int i_begin = 0, i_end = a.n_steps, slice = 0;
+    int* progress = nullptr;
+    if (a.unit_steps > 0) {
+        __shared__ int s_ticket;
+        const int n_groups = int((a.n_cells + blockDim.x - 1) / blockDim.x);
+        if (threadIdx.x == 0) s_ticket = atomicAdd(a.tickets + ens, 1);
+        __syncthreads();
+        slice = s_ticket / n_groups;
+        group = s_ticket - slice * n_groups;
+        i_begin = slice * a.unit_steps;
+        i_end = min(a.n_steps, i_begin + a.unit_steps);
+        progress = a.progress + (int64_t)ens * n_groups + group;
+        if (threadIdx.x == 0) {
+            while (*((volatile int*)progress) < slice) __nanosleep(256);
+            __threadfence();
+        }
+        __syncthreads();
+    }
+    const int64_t c = group * blockDim.x + threadIdx.x;
+    const bool live = c < a.n_cells && (a.active == nullptr || a.active[c] != 0);
+    if (live) {
     const PtgskParam& p = (a.ens_params != nullptr && a.pset[c] == 0) ? a.ens_params[ens] : a.params[a.pset[c]];
     const int64_t n = a.n_cells;
     const double* __restrict__ s_lw = a.scr[SCR_LW] + (int64_t)ens * a.ens_scr_stride;
@@ -816,11 +870,12 @@ __global__ void __launch_bounds__(SB2_BLOCK_B, SB2_MINBLOCKS_B) ptgsk_snow_kerne
     gs.temp_swe = state[7 * n + c];
     GsCache cache;
     gs_cache_clear(cache);
-    double f_t = a.f[0][c], f_p = a.f[1][c], f_r = a.f[2][c], f_lw = s_lw[c], f_ta = s_tadd[c];
-    for (int i = 0; i < a.n_steps; ++i) {
+    const int64_t o0 = (int64_t)i_begin * n + c;
+    double f_t = a.f[0][o0], f_p = a.f[1][o0], f_r = a.f[2][o0], f_lw = s_lw[o0], f_ta = s_tadd[o0];
+    for (int i = i_begin; i < i_end; ++i) {
         const double temp = f_t, prec = f_p * p.p_corr_scale_factor, rad = f_r, lw = f_lw, tadd = f_ta;
         const int64_t o = (int64_t)i * n + c;
-        if (i + 1 < a.n_steps) {
+        if (i + 1 < i_end) {
             const int64_t o1 = o + n;
             f_t = a.f[0][o1]; f_p = a.f[1][o1]; f_r = a.f[2][o1]; f_lw = s_lw[o1]; f_ta = s_tadd[o1];
         }
@@ -850,7 +905,7 @@ __global__ void __launch_bounds__(SB2_BLOCK_B, SB2_MINBLOCKS_B) ptgsk_snow_kerne
         if (COLLECT & 2) { a.resp[2][orow] = sca; a.resp[3][orow] = storage * snow_storage_fraction; }
         if (COLLECT & 4) a.resp[4][orow] = mmh_to_m3s(outflow * snow_storage_fraction, cell_area_m2);
     }
-    if ((COLLECT & 8) && a.collect_end_state) {
+    if ((COLLECT & 8) && a.collect_end_state && i_end == a.n_steps) {
         const int64_t orow = (a.first_step + a.n_steps - a.out_first_step) * n + c;
         a.st[1][orow] = gs.albedo;
         a.st[2][orow] = gs.lwc * snow_storage_fraction;
@@ -864,17 +919,48 @@ __global__ void __launch_bounds__(SB2_BLOCK_B, SB2_MINBLOCKS_B) ptgsk_snow_kerne
     state[0 * n + c] = gs.albedo; state[1 * n + c] = gs.lwc; state[2 * n + c] = gs.surface_heat; state[3 * n + c] = gs.alpha;
     state[4 * n + c] = gs.sdc_melt_mean; state[5 * n + c] = gs.acc_melt; state[6 * n + c] = gs.iso_pot_energy;
     state[7 * n + c] = gs.temp_swe;
+    }  // live
+    if (progress != nullptr) {  // publish this slice: the state stores above, then the counter
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) atomicExch(progress, slice + 1);
+    }
 }
 
 // COLLECT bits used here: 1 avg_discharge+charge, 4 glacier_melt/ae/pe, 8 state series (kirchner discharge)
 template <int COLLECT>
 __global__ void __launch_bounds__(SB2_BLOCK_C, SB2_MINBLOCKS_C) ptgsk_response_kernel(const PtgskRunArgs a) {
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int ens = blockIdx.y;
+    // Time split.  A block steps one group of blockDim cells; with ~115 registers 2 500 of the 3 125 one-warp blocks of a 100 000-cell
+    // shard are resident, so a launch of whole-window blocks runs as 1.25 waves -- the second wave leaves three quarters of the
+    // machine idle for as long as the first took.  The window is therefore cut into units of unit_steps steps: blocks take tickets
+    // (unit = ticket: cell group ticket % G, time slice ticket / G), wait until the same group's previous slice has published its
+    // state, step their slice and publish.  Tickets are handed out in start order, so the slice a block waits for always belongs to
+    // a block that is already running or done: no deadlock, and the tail shrinks to one slice.
+    int64_t group = blockIdx.x;
+    int i_begin = 0, i_end = a.n_steps, slice = 0;
+    int* progress = nullptr;
+    if (a.unit_steps > 0) {
+        __shared__ int s_ticket;
+        const int n_groups = int((a.n_cells + blockDim.x - 1) / blockDim.x);
+        if (threadIdx.x == 0) s_ticket = atomicAdd(a.tickets + ens, 1);
+        __syncthreads();
+        slice = s_ticket / n_groups;
+        group = s_ticket - slice * n_groups;
+        i_begin = slice * a.unit_steps;
+        i_end = min(a.n_steps, i_begin + a.unit_steps);
+        progress = a.progress + (int64_t)ens * n_groups + group;
+        if (threadIdx.x == 0) {
+            while (*((volatile int*)progress) < slice) __nanosleep(256);
+            __threadfence();
+        }
+        __syncthreads();
+    }
+    const int64_t c = group * blockDim.x + threadIdx.x;
     const bool in_range = c < a.n_cells;
     const int64_t cc = in_range ? c : a.n_cells - 1;  // out-of-range lanes shadow the last cell, never store
     const bool active = in_range && (a.active == nullptr || a.active[cc] != 0);
     const unsigned lane = threadIdx.x & 31u;
-    const int ens = blockIdx.y;
     const PtgskParam& p = (a.ens_params != nullptr && a.pset[cc] == 0) ? a.ens_params[ens] : a.params[a.pset[cc]];
     double* __restrict__ state = a.state + (int64_t)ens * a.ens_state_stride;
     double* __restrict__ partial = a.partial != nullptr ? a.partial + (int64_t)ens * a.ens_partial_stride : nullptr;
@@ -940,15 +1026,16 @@ __global__ void __launch_bounds__(SB2_BLOCK_C, SB2_MINBLOCKS_C) ptgsk_response_k
         const int prev = __shfl_up_sync(0xffffffffu, my_slot, 1);
         head = in_range && (lane == 0 || prev != my_slot);
     }
-    double f_t = a.f[0][cc], f_p = a.f[1][cc], f_pot = s_pot[cc], f_out = s_outflow[cc], f_sca = s_sca[cc];
+    const int64_t o0 = (int64_t)i_begin * n + cc;
+    double f_t = a.f[0][o0], f_p = a.f[1][o0], f_pot = s_pot[o0], f_out = s_outflow[o0], f_sca = s_sca[o0];
     bool failed = false;
-    for (int i = 0; i < a.n_steps; ++i) {
+    for (int i = i_begin; i < i_end; ++i) {
         const double temp = f_t, prec = f_p * p_corr, pot = f_pot, outflow = f_out, sca = f_sca;
-        if (i + 1 < a.n_steps) {
+        if (i + 1 < i_end) {
             const int64_t o1 = (int64_t)(i + 1) * n + cc;
             f_t = a.f[0][o1]; f_p = a.f[1][o1]; f_pot = s_pot[o1]; f_out = s_outflow[o1]; f_sca = s_sca[o1];
         }
-        if (SB2_PREFETCH_AHEAD > 1 && i + SB2_PREFETCH_AHEAD < a.n_steps) {
+        if (SB2_PREFETCH_AHEAD > 1 && i + SB2_PREFETCH_AHEAD < a.n_steps) {  // may reach into the next slice: same cells, same arrays
             const int64_t o2 = (int64_t)(i + SB2_PREFETCH_AHEAD) * n + cc;
             prefetch_l1(a.f[0] + o2); prefetch_l1(a.f[1] + o2); prefetch_l1(s_pot + o2); prefetch_l1(s_outflow + o2);
             prefetch_l1(s_sca + o2);
@@ -1003,12 +1090,17 @@ __global__ void __launch_bounds__(SB2_BLOCK_C, SB2_MINBLOCKS_C) ptgsk_response_k
         }
     }
     if (active) {
-        if ((COLLECT & 8) && a.collect_end_state) {
+        if ((COLLECT & 8) && a.collect_end_state && i_end == a.n_steps) {
             const int64_t orow = (a.first_step + a.n_steps - a.out_first_step) * n + cc;
             a.st[0][orow] = mmh_to_m3s(kq, cell_area_m2);
         }
         state[8 * n + cc] = kq;
         if (failed) atomicOr(a.error_flag, ERR_KIRCHNER_STEP);
+    }
+    if (progress != nullptr) {  // publish this slice: the state stores above, then the counter
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) atomicExch(progress, slice + 1);
     }
 }
 #if SB2_RESP_SMEM_CONST

@@ -49,11 +49,11 @@ __global__ void unit_eval_kernel(int fn, int64_t n, const double* __restrict__ i
             o[0] = q; o[1] = q_avg; o[2] = ok ? 1.0 : 0.0;
             break;
         }
-        case UNIT_GAMMA_P_PAIR: {  // in: a, x1, x2 -> P(a,x1), P(a,x2) advanced together
-            const double lg = sb_lgamma(a[0]);
-            const double pre1 = sb_exp_flat(a[0] * sb_log_flat(a[1]) - a[1] - lg), pre2 = sb_exp_flat(a[0] * sb_log_flat(a[2]) - a[2] - lg);
+        case UNIT_GAMMA_P_PAIR: {  // in: a1, x1, a2, x2 -> P(a1,x1), P(a2,x2) advanced together
+            const double pre1 = sb_exp_flat(a[0] * sb_log_flat(a[1]) - a[1] - sb_lgamma(a[0]));
+            const double pre2 = sb_exp_flat(a[2] * sb_log_flat(a[3]) - a[3] - sb_lgamma(a[2]));
             double P1 = 0.0, P2 = 0.0;
-            gamma_p_pair_inl(a[0], a[1], a[1] > 0.0, pre1, a[2], a[2] > 0.0, pre2, P1, P2);
+            gamma_p_pair_inl(a[0], a[1], a[1] > 0.0, pre1, a[2], a[3], a[3] > 0.0, pre2, P1, P2);
             o[0] = P1; o[1] = P2;
             break;
         }

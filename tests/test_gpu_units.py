@@ -52,11 +52,12 @@ def test_gamma_p_is_bit_identical_and_accurate(capi, oracle):
     assert _bits_equal(got, oracle.dm_eval("gamma_p", a, x))
     ref = sp.gammainc(a, x)
     assert np.max(np.abs(got - ref) / np.maximum(ref, 1e-300)) < 5e-13
-    # two arguments of one shape advanced together (gamma_p_pair_inl): each equals its own evaluation
-    x2 = rng.uniform(0.0, 1.0, 100000) * (3 * a + 25)
-    pair = capi.unit_eval("gamma_p_pair", np.stack([a, x, x2], axis=1))
+    # two problems advanced together (gamma_p_pair_inl, the Brent objective's calc_q): each equals its own evaluation
+    a2 = a + 1.0
+    x2 = np.where(rng.random(100000) < 0.5, x, rng.uniform(0.0, 1.0, 100000) * (3 * a + 25))
+    pair = capi.unit_eval("gamma_p_pair", np.stack([a, x, a2, x2], axis=1))
     assert _bits_equal(pair[:, 0], got)
-    assert _bits_equal(pair[:, 1], oracle.dm_eval("gamma_p", a, x2))
+    assert _bits_equal(pair[:, 1], oracle.dm_eval("gamma_p", a2, x2))
 
 
 def test_corr_lwc_known_answer_and_bit_identity(capi, oracle):

@@ -5,7 +5,9 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from shyft_b200 import _build
 
-VARIANTS = {"snowfn": ["-DSB2_SNOW_HOT_NOINLINE=1"], "snowfn12": ["-DSB2_SNOW_HOT_NOINLINE=1", "-DSB2_MINBLOCKS_B=12"], "snowfn20": ["-DSB2_SNOW_HOT_NOINLINE=1", "-DSB2_MINBLOCKS_B=20"],
+VARIANTS = {"us32": ["-DSB2_UNIT_STEPS=32"], "us128": ["-DSB2_UNIT_STEPS=128"], "us256": ["-DSB2_UNIT_STEPS=256"], "us100000": ["-DSB2_UNIT_STEPS=100000"],
+            "brent1": ["-DSB2_BRENT_VARIANT=1"], "brent2": ["-DSB2_BRENT_VARIANT=2"],
+            "snowfn": ["-DSB2_SNOW_HOT_NOINLINE=1"], "snowfn12": ["-DSB2_SNOW_HOT_NOINLINE=1", "-DSB2_MINBLOCKS_B=12"], "snowfn20": ["-DSB2_SNOW_HOT_NOINLINE=1", "-DSB2_MINBLOCKS_B=20"],
             "pf0": ["-DSB2_PREFETCH_AHEAD=0"], "pf2": ["-DSB2_PREFETCH_AHEAD=2"], "pf8": ["-DSB2_PREFETCH_AHEAD=8"],
             "pB32x12": ["-DSB2_MINBLOCKS_B=12"], "pB32x20": ["-DSB2_MINBLOCKS_B=20"], "pB64x8": ["-DSB2_BLOCK_B=64", "-DSB2_MINBLOCKS_B=8"],
             "pC64x8": ["-DSB2_BLOCK_C=64", "-DSB2_MINBLOCKS_C=8"], "pC32x20": ["-DSB2_BLOCK_C=32", "-DSB2_MINBLOCKS_C=20"], "pC32x12": ["-DSB2_BLOCK_C=32", "-DSB2_MINBLOCKS_C=12"], "pC64x6": ["-DSB2_BLOCK_C=64", "-DSB2_MINBLOCKS_C=6"], "pC32x24": ["-DSB2_BLOCK_C=32", "-DSB2_MINBLOCKS_C=24"], "pC128x4": ["-DSB2_BLOCK_C=128", "-DSB2_MINBLOCKS_C=4"], "pC32x16": ["-DSB2_BLOCK_C=32", "-DSB2_MINBLOCKS_C=16"],
