@@ -786,7 +786,7 @@ __device__ __forceinline__ void prefetch_l1(const double* p) { asm volatile("pre
 #define SB2_BLOCK_B 32
 #endif
 #ifndef SB2_MINBLOCKS_B
-#define SB2_MINBLOCKS_B 12
+#define SB2_MINBLOCKS_B 16
 #endif
 #ifndef SB2_UNIT_STEPS
 #define SB2_UNIT_STEPS 64    // steps per work unit of the response kernel (time split)

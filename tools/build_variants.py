@@ -5,7 +5,9 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from shyft_b200 import _build
 
-VARIANTS = {"us32": ["-DSB2_UNIT_STEPS=32"], "us128": ["-DSB2_UNIT_STEPS=128"], "us256": ["-DSB2_UNIT_STEPS=256"], "us100000": ["-DSB2_UNIT_STEPS=100000"],
+VARIANTS = {"pB32x18": ["-DSB2_MINBLOCKS_B=18"], "pB32x24": ["-DSB2_MINBLOCKS_B=24"], "pB16C20": ["-DSB2_MINBLOCKS_B=16", "-DSB2_MINBLOCKS_C=20"], "pB16us32": ["-DSB2_MINBLOCKS_B=16", "-DSB2_UNIT_STEPS=32"],
+            "pB32x16": ["-DSB2_MINBLOCKS_B=16"], "pB32x10": ["-DSB2_MINBLOCKS_B=10"], "pB32x8": ["-DSB2_MINBLOCKS_B=8"],
+            "us32": ["-DSB2_UNIT_STEPS=32"], "us128": ["-DSB2_UNIT_STEPS=128"], "us256": ["-DSB2_UNIT_STEPS=256"], "us100000": ["-DSB2_UNIT_STEPS=100000"],
             "brent1": ["-DSB2_BRENT_VARIANT=1"], "brent2": ["-DSB2_BRENT_VARIANT=2"],
             "snowfn": ["-DSB2_SNOW_HOT_NOINLINE=1"], "snowfn12": ["-DSB2_SNOW_HOT_NOINLINE=1", "-DSB2_MINBLOCKS_B=12"], "snowfn20": ["-DSB2_SNOW_HOT_NOINLINE=1", "-DSB2_MINBLOCKS_B=20"],
             "pf0": ["-DSB2_PREFETCH_AHEAD=0"], "pf2": ["-DSB2_PREFETCH_AHEAD=2"], "pf8": ["-DSB2_PREFETCH_AHEAD=8"],
