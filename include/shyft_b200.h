@@ -144,6 +144,25 @@ int sb2_get_state_series(const sb2_model* m, int series, int64_t start_step, int
 int sb2_catchment_discharges(const sb2_model* m, int64_t start_step, int64_t n_steps, double* out);
 int sb2_catchment_charges(const sb2_model* m, int64_t start_step, int64_t n_steps, double* out);
 
+/* ---- statistics readers over the resident series (core/cell_model.h:194-406 as used by api/api.h:178-1600) ------- */
+/* which series: forcing variable (cell.env_ts), response series (cell.rc) or state series (cell.sc, instant values) */
+enum { SB2_STAT_FORCING = 0, SB2_STAT_RESPONSE = 1, SB2_STAT_STATE = 2,
+       SB2_STAT_AE_POT_RATIO = 3 /* series ignored: 1 - exp(-3 q / ae_scale_factor) of the instant Kirchner state, api/api.h:1519-1564 (pt_gs_k) */ };
+/* stat_scope (core/cell_model.h:178-181): indexes are catchment ids or cell indexes; n_indexes == 0 selects every cell */
+enum { SB2_SCOPE_CATCHMENT_IX = 0, SB2_SCOPE_CELL_IX = 1 };
+enum { SB2_STAT_SUM = 0 /* sum_catchment_feature */, SB2_STAT_AREA_AVERAGE = 1 /* average_catchment_feature: r * (1/sum_area) */,
+       SB2_STAT_AREA_AVERAGE_VALUE = 2 /* average_catchment_feature_value: r / sum_area */ };
+/* sum_catchment_feature / average_catchment_feature (:230-268, :313-333): out [n_steps] (state series: points).  Errors as
+ * verify_cids_exist (:197-213): "one or more supplied catchment_indexes does not exist:<cid>" / "Supplied cell index reference ..." */
+int sb2_statistics_series(const sb2_model* m, int kind, int series, const int64_t* indexes, int n_indexes, int scope, int op,
+                          int64_t start_step, int64_t n_steps, double* out);
+/* catchment_feature (:381-402): the selected cells' values at one step, in cell order; *n_out = number written (<= size()) */
+int sb2_statistics_cells(const sb2_model* m, int kind, int series, const int64_t* indexes, int n_indexes, int scope, int64_t step,
+                         double* out, int64_t* n_out);
+/* basic_cell_statistics geo sums (api/api.h:183-288): what = 0 total, 1 forest, 2 glacier, 3 lake, 4 reservoir, 5 unspecified,
+ * 6 snow_storage area [m2], 7 area-weighted elevation [m] */
+int sb2_statistics_geo(const sb2_model* m, int what, const int64_t* indexes, int n_indexes, int scope, double* out);
+
 /* ---- routing (core/routing.h:145-383; region_model.h:909-949) -------------------------------------- */
 /* river_network: rivers [n][6] = id, downstream id (0 = none), downstream distance [m], uhg velocity, alpha, beta (routing.h:98-123).
  * Validates ids and acyclicity like river_network::add / set_downstream_by_id (routing.h:160-250). */

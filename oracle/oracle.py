@@ -397,3 +397,77 @@ def catchment_index(cids):
     m = np.zeros_like(cid)
     n = lib().sho_catchment_index(C.c_int64(cid.size), cid.ctypes.data_as(c_i64p), cix.ctypes.data_as(c_i64p), m.ctypes.data_as(c_i64p))
     return cix, m[:n].copy()
+
+
+# ---- statistics readers: cell_statistics, core/cell_model.h:194-406 (plain restatement, cell after cell) ---------------------
+CATCHMENT_IX, CELL_IX = 0, 1  # stat_scope (:178-181)
+
+
+def _stat_matches(catchment_ids, indexes, scope):
+    """verify_cids_exist (:197-213) + the cells selected by is_match (:215-218), in cell order"""
+    cids = np.asarray(catchment_ids, dtype=np.int64)
+    n = cids.size
+    if n == 0:
+        raise RuntimeError("no cells to make statistics on")
+    if len(indexes) == 0:
+        return list(range(n))
+    if scope == CELL_IX:
+        for cid in indexes:
+            if cid < 0 or cid > n:
+                raise RuntimeError(f"Supplied cell index reference {cid} is ouside valid range 0 ..{n}")
+        return [i for i in range(n) if any(cid == i for cid in indexes)]
+    known = set(cids.tolist())
+    for cid in indexes:
+        if cid not in known:
+            raise RuntimeError(f"one or more supplied catchment_indexes does not exist:{cid}")
+    return [i for i in range(n) if any(cids[i] == cid for cid in indexes)]
+
+
+def sum_catchment_feature(series, catchment_ids, indexes=(), scope=CATCHMENT_IX):
+    """:313-333; series [T][n_cells] -> [T]"""
+    r = np.zeros(series.shape[0])
+    for i in _stat_matches(catchment_ids, indexes, scope):
+        r = r + series[:, i]                     # pts_t::add
+    return r
+
+
+def average_catchment_feature(series, area, catchment_ids, indexes=(), scope=CATCHMENT_IX):
+    """:230-268: r += ts * area per cell, then r *= 1 / sum_area"""
+    r = np.zeros(series.shape[0])
+    sum_area = 0.0
+    for i in _stat_matches(catchment_ids, indexes, scope):
+        r = r + series[:, i] * area[i]           # pts_t::add_scale (time_series.h:399-401)
+        sum_area += area[i]
+    return r * (1 / sum_area) if sum_area != 0.0 else r * np.inf
+
+
+def sum_catchment_feature_value(series, catchment_ids, indexes, j, scope=CATCHMENT_IX):
+    """:347-369"""
+    r = 0.0
+    for i in _stat_matches(catchment_ids, indexes, scope):
+        r += series[j, i]
+    return r
+
+
+def average_catchment_feature_value(series, area, catchment_ids, indexes, j, scope=CATCHMENT_IX):
+    """:282-308: r / sum_area (a division, unlike the series form)"""
+    r, sum_area = 0.0, 0.0
+    for i in _stat_matches(catchment_ids, indexes, scope):
+        r += series[j, i] * area[i]
+        sum_area += area[i]
+    return r / sum_area
+
+
+def catchment_feature(series, catchment_ids, indexes, j, scope=CATCHMENT_IX):
+    """:381-402: the selected cells' values at step j, in cell order"""
+    return np.array([series[j, i] for i in _stat_matches(catchment_ids, indexes, scope)])
+
+
+def ae_pot_ratio(kirchner_discharge_m3s, area, ae_scale_factor):
+    """actual_evapotranspiration_cell_response_statistics::pot_ratio's per-cell series (api/api.h:1527-1541)"""
+    kd = np.asarray(kirchner_discharge_m3s, dtype=np.float64)
+    out = np.empty_like(kd)
+    for c in range(kd.shape[1]):
+        q_mmh = kd[:, c] / ((1 / (3600.0 * 1000.0)) * area[c])                     # m3s_to_mmh, unit_conversion.h:11-15
+        out[:, c] = 1.0 - dm_eval("exp", -q_mmh * 3.0 / ae_scale_factor)           # calc_pot_ratio, actual_evapotranspiration.h:40-43
+    return out

@@ -21,6 +21,7 @@
 #include "sb2_routing.cuh"
 #include "sb2_unit.cuh"
 #include "sb2_goal.cuh"
+#include "sb2_stats.cuh"
 
 using namespace sb2;
 
@@ -939,6 +940,69 @@ void goal_batch_ptgsk(sb2_model* m, int64_t n_sets, const double* P, double* goa
     check_device_errors(m);
 }
 
+// ---- statistics readers (core/cell_model.h:194-406) ------------------------------------------------------------------
+// verify_cids_exist (:197-213) + the per-cell selection of is_match (:215-218): a cell is selected once if any index matches
+std::vector<uint8_t> stat_selection(const sb2_model* m, const int64_t* indexes, int n_indexes, int scope) {
+    if (m->n == 0) throw Error("no cells to make statistics on");
+    std::vector<uint8_t> sel(size_t(m->n), n_indexes == 0 ? 1 : 0);
+    if (n_indexes == 0) return sel;
+    if (!indexes) throw Error("null index list");
+    if (scope == SB2_SCOPE_CELL_IX) {
+        for (int k = 0; k < n_indexes; ++k) {
+            const int64_t cid = indexes[k];
+            if (cid < 0 || cid > m->n)
+                throw Error("Supplied cell index reference " + std::to_string(cid) + " is ouside valid range 0 .." + std::to_string(m->n));
+            if (cid < m->n) sel[size_t(cid)] = 1;
+        }
+    } else if (scope == SB2_SCOPE_CATCHMENT_IX) {
+        std::vector<uint8_t> by_cix(size_t(m->n_catch()), 0);
+        for (int k = 0; k < n_indexes; ++k) {
+            auto f = m->cid_to_cix.find(indexes[k]);
+            if (f == m->cid_to_cix.end()) throw Error("one or more supplied catchment_indexes does not exist:" + std::to_string(indexes[k]));
+            by_cix[size_t(f->second)] = 1;
+        }
+        for (int64_t i = 0; i < m->n; ++i) sel[size_t(i)] = by_cix[size_t(m->cix_of_cell[i])];
+    } else
+        throw Error("unknown statistics scope");
+    return sel;
+}
+// per-cell ae_scale_factor for the pot_ratio statistic (null for every other series)
+const double* stat_ae_scale(sb2_model* m, int kind, DevArray<double>& buf) {
+    if (kind != SB2_STAT_AE_POT_RATIO) return nullptr;
+    sync_parameters(m);
+    buf.resize(size_t(m->n));
+    stat_cell_ae_scale_kernel<<<grid_for(m->n, 256), 256, 0, m->stream>>>(m->n, m->d_pset.p, m->d_ptgsk_params.p, buf.p);
+    CUDA_OK(cudaGetLastError());
+    ++m->launches;
+    return buf.p;
+}
+// the resident rows of a per-cell series: device pointer of row `start`, after checking [start, start+rows) is resident
+const double* stat_series_rows(const sb2_model* m, int kind, int series, int64_t start, int64_t rows) {
+    const double* base = nullptr;
+    int64_t first = 0, have = 0;
+    if (kind == SB2_STAT_AE_POT_RATIO) {
+        if (m->stack != SB2_PT_GS_K) throw Error("pot_ratio statistics are defined for the pt_gs_k stack");
+        kind = SB2_STAT_STATE;
+        series = SB2_S_KIRCHNER_DISCHARGE;
+    }
+    if (kind == SB2_STAT_FORCING) {
+        if (series < 0 || series >= SB2_N_FORCING) throw Error("unknown forcing variable");
+        base = m->d_forcing[series].p; first = m->forcing_first; have = m->forcing_rows;
+    } else if (kind == SB2_STAT_RESPONSE) {
+        if (series < 0 || series >= SB2_N_RESPONSE) throw Error("unknown response series");
+        base = m->d_resp[series].p; first = m->out_first; have = m->out_rows;
+        if (!base) throw Error("response series is not collected in the current collector mode");
+    } else if (kind == SB2_STAT_STATE) {
+        if (series < 0 || series >= SB2_N_STATE_SERIES) throw Error("unknown state series");
+        base = m->d_st[series].p; first = m->out_first; have = m->out_rows + 1;
+        if (!base) throw Error("state series is not collected in the current collector mode");
+    } else
+        throw Error("unknown statistics series kind");
+    if (!base) throw Error("the cell environment is not initialised");
+    if (rows < 0 || start < first || start + rows > first + have) throw Error("requested steps are outside the resident series window");
+    return base + (start - first) * m->n;
+}
+
 }  // namespace
 
 // ====================================================================================================================
@@ -1424,6 +1488,101 @@ int sb2_catchment_charges(const sb2_model* m, int64_t start_step, int64_t n_step
     return m ? catchment_copy(m, m->d_cc, start_step, n_steps, out) : 1;
 }
 
+
+// ---- statistics readers ------------------------------------------------------------------------------------------------
+int sb2_statistics_series(const sb2_model* cm, int kind, int series, const int64_t* indexes, int n_indexes, int scope, int op, int64_t start_step,
+                          int64_t n_steps, double* out) {
+    return guarded_c(cm, [&] {
+        sb2_model* m = const_cast<sb2_model*>(cm);
+        if (op < 0 || op > 2) throw Error("unknown statistics operation");
+        const std::vector<uint8_t> sel = stat_selection(m, indexes, n_indexes, scope);
+        const double* rows = stat_series_rows(m, kind, series, start_step, n_steps);
+        if (n_steps == 0) return;
+        DevArray<uint8_t> d_sel;
+        DevArray<double> d_out, d_scale;
+        d_sel.upload(sel, m->stream);
+        d_out.resize(size_t(n_steps));
+        const double* ae_scale = stat_ae_scale(m, kind, d_scale);
+        const int grid = int(std::min<int64_t>(n_steps, 148 * 8));
+        stat_reduce_rows_kernel<<<grid, 256, 0, m->stream>>>(rows, m->n, n_steps, d_sel.p, op == SB2_STAT_SUM ? nullptr : m->d_area.p, m->d_area.p,
+                                                             ae_scale, d_out.p);
+        CUDA_OK(cudaGetLastError());
+        ++m->launches;
+        CUDA_OK(cudaMemcpyAsync(out, d_out.p, size_t(n_steps) * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+        CUDA_OK(cudaStreamSynchronize(m->stream));
+        if (op != SB2_STAT_SUM) {
+            double sum_area = 0.0;  // in cell order, as the reference accumulates it
+            for (int64_t i = 0; i < m->n; ++i)
+                if (sel[size_t(i)]) sum_area += m->geo[size_t(i)].area;
+            if (op == SB2_STAT_AREA_AVERAGE) {  // pts_t::scale_by(1 / sum_area), cell_model.h:266
+                const double inv = 1 / sum_area;
+                for (int64_t t = 0; t < n_steps; ++t) out[t] *= inv;
+            } else {  // average_catchment_feature_value: r / sum_area, cell_model.h:306
+                for (int64_t t = 0; t < n_steps; ++t) out[t] = out[t] / sum_area;
+            }
+        }
+    });
+}
+int sb2_statistics_cells(const sb2_model* cm, int kind, int series, const int64_t* indexes, int n_indexes, int scope, int64_t step, double* out,
+                         int64_t* n_out) {
+    return guarded_c(cm, [&] {
+        sb2_model* m = const_cast<sb2_model*>(cm);
+        if (m->n == 0) throw Error("no cells to make extract from");
+        const std::vector<uint8_t> sel = stat_selection(m, indexes, n_indexes, scope);
+        const double* row = stat_series_rows(m, kind, series, step, 1);
+        std::vector<int64_t> cells;
+        for (int64_t i = 0; i < m->n; ++i)
+            if (sel[size_t(i)]) cells.push_back(i);
+        if (n_out) *n_out = int64_t(cells.size());
+        if (cells.empty()) return;
+        DevArray<int64_t> d_cells;
+        DevArray<double> d_out, d_scale;
+        d_cells.upload(cells, m->stream);
+        d_out.resize(cells.size());
+        const double* ae_scale = stat_ae_scale(m, kind, d_scale);
+        stat_gather_row_kernel<<<grid_for(int64_t(cells.size()), 256), 256, 0, m->stream>>>(row, d_cells.p, int64_t(cells.size()), m->d_area.p, ae_scale,
+                                                                                          d_out.p);
+        CUDA_OK(cudaGetLastError());
+        ++m->launches;
+        CUDA_OK(cudaMemcpyAsync(out, d_out.p, cells.size() * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+        CUDA_OK(cudaStreamSynchronize(m->stream));
+    });
+}
+// basic_cell_statistics::total_area ... elevation (api/api.h:183-288): host loops in the reference's order (index-major; only
+// total_area honours the scope, the land-type sums and the elevation compare catchment ids whatever the scope says)
+int sb2_statistics_geo(const sb2_model* cm, int what, const int64_t* indexes, int n_indexes, int scope, double* out) {
+    return guarded_c(cm, [&] {
+        const sb2_model* m = cm;
+        if (!out) throw Error("null output");
+        if (what < 0 || what > 7) throw Error("unknown geo statistic");
+        auto term = [&](const sb2_geo_cell& c) {
+            switch (what) {
+                case 0: return c.area;
+                case 1: return c.area * c.forest;
+                case 2: return c.area * c.glacier;
+                case 3: return c.area * c.lake;
+                case 4: return c.area * c.reservoir;
+                case 5: return c.area * (1.0 - c.glacier - c.lake - c.reservoir - c.forest);
+                case 6: return c.area * (1.0 - c.lake - c.reservoir);
+                default: return c.z * c.area;
+            }
+        };
+        double sum = 0.0, area_sum = 0.0;
+        if (n_indexes == 0) {
+            for (const auto& c : m->geo) { sum += term(c); area_sum += c.area; }
+        } else {
+            (void)stat_selection(m, indexes, n_indexes, scope);  // verify_cids_exist
+            for (int k = 0; k < n_indexes; ++k)
+                for (int64_t j = 0; j < m->n; ++j) {
+                    const auto& c = m->geo[size_t(j)];
+                    const bool match = what == 0 ? ((scope == SB2_SCOPE_CELL_IX && indexes[k] == j) || (scope == SB2_SCOPE_CATCHMENT_IX && c.catchment_id == indexes[k]))
+                                                 : (int(c.catchment_id) == indexes[k]);
+                    if (match) { sum += term(c); area_sum += c.area; }
+                }
+        }
+        *out = what == 7 ? sum / area_sum : sum;
+    });
+}
 // ---- routing (core/routing.h:326-383; region_model.h:909-949) ------------------------------------------------------------
 int sb2_set_river_network(sb2_model* m, int64_t n_rivers, const double* rivers) {
     return guarded(m, [&] {

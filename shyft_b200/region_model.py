@@ -69,6 +69,11 @@ class RegionEnvironment:
             setattr(self, name, kw.get(name))
 
 
+def _stats():
+    from . import statistics
+    return statistics
+
+
 class RegionModel:
     stack = PT_GS_K
     default_collect = COLLECT_ALL | COLLECT_STATE  # the "complete response" cell type (pt_gs_k_cell_model.h:210)
@@ -115,6 +120,11 @@ class RegionModel:
         self._bits = bits
 
     # -- sizes / indexing --------------------------------------------------------------------------------------------
+    @property
+    def statistics(self):
+        """basic_cell_statistics over this model's cells (model.statistics.discharge(cids), .temperature(cids), ...; api/api.h:179-420)"""
+        return _stats().BasicCellStatistics(self)
+
     def size(self):
         return int(self._L.sb2_size(self._h))
 
@@ -343,7 +353,13 @@ class RegionModel:
 
 
 class PTGSKModel(RegionModel):
+    """PTGSKModel with the statistics properties of shyft/api/pt_gs_k/__init__.py:14-20"""
     stack = PT_GS_K
+    gamma_snow_state = property(lambda self: _stats().GammaSnowStateStatistics(self))
+    gamma_snow_response = property(lambda self: _stats().GammaSnowResponseStatistics(self))
+    priestley_taylor_response = property(lambda self: _stats().PriestleyTaylorResponseStatistics(self))
+    actual_evaptranspiration_response = property(lambda self: _stats().ActualEvapotranspirationResponseStatistics(self))
+    kirchner_state = property(lambda self: _stats().KirchnerStateStatistics(self))
 
 
 class PTGSKOptModel(RegionModel):  # cell_discharge_response_t: discharge_collector + null state collector
