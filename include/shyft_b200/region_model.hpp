@@ -111,6 +111,28 @@ class region_model {
         ck(sb2_get_response(h_, series, 0, int64_t(time_axis.n), v.data(), SB2_TIME_MAJOR));
         return v;
     }
+    // statistics readers (api/api.h:178-1600 over core/cell_model.h:194-406): kind / series / op / scope are the SB2_STAT_* / SB2_SCOPE_*
+    // constants, e.g. basic_cell_statistics::discharge(cids) = statistics(SB2_STAT_RESPONSE, SB2_R_AVG_DISCHARGE, cids, SB2_STAT_SUM)
+    std::vector<double> statistics(int kind, int series, const std::vector<int64_t>& indexes, int op, int scope = SB2_SCOPE_CATCHMENT_IX) const {
+        std::vector<double> v(time_axis.n + ((kind == SB2_STAT_STATE || kind == SB2_STAT_AE_POT_RATIO) ? 1 : 0));
+        ck(sb2_statistics_series(h_, kind, series, indexes.data(), int(indexes.size()), scope, op, 0, int64_t(v.size()), v.data()));
+        return v;
+    }
+    double statistics_value(int kind, int series, const std::vector<int64_t>& indexes, size_t ith_timestep, int op,
+                            int scope = SB2_SCOPE_CATCHMENT_IX) const {
+        double v = 0.0;
+        ck(sb2_statistics_series(h_, kind, series, indexes.data(), int(indexes.size()), scope, op == SB2_STAT_AREA_AVERAGE ? SB2_STAT_AREA_AVERAGE_VALUE : op,
+                                 int64_t(ith_timestep), 1, &v));
+        return v;
+    }
+    std::vector<double> statistics_cells(int kind, int series, const std::vector<int64_t>& indexes, size_t ith_timestep,
+                                         int scope = SB2_SCOPE_CATCHMENT_IX) const {
+        std::vector<double> v(size());
+        int64_t n = 0;
+        ck(sb2_statistics_cells(h_, kind, series, indexes.data(), int(indexes.size()), scope, int64_t(ith_timestep), v.data(), &n));
+        v.resize(size_t(n));
+        return v;
+    }
     std::vector<double> river_output_flow_m3s(int64_t rid) { std::vector<double> v(time_axis.n); ck(sb2_river_flows(h_, rid, 0, int64_t(time_axis.n), nullptr, nullptr, v.data())); return v; }  // :926-933
     void set_river_network(const std::vector<double>& rivers6) { ck(sb2_set_river_network(h_, int64_t(rivers6.size() / 6), rivers6.data())); }
 
