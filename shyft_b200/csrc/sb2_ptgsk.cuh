@@ -144,7 +144,7 @@ __device__ __noinline__ double gs_corr_lwc(double z1, double a1, double b1, doub
     // the objective (calc_q(a2, b2, z) - Q1)^2, ~8 evaluations per search and two incomplete gammas each: log(x) is evaluated once for
     // both prefixes (same argument, same value), the two exp interleave, and P(a2+1, x), P(a2, x) advance together (gamma_p_pair_inl)
 #ifndef SB2_BRENT_VARIANT
-#define SB2_BRENT_VARIANT 0
+#define SB2_BRENT_VARIANT 1
 #endif
     auto f = [&](double z) {
 #if SB2_BRENT_VARIANT == 0
