@@ -241,7 +241,15 @@ SB2_MATH_FN double sb_lgamma(double a) {
 
 // num / den for den > 0 where num is often exactly zero (no precipitation, no outflow, ...): +-0 / den = +-0 exactly, and a zero
 // numerator sends CUDA's division through its ~90-instruction general path (ncu: three such calls per step of the snow kernel)
-__device__ __forceinline__ double div_pos(double num, double den) { return num == 0.0 ? num : num / den; }
+// (the compiler turns `num == 0 ? num : num / den` back into an unconditional division of num, so the zero lanes divide 1 / den
+// behind an optimisation barrier)
+__device__ __forceinline__ double div_pos(double num, double den) {
+    const bool z = num == 0.0;
+    double n1 = z ? 1.0 : num;
+    asm("" : "+d"(n1));  // opaque to the optimiser, or the select folds away again
+    const double q = n1 / den;
+    return z ? num : q;
+}
 
 SB2_HD double dmax(double a, double b) { return (a < b) ? b : a; }  // std::max(a,b): (a < b) ? b : a
 SB2_HD double dmin(double a, double b) { return b < a ? b : a; }  // std::min(a,b): (b < a) ? b : a
