@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(128) hbv_run_kernel(const HbvRunArgs a) {
             const double sca_m2 = cell_area_m2 * sca;
             gm_melt_m3s = (glacier_area_m2 <= sca_m2 || temp <= 0.0) ? 0.0 : p.gm_dtf * temp * (glacier_area_m2 - sca_m2) * (0.001 / 86400.0);
             pot = pt_potential_evapotranspiration<true>(p.pt_albedo, p.pt_alpha, temp, rad, rel_hum) * 3600.0;
-            gm_mmh = gm_melt_m3s == 0.0 ? 0.0 : m3s_to_mmh(gm_melt_m3s, cell_area_m2);  // +0 / positive = +0
+            gm_mmh = div_pos(gm_melt_m3s, (1 / (3600.0 * 1000.0)) * cell_area_m2);  // m3s_to_mmh; mostly 0 / x (no melt)
             if (HBV_STACK) {
                 const double snow_fraction = dmax(sca, glacier_fraction);
                 ae = (1.0 - snow_fraction) * (x0 < p.lp ? pot * (x0 / p.lp) : pot);  // hbv_actual_evapotranspiration.h:32-38

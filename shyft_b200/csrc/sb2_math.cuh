@@ -304,8 +304,8 @@ __device__ __noinline__ double gamma_p_with_prefix(double a, double x, double pr
 // Two incomplete gamma values at once: P(a1, x1) and P(a2, x2), each evaluated exactly as by gamma_p_with_prefix_inl (same terms,
 // same tests, same rescaling), but in ONE series loop and ONE continued-fraction loop that advance both problems together: two
 // independent dependency chains per lane and max(n1, n2) instead of n1 + n2 passes.  A problem that has converged has its result
-// latched and is carried along idle.  Used where both values are always needed: calc_q of the Brent search (shapes a+1 and a at
-// the same x, gamma_snow.h:209-212).
+// latched and is carried along idle.  Bit-identical to two single evaluations (tests/test_gpu_units.py) but measured SLOWER where it
+// was tried (calc_snow_state: the second value is rarely needed; the Brent objective: -7 %), so no production kernel calls it.
 __device__ __forceinline__ void gamma_p_pair_inl(double a1, double x1, bool need1, double pre1, double a2, double x2, bool need2, double pre2,
                                                  double& P1, double& P2) {
     const double eps = 1.0e-16;
