@@ -1,0 +1,24 @@
+import sys, time, os
+sys.path.insert(0, os.getcwd())
+import numpy as np, torch
+import bench
+import shyft_b200 as sb
+class A: pass
+args = bench.parse.__wrapped__() if hasattr(bench.parse, "__wrapped__") else None
+sys.argv = ["bench.py", "--years", "10"]
+args = bench.parse()
+geo_all, geo, ta, env, st0 = bench.build_workload(args, 0, 1)
+m = sb.PTGSKOptModel(geo, bench.PTGSK_DEFAULT, device=0)
+ip = sb.InterpolationParameter()
+def t(label, fn):
+    torch.cuda.synchronize(); t0 = time.perf_counter(); r = fn(); torch.cuda.synchronize(); print(f"{label:34s} {1000*(time.perf_counter()-t0):9.2f} ms"); return r
+for rep in range(2):
+    print("pass", rep)
+    t("initialize_cell_environment", lambda: m.initialize_cell_environment(ta))
+    t("_set_sources", lambda: m._set_sources(env))
+    t("set initial_state", lambda: setattr(m, "initial_state", st0))
+    t("set_states", lambda: m.set_states(st0))
+    t("run_windowed", lambda: m.run_windowed(ip, window_steps=512))
+    t("catchment_discharges", lambda: m.catchment_discharges())
+    t("get_states", lambda: m.get_states())
+    t("revert+run_windowed (device pass)", lambda: (m.revert_to_initial_state(), m.run_windowed(ip, window_steps=512)))
