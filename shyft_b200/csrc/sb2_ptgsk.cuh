@@ -857,9 +857,11 @@ __global__ void __launch_bounds__(SB2_BLOCK_B, SB2_MINBLOCKS_B) ptgsk_snow_kerne
     const bool iso = p.calculate_iso_pot_energy != 0;
     double* __restrict__ state = a.state + (int64_t)ens * a.ens_state_stride;
     GsState gs;
-    gs.albedo = state[0 * n + c]; gs.lwc = state[1 * n + c]; gs.surface_heat = state[2 * n + c]; gs.alpha = state[3 * n + c];
-    gs.sdc_melt_mean = state[4 * n + c]; gs.acc_melt = state[5 * n + c]; gs.iso_pot_energy = state[6 * n + c];
-    gs.temp_swe = state[7 * n + c];
+    // __ldcg: the state may have been written by the previous time slice on another SM a moment ago -- read it from L2, never from
+    // a line this SM's L1 still holds from an earlier slice
+    gs.albedo = __ldcg(state + 0 * n + c); gs.lwc = __ldcg(state + 1 * n + c); gs.surface_heat = __ldcg(state + 2 * n + c);
+    gs.alpha = __ldcg(state + 3 * n + c); gs.sdc_melt_mean = __ldcg(state + 4 * n + c); gs.acc_melt = __ldcg(state + 5 * n + c);
+    gs.iso_pot_energy = __ldcg(state + 6 * n + c); gs.temp_swe = __ldcg(state + 7 * n + c);
     GsCache cache;
     gs_cache_clear(cache);
     const int64_t o0 = (int64_t)i_begin * n + c;
@@ -1009,7 +1011,7 @@ __global__ void __launch_bounds__(SB2_BLOCK_C, SB2_MINBLOCKS_C) ptgsk_response_k
     const double c1 = p.c1, c2 = p.c2, c3 = p.c3, ae_scale_factor = p.ae_scale_factor, gm_dtf = p.gm_dtf, p_corr = p.p_corr_scale_factor;
 #endif
     const int64_t n = a.n_cells;
-    double kq = state[8 * n + cc];
+    double kq = __ldcg(state + 8 * n + cc);  // L2, not L1: written by the previous time slice, possibly on another SM
 
     int my_slot = -1;
     bool head = false;

@@ -9,6 +9,15 @@ sys.argv = ["bench.py", "--years", "10"]
 args = bench.parse()
 geo_all, geo, ta, env, st0 = bench.build_workload(args, 0, 1)
 m = sb.PTGSKOptModel(geo, bench.PTGSK_DEFAULT, device=0)
+if os.environ.get("PIN", "1") == "1":   # as bench.py's end-to-end leg: host buffers in pinned memory
+    keep = []
+    env_p = sb.RegionEnvironment()
+    for name in sb.capi.FORCING_NAMES:
+        xyz, vals = getattr(env, name)
+        v, tt = bench.pinned_copy(vals); keep.append(tt)
+        setattr(env_p, name, (xyz, v))
+    env = env_p
+    st0, tt = bench.pinned_copy(st0); keep.append(tt)
 ip = sb.InterpolationParameter()
 def t(label, fn):
     torch.cuda.synchronize(); t0 = time.perf_counter(); r = fn(); torch.cuda.synchronize(); print(f"{label:34s} {1000*(time.perf_counter()-t0):9.2f} ms"); return r
