@@ -271,6 +271,36 @@ def test_full_size_properties_config2_slice(sb):
     assert np.array_equal(m.catchment_discharges(), cq) and np.array_equal(m.get_states(), s1)
 
 
+def test_time_sliced_kernels_are_deterministic_and_slicing_invariant(sb):
+    """The snow / response kernels hand a window out in 64-step slices by ticket, each slice waiting for its cell group's previous
+    one (sb2_ptgsk.cuh).  With several waves of blocks (60 000 cells x 10 slices) three runs must agree bit for bit, and so must a
+    run cut into odd chunks (other slice boundaries, other ticket order) and a windowed run."""
+    n, T = 60000, 640
+    geo, ta, env, st0 = _synthetic(sb, n, T, 16, config_index=21, start=1417392000)  # 2014-12-01: snow, melt events, wet-snow snowfall
+    m = sb.PTGSKOptModel(geo)
+    ip = sb.InterpolationParameter()
+    assert m.run_interpolation(ip, ta, env)
+    m.set_states(st0)
+    m.run_cells()
+    q0, c0, s0 = m.catchment_discharges(), m.catchment_charges(), m.get_states()
+    assert np.all(np.isfinite(q0)) and np.all(np.isfinite(s0))
+    for _ in range(2):
+        m.revert_to_initial_state()
+        m.run_cells()
+        assert np.array_equal(m.catchment_discharges(), q0) and np.array_equal(m.catchment_charges(), c0)
+        assert np.array_equal(m.get_states(), s0)
+    m.revert_to_initial_state()
+    done = 0
+    for chunk in (37, 64, 1, 200, 129, 209):
+        m.run_cells(0, done, chunk)
+        done += chunk
+    assert done == T
+    assert np.array_equal(m.catchment_discharges(), q0) and np.array_equal(m.get_states(), s0)
+    m.revert_to_initial_state()
+    m.run_windowed(ip, window_steps=150)
+    assert np.array_equal(m.catchment_discharges(), q0) and np.array_equal(m.get_states(), s0)
+
+
 def test_cpp_host_shim_selftest():
     """include/shyft_b200/region_model.hpp (the C++ mirror of region_model<cell_t>) over the C ABI, reference literals."""
     import subprocess
