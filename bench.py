@@ -240,14 +240,22 @@ def main():
         m.run_windowed(ip, window_steps=args.window)
         reduce_catchments()
 
+    e2e_parts = {}
+
     def e2e_pass():
-        m.initialize_cell_environment(ta)
-        m._set_sources(env_pinned)
+        t = [time.perf_counter()]
+
+        def lap(name):
+            t.append(time.perf_counter())
+            e2e_parts.setdefault(name, []).append(1000.0 * (t[-1] - t[-2]))
+        m.initialize_cell_environment(ta); lap("initialize_cell_environment")
+        m._set_sources(env_pinned); lap("set_sources_h2d")
         m.initial_state = st_pinned
-        m.set_states(st_pinned)
-        m.run_windowed(ip, window_steps=args.window)
-        reduce_catchments()
-        return m.catchment_discharges(), m.get_states()
+        m.set_states(st_pinned); lap("set_states_h2d")
+        m.run_windowed(ip, window_steps=args.window); lap("run_windowed")
+        reduce_catchments(); lap("all_reduce")
+        out = m.catchment_discharges(), m.get_states(); lap("results_d2h")
+        return out
 
     def timed(fn, k):
         barrier()
@@ -315,7 +323,8 @@ def main():
                        "cells_per_gpu": n, "n_steps": T, "window_steps": args.window,
                        "l2": "inputs larger than L2: every window streams %.0f MB of forcing + series per pass" % (n * args.window * 56 / 1e6),
                        "interp_ms_per_step": statistics.mean(interp_ms_acc), "step_kernel_ms_per_step": k_ms},
-            "e2e": {"value": cell_steps / float(e2e_s.item()), "unit": "cell-timesteps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "e2e": {"value": cell_steps / float(e2e_s.item()), "unit": "cell-timesteps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "rank0_ms": {k: round(statistics.mean(v[1:]), 2) for k, v in e2e_parts.items()}},
             "gpu_launches": int(launches),
             "clocks": clocks,
             # run_cells of one window = the three kernels of the phase pipeline, launched back to back; "achieved" divides the

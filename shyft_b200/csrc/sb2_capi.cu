@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <memory>
 #include <string>
 #include <vector>
@@ -40,6 +41,48 @@ struct Error : std::runtime_error { using std::runtime_error::runtime_error; };
 
 thread_local std::string g_create_error;
 
+// Freed device buffers of >= 1 MB are parked (per device, by size, up to 12 GB) and handed back to the next allocation of the same
+// size: re-initialising a model's environment drops and re-creates GB-sized windows, and cudaFree / cudaMalloc of those cost
+// ~150 ms per run_interpolation + run_cells cycle (bench.py e2e leg).  A failed cudaMalloc empties the pool and retries.
+struct DevicePool {
+    std::mutex mu;
+    std::map<std::pair<int, size_t>, std::vector<void*>> parked;
+    size_t parked_bytes = 0;
+    static DevicePool& get() { static DevicePool p; return p; }
+    void* take(size_t bytes) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        std::lock_guard<std::mutex> g(mu);
+        auto f = parked.find({dev, bytes});
+        if (f == parked.end() || f->second.empty()) return nullptr;
+        void* p = f->second.back();
+        f->second.pop_back();
+        parked_bytes -= bytes;
+        return p;
+    }
+    bool park(void* p, size_t bytes) {
+        if (bytes < (1u << 20)) return false;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceSynchronize();  // what cudaFree would do: nothing in flight may still touch the buffer when another stream takes it
+        std::lock_guard<std::mutex> g(mu);
+        if (parked_bytes + bytes > (12ULL << 30)) return false;
+        parked[{dev, bytes}].push_back(p);
+        parked_bytes += bytes;
+        return true;
+    }
+    void flush() {  // current device only
+        int dev = 0;
+        cudaGetDevice(&dev);
+        std::lock_guard<std::mutex> g(mu);
+        for (auto& kv : parked)
+            if (kv.first.first == dev) {
+                for (void* p : kv.second) { cudaFree(p); parked_bytes -= kv.first.second; }
+                kv.second.clear();
+            }
+    }
+};
+
 template <class T>
 struct DevArray {  // library-owned device buffer
     T* p = nullptr;
@@ -48,15 +91,27 @@ struct DevArray {  // library-owned device buffer
     DevArray(const DevArray&) = delete;
     DevArray& operator=(const DevArray&) = delete;
     ~DevArray() { release(); }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void release() {
+        if (p && !DevicePool::get().park(p, n * sizeof(T))) cudaFree(p);
+        p = nullptr; n = 0;
+    }
     void resize(size_t count) {
         if (count == n) return;
         release();
         if (count) {
-            cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
-            if (e != cudaSuccess) {
-                cudaGetLastError();
-                throw Error("device allocation of " + std::to_string(count * sizeof(T)) + " bytes failed: " + cudaGetErrorString(e));
+            p = static_cast<T*>(DevicePool::get().take(count * sizeof(T)));
+            if (!p) {
+                cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+                if (e != cudaSuccess) {  // give the parked buffers back to the driver and try once more
+                    cudaGetLastError();
+                    DevicePool::get().flush();
+                    e = cudaMalloc((void**)&p, count * sizeof(T));
+                }
+                if (e != cudaSuccess) {
+                    cudaGetLastError();
+                    p = nullptr;
+                    throw Error("device allocation of " + std::to_string(count * sizeof(T)) + " bytes failed: " + cudaGetErrorString(e));
+                }
             }
         }
         n = count;
