@@ -122,6 +122,16 @@ int sb2_get_cell_forcing(const sb2_model* m, int var, int64_t start_step, int64_
 /* region_environment sources (api/api.h:137-168): n_src geo-located series already on the model axis, values [t][src];
  * the identity resampling of average_accessor (core/time_series.h:2033-2072) is applied on upload */
 int sb2_set_sources(sb2_model* m, int var, int64_t n_src, const double* xyz /* [src][3] */, const double* values /* [T][src] */);
+/* The same for sources on their OWN point axis (any resolution; region_environment series are projected onto the model axis by
+ * average_accessor<ts, timeaxis>, core/region_model.h:426-438 over core/time_series.h:202-310, 2033-2072): t_us [n_points] strictly
+ * increasing point times shared by the n_src series, t_end_us = the series' total_period().end, values [n_points][n_src],
+ * point_interpretation = the series' ts_point_fx.  The projection (true average per model step, NaN-aware, NaN from t_end on) runs
+ * on the device. */
+enum { SB2_POINT_AVERAGE_VALUE = 0 /* stair-case */, SB2_POINT_INSTANT_VALUE = 1 /* linear between points */ };
+int sb2_set_sources_on_axis(sb2_model* m, int var, int64_t n_src, const double* xyz, int64_t n_points, const int64_t* t_us, int64_t t_end_us,
+                            const double* values, int point_interpretation);
+/* the sources of a variable as projected onto the model axis: out [T][n_src] */
+int sb2_get_sources_on_model_axis(const sb2_model* m, int var, double* out);
 /* interpolate(ip, env, best_effort) (:397-527) over the whole axis; returns 0 also when best_effort swallowed a
  * per-variable failure, in which case *all_ok (nullable) is 0 and that variable stays NaN */
 int sb2_interpolate(sb2_model* m, const sb2_interpolation_parameter* ip, int best_effort, int* all_ok);

@@ -94,6 +94,12 @@ class region_model {
         ip_parameter = ip;
         return ok != 0;
     }
+    // a variable's series on their own point axis (any resolution), projected onto the model axis on the device (:426-438)
+    void set_sources_on_axis(int var, const std::vector<double>& xyz, const std::vector<int64_t>& t_us, int64_t t_end_us,
+                             const std::vector<double>& values /* [points][sources] */, int point_interpretation) {
+        ck(sb2_set_sources_on_axis(h_, var, int64_t(xyz.size() / 3), xyz.data(), int64_t(t_us.size()), t_us.data(), t_end_us, values.data(),
+                                   point_interpretation));
+    }
     bool run_interpolation(const interpolation_parameter& ip, const fixed_dt& ta, const region_environment& env, bool best_effort = true) {         // :546-549
         initialize_cell_environment(ta);
         return interpolate(ip, env, best_effort);

@@ -11,6 +11,7 @@
 #include "sho_hbv.hpp"
 #include "sho_pt_gs_k.hpp"
 #include "sho_region.hpp"
+#include "sho_ts.hpp"
 
 using namespace sho;
 
@@ -290,6 +291,22 @@ int sho_btk_covariance(int64_t n_src, const double* src_xyz, int64_t n_dst, cons
     SHO_END
 }
 double sho_btk_prior_gradient(int64_t t_us, int64_t dt_us) { return btk::parameter().temperature_gradient(t_us, dt_us); }
+// average_value with the caller's hint (replays test/time_series_test.cpp); returns the value, updates *ix
+double sho_average_value(const int64_t* t, const double* v, int64_t n, int64_t p_start, int64_t p_end, int64_t* ix, int linear) {
+    ts::point_source src{t, v, size_t(n), 1, n ? t[n - 1] : 0};
+    size_t last = *ix < 0 ? ts::npos : size_t(*ix);
+    const double r = ts::average_value(src, p_start, p_end, last, linear != 0);
+    *ix = last == ts::npos ? -1 : int64_t(last);
+    return r;
+}
+// average_accessor of n_src sources sharing one point axis: values [n_points][n_src] -> out [ta_n][n_src]
+void sho_average_accessor(const int64_t* t, const double* values, int64_t n_points, int64_t n_src, int64_t t_end, int linear, int64_t ta_t0,
+                          int64_t ta_dt, int64_t ta_n, double* out) {
+    for (int64_t s = 0; s < n_src; ++s) {
+        ts::point_source src{t, values + s, size_t(n_points), size_t(n_src), t_end};
+        ts::average_accessor(src, linear != 0, ta_t0, ta_dt, size_t(ta_n), out + s, size_t(n_src));
+    }
+}
 void sho_average_accessor_same_axis(double* v, int64_t n, int64_t dt_us) { for (int64_t i = 0; i < n; ++i) v[i] = average_accessor_same_axis(v[i], dt_us); }
 
 // ---- routing ----------------------------------------------------------------

@@ -36,7 +36,7 @@ def geo_matrix(geo_records):
 
 def build(force=False):
     so = os.path.join(_HERE, "libsho_oracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("capi.cpp", "sho_detmath.hpp", "sho_core.hpp", "sho_pt_gs_k.hpp", "sho_hbv.hpp", "sho_region.hpp")]
+    srcs = [os.path.join(_HERE, f) for f in ("capi.cpp", "sho_detmath.hpp", "sho_core.hpp", "sho_pt_gs_k.hpp", "sho_hbv.hpp", "sho_region.hpp", "sho_ts.hpp")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "libsho_oracle.so"], stdout=subprocess.DEVNULL)
     return so
@@ -52,7 +52,8 @@ def lib():
             getattr(L, name).restype = C.c_int64
         for name in ("sho_gamma_p", "sho_gamma_quantile", "sho_pt_potential_evapotranspiration", "sho_ae_calculate_step",
                      "sho_glacier_melt_step", "sho_gs_corr_lwc", "sho_gs_calc_q", "sho_hbv_soil_step", "sho_hbv_tank_step",
-                     "sho_hbv_ae_step", "sho_btk_prior_gradient", "sho_nash_sutcliffe", "sho_rmse", "sho_kling_gupta", "sho_abs_diff_sum"):
+                     "sho_hbv_ae_step", "sho_btk_prior_gradient", "sho_nash_sutcliffe", "sho_rmse", "sho_kling_gupta", "sho_abs_diff_sum",
+                     "sho_average_value"):
             getattr(L, name).restype = C.c_double
     return _LIB
 
@@ -470,4 +471,25 @@ def ae_pot_ratio(kirchner_discharge_m3s, area, ae_scale_factor):
     for c in range(kd.shape[1]):
         q_mmh = kd[:, c] / ((1 / (3600.0 * 1000.0)) * area[c])                     # m3s_to_mmh, unit_conversion.h:11-15
         out[:, c] = 1.0 - dm_eval("exp", -q_mmh * 3.0 / ae_scale_factor)           # calc_pot_ratio, actual_evapotranspiration.h:40-43
+    return out
+
+
+# ---- projection of point sources onto a time axis: core/time_series.h:144-310, 2033-2072 (oracle/sho_ts.hpp) -----------------
+def average_value(t_us, v, p_start_us, p_end_us, ix=-1, linear=False):
+    """average_value(source, period, last_idx, linear) -> (value, last_idx); ix = -1 is "no hint" (npos)"""
+    t = np.ascontiguousarray(t_us, dtype=np.int64)
+    vv = _f64(v)
+    hint = C.c_int64(ix)
+    r = lib().sho_average_value(t.ctypes.data_as(c_i64p), _d(vv), C.c_int64(t.size), C.c_int64(p_start_us), C.c_int64(p_end_us), C.byref(hint),
+                                C.c_int(1 if linear else 0))
+    return r, hint.value
+
+
+def average_accessor(t_us, values, t_end_us, linear, ta_t0_us, ta_dt_us, ta_n):
+    """average_accessor<point_ts, fixed_dt>::value(i), i = 0..ta_n-1, for sources sharing one point axis: values [n_points][n_src]"""
+    t = np.ascontiguousarray(t_us, dtype=np.int64)
+    vv = _f64(values).reshape(t.size, -1)
+    out = np.zeros((ta_n, vv.shape[1]))
+    lib().sho_average_accessor(t.ctypes.data_as(c_i64p), _d(vv), C.c_int64(t.size), C.c_int64(vv.shape[1]), C.c_int64(t_end_us), C.c_int(1 if linear else 0),
+                               C.c_int64(ta_t0_us), C.c_int64(ta_dt_us), C.c_int64(ta_n), _d(out))
     return out

@@ -6,6 +6,6 @@ Python mirror of the reference's region-model surface (`region_model`), the cali
 """
 from .capi import (COLLECT_ALL, COLLECT_DISCHARGE, COLLECT_NONE, COLLECT_SNOW, COLLECT_STATE, HBV_STACK, PT_GS_K, PT_HS_K,  # noqa: F401
                    InterpolationParameter)
-from .region_model import (HbvStackModel, HbvStackOptModel, PTGSKModel, PTGSKOptModel, PTHSKModel, PTHSKOptModel, RegionEnvironment,  # noqa: F401
-                           RegionModel, TimeAxis, geo_cell_data_vector)
+from .region_model import (GeoPointSources, HbvStackModel, HbvStackOptModel, PTGSKModel, PTGSKOptModel, PTHSKModel, PTHSKOptModel,  # noqa: F401
+                           RegionEnvironment, RegionModel, TimeAxis, geo_cell_data_vector)
 from .calibration import Optimizer, TargetSpecification  # noqa: F401,E402

@@ -1363,17 +1363,24 @@ int sb2_get_cell_forcing(const sb2_model* cm, int var, int64_t start_step, int64
     });
 }
 
+// common part of sb2_set_sources / sb2_set_sources_on_axis: returns the Source with its geometry installed, plans invalidated
+static Source* begin_sources(sb2_model* m, int var, int64_t n_src, const double* xyz) {
+    if (var < 0 || var >= SB2_N_FORCING) throw Error("unknown forcing variable");
+    if (!(m->T > 0)) throw Error("initialize_cell_environment has not been called");
+    Source& s = m->src[var];
+    s.n_src = n_src;
+    m->idw[var].valid = false;
+    if (var == SB2_TEMPERATURE) m->btk_cache.clear();
+    if (n_src == 0) { s.xyz.clear(); s.h_values.clear(); s.d_xyz.release(); s.d_values.release(); return nullptr; }
+    s.xyz.assign(xyz, xyz + 3 * n_src);
+    s.d_xyz.upload(s.xyz, m->stream);
+    return &s;
+}
 int sb2_set_sources(sb2_model* m, int var, int64_t n_src, const double* xyz, const double* values) {
     return guarded(m, [&] {
-        if (var < 0 || var >= SB2_N_FORCING) throw Error("unknown forcing variable");
-        if (!(m->T > 0)) throw Error("initialize_cell_environment has not been called");
-        Source& s = m->src[var];
-        s.n_src = n_src;
-        m->idw[var].valid = false;
-        if (var == SB2_TEMPERATURE) m->btk_cache.clear();
-        if (n_src == 0) { s.xyz.clear(); s.h_values.clear(); s.d_xyz.release(); s.d_values.release(); return; }
-        s.xyz.assign(xyz, xyz + 3 * n_src);
-        s.d_xyz.upload(s.xyz, m->stream);
+        Source* sp = begin_sources(m, var, n_src, xyz);
+        if (!sp) return;
+        Source& s = *sp;
         const size_t count = size_t(m->T) * n_src;
         s.d_values.upload(values, count, m->stream);
         // average_accessor of a stair-case source on the model axis (time_series.h:202-310,2033-2072)
@@ -1384,6 +1391,48 @@ int sb2_set_sources(sb2_model* m, int var, int64_t n_src, const double* xyz, con
         s.has_nonfinite = false;
         for (size_t i = 0; i < count && !s.has_nonfinite; ++i) s.has_nonfinite = !std::isfinite(values[i]);
         if (var == SB2_TEMPERATURE) s.h_values.assign(values, values + count);
+        CUDA_OK(cudaStreamSynchronize(m->stream));
+    });
+}
+int sb2_set_sources_on_axis(sb2_model* m, int var, int64_t n_src, const double* xyz, int64_t n_points, const int64_t* t_us, int64_t t_end_us,
+                            const double* values, int point_interpretation) {
+    return guarded(m, [&] {
+        if (n_src > 0 && n_points > 0) {
+            if (!t_us || !values) throw Error("set_sources_on_axis: null time or value array");
+            for (int64_t i = 1; i < n_points; ++i)
+                if (!(t_us[i] > t_us[i - 1])) throw Error("set_sources_on_axis: point times must be strictly increasing");
+            if (t_end_us < t_us[n_points - 1]) throw Error("set_sources_on_axis: the total period ends before the last point");
+        }
+        Source* sp = begin_sources(m, var, n_src, xyz);
+        if (!sp) return;
+        Source& s = *sp;
+        const size_t count = size_t(m->T) * n_src;
+        DevArray<int64_t> d_t;
+        DevArray<double> d_pts;
+        d_t.upload(t_us, size_t(n_points), m->stream);
+        d_pts.upload(values, size_t(n_points) * n_src, m->stream);
+        s.d_values.resize(count);
+        average_accessor_kernel<<<grid_for(int64_t(count), 256), 256, 0, m->stream>>>(d_t.p, d_pts.p, n_points, n_src, t_end_us,
+                                                                                     point_interpretation == SB2_POINT_INSTANT_VALUE ? 1 : 0, m->t0, m->dt,
+                                                                                     m->T, s.d_values.p);
+        CUDA_OK(cudaGetLastError());
+        ++m->launches;
+        // the projected series back on the host: NaN bookkeeping of interpolate(), BTK validity sets
+        std::vector<double> h(count);
+        CUDA_OK(cudaMemcpyAsync(h.data(), s.d_values.p, count * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+        CUDA_OK(cudaStreamSynchronize(m->stream));
+        s.has_nonfinite = false;
+        for (size_t i = 0; i < count && !s.has_nonfinite; ++i) s.has_nonfinite = !std::isfinite(h[i]);
+        if (var == SB2_TEMPERATURE) s.h_values = std::move(h);
+    });
+}
+int sb2_get_sources_on_model_axis(const sb2_model* cm, int var, double* out) {
+    return guarded_c(cm, [&] {
+        sb2_model* m = const_cast<sb2_model*>(cm);
+        if (var < 0 || var >= SB2_N_FORCING) throw Error("unknown forcing variable");
+        const Source& s = m->src[var];
+        if (s.n_src == 0 || !s.d_values.p) throw Error("no sources set for this variable");
+        CUDA_OK(cudaMemcpyAsync(out, s.d_values.p, size_t(m->T) * s.n_src * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
         CUDA_OK(cudaStreamSynchronize(m->stream));
     });
 }

@@ -524,6 +524,85 @@ __global__ void average_accessor_same_axis_kernel(double* __restrict__ p, int64_
         p[i] = isfinite(v) ? (dt_seconds * v) / dt_seconds : nan("");
     }
 }
+// average_accessor<point_ts, fixed_dt>::value(i) for sources on their own point axis (core/time_series.h:2033-2072 over
+// accumulate_value :202-291): the true average of the source over every model step -- stair-case (POINT_AVERAGE_VALUE) or linear
+// between points (POINT_INSTANT_VALUE, strict: nothing after the last point), NaN stretches left out of both area and time,
+// NaN at and after the source's total period end (extension policy USE_NAN).  One thread per (model step, source); the left anchor
+// is what the reference's hinted search yields under sequential access: the last point at or before the step start, or point 0
+// when the source starts later (hint_based_search :165-166 returns 0, not npos, from hint 0).  Same operations in the same order
+// as the reference (to_seconds = us / 1e6, a = dv / dt, b = r.v - a * t_r on epoch seconds): bit-identical to the oracle.
+__device__ __forceinline__ double us_to_seconds(int64_t us) { return double(us) / 1000000.0; }
+__global__ void average_accessor_kernel(const int64_t* __restrict__ t /* [n_points] */, const double* __restrict__ values /* [n_points][n_src] */,
+                                        int64_t n_points, int64_t n_src, int64_t t_end, int linear, int64_t ta_t0, int64_t ta_dt, int64_t ta_n,
+                                        double* __restrict__ out /* [ta_n][n_src] */) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= ta_n * n_src) return;
+    const int64_t step = idx / n_src, s = idx - step * n_src;
+    const int64_t p_start = ta_t0 + step * ta_dt, p_end = p_start + ta_dt;
+    const double nan_v = nan_();
+    double result = nan_v;
+    if (n_points > 0 && p_start < t_end) {
+        int64_t i = 0;
+        if (!(p_start < t[0])) {  // index_of(p_start): last point with t <= p_start
+            int64_t lo = 0, hi = n_points;  // t[lo] <= p_start < t[hi]
+            while (hi - lo > 1) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (t[mid] <= p_start) lo = mid; else hi = mid;
+            }
+            i = lo;
+        }
+        const bool extrapolate_flat = !linear;  // strict_linear_between = true
+        int64_t l_t = 0, tsum = 0;
+        double l_v = 0.0, area = 0.0;
+        bool l_finite = false;
+        while (true) {
+            if (!l_finite) {
+                l_t = t[i]; l_v = values[i * n_src + s]; ++i;
+                l_finite = isfinite(l_v);
+                if (i == n_points) {
+                    if (l_finite && l_t < p_end && extrapolate_flat) {
+                        const int64_t dt = p_end - (p_start > l_t ? p_start : l_t);
+                        tsum += dt;
+                        area += us_to_seconds(dt) * l_v;
+                    }
+                    break;
+                }
+                if (l_t >= p_end) break;
+            } else {
+                const int64_t r_t = t[i];
+                const double r_v = values[i * n_src + s];
+                ++i;
+                const bool r_finite = isfinite(r_v);
+                const int64_t px_start = l_t > p_start ? l_t : p_start, px_end = r_t < p_end ? r_t : p_end;
+                int64_t dt = px_end - px_start;
+                if (linear && r_finite) {
+                    const double a = (r_v - l_v) / us_to_seconds(r_t - l_t);
+                    const double b = r_v - a * us_to_seconds(r_t);
+                    area += us_to_seconds(dt) * (0.5 * a * us_to_seconds(px_start + px_end) + b);
+                    tsum += dt;
+                } else if (extrapolate_flat) {
+                    area += l_v * us_to_seconds(dt);
+                    tsum += dt;
+                }
+                if (i == n_points) {
+                    if (r_finite && r_t < p_end && extrapolate_flat) {
+                        dt = p_end - r_t;
+                        tsum += dt;
+                        area += us_to_seconds(dt) * r_v;
+                    }
+                    break;
+                }
+                if (r_t >= p_end) break;
+                l_finite = r_finite;
+                l_t = r_t;
+                l_v = r_v;
+            }
+        }
+        result = tsum > 0 ? area / us_to_seconds(tsum) : nan_v;
+    }
+    out[idx] = result;
+}
+
 // [rows][cols] -> [cols][rows] tiled transpose (cell-major <-> time-major at the ABI)
 __global__ void transpose_kernel(const double* __restrict__ in, double* __restrict__ out, int64_t rows, int64_t cols) {
     __shared__ double tile[32][33];

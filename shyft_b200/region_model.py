@@ -58,10 +58,28 @@ class TimeAxis:
         return self.start + i * self.delta_t
 
 
-class RegionEnvironment:
-    """a_region_environment (api/api.h:137-168): per variable a set of geo-located series already on the model axis.
+class GeoPointSources:
+    """The geo-located series of one variable on their OWN point axis (vector<geo_point_ts>, api/api.h:137-168): `times` [P] point
+    times in seconds (strictly increasing, shared by the S series), `t_end` the series' total_period().end in seconds, `values`
+    [P][S], `point_fx` "average" (stair-case, POINT_AVERAGE_VALUE) or "instant" (linear between points).  The projection onto the
+    model axis (average_accessor, core/time_series.h:202-310, 2033-2072) runs on the device when the environment is set."""
 
-    `env.temperature = (xyz [S,3], values [T,S])`; a variable left as None keeps the cells' series NaN (region_model.h:448-452).
+    def __init__(self, xyz, times, values, t_end=None, point_fx="average"):
+        self.xyz, self.values = f64(xyz), f64(values)
+        self.times_us = np.ascontiguousarray(np.round(np.asarray(times, dtype=np.float64) * USEC), dtype=np.int64)
+        if t_end is None:  # a fixed-interval series ends one interval after its last point
+            t_end = times[-1] + (times[-1] - times[-2]) if len(times) > 1 else times[-1]
+        self.t_end_us = int(round(float(t_end) * USEC))
+        if point_fx not in ("average", "instant"):
+            raise RuntimeError("point_fx must be 'average' or 'instant'")
+        self.point_fx = point_fx
+
+
+class RegionEnvironment:
+    """a_region_environment (api/api.h:137-168): per variable a set of geo-located series.
+
+    `env.temperature = (xyz [S,3], values [T,S])` for series already on the model axis, or a `GeoPointSources` for series on their
+    own axis (3-hourly, daily, irregular ...); a variable left as None keeps the cells' series NaN (region_model.h:448-452).
     """
 
     def __init__(self, **kw):
@@ -245,11 +263,27 @@ class RegionModel:
             if src is None:
                 self._ck(self._L.sb2_set_sources(self._h, C.c_int(vi), C.c_int64(0), None, None))
                 continue
+            if isinstance(src, GeoPointSources):
+                if src.values.shape != (src.times_us.size, src.xyz.shape[0]):
+                    raise RuntimeError(f"{name}: source values must be [n_points][n_sources]")
+                self._ck(self._L.sb2_set_sources_on_axis(self._h, C.c_int(vi), C.c_int64(src.xyz.shape[0]), dptr(src.xyz), C.c_int64(src.times_us.size),
+                                                         src.times_us.ctypes.data_as(capi.c_i64p), C.c_int64(src.t_end_us), dptr(src.values),
+                                                         C.c_int(1 if src.point_fx == "instant" else 0)))
+                continue
             xyz, values = f64(src[0]), f64(src[1])
             if values.shape != (self.time_axis.n, xyz.shape[0]):
                 raise RuntimeError(f"{name}: source values must be [n_steps][n_sources]")
             self._ck(self._L.sb2_set_sources(self._h, C.c_int(vi), C.c_int64(xyz.shape[0]), dptr(xyz), dptr(values)))
         self.region_env = env
+
+    def sources_on_model_axis(self, name):
+        """the sources of a variable as projected onto the model axis: [n_steps][n_sources]"""
+        vi = FORCING_NAMES.index(name)
+        src = getattr(self.region_env, name)
+        n_src = (src.xyz if isinstance(src, GeoPointSources) else f64(src[0])).shape[0]
+        out = np.zeros((self.time_axis.n, n_src))
+        self._ck(self._L.sb2_get_sources_on_model_axis(self._h, C.c_int(vi), dptr(out)))
+        return out
 
     def interpolate(self, ip_parameter, env, best_effort=True):
         self._set_sources(env)

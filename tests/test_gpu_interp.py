@@ -125,3 +125,55 @@ def test_dense_tensor_core_idw_equals_per_neighbour_idw(sb):
     assert np.isnan(out[False]["wind_speed"]).any() and not np.isnan(out[False]["wind_speed"]).all()
     for k in FORCING:
         assert_parity(out[True][k], out[False][k], "dense vs per-neighbour idw " + k, rtol=1e-13)
+
+
+def test_sources_on_their_own_axis_are_projected_on_the_device(sb, oracle):
+    """region_environment series at their native resolution.  3-hourly stair-case precipitation with gaps,
+    20-minute linear (instant-value) temperature that starts late and ends early, irregular radiation: the device projection equals
+    the oracle's average_accessor bit for bit, and interpolation from it equals interpolation from the pre-projected series."""
+    from shyft_b200 import synthetic
+    n, T, S = 600, 72, 6
+    geo, ta, env0 = synthetic.make_region(n, T, S, config_index=14, cells_per_catchment=200)[:3]
+    rng = np.random.default_rng(14)
+    t0, dt = ta.start, ta.delta_t
+    xyz = env0.temperature[0]
+    # temperature: 20-minute instant values from t0+2h40 to t0+60h (NaN before the first point, NaN from the total period end on)
+    tt = t0 + 9600 + 1200 * np.arange(172)
+    tv = 5.0 + rng.normal(0, 2, (tt.size, S)).cumsum(axis=0) * 0.1
+    tv[40:43, 2] = np.nan
+    temp = sb.GeoPointSources(xyz, tt, tv, t_end=tt[-1] + 1200, point_fx="instant")
+    # precipitation: 3-hourly stair-case with a gap
+    pt = t0 - 3 * 3600 + 10800 * np.arange(30)
+    pv = rng.exponential(1.0, (pt.size, S)) * (rng.random((pt.size, S)) < 0.4)
+    pv[7, :] = np.nan
+    prec = sb.GeoPointSources(xyz, pt, pv, point_fx="average")
+    # radiation: irregular point times
+    rt = np.sort(t0 + rng.choice(np.arange(0, 80 * 3600, 600), 90, replace=False))
+    rv = rng.uniform(0, 400, (rt.size, S))
+    rad = sb.GeoPointSources(xyz, rt, rv, t_end=rt[-1] + 3600, point_fx="average")
+    env = sb.RegionEnvironment(temperature=temp, precipitation=prec, radiation=rad, wind_speed=env0.wind_speed, rel_hum=env0.rel_hum)
+    m = sb.PTGSKModel(geo)
+    ip = sb.InterpolationParameter(use_idw_for_temperature=1)
+    m.run_interpolation(ip, ta, env, best_effort=True)
+    US = 10**6
+    projected = {}
+    for name, src in (("temperature", temp), ("precipitation", prec), ("radiation", rad)):
+        want = oracle.average_accessor(src.times_us, src.values, src.t_end_us, src.point_fx == "instant", t0 * US, dt * US, T)
+        got = m.sources_on_model_axis(name)
+        assert np.array_equal(np.isnan(got), np.isnan(want)), name
+        assert np.array_equal(got[~np.isnan(got)], want[~np.isnan(want)]), name     # same operations in the same order
+        projected[name] = want
+    assert np.isnan(projected["temperature"][:2]).all() and np.isnan(projected["temperature"][60:]).all()
+    assert np.isfinite(projected["temperature"][3:60, 0]).all()
+    f_native = {k: m.cell_forcing(k) for k in ("temperature", "precipitation", "radiation")}
+    # the same environment handed over pre-projected: identical cell forcing
+    env_pre = sb.RegionEnvironment(temperature=(xyz, projected["temperature"]), precipitation=(xyz, projected["precipitation"]),
+                                   radiation=(xyz, projected["radiation"]), wind_speed=env0.wind_speed, rel_hum=env0.rel_hum)
+    m2 = sb.PTGSKModel(geo)
+    m2.run_interpolation(ip, ta, env_pre, best_effort=True)
+    for k, v in f_native.items():
+        w = m2.cell_forcing(k)
+        assert np.array_equal(np.isnan(v), np.isnan(w)) and np.allclose(v[~np.isnan(v)], w[~np.isnan(w)], rtol=1e-12, atol=0), k
+    with pytest.raises(RuntimeError, match="strictly increasing"):
+        bad = sb.GeoPointSources(xyz, [t0, t0], np.zeros((2, S)), t_end=t0 + 10)
+        m._set_sources(sb.RegionEnvironment(temperature=bad))
