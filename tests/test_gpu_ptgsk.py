@@ -168,6 +168,33 @@ def test_config1_slice_parity_through_a_winter(sb, oracle, collect):
         assert_parity(cc[:, k], want["charge_m3s"][:, cix == k].sum(axis=1), f"catchment {k} charge", rtol=1e-9, atol_frac=1e-12)
 
 
+@pytest.mark.parametrize("n,T", [(1, 1), (1, 130), (31, 63), (33, 65), (100, 129), (257, 1)])
+def test_ragged_sizes_are_bit_identical(sb, oracle, n, T):
+    """One cell, one step, cell counts around a warp and step counts around the 64-step slice of the time split: every series and
+    the end state equal the oracle's bit for bit (out-of-range lanes of the last warp shadow a cell and store nothing)."""
+    geo, ta, env, st0 = _synthetic(sb, n, T, 4, config_index=30 + n % 7, cells_per_catchment=max(1, n // 3), start=1424476800)  # 2015-02-21
+    st0[:, 5] = -1.0                      # acc_melt < 0: accumulation branch
+    st0[:, 4] = np.linspace(5.0, 80.0, n)  # sdc_melt_mean: a snow pack from the first step on
+    st0[:, 1] = 2.0                       # some liquid water: wet-snow paths, Brent on snowfall
+    m = sb.PTGSKModel(geo, PTGSK_DEFAULT)
+    ip = sb.InterpolationParameter(use_idw_for_temperature=1)
+    assert m.run_interpolation(ip, ta, env)
+    gm, f = _oracle_forcing(oracle, geo, ta, env, ip_idw=True)
+    for name in FORCING:
+        m.set_cell_forcing(name, f[name])
+    m.set_states(st0)
+    m.set_state_collection(-1, True)
+    m.run_cells()
+    want = oracle.ptgsk_run_cells(gm, PTGSK_DEFAULT, f, st0, ta.start * 10**6, ta.delta_t * 10**6, collect_response=True, collect_state=True, ncore=2)
+    for name in ("avg_discharge", "charge_m3s", "snow_sca", "snow_swe", "snow_outflow", "glacier_melt", "ae_output", "pe_output"):
+        assert np.array_equal(m.response(name), want[name], equal_nan=True), name
+    for name in sb.capi.STATE_SERIES_NAMES[sb.PT_GS_K]:
+        assert np.array_equal(m.state_series(name), want[name], equal_nan=True), name
+    assert np.array_equal(m.get_states(), want["state"])
+    assert m.catchment_discharges().shape == (T, m.number_of_catchments())
+    assert np.allclose(m.catchment_discharges().sum(axis=1), want["avg_discharge"].sum(axis=1), rtol=1e-12)
+
+
 def test_catchment_indexing_is_bit_exact(sb, oracle):
     rng = np.random.default_rng(5)
     cids = rng.integers(1, 40, 777) * 13
