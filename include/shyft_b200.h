@@ -112,6 +112,18 @@ int sb2_get_initial_state(const sb2_model* m, double* states, int64_t n_cells);
 int sb2_revert_to_initial_state(sb2_model* m);                                          /* :814-818 */
 int sb2_adjust_q(sb2_model* m, double q_scale, const int64_t* cids, int n);             /* :831-837 */
 int sb2_set_collector_mode(sb2_model* m, int collect_bits);                             /* cell type + set_state_collection / set_snow_sca_swe_collection :844-858 */
+/* region_model::adjust_state_to_target_flow (:626-637) = adjust_state_model::tune_flow (core/model_state_tuning.h:38-118): scale the
+ * ground storage of the cells of `cids` (empty = all) from the CURRENT state so that the mean avg_discharge of the n_steps steps from
+ * start_step equals wanted_flow_m3s; the reference's q_adjust_result (:11-16) comes back by value.  On return the current state is the
+ * adjusted one, the initial state and the catchment calculation filter are as before.  Needs a resident cell environment. */
+typedef struct sb2_q_adjust_result {
+    double q_0;             /* m3/s before the adjustment */
+    double q_r;             /* m3/s reached */
+    char diagnostics[512];  /* empty if ok */
+} sb2_q_adjust_result;
+int sb2_adjust_state_to_target_flow(sb2_model* m, double wanted_flow_m3s, const int64_t* cids, int n_cids, int64_t start_step,
+                                    double scale_range /* 3.0 */, double scale_eps /* 1e-3 */, int64_t max_iter /* 300 */,
+                                    int64_t n_steps /* 1 */, sb2_q_adjust_result* result);
 
 /* ---- environment ------------------------------------------------------------------------------ */
 /* initialize_cell_environment(time_axis) (:359-364): fixed_dt{t0, dt, n} in microseconds; env_ts reset to NaN */

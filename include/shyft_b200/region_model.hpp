@@ -43,6 +43,11 @@ struct region_environment {
     }
 };
 
+struct q_adjust_result {  // core/model_state_tuning.h:11-16
+    double q_0 = 0.0, q_r = 0.0;
+    std::string diagnostics;
+};
+
 template <int STACK>
 class region_model {
     sb2_model* h_ = nullptr;
@@ -82,6 +87,14 @@ class region_model {
     void revert_to_initial_state() { ck(sb2_revert_to_initial_state(h_)); }                                                                   // :814-818
     void adjust_q(double q_scale, const std::vector<int64_t>& cids) { ck(sb2_adjust_q(h_, q_scale, cids.data(), int(cids.size()))); }          // :831-837
     void set_collector_mode(int bits) { ck(sb2_set_collector_mode(h_, bits)); }
+    // :626-637; q_adjust_result of core/model_state_tuning.h:11-16
+    q_adjust_result adjust_state_to_target_flow(double wanted_flow_m3s, const std::vector<int64_t>& cids, size_t start_step = 0, double scale_range = 3.0,
+                                                double scale_eps = 1e-3, size_t max_iter = 300, size_t n_steps = 1) {
+        sb2_q_adjust_result r{};
+        ck(sb2_adjust_state_to_target_flow(h_, wanted_flow_m3s, cids.data(), int(cids.size()), int64_t(start_step), scale_range, scale_eps,
+                                           int64_t(max_iter), int64_t(n_steps), &r));
+        return q_adjust_result{r.q_0, r.q_r, std::string(r.diagnostics)};
+    }
 
     void initialize_cell_environment(const fixed_dt& ta) { ck(sb2_initialize_cell_environment(h_, ta.t, ta.dt, int64_t(ta.n))); time_axis = ta; }  // :359-364
     bool interpolate(const interpolation_parameter& ip, const region_environment& env, bool best_effort = true) {                                   // :397-527

@@ -493,3 +493,155 @@ def average_accessor(t_us, values, t_end_us, linear, ta_t0_us, ta_dt_us, ta_n):
     lib().sho_average_accessor(t.ctypes.data_as(c_i64p), _d(vv), C.c_int64(t.size), C.c_int64(vv.shape[1]), C.c_int64(t_end_us), C.c_int(1 if linear else 0),
                                C.c_int64(ta_t0_us), C.c_int64(ta_dt_us), C.c_int64(ta_n), _d(out))
     return out
+
+
+# ---- state tuning: core/model_state_tuning.h:38-118 over region_model::adjust_state_to_target_flow (core/region_model.h:626-637) ----
+# dlib 19.16 (pinned in build_support/build_dependencies.sh) is not under /root/reference: find_min_single_variable is restated from
+# its published algorithm (dlib/optimization/optimization_line_search.h: bracket by radius doubling, then three-point parabola
+# steps with the 0.1 keep-away rule).  PARITY UNPINNED at the dlib boundary: the reference's tests only assert the reached flow to
+# 2 decimals (shyft/tests/api/test_region_model_stacks.py:318-333; test/cell_builder_test.cpp:281-296) -- those asserts pass here.
+class MinimiserFailure(RuntimeError):
+    pass
+
+
+def _poly_min_3(p1, p2, p3, f1, f2, f3):
+    t1 = f1 * (p3 * p3 - p2 * p2) + f2 * (p1 * p1 - p3 * p3) + f3 * (p2 * p2 - p1 * p1)
+    t2 = 2 * (f1 * (p3 - p2) + f2 * (p1 - p3) + f3 * (p2 - p1))
+    if t2 == 0:
+        return p2
+    r = t1 / t2
+    return r if p1 <= r <= p3 else min(max(p1, r), p3)
+
+
+def find_min_single_variable(f, start, begin=-1e200, end=1e200, eps=1e-3, max_iter=100, initial_search_radius=1.0):
+    """-> (argmin, f(argmin)); raises MinimiserFailure like dlib's argument check / iteration limit"""
+    if not (eps > 0 and max_iter > 1 and begin <= start <= end and initial_search_radius > 0):
+        raise MinimiserFailure("find_min_single_variable: eps > 0, max_iter > 1 and begin <= starting_point <= end are required")
+    radius = initial_search_radius
+    evals = 1
+    if begin == end:
+        return start, f(start)
+    p1, p3 = max(start - radius, begin), min(start + radius, end)
+    f1, f3 = f(p1), f(p3)
+    if start == p1 or start == p3:
+        p2 = (p1 + p3) / 2
+    else:
+        p2 = start
+    f2 = f(p2)
+    evals += 2
+    too_many = "The max number of iterations of single variable optimization have been reached without converging."
+    while not (f1 > f2 and f2 < f3):
+        if evals >= max_iter:
+            raise MinimiserFailure(too_many)
+        if p3 - p1 < eps:
+            if f1 < min(f2, f3):
+                return p1, f1
+            if f2 < min(f1, f3):
+                return p2, f2
+            return p3, f3
+        if f1 <= f3:
+            if p1 == begin or (f1 == f2 and (end - begin) < radius):
+                p3, f3 = p2, f2
+                p2 = (p1 + p2) / 2.0
+                f2 = f(p2)
+            else:
+                p3, f3, p2, f2 = p2, f2, p1, f1
+                p1 = max(p1 - radius, begin)
+                f1 = f(p1)
+                radius *= 2
+        else:
+            if p3 == end or (f2 == f3 and (end - begin) < radius):
+                p1, f1 = p2, f2
+                p2 = (p3 + p2) / 2.0
+                f2 = f(p2)
+            else:
+                p1, f1, p2, f2 = p2, f2, p3, f3
+                p3 = min(p3 + radius, end)
+                f3 = f(p3)
+                radius *= 2
+        evals += 1
+    tau = 0.1
+    while evals < max_iter and p3 - p1 > eps:
+        pm = _poly_min_3(p1, p2, p3, f1, f2, f3)
+        if pm < p2:
+            d = (p2 - p1) * tau
+            if abs(p1 - pm) < d:
+                pm = p1 + d
+            elif abs(p2 - pm) < d:
+                pm = p2 - d
+        else:
+            d = (p3 - p2) * tau
+            if abs(p2 - pm) < d:
+                pm = p2 + d
+            elif abs(p3 - pm) < d:
+                pm = p3 - d
+        ratio = abs(p1 - p2) / abs(p2 - p3)
+        if not (0.01 < ratio < 100):
+            if ratio > 1 and pm > p2:
+                pm = (p1 + p2) / 2
+            elif pm < p2:
+                pm = (p2 + p3) / 2
+        fm = f(pm)
+        if pm < p2:
+            if f1 > fm and fm < f2:
+                p3, f3, p2, f2 = p2, f2, pm, fm
+            else:
+                p1, f1 = pm, fm
+        else:
+            if f2 > fm and fm < f3:
+                p1, f1, p2, f2 = p2, f2, pm, fm
+            else:
+                p3, f3 = pm, fm
+        evals += 1
+    if evals >= max_iter:
+        raise MinimiserFailure(too_many)
+    return p2, f2
+
+
+def adjust_state_to_target_flow(run_cells, state, q_columns, catchment_ids, wanted_flow_m3s, cids=(), start_step=0, scale_range=3.0,
+                                scale_eps=1e-3, max_iter=300, n_steps=1):
+    """tune_flow over the oracle's run_cells.
+
+    run_cells(state, start_step, n_steps, cell_mask) -> dict with "avg_discharge" [T][n] (any of the *_run_cells above, curried);
+    state [n][k] = s0; q_columns = the ground-storage columns state.adjust_q scales (kirchner.q; sm, uz, lz for hbv_stack).
+    -> dict(q_0, q_r, diagnostics, state = the adjusted state, scale, evaluations)."""
+    s0 = np.array(state, dtype=np.float64)
+    cat = np.asarray(catchment_ids, dtype=np.int64)
+    in_scope = np.ones(cat.size, dtype=bool) if len(cids) == 0 else np.isin(cat, np.asarray(cids, dtype=np.int64))
+    if len(cids):
+        for cid in cids:  # set_catchment_calculation_filter in the adjust_state_model ctor (region_model.h:715-729)
+            if cid not in set(cat.tolist()):
+                raise RuntimeError("set_catchment_calculation_filter: no cells have supplied cid")
+    evaluations = []
+
+    def adjusted(q_scale):
+        s = s0.copy()
+        for c in q_columns:
+            s[in_scope, c] = s[in_scope, c] * q_scale
+        return s
+
+    def discharge(q_scale):  # model_state_tuning.h:59-73
+        out = run_cells(adjusted(q_scale), start_step, n_steps, in_scope.astype(np.uint8))
+        q_sum = 0.0
+        for i in range(start_step, start_step + n_steps):
+            q_sum += sum_catchment_feature_value(out["avg_discharge"], cat, list(cids), i)
+        evaluations.append((q_scale, q_sum / float(n_steps)))
+        return q_sum / float(n_steps)
+
+    r = dict(q_0=0.0, q_r=0.0, diagnostics="", state=s0, scale=float("nan"), evaluations=evaluations)
+    try:
+        q_0 = discharge(1.0)
+        scale = wanted_flow_m3s / q_0
+        diag = ""
+        try:
+            if not np.isfinite(q_0):
+                raise RuntimeError("the initial simulated discharge is nan")
+            scale, _ = find_min_single_variable(lambda x: (discharge(x) - wanted_flow_m3s) ** 2, scale, scale / scale_range,
+                                                scale * scale_range, scale * scale_eps, max_iter)
+        except Exception as e:  # noqa: BLE001  (the reference catches std::exception)
+            diag = f"failed to find solution within {max_iter}, exception was:{e}"
+        q_r = discharge(scale)
+        r.update(q_0=q_0, q_r=q_r, diagnostics=diag, state=adjusted(scale), scale=scale)
+    except Exception as e:  # noqa: BLE001
+        r["diagnostics"] = "Failed to tune_flow" + str(e)
+    return r

@@ -1470,28 +1470,121 @@ int sb2_is_cell_env_ts_ok(sb2_model* m, int* ok) {
     });
 }
 
+namespace {
+// region_model::run_cells (core/region_model.h:578-597) on the resident cell environment
+void run_cells_resident(sb2_model* m, int start_step, int n_steps) {
+    validate_run_args(m, start_step, n_steps);
+    if (!m->d_forcing[0].p || m->forcing_first != 0 || m->forcing_rows != m->T)
+        throw Error("run_cells: cell environment is not resident for the whole time axis (use interpolate / set_cell_forcing, or run_windowed)");
+    snapshot_initial_state_if_unset(m);
+    const int64_t first = n_steps > 0 ? start_step : 0;  // pt_gs_k.h:358-359: n_steps == 0 runs the whole axis
+    const int64_t count = n_steps > 0 ? n_steps : m->T;
+    const bool fresh = m->out_rows != m->T || m->out_first != 0;
+    ensure_series(m, 0, m->T);
+    // begin_run -> ts_init (cell_model.h:135-138,163-170): new series are NaN everywhere, existing ones NaN over the run range
+    for (int r = 0; r < SB2_N_RESPONSE; ++r)
+        if (m->d_resp[r].p) fill_nan(m, m->d_resp[r].p + (fresh ? 0 : first * m->n), (fresh ? m->T : count) * m->n);
+    for (int s = 0; s < SB2_N_STATE_SERIES; ++s)
+        if (m->d_st[s].p) fill_nan(m, m->d_st[s].p + (fresh ? 0 : first * m->n), (fresh ? m->T + 1 : count + 1) * m->n);
+    time_begin(m, 2);
+    launch_step_range(m, first, count, true);
+    m->last_step_ms = time_end(m, 2, 3);
+    m->ran_first = first; m->ran_steps = count;
+    m->rlocal_valid = m->rnet_valid = false;
+    check_device_errors(m);
+}
+}  // namespace
+
 // ---- the hot path ----------------------------------------------------------------------------------------------------
 int sb2_run_cells(sb2_model* m, int start_step, int n_steps) {
+    return guarded(m, [&] { run_cells_resident(m, start_step, n_steps); });
+}
+
+// ---- state tuning -------------------------------------------------------------------------------------
+// region_model::adjust_state_to_target_flow (core/region_model.h:626-637) over adjust_state_model::{discharge, tune_flow}
+// (core/model_state_tuning.h:38-118).  One evaluation of discharge(q_scale) stays on the device: state snapshot s0 copied back
+// device-to-device, the ground-storage rows scaled for the selected cells, run_cells over [i0, i0 + n), the selected cells'
+// avg_discharge rows reduced by stat_reduce_rows_kernel; only the n row sums come back to the host, where dlib's one-dimensional
+// minimiser (restated in sb2_host.hpp) picks the next q_scale.
+int sb2_adjust_state_to_target_flow(sb2_model* m, double wanted_flow_m3s, const int64_t* cids, int n_cids, int64_t start_step, double scale_range,
+                                    double scale_eps, int64_t max_iter, int64_t n_steps, sb2_q_adjust_result* result) {
     return guarded(m, [&] {
-        validate_run_args(m, start_step, n_steps);
-        if (!m->d_forcing[0].p || m->forcing_first != 0 || m->forcing_rows != m->T)
-            throw Error("run_cells: cell environment is not resident for the whole time axis (use interpolate / set_cell_forcing, or run_windowed)");
-        snapshot_initial_state_if_unset(m);
-        const int64_t first = n_steps > 0 ? start_step : 0;  // pt_gs_k.h:358-359: n_steps == 0 runs the whole axis
-        const int64_t count = n_steps > 0 ? n_steps : m->T;
-        const bool fresh = m->out_rows != m->T || m->out_first != 0;
-        ensure_series(m, 0, m->T);
-        // begin_run -> ts_init (cell_model.h:135-138,163-170): new series are NaN everywhere, existing ones NaN over the run range
-        for (int r = 0; r < SB2_N_RESPONSE; ++r)
-            if (m->d_resp[r].p) fill_nan(m, m->d_resp[r].p + (fresh ? 0 : first * m->n), (fresh ? m->T : count) * m->n);
-        for (int s = 0; s < SB2_N_STATE_SERIES; ++s)
-            if (m->d_st[s].p) fill_nan(m, m->d_st[s].p + (fresh ? 0 : first * m->n), (fresh ? m->T + 1 : count + 1) * m->n);
-        time_begin(m, 2);
-        launch_step_range(m, first, count, true);
-        m->last_step_ms = time_end(m, 2, 3);
-        m->ran_first = first; m->ran_steps = count;
-        m->rlocal_valid = m->rnet_valid = false;
-        check_device_errors(m);
+        if (!result) throw Error("null result");
+        result->q_0 = result->q_r = 0.0;
+        result->diagnostics[0] = 0;
+        auto set_diag = [&](const std::string& d) {
+            std::snprintf(result->diagnostics, sizeof(result->diagnostics), "%s", d.c_str());
+        };
+        if (n_cids > 0 && !cids) throw Error("null catchment id list");
+        const std::vector<uint8_t> old_filter = m->catchment_filter;
+        // adjust_state_model ctor: filter := cids (throws for unknown ids, outside the reference's try block), s0 := get_states
+        if (n_cids > 0) {
+            if (int64_t(n_cids) > m->n_catch()) throw Error("set_catchment_calculation_filter: supplied list > available catchments");
+            for (int i = 0; i < n_cids; ++i)
+                if (!m->cid_to_cix.count(cids[i])) throw Error("set_catchment_calculation_filter: no cells have supplied cid");
+            m->catchment_filter.assign(size_t(m->n_catch()), 0);
+            for (int i = 0; i < n_cids; ++i) m->catchment_filter[size_t(m->cid_to_cix[cids[i]])] = 1;
+        } else
+            m->catchment_filter.clear();
+        m->filter_dirty = true;
+        std::vector<uint8_t> sel(size_t(m->n), n_cids == 0 ? 1 : 0);
+        if (n_cids > 0)
+            for (int64_t i = 0; i < m->n; ++i) sel[size_t(i)] = m->catchment_filter[size_t(m->cix_of_cell[i])];
+        DevArray<uint8_t> d_sel;
+        DevArray<double> d_s0, d_rows;
+        d_sel.upload(sel, m->stream);
+        d_s0.resize(m->d_state.n);
+        CUDA_OK(cudaMemcpyAsync(d_s0.p, m->d_state.p, m->d_state.n * sizeof(double), cudaMemcpyDeviceToDevice, m->stream));
+        const int first_q = m->stack == SB2_HBV_STACK ? m->n_state - 3 : m->n_state - 1;
+        auto adjust_from_s0 = [&](double q_scale) {  // revert_to_state_0(); rm.adjust_q(q_scale, cids)
+            CUDA_OK(cudaMemcpyAsync(m->d_state.p, d_s0.p, m->d_state.n * sizeof(double), cudaMemcpyDeviceToDevice, m->stream));
+            for (int s = first_q; s < m->n_state; ++s) {
+                scale_selected_kernel<<<grid_for(m->n, 256), 256, 0, m->stream>>>(m->d_state.p + size_t(s) * m->n, d_sel.p, m->n, q_scale);
+                ++m->launches;
+            }
+            CUDA_OK(cudaGetLastError());
+        };
+        std::vector<double> rows;
+        auto discharge = [&](double q_scale) -> double {  // model_state_tuning.h:59-73
+            adjust_from_s0(q_scale);
+            run_cells_resident(m, int(start_step), int(n_steps));
+            const double* q = stat_series_rows(m, SB2_STAT_RESPONSE, SB2_R_AVG_DISCHARGE, start_step, n_steps);
+            d_rows.resize(size_t(n_steps));
+            rows.resize(size_t(n_steps));
+            stat_reduce_rows_kernel<<<int(std::min<int64_t>(n_steps, 148 * 8)), 256, 0, m->stream>>>(q, m->n, n_steps, d_sel.p, nullptr, m->d_area.p,
+                                                                                                     nullptr, d_rows.p);
+            CUDA_OK(cudaGetLastError());
+            ++m->launches;
+            CUDA_OK(cudaMemcpyAsync(rows.data(), d_rows.p, rows.size() * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+            CUDA_OK(cudaStreamSynchronize(m->stream));
+            double q_sum = 0.0;
+            for (double v : rows) q_sum += v;
+            return q_sum / double(n_steps);
+        };
+        auto restore_filter = [&] { m->catchment_filter = old_filter; m->filter_dirty = true; };
+        try {  // region_model.h:630-634
+            sb2_q_adjust_result r{};
+            r.q_0 = discharge(1.0);
+            double scale = wanted_flow_m3s / r.q_0;
+            std::string diag;
+            try {
+                if (!std::isfinite(r.q_0)) throw Error("the initial simulated discharge is nan");
+                host::find_min_single_variable(
+                    [&](double x) { const double d = discharge(x) - wanted_flow_m3s; return d * d; }, scale, scale / scale_range, scale * scale_range,
+                    scale * scale_eps, long(max_iter));
+            } catch (const std::exception& e) {
+                diag = "failed to find solution within " + std::to_string(max_iter) + ", exception was:" + e.what();
+            }
+            r.q_r = discharge(scale);
+            adjust_from_s0(scale);
+            CUDA_OK(cudaStreamSynchronize(m->stream));
+            result->q_0 = r.q_0;
+            result->q_r = r.q_r;
+            set_diag(diag);
+        } catch (const std::exception& e) {
+            set_diag(std::string("Failed to tune_flow") + e.what());
+        }
+        restore_filter();
     });
 }
 

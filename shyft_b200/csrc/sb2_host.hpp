@@ -230,5 +230,81 @@ inline std::vector<double> make_uhg_from_gamma(int n_steps, double alpha, double
     return r;
 }
 
+// ---- one-dimensional minimiser of the state tuning (core/model_state_tuning.h:98-108) ---------------------------------
+// The reference calls dlib 19.16 find_min_single_variable(f, x, begin, end, eps, max_iter) (dlib/optimization/optimization_line_search.h;
+// the library is not under /root/reference).  Its published algorithm, written out here: (1) three points p1 < p2 < p3 around the start
+// (search radius 1, clipped to [begin, end]); (2) walk / shrink until f1 > f2 < f3, doubling the radius on every outward step;
+// (3) shrink the bracket with the minimum of the parabola through the three points (Fletcher eq. 4.2.1), kept at least a tenth of the
+// sub-interval away from the points it would split and pushed to the wider side when one side is > 100 x the other; stop when
+// p3 - p1 <= eps.  Throws like dlib does: argument check first, "exceeded the allowable number of iterations" on max_iter.
+struct MinimiserFailure : std::runtime_error { using std::runtime_error::runtime_error; };
+
+inline double parabola_min_3pt(double p1, double p2, double p3, double f1, double f2, double f3) {
+    const double num = f1 * (p3 * p3 - p2 * p2) + f2 * (p1 * p1 - p3 * p3) + f3 * (p2 * p2 - p1 * p1);
+    const double den = 2 * (f1 * (p3 - p2) + f2 * (p1 - p3) + f3 * (p2 - p1));
+    if (den == 0) return p2;
+    const double r = num / den;
+    if (p1 <= r && r <= p3) return r;
+    return std::min(std::max(p1, r), p3);
+}
+template <class F>
+double find_min_single_variable(F&& f, double& x, double begin, double end, double eps, long max_iter, double radius = 1.0) {
+    if (!(eps > 0 && max_iter > 1 && begin <= x && x <= end && radius > 0))
+        throw MinimiserFailure("find_min_single_variable: eps > 0, max_iter > 1 and begin <= starting_point <= end are required");
+    long evals = 1;
+    if (begin == end) return f(x);
+    double p1 = std::max(x - radius, begin), p3 = std::min(x + radius, end), p2;
+    double f1 = f(p1), f3 = f(p3), f2;
+    if (x == p1 || x == p3) { p2 = (p1 + p3) / 2; f2 = f(p2); }
+    else { p2 = x; f2 = f(x); }
+    evals += 2;
+    while (!(f1 > f2 && f2 < f3)) {
+        if (evals >= max_iter) throw MinimiserFailure("The max number of iterations of single variable optimization have been reached without converging.");
+        if (p3 - p1 < eps) {
+            if (f1 < std::min(f2, f3)) { x = p1; return f1; }
+            if (f2 < std::min(f1, f3)) { x = p2; return f2; }
+            x = p3; return f3;
+        }
+        if (f1 <= f3) {  // the low side is the left one
+            if (p1 == begin || (f1 == f2 && (end - begin) < radius)) { p3 = p2; f3 = f2; p2 = (p1 + p2) / 2.0; f2 = f(p2); }
+            else { p3 = p2; f3 = f2; p2 = p1; f2 = f1; p1 = std::max(p1 - radius, begin); f1 = f(p1); radius *= 2; }
+        } else {
+            if (p3 == end || (f2 == f3 && (end - begin) < radius)) { p1 = p2; f1 = f2; p2 = (p3 + p2) / 2.0; f2 = f(p2); }
+            else { p1 = p2; f1 = f2; p2 = p3; f2 = f3; p3 = std::min(p3 + radius, end); f3 = f(p3); radius *= 2; }
+        }
+        ++evals;
+    }
+    const double tau = 0.1;
+    while (evals < max_iter && p3 - p1 > eps) {
+        double pm = parabola_min_3pt(p1, p2, p3, f1, f2, f3);
+        if (pm < p2) {
+            const double d = (p2 - p1) * tau;
+            if (std::fabs(p1 - pm) < d) pm = p1 + d;
+            else if (std::fabs(p2 - pm) < d) pm = p2 - d;
+        } else {
+            const double d = (p3 - p2) * tau;
+            if (std::fabs(p2 - pm) < d) pm = p2 + d;
+            else if (std::fabs(p3 - pm) < d) pm = p3 - d;
+        }
+        const double ratio = std::fabs(p1 - p2) / std::fabs(p2 - p3);
+        if (!(ratio < 100 && ratio > 0.01)) {
+            if (ratio > 1 && pm > p2) pm = (p1 + p2) / 2;
+            else if (pm < p2) pm = (p2 + p3) / 2;
+        }
+        const double fm = f(pm);
+        if (pm < p2) {
+            if (f1 > fm && fm < f2) { p3 = p2; f3 = f2; p2 = pm; f2 = fm; }
+            else { p1 = pm; f1 = fm; }
+        } else {
+            if (f2 > fm && fm < f3) { p1 = p2; f1 = f2; p2 = pm; f2 = fm; }
+            else { p3 = pm; f3 = fm; }
+        }
+        ++evals;
+    }
+    if (evals >= max_iter) throw MinimiserFailure("The max number of iterations of single variable optimization have been reached without converging.");
+    x = p2;
+    return f2;
+}
+
 }  // namespace host
 }  // namespace sb2

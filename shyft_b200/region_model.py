@@ -231,6 +231,16 @@ class RegionModel:
         a = np.ascontiguousarray(cids, dtype=np.int64)
         self._ck(self._L.sb2_adjust_q(self._h, C.c_double(q_scale), a.ctypes.data_as(capi.c_i64p), C.c_int(a.size)))
 
+    def adjust_state_to_target_flow(self, wanted_flow_m3s, cids=(), start_step=0, scale_range=3.0, scale_eps=1.0e-3, max_iter=300, n_steps=1):
+        """region_model::adjust_state_to_target_flow (core/region_model.h:626-637; api/boostpython/expose.h:380): -> q_adjust_result
+        with .q_0, .q_r, .diagnostics; the current state is left adjusted, initial state and calculation filter are kept."""
+        a = np.ascontiguousarray(cids, dtype=np.int64)
+        r = capi.QAdjustResult()
+        self._ck(self._L.sb2_adjust_state_to_target_flow(self._h, C.c_double(wanted_flow_m3s), a.ctypes.data_as(capi.c_i64p), C.c_int(a.size),
+                                                         C.c_int64(start_step), C.c_double(scale_range), C.c_double(scale_eps), C.c_int64(max_iter),
+                                                         C.c_int64(n_steps), C.byref(r)))
+        return r
+
     def set_state_collection(self, catchment_id, on_or_off):
         # the device collects a series for all cells or for none; per-catchment switching (:844-849) selects all
         self._state_collection = bool(on_or_off)
