@@ -111,6 +111,16 @@ int sb2_set_initial_state(sb2_model* m, const double* states, int64_t n_cells); 
 int sb2_get_initial_state(const sb2_model* m, double* states, int64_t n_cells);
 int sb2_revert_to_initial_state(sb2_model* m);                                          /* :814-818 */
 int sb2_adjust_q(sb2_model* m, double q_scale, const int64_t* cids, int n);             /* :831-837 */
+/* Cell-identified state (api/api_state.h:34-148; `model.state.extract_state(cids)` / `.apply_state(states, cids)` in Python,
+ * api/boostpython/expose.h:59-88).  cell_state_id_of (:58-60): (catchment id, (int)mid_point.x, (int)mid_point.y, (int)area).
+ * extract: the states of the cells of `cids` (empty = all), in cell order, gathered on the device; ids / states hold up to sb2_size()
+ * entries.  apply: every supplied state whose id.cid passes `cids` is written to the cell with the same id (among the cells of `cids`);
+ * the positions of those that found no cell come back in `missing` (capacity n), exactly as state_io_handler::apply_state :119-140. */
+typedef struct sb2_cell_state_id { int64_t cid, x, y, area; } sb2_cell_state_id;
+int sb2_extract_state(const sb2_model* m, const int64_t* cids, int n_cids, sb2_cell_state_id* ids, double* states /* [.][state_size] */,
+                      int64_t* n_out);
+int sb2_apply_state(sb2_model* m, int64_t n, const sb2_cell_state_id* ids, const double* states /* [n][state_size] */, const int64_t* cids,
+                    int n_cids, int64_t* missing, int64_t* n_missing);
 int sb2_set_collector_mode(sb2_model* m, int collect_bits);                             /* cell type + set_state_collection / set_snow_sca_swe_collection :844-858 */
 /* region_model::adjust_state_to_target_flow (:626-637) = adjust_state_model::tune_flow (core/model_state_tuning.h:38-118): scale the
  * ground storage of the cells of `cids` (empty = all) from the CURRENT state so that the mean avg_discharge of the n_steps steps from

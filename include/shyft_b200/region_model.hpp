@@ -87,6 +87,22 @@ class region_model {
     void revert_to_initial_state() { ck(sb2_revert_to_initial_state(h_)); }                                                                   // :814-818
     void adjust_q(double q_scale, const std::vector<int64_t>& cids) { ck(sb2_adjust_q(h_, q_scale, cids.data(), int(cids.size()))); }          // :831-837
     void set_collector_mode(int bits) { ck(sb2_set_collector_mode(h_, bits)); }
+    // state_io_handler (api/api_state.h:93-142): ids and flattened states of the cells of `cids`; apply returns the unmatched positions
+    void extract_state(const std::vector<int64_t>& cids, std::vector<sb2_cell_state_id>& ids, std::vector<double>& states) const {
+        ids.resize(size());
+        states.resize(size() * size_t(sb2_state_size(h_)));
+        int64_t n = 0;
+        ck(sb2_extract_state(h_, cids.data(), int(cids.size()), ids.data(), states.data(), &n));
+        ids.resize(size_t(n));
+        states.resize(size_t(n) * size_t(sb2_state_size(h_)));
+    }
+    std::vector<int64_t> apply_state(const std::vector<sb2_cell_state_id>& ids, const std::vector<double>& states, const std::vector<int64_t>& cids) {
+        std::vector<int64_t> missing(ids.size() + 1);
+        int64_t n = 0;
+        ck(sb2_apply_state(h_, int64_t(ids.size()), ids.data(), states.data(), cids.data(), int(cids.size()), missing.data(), &n));
+        missing.resize(size_t(n));
+        return missing;
+    }
     // :626-637; q_adjust_result of core/model_state_tuning.h:11-16
     q_adjust_result adjust_state_to_target_flow(double wanted_flow_m3s, const std::vector<int64_t>& cids, size_t start_step = 0, double scale_range = 3.0,
                                                 double scale_eps = 1e-3, size_t max_iter = 300, size_t n_steps = 1) {

@@ -645,3 +645,35 @@ def adjust_state_to_target_flow(run_cells, state, q_columns, catchment_ids, want
     except Exception as e:  # noqa: BLE001
         r["diagnostics"] = "Failed to tune_flow" + str(e)
     return r
+
+
+# ---- cell-identified state: api/api_state.h:34-142 (plain restatement; integer work, must be exact) ---------------------------
+def cell_state_id_of(geo_row):
+    """:58-60 -- (catchment_id, (int)x, (int)y, (int)area); geo_row in GEO_COLS order"""
+    return (int(geo_row[4]), int(geo_row[0]), int(geo_row[1]), int(geo_row[3]))  # Python int() truncates toward zero like the C cast
+
+
+def extract_state(geo, states, cids=()):
+    """state_io_handler::extract_state :105-114 -> list of (id, state row) in cell order"""
+    out = []
+    for i in range(len(geo)):
+        if len(cids) == 0 or int(geo[i][4]) in cids:
+            out.append((cell_state_id_of(geo[i]), np.array(states[i], dtype=np.float64)))
+    return out
+
+
+def apply_state(geo, states, id_states, cids=()):
+    """state_io_handler::apply_state :119-140 -> (new states, missing positions)"""
+    st = np.array(states, dtype=np.float64)
+    cmap = {}
+    for i in range(len(geo)):
+        if len(cids) == 0 or int(geo[i][4]) in cids:
+            cmap[cell_state_id_of(geo[i])] = i
+    missing = []
+    for k, (sid, row) in enumerate(id_states):
+        if len(cids) == 0 or sid[0] in cids:
+            if sid in cmap:
+                st[cmap[sid]] = row
+            else:
+                missing.append(k)
+    return st, missing

@@ -9,3 +9,4 @@ from .capi import (COLLECT_ALL, COLLECT_DISCHARGE, COLLECT_NONE, COLLECT_SNOW, C
 from .region_model import (GeoPointSources, HbvStackModel, HbvStackOptModel, PTGSKModel, PTGSKOptModel, PTHSKModel, PTHSKOptModel,  # noqa: F401
                            RegionEnvironment, RegionModel, TimeAxis, geo_cell_data_vector)
 from .calibration import Optimizer, TargetSpecification  # noqa: F401,E402
+from .state_io import StateIoHandler, StateWithIdVector, cell_state_id_of  # noqa: F401,E402

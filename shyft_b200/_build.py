@@ -46,10 +46,16 @@ def build_library(force=False, verbose=False, extra_flags=(), output=None):
     out = output or LIB
     if not force and not _stale(out, _sources()):
         return out
-    cmd = [nvcc_path()] + NVCC_FLAGS + list(extra_flags) + ["-shared", "-o", out, os.path.join(CSRC, "sb2_capi.cu")]
+    tmp = out + ".tmp%d" % os.getpid()   # written aside and renamed: a concurrent reader never sees a half-written library
+    cmd = [nvcc_path()] + NVCC_FLAGS + list(extra_flags) + ["-shared", "-o", tmp, os.path.join(CSRC, "sb2_capi.cu")]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
-    subprocess.check_call(cmd, cwd=CSRC)
+    try:
+        subprocess.check_call(cmd, cwd=CSRC)
+        os.replace(tmp, out)
+    finally:
+        if os.path.exists(tmp):
+            os.remove(tmp)
     return out
 
 

@@ -142,6 +142,7 @@ struct IdwPlan {  // neighbour lists of one variable (inverse_distance.h:160-203
     DevArray<double> dense, addc;  // [n_src][cells], [cells]
     DevArray<int32_t> ulist;       // station compaction of the dense apply kernel: [tiles][k_slots] union lists ...
     DevArray<uint8_t> ukc;         // ... and k-steps in use per tile (idw_union_plan_kernel)
+    int kc_max = 0;                // the widest union, in k-steps
 };
 
 struct BtkOps {  // operators of one valid-station subset
@@ -157,6 +158,13 @@ const int kStateSize[3] = {9, 3 + 2 * kSnowBins, 5 + 2 * kSnowBins};
 inline int grid_for(int64_t n, int block) { return int((n + block - 1) / block); }
 
 }  // namespace
+
+#ifndef SB2_DENSE_TILE_COMPACT
+#define SB2_DENSE_TILE_COMPACT 32  // steps staged per buffer, compacted inverse distance over 64-station rows
+#endif
+#ifndef SB2_DENSE_TILE_BTK
+#define SB2_DENSE_TILE_BTK 0       // 0 = the default of dense_tile_steps
+#endif
 
 struct sb2_model {
     int stack = 0, device = 0;
@@ -588,23 +596,32 @@ void run_idw(sb2_model* m, int var, int64_t first, int64_t n_steps, double* out)
             idw_union_plan_kernel<<<grid_for(n_tiles * 32, 128), 128, 0, m->stream>>>(m->n, nvp, pl.dense.p, 8 * ntile, ks * 4, pl.ulist.p, pl.ukc.p);
             CUDA_OK(cudaGetLastError());
             ++m->launches;
+            std::vector<uint8_t> h_kc(size_t(n_tiles), 0);  // the widest union decides how many k-steps the apply kernel carries
+            CUDA_OK(cudaMemcpyAsync(h_kc.data(), pl.ukc.p, h_kc.size(), cudaMemcpyDeviceToHost, m->stream));
+            CUDA_OK(cudaStreamSynchronize(m->stream));
+            pl.kc_max = 0;
+            for (uint8_t k : h_kc) pl.kc_max = std::max(pl.kc_max, int(k));
             pl.dense_valid = true;
         }
         const int nv = int(s.n_src);
         const double* v = s.d_values.p + first * s.n_src;
         const int use_tma = (nv % 2 == 0 && (reinterpret_cast<uintptr_t>(v) & 15) == 0) ? 1 : 0;
-#define SB2_DENSE(KS, NT)                                                                                                                 \
+#define SB2_DENSE(KS, NT, KROW, TS)                                                                                                       \
     do {                                                                                                                                  \
-        const int smem = 2 * (KS > 16 ? 32 : 64) * (KS * 4 + 4) * int(sizeof(double));                                                    \
-        auto kern = dense_apply_dmma_kernel<KS, NT, 0, true>;                                                                             \
+        const int smem = dense_smem_bytes(KROW, TS);                                                                                      \
+        auto kern = dense_apply_dmma_kernel<KS, NT, 0, true, KROW, TS>;                                                                   \
         CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                                           \
         kern<<<grid_for(m->n, 32 * NT), 128, smem, m->stream>>>(m->n, nullptr, nv, pl.dense.p, pl.addc.p, nullptr, v, s.n_src, nullptr,   \
-                                                                int(n_steps), m->d_active.p, out, pl.ulist.p, pl.ukc.p, use_tma);         \
+                                                                int(n_steps), m->d_active.p, out, pl.ulist.p, pl.ukc.p, use_tma,          \
+                                                                4 * (nv <= 16 ? 4 : (nv <= 32 ? 8 : (nv <= 64 ? 16 : 24))));              \
     } while (0)
-        if (nv <= 16) SB2_DENSE(4, 4);
-        else if (nv <= 32) SB2_DENSE(8, 4);
-        else if (nv <= 64) SB2_DENSE(16, 2);
-        else SB2_DENSE(24, 1);
+        if (nv <= 16) SB2_DENSE(4, 4, 4, 0);
+        else if (nv <= 32) SB2_DENSE(8, 4, 8, 0);
+        else if (nv <= 64) {  // rows of 64 stations, k-steps by the widest union of a 16-cell tile
+            if (pl.kc_max <= 4) SB2_DENSE(4, 2, 16, SB2_DENSE_TILE_COMPACT);
+            else if (pl.kc_max <= 8) SB2_DENSE(8, 2, 16, SB2_DENSE_TILE_COMPACT);
+            else SB2_DENSE(16, 2, 16, 0);
+        } else SB2_DENSE(24, 1, 24, 0);
 #undef SB2_DENSE
         CUDA_OK(cudaGetLastError());
         ++m->launches;
@@ -710,19 +727,19 @@ void run_btk(sb2_model* m, int64_t first, int64_t n_steps, double* out) {
         double* o = out + i * m->n;
         const double* pri = m->d_prior_gradient.p + first + i;
         const int use_tma = (nv % 2 == 0 && (reinterpret_cast<uintptr_t>(m->d_btk_resid.p) & 15) == 0) ? 1 : 0;
-#define SB2_BTK(KS, NT)                                                                                                                   \
+#define SB2_BTK(KS, NT, TS)                                                                                                               \
     do {                                                                                                                                  \
-        const int smem = 2 * (KS > 16 ? 32 : 64) * (KS * 4 + 4) * int(sizeof(double));                                                    \
-        auto kern = dense_apply_dmma_kernel<KS, NT, 1, false>;                                                                            \
+        const int smem = dense_smem_bytes(KS, TS);                                                                                        \
+        auto kern = dense_apply_dmma_kernel<KS, NT, 1, false, KS, TS>;                                                                    \
         CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                                           \
         kern<<<grid_for(m->n, 32 * NT), 128, smem, m->stream>>>(m->n, m->d_z.p, nv, op->omega.p, op->bm.p, m->d_btk_beta.p,               \
                                                                 m->d_btk_resid.p, nv, pri, int(seg), m->d_active.p, o, nullptr, nullptr,  \
-                                                                use_tma);                                                                 \
+                                                                use_tma, 0);                                                              \
     } while (0)
-        if (nv <= 16) SB2_BTK(4, 4);
-        else if (nv <= 32) SB2_BTK(8, 4);
-        else if (nv <= 64) SB2_BTK(16, 2);
-        else if (nv <= 96) SB2_BTK(24, 1);
+        if (nv <= 16) SB2_BTK(4, 4, 0);
+        else if (nv <= 32) SB2_BTK(8, 4, 0);
+        else if (nv <= 64) SB2_BTK(16, 2, SB2_DENSE_TILE_BTK);
+        else if (nv <= 96) SB2_BTK(24, 1, 0);
         else {  // more stations than the register-resident operator tile holds: one thread per cell, operator rows streamed
             const int tile = idw_tile_steps(nv);
             const size_t smem = size_t(tile) * nv * sizeof(double);
@@ -1288,6 +1305,81 @@ int sb2_adjust_q(sb2_model* m, double q_scale, const int64_t* cids, int n) {
             ++m->launches;
         }
         CUDA_OK(cudaGetLastError());
+        CUDA_OK(cudaStreamSynchronize(m->stream));
+    });
+}
+// ---- cell-identified state io: state_io_handler (api/api_state.h:93-142) -------------------------------------------------
+namespace {
+struct StateIdLess {
+    bool operator()(const sb2_cell_state_id& a, const sb2_cell_state_id& b) const {  // cell_state_id::operator< (:46-54)
+        if (a.cid != b.cid) return a.cid < b.cid;
+        if (a.x != b.x) return a.x < b.x;
+        if (a.y != b.y) return a.y < b.y;
+        return a.area < b.area;
+    }
+};
+sb2_cell_state_id cell_state_id_of(const sb2_geo_cell& g) {  // :58-60, the coordinates and the area go through int
+    return sb2_cell_state_id{g.catchment_id, int64_t(int(g.x)), int64_t(int(g.y)), int64_t(int(g.area))};
+}
+bool cid_in_scope(const int64_t* cids, int n, int64_t cid) { return n == 0 || std::find(cids, cids + n, cid) != cids + n; }
+}  // namespace
+
+int sb2_extract_state(const sb2_model* cm, const int64_t* cids, int n_cids, sb2_cell_state_id* ids, double* states, int64_t* n_out) {
+    return guarded_c(cm, [&] {
+        sb2_model* m = const_cast<sb2_model*>(cm);
+        if (!n_out || (n_cids > 0 && !cids)) throw Error("null argument");
+        std::vector<int64_t> cells;
+        for (int64_t i = 0; i < m->n; ++i)
+            if (cid_in_scope(cids, n_cids, m->geo[size_t(i)].catchment_id)) cells.push_back(i);
+        *n_out = int64_t(cells.size());
+        if (cells.empty()) return;
+        if (!ids || !states) throw Error("null output");
+        for (size_t k = 0; k < cells.size(); ++k) ids[k] = cell_state_id_of(m->geo[size_t(cells[k])]);
+        DevArray<int64_t> d_cells;
+        DevArray<double> d_out;
+        d_cells.upload(cells, m->stream);
+        const int64_t total = int64_t(cells.size()) * m->n_state;
+        d_out.resize(size_t(total));
+        state_gather_kernel<<<grid_for(total, 256), 256, 0, m->stream>>>(m->d_state.p, m->n, m->n_state, d_cells.p, int64_t(cells.size()), d_out.p);
+        CUDA_OK(cudaGetLastError());
+        ++m->launches;
+        CUDA_OK(cudaMemcpyAsync(states, d_out.p, size_t(total) * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+        CUDA_OK(cudaStreamSynchronize(m->stream));
+    });
+}
+int sb2_apply_state(sb2_model* m, int64_t n, const sb2_cell_state_id* ids, const double* states, const int64_t* cids, int n_cids, int64_t* missing,
+                    int64_t* n_missing) {
+    return guarded(m, [&] {
+        if (n < 0 || (n > 0 && (!ids || !states)) || (n_cids > 0 && !cids) || !n_missing) throw Error("null argument");
+        std::map<sb2_cell_state_id, int64_t, StateIdLess> cmap;  // cells in scope by id; a later cell with the same id replaces an earlier one
+        for (int64_t i = 0; i < m->n; ++i)
+            if (cid_in_scope(cids, n_cids, m->geo[size_t(i)].catchment_id)) cmap[cell_state_id_of(m->geo[size_t(i)])] = i;
+        std::map<int64_t, int64_t> row_of_cell;  // the last state applied to a cell wins, as in the sequential loop
+        *n_missing = 0;
+        for (int64_t k = 0; k < n; ++k) {
+            if (!cid_in_scope(cids, n_cids, ids[k].cid)) continue;
+            auto f = cmap.find(ids[k]);
+            if (f != cmap.end()) row_of_cell[f->second] = k;
+            else {
+                if (!missing) throw Error("null output");
+                missing[(*n_missing)++] = k;
+            }
+        }
+        if (row_of_cell.empty()) return;
+        std::vector<int64_t> cells;
+        std::vector<double> rows;
+        for (auto& kv : row_of_cell) {
+            cells.push_back(kv.first);
+            rows.insert(rows.end(), states + kv.second * m->n_state, states + (kv.second + 1) * m->n_state);
+        }
+        DevArray<int64_t> d_cells;
+        DevArray<double> d_rows;
+        d_cells.upload(cells, m->stream);
+        d_rows.upload(rows, m->stream);
+        const int64_t total = int64_t(rows.size());
+        state_scatter_kernel<<<grid_for(total, 256), 256, 0, m->stream>>>(m->d_state.p, m->n, m->n_state, d_cells.p, int64_t(cells.size()), d_rows.p);
+        CUDA_OK(cudaGetLastError());
+        ++m->launches;
         CUDA_OK(cudaStreamSynchronize(m->stream));
     });
 }

@@ -315,16 +315,22 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
     }
 }
 
-template <int KSTEPS, int NT, int MODE, bool COMPACT>
+// KSTEPS = k-steps (groups of four k-slots) the operator fragments cover; KROW = groups of four stations a staged row holds (the row
+// always carries every valid station; with COMPACT the k-slots index into it through the union list, so KSTEPS may be far smaller
+// than KROW -- fewer registers, more resident warps); TILE_STEPS = steps staged per buffer.
+__host__ __device__ constexpr int dense_tile_steps(int krow, int tile_steps) { return tile_steps > 0 ? tile_steps : (krow > 16 ? 32 : 64); }
+__host__ __device__ constexpr int dense_smem_bytes(int krow, int tile_steps) { return 2 * dense_tile_steps(krow, tile_steps) * (krow * 4 + 4) * 8; }
+template <int KSTEPS, int NT, int MODE, bool COMPACT, int KROW = KSTEPS, int TILE_STEPS = 0>
 __global__ void __launch_bounds__(128) dense_apply_dmma_kernel(int64_t n_cells, const double* __restrict__ cz, int n_valid,
                                                                const double* __restrict__ omega /* [n_valid][cells] */, const double* __restrict__ bm,
                                                                const double* __restrict__ beta /* [n_steps][2] */,
                                                                const double* __restrict__ resid /* [n_steps][row_stride] */, int64_t row_stride,
                                                                const double* __restrict__ prior_gradient /* [n_steps] */, int n_steps,
                                                                const uint8_t* __restrict__ active, double* __restrict__ out /* [n_steps][cells] */,
-                                                               const int32_t* __restrict__ ulist, const uint8_t* __restrict__ ukc, int use_tma) {
-    constexpr int KP = KSTEPS * 4 + 4;  // padded row stride (doubles), == 4 mod 16
-    constexpr int TILE = KSTEPS > 16 ? 32 : 64;  // steps of A staged per buffer
+                                                               const int32_t* __restrict__ ulist, const uint8_t* __restrict__ ukc, int use_tma,
+                                                               int ul_stride /* k-slots per tile in ulist */) {
+    constexpr int KP = KROW * 4 + 4;  // padded row stride (doubles), == 4 mod 16
+    constexpr int TILE = dense_tile_steps(KROW, TILE_STEPS);  // steps of A staged per buffer
     extern __shared__ __align__(16) double sr_dyn[];  // two buffers of TILE * KP doubles
     __shared__ double sbeta[2][TILE * 2];
     __shared__ double spri[2][TILE];
@@ -338,8 +344,8 @@ __global__ void __launch_bounds__(128) dense_apply_dmma_kernel(int64_t n_cells, 
     // ukc: k-steps in use) -- the zero weights of a 64-station operator are 3 k-steps out of 4.  Otherwise the slots are the stations.
     int ul[KSTEPS];
 #pragma unroll
-    for (int ks = 0; ks < KSTEPS; ++ks) ul[ks] = COMPACT ? ulist[tile * (KSTEPS * 4) + ks * 4 + q] : ks * 4 + q;
-    const int kc = COMPACT ? ukc[tile] : KSTEPS;
+    for (int ks = 0; ks < KSTEPS; ++ks) ul[ks] = COMPACT ? ulist[tile * ul_stride + ks * 4 + q] : ks * 4 + q;
+    const int kc = COMPACT ? min(int(ukc[tile]), KSTEPS) : KSTEPS;
     // B fragments: breg[nt][ks] = omega[cell cbase + nt*8 + g][station of slot ks*4 + q]
     double breg[NT][KSTEPS];
 #pragma unroll
@@ -636,6 +642,23 @@ __global__ void broadcast_source_kernel(int64_t n_cells, const double* __restric
     for (int i = 0; i < n_steps; ++i) out[(int64_t)i * n_cells + c] = src[i];
 }
 // state.adjust_q on the selected cells (region_model.h:831-837)
+// cell-identified state io (api/api_state.h:105-140): rows of the [n_state][n_cells] state <-> compact [k][n_state] records
+__global__ void state_gather_kernel(const double* __restrict__ state, int64_t n_cells, int n_state, const int64_t* __restrict__ cells, int64_t k,
+                                    double* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= k * n_state) return;
+    const int64_t r = i / n_state;
+    const int s = int(i - r * n_state);
+    out[i] = state[(int64_t)s * n_cells + cells[r]];
+}
+__global__ void state_scatter_kernel(double* __restrict__ state, int64_t n_cells, int n_state, const int64_t* __restrict__ cells, int64_t k,
+                                     const double* __restrict__ in) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= k * n_state) return;
+    const int64_t r = i / n_state;
+    const int s = int(i - r * n_state);
+    state[(int64_t)s * n_cells + cells[r]] = in[i];
+}
 __global__ void scale_selected_kernel(double* __restrict__ v, const uint8_t* __restrict__ sel, int64_t n, double scale) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n && sel[i]) v[i] *= scale;

@@ -143,6 +143,12 @@ class RegionModel:
         """basic_cell_statistics over this model's cells (model.statistics.discharge(cids), .temperature(cids), ...; api/api.h:179-420)"""
         return _stats().BasicCellStatistics(self)
 
+    @property
+    def state(self):
+        """state_io_handler of this model's cells (model.state.extract_state(cids) / .apply_state(states, cids); api/api_state.h:93-142)"""
+        from .state_io import StateIoHandler
+        return StateIoHandler(self)
+
     def size(self):
         return int(self._L.sb2_size(self._h))
 

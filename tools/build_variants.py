@@ -15,6 +15,8 @@ VARIANTS = {
     "noconst": ["-DSB2_RESP_SMEM_CONST=0"],
     # both
     "us32": ["-DSB2_UNIT_STEPS=32"], "us128": ["-DSB2_UNIT_STEPS=128"], "us256": ["-DSB2_UNIT_STEPS=256"], "nosplit": ["-DSB2_UNIT_STEPS=100000"],
+    # interpolation contraction: steps staged per buffer
+    "dc16": ["-DSB2_DENSE_TILE_COMPACT=16"], "dc64": ["-DSB2_DENSE_TILE_COMPACT=64"], "btk32": ["-DSB2_DENSE_TILE_BTK=32"], "btk16": ["-DSB2_DENSE_TILE_BTK=16"],
     "pf0": ["-DSB2_PREFETCH_AHEAD=0"], "pf2": ["-DSB2_PREFETCH_AHEAD=2"], "pf8": ["-DSB2_PREFETCH_AHEAD=8"],
 }
 out_dir = os.path.join(_build.ROOT, "build")
