@@ -1043,7 +1043,10 @@ const double* stat_ae_scale(sb2_model* m, int kind, DevArray<double>& buf) {
     if (kind != SB2_STAT_AE_POT_RATIO) return nullptr;
     sync_parameters(m);
     buf.resize(size_t(m->n));
-    stat_cell_ae_scale_kernel<<<grid_for(m->n, 256), 256, 0, m->stream>>>(m->n, m->d_pset.p, m->d_ptgsk_params.p, buf.p);
+    if (m->stack == SB2_PT_GS_K)
+        stat_cell_ae_scale_kernel<<<grid_for(m->n, 256), 256, 0, m->stream>>>(m->n, m->d_pset.p, m->d_ptgsk_params.p, buf.p);
+    else
+        stat_cell_ae_scale_hbv_kernel<<<grid_for(m->n, 256), 256, 0, m->stream>>>(m->n, m->d_pset.p, m->d_hbv_params.p, buf.p);
     CUDA_OK(cudaGetLastError());
     ++m->launches;
     return buf.p;
@@ -1053,7 +1056,7 @@ const double* stat_series_rows(const sb2_model* m, int kind, int series, int64_t
     const double* base = nullptr;
     int64_t first = 0, have = 0;
     if (kind == SB2_STAT_AE_POT_RATIO) {
-        if (m->stack != SB2_PT_GS_K) throw Error("pot_ratio statistics are defined for the pt_gs_k stack");
+        if (m->stack == SB2_HBV_STACK) throw Error("pot_ratio statistics need a Kirchner stack (pt_gs_k, pt_hs_k)");
         kind = SB2_STAT_STATE;
         series = SB2_S_KIRCHNER_DISCHARGE;
     }

@@ -9,6 +9,7 @@
 #pragma once
 #include <stdint.h>
 
+#include "sb2_hbv.cuh"
 #include "sb2_ptgsk.cuh"
 
 namespace sb2 {
@@ -56,6 +57,12 @@ __global__ void stat_gather_row_kernel(const double* __restrict__ row /* [n_cell
 // ae.ae_scale_factor of every cell's parameter set (region parameter or catchment override)
 __global__ void stat_cell_ae_scale_kernel(int64_t n_cells, const int32_t* __restrict__ pset, const PtgskParam* __restrict__ params,
                                           double* __restrict__ out) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n_cells) out[c] = params[pset[c]].ae_scale_factor;
+}
+
+__global__ void stat_cell_ae_scale_hbv_kernel(int64_t n_cells, const int32_t* __restrict__ pset, const HbvParam* __restrict__ params,
+                                              double* __restrict__ out) {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c < n_cells) out[c] = params[pset[c]].ae_scale_factor;
 }

@@ -418,7 +418,13 @@ class PTGSKOptModel(RegionModel):  # cell_discharge_response_t: discharge_collec
 
 
 class PTHSKModel(RegionModel):
+    """PTHSKModel with the statistics properties of shyft/api/pt_hs_k/__init__.py:13-19"""
     stack = PT_HS_K
+    hbv_snow_state = property(lambda self: _stats().HbvSnowStateStatistics(self))
+    hbv_snow_response = property(lambda self: _stats().HbvSnowResponseStatistics(self))
+    priestley_taylor_response = property(lambda self: _stats().PriestleyTaylorResponseStatistics(self))
+    actual_evaptranspiration_response = property(lambda self: _stats().ActualEvapotranspirationResponseStatistics(self))
+    kirchner_state = property(lambda self: _stats().KirchnerStateStatistics(self))
 
 
 class PTHSKOptModel(RegionModel):
@@ -427,9 +433,23 @@ class PTHSKOptModel(RegionModel):
 
 
 class HbvStackModel(RegionModel):
+    """HbvModel with the statistics properties of shyft/api/hbv_stack/__init__.py:13-19"""
     stack = HBV_STACK
+    hbv_snow_state = property(lambda self: _stats().HbvSnowStateStatistics(self))
+    hbv_snow_response = property(lambda self: _stats().HbvSnowResponseStatistics(self))
+    priestley_taylor_response = property(lambda self: _stats().PriestleyTaylorResponseStatistics(self))
+    hbv_actual_evaptranspiration_response = property(lambda self: _stats().HbvActualEvapotranspirationResponseStatistics(self))
+    soil_state = property(lambda self: _stats().HbvSoilStateStatistics(self))
+    soil_response = property(lambda self: _stats().HbvSoilResponseStatistics(self))
+    tank_state = property(lambda self: _stats().HbvTankStateStatistics(self))
+
+
+HbvModel, HbvOptModel = HbvStackModel, None  # the reference's Python names (shyft/api/hbv_stack/__init__.py); HbvOptModel bound below
 
 
 class HbvStackOptModel(RegionModel):
     stack = HBV_STACK
     default_collect = COLLECT_DISCHARGE
+
+
+HbvOptModel = HbvStackOptModel

@@ -137,3 +137,53 @@ class ActualEvapotranspirationResponseStatistics(_Reader):
 
 _attach(ActualEvapotranspirationResponseStatistics, "output", _RESPONSE, _resp("ae_output"), _AVERAGE)
 _attach(ActualEvapotranspirationResponseStatistics, "pot_ratio", _AE_POT_RATIO, lambda m: 0, _AVERAGE)  # api/api.h:1519-1564
+
+
+# ---- the HBV stacks (pt_hs_k, hbv_stack): shyft/api/pt_hs_k/__init__.py:13-19, shyft/api/hbv_stack/__init__.py:13-19 ----------
+class HbvSnowStateStatistics(_Reader):
+    """hbv_snow_cell_state_statistics (api/api.h:1049-1160): area-weighted swe and sca.  The per-bin series sp[i] / sw[i] are not
+    collected on the device."""
+
+    def _no_bins(self, *a, **k):
+        raise RuntimeError("hbv_snow per-bin state series (sp, sw) are not collected by shyft_b200")
+    sp = sw = sp_value = sw_value = _no_bins
+
+
+_attach(HbvSnowStateStatistics, "swe", _STATE, _state("snow_swe"), _AVERAGE)
+_attach(HbvSnowStateStatistics, "sca", _STATE, _state("snow_sca"), _AVERAGE)
+
+
+class HbvSnowResponseStatistics(_Reader):
+    """hbv_snow_cell_response_statistics (api/api.h:1162-1205): snow outflow and glacier melt, summed [m3/s]"""
+
+
+_attach(HbvSnowResponseStatistics, "outflow", _RESPONSE, _resp("snow_outflow"), _SUM)
+_attach(HbvSnowResponseStatistics, "glacier_melt", _RESPONSE, _resp("glacier_melt"), _SUM)
+
+
+class HbvSoilStateStatistics(_Reader):
+    """hbv_soil_cell_state_statistics (api/api.h:423-443): the reference names the sum of soil_moisture `discharge`"""
+
+
+_attach(HbvSoilStateStatistics, "discharge", _STATE, _state("soil_moisture"), _SUM)
+
+
+class HbvTankStateStatistics(_Reader):
+    """hbv_tank_cell_state_statistics (api/api.h:445-465): `discharge` = the sum of tank_uz (so marked "to be modified" in the reference)"""
+
+
+_attach(HbvTankStateStatistics, "discharge", _STATE, _state("tank_uz"), _SUM)
+
+
+class HbvSoilResponseStatistics(_Reader):
+    """hbv_soil_cell_response_statistics (api/api.h:1471-1491): area-weighted soil outflow"""
+
+
+_attach(HbvSoilResponseStatistics, "output", _RESPONSE, _resp("soil_outflow"), _AVERAGE)
+
+
+class HbvActualEvapotranspirationResponseStatistics(_Reader):
+    """hbv_actual_evapotranspiration_cell_response_statistics (api/api.h:1568-1590): area-weighted actual evapotranspiration"""
+
+
+_attach(HbvActualEvapotranspirationResponseStatistics, "output", _RESPONSE, _resp("ae_output"), _AVERAGE)

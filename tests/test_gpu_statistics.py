@@ -134,3 +134,57 @@ def test_statistics_of_an_uncollected_series_fail_loudly(sb):
     assert m.statistics.discharge([]).size == 24
     with pytest.raises(RuntimeError, match="not collected"):
         m.statistics._series(1, 6, [], 0, 1)   # ae_output
+
+
+@pytest.mark.parametrize("stack", [1, 2])
+def test_hbv_stack_readers_against_the_oracle_restatement(sb, oracle, stack):
+    """shyft/api/pt_hs_k/__init__.py:13-19 and shyft/api/hbv_stack/__init__.py:13-19: the per-method statistics of the HBV stacks"""
+    from fixtures import FORCING, HBV_DEFAULT, PTHSK_DEFAULT, geo_matrix
+    from shyft_b200 import synthetic
+    from shyft_b200.statistics import CELL_IX
+    n, T = 900, 120
+    geo, ta, env = synthetic.make_region(n, T, 9, config_index=13, cells_per_catchment=128, start=1420070400)[:3]
+    geo["area"] = np.random.default_rng(4).uniform(0.5e6, 2.0e6, n)
+    par = PTHSK_DEFAULT if stack == 1 else HBV_DEFAULT
+    m = (sb.PTHSKModel if stack == 1 else sb.HbvStackModel)(geo, par)
+    assert m.run_interpolation(sb.InterpolationParameter(), ta, env)
+    st0 = synthetic.default_state(stack, n)
+    m.set_states(st0)
+    m.set_state_collection(-1, True)
+    m.run_cells()
+    cids, area = geo["catchment_id"], geo["area"]
+    sel = [int(cids[0]), int(cids[-1])]
+    some_cells = [0, 450, 899]
+    tol = dict(rtol=1e-12, atol=1e-300)
+    run = oracle.pthsk_run_cells if stack == 1 else oracle.hbv_stack_run_cells
+    want = run(geo_matrix(geo), par, {k: m.cell_forcing(k) for k in FORCING}, st0, ta.start * 10**6, ta.delta_t * 10**6, ncore=4)
+    r = 1e-9   # the series themselves carry the step kernels' parity tolerance
+    assert np.allclose(m.statistics.discharge(sel), oracle.sum_catchment_feature(want["avg_discharge"], cids, sel), rtol=r)
+    assert np.allclose(m.hbv_snow_response.outflow(sel), oracle.sum_catchment_feature(want["snow_outflow"], cids, sel), rtol=r)
+    assert np.allclose(m.hbv_snow_response.glacier_melt([]), oracle.sum_catchment_feature(want["glacier_melt"], cids, []), rtol=r, atol=1e-300)
+    assert np.allclose(m.priestley_taylor_response.output(sel), oracle.average_catchment_feature(want["pe_output"], area, cids, sel), rtol=r)
+    assert m.hbv_snow_response.outflow_value(some_cells, 30, ix_type=CELL_IX) == pytest.approx(
+        oracle.sum_catchment_feature_value(want["snow_outflow"], cids, some_cells, 30, oracle.CELL_IX), rel=r)
+    swe, sca = m.state_series("snow_swe"), m.state_series("snow_sca")
+    assert swe.shape == (T + 1, n) and np.nanmax(swe) > 1.0
+    assert np.allclose(m.hbv_snow_state.swe(sel), oracle.average_catchment_feature(swe, area, cids, sel), **tol)
+    assert np.allclose(m.hbv_snow_state.sca([]), oracle.average_catchment_feature(sca, area, cids, []), **tol)
+    assert np.array_equal(m.hbv_snow_state.swe(sel, 7), oracle.catchment_feature(swe, cids, sel, 7))
+    assert m.hbv_snow_state.sca_value(sel, 50) == pytest.approx(oracle.average_catchment_feature_value(sca, area, cids, sel, 50), rel=1e-12)
+    with pytest.raises(RuntimeError, match="not collected"):
+        m.hbv_snow_state.sp(sel)
+    if stack == 1:
+        kd = m.state_series("kirchner_discharge")
+        assert np.allclose(m.kirchner_state.discharge(sel), oracle.sum_catchment_feature(kd, cids, sel), **tol)
+        assert np.allclose(m.actual_evaptranspiration_response.output(sel), oracle.average_catchment_feature(want["ae_output"], area, cids, sel), rtol=r)
+        pr = oracle.ae_pot_ratio(kd, area, par[3])
+        assert np.allclose(m.actual_evaptranspiration_response.pot_ratio(sel), oracle.average_catchment_feature(pr, area, cids, sel), **tol)
+    else:
+        sm, uz = m.state_series("soil_moisture"), m.state_series("tank_uz")
+        assert np.allclose(m.soil_state.discharge(sel), oracle.sum_catchment_feature(sm, cids, sel), **tol)
+        assert np.allclose(m.tank_state.discharge([]), oracle.sum_catchment_feature(uz, cids, []), **tol)
+        assert m.tank_state.discharge_value(sel, 3) == pytest.approx(oracle.sum_catchment_feature_value(uz, cids, sel, 3), rel=1e-12)
+        assert np.allclose(m.soil_response.output(sel), oracle.average_catchment_feature(want["soil_outflow"], area, cids, sel), rtol=r)
+        assert np.allclose(m.hbv_actual_evaptranspiration_response.output(sel), oracle.average_catchment_feature(want["ae_output"], area, cids, sel), rtol=r)
+        with pytest.raises(RuntimeError, match="Kirchner stack"):
+            m.statistics._series(3, 0, [], 0, 1, 0, 1)   # pot_ratio
