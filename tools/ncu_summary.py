@@ -35,20 +35,18 @@ with open(out, "w") as f:
     f.write(f"\n# hot source lines (first captured launch): % of warp-stall samples, % of executed warp instructions\n")
     for a in sorted(agg, key=lambda a: -a[3])[:25]:
         f.write(f"{a[0]:16s}:{a[1]:<4d} {100 * a[3] / tot_s:5.1f}% {100 * a[4] / tot_i:5.1f}%  {a[2]}\n")
-    sass = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
-    rs = list(csv.reader(io.StringIO(sass)))
-    if len(rs) > 2:
-        h2 = rs[1]
-        idx = {h: i for i, h in enumerate(h2)}
-        for r in rs[2:]:
-            if len(r) < len(h2):
-                continue
-            for h in h2:
-                if h.startswith("stall_") and "Not Issued" not in h:
-                    try:
-                        stall[h] += int(r[idx[h]])
-                    except ValueError:
-                        pass
-        s = sum(stall.values()) or 1
-        f.write("\n# warp stall reasons (all samples)\n" + "  ".join(f"{k} {100 * v / s:.1f}%" for k, v in stall.most_common(8)) + "\n")
+    # warp stall reasons per captured launch, from the raw page's PC-sampling counters (smsp__pcsamp_warps_issue_stalled_*)
+    pre = "smsp__pcsamp_warps_issue_stalled_"
+    cols = [(i, h[len(pre):]) for i, h in enumerate(hdr) if h.startswith(pre) and not h.endswith("_not_issued")]
+    f.write("\n# warp stall reasons, % of PC samples, one line per captured launch\n")
+    for r in rows[2:]:
+        vals = []
+        for i, name in cols:
+            try:
+                vals.append((float(r[i]), name))
+            except ValueError:
+                pass
+        tot = sum(v for v, _ in vals) or 1.0
+        name_i = hdr.index("Kernel Name")
+        f.write(r[name_i].split("(")[0][-40:] + ": " + "  ".join(f"{n} {100 * v / tot:.1f}%" for v, n in sorted(vals, reverse=True)[:8]) + "\n")
 print("wrote", out)
