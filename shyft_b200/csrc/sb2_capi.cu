@@ -619,7 +619,10 @@ void run_idw(sb2_model* m, int var, int64_t first, int64_t n_steps, double* out)
         else if (nv <= 32) SB2_DENSE(8, 4, 8, 0);
         else if (nv <= 64) {  // rows of 64 stations, k-steps by the widest union of a 16-cell tile
             if (pl.kc_max <= 4) SB2_DENSE(4, 2, 16, SB2_DENSE_TILE_COMPACT);
+            else if (pl.kc_max <= 6) SB2_DENSE(6, 2, 16, SB2_DENSE_TILE_COMPACT);
             else if (pl.kc_max <= 8) SB2_DENSE(8, 2, 16, SB2_DENSE_TILE_COMPACT);
+            else if (pl.kc_max <= 10) SB2_DENSE(10, 2, 16, SB2_DENSE_TILE_COMPACT);
+            else if (pl.kc_max <= 12) SB2_DENSE(12, 2, 16, SB2_DENSE_TILE_COMPACT);
             else SB2_DENSE(16, 2, 16, 0);
         } else SB2_DENSE(24, 1, 24, 0);
 #undef SB2_DENSE

@@ -137,6 +137,9 @@ __device__ __forceinline__ double gs_calc_q(double a, double b, double z, double
     return a * b * gamma_p(a + 1.0, x, lg_a1) + z * (1.0 - gamma_p(a, x, lg_a));
 }
 
+#ifndef SB2_LWC_FLAT
+#define SB2_LWC_FLAT 0  // Brent objective with log / exp expanded in place (0: the shared out-of-line copies)
+#endif
 // corr_lwc = boost brent_find_minima(f, 0, z1, bits=12, 60 iterations), gamma_snow.h:214-227
 __device__ __noinline__ double gs_corr_lwc(double z1, double a1, double b1, double a2, double b2) {
     const double Q1 = gs_calc_q(a1, b1, z1, sb_lgamma(a1), sb_lgamma(a1 + 1.0));
@@ -151,8 +154,13 @@ __device__ __noinline__ double gs_corr_lwc(double z1, double a1, double b1, doub
         double p1 = 0.0, p0 = 0.0;  // P(a2+1, x), P(a2, x); gamma_p(): 0 unless x > 0, 1 at x = inf
         if (x == inf_()) p1 = p0 = 1.0;
         else if (x > 0.0) {
+#if SB2_LWC_FLAT
             const double lx = sb_log_flat(x);
             const double pre1 = sb_exp_flat((a2 + 1.0) * lx - x - lg_a21), pre0 = sb_exp_flat(a2 * lx - x - lg_a2);
+#else
+            const double lx = sb_log(x);
+            const double pre1 = sb_exp((a2 + 1.0) * lx - x - lg_a21), pre0 = sb_exp(a2 * lx - x - lg_a2);
+#endif
             p1 = gamma_p_with_prefix(a2 + 1.0, x, pre1);
             p0 = gamma_p_with_prefix(a2, x, pre0);
         }
@@ -346,6 +354,20 @@ __device__ __forceinline__ void gs_energy_terms(const PtgskParam& p, double BB0,
     else tadd = turb * (T - sst + 1.7 * (vapour_pressure - 6.132 * (FLAT ? sb_exp_flat(0.103 * T - 0.186) : sb_exp(0.103 * T - 0.186)))) - 0.98 * sigma * sb_pow4(sst + 273.15);
 }
 
+// Division sites of the step body: in line (default) or through one shared out-of-line copy (SB2_GS_DIV_CALL=1, a smaller per-step code
+// footprint for the instruction-fetch-bound snow kernel; same IEEE quotient either way).
+#ifndef SB2_GS_DIV_CALL
+#define SB2_GS_DIV_CALL 0
+#endif
+__device__ __noinline__ double sb_div_call(double a, double b) { return a / b; }
+#if SB2_GS_DIV_CALL
+#define GS_DIV(a, b) sb_div_call((a), (b))
+#else
+#define GS_DIV(a, b) ((a) / (b))
+#endif
+#ifndef SB2_SNOW_FLAT
+#define SB2_SNOW_FLAT 0  // end-of-step calc_snow_state of the snow kernel with exp / log / incomplete gamma expanded in place (0: the shared out-of-line copy)
+#endif
 // gamma_snow::calculator::step, gamma_snow.h:291-493, given the two forcing-only addends (lw, tadd) of gs_energy_terms
 template <bool FLAT = false>
 __device__ __forceinline__ void gs_step_core(GsState& s, GsCache& cache, double& r_sca, double& r_storage, double& r_outflow, const PtgskParam& p, int doy,
@@ -381,7 +403,7 @@ __device__ __forceinline__ void gs_step_core(GsState& s, GsCache& cache, double&
     const double snow_cv = p.snow_cv + forest_fraction * p.snow_cv_forest_factor + altitude * p.snow_cv_altitude_factor;
     const double albedo_range = max_albedo - min_albedo;
 
-    if (snow > tol) albedo += snow * albedo_range / p.snowfall_reset_depth;
+    if (snow > tol) albedo += GS_DIV(snow * albedo_range, p.snowfall_reset_depth);
     else {
         if (T < 0.0) albedo -= p.slow_albedo_decay_step;
         else albedo = min_albedo + p.fast_albedo_decay_step * (albedo - min_albedo);
@@ -397,7 +419,7 @@ __device__ __forceinline__ void gs_step_core(GsState& s, GsCache& cache, double&
     if (p.calculate_iso_pot_energy) {
         const double turb = p.wind_scale * wind_speed + p.wind_const;
         const double iso_effect = effect - BB0 + turb * (T + 1.7 * (gs_vapour_pressure(T, rel_hum) - 6.12));
-        iso_pot_energy += iso_effect * dt_seconds / melt_heat;
+        iso_pot_energy += GS_DIV(iso_effect * dt_seconds, melt_heat);
     }
 
     const double sst = dmin(0.0, 1.16 * T - 2.09);
@@ -410,9 +432,9 @@ __device__ __forceinline__ void gs_step_core(GsState& s, GsCache& cache, double&
     double energy = effect * dt_seconds;
     if (delta_sh > 0.0) energy -= delta_sh;
 
-    double potential_melt = dmax(0.0, energy / melt_heat);
+    double potential_melt = dmax(0.0, GS_DIV(energy, melt_heat));
 
-    double sdc_scale = sdc_melt_mean / alpha;
+    double sdc_scale = GS_DIV(sdc_melt_mean, alpha);
     const double y0 = p.initial_bare_ground_fraction;
     if (gs_cache_hit(cache, alpha, sdc_scale, acc_melt, lwc, temp_swe)) {
         storage = SB2_CK_STORAGE(cache);
@@ -428,12 +450,12 @@ __device__ __forceinline__ void gs_step_core(GsState& s, GsCache& cache, double&
         else {
             const double alpha_prev = alpha;
             const double sdc_scale_prev = sdc_scale;
-            const double sdc_snow = snow / (1.0 - y0);
-            alpha = (sdc_melt_mean * alpha + sdc_snow / (snow_cv * snow_cv)) / (sdc_snow + sdc_melt_mean);
+            const double sdc_snow = GS_DIV(snow, 1.0 - y0);
+            alpha = GS_DIV(sdc_melt_mean * alpha + GS_DIV(sdc_snow, snow_cv * snow_cv), sdc_snow + sdc_melt_mean);
             sdc_melt_mean += sdc_snow;
-            sdc_scale = sdc_melt_mean / alpha;
+            sdc_scale = GS_DIV(sdc_melt_mean, alpha);
             if (lwc > 0.0 && sdc_snow > 0.01 * sdc_melt_mean) {
-                double z1 = lwc / p.max_water;
+                double z1 = GS_DIV(lwc, p.max_water);
                 z1 = gs_corr_lwc(z1, alpha_prev, sdc_scale_prev > 0.0 ? sdc_scale_prev : sdc_scale, alpha, sdc_scale);
                 lwc = z1 * p.max_water;
                 gs_calc_snow_state(alpha, sdc_scale, y0, acc_melt, lwc, p.max_water, temp_swe, storage, sca, SB2_CK_LGKEY(cache), SB2_CK_LGVAL(cache));
@@ -447,9 +469,9 @@ __device__ __forceinline__ void gs_step_core(GsState& s, GsCache& cache, double&
         } else if (potential_melt > 0.0) {
             sdc_melt_mean -= potential_melt;
             lwc += potential_melt;
-            alpha = dmax(0.1, sdc_melt_mean / sdc_scale);
-            if (alpha > 1.0 / (snow_cv * snow_cv)) alpha = 1.0 / (snow_cv * snow_cv);
-            sdc_scale = sdc_melt_mean / alpha;
+            alpha = dmax(0.1, GS_DIV(sdc_melt_mean, sdc_scale));
+            if (alpha > GS_DIV(1.0, snow_cv * snow_cv)) alpha = GS_DIV(1.0, snow_cv * snow_cv);
+            sdc_scale = GS_DIV(sdc_melt_mean, alpha);
         }
     } else {  // :452-470
         temp_swe += div_pos(snow, 1.0 - y0);  // y0 < 1
@@ -472,7 +494,7 @@ __device__ __forceinline__ void gs_step_core(GsState& s, GsCache& cache, double&
             if (storage < dmax(0.2, 2 * temp_swe) || storage < 0.2 * rain) {
                 storage += snow;
                 gs_reset_snow_pack(sca, lwc, alpha, sdc_melt_mean, acc_melt, temp_swe, storage, p);
-                sdc_scale = sdc_melt_mean / alpha;
+                sdc_scale = GS_DIV(sdc_melt_mean, alpha);
             }
         }
     }
@@ -892,7 +914,7 @@ __global__ void __launch_bounds__(SB2_BLOCK_B, SB2_MINBLOCKS_B) ptgsk_snow_kerne
         double wind = 0.0, rel_hum = 0.0;
         if (iso) { wind = a.f[3][o]; rel_hum = a.f[4][o]; }
         double sca, storage, outflow;
-        gs_step_core<true>(gs, cache, sca, storage, outflow, p, a.day_of_year[step], a.sec_of_year[step], a.dt_seconds, a.dt_us, a.bb0, temp, rad, prec,
+        gs_step_core<(SB2_SNOW_FLAT != 0)>(gs, cache, sca, storage, outflow, p, a.day_of_year[step], a.sec_of_year[step], a.dt_seconds, a.dt_us, a.bb0, temp, rad, prec,
                            lw, tadd, wind, rel_hum, forest_fraction, altitude);
         s_outflow[o] = outflow;
         s_sca[o] = sca;

@@ -33,7 +33,8 @@ class StateWithIdVector:
 
     def __init__(self, ids, states):
         self.ids = np.ascontiguousarray(ids, dtype=ID_DTYPE)
-        self.states = np.ascontiguousarray(states, dtype=np.float64).reshape(self.ids.shape[0], -1)
+        st = np.ascontiguousarray(states, dtype=np.float64)
+        self.states = st if st.ndim == 2 else st.reshape(self.ids.shape[0], -1)
 
     def __len__(self):
         return int(self.ids.shape[0])

@@ -17,6 +17,9 @@ VARIANTS = {
     "us32": ["-DSB2_UNIT_STEPS=32"], "us128": ["-DSB2_UNIT_STEPS=128"], "us256": ["-DSB2_UNIT_STEPS=256"], "nosplit": ["-DSB2_UNIT_STEPS=100000"],
     # interpolation contraction: steps staged per buffer
     "dc16": ["-DSB2_DENSE_TILE_COMPACT=16"], "dc64": ["-DSB2_DENSE_TILE_COMPACT=64"], "btk32": ["-DSB2_DENSE_TILE_BTK=32"], "btk16": ["-DSB2_DENSE_TILE_BTK=16"],
+    # snow kernel code footprint (instruction-fetch bound, profiles/README.md)
+    "snowflat": ["-DSB2_SNOW_FLAT=1"], "lwcflat": ["-DSB2_LWC_FLAT=1"], "us32b": ["-DSB2_UNIT_STEPS=32"], "us128b": ["-DSB2_UNIT_STEPS=128"],
+    "divcall": ["-DSB2_GS_DIV_CALL=1"], "snowcall": ["-DSB2_SNOW_FLAT=0"], "smallsnow": ["-DSB2_GS_DIV_CALL=1", "-DSB2_SNOW_FLAT=0"],
     "pf0": ["-DSB2_PREFETCH_AHEAD=0"], "pf2": ["-DSB2_PREFETCH_AHEAD=2"], "pf8": ["-DSB2_PREFETCH_AHEAD=8"],
 }
 out_dir = os.path.join(_build.ROOT, "build")
