@@ -31,7 +31,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 BYTES_PER_CELL_STEP = 56  # 5 forcings read + avg_discharge, charge_m3s written
-TRAFFIC_PER_CELL_STEP = 179.0  # ncu dram__bytes_read+write of the three kernels / cell-steps of the captured window (9.15 GB / 51.2 M)
+TRAFFIC_PER_CELL_STEP = 178.0  # ncu dram__bytes_read+write of the three kernels / cell-steps of the captured window (9.12 GB / 51.2 M)
 PTGSK_DEFAULT = [-2.439, 0.966, -0.10, 1.5, -0.5, 2.0, 0.1, 1.0, 5.0, 5.0, 30.0, 0.9, 0.6, 5.0, 0.4, 0.4, 1.0, 0.0, 0.0, 0.2, 1.26, 0.04, 100.0, 0.0,
                  6.0, 1.0, 7.0, 0.0, 221.0, 0.0, 1.0]
 
@@ -329,15 +329,15 @@ def main():
             "clocks": clocks,
             # run_cells of one window = the three kernels of the phase pipeline, launched back to back; "achieved" divides the
             # ALGORITHMIC bytes (56 B per cell-step) by their summed CUDA-event time.  "traffic" is the DRAM
-            # traffic ncu measures for one 512-step window of 100 000 cells (profiles/ncu_pipeline_r01_j_final_winter_window.txt: 3 x the
+            # traffic ncu measures for one 512-step window of 100 000 cells (profiles/ncu_pipeline_r01_m_winter_window.txt: 3 x the
             # algorithmic bytes, because the phases hand five scratch arrays to each other through HBM -- the stack is fp64-bound).
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": TRAFFIC_PER_CELL_STEP * n * min(args.window, T),
                          "kernel": "run_cells window = ptgsk_forcing_terms_kernel + ptgsk_snow_kernel<0> + ptgsk_response_kernel<1>",
                          "launches_per_step": n_windows, "avg_launch_ms": k_ms / n_windows,
                          "algorithmic_bytes_per_launch": BYTES_PER_CELL_STEP * n * min(args.window, T), "peak_source": peak_src,
-                         "binding_roof": {"pipe": "fp64", "pipe_active_pct_ncu": {"forcing_terms": 70.2, "snow": 42.7, "response": 70.1},
-                                          "source": "profiles/ncu_pipeline_r01_j_final_winter_window.txt (sm__pipe_fp64_cycles_active, winter window)"},
+                         "binding_roof": {"pipe": "fp64", "pipe_active_pct_ncu": {"forcing_terms": 70.2, "snow": 54.6, "response": 70.1},
+                                          "source": "profiles/ncu_pipeline_r01_m_winter_window.txt (sm__pipe_fp64_cycles_active, winter window)"},
                          "note": "fp64-compute bound, not HBM bound: 16-25 exp/log, an adaptive ODE step and incomplete gamma functions "
                                  "per cell-step against 56 bytes (DESIGN.md section 3, SURVEY H3)"},
         }
