@@ -220,6 +220,10 @@ def main():
         setattr(env_pinned, name, (xyz, v))
     st_pinned, t = pinned_copy(st0)
     keep.append(t)
+    q_pinned, t = pinned_copy(np.zeros((T, m.number_of_catchments())))   # results of the end-to-end leg land in pinned memory too
+    keep.append(t)
+    s_pinned, t = pinned_copy(np.zeros_like(st0))
+    keep.append(t)
     h2d = sum(getattr(env, k)[1].nbytes + getattr(env, k)[0].nbytes for k in sb.capi.FORCING_NAMES) + st0.nbytes
     d2h = T * m.number_of_catchments() * 8 + st0.nbytes
 
@@ -254,7 +258,7 @@ def main():
         m.set_states(st_pinned); lap("set_states_h2d")
         m.run_windowed(ip, window_steps=args.window); lap("run_windowed")
         reduce_catchments(); lap("all_reduce")
-        out = m.catchment_discharges(), m.get_states(); lap("results_d2h")
+        out = m.catchment_discharges(out=q_pinned), m.get_states(out=s_pinned); lap("results_d2h")
         return out
 
     def timed(fn, k):

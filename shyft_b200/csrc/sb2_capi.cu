@@ -219,7 +219,7 @@ struct sb2_model {
     DevArray<double> d_scr[5];  // pt_gs_k phase pipeline scratch [partial_steps][n] (sb2_ptgsk.cuh)
     DevArray<int> d_tickets;    // response kernel time split: [0] ticket counter, [1..] finished slices per cell group
     int partial_steps = 0;
-    DevArray<int> d_error_flag;
+    DevArray<int> d_error_flag, d_scan_flag;
     // routing (core/routing.h)
     std::vector<double> rivers;  // [n][6] id downstream distance velocity alpha beta
     std::unique_ptr<RoutingPlan> route;      // built on first use, dropped when the network or the parameters change
@@ -1482,14 +1482,20 @@ int sb2_set_sources(sb2_model* m, int var, int64_t n_src, const double* xyz, con
         const size_t count = size_t(m->T) * n_src;
         s.d_values.upload(values, count, m->stream);
         // average_accessor of a stair-case source on the model axis (time_series.h:202-310,2033-2072)
+        // ... which also reports whether any value is NaN / inf: the scan of the values runs on the device, not over the host buffer
+        m->d_scan_flag.ensure(1);
+        CUDA_OK(cudaMemsetAsync(m->d_scan_flag.p, 0, sizeof(int), m->stream));
         average_accessor_same_axis_kernel<<<std::min<int64_t>(grid_for(count, 256), 148 * 16), 256, 0, m->stream>>>(s.d_values.p, int64_t(count),
-                                                                                                             double(m->dt) / 1e6);
+                                                                                                             double(m->dt) / 1e6, m->d_scan_flag.p);
         CUDA_OK(cudaGetLastError());
         ++m->launches;
-        s.has_nonfinite = false;
-        for (size_t i = 0; i < count && !s.has_nonfinite; ++i) s.has_nonfinite = !std::isfinite(values[i]);
-        if (var == SB2_TEMPERATURE) s.h_values.assign(values, values + count);
+        int flag = 0;
+        CUDA_OK(cudaMemcpyAsync(&flag, m->d_scan_flag.p, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
         CUDA_OK(cudaStreamSynchronize(m->stream));
+        s.has_nonfinite = flag != 0;
+        // the host copy serves the valid-station bookkeeping of Bayesian kriging (run_btk), needed only when stations drop out
+        if (var == SB2_TEMPERATURE && s.has_nonfinite) s.h_values.assign(values, values + count);
+        else s.h_values.clear();
     });
 }
 int sb2_set_sources_on_axis(sb2_model* m, int var, int64_t n_src, const double* xyz, int64_t n_points, const int64_t* t_us, int64_t t_end_us,

@@ -524,11 +524,15 @@ __global__ void fill_kernel(double* __restrict__ p, int64_t n, double v) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
 }
 // identity resampling of average_accessor for a stair-case source on the model axis (time_series.h:202-310): (dt_s*v)/dt_s
-__global__ void average_accessor_same_axis_kernel(double* __restrict__ p, int64_t n, double dt_seconds) {
+__global__ void average_accessor_same_axis_kernel(double* __restrict__ p, int64_t n, double dt_seconds, int* __restrict__ nonfinite) {
+    bool bad = false;  // any NaN / inf among the values: the caller keeps a host copy of such series (validity bookkeeping), of no others
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const double v = p[i];
-        p[i] = isfinite(v) ? (dt_seconds * v) / dt_seconds : nan("");
+        const bool fin = isfinite(v);
+        bad |= !fin;
+        p[i] = fin ? (dt_seconds * v) / dt_seconds : nan("");
     }
+    if (bad) atomicOr(nonfinite, 1);
 }
 // average_accessor<point_ts, fixed_dt>::value(i) for sources on their own point axis (core/time_series.h:2033-2072 over
 // accumulate_value :202-291): the true average of the source over every model step -- stair-case (POINT_AVERAGE_VALUE) or linear

@@ -212,10 +212,17 @@ class RegionModel:
             raise RuntimeError("state rows must have state_size values")
         self._ck(self._L.sb2_set_states(self._h, dptr(s), C.c_int64(s.shape[0])))
 
-    def get_states(self):
-        s = np.zeros((self.size(), self.state_size))
+    def get_states(self, out=None):
+        """-> [cell][state_size]; `out` = a caller-owned C-contiguous float64 array of that shape to fill instead (e.g. pinned host memory)"""
+        s = np.zeros((self.size(), self.state_size)) if out is None else self._checked_out(out, (self.size(), self.state_size))
         self._ck(self._L.sb2_get_states(self._h, dptr(s), C.c_int64(s.shape[0])))
         return s
+
+    @staticmethod
+    def _checked_out(out, shape):
+        if not (isinstance(out, np.ndarray) and out.dtype == np.float64 and out.flags.c_contiguous and out.shape == tuple(shape)):
+            raise RuntimeError(f"out must be a C-contiguous float64 array of shape {tuple(shape)}")
+        return out
 
     current_state = property(lambda self: self.get_states())
 
@@ -347,9 +354,10 @@ class RegionModel:
                                               C.c_int64(n_points), dptr(out), C.c_int(layout)))
         return out
 
-    def catchment_discharges(self, start_step=0, n_steps=None):
+    def catchment_discharges(self, start_step=0, n_steps=None, out=None):
         n_steps = self.time_axis.n - start_step if n_steps is None else n_steps
-        out = np.zeros((n_steps, self.number_of_catchments()))
+        shape = (n_steps, self.number_of_catchments())
+        out = np.zeros(shape) if out is None else self._checked_out(out, shape)
         self._ck(self._L.sb2_catchment_discharges(self._h, C.c_int64(start_step), C.c_int64(n_steps), dptr(out)))
         return out
 
