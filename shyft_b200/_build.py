@@ -70,3 +70,29 @@ def build_host_shim_test(force=False):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "include"), "-o", out, src, "-L", HERE, "-lshyft_b200",
                                "-Wl,-rpath," + HERE, "-Wl,-rpath,$ORIGIN/../../shyft_b200"])
     return out
+
+
+def pybind_module_path():
+    import sysconfig
+    return os.path.join(HERE, "_shyft_b200_cpp" + sysconfig.get_config_var("EXT_SUFFIX"))
+
+
+def build_pybind_module(force=False):
+    """g++ build of the pybind11 module over the C++ shim (shyft_b200/pybind/module.cpp -> shyft_b200/_shyft_b200_cpp.*.so)."""
+    import sysconfig
+
+    import pybind11
+    src = os.path.join(HERE, "pybind", "module.cpp")
+    out = pybind_module_path()
+    deps = [src, os.path.join(ROOT, "include", "shyft_b200.h"), os.path.join(ROOT, "include", "shyft_b200", "region_model.hpp"), LIB]
+    if force or _stale(out, deps):
+        tmp = out + ".tmp%d" % os.getpid()
+        try:
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-fvisibility=hidden", "-I", pybind11.get_include(),
+                                   "-I", sysconfig.get_paths()["include"], "-I", os.path.join(ROOT, "include"), "-o", tmp, src,
+                                   "-L", HERE, "-lshyft_b200", "-Wl,-rpath,$ORIGIN"])
+            os.replace(tmp, out)
+        finally:
+            if os.path.exists(tmp):
+                os.remove(tmp)
+    return out
