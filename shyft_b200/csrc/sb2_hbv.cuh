@@ -230,8 +230,18 @@ __device__ __forceinline__ bool hbv_snow_step(double (&sp)[HBV_NB], double (&sw)
     return ok;
 }
 
+// launch bounds = (threads the register allocation assumes per block, blocks per SM it aims at); blocks are one warp (SB2_BLOCK), so
+// (128, 4) = 128 registers -> 16 resident warps, (128, 5) = 96 registers -> 20.  Measured on 400 000 cells (tools/tune_c3.sh):
+// pt_hs_k 87.8 ms at the compiler's 146 registers, 78.4 at 128, 79.4 at 96, 89.7 at 80; hbv_stack 49.1 at 122, 49.5 at 128, 46.2 at 96,
+// 47.2 at 80.
+#ifndef SB2_HBV_MINBLOCKS_K
+#define SB2_HBV_MINBLOCKS_K 4   // pt_hs_k (Kirchner)
+#endif
+#ifndef SB2_HBV_MINBLOCKS_S
+#define SB2_HBV_MINBLOCKS_S 5   // hbv_stack (soil + tank)
+#endif
 template <bool HBV_STACK>
-__global__ void __launch_bounds__(128) hbv_run_kernel(const HbvRunArgs a) {
+__global__ void __launch_bounds__(128, (HBV_STACK ? SB2_HBV_MINBLOCKS_S : SB2_HBV_MINBLOCKS_K)) hbv_run_kernel(const HbvRunArgs a) {
     constexpr int NS = HBV_STACK ? 5 + 2 * HBV_NB : 3 + 2 * HBV_NB;
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool in_range = c < a.n_cells;

@@ -20,6 +20,8 @@ VARIANTS = {
     # snow kernel code footprint (instruction-fetch bound, profiles/README.md)
     "snowflat": ["-DSB2_SNOW_FLAT=1"], "lwcflat": ["-DSB2_LWC_FLAT=1"], "us32b": ["-DSB2_UNIT_STEPS=32"], "us128b": ["-DSB2_UNIT_STEPS=128"],
     "divcall": ["-DSB2_GS_DIV_CALL=1"], "snowcall": ["-DSB2_SNOW_FLAT=0"], "smallsnow": ["-DSB2_GS_DIV_CALL=1", "-DSB2_SNOW_FLAT=0"],
+    # hbv step kernel (pt_hs_k / hbv_stack): launch bounds as (block, min blocks per SM)
+    "hbvk5": ["-DSB2_HBV_MINBLOCKS_K=5"], "hbvs4": ["-DSB2_HBV_MINBLOCKS_S=4"], "hbvs6": ["-DSB2_HBV_MINBLOCKS_S=6"],
     "pf0": ["-DSB2_PREFETCH_AHEAD=0"], "pf2": ["-DSB2_PREFETCH_AHEAD=2"], "pf8": ["-DSB2_PREFETCH_AHEAD=8"],
 }
 out_dir = os.path.join(_build.ROOT, "build")
