@@ -40,10 +40,12 @@ enum {
 enum { SB2_R_AVG_DISCHARGE = 0, SB2_R_CHARGE_M3S, SB2_R_SNOW_SCA, SB2_R_SNOW_SWE, SB2_R_SNOW_OUTFLOW, SB2_R_GLACIER_MELT,
        SB2_R_AE_OUTPUT, SB2_R_PE_OUTPUT, SB2_R_SOIL_OUTFLOW, SB2_N_RESPONSE };
 /* pt_gs_k state series ids (state_collector member order, core/pt_gs_k_cell_model.h:146-208).
- * pt_hs_k: 0 kirchner_discharge, 1 snow_sca, 2 snow_swe (core/pt_hs_k_cell_model.h:148-206);
- * hbv_stack: 0 snow_swe, 1 snow_sca, 2 soil_moisture, 3 tank_uz, 4 tank_lz (core/hbv_stack_cell_model.h:148-213) */
+ * pt_hs_k: 0 kirchner_discharge, 1 snow_sca, 2 snow_swe, 3..7 sp[0..4], 8..12 sw[0..4] (core/pt_hs_k_cell_model.h:148-206);
+ * hbv_stack: 0 snow_swe, 1 snow_sca, 2 soil_moisture, 3 tank_uz, 4 tank_lz, 5..9 sp[0..4], 10..14 sw[0..4]
+ * (core/hbv_stack_cell_model.h:148-213); sp / sw = the snow pack and its liquid water per quantile bin (five bins). */
 enum { SB2_S_KIRCHNER_DISCHARGE = 0, SB2_S_GS_ALBEDO, SB2_S_GS_LWC, SB2_S_GS_SURFACE_HEAT, SB2_S_GS_ALPHA, SB2_S_GS_SDC_MELT_MEAN,
-       SB2_S_GS_ACC_MELT, SB2_S_GS_ISO_POT_ENERGY, SB2_S_GS_TEMP_SWE, SB2_N_STATE_SERIES };
+       SB2_S_GS_ACC_MELT, SB2_S_GS_ISO_POT_ENERGY, SB2_S_GS_TEMP_SWE, SB2_N_STATE_SERIES = 15 };
+enum { SB2_S_PTHSK_SP0 = 3, SB2_S_PTHSK_SW0 = 8, SB2_S_HBV_SP0 = 5, SB2_S_HBV_SW0 = 10 };
 
 /* geo_cell_data (core/geo_cell_data.h:107-138) flattened; one per cell, in the caller's cell order */
 typedef struct sb2_geo_cell {

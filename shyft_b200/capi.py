@@ -23,8 +23,9 @@ RESPONSE_NAMES = ("avg_discharge", "charge_m3s", "snow_sca", "snow_swe", "snow_o
 STATE_SERIES_NAMES = {
     PT_GS_K: ("kirchner_discharge", "gs_albedo", "gs_lwc", "gs_surface_heat", "gs_alpha", "gs_sdc_melt_mean", "gs_acc_melt", "gs_iso_pot_energy",
               "gs_temp_swe"),
-    PT_HS_K: ("kirchner_discharge", "snow_sca", "snow_swe"),
-    HBV_STACK: ("snow_swe", "snow_sca", "soil_moisture", "tank_uz", "tank_lz"),
+    PT_HS_K: ("kirchner_discharge", "snow_sca", "snow_swe") + tuple(f"snow_sp_{i}" for i in range(5)) + tuple(f"snow_sw_{i}" for i in range(5)),
+    HBV_STACK: ("snow_swe", "snow_sca", "soil_moisture", "tank_uz", "tank_lz") + tuple(f"snow_sp_{i}" for i in range(5))
+    + tuple(f"snow_sw_{i}" for i in range(5)),
 }
 
 # sb2_geo_cell, 12 x 8 bytes, no padding

@@ -375,7 +375,7 @@ bool wants_response(const sb2_model* m, int r) {
     if (r <= SB2_R_PE_OUTPUT) return bits & 4;
     return (bits & 4) && m->stack == SB2_HBV_STACK;  // soil_outflow
 }
-int n_state_series(const sb2_model* m) { return m->stack == SB2_PT_GS_K ? 9 : (m->stack == SB2_PT_HS_K ? 3 : 5); }
+int n_state_series(const sb2_model* m) { return m->stack == SB2_PT_GS_K ? 9 : (m->stack == SB2_PT_HS_K ? 3 + 2 * kSnowBins : 5 + 2 * kSnowBins); }
 
 void ensure_series(sb2_model* m, int64_t first, int64_t rows) {
     if (m->out_rows != rows) free_series(m);  // a window buffer of the same size is reused as is
@@ -472,7 +472,7 @@ void launch_step_range(sb2_model* m, int64_t first, int64_t n_steps, bool collec
             a.n_steps = chunk; a.first_step = s0;
             a.dt_seconds = dt_seconds; a.dt_hours = dt_seconds / 3600.0; a.dt_us = double(m->dt);
             for (int r = 0; r < 9; ++r) a.resp[r] = m->d_resp[r].p;
-            for (int s = 0; s < 5; ++s) a.st[s] = m->d_st[s].p;
+            for (int s = 0; s < n_state_series(m); ++s) a.st[s] = m->d_st[s].p;
             a.out_first_step = m->out_first;
             a.collect_end_state = (last && collect_end_state) ? 1 : 0;
             a.slot = m->d_slot.p; a.partial = m->d_partial.p; a.n_slots = m->n_slots; a.error_flag = m->d_error_flag.p;

@@ -82,7 +82,7 @@ struct HbvRunArgs {
     int64_t first_step;
     double dt_seconds, dt_hours, dt_us;
     double* __restrict__ resp[9];
-    double* __restrict__ st[5];
+    double* __restrict__ st[5 + 2 * HBV_NB];  // state series, ids of include/shyft_b200.h (the per-bin sp / sw series last)
     int64_t out_first_step;
     int collect_end_state;
     const int32_t* __restrict__ slot;
@@ -281,6 +281,9 @@ __global__ void __launch_bounds__(128, (HBV_STACK ? SB2_HBV_MINBLOCKS_S : SB2_HB
         } else {          // pt_hs_k_cell_model.h:193-205 on state.scale_snow (pt_hs_k.h:165-169)
             a.st[0][orow] = mmh_to_m3s(x0, cell_area_m2); a.st[1][orow] = sca; a.st[2][orow] = swe * snow_storage_fraction;
         }
+        constexpr int SP0 = HBV_STACK ? 5 : 3;
+#pragma unroll
+        for (int i = 0; i < HBV_NB; ++i) { a.st[SP0 + i][orow] = sp[i]; a.st[SP0 + HBV_NB + i][orow] = sw[i]; }  // the bins as they are (:199-202 / :209-212)
     };
 
     bool failed_snow = false, failed_k = false;

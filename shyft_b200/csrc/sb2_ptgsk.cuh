@@ -815,7 +815,10 @@ __device__ __forceinline__ void prefetch_l1(const double* p) { asm volatile("pre
 #define SB2_MINBLOCKS_C 16
 #endif
 
-__global__ void __launch_bounds__(SB2_BLOCK_A) ptgsk_forcing_terms_kernel(const PtgskRunArgs a) {
+#ifndef SB2_MINBLOCKS_A
+#define SB2_MINBLOCKS_A 1
+#endif
+__global__ void __launch_bounds__(SB2_BLOCK_A, SB2_MINBLOCKS_A) ptgsk_forcing_terms_kernel(const PtgskRunArgs a) {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= a.n_cells) return;
     if (a.active != nullptr && a.active[c] == 0) return;

@@ -141,12 +141,26 @@ _attach(ActualEvapotranspirationResponseStatistics, "pot_ratio", _AE_POT_RATIO, 
 
 # ---- the HBV stacks (pt_hs_k, hbv_stack): shyft/api/pt_hs_k/__init__.py:13-19, shyft/api/hbv_stack/__init__.py:13-19 ----------
 class HbvSnowStateStatistics(_Reader):
-    """hbv_snow_cell_state_statistics (api/api.h:1049-1160): area-weighted swe and sca.  The per-bin series sp[i] / sw[i] are not
-    collected on the device."""
+    """hbv_snow_cell_state_statistics (api/api.h:1049-1160): area-weighted swe and sca, and the per-bin series sp[i] / sw[i]
+    (one area-weighted series, one per-cell vector or one value per snow bin, as the reference returns them)"""
+    N_BINS = 5
 
-    def _no_bins(self, *a, **k):
-        raise RuntimeError("hbv_snow per-bin state series (sp, sw) are not collected by shyft_b200")
-    sp = sw = sp_value = sw_value = _no_bins
+    def _bins(self, which, indexes, ith_timestep, ix_type, value):
+        out = []
+        for i in range(self.N_BINS):
+            s = _state(f"snow_{which}_{i}")(self._m)
+            if value:
+                out.append(self._value(_STATE, s, indexes, ith_timestep, ix_type, _AVERAGE))
+            elif ith_timestep is None:
+                out.append(self._series(_STATE, s, indexes, ix_type, _AVERAGE))
+            else:
+                out.append(self._cells(_STATE, s, indexes, ith_timestep, ix_type))
+        return out
+
+    def sp(self, indexes=(), ith_timestep=None, ix_type=CATCHMENT_IX): return self._bins("sp", indexes, ith_timestep, ix_type, False)
+    def sw(self, indexes=(), ith_timestep=None, ix_type=CATCHMENT_IX): return self._bins("sw", indexes, ith_timestep, ix_type, False)
+    def sp_value(self, indexes, ith_timestep, ix_type=CATCHMENT_IX): return self._bins("sp", indexes, ith_timestep, ix_type, True)
+    def sw_value(self, indexes, ith_timestep, ix_type=CATCHMENT_IX): return self._bins("sw", indexes, ith_timestep, ix_type, True)
 
 
 _attach(HbvSnowStateStatistics, "swe", _STATE, _state("snow_swe"), _AVERAGE)

@@ -102,3 +102,35 @@ def test_windowed_run_with_routing_equals_resident_run(sb, stack):
         assert_parity(b.river_local_inflow_m3s(rid), a.river_local_inflow_m3s(rid), f"{stack} river {rid} local inflow (windowed)", rtol=1e-13)
         assert_parity(b.river_output_flow_m3s(rid), a.river_output_flow_m3s(rid), f"{stack} river {rid} output (windowed)", rtol=1e-13)
     assert a.river_output_flow_m3s(8).max() > a.river_local_inflow_m3s(8).max()  # the chain accumulates upstream flow
+
+
+@pytest.mark.parametrize("stack", [1, 2])
+def test_per_bin_snow_state_series(sb, oracle, stack):
+    """state_collector of the HBV stacks (core/pt_hs_k_cell_model.h:193-205, core/hbv_stack_cell_model.h:196-212): sp[i] / sw[i] of the
+    five snow bins at the beginning of every step and after the last one, against the oracle stepped one step at a time"""
+    cls, par = (sb.PTHSKModel, PTHSK_DEFAULT) if stack == 1 else (sb.HbvStackModel, HBV_DEFAULT)
+    m, geo, ta, st0, f = _setup(sb, cls, par, stack, n=48, T=400)
+    m.set_state_collection(-1, True)
+    m.run_cells()
+    run = oracle.pthsk_run_cells if stack == 1 else oracle.hbv_stack_run_cells
+    G = geo_matrix(geo)
+    st = st0.copy()
+    want = np.zeros((401, 48, 10))
+    for i in range(400):
+        want[i] = st[:, 2:12]
+        st = run(G, par, f, st, ta.start * 10**6, ta.delta_t * 10**6, start_step=i, n_steps=1)["state"]
+    want[400] = st[:, 2:12]
+    assert want[:, :, :5].max() > 1.0      # there is snow in the bins
+    for i in range(5):
+        assert np.array_equal(m.state_series(f"snow_sp_{i}"), want[:, :, i]), i
+        assert np.array_equal(m.state_series(f"snow_sw_{i}"), want[:, :, 5 + i]), i
+    # the statistics readers over them (api/api.h:1086-1160): one area-weighted series / per-cell vector / value per bin
+    cids, area = geo["catchment_id"], geo["area"]
+    sel = [int(cids[0])]
+    sp = m.hbv_snow_state.sp(sel)
+    assert len(sp) == 5 and sp[0].shape == (401,)
+    for i in range(5):
+        assert np.allclose(sp[i], oracle.average_catchment_feature(want[:, :, i], area, cids, sel), rtol=1e-12, atol=1e-300)
+        assert np.array_equal(m.hbv_snow_state.sw(sel, 200)[i], oracle.catchment_feature(want[:, :, 5 + i], cids, sel, 200))
+    v = m.hbv_snow_state.sp_value(sel, 200)
+    assert v == pytest.approx([oracle.average_catchment_feature_value(want[:, :, i], area, cids, sel, 200) for i in range(5)], rel=1e-12)

@@ -171,8 +171,7 @@ def test_hbv_stack_readers_against_the_oracle_restatement(sb, oracle, stack):
     assert np.allclose(m.hbv_snow_state.sca([]), oracle.average_catchment_feature(sca, area, cids, []), **tol)
     assert np.array_equal(m.hbv_snow_state.swe(sel, 7), oracle.catchment_feature(swe, cids, sel, 7))
     assert m.hbv_snow_state.sca_value(sel, 50) == pytest.approx(oracle.average_catchment_feature_value(sca, area, cids, sel, 50), rel=1e-12)
-    with pytest.raises(RuntimeError, match="not collected"):
-        m.hbv_snow_state.sp(sel)
+    assert len(m.hbv_snow_state.sp(sel)) == 5 and len(m.hbv_snow_state.sw_value(sel, 3)) == 5   # per-bin series (tests/test_gpu_hbv_routing.py)
     if stack == 1:
         kd = m.state_series("kirchner_discharge")
         assert np.allclose(m.kirchner_state.discharge(sel), oracle.sum_catchment_feature(kd, cids, sel), **tol)
