@@ -392,6 +392,26 @@ def abs_diff_sum(o, m):
     return float(lib().sho_abs_diff_sum(_d(o), _d(m), C.c_int64(o.size)))
 
 
+def max_abs_average_to_axis(values, dt_us, first, k, n_out):
+    """max_abs_average_accessor (core/time_series.h:2198-2267) over aligned coarser periods: the larger of the true averages of
+    max(0, v) and max(0, -v) (finite values only are mapped, source_max_abs :2208-2213)"""
+    v = _f64(values)
+    fin = np.isfinite(v)
+    pos = np.where(fin, np.maximum(0.0, v), v)
+    neg = np.where(fin, np.maximum(0.0, -v), v)
+    a, b = average_to_axis(pos, dt_us, first, k, n_out), average_to_axis(neg, dt_us, first, k, n_out)
+    return np.where(a < b, b, a)   # std::max(pos_val, neg_val)
+
+
+def abs_diff_sum_scaled(o, m, s):
+    """abs_diff_sum_goal_function_scaled (core/time_series.h:2435-2448)"""
+    r = 0.0
+    for tv, dv, sv in zip(_f64(o), _f64(m), _f64(s)):
+        if np.isfinite(tv) and np.isfinite(dv) and np.isfinite(sv) and abs(sv) > 1e-20:
+            r += abs(tv - dv) / sv
+    return r
+
+
 def catchment_index(cids):
     cid = np.ascontiguousarray(cids, dtype=np.int64)
     cix = np.zeros_like(cid)

@@ -850,6 +850,12 @@ void ensure_routing_plan(sb2_model* m) {
 // ---- calibration goal function (core/model_calibration.h:830-899) ---------------------------------------------------------
 void build_goal_targets(sb2_model* m, std::vector<GoalTarget>& gt, const double* cq, const double* cc, int64_t ens_stride) {
     gt.clear();
+    // optimizer::run hands ONE cache vector (catchment_d) to both compute_discharge_sum and compute_charge_sum
+    // (model_calibration.h:837,843,855) and each fills it only when empty: whichever of the DISCHARGE / CELL_CHARGE targets comes
+    // first in the list decides the series all of them are compared with.  Kept as the reference behaves.
+    int first_kind = -1;
+    for (auto& tp : m->targets)
+        if (first_kind < 0 && (tp->property == SB2_TARGET_DISCHARGE || tp->property == SB2_TARGET_CELL_CHARGE)) first_kind = tp->property;
     for (auto& tp : m->targets) {
         sb2_model::Target& t = *tp;
         GoalTarget g{};
@@ -857,11 +863,11 @@ void build_goal_targets(sb2_model* m, std::vector<GoalTarget>& gt, const double*
         g.first_step = (t.t0 - m->t0) / m->dt;
         g.steps_per_period = int32_t(t.dt / m->dt);
         g.n = int32_t(t.obs.size());
-        g.calc_mode = t.calc_mode;
+        g.calc_mode = (t.calc_mode == SB2_GOAL_ABS_DIFF && t.property == SB2_TARGET_CELL_CHARGE) ? GOAL_ABS_DIFF_SCALED : t.calc_mode;  // :870-873
         g.s_r = t.s_r; g.s_a = t.s_a; g.s_b = t.s_b;
         g.dt_seconds = double(m->dt) / 1e6;
         if (t.property == SB2_TARGET_DISCHARGE || t.property == SB2_TARGET_CELL_CHARGE) {
-            g.series = t.property == SB2_TARGET_DISCHARGE ? cq : cc;
+            g.series = first_kind == SB2_TARGET_DISCHARGE ? cq : cc;
             g.ens_stride = ens_stride;
             g.n_col = int32_t(m->n_catch());
             g.cix = t.d_cix.p;
@@ -1954,8 +1960,6 @@ int sb2_set_targets(sb2_model* m, int n_targets, const sb2_target* targets) {
             if (s.dt_us <= 0 || s.dt_us % m->dt != 0 || (s.t0_us - m->t0) % m->dt != 0 || s.t0_us < m->t0 ||
                 (s.t0_us - m->t0) / m->dt + int64_t(s.n) * (s.dt_us / m->dt) > m->T)
                 throw Error("target_specification: the target time-axis must be aligned with, and inside, the model time-axis");
-            if (s.property == SB2_TARGET_CELL_CHARGE && s.calc_mode == SB2_GOAL_ABS_DIFF)
-                throw Error("target_specification: ABS_DIFF on CELL_CHARGE (scaled variant) is not supported");
             t->obs.assign(s.values, s.values + s.n);
             t->t0 = s.t0_us; t->dt = s.dt_us;
             t->cids.assign(s.catchment_ids, s.catchment_ids + s.n_catchments);

@@ -13,7 +13,8 @@
 
 namespace sb2 {
 
-enum { GOAL_NASH_SUTCLIFFE = 0, GOAL_KLING_GUPTA = 1, GOAL_ABS_DIFF = 2, GOAL_RMSE = 3 };
+enum { GOAL_NASH_SUTCLIFFE = 0, GOAL_KLING_GUPTA = 1, GOAL_ABS_DIFF = 2, GOAL_RMSE = 3,
+       GOAL_ABS_DIFF_SCALED = 4 };  // ABS_DIFF of a CELL_CHARGE target: abs_diff_sum_goal_function_scaled (core/time_series.h:2435-2448)
 
 struct GoalTarget {
     const double* series;     // simulated series [n_ens][T][n_col] (device): catchment sums, or a per-target snow series
@@ -40,24 +41,33 @@ __global__ void __launch_bounds__(256) goal_kernel(const GoalTarget* __restrict_
     const int e = blockIdx.y;
     const double* s = t.series + (int64_t)e * t.ens_stride;
     const int n_catch = t.n_col;
-    auto sim_value = [&](int i) {  // average_accessor of the stair-case sum over target period i
-        double area = 0.0, tsum = 0.0;
+    // average_accessor of the stair-case sum over target period i; `scale` = max_abs_average_accessor of the same period
+    // (core/time_series.h:2198-2267): the larger of the period averages of max(0, v) and max(0, -v)
+    auto sim_value2 = [&](int i, double& scale) {
+        double area = 0.0, tsum = 0.0, apos = 0.0, aneg = 0.0;
         for (int j = 0; j < t.steps_per_period; ++j) {
             const int64_t step = t.first_step + (int64_t)i * t.steps_per_period + j;
             if (step >= T) break;
             double v = 0.0;
             for (int c = 0; c < t.n_cix; ++c) v += s[step * n_catch + t.cix[c]];
-            if (isfinite(v)) { area += v * t.dt_seconds; tsum += t.dt_seconds; }
+            if (isfinite(v)) {
+                area += v * t.dt_seconds; tsum += t.dt_seconds;
+                apos += dmax(0.0, v) * t.dt_seconds; aneg += dmax(0.0, -v) * t.dt_seconds;
+            }
         }
+        scale = tsum > 0.0 ? dmax(apos / tsum, aneg / tsum) : nan_();
         return tsum > 0.0 ? area / tsum : nan_();
     };
+    auto sim_value = [&](int i) { double unused; return sim_value2(i, unused); };
     // pass 1: sums over the periods where both are finite
     double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0;  // meaning depends on calc_mode
     for (int i = threadIdx.x; i < t.n; i += blockDim.x) {
-        const double o = t.obs[i], m = sim_value(i);
+        double sv;
+        const double o = t.obs[i], m = sim_value2(i, sv);
         if (isfinite(o) && isfinite(m)) {
             const double d = o - m;
-            if (t.calc_mode == GOAL_KLING_GUPTA) { a0 += o; a1 += m; a2 += o * o; a3 += m * m; a4 += o * m; a5 += 1.0; }
+            if (t.calc_mode == GOAL_ABS_DIFF_SCALED) { if (isfinite(sv) && fabs(sv) > 1e-20) a0 += fabs(d) / sv; }
+            else if (t.calc_mode == GOAL_KLING_GUPTA) { a0 += o; a1 += m; a2 += o * o; a3 += m * m; a4 += o * m; a5 += 1.0; }
             else if (t.calc_mode == GOAL_ABS_DIFF) { a0 += fabs(d); }
             else { a0 += d * d; a1 += o; a5 += 1.0; }
         }
@@ -91,7 +101,7 @@ __global__ void __launch_bounds__(256) goal_kernel(const GoalTarget* __restrict_
     } else if (t.calc_mode == GOAL_RMSE) {
         const double obs_avg = s1 / cnt;
         result = cnt > 0.0 ? sqrt(s0 / cnt) / obs_avg : nan_();
-    } else if (t.calc_mode == GOAL_ABS_DIFF) {
+    } else if (t.calc_mode == GOAL_ABS_DIFF || t.calc_mode == GOAL_ABS_DIFF_SCALED) {
         result = s0;
     } else {  // Kling-Gupta over dlib::running_scalar_covariance semantics (n-1 denominators)
         const double qo = s0 / cnt, qs = s1 / cnt;

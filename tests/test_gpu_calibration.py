@@ -111,3 +111,38 @@ def test_snow_targets_use_area_weighted_catchment_means(sb, oracle, setup):
     run = oracle.ptgsk_run_cells(gm, p, f, st0, ta.start * 10**6, 3600 * 10**6, ncore=8)
     sim = oracle.average_to_axis((run["snow_swe"][:, sel] * area[sel]).sum(axis=1) / area[sel].sum(), 3600 * 10**6, 0, 24, 60)
     assert opt.calculate_goal_function(p) == pytest.approx(oracle.rmse(swe_obs, sim), rel=1e-9)
+
+
+def test_cell_charge_targets_and_the_shared_series_cache(sb, oracle, setup):
+    """CELL_CHARGE targets (model_calibration.h:854-856): ABS_DIFF on them is the scaled form over max_abs_average_accessor
+    (:870-873; core/time_series.h:2198-2267, 2435-2448).  And the reference's one cache vector for discharge AND charge sums: the first
+    DISCHARGE / CELL_CHARGE target of the list decides which series every such target sees."""
+    m, geo, gm, ta, st0, f, obs, sel = setup
+    H = 3600 * 10**6
+    truth = oracle.ptgsk_run_cells(gm, PTGSK_DEFAULT, f, st0, ta.start * 10**6, H, ncore=8)
+    charge_obs = oracle.average_to_axis(truth["charge_m3s"][:, sel].sum(axis=1), H, 0, 24, 60) + 0.25
+    p = _perturbed(np.random.default_rng(11), 1)[0]
+    run = oracle.ptgsk_run_cells(gm, p, f, st0, ta.start * 10**6, H, ncore=8)
+    ch = run["charge_m3s"][:, sel].sum(axis=1)
+    q = run["avg_discharge"][:, sel].sum(axis=1)
+    sim_c, scale_c = oracle.average_to_axis(ch, H, 0, 24, 60), oracle.max_abs_average_to_axis(ch, H, 0, 24, 60)
+    assert (ch < 0).any() and (ch > 0).any() and np.all(scale_c >= np.abs(sim_c) - 1e-12)
+    # RMSE and (scaled) ABS_DIFF of the charge
+    opt = sb.Optimizer(m, [sb.TargetSpecification(charge_obs, ta.start, DAY, [1, 2], 1.0, 3, catchment_property=4)])
+    assert opt.calculate_goal_function(p) == pytest.approx(oracle.rmse(charge_obs, sim_c), rel=1e-9)
+    opt = sb.Optimizer(m, [sb.TargetSpecification(charge_obs, ta.start, DAY, [1, 2], 1.0, 2, catchment_property=4)])
+    assert opt.calculate_goal_function(p) == pytest.approx(oracle.abs_diff_sum_scaled(charge_obs, sim_c, scale_c), rel=1e-9)
+    # a DISCHARGE target first: the CELL_CHARGE target after it is evaluated on the cached DISCHARGE sums (and scaled by them)
+    sim_q, scale_q = oracle.average_to_axis(q, H, 0, 24, 60), oracle.max_abs_average_to_axis(q, H, 0, 24, 60)
+    opt = sb.Optimizer(m, [sb.TargetSpecification(obs, ta.start, DAY, [1, 2], 1.0, 0),
+                           sb.TargetSpecification(charge_obs, ta.start, DAY, [1, 2], 3.0, 2, catchment_property=4)])
+    want = (1.0 * oracle.nash_sutcliffe(obs, sim_q) + 3.0 * oracle.abs_diff_sum_scaled(charge_obs, sim_q, scale_q)) / 4.0
+    assert opt.calculate_goal_function(p) == pytest.approx(want, rel=1e-9)
+    # the other way round: the DISCHARGE target sees the cached CHARGE sums
+    opt = sb.Optimizer(m, [sb.TargetSpecification(charge_obs, ta.start, DAY, [1, 2], 3.0, 3, catchment_property=4),
+                           sb.TargetSpecification(obs, ta.start, DAY, [1, 2], 1.0, 0)])
+    want = (3.0 * oracle.rmse(charge_obs, sim_c) + 1.0 * oracle.nash_sutcliffe(obs, sim_c)) / 4.0
+    assert opt.calculate_goal_function(p) == pytest.approx(want, rel=1e-9)
+    # batched evaluation of charge targets equals one at a time
+    P = _perturbed(np.random.default_rng(12), 9)
+    assert np.array_equal(opt.calculate_goal_function_batch(P), np.array([opt.calculate_goal_function(x) for x in P]))
