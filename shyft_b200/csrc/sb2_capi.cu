@@ -238,9 +238,13 @@ struct sb2_model {
         double s_r = 1.0, s_a = 1.0, s_b = 1.0;
         DevArray<double> d_obs, d_series;
         DevArray<int32_t> d_cix;
+        bool aligned = true;                      // target periods are whole runs of model steps inside the model axis
+        DevArray<double> d_projected, d_scale;   // not aligned: the property (and its max-abs scale) projected onto the target axis
     };
     std::vector<std::unique_ptr<Target>> targets;
     DevArray<int32_t> d_cell_ptr, d_cell_of_catch;  // cells grouped by catchment (area-weighted snow means)
+    DevArray<int64_t> d_axis_t;                     // the model axis' point times (projection of a property onto a foreign target axis)
+    DevArray<int32_t> d_one_zero;
     // bookkeeping
     int64_t launches = 0;
     float last_step_ms = 0.f, last_interp_ms = 0.f;
@@ -866,6 +870,8 @@ void build_goal_targets(sb2_model* m, std::vector<GoalTarget>& gt, const double*
         g.calc_mode = (t.calc_mode == SB2_GOAL_ABS_DIFF && t.property == SB2_TARGET_CELL_CHARGE) ? GOAL_ABS_DIFF_SCALED : t.calc_mode;  // :870-873
         g.s_r = t.s_r; g.s_a = t.s_a; g.s_b = t.s_b;
         g.dt_seconds = double(m->dt) / 1e6;
+        g.rows = m->T;
+        g.scale = nullptr;
         if (t.property == SB2_TARGET_DISCHARGE || t.property == SB2_TARGET_CELL_CHARGE) {
             g.series = first_kind == SB2_TARGET_DISCHARGE ? cq : cc;
             g.ens_stride = ens_stride;
@@ -878,6 +884,41 @@ void build_goal_targets(sb2_model* m, std::vector<GoalTarget>& gt, const double*
             g.n_col = 1;
             g.cix = t.d_cix.p;  // holds a single 0
             g.n_cix = 1;
+        }
+        if (!t.aligned) {  // project the property onto the target axis first (single evaluation only; the batch path asks for aligned axes)
+            if (ens_stride != 0) throw Error("target_specification: batched evaluation needs target axes aligned with the model axis");
+            const int64_t T = m->T, n = int64_t(t.obs.size());
+            if (!m->d_axis_t.p || int64_t(m->d_axis_t.n) != T) {
+                std::vector<int64_t> tt(static_cast<size_t>(T), 0);
+                for (int64_t i = 0; i < T; ++i) tt[size_t(i)] = m->t0 + i * m->dt;
+                m->d_axis_t.upload(tt, m->stream);
+            }
+            DevArray<double> d_prop, d_a, d_b;
+            d_prop.resize(size_t(T));
+            t.d_projected.resize(size_t(n));
+            auto project = [&](int mode, double* out) {
+                goal_property_kernel<<<grid_for(T, 256), 256, 0, m->stream>>>(g.series, T, g.n_col, g.cix, g.n_cix, mode, d_prop.p);
+                average_accessor_kernel<<<grid_for(n, 256), 256, 0, m->stream>>>(m->d_axis_t.p, d_prop.p, T, 1, m->t0 + T * m->dt, 0, t.t0, t.dt, n, out);
+                CUDA_OK(cudaGetLastError());
+                m->launches += 2;
+            };
+            project(0, t.d_projected.p);
+            if (g.calc_mode == GOAL_ABS_DIFF_SCALED) {
+                d_a.resize(size_t(n)); d_b.resize(size_t(n));
+                t.d_scale.resize(size_t(n));
+                project(1, d_a.p);
+                project(2, d_b.p);
+                goal_max_kernel<<<grid_for(n, 256), 256, 0, m->stream>>>(d_a.p, d_b.p, n, t.d_scale.p);
+                CUDA_OK(cudaGetLastError());
+                ++m->launches;
+                g.scale = t.d_scale.p;
+            }
+            CUDA_OK(cudaStreamSynchronize(m->stream));  // the temporaries go out of scope
+            m->d_one_zero.ensure(1);
+            CUDA_OK(cudaMemsetAsync(m->d_one_zero.p, 0, sizeof(int32_t), m->stream));
+            g.series = t.d_projected.p; g.ens_stride = 0; g.n_col = 1; g.cix = m->d_one_zero.p; g.n_cix = 1;
+            g.first_step = 0; g.steps_per_period = 1; g.rows = n;
+            g.dt_seconds = 1.0;  // (v * 1) / 1 = v: the projected value is taken as it is
         }
         gt.push_back(g);
     }
@@ -929,7 +970,7 @@ double evaluate_goal_single(sb2_model* m) {
     DevArray<double> d_out;
     d_gt.upload(gt, m->stream);
     d_out.resize(gt.size());
-    goal_kernel<<<dim3((unsigned)gt.size(), 1), 256, 0, m->stream>>>(d_gt.p, int(gt.size()), m->T, d_out.p);
+    goal_kernel<<<dim3((unsigned)gt.size(), 1), 256, 0, m->stream>>>(d_gt.p, int(gt.size()), d_out.p);
     CUDA_OK(cudaGetLastError());
     ++m->launches;
     std::vector<double> partial(gt.size());
@@ -1011,7 +1052,7 @@ void goal_batch_ptgsk(sb2_model* m, int64_t n_sets, const double* P, double* goa
             CUDA_OK(cudaGetLastError());
             m->launches += 2;
         }
-        goal_kernel<<<dim3((unsigned)gt.size(), (unsigned)ne), 256, 0, m->stream>>>(d_gt.p, int(gt.size()), T, d_out.p);
+        goal_kernel<<<dim3((unsigned)gt.size(), (unsigned)ne), 256, 0, m->stream>>>(d_gt.p, int(gt.size()), d_out.p);
         CUDA_OK(cudaGetLastError());
         ++m->launches;
         CUDA_OK(cudaMemcpyAsync(partial.data(), d_out.p, size_t(ne) * gt.size() * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
@@ -1957,9 +1998,11 @@ int sb2_set_targets(sb2_model* m, int n_targets, const sb2_target* targets) {
             auto t = std::make_unique<sb2_model::Target>();
             if (s.n <= 0 || !s.values) throw Error("target_specification: empty target time-series");
             if (s.calc_mode < 0 || s.calc_mode > 3 || s.property < 0 || s.property > 4) throw Error("target_specification: unknown calc_mode or property");
-            if (s.dt_us <= 0 || s.dt_us % m->dt != 0 || (s.t0_us - m->t0) % m->dt != 0 || s.t0_us < m->t0 ||
-                (s.t0_us - m->t0) / m->dt + int64_t(s.n) * (s.dt_us / m->dt) > m->T)
-                throw Error("target_specification: the target time-axis must be aligned with, and inside, the model time-axis");
+            if (s.dt_us <= 0) throw Error("target_specification: the target time-axis needs a positive delta_t");
+            // whole runs of model steps inside the model axis are reduced in the goal kernel itself; any other fixed_dt axis goes
+            // through the general projection (average_accessor_kernel), as average_accessor<pts_t, ta_t> does it (:859)
+            t->aligned = !(s.dt_us % m->dt != 0 || (s.t0_us - m->t0) % m->dt != 0 || s.t0_us < m->t0 ||
+                           (s.t0_us - m->t0) / m->dt + int64_t(s.n) * (s.dt_us / m->dt) > m->T);
             t->obs.assign(s.values, s.values + s.n);
             t->t0 = s.t0_us; t->dt = s.dt_us;
             t->cids.assign(s.catchment_ids, s.catchment_ids + s.n_catchments);
@@ -2020,7 +2063,7 @@ int sb2_calculate_goal_function_batch(sb2_model* m, int64_t n_sets, const double
         if (n_sets <= 0) return;
         bool device_batch = m->stack == SB2_PT_GS_K;
         for (auto& t : m->targets)
-            if (t->property != SB2_TARGET_DISCHARGE && t->property != SB2_TARGET_CELL_CHARGE) device_batch = false;
+            if ((t->property != SB2_TARGET_DISCHARGE && t->property != SB2_TARGET_CELL_CHARGE) || !t->aligned) device_batch = false;
         if (device_batch) {
             if (!m->has_initial) throw Error("Initial state not yet established or set");
             if (!m->d_forcing[0].p || m->forcing_first != 0 || m->forcing_rows != m->T)

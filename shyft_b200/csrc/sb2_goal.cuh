@@ -30,17 +30,21 @@ struct GoalTarget {
     int32_t calc_mode;
     double s_r, s_a, s_b;
     double dt_seconds;        // model step length
+    int64_t rows;             // rows of `series` (the model axis; or, for a target whose axis is not aligned with it, the target periods
+                              // themselves: series = the property already projected by average_accessor_kernel, one row per period)
+    const double* scale;      // [n] max_abs_average_accessor values for such a pre-projected target (null: evaluated here)
 };
 
 // property[t] for one (ensemble member, target): sum over the target's catchments of series[t][cix]; then the period average.
 // One block per (target, member); out[e * n_targets + k] = partial goal value.
-__global__ void __launch_bounds__(256) goal_kernel(const GoalTarget* __restrict__ targets, int n_targets, int64_t T, double* __restrict__ out) {
+__global__ void __launch_bounds__(256) goal_kernel(const GoalTarget* __restrict__ targets, int n_targets, double* __restrict__ out) {
     __shared__ double red[6][256];
     __shared__ double obs_avg_s;
     const GoalTarget t = targets[blockIdx.x];
     const int e = blockIdx.y;
     const double* s = t.series + (int64_t)e * t.ens_stride;
     const int n_catch = t.n_col;
+    const int64_t T = t.rows;
     // average_accessor of the stair-case sum over target period i; `scale` = max_abs_average_accessor of the same period
     // (core/time_series.h:2198-2267): the larger of the period averages of max(0, v) and max(0, -v)
     auto sim_value2 = [&](int i, double& scale) {
@@ -55,7 +59,7 @@ __global__ void __launch_bounds__(256) goal_kernel(const GoalTarget* __restrict_
                 apos += dmax(0.0, v) * t.dt_seconds; aneg += dmax(0.0, -v) * t.dt_seconds;
             }
         }
-        scale = tsum > 0.0 ? dmax(apos / tsum, aneg / tsum) : nan_();
+        scale = t.scale != nullptr ? t.scale[i] : (tsum > 0.0 ? dmax(apos / tsum, aneg / tsum) : nan_());
         return tsum > 0.0 ? area / tsum : nan_();
     };
     auto sim_value = [&](int i) { double unused; return sim_value2(i, unused); };
@@ -118,6 +122,22 @@ __global__ void __launch_bounds__(256) goal_kernel(const GoalTarget* __restrict_
         result = sqrt(er + ea + eb);
     }
     if (threadIdx.x == 0) out[(int64_t)e * n_targets + blockIdx.x] = result;
+}
+
+// The property series of one target on the model axis, for targets whose own axis is not aligned with it:
+// out[t] = sum over the target's catchments of series[t][cix]; mode 1 / 2 = max(0, v) / max(0, -v) of it (source_max_abs, finite values only)
+__global__ void goal_property_kernel(const double* __restrict__ series, int64_t rows, int n_col, const int32_t* __restrict__ cix, int n_cix, int mode,
+                                     double* __restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= rows) return;
+    double v = 0.0;
+    for (int c = 0; c < n_cix; ++c) v += series[t * n_col + cix[c]];
+    if (mode != 0 && isfinite(v)) v = mode == 1 ? dmax(0.0, v) : dmax(0.0, -v);
+    out[t] = v;
+}
+__global__ void goal_max_kernel(const double* __restrict__ a, const double* __restrict__ b, int64_t n, double* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = dmax(a[i], b[i]);  // std::max(pos_val, neg_val), core/time_series.h:2261
 }
 
 // area-weighted catchment means of a per-cell series: out[t][k] = sum_{cells of k} v[t][c]*area[c] / sum area  (model_calibration.h:765-790)

@@ -82,8 +82,8 @@ def test_weighted_multi_target_goal_with_missing_observations(sb, oracle, setup)
     g1 = oracle.nash_sutcliffe(obs2, oracle.average_to_axis(run[:, sel].sum(axis=1), 3600 * 10**6, 0, 24, 60))
     g2 = oracle.kling_gupta(obs3, oracle.average_to_axis(run[:, sel3].sum(axis=1), 3600 * 10**6, 240, 6, 100), 1.0, 0.5, 2.0)
     assert got == pytest.approx((2.0 * g1 + 0.5 * g2) / 2.5, rel=1e-9)
-    with pytest.raises(RuntimeError, match="aligned"):
-        sb.Optimizer(m, [sb.TargetSpecification(obs, ta.start + 1800, DAY, [1])])
+    with pytest.raises(RuntimeError, match="positive delta_t"):
+        sb.Optimizer(m, [sb.TargetSpecification(obs, ta.start, 0, [1])])
     with pytest.raises(RuntimeError, match="not found"):
         sb.Optimizer(m, [sb.TargetSpecification(obs, ta.start, DAY, [77])])
 
@@ -145,4 +145,45 @@ def test_cell_charge_targets_and_the_shared_series_cache(sb, oracle, setup):
     assert opt.calculate_goal_function(p) == pytest.approx(want, rel=1e-9)
     # batched evaluation of charge targets equals one at a time
     P = _perturbed(np.random.default_rng(12), 9)
+    assert np.array_equal(opt.calculate_goal_function_batch(P), np.array([opt.calculate_goal_function(x) for x in P]))
+
+
+def test_target_axes_not_aligned_with_the_model_axis(sb, oracle, setup):
+    """average_accessor<pts_t, ta_t>(property_sum, t.ts.time_axis()) (model_calibration.h:859) for ANY fixed_dt target axis: shifted by
+    half a step, 90-minute periods, starting before and ending after the model axis -- against the oracle's line-by-line accumulate_value"""
+    m, geo, gm, ta, st0, f, obs, sel = setup
+    H = 3600 * 10**6
+    T = ta.n
+    p = _perturbed(np.random.default_rng(31), 1)[0]
+    run = oracle.ptgsk_run_cells(gm, p, f, st0, ta.start * 10**6, H, ncore=8)
+    q = run["avg_discharge"][:, sel].sum(axis=1)
+    ch = run["charge_m3s"][:, sel].sum(axis=1)
+    t_us = ta.start * 10**6 + H * np.arange(T, dtype=np.int64)
+    t_end = ta.start * 10**6 + H * T
+    rng = np.random.default_rng(32)
+
+    def project(series, t0_s, dt_s, n):
+        return oracle.average_accessor(t_us, series[:, None], t_end, False, t0_s * 10**6, dt_s * 10**6, n)[:, 0]
+
+    cases = [(ta.start + 1800, DAY, 59),            # shifted by half a model step
+             (ta.start + 2 * 3600, 5400, 700),      # 90-minute periods
+             (ta.start - 3 * DAY - 900, DAY, 66)]   # starts three days before the model axis, runs past its end
+    for t0_s, dt_s, n in cases:
+        sim = project(q, t0_s, dt_s, n)
+        assert np.isfinite(sim).sum() >= n - 8 and (np.isnan(sim).any() or t0_s > ta.start)
+        target = np.where(np.isfinite(sim), sim, 1.0) * rng.uniform(0.8, 1.2, n)
+        for mode, fn in ((0, oracle.nash_sutcliffe), (1, oracle.kling_gupta), (2, oracle.abs_diff_sum), (3, oracle.rmse)):
+            opt = sb.Optimizer(m, [sb.TargetSpecification(target, t0_s, dt_s, [1, 2], 1.0, mode)])
+            assert opt.calculate_goal_function(p) == pytest.approx(fn(target, sim), rel=1e-9), (t0_s, dt_s, mode)
+    # scaled ABS_DIFF of the charge on a shifted axis
+    t0_s, dt_s, n = ta.start + 1800, 6 * 3600, 200
+    sim = project(ch, t0_s, dt_s, n)
+    pos = project(np.maximum(0.0, ch), t0_s, dt_s, n)
+    neg = project(np.maximum(0.0, -ch), t0_s, dt_s, n)
+    scale = np.where(pos < neg, neg, pos)
+    target = sim + rng.normal(0.0, 0.3, n)
+    opt = sb.Optimizer(m, [sb.TargetSpecification(target, t0_s, dt_s, [1, 2], 1.0, 2, catchment_property=4)])
+    assert opt.calculate_goal_function(p) == pytest.approx(oracle.abs_diff_sum_scaled(target, sim, scale), rel=1e-9)
+    # the batch entry evaluates such targets one set at a time
+    P = _perturbed(rng, 3)
     assert np.array_equal(opt.calculate_goal_function_batch(P), np.array([opt.calculate_goal_function(x) for x in P]))
