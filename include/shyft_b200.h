@@ -155,6 +155,12 @@ enum { SB2_POINT_AVERAGE_VALUE = 0 /* stair-case */, SB2_POINT_INSTANT_VALUE = 1
 int sb2_set_sources_on_axis(sb2_model* m, int var, int64_t n_src, const double* xyz, int64_t n_points, const int64_t* t_us, int64_t t_end_us,
                             const double* values, int point_interpretation);
 /* the sources of a variable as projected onto the model axis: out [T][n_src] */
+/* ... and for sources that EACH bring their own point axis (every geo_point_ts of a region_environment owns its time-series,
+ * api/api.h:137-168): source s has n_points[s] points, stored one source after the other in t_us / values (sum of n_points entries),
+ * its own total-period end t_end_us[s] and point interpretation[s].  Projected on the device like the shared-axis form. */
+int sb2_set_sources_on_axes(sb2_model* m, int var, int64_t n_src, const double* xyz /* [src][3] */, const int64_t* n_points /* [src] */,
+                            const int64_t* t_us, const int64_t* t_end_us /* [src] */, const double* values,
+                            const int32_t* point_interpretation /* [src] */);
 int sb2_get_sources_on_model_axis(const sb2_model* m, int var, double* out);
 /* interpolate(ip, env, best_effort) (:397-527) over the whole axis; returns 0 also when best_effort swallowed a
  * per-variable failure, in which case *all_ok (nullable) is 0 and that variable stays NaN */

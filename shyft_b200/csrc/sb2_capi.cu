@@ -1577,6 +1577,48 @@ int sb2_set_sources_on_axis(sb2_model* m, int var, int64_t n_src, const double* 
         if (var == SB2_TEMPERATURE) s.h_values = std::move(h);
     });
 }
+int sb2_set_sources_on_axes(sb2_model* m, int var, int64_t n_src, const double* xyz, const int64_t* n_points, const int64_t* t_us,
+                            const int64_t* t_end_us, const double* values, const int32_t* point_interpretation) {
+    return guarded(m, [&] {
+        std::vector<int64_t> off(size_t(std::max<int64_t>(n_src, 0)) + 1, 0);
+        if (n_src > 0) {
+            if (!n_points || !t_us || !t_end_us || !values || !point_interpretation) throw Error("set_sources_on_axes: null argument");
+            for (int64_t s = 0; s < n_src; ++s) {
+                if (n_points[s] < 0) throw Error("set_sources_on_axes: negative point count");
+                off[size_t(s) + 1] = off[size_t(s)] + n_points[s];
+                const int64_t* t = t_us + off[size_t(s)];
+                for (int64_t i = 1; i < n_points[s]; ++i)
+                    if (!(t[i] > t[i - 1])) throw Error("set_sources_on_axes: point times must be strictly increasing");
+                if (n_points[s] > 0 && t_end_us[s] < t[n_points[s] - 1]) throw Error("set_sources_on_axes: the total period ends before the last point");
+            }
+        }
+        Source* sp = begin_sources(m, var, n_src, xyz);
+        if (!sp) return;
+        Source& s = *sp;
+        const size_t count = size_t(m->T) * n_src, total = size_t(off.back());
+        DevArray<int64_t> d_t, d_off, d_end;
+        DevArray<double> d_pts;
+        DevArray<int32_t> d_lin;
+        std::vector<int32_t> lin(static_cast<size_t>(n_src), 0);
+        for (int64_t k = 0; k < n_src; ++k) lin[size_t(k)] = point_interpretation[k] == SB2_POINT_INSTANT_VALUE ? 1 : 0;
+        d_t.upload(t_us, total, m->stream);
+        d_pts.upload(values, total, m->stream);
+        d_off.upload(off, m->stream);
+        d_end.upload(t_end_us, size_t(n_src), m->stream);
+        d_lin.upload(lin, m->stream);
+        s.d_values.resize(count);
+        average_accessor_ragged_kernel<<<grid_for(int64_t(count), 256), 256, 0, m->stream>>>(d_t.p, d_pts.p, d_off.p, d_end.p, d_lin.p, n_src, m->t0, m->dt,
+                                                                                            m->T, s.d_values.p);
+        CUDA_OK(cudaGetLastError());
+        ++m->launches;
+        std::vector<double> h(count);  // NaN bookkeeping of interpolate(), BTK validity sets -- as sb2_set_sources_on_axis
+        CUDA_OK(cudaMemcpyAsync(h.data(), s.d_values.p, count * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+        CUDA_OK(cudaStreamSynchronize(m->stream));
+        s.has_nonfinite = false;
+        for (size_t i = 0; i < count && !s.has_nonfinite; ++i) s.has_nonfinite = !std::isfinite(h[i]);
+        if (var == SB2_TEMPERATURE) s.h_values = std::move(h);
+    });
+}
 int sb2_get_sources_on_model_axis(const sb2_model* cm, int var, double* out) {
     return guarded_c(cm, [&] {
         sb2_model* m = const_cast<sb2_model*>(cm);

@@ -542,13 +542,8 @@ __global__ void average_accessor_same_axis_kernel(double* __restrict__ p, int64_
 // when the source starts later (hint_based_search :165-166 returns 0, not npos, from hint 0).  Same operations in the same order
 // as the reference (to_seconds = us / 1e6, a = dv / dt, b = r.v - a * t_r on epoch seconds): bit-identical to the oracle.
 __device__ __forceinline__ double us_to_seconds(int64_t us) { return double(us) / 1000000.0; }
-__global__ void average_accessor_kernel(const int64_t* __restrict__ t /* [n_points] */, const double* __restrict__ values /* [n_points][n_src] */,
-                                        int64_t n_points, int64_t n_src, int64_t t_end, int linear, int64_t ta_t0, int64_t ta_dt, int64_t ta_n,
-                                        double* __restrict__ out /* [ta_n][n_src] */) {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= ta_n * n_src) return;
-    const int64_t step = idx / n_src, s = idx - step * n_src;
-    const int64_t p_start = ta_t0 + step * ta_dt, p_end = p_start + ta_dt;
+__device__ __forceinline__ double average_accessor_value(const int64_t* __restrict__ t /* [n_points] */, const double* __restrict__ values /* point i at values[i * v_stride] */,
+                                                         int64_t v_stride, int64_t n_points, int64_t t_end, int linear, int64_t p_start, int64_t p_end) {
     const double nan_v = nan_();
     double result = nan_v;
     if (n_points > 0 && p_start < t_end) {
@@ -567,7 +562,7 @@ __global__ void average_accessor_kernel(const int64_t* __restrict__ t /* [n_poin
         bool l_finite = false;
         while (true) {
             if (!l_finite) {
-                l_t = t[i]; l_v = values[i * n_src + s]; ++i;
+                l_t = t[i]; l_v = values[i * v_stride]; ++i;
                 l_finite = isfinite(l_v);
                 if (i == n_points) {
                     if (l_finite && l_t < p_end && extrapolate_flat) {
@@ -580,7 +575,7 @@ __global__ void average_accessor_kernel(const int64_t* __restrict__ t /* [n_poin
                 if (l_t >= p_end) break;
             } else {
                 const int64_t r_t = t[i];
-                const double r_v = values[i * n_src + s];
+                const double r_v = values[i * v_stride];
                 ++i;
                 const bool r_finite = isfinite(r_v);
                 const int64_t px_start = l_t > p_start ? l_t : p_start, px_end = r_t < p_end ? r_t : p_end;
@@ -610,7 +605,29 @@ __global__ void average_accessor_kernel(const int64_t* __restrict__ t /* [n_poin
         }
         result = tsum > 0 ? area / us_to_seconds(tsum) : nan_v;
     }
-    out[idx] = result;
+    return result;
+}
+
+__global__ void average_accessor_kernel(const int64_t* __restrict__ t /* [n_points] */, const double* __restrict__ values /* [n_points][n_src] */,
+                                        int64_t n_points, int64_t n_src, int64_t t_end, int linear, int64_t ta_t0, int64_t ta_dt, int64_t ta_n,
+                                        double* __restrict__ out /* [ta_n][n_src] */) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= ta_n * n_src) return;
+    const int64_t step = idx / n_src, s = idx - step * n_src;
+    const int64_t p_start = ta_t0 + step * ta_dt;
+    out[idx] = average_accessor_value(t, values + s, n_src, n_points, t_end, linear, p_start, p_start + ta_dt);
+}
+// The same for sources that each bring their own point axis (every geo_point_ts of a region_environment is a time-series of its own,
+// api/api.h:137-168): source s owns points off[s] .. off[s+1]-1 of the concatenated t / values arrays, its own period end and point
+// interpretation.
+__global__ void average_accessor_ragged_kernel(const int64_t* __restrict__ t, const double* __restrict__ values, const int64_t* __restrict__ off,
+                                               const int64_t* __restrict__ t_end, const int32_t* __restrict__ linear, int64_t n_src, int64_t ta_t0,
+                                               int64_t ta_dt, int64_t ta_n, double* __restrict__ out /* [ta_n][n_src] */) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= ta_n * n_src) return;
+    const int64_t step = idx / n_src, s = idx - step * n_src;
+    const int64_t p_start = ta_t0 + step * ta_dt;
+    out[idx] = average_accessor_value(t + off[s], values + off[s], 1, off[s + 1] - off[s], t_end[s], linear[s], p_start, p_start + ta_dt);
 }
 
 // [rows][cols] -> [cols][rows] tiled transpose (cell-major <-> time-major at the ABI)

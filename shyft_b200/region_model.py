@@ -75,6 +75,31 @@ class GeoPointSources:
         self.point_fx = point_fx
 
 
+class GeoPointSourceVector:
+    """vector<geo_point_ts> whose series each have their own point axis: a list of (xyz, times [s], values, t_end [s] or None, point_fx)
+    -- one entry per station (api/api.h:137-168)."""
+
+    def __init__(self, sources):
+        xyz, n_points, t, v, t_end, fx = [], [], [], [], [], []
+        for x, times, values, end, point_fx in sources:
+            times = np.asarray(times, dtype=np.float64)
+            values = f64(values).ravel()
+            if values.size != times.size:
+                raise RuntimeError("a source needs one value per point")
+            if point_fx not in ("average", "instant"):
+                raise RuntimeError("point_fx must be 'average' or 'instant'")
+            if end is None:
+                end = times[-1] + (times[-1] - times[-2]) if times.size > 1 else times[-1]
+            xyz.append(x); n_points.append(times.size); t.append(np.round(times * USEC).astype(np.int64)); v.append(values)
+            t_end.append(int(round(float(end) * USEC))); fx.append(1 if point_fx == "instant" else 0)
+        self.xyz = f64(xyz).reshape(-1, 3)
+        self.n_points = np.ascontiguousarray(n_points, dtype=np.int64)
+        self.times_us = np.ascontiguousarray(np.concatenate(t) if t else np.zeros(0), dtype=np.int64)
+        self.values = f64(np.concatenate(v) if v else np.zeros(0))
+        self.t_end_us = np.ascontiguousarray(t_end, dtype=np.int64)
+        self.point_fx = np.ascontiguousarray(fx, dtype=np.int32)
+
+
 class RegionEnvironment:
     """a_region_environment (api/api.h:137-168): per variable a set of geo-located series.
 
@@ -293,6 +318,12 @@ class RegionModel:
                                                          src.times_us.ctypes.data_as(capi.c_i64p), C.c_int64(src.t_end_us), dptr(src.values),
                                                          C.c_int(1 if src.point_fx == "instant" else 0)))
                 continue
+            if isinstance(src, GeoPointSourceVector):
+                self._ck(self._L.sb2_set_sources_on_axes(self._h, C.c_int(vi), C.c_int64(src.xyz.shape[0]), dptr(src.xyz),
+                                                         src.n_points.ctypes.data_as(capi.c_i64p), src.times_us.ctypes.data_as(capi.c_i64p),
+                                                         src.t_end_us.ctypes.data_as(capi.c_i64p), dptr(src.values),
+                                                         src.point_fx.ctypes.data_as(C.POINTER(C.c_int32))))
+                continue
             xyz, values = f64(src[0]), f64(src[1])
             if values.shape != (self.time_axis.n, xyz.shape[0]):
                 raise RuntimeError(f"{name}: source values must be [n_steps][n_sources]")
@@ -303,7 +334,7 @@ class RegionModel:
         """the sources of a variable as projected onto the model axis: [n_steps][n_sources]"""
         vi = FORCING_NAMES.index(name)
         src = getattr(self.region_env, name)
-        n_src = (src.xyz if isinstance(src, GeoPointSources) else f64(src[0])).shape[0]
+        n_src = (src.xyz if isinstance(src, (GeoPointSources, GeoPointSourceVector)) else f64(src[0])).shape[0]
         out = np.zeros((self.time_axis.n, n_src))
         self._ck(self._L.sb2_get_sources_on_model_axis(self._h, C.c_int(vi), dptr(out)))
         return out

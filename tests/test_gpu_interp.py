@@ -177,3 +177,51 @@ def test_sources_on_their_own_axis_are_projected_on_the_device(sb, oracle):
     with pytest.raises(RuntimeError, match="strictly increasing"):
         bad = sb.GeoPointSources(xyz, [t0, t0], np.zeros((2, S)), t_end=t0 + 10)
         m._set_sources(sb.RegionEnvironment(temperature=bad))
+
+
+def test_every_station_on_its_own_axis(sb, oracle):
+    """vector<geo_point_ts>: each station's series has its own time axis, length, end and point interpretation (api/api.h:137-168);
+    sb2_set_sources_on_axes projects them all in one launch, bit-identical to the oracle's average_accessor station by station."""
+    from shyft_b200 import synthetic
+    n, T, S = 300, 96, 5
+    geo, ta, env0 = synthetic.make_region(n, T, S, config_index=15, cells_per_catchment=100)[:3]
+    rng = np.random.default_rng(15)
+    t0, dt = ta.start, ta.delta_t
+    xyz = env0.temperature[0]
+    stations = []
+    for s in range(S):
+        step = (600, 3600, 10800, 1800, 86400)[s]
+        start = t0 + (-7200, 0, -10800, 5400, -86400)[s]
+        npts = (700, 80, 40, 150, 6)[s]
+        times = start + step * np.arange(npts)
+        if s == 3:  # irregular
+            times = np.sort(t0 + rng.choice(np.arange(0, 90 * 3600, 300), npts, replace=False))
+        vals = 2.0 + rng.normal(0, 1.0, npts).cumsum() * 0.2
+        if s == 1:
+            vals[10:14] = np.nan
+        stations.append((xyz[s], times, vals, None if s != 3 else times[-1] + 900, "instant" if s in (0, 3) else "average"))
+    src = sb.GeoPointSourceVector(stations)
+    env = sb.RegionEnvironment(temperature=src, precipitation=env0.precipitation, radiation=env0.radiation, wind_speed=env0.wind_speed,
+                               rel_hum=env0.rel_hum)
+    m = sb.PTGSKModel(geo)
+    ip = sb.InterpolationParameter(use_idw_for_temperature=1)
+    m.run_interpolation(ip, ta, env, best_effort=True)
+    got = m.sources_on_model_axis("temperature")
+    US = 10**6
+    want = np.zeros((T, S))
+    off = np.concatenate([[0], np.cumsum(src.n_points)])
+    for s in range(S):
+        want[:, s] = oracle.average_accessor(src.times_us[off[s]:off[s + 1]], src.values[off[s]:off[s + 1], None], int(src.t_end_us[s]),
+                                             bool(src.point_fx[s]), t0 * US, dt * US, T)[:, 0]
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    assert np.array_equal(got[~np.isnan(got)], want[~np.isnan(want)])
+    assert np.isnan(want[:, 4]).sum() == 0 and np.isnan(want[:, 1]).any() and np.isnan(want[90:, 3]).all()
+    # interpolation from them = interpolation from the projected series
+    m2 = sb.PTGSKModel(geo)
+    env_pre = sb.RegionEnvironment(temperature=(xyz, want), precipitation=env0.precipitation, radiation=env0.radiation,
+                                   wind_speed=env0.wind_speed, rel_hum=env0.rel_hum)
+    m2.run_interpolation(ip, ta, env_pre, best_effort=True)
+    a, b = m.cell_forcing("temperature"), m2.cell_forcing("temperature")
+    assert np.array_equal(np.isnan(a), np.isnan(b)) and np.allclose(a[~np.isnan(a)], b[~np.isnan(b)], rtol=1e-12, atol=0)
+    with pytest.raises(RuntimeError, match="strictly increasing"):
+        m._set_sources(sb.RegionEnvironment(temperature=sb.GeoPointSourceVector([(xyz[0], [t0, t0], [1.0, 2.0], t0 + 10, "average")])))
