@@ -216,6 +216,17 @@ int sho_hbv_snow_step(const double* s_q /*n*/, const double* intervals /*n*/, in
     *swe = s.swe; *sca = s.sca; *outflow = r.outflow;
     SHO_END
 }
+// hbv_snow::state::distribute(p) (core/hbv_snow.h:113-116 over hbv_snow_common.h:45-67)
+int sho_hbv_snow_distribute(const double* s_q /*n*/, const double* intervals /*n*/, int n, double lw, double* sp, double* sw, double* swe, double* sca) {
+    SHO_TRY
+    hbv_snow::parameter p;
+    p.s.assign(s_q, s_q + n); p.intervals.assign(intervals, intervals + n); p.lw = lw;
+    hbv_snow::state s; s.swe = *swe; s.sca = *sca;
+    s.distribute(p);
+    std::copy(s.sp.begin(), s.sp.end(), sp); std::copy(s.sw.begin(), s.sw.end(), sw);
+    *swe = s.swe; *sca = s.sca;
+    SHO_END
+}
 double sho_hbv_soil_step(double fc, double beta, double* sm, double insoil, double act_evap) {
     hbv_soil::parameter p; p.fc = fc; p.beta = beta;
     hbv_soil::state s; s.sm = *sm; hbv_soil::response r;

@@ -259,6 +259,15 @@ def hbv_snow_step(sp, sw, swe, sca, prec, temp, dt_us=3600 * 10**6, s=None, inte
     return sp, sw, cswe.value, csca.value, out.value
 
 
+def hbv_snow_distribute(swe, sca, s, intervals, lw=0.1):
+    """hbv_snow::state::distribute(p): the bins sp / sw of a pack given by swe and sca"""
+    s, iv = _f64(s), _f64(intervals)
+    sp, sw = np.zeros(s.size), np.zeros(s.size)
+    cswe, csca = C.c_double(swe), C.c_double(sca)
+    _check(lib().sho_hbv_snow_distribute(_d(s), _d(iv), C.c_int(s.size), C.c_double(lw), _d(sp), _d(sw), C.byref(cswe), C.byref(csca)))
+    return sp, sw, cswe.value, csca.value
+
+
 def hbv_soil_step(sm, insoil, act_evap, fc=300.0, beta=2.0):
     s = C.c_double(sm)
     out = lib().sho_hbv_soil_step(C.c_double(fc), C.c_double(beta), C.byref(s), C.c_double(insoil), C.c_double(act_evap))
