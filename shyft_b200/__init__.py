@@ -6,7 +6,7 @@ Python mirror of the reference's region-model surface (`region_model`), the cali
 """
 from .capi import (COLLECT_ALL, COLLECT_DISCHARGE, COLLECT_NONE, COLLECT_SNOW, COLLECT_STATE, HBV_STACK, PT_GS_K, PT_HS_K,  # noqa: F401
                    InterpolationParameter)
-from .region_model import (GeoPointSources, GeoPointSourceVector, HbvStackModel, HbvStackOptModel, PTGSKModel, PTGSKOptModel, PTHSKModel, PTHSKOptModel,  # noqa: F401
+from .region_model import (GeoPointSources, GeoPointSourceVector, HbvModel, HbvOptModel, HbvStackModel, HbvStackOptModel, PTGSKModel, PTGSKOptModel, PTHSKModel, PTHSKOptModel,  # noqa: F401
                            RegionEnvironment, RegionModel, TimeAxis, geo_cell_data_vector)
 from .calibration import Optimizer, TargetSpecification  # noqa: F401,E402
 from .state_io import StateIoHandler, StateWithIdVector, cell_state_id_of  # noqa: F401,E402

@@ -134,3 +134,50 @@ def test_per_bin_snow_state_series(sb, oracle, stack):
         assert np.array_equal(m.hbv_snow_state.sw(sel, 200)[i], oracle.catchment_feature(want[:, :, 5 + i], cids, sel, 200))
     v = m.hbv_snow_state.sp_value(sel, 200)
     assert v == pytest.approx([oracle.average_catchment_feature_value(want[:, :, i], area, cids, sel, 200) for i in range(5)], rel=1e-12)
+
+
+def test_reference_python_hbv_model_run(sb, oracle):
+    """shyft/tests/api/test_region_model_stacks.py:423-480 (HbvModel): 20 cells x 240 h, one constant point source per variable given as
+    a single-point series over the whole period (create_time_point_ts :31-40 -- projected on the device by average_accessor),
+    IDW temperature with gradient_by_equation, default HbvState with tank.uz = tank.lz = 40; discharge_value(cids, 0) >= 32"""
+    from fixtures import py_region_fixture
+    fx = py_region_fixture()
+    g = fx["geo"]
+    geo = sb.geo_cell_data_vector(g[:, 0], g[:, 1], g[:, 2], area=g[:, 3], catchment_id=g[:, 4].astype(np.int64), radiation_slope_factor=g[:, 5],
+                                  glacier=g[:, 6], lake=g[:, 7], reservoir=g[:, 8], forest=g[:, 9])
+    m = sb.HbvModel(geo, HBV_DEFAULT)
+    assert m.size() == 20
+    ta = sb.TimeAxis(fx["t0"], 3600, 240)
+    ip = sb.InterpolationParameter(use_idw_for_temperature=1)
+    ip.temperature_idw.default_temp_gradient = -0.005
+    ip.temperature_idw.gradient_by_equation = 1
+    ip.temperature_idw.max_members = 6
+    ip.temperature_idw.max_distance = 20000
+    assert ip.temperature_idw.zscale == 1.0
+    ip.temperature_idw.zscale = 0.5
+    ip.temperature_idw.distance_measure_factor = 1.0
+    assert ip.precipitation.scale_factor == pytest.approx(1.02)
+    end = fx["t0"] + 240 * 3600
+    env = sb.RegionEnvironment(**{k: sb.GeoPointSources(fx["station"][None, :], [fx["t0"]], [[v]], t_end=end, point_fx="average")
+                                  for k, v in fx["consts"].items()})
+    assert m.run_interpolation(ip, ta, env)
+    s0 = np.zeros((20, 15))
+    s0[:, 13:15] = 40.0   # HbvState(): snow 0, soil.sm 0 (hbv_soil.h:28-29), tank.uz = tank.lz = 40 as the test sets them
+    m.set_states(s0)
+    m.set_state_collection(-1, False)
+    m.run_cells()
+    q_without = m.statistics.discharge([])
+    m.set_states(s0)
+    m.set_state_collection(-1, True)
+    m.run_cells()
+    q = m.statistics.discharge([])
+    assert np.array_equal(q, q_without)
+    assert m.statistics.discharge_value([], 0) >= 32.0
+    with pytest.raises(RuntimeError, match="does not exist"):
+        m.statistics.discharge([0, 4, 5])
+    # the same run on the oracle
+    f = {k: m.cell_forcing(k) for k in FORCING}
+    assert np.all(f["temperature"] == 10.0) and np.allclose(f["radiation"], 300.0 * 0.9)   # single-source copy / slope factor
+    want = oracle.hbv_stack_run_cells(g, HBV_DEFAULT, f, s0, fx["t0"] * 10**6, 3600 * 10**6)
+    assert_parity(m.response("avg_discharge"), want["avg_discharge"], "hbv python fixture discharge")
+    assert want["avg_discharge"][0].sum() >= 32.0

@@ -67,3 +67,28 @@ def test_against_the_oracle_on_a_region(sb, oracle, cls_name, stack):
     st_want, missing_want = oracle.apply_state(G, st, [(tuple(int(t) for t in ids[k].tolist()), rows[k]) for k in range(len(ids))], [5, 9, 11])
     assert missing == missing_want
     assert np.array_equal(m.get_states(), st_want)
+
+
+def test_reference_python_state_with_id_handler_story(sb):
+    """shyft/tests/api/test_region_model_stacks.py:556-600 (test_state_with_id_handler), two catchments"""
+    n = 20
+    cid = np.array([1 + (i * 7) % 2 for i in range(n)])
+    geo = sb.geo_cell_data_vector(500 + 1000.0 * np.arange(n), np.full(n, 500.0), 500.0 * np.arange(n) / n, catchment_id=cid, glacier=0.01,
+                                  lake=0.05, reservoir=0.19, forest=0.3)
+    m = sb.PTGSKModel(geo)
+    s12, s1, s2 = m.state.extract_state([]), m.state.extract_state([1]), m.state.extract_state([2])
+    assert len(s1) + len(s2) == len(s12) and len(s1) > 0 and len(s2) > 0
+    ms2 = sb.StateWithIdVector.deserialize_from_bytes(s2.serialize_to_bytes())
+    assert len(ms2) == len(s2) and np.array_equal(ms2.ids, s2.ids) and np.array_equal(ms2.states[:, 8], s2.states[:, 8])
+    assert np.all(s1.ids["cid"] == 1) and np.all(s2.ids["cid"] == 2)
+    s12.states[:, 8] = 100 + np.arange(len(s12))
+    m.state.apply_state(s12, [])
+    ms_12 = m.state.extract_state([])
+    assert np.array_equal(ms_12.states[:, 8], 100.0 + np.arange(n))
+    s2.states[:, 8] = 200 + np.arange(len(s2))
+    assert m.state.apply_state(s2, [2]) == []
+    ms_12 = m.state.extract_state([])
+    for i in range(n):
+        if ms_12.ids["cid"][i] == 1:
+            assert ms_12.states[i, 8] == 100 + i
+    assert np.array_equal(m.state.extract_state([2]).states[:, 8], 200.0 + np.arange(len(s2)))
