@@ -159,6 +159,9 @@ inline int grid_for(int64_t n, int block) { return int((n + block - 1) / block);
 
 }  // namespace
 
+#ifndef SB2_HBV_UNIT_STEPS
+#define SB2_HBV_UNIT_STEPS 64      // steps per time slice of the pt_hs_k / hbv_stack step kernel (0: whole chunks)
+#endif
 #ifndef SB2_DENSE_TILE_COMPACT
 #define SB2_DENSE_TILE_COMPACT 32  // steps staged per buffer, compacted inverse distance over 64-station rows
 #endif
@@ -482,8 +485,14 @@ void launch_step_range(sb2_model* m, int64_t first, int64_t n_steps, bool collec
             a.slot = m->d_slot.p; a.partial = m->d_partial.p; a.n_slots = m->n_slots; a.error_flag = m->d_error_flag.p;
             a.collect = m->collect_bits & 15;
             const int g = grid_for(n, block);
-            if (m->stack == SB2_PT_HS_K) hbv_run_kernel<false><<<g, block, 0, m->stream>>>(a);
-            else hbv_run_kernel<true><<<g, block, 0, m->stream>>>(a);
+            // time slices handed out by ticket while the launch is only a few waves of one-warp blocks (see the kernel)
+            const bool split = use_time_split(g) && SB2_HBV_UNIT_STEPS > 0;
+            const int n_slices = split ? grid_for(chunk, SB2_HBV_UNIT_STEPS) : 1;
+            m->d_tickets.ensure(size_t(1 + g));
+            a.unit_steps = split ? SB2_HBV_UNIT_STEPS : 0; a.tickets = m->d_tickets.p; a.progress = m->d_tickets.p + 1;
+            if (split) CUDA_OK(cudaMemsetAsync(m->d_tickets.p, 0, size_t(1 + g) * sizeof(int), m->stream));
+            if (m->stack == SB2_PT_HS_K) hbv_run_kernel<false><<<g * n_slices, block, 0, m->stream>>>(a);
+            else hbv_run_kernel<true><<<g * n_slices, block, 0, m->stream>>>(a);
         }
         CUDA_OK(cudaGetLastError());
         const int64_t total = int64_t(chunk) * m->n_catch();

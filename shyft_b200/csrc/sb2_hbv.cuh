@@ -90,6 +90,9 @@ struct HbvRunArgs {
     int64_t n_slots;
     int* __restrict__ error_flag;
     int collect;  // bits as SB2_COLLECT_*
+    int unit_steps;              // > 0: the chunk is stepped in time slices of this many steps handed out by ticket (as ptgsk_response_kernel)
+    int* __restrict__ tickets;   // [1] ticket counter, zeroed per launch
+    int* __restrict__ progress;  // [cell groups] finished slices per group, zeroed per launch
 };
 
 // hbv_snow_common::integrate(f, x, n, a = x[0], b, f_b_is_zero), core/hbv_snow_common.h:14-43
@@ -243,7 +246,30 @@ __device__ __forceinline__ bool hbv_snow_step(double (&sp)[HBV_NB], double (&sw)
 template <bool HBV_STACK>
 __global__ void __launch_bounds__(128, (HBV_STACK ? SB2_HBV_MINBLOCKS_S : SB2_HBV_MINBLOCKS_K)) hbv_run_kernel(const HbvRunArgs a) {
     constexpr int NS = HBV_STACK ? 5 + 2 * HBV_NB : 3 + 2 * HBV_NB;
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // Time split by ticket (see ptgsk_response_kernel): 12 500 one-warp blocks of a 400 000-cell shard are 4-5 waves of the 2 400-3 000
+    // resident ones, so whole-chunk blocks leave a ragged last wave; slices of unit_steps steps shrink that tail to one slice.  A block
+    // waits until the previous slice of its cell group has published the state; tickets are handed out in start order, so that slice
+    // always belongs to a block already running or done.
+    int64_t group = blockIdx.x;
+    int i_begin = 0, i_end = a.n_steps, slice = 0;
+    int* progress = nullptr;
+    if (a.unit_steps > 0) {
+        __shared__ int s_ticket;
+        const int n_groups = int((a.n_cells + blockDim.x - 1) / blockDim.x);
+        if (threadIdx.x == 0) s_ticket = atomicAdd(a.tickets, 1);
+        __syncthreads();
+        slice = s_ticket / n_groups;
+        group = s_ticket - slice * n_groups;
+        i_begin = slice * a.unit_steps;
+        i_end = min(a.n_steps, i_begin + a.unit_steps);
+        progress = a.progress + group;
+        if (threadIdx.x == 0) {
+            while (*((volatile int*)progress) < slice) __nanosleep(256);
+            __threadfence();
+        }
+        __syncthreads();
+    }
+    const int64_t c = group * blockDim.x + threadIdx.x;
     const bool in_range = c < a.n_cells;
     const int64_t cc = in_range ? c : a.n_cells - 1;
     const bool active = in_range && (a.active == nullptr || a.active[cc] != 0);
@@ -260,13 +286,14 @@ __global__ void __launch_bounds__(128, (HBV_STACK ? SB2_HBV_MINBLOCKS_S : SB2_HB
     const double land_fraction = 1 - direct_response_fraction;  // kirchner_fraction in pt_hs_k
     const double glacier_area_m2 = cell_area_m2 * glacier_fraction;
 
-    double swe = a.state[0 * n + cc], sca = a.state[1 * n + cc];
+    // __ldcg: the state may have been written by the previous time slice on another SM a moment ago -- read it from L2
+    double swe = __ldcg(a.state + 0 * n + cc), sca = __ldcg(a.state + 1 * n + cc);
     double sp[HBV_NB], sw[HBV_NB];
 #pragma unroll
-    for (int i = 0; i < HBV_NB; ++i) { sp[i] = a.state[(2 + i) * n + cc]; sw[i] = a.state[(2 + HBV_NB + i) * n + cc]; }
-    double x0 = a.state[(2 + 2 * HBV_NB) * n + cc];                      // kirchner.q | soil.sm
-    double x1 = HBV_STACK ? a.state[(3 + 2 * HBV_NB) * n + cc] : 0.0;    // tank.uz
-    double x2 = HBV_STACK ? a.state[(4 + 2 * HBV_NB) * n + cc] : 0.0;    // tank.lz
+    for (int i = 0; i < HBV_NB; ++i) { sp[i] = __ldcg(a.state + (2 + i) * n + cc); sw[i] = __ldcg(a.state + (2 + HBV_NB + i) * n + cc); }
+    double x0 = __ldcg(a.state + (2 + 2 * HBV_NB) * n + cc);                      // kirchner.q | soil.sm
+    double x1 = HBV_STACK ? __ldcg(a.state + (3 + 2 * HBV_NB) * n + cc) : 0.0;    // tank.uz
+    double x2 = HBV_STACK ? __ldcg(a.state + (4 + 2 * HBV_NB) * n + cc) : 0.0;    // tank.lz
 
     int my_slot = -1;
     bool head = false;
@@ -287,7 +314,7 @@ __global__ void __launch_bounds__(128, (HBV_STACK ? SB2_HBV_MINBLOCKS_S : SB2_HB
     };
 
     bool failed_snow = false, failed_k = false;
-    for (int i = 0; i < a.n_steps; ++i) {
+    for (int i = i_begin; i < i_end; ++i) {
         const int64_t o = (int64_t)i * n + cc;
         const int64_t step = a.first_step + i;
         const int64_t orow = (step - a.out_first_step) * n + cc;
@@ -377,7 +404,7 @@ __global__ void __launch_bounds__(128, (HBV_STACK ? SB2_HBV_MINBLOCKS_S : SB2_HB
         }
     }
     if (active) {
-        if ((a.collect & 8) && a.collect_end_state) collect_state((a.first_step + a.n_steps - a.out_first_step) * n + cc);
+        if ((a.collect & 8) && a.collect_end_state && i_end == a.n_steps) collect_state((a.first_step + a.n_steps - a.out_first_step) * n + cc);
         a.state[0 * n + cc] = swe; a.state[1 * n + cc] = sca;
 #pragma unroll
         for (int i = 0; i < HBV_NB; ++i) { a.state[(2 + i) * n + cc] = sp[i]; a.state[(2 + HBV_NB + i) * n + cc] = sw[i]; }
@@ -386,6 +413,11 @@ __global__ void __launch_bounds__(128, (HBV_STACK ? SB2_HBV_MINBLOCKS_S : SB2_HB
         if (failed_snow) atomicOr(a.error_flag, ERR_HBV_NEGATIVE_OUTFLOW);
         if (failed_k) atomicOr(a.error_flag, ERR_KIRCHNER_STEP);
         (void)NS;
+    }
+    if (progress != nullptr) {  // publish this slice: the state stores above, then the counter
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) atomicExch(progress, slice + 1);
     }
 }
 

@@ -24,6 +24,7 @@ VARIANTS = {
     "hbvk5": ["-DSB2_HBV_MINBLOCKS_K=5"], "hbvs4": ["-DSB2_HBV_MINBLOCKS_S=4"], "hbvs6": ["-DSB2_HBV_MINBLOCKS_S=6"],
     # forcing-terms kernel: registers (blocks of 128 per SM), steps per thread
     "A8": ["-DSB2_MINBLOCKS_A=8"], "A9": ["-DSB2_MINBLOCKS_A=9"], "A10": ["-DSB2_MINBLOCKS_A=10"], "As4": ["-DSB2_STEPS_A=4"], "As16": ["-DSB2_STEPS_A=16"],
+    "hbvus0": ["-DSB2_HBV_UNIT_STEPS=0"], "hbvus32": ["-DSB2_HBV_UNIT_STEPS=32"], "hbvus128": ["-DSB2_HBV_UNIT_STEPS=128"],
     "pf0": ["-DSB2_PREFETCH_AHEAD=0"], "pf2": ["-DSB2_PREFETCH_AHEAD=2"], "pf8": ["-DSB2_PREFETCH_AHEAD=8"],
 }
 out_dir = os.path.join(_build.ROOT, "build")
