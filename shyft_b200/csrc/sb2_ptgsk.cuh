@@ -815,10 +815,13 @@ __device__ __forceinline__ void prefetch_l1(const double* p) { asm volatile("pre
 #define SB2_MINBLOCKS_C 16
 #endif
 
-#ifndef SB2_MINBLOCKS_A
-#define SB2_MINBLOCKS_A 1
-#endif
+// no minimum-blocks bound: left to itself the compiler settles on 72 registers (28 resident warps); (128, 1) lets it take 94 and costs
+// 2.4 ms per year, (128, 8..10) = 64..48 registers measured no gain (tools/build_variants.py A8..A10)
+#ifdef SB2_MINBLOCKS_A
 __global__ void __launch_bounds__(SB2_BLOCK_A, SB2_MINBLOCKS_A) ptgsk_forcing_terms_kernel(const PtgskRunArgs a) {
+#else
+__global__ void __launch_bounds__(SB2_BLOCK_A) ptgsk_forcing_terms_kernel(const PtgskRunArgs a) {
+#endif
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= a.n_cells) return;
     if (a.active != nullptr && a.active[c] == 0) return;
