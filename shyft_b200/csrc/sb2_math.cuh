@@ -381,6 +381,10 @@ __device__ __forceinline__ void gamma_p_pair_inl(double a1, double x1, bool need
     }
 }
 
+__device__ __noinline__ void gamma_p_pair(double a1, double x1, double pre1, double a2, double x2, double pre2, double& P1, double& P2) {
+    gamma_p_pair_inl(a1, x1, true, pre1, a2, x2, true, pre2, P1, P2);
+}
+
 __device__ __forceinline__ double gamma_p(double a, double x, double lgamma_a) {
     if (!(x > 0.0)) return 0.0;
     if (x == inf_()) return 1.0;

@@ -137,6 +137,9 @@ __device__ __forceinline__ double gs_calc_q(double a, double b, double z, double
     return a * b * gamma_p(a + 1.0, x, lg_a1) + z * (1.0 - gamma_p(a, x, lg_a));
 }
 
+#ifndef SB2_LWC_PAIR
+#define SB2_LWC_PAIR 0  // Brent objective: P(a+1, x) and P(a, x) advanced together (gamma_p_pair) instead of two calls
+#endif
 #ifndef SB2_LWC_FLAT
 #define SB2_LWC_FLAT 0  // Brent objective with log / exp expanded in place (0: the shared out-of-line copies)
 #endif
@@ -161,8 +164,12 @@ __device__ __noinline__ double gs_corr_lwc(double z1, double a1, double b1, doub
             const double lx = sb_log(x);
             const double pre1 = sb_exp((a2 + 1.0) * lx - x - lg_a21), pre0 = sb_exp(a2 * lx - x - lg_a2);
 #endif
+#if SB2_LWC_PAIR
+            gamma_p_pair(a2 + 1.0, x, pre1, a2, x, pre0, p1, p0);  // both values in one pair of loops (bit-identical, sb2_math.cuh)
+#else
             p1 = gamma_p_with_prefix(a2 + 1.0, x, pre1);
             p0 = gamma_p_with_prefix(a2, x, pre0);
+#endif
         }
         const double d = (a2 * b2 * p1 + z * (1.0 - p0)) - Q1;
         return d * d;

@@ -25,6 +25,7 @@ VARIANTS = {
     # forcing-terms kernel: registers (blocks of 128 per SM), steps per thread
     "A8": ["-DSB2_MINBLOCKS_A=8"], "A9": ["-DSB2_MINBLOCKS_A=9"], "A10": ["-DSB2_MINBLOCKS_A=10"], "As4": ["-DSB2_STEPS_A=4"], "As16": ["-DSB2_STEPS_A=16"],
     "hbvus0": ["-DSB2_HBV_UNIT_STEPS=0"], "hbvus32": ["-DSB2_HBV_UNIT_STEPS=32"], "hbvus128": ["-DSB2_HBV_UNIT_STEPS=128"],
+    "lwcpair": ["-DSB2_LWC_PAIR=1"],
     "pf0": ["-DSB2_PREFETCH_AHEAD=0"], "pf2": ["-DSB2_PREFETCH_AHEAD=2"], "pf8": ["-DSB2_PREFETCH_AHEAD=8"],
 }
 out_dir = os.path.join(_build.ROOT, "build")
