@@ -58,3 +58,30 @@ def device_catchment_discharges(model):
     import torch
     ptr, rows, cols = model.device_catchment_discharges()
     return torch.as_tensor(DeviceArrayView(ptr, rows, cols), device="cuda")
+
+
+# ---- calibration ensembles: the parameter sets are sharded, the cells are not ----------------------------------
+def partition_parameter_sets(n_sets, world_size, rank):
+    """Contiguous, balanced range of a population's parameter sets for this rank -> (begin, end); every rank holds all cells."""
+    return partition_cells(n_sets, world_size, rank)
+
+
+def gather_goal_values(local_goals, n_sets, device=None):
+    """All ranks' goal-function values in population order on every rank: one all_gather of one fp64 per set (ragged shards padded),
+    no collective on the data path.  `local_goals` = this rank's values for partition_parameter_sets(n_sets, world, rank)."""
+    import torch
+    import torch.distributed as dist
+    local = torch.as_tensor(np.asarray(local_goals, dtype=np.float64))
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return local.numpy().copy()
+    world, rank = dist.get_world_size(), dist.get_rank()
+    width = -(-int(n_sets) // world)
+    buf = torch.full((width,), float("nan"), dtype=torch.float64, device=device)
+    buf[: local.numel()] = local.to(buf.device)
+    parts = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(parts, buf)
+    out = np.empty(int(n_sets))
+    for r in range(world):
+        b, e = partition_parameter_sets(n_sets, world, r)
+        out[b:e] = parts[r][: e - b].cpu().numpy()
+    return out

@@ -74,3 +74,27 @@ def test_world_size_2_gloo_catchment_reduce(tmp_path):
         ok, b, e = np.load(tmp_path / f"ok_{r}.npy")
         assert ok == 1.0
     assert np.load(tmp_path / "ok_0.npy")[2] == np.load(tmp_path / "ok_1.npy")[1]
+
+
+def _ensemble_worker(rank, world, port, n_sets, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from shyft_b200 import sharding
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    goal = lambda i: 0.25 * i * i - 3.0 * i            # stand-in for one goal-function evaluation of parameter set i
+    b, e = sharding.partition_parameter_sets(n_sets, world, rank)
+    got = sharding.gather_goal_values([goal(i) for i in range(b, e)], n_sets)
+    np.save(os.path.join(out_dir, f"goals_{rank}.npy"), got)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_parameter_set_sharding(tmp_path):
+    """BASELINE config 5: the population is split over the ranks, every rank gets all goal values back in population order"""
+    import torch.multiprocessing as mp
+    n_sets = 37                                          # ragged: 19 + 18
+    mp.spawn(_ensemble_worker, args=(2, _free_port(), n_sets, str(tmp_path)), nprocs=2, join=True)
+    want = np.array([0.25 * i * i - 3.0 * i for i in range(n_sets)])
+    for r in range(2):
+        assert np.array_equal(np.load(tmp_path / f"goals_{r}.npy"), want)

@@ -56,9 +56,17 @@ if 3 in which:  # pt_hs_k and hbv_stack, 400k cells x 5 years hourly, river rout
         del m
 
 if 5 in which:  # calibration ensemble: parameter sets x 10k-cell catchment x 3 years hourly, NSE goal
+    # under torchrun (python -m torch.distributed.run --nproc-per-node N tools/bench_configs.py 5) the population is sharded over the
+    # ranks, every rank holds all cells; the only exchange is one all_gather of the goal values (shyft_b200/sharding.py)
+    import torch.distributed as dist
+    from shyft_b200 import sharding
+    world, rank, local_rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n, T, sets = 10000, 26280, int(os.environ.get("SB2_C5_SETS", "256"))
     geo, ta, env = synthetic.make_region(n, T, 64, config_index=4)
-    m = sb.PTGSKOptModel(geo, PTGSK)
+    m = sb.PTGSKOptModel(geo, PTGSK, device=local_rank)
     m.run_interpolation(sb.InterpolationParameter(), ta, env)
     m.set_states(synthetic.default_state(0, n))
     m.run_cells()
@@ -69,13 +77,27 @@ if 5 in which:  # calibration ensemble: parameter sets x 10k-cell catchment x 3 
     P[:, 0] = rng.uniform(-3.0, -1.9, sets); P[:, 1] = rng.uniform(0.8, 0.99, sets); P[:, 2] = rng.uniform(-0.15, -0.05, sets)
     P[:, 3] = rng.uniform(0.5, 2.5, sets); P[:, 4] = rng.uniform(-2, 2, sets); P[:, 5] = rng.uniform(1, 4, sets)
     P[:, 14] = rng.uniform(0.2, 0.8, sets); P[:, 16] = rng.uniform(0.8, 1.4, sets)
+    b, e = sharding.partition_parameter_sets(sets, world, rank)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
-    g = opt.calculate_goal_function_batch(P)
+    g_local = opt.calculate_goal_function_batch(P[b:e])
+    g = sharding.gather_goal_values(g_local, sets, device=torch.device("cuda", local_rank) if world > 1 else None)
     torch.cuda.synchronize()
     s = time.perf_counter() - t0
+    if world > 1:
+        t_all = torch.tensor([s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+        s = float(t_all.item())
+        if rank != 0:
+            dist.barrier(); dist.destroy_process_group(); sys.exit(0)
     t0 = time.perf_counter()
     g1 = np.array([opt.calculate_goal_function(p) for p in P[:8]])
     s1 = (time.perf_counter() - t0) / 8
-    print(json.dumps({"config": 5, "sets": sets, "cells": n, "steps": T, "batch_seconds": s, "cell_steps_per_s": sets * n * T / s,
+    print(json.dumps({"config": 5, "n_gpus": world, "sets": sets, "cells": n, "steps": T, "batch_seconds": s, "cell_steps_per_s": sets * n * T / s,
                       "one_at_a_time_seconds_per_set": s1, "cell_steps_per_s_one_at_a_time": n * T / s1, "batch_equals_single": bool(np.array_equal(g[:8], g1)),
                       "best_goal": float(g.min()), "extrapolated_4096_sets_seconds": s * 4096 / sets}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
