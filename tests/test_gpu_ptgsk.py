@@ -125,11 +125,11 @@ def _oracle_forcing(oracle, geo, ta, env, ip_idw=True):
     return gm, f
 
 
-@pytest.mark.parametrize("collect", ["all+state", "discharge"])
-def test_config1_slice_parity_through_a_winter(sb, oracle, collect):
-    """BASELINE config 1 shape (synthetic cells x 1 year hourly, IDW interpolation), 256 cells: every collected series and
-    the end state against the oracle, step by step."""
-    n, T, S = 256, 8760, 16
+@pytest.mark.parametrize("collect,n", [("all+state", 256), ("discharge", 1000)])
+def test_config1_slice_parity_through_a_winter(sb, oracle, collect, n):
+    """BASELINE configs[0] (1 000 synthetic cells x 1 year hourly, IDW interpolation, discharge collector) in full, and 256 cells of it
+    with every response and state series collected: each series and the end state against the oracle, step by step."""
+    T, S = 8760, 16
     geo, ta, env, st0 = _synthetic(sb, n, T, S, config_index=0, cells_per_catchment=100)
     m = (sb.PTGSKModel if collect == "all+state" else sb.PTGSKOptModel)(geo, PTGSK_DEFAULT)
     ip = sb.InterpolationParameter(use_idw_for_temperature=1)
