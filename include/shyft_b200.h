@@ -216,8 +216,9 @@ int sb2_river_flows(sb2_model* m, int64_t rid, int64_t start_step, int64_t n_ste
 enum { SB2_GOAL_NASH_SUTCLIFFE = 0, SB2_GOAL_KLING_GUPTA = 1, SB2_GOAL_ABS_DIFF = 2, SB2_GOAL_RMSE = 3 };             /* target_spec_calc_type :217-222 */
 enum { SB2_TARGET_DISCHARGE = 0, SB2_TARGET_SNOW_COVERED_AREA = 1, SB2_TARGET_SNOW_WATER_EQUIVALENT = 2,
        SB2_TARGET_ROUTED_DISCHARGE = 3, SB2_TARGET_CELL_CHARGE = 4 };                                                  /* target_property_type :225-231 */
-/* target_specification (:242-329).  The target series lives on its own fixed_dt axis, which must be aligned with the model
- * axis (start on a model step, dt a whole multiple of the model dt, inside the model axis). */
+/* target_specification (:242-329).  The target series lives on its own axis: fixed_dt {t0_us, dt_us, n} -- periods that are whole
+ * runs of model steps are reduced in the goal kernel itself, any other fixed_dt axis is projected first -- or, when period_points_us
+ * is set, a point axis of n periods [period_points_us[i], period_points_us[i+1]) (n + 1 strictly increasing times; time_axis::point_dt). */
 typedef struct sb2_target {
     const double* values; int64_t t0_us, dt_us, n;
     const int64_t* catchment_ids; int32_t n_catchments;
@@ -225,6 +226,7 @@ typedef struct sb2_target {
     double scale_factor;
     int32_t calc_mode, property;
     double s_r, s_a, s_b;           /* Kling-Gupta weights */
+    const int64_t* period_points_us; /* NULL: the fixed_dt axis above */
 } sb2_target;
 /* optimizer(model, targets, ...) + prepare_optimize (:517-552): stores the targets, switches snow collection on when a target
  * needs it, sets the calculation filter to the union of the target catchments, snapshots the initial state if unset. */

@@ -22,9 +22,15 @@ class TargetSpecification:
     """target_specification<PS> (:242-329): observed series on its own fixed axis + what it is compared with."""
 
     def __init__(self, values, start, delta_t, catchment_indexes=(), scale_factor=1.0, calc_mode=NASH_SUTCLIFFE, s_r=1.0, s_a=1.0, s_b=1.0,
-                 catchment_property=DISCHARGE, river_id=0, uid=""):
+                 catchment_property=DISCHARGE, river_id=0, uid="", time_points=None):
+        """`start`, `delta_t` [s]: a fixed_dt target axis; or `time_points` [s]: len(values) + 1 period boundaries of a point axis"""
         self.values = f64(values)
         self.start, self.delta_t = int(start), int(delta_t)
+        self.time_points_us = None
+        if time_points is not None:
+            self.time_points_us = np.ascontiguousarray(np.round(np.asarray(time_points, dtype=np.float64) * USEC), dtype=np.int64)
+            if self.time_points_us.size != self.values.size + 1:
+                raise RuntimeError("time_points must hold one more entry than values (the end of the last period)")
         self.catchment_indexes = np.ascontiguousarray(catchment_indexes, dtype=np.int64)
         self.scale_factor, self.calc_mode, self.catchment_property = float(scale_factor), int(calc_mode), int(catchment_property)
         self.s_r, self.s_a, self.s_b, self.river_id, self.uid = float(s_r), float(s_a), float(s_b), int(river_id), uid
@@ -48,6 +54,7 @@ class Optimizer:
             a.n_catchments = t.catchment_indexes.size
             a.river_id, a.scale_factor, a.calc_mode, a.property = t.river_id, t.scale_factor, t.calc_mode, t.catchment_property
             a.s_r, a.s_a, a.s_b = t.s_r, t.s_a, t.s_b
+            a.period_points_us = t.time_points_us.ctypes.data_as(capi.c_i64p) if t.time_points_us is not None else None
         self.model._ck(self.model._L.sb2_set_targets(self.model._h, C.c_int(len(self.targets)), arr))
 
     def calculate_goal_function(self, p):

@@ -58,7 +58,7 @@ class Target(C.Structure):
     """sb2_target: target_specification (core/model_calibration.h:242-329)"""
     _fields_ = [("values", c_dp), ("t0_us", C.c_int64), ("dt_us", C.c_int64), ("n", C.c_int64), ("catchment_ids", c_i64p),
                 ("n_catchments", C.c_int32), ("river_id", C.c_int64), ("scale_factor", C.c_double), ("calc_mode", C.c_int32),
-                ("property", C.c_int32), ("s_r", C.c_double), ("s_a", C.c_double), ("s_b", C.c_double)]
+                ("property", C.c_int32), ("s_r", C.c_double), ("s_a", C.c_double), ("s_b", C.c_double), ("period_points_us", c_i64p)]
 
 
 class QAdjustResult(C.Structure):

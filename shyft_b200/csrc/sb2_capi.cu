@@ -242,6 +242,8 @@ struct sb2_model {
         DevArray<double> d_obs, d_series;
         DevArray<int32_t> d_cix;
         bool aligned = true;                      // target periods are whole runs of model steps inside the model axis
+        std::vector<int64_t> points;              // point axis: n + 1 period boundaries (empty: fixed_dt)
+        DevArray<int64_t> d_points;
         DevArray<double> d_projected, d_scale;   // not aligned: the property (and its max-abs scale) projected onto the target axis
     };
     std::vector<std::unique_ptr<Target>> targets;
@@ -907,7 +909,11 @@ void build_goal_targets(sb2_model* m, std::vector<GoalTarget>& gt, const double*
             t.d_projected.resize(size_t(n));
             auto project = [&](int mode, double* out) {
                 goal_property_kernel<<<grid_for(T, 256), 256, 0, m->stream>>>(g.series, T, g.n_col, g.cix, g.n_cix, mode, d_prop.p);
-                average_accessor_kernel<<<grid_for(n, 256), 256, 0, m->stream>>>(m->d_axis_t.p, d_prop.p, T, 1, m->t0 + T * m->dt, 0, t.t0, t.dt, n, out);
+                if (t.points.empty())
+                    average_accessor_kernel<<<grid_for(n, 256), 256, 0, m->stream>>>(m->d_axis_t.p, d_prop.p, T, 1, m->t0 + T * m->dt, 0, t.t0, t.dt, n, out);
+                else
+                    average_accessor_periods_kernel<<<grid_for(n, 256), 256, 0, m->stream>>>(m->d_axis_t.p, d_prop.p, T, m->t0 + T * m->dt, 0,
+                                                                                            t.d_points.p, n, out);
                 CUDA_OK(cudaGetLastError());
                 m->launches += 2;
             };
@@ -2049,10 +2055,15 @@ int sb2_set_targets(sb2_model* m, int n_targets, const sb2_target* targets) {
             auto t = std::make_unique<sb2_model::Target>();
             if (s.n <= 0 || !s.values) throw Error("target_specification: empty target time-series");
             if (s.calc_mode < 0 || s.calc_mode > 3 || s.property < 0 || s.property > 4) throw Error("target_specification: unknown calc_mode or property");
-            if (s.dt_us <= 0) throw Error("target_specification: the target time-axis needs a positive delta_t");
+            if (s.period_points_us) {  // point axis
+                t->points.assign(s.period_points_us, s.period_points_us + s.n + 1);
+                for (int64_t i = 1; i <= s.n; ++i)
+                    if (!(t->points[size_t(i)] > t->points[size_t(i) - 1])) throw Error("target_specification: the axis points must be strictly increasing");
+                t->d_points.upload(t->points, m->stream);
+            } else if (s.dt_us <= 0) throw Error("target_specification: the target time-axis needs a positive delta_t");
             // whole runs of model steps inside the model axis are reduced in the goal kernel itself; any other fixed_dt axis goes
             // through the general projection (average_accessor_kernel), as average_accessor<pts_t, ta_t> does it (:859)
-            t->aligned = !(s.dt_us % m->dt != 0 || (s.t0_us - m->t0) % m->dt != 0 || s.t0_us < m->t0 ||
+            t->aligned = !(s.period_points_us != nullptr || s.dt_us % m->dt != 0 || (s.t0_us - m->t0) % m->dt != 0 || s.t0_us < m->t0 ||
                            (s.t0_us - m->t0) / m->dt + int64_t(s.n) * (s.dt_us / m->dt) > m->T);
             t->obs.assign(s.values, s.values + s.n);
             t->t0 = s.t0_us; t->dt = s.dt_us;

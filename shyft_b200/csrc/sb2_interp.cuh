@@ -617,6 +617,12 @@ __global__ void average_accessor_kernel(const int64_t* __restrict__ t /* [n_poin
     const int64_t p_start = ta_t0 + step * ta_dt;
     out[idx] = average_accessor_value(t, values + s, n_src, n_points, t_end, linear, p_start, p_start + ta_dt);
 }
+// One source projected onto an axis given by its period boundaries (time_axis::point_dt: period i = [pts[i], pts[i+1]))
+__global__ void average_accessor_periods_kernel(const int64_t* __restrict__ t, const double* __restrict__ values, int64_t n_points, int64_t t_end,
+                                                int linear, const int64_t* __restrict__ pts /* [n + 1] */, int64_t n, double* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = average_accessor_value(t, values, 1, n_points, t_end, linear, pts[i], pts[i + 1]);
+}
 // The same for sources that each bring their own point axis (every geo_point_ts of a region_environment is a time-series of its own,
 // api/api.h:137-168): source s owns points off[s] .. off[s+1]-1 of the concatenated t / values arrays, its own period end and point
 // interpretation.

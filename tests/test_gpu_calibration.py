@@ -187,3 +187,29 @@ def test_target_axes_not_aligned_with_the_model_axis(sb, oracle, setup):
     # the batch entry evaluates such targets one set at a time
     P = _perturbed(rng, 3)
     assert np.array_equal(opt.calculate_goal_function_batch(P), np.array([opt.calculate_goal_function(x) for x in P]))
+
+
+def test_target_on_a_point_axis(sb, oracle, setup):
+    """a target whose periods are given by explicit points (time_axis::point_dt under apoint_ts, api/boostpython/api_target_specification.cpp:48):
+    irregular periods -- hours, days, a week, with a gap-free but uneven cut -- against the oracle's accumulate_value period by period"""
+    m, geo, gm, ta, st0, f, obs, sel = setup
+    H = 3600 * 10**6
+    T = ta.n
+    p = _perturbed(np.random.default_rng(41), 1)[0]
+    q = oracle.ptgsk_run_cells(gm, p, f, st0, ta.start * 10**6, H, ncore=8)["avg_discharge"][:, sel].sum(axis=1)
+    t_us = ta.start * 10**6 + H * np.arange(T, dtype=np.int64)
+    t_end = ta.start * 10**6 + H * T
+    rng = np.random.default_rng(42)
+    cuts = np.concatenate([[0], np.cumsum(rng.choice([1800, 3600, 5400, 6 * 3600, 86400, 7 * 86400], 60))])
+    cuts = cuts[cuts < (T + 30) * 3600]
+    pts = ta.start + 900 + cuts                                  # seconds; the last periods reach past the model axis
+    n = pts.size - 1
+    sim = np.array([oracle.average_accessor(t_us, q[:, None], t_end, False, int(pts[i]) * 10**6, int(pts[i + 1] - pts[i]) * 10**6, 1)[0, 0]
+                    for i in range(n)])
+    assert np.isfinite(sim).sum() >= n - 3
+    target = np.where(np.isfinite(sim), sim, 1.0) * rng.uniform(0.9, 1.1, n)
+    for mode, fn in ((0, oracle.nash_sutcliffe), (2, oracle.abs_diff_sum), (3, oracle.rmse)):
+        opt = sb.Optimizer(m, [sb.TargetSpecification(target, 0, 0, [1, 2], 1.0, mode, time_points=pts)])
+        assert opt.calculate_goal_function(p) == pytest.approx(fn(target, sim), rel=1e-9), mode
+    with pytest.raises(RuntimeError, match="strictly increasing"):
+        sb.Optimizer(m, [sb.TargetSpecification([1.0, 2.0], 0, 0, [1], time_points=[ta.start, ta.start + 10, ta.start + 10])])
