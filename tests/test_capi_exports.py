@@ -62,3 +62,34 @@ def test_product_does_not_reference_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "libsho_oracle" not in text and "from oracle" not in text and "import oracle" not in text, f
+
+
+def test_ctypes_structs_agree_with_the_c_compiler(tmp_path):
+    """sizeof / offsetof of every struct that crosses the ABI, as gcc lays them out from include/shyft_b200.h, against the ctypes mirrors"""
+    import shutil
+    import subprocess
+    from shyft_b200 import capi
+    from shyft_b200.state_io import ID_DTYPE
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no C compiler")
+    src = tmp_path / "layout.c"
+    src.write_text(r"""
+#include <stdio.h>
+#include <stddef.h>
+#include "shyft_b200.h"
+int main(void) {
+    printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(sb2_geo_cell), sizeof(sb2_idw_parameter), sizeof(sb2_btk_parameter), sizeof(sb2_interpolation_parameter),
+           sizeof(sb2_target), sizeof(sb2_q_adjust_result), sizeof(sb2_cell_state_id));
+    printf("%zu %zu %zu %zu %zu\n", offsetof(sb2_target, n_catchments), offsetof(sb2_target, scale_factor), offsetof(sb2_target, property),
+           offsetof(sb2_target, period_points_us), offsetof(sb2_q_adjust_result, diagnostics));
+    return 0;
+}
+""")
+    exe = tmp_path / "layout"
+    subprocess.check_call([gcc, "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    sizes, offsets = [list(map(int, line.split())) for line in subprocess.check_output([str(exe)], text=True).splitlines()]
+    assert sizes == [capi.GEO_DTYPE.itemsize, ctypes.sizeof(capi.IdwParameter), ctypes.sizeof(capi.BtkParameter),
+                     ctypes.sizeof(capi.InterpolationParameter), ctypes.sizeof(capi.Target), ctypes.sizeof(capi.QAdjustResult), ID_DTYPE.itemsize]
+    assert offsets == [capi.Target.n_catchments.offset, capi.Target.scale_factor.offset, capi.Target.property.offset,
+                       capi.Target.period_points_us.offset, capi.QAdjustResult._diagnostics.offset]
