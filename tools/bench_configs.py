@@ -45,7 +45,7 @@ if 3 in which:  # pt_hs_k and hbv_stack, 400k cells x 5 years hourly, river rout
         def run():
             m.revert_to_initial_state() if run.n else None
             run.n += 1
-            m.run_windowed(ip, window_steps=256)
+            m.run_windowed(ip, window_steps=int(os.environ.get("SB2_C3_WINDOW", "1024")))
             m.river_output_flow_m3s(8)
         run.n = 0
         s = timed(run)
