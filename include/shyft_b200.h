@@ -243,6 +243,14 @@ int sb2_calculate_goal_function_batch(sb2_model* m, int64_t n_sets, const double
  * fn 0 exp(x), 1 log(x), 2 pow(x,y), 3 lgamma(a), 4 gamma_p(a,x), 5 corr_lwc(z1,a1,b1,a2,b2), 6 calc_snow_state(shape,scale,y0,
  * lambda,lwd,max_water_frac,temp_swe) -> swe,sca, 7 kirchner step(c1,c2,c3,dt_hours,q,p,e) -> q,q_avg,ok.  Errors: sb2_last_error(NULL). */
 int sb2_unit_eval(int device, int fn, int64_t n, const double* in, int n_in, double* out, int n_out);
+/* Host-side algorithms of the library, callable without a device (CPU unit tests against the oracle): fn 0 the one-dimensional
+ * minimiser of the state tuning (dlib find_min_single_variable restated, core/model_state_tuning.h:98-108) on
+ * f(x) = (x - a)^2 + b cosh(x - c): in = a b c start begin end eps max_iter -> out = x f(x) evaluations failed(0/1);
+ * fn 1 calendar: in = t_us -> day_of_year, seconds_of_year (core/utctime_utilities.cpp:230-255);
+ * fn 2 make_uhg_from_gamma: in = n_steps alpha beta -> out[0] = length, out[1..] = weights (core/routing.h:399-421);
+ * fn 3 unit-hydrograph steps: in = distance velocity dt_us -> n (core/routing.h:119-123, 326-330).  Returns 0 / 1 (bad arguments). */
+int sb2_host_eval(int fn, const double* in, int n_in, double* out, int n_out);
+
 /* IDW with all station values finite runs as a dense tensor-core contraction (results within ~1e-15 of the per-neighbour
  * weighted mean); on = 0 forces the per-neighbour kernel, which is bit-identical to the reference's operation order. */
 int sb2_set_idw_dense(sb2_model* m, int on);

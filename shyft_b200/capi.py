@@ -78,7 +78,7 @@ sb2_get_initial_state sb2_revert_to_initial_state sb2_adjust_q sb2_adjust_state_
 sb2_set_cell_forcing sb2_get_cell_forcing sb2_set_sources sb2_set_sources_on_axis sb2_set_sources_on_axes sb2_get_sources_on_model_axis sb2_interpolate sb2_is_cell_env_ts_ok sb2_run_cells sb2_run_windowed
 sb2_get_response sb2_get_state_series sb2_catchment_discharges sb2_catchment_charges sb2_statistics_series sb2_statistics_cells
 sb2_statistics_geo sb2_set_river_network sb2_river_flows
-sb2_set_targets sb2_calculate_goal_function sb2_calculate_goal_function_batch sb2_unit_eval sb2_set_idw_dense sb2_set_stream sb2_device_catchment_discharges sb2_device_catchment_charges sb2_kernel_launches sb2_last_run_kernel_ms""".split()
+sb2_set_targets sb2_calculate_goal_function sb2_calculate_goal_function_batch sb2_unit_eval sb2_host_eval sb2_set_idw_dense sb2_set_stream sb2_device_catchment_discharges sb2_device_catchment_charges sb2_kernel_launches sb2_last_run_kernel_ms""".split()
 
 _LIB = None
 
@@ -124,6 +124,15 @@ UNIT_FUNCTIONS = dict(exp=(0, 1, 1), log=(1, 1, 1), pow=(2, 2, 1), lgamma=(3, 1,
                       # the forms the production kernels use (sb2_unit.cuh)
                       exp_flat=(8, 1, 1), log_flat=(9, 1, 1), pow_flat=(10, 2, 1), calc_snow_state_hot=(11, 7, 2), kirchner_step_warp=(12, 7, 3),
                       gamma_p_pair=(13, 4, 2))
+
+
+def host_eval(fn, inputs, n_out):
+    """sb2_host_eval: a host-side algorithm of the library (no device needed) -> out [n_out]"""
+    a = f64(inputs).ravel()
+    out = np.zeros(n_out)
+    if lib().sb2_host_eval(C.c_int(fn), dptr(a), C.c_int(a.size), dptr(out), C.c_int(n_out)) != 0:
+        raise RuntimeError("sb2_host_eval: bad arguments")
+    return out
 
 
 def unit_eval(fn, inputs, device=0):

@@ -2159,6 +2159,50 @@ int sb2_unit_eval(int device, int fn, int64_t n, const double* in, int n_in, dou
     }
 }
 
+int sb2_host_eval(int fn, const double* in, int n_in, double* out, int n_out) {
+    try {
+        if (!in || !out) return 1;
+        if (fn == 0) {
+            if (n_in < 8 || n_out < 4) return 1;
+            const double a = in[0], b = in[1], c = in[2];
+            long evals = 0;
+            auto f = [&](double x) { ++evals; return (x - a) * (x - a) + b * std::cosh(x - c); };
+            double x = in[3];
+            out[3] = 0.0;
+            try {
+                out[1] = host::find_min_single_variable(f, x, in[4], in[5], in[6], long(in[7]));
+            } catch (const host::MinimiserFailure&) {
+                out[1] = std::nan("");
+                out[3] = 1.0;
+            }
+            out[0] = x;
+            out[2] = double(evals);
+            return 0;
+        }
+        if (fn == 1) {
+            if (n_in < 1 || n_out < 2) return 1;
+            out[0] = double(host::day_of_year(int64_t(in[0])));
+            out[1] = double(host::seconds_of_year(int64_t(in[0])));
+            return 0;
+        }
+        if (fn == 2) {
+            if (n_in < 3 || n_out < 1) return 1;
+            const std::vector<double> w = host::make_uhg_from_gamma(int(in[0]), in[1], in[2]);
+            if (int(w.size()) + 1 > n_out) return 1;
+            out[0] = double(w.size());
+            std::copy(w.begin(), w.end(), out + 1);
+            return 0;
+        }
+        if (fn == 3) {
+            if (n_in < 3 || n_out < 1) return 1;
+            out[0] = double(host::uhg_steps(in[0], in[1], int64_t(in[2])));
+            return 0;
+        }
+        return 1;
+    } catch (const std::exception&) {
+        return 1;
+    }
+}
 int sb2_set_idw_dense(sb2_model* m, int on) {
     return guarded(m, [&] { m->force_sparse_idw = on == 0; });
 }
