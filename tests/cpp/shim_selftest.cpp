@@ -52,6 +52,29 @@ int main() {
         std::vector<std::vector<double>> cr2;
         model.catchment_discharges(cr2);
         CHECK(cr2[0] == cr[0]);
+        // state tuning, the reference's Python sequence (test_region_model_stacks.py:317-326) through the shim
+        model.revert_to_initial_state();
+        model.run_cells(0, 10, 2);
+        const std::vector<int64_t> all_cids;
+        const double q_avg = (model.statistics_value(SB2_STAT_RESPONSE, SB2_R_AVG_DISCHARGE, all_cids, 10, SB2_STAT_SUM) +
+                              model.statistics_value(SB2_STAT_RESPONSE, SB2_R_AVG_DISCHARGE, all_cids, 11, SB2_STAT_SUM)) / 2.0;
+        model.revert_to_initial_state();
+        const q_adjust_result adj = model.adjust_state_to_target_flow(0.7 * q_avg, all_cids, 10, 3.0, 1e-3, 350, 2);
+        CHECK(adj.diagnostics.empty());
+        CHECK_NEAR(adj.q_r, 0.7 * q_avg, 0.005);
+        CHECK_NEAR(adj.q_0, q_avg, 0.005);
+        // cell-identified state (api/api_state.h:93-142): extract, modify, apply, extract again
+        std::vector<sb2_cell_state_id> ids;
+        std::vector<double> st;
+        model.extract_state(all_cids, ids, st);
+        CHECK(ids.size() == size_t(n) && ids[3].cid == 1 && ids[3].x == 3500 && ids[3].y == 500 && ids[3].area == 1000000);
+        for (int i = 0; i < n; ++i) st[size_t(i) * 9 + 8] = 100.0 + i;
+        ids[5].x += 1;  // no such cell
+        const std::vector<int64_t> missing = model.apply_state(ids, st, all_cids);
+        CHECK(missing.size() == 1 && missing[0] == 5);
+        std::vector<double> back;
+        model.get_states(back);
+        CHECK(back[4 * 9 + 8] == 104.0 && back[5 * 9 + 8] != 105.0 && back[19 * 9 + 8] == 119.0);
         // argument validation with the reference's messages (:586-592)
         bool threw = false;
         try { model.run_cells(0, T, 1); } catch (const std::runtime_error& e) { threw = std::string(e.what()).find("start_step must in range") != std::string::npos; }
