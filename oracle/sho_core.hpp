@@ -19,7 +19,14 @@
 //  * "parity unpinned": boost::math::gamma_p / lgamma under
 //    policy<digits10<5>> / <digits10<10>> (core/gamma_snow.h:189-201) cannot
 //    be reproduced offline (precision-selected Lanczos tables are not
-//    available); the oracle evaluates them in full double precision.
+//    available); the oracle evaluates them in full double precision.  The one
+//    reference pin that passes through that branch -- the melt-out discharge
+//    0.5 * 0.8333 +- 0.1 % of test/pt_gs_k_test.cpp:234-245 -- holds
+//    (tests/test_oracle_stack_known_answers.py).
+//  * "parity unpinned": dlib 19.16 find_min_single_variable behind
+//    adjust_state_to_target_flow (core/model_state_tuning.h:98-108; restated
+//    in oracle/oracle.py); the reference asserts the reached flow to 2
+//    decimals only, and those asserts hold.
 // ============================================================================
 #pragma once
 #include <algorithm>
