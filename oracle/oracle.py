@@ -36,7 +36,7 @@ def geo_matrix(geo_records):
 
 def build(force=False):
     so = os.path.join(_HERE, "libsho_oracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("capi.cpp", "sho_detmath.hpp", "sho_core.hpp", "sho_pt_gs_k.hpp", "sho_hbv.hpp", "sho_region.hpp", "sho_ts.hpp")]
+    srcs = [os.path.join(_HERE, f) for f in ("capi.cpp", "sho_detmath.hpp", "sho_math_tables.inc", "sho_core.hpp", "sho_pt_gs_k.hpp", "sho_hbv.hpp", "sho_region.hpp", "sho_ts.hpp")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "libsho_oracle.so"], stdout=subprocess.DEVNULL)
     return so

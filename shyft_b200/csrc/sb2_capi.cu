@@ -452,7 +452,7 @@ void launch_step_range(sb2_model* m, int64_t first, int64_t n_steps, bool collec
                 a.scr[k] = m->d_scr[k].p;
             }
             a.ens_scr_stride = 0;
-            ptgsk_forcing_terms_kernel<<<dim3((unsigned)grid_for(n, SB2_BLOCK_A), (unsigned)grid_for(chunk, SB2_STEPS_A)), SB2_BLOCK_A, 0, m->stream>>>(a);
+            ptgsk_forcing_terms_kernel<<<dim3((unsigned)grid_for(n, SB2_BLOCK_A), (unsigned)grid_for(chunk, SB2_STEPS_A)), SB2_BLOCK_A, SB2_MTAB_BYTES, m->stream>>>(a);
             const int gb = grid_for(n, SB2_BLOCK_B), gc = grid_for(n, SB2_BLOCK_C);
             // snow and response kernels in slices of SB2_UNIT_STEPS steps handed out by ticket (see the kernels); counters zeroed per launch
             const bool split = use_time_split(gb);
@@ -461,13 +461,13 @@ void launch_step_range(sb2_model* m, int64_t first, int64_t n_steps, bool collec
             a.unit_steps = split ? SB2_UNIT_STEPS : 0; a.tickets = m->d_tickets.p; a.progress = m->d_tickets.p + 1;
             CUDA_OK(cudaMemsetAsync(m->d_tickets.p, 0, size_t(1 + gb) * sizeof(int), m->stream));
             switch (m->collect_bits & 14) {
-#define SB2_CASE(B) case B: ptgsk_snow_kernel<B><<<gb * n_slices, SB2_BLOCK_B, 0, m->stream>>>(a); break;
+#define SB2_CASE(B) case B: ptgsk_snow_kernel<B><<<gb * n_slices, SB2_BLOCK_B, SB2_MTAB_BYTES, m->stream>>>(a); break;
                 SB2_CASE(0) SB2_CASE(2) SB2_CASE(4) SB2_CASE(6) SB2_CASE(8) SB2_CASE(10) SB2_CASE(12) SB2_CASE(14)
 #undef SB2_CASE
             }
             CUDA_OK(cudaMemsetAsync(m->d_tickets.p, 0, size_t(1 + gc) * sizeof(int), m->stream));
             switch (m->collect_bits & 13) {
-#define SB2_CASE(B) case B: ptgsk_response_kernel<B><<<gc * n_slices, SB2_BLOCK_C, 0, m->stream>>>(a); break;
+#define SB2_CASE(B) case B: ptgsk_response_kernel<B><<<gc * n_slices, SB2_BLOCK_C, SB2_MTAB_BYTES, m->stream>>>(a); break;
                 SB2_CASE(0) SB2_CASE(1) SB2_CASE(4) SB2_CASE(5) SB2_CASE(8) SB2_CASE(9) SB2_CASE(12) SB2_CASE(13)
 #undef SB2_CASE
             }
@@ -493,8 +493,8 @@ void launch_step_range(sb2_model* m, int64_t first, int64_t n_steps, bool collec
             m->d_tickets.ensure(size_t(1 + g));
             a.unit_steps = split ? SB2_HBV_UNIT_STEPS : 0; a.tickets = m->d_tickets.p; a.progress = m->d_tickets.p + 1;
             if (split) CUDA_OK(cudaMemsetAsync(m->d_tickets.p, 0, size_t(1 + g) * sizeof(int), m->stream));
-            if (m->stack == SB2_PT_HS_K) hbv_run_kernel<false><<<g * n_slices, block, 0, m->stream>>>(a);
-            else hbv_run_kernel<true><<<g * n_slices, block, 0, m->stream>>>(a);
+            if (m->stack == SB2_PT_HS_K) hbv_run_kernel<false><<<g * n_slices, block, SB2_MTAB_BYTES, m->stream>>>(a);
+            else hbv_run_kernel<true><<<g * n_slices, block, SB2_MTAB_BYTES, m->stream>>>(a);
         }
         CUDA_OK(cudaGetLastError());
         const int64_t total = int64_t(chunk) * m->n_catch();
@@ -1047,7 +1047,7 @@ void goal_batch_ptgsk(sb2_model* m, int64_t n_sets, const double* P, double* goa
             for (int k = 0; k < 5; ++k) a.scr[k] = d_scr[k].p;
             a.ens_scr_stride = ps * n;
             // the same phase pipeline as run_cells, one grid layer per member
-            ptgsk_forcing_terms_kernel<<<dim3((unsigned)grid_for(n, SB2_BLOCK_A), (unsigned)grid_for(chunk, SB2_STEPS_A), (unsigned)ne), SB2_BLOCK_A, 0,
+            ptgsk_forcing_terms_kernel<<<dim3((unsigned)grid_for(n, SB2_BLOCK_A), (unsigned)grid_for(chunk, SB2_STEPS_A), (unsigned)ne), SB2_BLOCK_A, SB2_MTAB_BYTES,
                                          m->stream>>>(a);
             {
                 const int gb = grid_for(n, SB2_BLOCK_B), gc = grid_for(n, SB2_BLOCK_C);
@@ -1055,9 +1055,9 @@ void goal_batch_ptgsk(sb2_model* m, int64_t n_sets, const double* P, double* goa
                 const int n_slices = split ? grid_for(chunk, SB2_UNIT_STEPS) : 1;
                 a.unit_steps = split ? SB2_UNIT_STEPS : 0; a.tickets = d_tickets.p; a.progress = d_tickets.p + E;
                 CUDA_OK(cudaMemsetAsync(d_tickets.p, 0, d_tickets.n * sizeof(int), m->stream));
-                ptgsk_snow_kernel<0><<<dim3((unsigned)(gb * n_slices), (unsigned)ne), SB2_BLOCK_B, 0, m->stream>>>(a);
+                ptgsk_snow_kernel<0><<<dim3((unsigned)(gb * n_slices), (unsigned)ne), SB2_BLOCK_B, SB2_MTAB_BYTES, m->stream>>>(a);
                 CUDA_OK(cudaMemsetAsync(d_tickets.p, 0, d_tickets.n * sizeof(int), m->stream));
-                ptgsk_response_kernel<0><<<dim3((unsigned)(gc * n_slices), (unsigned)ne), SB2_BLOCK_C, 0, m->stream>>>(a);
+                ptgsk_response_kernel<0><<<dim3((unsigned)(gc * n_slices), (unsigned)ne), SB2_BLOCK_C, SB2_MTAB_BYTES, m->stream>>>(a);
             }
             m->launches += 2;
             CUDA_OK(cudaGetLastError());
@@ -2149,7 +2149,7 @@ int sb2_unit_eval(int device, int fn, int64_t n, const double* in, int n_in, dou
         d_in.upload(in, size_t(n) * n_in, 0);
         d_out.resize(size_t(n) * n_out);
         CUDA_OK(cudaMemsetAsync(d_out.p, 0, size_t(n) * n_out * sizeof(double), 0));
-        unit_eval_kernel<<<grid_for(n, 128), 128>>>(fn, n, d_in.p, n_in, d_out.p, n_out);
+        unit_eval_kernel<<<grid_for(n, 128), 128, SB2_MTAB_BYTES>>>(fn, n, d_in.p, n_in, d_out.p, n_out);
         CUDA_OK(cudaGetLastError());
         CUDA_OK(cudaMemcpy(out, d_out.p, size_t(n) * n_out * sizeof(double), cudaMemcpyDeviceToHost));
         return 0;

@@ -246,6 +246,7 @@ __device__ __forceinline__ bool hbv_snow_step(double (&sp)[HBV_NB], double (&sw)
 template <bool HBV_STACK>
 __global__ void __launch_bounds__(128, (HBV_STACK ? SB2_HBV_MINBLOCKS_S : SB2_HBV_MINBLOCKS_K)) hbv_run_kernel(const HbvRunArgs a) {
     constexpr int NS = HBV_STACK ? 5 + 2 * HBV_NB : 3 + 2 * HBV_NB;
+    sb_math_stage_tables();  // exp / log tables of the shared math spec into this block's shared memory (sb2_math.cuh)
     // Time split by ticket (see ptgsk_response_kernel): 12 500 one-warp blocks of a 400 000-cell shard are 4-5 waves of the 2 400-3 000
     // resident ones, so whole-chunk blocks leave a ragged last wave; slices of unit_steps steps shrink that tail to one slice.  A block
     // waits until the previous slice of its cell group has published the state; tickets are handed out in start order, so that slice
@@ -336,7 +337,7 @@ __global__ void __launch_bounds__(128, (HBV_STACK ? SB2_HBV_MINBLOCKS_S : SB2_HB
                 ae = (1.0 - snow_fraction) * (x0 < p.lp ? pot * (x0 / p.lp) : pot);  // hbv_actual_evapotranspiration.h:32-38
                 {  // hbv_soil::step, hbv_soil.h:59-64
                     const double t = x0 + snow_outflow;
-                    const double of = snow_outflow * sb_pow(t / p.fc, p.beta);
+                    const double of = snow_outflow * sb_pow<true>(t / p.fc, p.beta);
                     soil_outflow = of > t ? t : of;
                     x0 = dmax(0.0, x0 + snow_outflow - soil_outflow - ae);
                 }
@@ -353,7 +354,7 @@ __global__ void __launch_bounds__(128, (HBV_STACK ? SB2_HBV_MINBLOCKS_S : SB2_HB
                 }
                 total_discharge = dmax(0.0, prec - ae) * direct_response_fraction + gm_direct * gm_mmh + tank_outflow * land_fraction;
             } else {
-                ae = pot * (1.0 - sb_exp_flat(-x0 * 3.0 / p.ae_scale_factor)) * (1.0 - dmax(sca, glacier_fraction));
+                ae = pot * (1.0 - sb_exp_flat<true>(-x0 * 3.0 / p.ae_scale_factor)) * (1.0 - dmax(sca, glacier_fraction));
             }
         }
         if (!HBV_STACK) {

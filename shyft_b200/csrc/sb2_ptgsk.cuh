@@ -19,6 +19,8 @@
 
 #include "sb2_math.cuh"
 
+// Every device function of this file reads the exp / log tables from the block's shared memory (sb_*<true>): a kernel that calls
+// into it starts with sb_math_stage_tables() and is launched with SB2_MTAB_BYTES of dynamic shared memory.
 namespace sb2 {
 
 // parameter set as the kernel reads it (host fills it from parameter::set order, core/pt_gs_k.h:77-112)
@@ -134,7 +136,7 @@ __device__ __forceinline__ double m3s_to_mmh(double m3s, double area) { return m
 // calc_q, gamma_snow.h:209-212
 __device__ __forceinline__ double gs_calc_q(double a, double b, double z, double lg_a, double lg_a1) {
     const double x = z / b;
-    return a * b * gamma_p(a + 1.0, x, lg_a1) + z * (1.0 - gamma_p(a, x, lg_a));
+    return a * b * gamma_p<true>(a + 1.0, x, lg_a1) + z * (1.0 - gamma_p<true>(a, x, lg_a));
 }
 
 #ifndef SB2_LWC_PAIR
@@ -145,8 +147,8 @@ __device__ __forceinline__ double gs_calc_q(double a, double b, double z, double
 #endif
 // corr_lwc = boost brent_find_minima(f, 0, z1, bits=12, 60 iterations), gamma_snow.h:214-227
 __device__ __noinline__ double gs_corr_lwc(double z1, double a1, double b1, double a2, double b2) {
-    const double Q1 = gs_calc_q(a1, b1, z1, sb_lgamma(a1), sb_lgamma(a1 + 1.0));
-    const double lg_a2 = sb_lgamma(a2), lg_a21 = sb_lgamma(a2 + 1.0);
+    const double Q1 = gs_calc_q(a1, b1, z1, sb_lgamma<true>(a1), sb_lgamma<true>(a1 + 1.0));
+    const double lg_a2 = sb_lgamma<true>(a2), lg_a21 = sb_lgamma<true>(a2 + 1.0);
     // the objective (calc_q(a2, b2, z) - Q1)^2, ~8 evaluations per search and two incomplete gammas each: log(x) is evaluated once for
     // both prefixes (same argument, same value), the two exp interleave, and P(a2+1, x), P(a2, x) advance together (gamma_p_pair_inl)
     // the objective (calc_q(a2, b2, z) - Q1)^2, ~10 evaluations per search: log(x) is evaluated once for both prefixes (same argument,
@@ -158,11 +160,11 @@ __device__ __noinline__ double gs_corr_lwc(double z1, double a1, double b1, doub
         if (x == inf_()) p1 = p0 = 1.0;
         else if (x > 0.0) {
 #if SB2_LWC_FLAT
-            const double lx = sb_log_flat(x);
-            const double pre1 = sb_exp_flat((a2 + 1.0) * lx - x - lg_a21), pre0 = sb_exp_flat(a2 * lx - x - lg_a2);
+            const double lx = sb_log_flat<true>(x);
+            const double pre1 = sb_exp_flat<true>((a2 + 1.0) * lx - x - lg_a21), pre0 = sb_exp_flat<true>(a2 * lx - x - lg_a2);
 #else
-            const double lx = sb_log(x);
-            const double pre1 = sb_exp((a2 + 1.0) * lx - x - lg_a21), pre0 = sb_exp(a2 * lx - x - lg_a2);
+            const double lx = sb_log<true>(x);
+            const double pre1 = sb_exp<true>((a2 + 1.0) * lx - x - lg_a21), pre0 = sb_exp<true>(a2 * lx - x - lg_a2);
 #endif
 #if SB2_LWC_PAIR
             gamma_p_pair(a2 + 1.0, x, pre1, a2, x, pre0, p1, p0);  // both values in one pair of loops (bit-identical, sb2_math.cuh)
@@ -242,10 +244,10 @@ __device__ __forceinline__ void gs_calc_snow_state_impl(double shape, double sca
         return;
     } else {
         const double x = lambda / scale;
-        if (shape != lg_key) { lg_key = shape; lg_val = sb_lgamma(shape); }
+        if (shape != lg_key) { lg_key = shape; lg_val = sb_lgamma<true>(shape); }
         lg = lg_val;
         have_lg = true;
-        const double pre = gamma_prefix(shape, x, lg);
+        const double pre = gamma_prefix<true>(shape, x, lg);
         y = (x > 0.0) ? gamma_p_with_prefix(shape, x, pre) : 0.0;
         y1 = y - pre / shape;
         swe = m * (1.0 - y1) - lambda * (1 - y);
@@ -256,10 +258,10 @@ __device__ __forceinline__ void gs_calc_snow_state_impl(double shape, double sca
         const double sat = lwd / max_water_frac;
         const double x = sat / scale;
         if (!have_lg) {
-            if (shape != lg_key) { lg_key = shape; lg_val = sb_lgamma(shape); }
+            if (shape != lg_key) { lg_key = shape; lg_val = sb_lgamma<true>(shape); }
             lg = lg_val;
         }
-        const double pre = gamma_prefix(shape, x, lg);
+        const double pre = gamma_prefix<true>(shape, x, lg);
         const double ssa = (x == inf_()) ? 1.0 : gamma_p_with_prefix(shape, x, pre);
         const double ssa1 = ssa - pre / shape;
         const double liqwat = max_water_frac * (m * (ssa1 - y1) + sat * (1.0 - ssa) - lambda * (1.0 - y));
@@ -295,10 +297,10 @@ void gs_calc_snow_state_hot(double shape, double scale, double y0, double lambda
         return;
     } else {
         const double x = lambda / scale;
-        if (shape != lg_key) { lg_key = shape; lg_val = sb_lgamma(shape); }
+        if (shape != lg_key) { lg_key = shape; lg_val = sb_lgamma<true>(shape); }
         lg = lg_val;
         have_lg = true;
-        const double pre = sb_exp_flat(shape * sb_log_flat(x) - x - lg);
+        const double pre = sb_exp_flat<true>(shape * sb_log_flat<true>(x) - x - lg);
         y = (x > 0.0) ? gamma_p_with_prefix_inl(shape, x, pre) : 0.0;
         y1 = y - pre / shape;
         swe = m * (1.0 - y1) - lambda * (1 - y);
@@ -309,10 +311,10 @@ void gs_calc_snow_state_hot(double shape, double scale, double y0, double lambda
         const double sat = lwd / max_water_frac;
         const double x = sat / scale;
         if (!have_lg) {
-            if (shape != lg_key) { lg_key = shape; lg_val = sb_lgamma(shape); }
+            if (shape != lg_key) { lg_key = shape; lg_val = sb_lgamma<true>(shape); }
             lg = lg_val;
         }
-        const double pre = sb_exp_flat(shape * sb_log_flat(x) - x - lg);
+        const double pre = sb_exp_flat<true>(shape * sb_log_flat<true>(x) - x - lg);
         const double ssa = (x == inf_()) ? 1.0 : gamma_p_with_prefix_inl(shape, x, pre);
         const double ssa1 = ssa - pre / shape;
         const double liqwat = max_water_frac * (m * (ssa1 - y1) + sat * (1.0 - ssa) - lambda * (1.0 - y));
@@ -355,10 +357,10 @@ __device__ __forceinline__ void gs_energy_terms(const PtgskParam& p, double BB0,
     const double T_k = T + 273.15;
     const double turb = p.wind_scale * wind_speed + p.wind_const;
     const double vapour_pressure = gs_vapour_pressure(T, rel_hum);
-    lw = 0.98 * sigma * (FLAT ? sb_pow_flat(vapour_pressure / T_k, 6.87e-2) : sb_pow(vapour_pressure / T_k, 6.87e-2)) * sb_pow4(T_k);
+    lw = 0.98 * sigma * (FLAT ? sb_pow_flat<true>(vapour_pressure / T_k, 6.87e-2) : sb_pow<true>(vapour_pressure / T_k, 6.87e-2)) * sb_pow4(T_k);
     const double sst = dmin(0.0, 1.16 * T - 2.09);
     if (sst > -tol) tadd = turb * (T + 1.7 * (vapour_pressure - 6.12)) - BB0;
-    else tadd = turb * (T - sst + 1.7 * (vapour_pressure - 6.132 * (FLAT ? sb_exp_flat(0.103 * T - 0.186) : sb_exp(0.103 * T - 0.186)))) - 0.98 * sigma * sb_pow4(sst + 273.15);
+    else tadd = turb * (T - sst + 1.7 * (vapour_pressure - 6.132 * (FLAT ? sb_exp_flat<true>(0.103 * T - 0.186) : sb_exp<true>(0.103 * T - 0.186)))) - 0.98 * sigma * sb_pow4(sst + 273.15);
 }
 
 // Division sites of the step body: in line (default) or through one shared out-of-line copy (SB2_GS_DIV_CALL=1, a smaller per-step code
@@ -540,11 +542,11 @@ __device__ __forceinline__ double pt_potential_evapotranspiration(double land_al
     const double ck2 = neg ? 17.84362 : 17.08085;
     const double ck3 = neg ? 245.425 : 234.175;
     const double ctt_inv = 1 / (ck3 + temperature);
-    const double sat_pressure = ck1 * (FLAT ? sb_exp_flat(ck2 * temperature * ctt_inv) : sb_exp(ck2 * temperature * ctt_inv));
+    const double sat_pressure = ck1 * (FLAT ? sb_exp_flat<true>(ck2 * temperature * ctt_inv) : sb_exp<true>(ck2 * temperature * ctt_inv));
     const double delta = sat_pressure * ck2 * ck3 * ctt_inv * ctt_inv;
     const double vapour_pressure = sat_pressure * rhumidity;
     const double k_temp = temperature + 273.15;
-    const double e_atm = 1.24 * (FLAT ? sb_pow_flat(10 * vapour_pressure / k_temp, 0.143) : sb_pow(10 * vapour_pressure / k_temp, 0.143)) * (0.85 + 0.5 * rhumidity);
+    const double e_atm = 1.24 * (FLAT ? sb_pow_flat<true>(10 * vapour_pressure / k_temp, 0.143) : sb_pow<true>(10 * vapour_pressure / k_temp, 0.143)) * (0.85 + 0.5 * rhumidity);
     const double net_radiation = bolz * sb_pow4(k_temp) * (e_atm - 0.98) + global_radiation * (1.0 - land_albedo);
     const double epot = alpha * delta * net_radiation / (delta + psycr);
     if (epot < 0.0) return 0.0;
@@ -555,8 +557,8 @@ __device__ __forceinline__ double pt_potential_evapotranspiration(double land_al
 // the right-hand side d ln q / dt (kirchner.h:186-198); out of line so that the seven Runge-Kutta stages share one copy of
 // the two exponentials (the step loop then stays inside the instruction cache)
 __device__ __noinline__ double kirchner_rhs(double c1, double c2, double c3, double pe, double x) {
-    const double g = sb_exp_inl(c1 + c2 * x + c3 * x * x);  // the two exponentials interleave
-    return g >= 1.e-30 ? g * (pe * sb_exp_inl(-x) - 1.0) : 0.0;
+    const double g = sb_exp_inl<true>(c1 + c2 * x + c3 * x * x);  // the two exponentials interleave
+    return g >= 1.e-30 ? g * (pe * sb_exp_inl<true>(-x) - 1.0) : 0.0;
 }
 // INL = true: the response kernel, whose whole step loop is ~1 000 instructions and stays inside the instruction cache when
 // every exp/log is expanded in place (no call / argument shuffling, coefficients in uniform registers)
@@ -565,8 +567,8 @@ struct KirchnerRhs {
     double c1, c2, c3, pe;  // pe = p - e
     __device__ __forceinline__ double operator()(double x) const {
         if (INL) {
-            const double g = sb_exp_inl(c1 + c2 * x + c3 * x * x);
-            return g >= 1.e-30 ? g * (pe * sb_exp_inl(-x) - 1.0) : 0.0;
+            const double g = sb_exp_inl<true>(c1 + c2 * x + c3 * x * x);
+            return g >= 1.e-30 ? g * (pe * sb_exp_inl<true>(-x) - 1.0) : 0.0;
         }
         return kirchner_rhs(c1, c2, c3, pe, x);
     }
@@ -605,7 +607,7 @@ template <bool INL = false>
 __device__ __forceinline__ bool kirchner_step(double c1, double c2, double c3, double t1, double& q, double& q_avg, double p, double e) {
     const double eps_abs = 1.0e-7, eps_rel = 1.0e-8;
     if (q < 0.00001) q = 0.00001;
-    double x = INL ? sb_log_inl(q) : sb_log(q);
+    double x = INL ? sb_log_inl<true>(q) : sb_log<true>(q);
     double t = 0.0, dt = t1;
     const KirchnerRhs<INL> rhs{c1, c2, c3, p - e};
     double dxdt = rhs(x);
@@ -648,19 +650,19 @@ __device__ __forceinline__ bool kirchner_step(double c1, double c2, double c3, d
             }
             const double err = err_num / err_den;
             if (err > 1.0) {
-                dt *= dmax(9.0 / 10.0 * sb_pow(err, -1.0 / (4 - 1)), 1.0 / 5.0);
+                dt *= dmax(9.0 / 10.0 * sb_pow<true>(err, -1.0 / (4 - 1)), 1.0 / 5.0);
                 if (++fails >= 500) return false;
                 continue;
             }
             t += dt;
             // the grown dt is only ever used by a following sub-step of this model step (initialize() resets it)
-            if (err < 0.5 && t < t1) dt *= 9.0 / 10.0 * sb_pow(dmax(0.00032, err), -1.0 / 5);
+            if (err < 0.5 && t < t1) dt *= 9.0 / 10.0 * sb_pow<true>(dmax(0.00032, err), -1.0 / 5);
             break;
         }
         x_old = x; k1 = dxdt; k7 = dxdt_new;
         x = x_new; dxdt = dxdt_new;
         if (t < t1) {
-            const double fq = INL ? sb_exp_inl(x) : sb_exp(x);
+            const double fq = INL ? sb_exp_inl<true>(x) : sb_exp<true>(x);
             area += 0.5 * (f_a + fq) * (t - t_a);
             f_a = fq; t_a = t;
         }
@@ -668,7 +670,7 @@ __device__ __forceinline__ bool kirchner_step(double c1, double c2, double c3, d
     // One accepted sub-step of the whole model step (t_old = 0, t = t1; > 99.9 % of all steps): theta = 1 exactly, every b_i(theta)
     // collapses to the tableau's b_i (A = 1, B = C = D = 0, all exact) and b7(theta) = 0, i.e. calc_state(t1) is x_new bit for bit.
     if (!(t_old == 0.0 && t == t1 && fabs(k7) < inf_())) x = kirchner_calc_state(x_old, t - t_old, (t1 - t_old) / (t - t_old), k1, k3, k4, k5, k6, k7);
-    q = INL ? sb_exp_inl(x) : sb_exp(x);
+    q = INL ? sb_exp_inl<true>(x) : sb_exp<true>(x);
     area += 0.5 * (f_a + q) * (t1 - t_a);
     q_avg = (t1 == 1.0) ? area : area / (t1 - 0.0);  // x / 1.0 = x
     return true;
@@ -693,10 +695,10 @@ __constant__ double kDopri[27] = {
 __device__ __forceinline__ double kirchner_rhs_flat(double c1, double c2, double c3, double pe, double x) {
     // both exponentials through one range test, so that the two polynomials (four independent fma chains) interleave
     const double a = c1 + c2 * x + c3 * x * x;
-    int ka, kx;
-    const double pa = sb_exp_core(a, ka), px = sb_exp_core(-x, kx);
-    double g = __hiloint2double(__double2hiint(pa) + (ka << 20), __double2loint(pa));
-    double ex = __hiloint2double(__double2hiint(px) + (kx << 20), __double2loint(px));
+    int ea, ex_;
+    const double va = sb_exp_core<true>(a, ea), vx = sb_exp_core<true>(-x, ex_);
+    double g = sb_scale2(va, ea);
+    double ex = sb_scale2(vx, ex_);
     if (!(fabs(a) < 690.0 && fabs(x) < 690.0)) { g = sb_exp_slow(a); ex = sb_exp_slow(-x); }
     const double h = g * (pe * ex - 1.0);
     return g >= kDopri[26] ? h : 0.0;
@@ -704,7 +706,7 @@ __device__ __forceinline__ double kirchner_rhs_flat(double c1, double c2, double
 __device__ __forceinline__ bool kirchner_step_warp(double c1, double c2, double c3, double t1, double& q, double& q_avg, double p, double e) {
     const double eps_abs = 1.0e-7, eps_rel = 1.0e-8;
     if (q < 0.00001) q = 0.00001;
-    double x = sb_log_inl(q);
+    double x = sb_log_inl<true>(q);
     double t = 0.0, dt = t1;
     const double pe = p - e;
     double dxdt = kirchner_rhs_flat(c1, c2, c3, pe, x);
@@ -749,16 +751,16 @@ __device__ __forceinline__ bool kirchner_step_warp(double c1, double c2, double 
             } else {
                 const double err = err_num / err_den;
                 if (err > 1.0) {
-                    dt *= dmax(9.0 / 10.0 * sb_pow(err, -1.0 / (4 - 1)), 1.0 / 5.0);
+                    dt *= dmax(9.0 / 10.0 * sb_pow<true>(err, -1.0 / (4 - 1)), 1.0 / 5.0);
                     if (++fails >= 500) { failed = true; running = false; }
                 } else {
                     fails = 0;
                     if (t_new < t1) {
-                        if (err < 0.5) dt *= 9.0 / 10.0 * sb_pow(dmax(0.00032, err), -1.0 / 5);
+                        if (err < 0.5) dt *= 9.0 / 10.0 * sb_pow<true>(dmax(0.00032, err), -1.0 / 5);
                         t = t_new;
                         x = x_new;
                         dxdt = dxdt_new;
-                        const double fq = sb_exp(x);
+                        const double fq = sb_exp<true>(x);
                         area += 0.5 * (f_a + fq) * (t - t_a);
                         f_a = fq;
                         t_a = t;
@@ -773,7 +775,7 @@ __device__ __forceinline__ bool kirchner_step_warp(double c1, double c2, double 
             }
         }
     }
-    q = sb_exp_flat(x);
+    q = sb_exp_flat<true>(x);
     area += 0.5 * (f_a + q) * (t1 - t_a);
     q_avg = (t1 == 1.0) ? area : area / (t1 - 0.0);  // x / 1.0 = x
     return !failed;
@@ -829,6 +831,7 @@ __global__ void __launch_bounds__(SB2_BLOCK_A, SB2_MINBLOCKS_A) ptgsk_forcing_te
 #else
 __global__ void __launch_bounds__(SB2_BLOCK_A) ptgsk_forcing_terms_kernel(const PtgskRunArgs a) {
 #endif
+    sb_math_stage_tables();
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= a.n_cells) return;
     if (a.active != nullptr && a.active[c] == 0) return;
@@ -856,6 +859,7 @@ __global__ void __launch_bounds__(SB2_BLOCK_A) ptgsk_forcing_terms_kernel(const 
 // COLLECT bits used here: 2 snow sca/swe, 4 snow_outflow, 8 state series (the eight gamma_snow fields)
 template <int COLLECT>
 __global__ void __launch_bounds__(SB2_BLOCK_B, SB2_MINBLOCKS_B) ptgsk_snow_kernel(const PtgskRunArgs a) {
+    sb_math_stage_tables();
     const int ens = blockIdx.y;
     // time split by ticket, as in ptgsk_response_kernel (1.76 waves of whole-window blocks otherwise); the memo starts empty in
     // every slice, which costs one snow-state evaluation per cell and slice
@@ -959,6 +963,7 @@ __global__ void __launch_bounds__(SB2_BLOCK_B, SB2_MINBLOCKS_B) ptgsk_snow_kerne
 // COLLECT bits used here: 1 avg_discharge+charge, 4 glacier_melt/ae/pe, 8 state series (kirchner discharge)
 template <int COLLECT>
 __global__ void __launch_bounds__(SB2_BLOCK_C, SB2_MINBLOCKS_C) ptgsk_response_kernel(const PtgskRunArgs a) {
+    sb_math_stage_tables();
     const int ens = blockIdx.y;
     // Time split.  A block steps one group of blockDim cells; with ~115 registers 2 500 of the 3 125 one-warp blocks of a 100 000-cell
     // shard are resident, so a launch of whole-window blocks runs as 1.25 waves -- the second wave leaves three quarters of the
@@ -1079,7 +1084,7 @@ __global__ void __launch_bounds__(SB2_BLOCK_C, SB2_MINBLOCKS_C) ptgsk_response_k
             const double gm_melt_m3s =
                 (glacier_area_m2 <= sca_m2 || temp <= 0.0) ? 0.0 : gm_dtf * temp * (glacier_area_m2 - sca_m2) * (0.001 / 86400.0);
             // actual_evapotranspiration::calculate_step, actual_evapotranspiration.h:56-62
-            const double ae = pot * (1.0 - sb_exp_flat(-kq * 3.0 / ae_scale_factor)) * (1.0 - dmax(sca, glacier_fraction));
+            const double ae = pot * (1.0 - sb_exp_flat<true>(-kq * 3.0 / ae_scale_factor)) * (1.0 - dmax(sca, glacier_fraction));
             const double gm_mmh = div_pos(gm_melt_m3s, (1 / (3600.0 * 1000.0)) * cell_area_m2);  // m3s_to_mmh; mostly 0 / x (no melt)
             double q_avg, kq_new = active ? kq : 1.0;
             const double k_in = outflow * snow_storage_fraction + prec * kirchner_routed_prec + gm_routed * gm_mmh;

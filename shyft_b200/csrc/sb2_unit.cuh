@@ -11,6 +11,7 @@ enum { UNIT_EXP = 0, UNIT_LOG, UNIT_POW, UNIT_LGAMMA, UNIT_GAMMA_P, UNIT_CORR_LW
        UNIT_EXP_FLAT, UNIT_LOG_FLAT, UNIT_POW_FLAT, UNIT_CALC_SNOW_STATE_HOT, UNIT_KIRCHNER_STEP_WARP, UNIT_GAMMA_P_PAIR, UNIT_N };
 
 __global__ void unit_eval_kernel(int fn, int64_t n, const double* __restrict__ in, int n_in, double* __restrict__ out, int n_out) {
+    sb_math_stage_tables();  // the step-kernel forms below read the tables from shared memory, the plain ones from global memory
     const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool in_range = i0 < n;
     const int64_t i = in_range ? i0 : n - 1;  // lanes past the end shadow the last element (warp-synchronous functions need all 32 lanes)
@@ -35,9 +36,9 @@ __global__ void unit_eval_kernel(int fn, int64_t n, const double* __restrict__ i
             o[0] = q; o[1] = q_avg; o[2] = ok ? 1.0 : 0.0;
             break;
         }
-        case UNIT_EXP_FLAT: o[0] = sb_exp_flat(a[0]); break;
-        case UNIT_LOG_FLAT: o[0] = sb_log_flat(a[0]); break;
-        case UNIT_POW_FLAT: o[0] = sb_pow_flat(a[0], a[1]); break;
+        case UNIT_EXP_FLAT: o[0] = sb_exp_flat<true>(a[0]); break;
+        case UNIT_LOG_FLAT: o[0] = sb_log_flat<true>(a[0]); break;
+        case UNIT_POW_FLAT: o[0] = sb_pow_flat<true>(a[0], a[1]); break;
         case UNIT_CALC_SNOW_STATE_HOT: {
             double lg_key = nan_(), lg_val = 0.0;
             gs_calc_snow_state_hot(a[0], a[1], a[2], a[3], a[4], a[5], a[6], o[0], o[1], lg_key, lg_val);

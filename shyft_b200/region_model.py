@@ -440,6 +440,11 @@ class RegionModel:
         self._ck(self._L.sb2_device_catchment_discharges(self._h, C.byref(p), C.byref(t), C.byref(k)))
         return p.value, t.value, k.value
 
+    def device_catchment_charges(self):
+        p, t, k = C.c_void_p(), C.c_int64(0), C.c_int64(0)
+        self._ck(self._L.sb2_device_catchment_charges(self._h, C.byref(p), C.byref(t), C.byref(k)))
+        return p.value, t.value, k.value
+
 
 class PTGSKModel(RegionModel):
     """PTGSKModel with the statistics properties of shyft/api/pt_gs_k/__init__.py:14-20"""

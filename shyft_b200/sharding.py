@@ -60,6 +60,22 @@ def device_catchment_discharges(model):
     return torch.as_tensor(DeviceArrayView(ptr, rows, cols), device="cuda")
 
 
+def device_catchment_charges(model):
+    """The model's catchment charge sums as a torch tensor aliasing library memory [T][n_catchments]."""
+    import torch
+    ptr, rows, cols = model.device_catchment_charges()
+    return torch.as_tensor(DeviceArrayView(ptr, rows, cols), device="cuda")
+
+
+def global_catchment_series(model, global_cids, what="discharge"):
+    """The region's [T][n_global_catchments] catchment series on every rank: this rank's catchment sums placed at their global
+    catchment index, then summed over the ranks (NCCL all-reduce; a catchment that straddles a shard boundary gets both halves).
+    The semantics of region_model::get_catchment_discharges / charges over the whole cell vector (core/region_model.h:873-900)."""
+    local = device_catchment_discharges(model) if what == "discharge" else device_catchment_charges(model)
+    g = scatter_local_to_global(local, model.catchment_ids, global_cids, xp=__import__("torch"))
+    return all_reduce_catchment_series(g)
+
+
 # ---- calibration ensembles: the parameter sets are sharded, the cells are not (SURVEY.md 8e) ----------------------------------
 def partition_parameter_sets(n_sets, world_size, rank):
     """Contiguous, balanced range of a population's parameter sets for this rank -> (begin, end); every rank holds all cells."""

@@ -98,3 +98,47 @@ def test_world_size_2_gloo_parameter_set_sharding(tmp_path):
     want = np.array([0.25 * i * i - 3.0 * i for i in range(n_sets)])
     for r in range(2):
         assert np.array_equal(np.load(tmp_path / f"goals_{r}.npy"), want)
+
+
+def _oracle_shard_worker(rank, world, port, out_dir):
+    """each rank steps ITS cells with the CPU oracle (the stand-in for the device model of a shard), reports catchment sums in its own
+    first-appearance order, and the shards' series meet in the all-reduce -- the flow of bench.py --gpus N / tests/test_gpu_multi.py"""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    from fixtures import PTGSK_DEFAULT
+    from oracle import oracle as O
+    from shyft_b200 import sharding, synthetic
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n, T = 90, 240
+    geo, ta, env = synthetic.make_region(n, T, 6, config_index=7, cells_per_catchment=40, start=1417392000)   # catchment 2 straddles cell 45
+    gm = O.geo_matrix(geo)
+    f = {}
+    for name in ("temperature", "precipitation", "radiation", "wind_speed", "rel_hum"):
+        xyz, vals = getattr(env, name)
+        f[name] = O.idw_run(name, xyz, O.average_accessor_same_axis(vals, 3600 * 10**6), gm[:, :3], O.idw_par(), dst_slope=gm[:, 5])
+    st0 = synthetic.default_state(0, n)
+    b, e = sharding.partition_cells(n, world, rank)
+    run = lambda lo, hi: O.ptgsk_run_cells(gm[lo:hi], PTGSK_DEFAULT, {k: np.ascontiguousarray(v[:, lo:hi]) for k, v in f.items()}, st0[lo:hi],
+                                           ta.start * 10**6, 3600 * 10**6)["avg_discharge"]
+    q = run(b, e)
+    _, gcids = sharding.global_catchment_index(geo["catchment_id"])
+    lcix, lcids = sharding.global_catchment_index(geo["catchment_id"][b:e])
+    local = np.stack([q[:, lcix == k].sum(axis=1) for k in range(lcids.size)], axis=1)
+    g = sharding.all_reduce_catchment_series(sharding.scatter_local_to_global(torch.from_numpy(local), lcids, gcids, xp=torch))
+    if rank == 0:
+        q_all = run(0, n)
+        gcix, _ = sharding.global_catchment_index(geo["catchment_id"])
+        want = np.stack([q_all[:, gcix == k].sum(axis=1) for k in range(gcids.size)], axis=1)
+        np.save(os.path.join(out_dir, "oracle_shards.npy"), np.array([np.allclose(g.numpy(), want, rtol=1e-12, atol=0), float(want.max() > 0), gcids.size]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_sharded_oracle_run_equals_whole_region(tmp_path):
+    import torch.multiprocessing as mp
+    mp.spawn(_oracle_shard_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    ok, positive, n_catch = np.load(tmp_path / "oracle_shards.npy")
+    assert ok == 1.0 and positive == 1.0 and n_catch == 3
