@@ -301,6 +301,11 @@ PtgskParam make_ptgsk_param(const double* v, int64_t dt_us) {
     const double albedo_range = p.max_albedo - p.min_albedo;
     p.slow_albedo_decay_step = 0.5 * albedo_range * dt_in_days / p.slow_albedo_decay_rate;
     p.fast_albedo_decay_step = sb_pow(2.0, -dt_in_days / p.fast_albedo_decay_rate);
+    // parameter-only divisors of the step with their reciprocals (div_by, sb2_math.cuh): the divisor expressions are the step's own
+    p.inv_snowfall_reset_depth = make_inv_divisor(p.snowfall_reset_depth);
+    p.inv_one_minus_y0 = make_inv_divisor(1.0 - p.initial_bare_ground_fraction);
+    p.inv_max_water = make_inv_divisor(p.max_water);
+    p.inv_ae_scale = make_inv_divisor(p.ae_scale_factor);
     return p;
 }
 std::vector<double> default_parameter(int stack) {
@@ -411,6 +416,14 @@ void fill_nan(sb2_model* m, double* p, int64_t count) {
 // is small and the split only costs (ensembles: 6.8 -> 4.9 G cell-steps/s when split).
 bool use_time_split(int64_t blocks_per_launch) { return blocks_per_launch < 16000; }
 
+// step-length divisors, the Kirchner solver's dt * tableau products and the region parameter set by value (PtgskRunArgs)
+void fill_step_constants(sb2_model* m, PtgskRunArgs& a) {
+    a.inv_dt_seconds = make_inv_divisor(a.dt_seconds);
+    a.inv_dt_us = make_inv_divisor(a.dt_us);
+    fill_dopri_products(a.dt_hours, a.dtb);
+    a.par0 = make_ptgsk_param(m->region_param.data(), m->dt > 0 ? m->dt : 3600000000LL);
+}
+
 // ---- the cell step over [first, first+n_steps) with forcing/series windows already in place -------------------
 void launch_step_range(sb2_model* m, int64_t first, int64_t n_steps, bool collect_end_state) {
     sync_parameters(m);
@@ -440,6 +453,7 @@ void launch_step_range(sb2_model* m, int64_t first, int64_t n_steps, bool collec
             a.n_steps = chunk; a.first_step = s0;
             a.dt_seconds = dt_seconds; a.dt_hours = dt_seconds / 3600.0; a.dt_us = double(m->dt);
             a.bb0 = 0.98 * 5.670373e-8 * sb_pow4(273.15);
+            fill_step_constants(m, a);
             a.day_of_year = m->d_doy.p; a.sec_of_year = m->d_soy.p;
             for (int r = 0; r < 8; ++r) a.resp[r] = m->d_resp[r].p;
             for (int s = 0; s < 9; ++s) a.st[s] = m->d_st[s].p;
@@ -452,7 +466,11 @@ void launch_step_range(sb2_model* m, int64_t first, int64_t n_steps, bool collec
                 a.scr[k] = m->d_scr[k].p;
             }
             a.ens_scr_stride = 0;
-            ptgsk_forcing_terms_kernel<<<dim3((unsigned)grid_for(n, SB2_BLOCK_A), (unsigned)grid_for(chunk, SB2_STEPS_A)), SB2_BLOCK_A, SB2_MTAB_BYTES, m->stream>>>(a);
+            // UPAR kernels: no catchment override in use -> every cell reads the region parameter set from the constant bank
+            const bool upar = m->catch_param.empty();
+            const dim3 ga((unsigned)grid_for(n, SB2_BLOCK_A), (unsigned)grid_for(chunk, SB2_STEPS_A));
+            if (upar) ptgsk_forcing_terms_kernel<true><<<ga, SB2_BLOCK_A, SB2_MTAB_BYTES, m->stream>>>(a);
+            else ptgsk_forcing_terms_kernel<false><<<ga, SB2_BLOCK_A, SB2_MTAB_BYTES, m->stream>>>(a);
             const int gb = grid_for(n, SB2_BLOCK_B), gc = grid_for(n, SB2_BLOCK_C);
             // snow and response kernels in slices of SB2_UNIT_STEPS steps handed out by ticket (see the kernels); counters zeroed per launch
             const bool split = use_time_split(gb);
@@ -461,13 +479,15 @@ void launch_step_range(sb2_model* m, int64_t first, int64_t n_steps, bool collec
             a.unit_steps = split ? SB2_UNIT_STEPS : 0; a.tickets = m->d_tickets.p; a.progress = m->d_tickets.p + 1;
             CUDA_OK(cudaMemsetAsync(m->d_tickets.p, 0, size_t(1 + gb) * sizeof(int), m->stream));
             switch (m->collect_bits & 14) {
-#define SB2_CASE(B) case B: ptgsk_snow_kernel<B><<<gb * n_slices, SB2_BLOCK_B, SB2_MTAB_BYTES, m->stream>>>(a); break;
+#define SB2_CASE(B) case B: if (upar) ptgsk_snow_kernel<B, true><<<gb * n_slices, SB2_BLOCK_B, SB2_MTAB_BYTES, m->stream>>>(a); \
+                            else ptgsk_snow_kernel<B, false><<<gb * n_slices, SB2_BLOCK_B, SB2_MTAB_BYTES, m->stream>>>(a); break;
                 SB2_CASE(0) SB2_CASE(2) SB2_CASE(4) SB2_CASE(6) SB2_CASE(8) SB2_CASE(10) SB2_CASE(12) SB2_CASE(14)
 #undef SB2_CASE
             }
             CUDA_OK(cudaMemsetAsync(m->d_tickets.p, 0, size_t(1 + gc) * sizeof(int), m->stream));
             switch (m->collect_bits & 13) {
-#define SB2_CASE(B) case B: ptgsk_response_kernel<B><<<gc * n_slices, SB2_BLOCK_C, SB2_MTAB_BYTES, m->stream>>>(a); break;
+#define SB2_CASE(B) case B: if (upar) ptgsk_response_kernel<B, true><<<gc * n_slices, SB2_BLOCK_C, SB2_MTAB_BYTES, m->stream>>>(a); \
+                            else ptgsk_response_kernel<B, false><<<gc * n_slices, SB2_BLOCK_C, SB2_MTAB_BYTES, m->stream>>>(a); break;
                 SB2_CASE(0) SB2_CASE(1) SB2_CASE(4) SB2_CASE(5) SB2_CASE(8) SB2_CASE(9) SB2_CASE(12) SB2_CASE(13)
 #undef SB2_CASE
             }
@@ -480,6 +500,7 @@ void launch_step_range(sb2_model* m, int64_t first, int64_t n_steps, bool collec
             for (int v = 0; v < 5; ++v) a.f[v] = m->d_forcing[v].p + (s0 - m->forcing_first) * n;
             a.n_steps = chunk; a.first_step = s0;
             a.dt_seconds = dt_seconds; a.dt_hours = dt_seconds / 3600.0; a.dt_us = double(m->dt);
+            fill_dopri_products(a.dt_hours, a.dtb);
             for (int r = 0; r < 9; ++r) a.resp[r] = m->d_resp[r].p;
             for (int s = 0; s < n_state_series(m); ++s) a.st[s] = m->d_st[s].p;
             a.out_first_step = m->out_first;
@@ -1040,6 +1061,7 @@ void goal_batch_ptgsk(sb2_model* m, int64_t n_sets, const double* P, double* goa
             a.n_steps = chunk; a.first_step = done;
             a.dt_seconds = dt_seconds; a.dt_hours = dt_seconds / 3600.0; a.dt_us = double(m->dt);
             a.bb0 = 0.98 * 5.670373e-8 * sb_pow4(273.15);
+            fill_step_constants(m, a);
             a.day_of_year = m->d_doy.p; a.sec_of_year = m->d_soy.p;
             a.out_first_step = 0; a.collect_end_state = 0;
             a.slot = m->d_slot.p; a.partial = d_partial.p; a.n_slots = m->n_slots; a.error_flag = m->d_error_flag.p;
@@ -1047,17 +1069,17 @@ void goal_batch_ptgsk(sb2_model* m, int64_t n_sets, const double* P, double* goa
             for (int k = 0; k < 5; ++k) a.scr[k] = d_scr[k].p;
             a.ens_scr_stride = ps * n;
             // the same phase pipeline as run_cells, one grid layer per member
-            ptgsk_forcing_terms_kernel<<<dim3((unsigned)grid_for(n, SB2_BLOCK_A), (unsigned)grid_for(chunk, SB2_STEPS_A), (unsigned)ne), SB2_BLOCK_A, SB2_MTAB_BYTES,
-                                         m->stream>>>(a);
+            ptgsk_forcing_terms_kernel<false><<<dim3((unsigned)grid_for(n, SB2_BLOCK_A), (unsigned)grid_for(chunk, SB2_STEPS_A), (unsigned)ne), SB2_BLOCK_A,
+                                                SB2_MTAB_BYTES, m->stream>>>(a);
             {
                 const int gb = grid_for(n, SB2_BLOCK_B), gc = grid_for(n, SB2_BLOCK_C);
                 const bool split = use_time_split(int64_t(gb) * ne);
                 const int n_slices = split ? grid_for(chunk, SB2_UNIT_STEPS) : 1;
                 a.unit_steps = split ? SB2_UNIT_STEPS : 0; a.tickets = d_tickets.p; a.progress = d_tickets.p + E;
                 CUDA_OK(cudaMemsetAsync(d_tickets.p, 0, d_tickets.n * sizeof(int), m->stream));
-                ptgsk_snow_kernel<0><<<dim3((unsigned)(gb * n_slices), (unsigned)ne), SB2_BLOCK_B, SB2_MTAB_BYTES, m->stream>>>(a);
+                ptgsk_snow_kernel<0, false><<<dim3((unsigned)(gb * n_slices), (unsigned)ne), SB2_BLOCK_B, SB2_MTAB_BYTES, m->stream>>>(a);
                 CUDA_OK(cudaMemsetAsync(d_tickets.p, 0, d_tickets.n * sizeof(int), m->stream));
-                ptgsk_response_kernel<0><<<dim3((unsigned)(gc * n_slices), (unsigned)ne), SB2_BLOCK_C, SB2_MTAB_BYTES, m->stream>>>(a);
+                ptgsk_response_kernel<0, false><<<dim3((unsigned)(gc * n_slices), (unsigned)ne), SB2_BLOCK_C, SB2_MTAB_BYTES, m->stream>>>(a);
             }
             m->launches += 2;
             CUDA_OK(cudaGetLastError());
@@ -2141,7 +2163,7 @@ int sb2_calculate_goal_function_batch(sb2_model* m, int64_t n_sets, const double
 // ---- diagnostics ---------------------------------------------------------------------------------------------------------------
 int sb2_unit_eval(int device, int fn, int64_t n, const double* in, int n_in, double* out, int n_out) {
     try {
-        static const int need_in[UNIT_N] = {1, 1, 2, 1, 2, 5, 7, 7, 1, 1, 2, 7, 7, 4}, need_out[UNIT_N] = {1, 1, 1, 1, 1, 1, 2, 3, 1, 1, 1, 2, 3, 2};
+        static const int need_in[UNIT_N] = {1, 1, 2, 1, 2, 5, 7, 7, 1, 1, 2, 7, 7, 4, 2, 7}, need_out[UNIT_N] = {1, 1, 1, 1, 1, 1, 2, 3, 1, 1, 1, 2, 3, 2, 2, 3};
         if (fn < 0 || fn >= UNIT_N) throw Error("unknown unit function");
         if (n_in < need_in[fn] || n_out < need_out[fn]) throw Error("unit function: too few input or output columns");
         CUDA_OK(cudaSetDevice(device));
@@ -2149,6 +2171,9 @@ int sb2_unit_eval(int device, int fn, int64_t n, const double* in, int n_in, dou
         d_in.upload(in, size_t(n) * n_in, 0);
         d_out.resize(size_t(n) * n_out);
         CUDA_OK(cudaMemsetAsync(d_out.p, 0, size_t(n) * n_out * sizeof(double), 0));
+        double dtb[26];
+        fill_dopri_products(1.0, dtb);
+        CUDA_OK(cudaMemcpyToSymbol(kUnitDtb, dtb, sizeof(dtb)));
         unit_eval_kernel<<<grid_for(n, 128), 128, SB2_MTAB_BYTES>>>(fn, n, d_in.p, n_in, d_out.p, n_out);
         CUDA_OK(cudaGetLastError());
         CUDA_OK(cudaMemcpy(out, d_out.p, size_t(n) * n_out * sizeof(double), cudaMemcpyDeviceToHost));

@@ -81,6 +81,7 @@ struct HbvRunArgs {
     int n_steps;
     int64_t first_step;
     double dt_seconds, dt_hours, dt_us;
+    double dtb[26];              // dt_hours * Dormand-Prince tableau (kirchner_try<true>, sb2_ptgsk.cuh)
     double* __restrict__ resp[9];
     double* __restrict__ st[5 + 2 * HBV_NB];  // state series, ids of include/shyft_b200.h (the per-bin sp / sw series last)
     int64_t out_first_step;
@@ -244,7 +245,7 @@ __device__ __forceinline__ bool hbv_snow_step(double (&sp)[HBV_NB], double (&sw)
 #define SB2_HBV_MINBLOCKS_S 5   // hbv_stack (soil + tank)
 #endif
 template <bool HBV_STACK>
-__global__ void __launch_bounds__(128, (HBV_STACK ? SB2_HBV_MINBLOCKS_S : SB2_HBV_MINBLOCKS_K)) hbv_run_kernel(const HbvRunArgs a) {
+__global__ void __launch_bounds__(128, (HBV_STACK ? SB2_HBV_MINBLOCKS_S : SB2_HBV_MINBLOCKS_K)) hbv_run_kernel(const __grid_constant__ HbvRunArgs a) {
     constexpr int NS = HBV_STACK ? 5 + 2 * HBV_NB : 3 + 2 * HBV_NB;
     sb_math_stage_tables();  // exp / log tables of the shared math spec into this block's shared memory (sb2_math.cuh)
     // Time split by ticket (see ptgsk_response_kernel): 12 500 one-warp blocks of a 400 000-cell shard are 4-5 waves of the 2 400-3 000
@@ -360,7 +361,7 @@ __global__ void __launch_bounds__(128, (HBV_STACK ? SB2_HBV_MINBLOCKS_S : SB2_HB
         if (!HBV_STACK) {
             double q_avg, kq_new = active ? x0 : 1.0;
             const double k_in = snow_outflow * snow_storage_fraction + prec * kirchner_routed_prec + gm_routed * gm_mmh;
-            if (!kirchner_step_warp(p.c1, p.c2, p.c3, a.dt_hours, kq_new, q_avg, active ? k_in : 0.0, active ? ae : 0.0)) {
+            if (!kirchner_step_warp<true>(a.dtb, p.c1, p.c2, p.c3, a.dt_hours, kq_new, q_avg, active ? k_in : 0.0, active ? ae : 0.0)) {
                 failed_k = true;
                 q_avg = nan("");
             }

@@ -42,6 +42,9 @@ struct PtgskParam {
     int32_t n_winter_days;
     int32_t calculate_iso_pot_energy;
     int32_t pad_;
+    // divisors that depend on the parameter set only, with their reciprocals (div_by, sb2_math.cuh): snowfall_reset_depth,
+    // 1 - initial_bare_ground_fraction, max_water, ae_scale_factor
+    InvDivisor inv_snowfall_reset_depth, inv_one_minus_y0, inv_max_water, inv_ae_scale;
 };
 
 enum : int { ERR_KIRCHNER_STEP = 1, ERR_MASS_BALANCE = 2 };
@@ -68,6 +71,11 @@ struct PtgskRunArgs {
     double dt_hours;                           // to_seconds(T1-T0)/to_seconds(deltahours(1))
     double dt_us;                              // double(dt.count())
     double bb0;                                // 0.98*sigma*pow(273.15,4), gamma_snow.h:286 (host-evaluated)
+    InvDivisor inv_dt_seconds, inv_dt_us;      // the step length as a divisor (div_by, sb2_math.cuh)
+    double dtb[26];                            // dt_hours * (Dormand-Prince tableau entry k), host-evaluated: the first try of every Kirchner step
+    // the region parameter set (params[0]) by value: with no catchment overrides and no ensemble every cell reads its parameters from
+    // the kernel's constant bank (UPAR kernels) instead of through a pointer the step's stores might alias
+    PtgskParam par0;
     const int32_t* __restrict__ day_of_year;   // [T] calendar::day_of_year(period.start), UTC
     const int32_t* __restrict__ sec_of_year;   // [T] (period.start - trim(period.start, YEAR)) in seconds
     // collected series: element (absolute step - out_first_step, cell) at r[s][...*n_cells + c]; null = not collected
@@ -230,8 +238,9 @@ __device__ __noinline__ double gs_corr_lwc(double z1, double a1, double b1, doub
 
 // calc_snow_state, gamma_snow.h:230-260
 // `lg_key`/`lg_val` memoise lgamma(shape): the shape (alpha) changes on few steps, and equal bits in give equal bits out
-__device__ __forceinline__ void gs_calc_snow_state_impl(double shape, double scale, double y0, double lambda, double lwd, double max_water_frac,
+__device__ __forceinline__ void gs_calc_snow_state_impl(double shape, double scale, double y0, double lambda, double lwd, const InvDivisor& inv_mwf,
                                                         double temp_swe, double& swe, double& sca, double& lg_key, double& lg_val) {
+    const double max_water_frac = inv_mwf.d;
     double y = 0.0, y1 = 0.0;
     const double m = shape * scale;
     double lg = 0.0;
@@ -255,7 +264,7 @@ __device__ __forceinline__ void gs_calc_snow_state_impl(double shape, double sca
     }
     if (lwd > m) swe *= 1.0 + max_water_frac;
     else if (lwd > 0.0) {
-        const double sat = lwd / max_water_frac;
+        const double sat = div_by(lwd, inv_mwf);
         const double x = sat / scale;
         if (!have_lg) {
             if (shape != lg_key) { lg_key = shape; lg_val = sb_lgamma<true>(shape); }
@@ -283,8 +292,9 @@ __device__ __noinline__
 #else
 __device__ __forceinline__
 #endif
-void gs_calc_snow_state_hot(double shape, double scale, double y0, double lambda, double lwd, double max_water_frac,
+void gs_calc_snow_state_hot(double shape, double scale, double y0, double lambda, double lwd, const InvDivisor& inv_mwf,
                                                        double temp_swe, double& swe, double& sca, double& lg_key, double& lg_val) {
+    const double max_water_frac = inv_mwf.d;
     double y = 0.0, y1 = 0.0;
     const double m = shape * scale;
     double lg = 0.0;
@@ -308,7 +318,7 @@ void gs_calc_snow_state_hot(double shape, double scale, double y0, double lambda
     }
     if (lwd > m) swe *= 1.0 + max_water_frac;
     else if (lwd > 0.0) {
-        const double sat = lwd / max_water_frac;
+        const double sat = div_by(lwd, inv_mwf);
         const double x = sat / scale;
         if (!have_lg) {
             if (shape != lg_key) { lg_key = shape; lg_val = sb_lgamma<true>(shape); }
@@ -324,9 +334,9 @@ void gs_calc_snow_state_hot(double shape, double scale, double y0, double lambda
     swe *= 1.0 - y0;
 }
 
-__device__ __noinline__ void gs_calc_snow_state(double shape, double scale, double y0, double lambda, double lwd, double max_water_frac,
+__device__ __noinline__ void gs_calc_snow_state(double shape, double scale, double y0, double lambda, double lwd, const InvDivisor& inv_mwf,
                                                 double temp_swe, double& swe, double& sca, double& lg_key, double& lg_val) {
-    gs_calc_snow_state_impl(shape, scale, y0, lambda, lwd, max_water_frac, temp_swe, swe, sca, lg_key, lg_val);
+    gs_calc_snow_state_impl(shape, scale, y0, lambda, lwd, inv_mwf, temp_swe, swe, sca, lg_key, lg_val);
 }
 
 // reset_snow_pack, gamma_snow.h:262-274 (alpha uses p.snow_cv, not the effective cv)
@@ -378,16 +388,22 @@ __device__ __noinline__ double sb_div_call(double a, double b) { return a / b; }
 #define SB2_SNOW_FLAT 0  // end-of-step calc_snow_state of the snow kernel with exp / log / incomplete gamma expanded in place (0: the shared out-of-line copy)
 #endif
 // gamma_snow::calculator::step, gamma_snow.h:291-493, given the two forcing-only addends (lw, tadd) of gs_energy_terms
+// Every division by a step-invariant divisor goes through div_by (same bits as the IEEE quotient, a tenth of the instructions):
+// k.inv_dt_seconds / k.inv_dt_us (the step length), the parameter-only divisors of PtgskParam, the physical constants, and inv_cv2 =
+// the cell's effective snow_cv squared (p.snow_cv + forest_fraction * p.snow_cv_forest_factor + altitude * p.snow_cv_altitude_factor,
+// :327; its reciprocal inv_cv2.y IS 1.0 / (snow_cv * snow_cv) of :437).
+struct GsStepConst { InvDivisor inv_dt_seconds, inv_dt_us; };
 template <bool FLAT = false>
 __device__ __forceinline__ void gs_step_core(GsState& s, GsCache& cache, double& r_sca, double& r_storage, double& r_outflow, const PtgskParam& p, int doy,
-                                             int sec_of_year, double dt_seconds, double dt_us, double BB0, double T, double rad, double prec_mm_h,
-                                             double lw, double tadd, double wind_speed, double rel_hum, double forest_fraction, double altitude) {
+                                             int sec_of_year, double dt_seconds, double dt_us, const GsStepConst& k, double BB0, double T, double rad,
+                                             double prec_mm_h, double lw, double tadd, double wind_speed, double rel_hum, const InvDivisor& inv_cv2) {
     const double tol = 1.0e-10;
     const double melt_heat = 333660.0, water_heat = 4180.0, ice_heat = 2050.0;
     double sdc_melt_mean = s.sdc_melt_mean;
     double acc_melt = s.acc_melt;
     double iso_pot_energy = s.iso_pot_energy;
-    const double prec = div_pos(prec_mm_h * dt_us, 3600000000.0);
+    const InvDivisor k_usec_per_hour = make_inv_divisor(3600000000.0), k_melt_heat = make_inv_divisor(333660.0);  // folded at compile time
+    const double prec = div_by(prec_mm_h * dt_us, k_usec_per_hour);
 
     if (doy == p.winter_end_day_of_year) acc_melt = iso_pot_energy = 0.0;  // is_start_melt_season :95-97
 
@@ -409,10 +425,9 @@ __device__ __forceinline__ void gs_step_core(GsState& s, GsCache& cache, double&
 
     const double min_albedo = p.min_albedo;
     const double max_albedo = p.max_albedo;
-    const double snow_cv = p.snow_cv + forest_fraction * p.snow_cv_forest_factor + altitude * p.snow_cv_altitude_factor;
     const double albedo_range = max_albedo - min_albedo;
 
-    if (snow > tol) albedo += GS_DIV(snow * albedo_range, p.snowfall_reset_depth);
+    if (snow > tol) albedo += div_by(snow * albedo_range, p.inv_snowfall_reset_depth);
     else {
         if (T < 0.0) albedo -= p.slow_albedo_decay_step;
         else albedo = min_albedo + p.fast_albedo_decay_step * (albedo - min_albedo);
@@ -422,13 +437,13 @@ __device__ __forceinline__ void gs_step_core(GsState& s, GsCache& cache, double&
     double effect = rad * (1.0 - albedo);
     effect += lw;
 
-    if (T > 0.0 && snow < tol) effect += div_pos(rain * T * water_heat, dt_seconds);
-    if (T <= 0.0 && rain < tol) effect += div_pos(snow * T * ice_heat, dt_seconds);
+    if (T > 0.0 && snow < tol) effect += div_by(rain * T * water_heat, k.inv_dt_seconds);
+    if (T <= 0.0 && rain < tol) effect += div_by(snow * T * ice_heat, k.inv_dt_seconds);
 
     if (p.calculate_iso_pot_energy) {
         const double turb = p.wind_scale * wind_speed + p.wind_const;
         const double iso_effect = effect - BB0 + turb * (T + 1.7 * (gs_vapour_pressure(T, rel_hum) - 6.12));
-        iso_pot_energy += GS_DIV(iso_effect * dt_seconds, melt_heat);
+        iso_pot_energy += div_by(iso_effect * dt_seconds, k_melt_heat);
     }
 
     const double sst = dmin(0.0, 1.16 * T - 2.09);
@@ -441,7 +456,7 @@ __device__ __forceinline__ void gs_step_core(GsState& s, GsCache& cache, double&
     double energy = effect * dt_seconds;
     if (delta_sh > 0.0) energy -= delta_sh;
 
-    double potential_melt = dmax(0.0, GS_DIV(energy, melt_heat));
+    double potential_melt = dmax(0.0, div_by(energy, k_melt_heat));
 
     double sdc_scale = GS_DIV(sdc_melt_mean, alpha);
     const double y0 = p.initial_bare_ground_fraction;
@@ -449,7 +464,7 @@ __device__ __forceinline__ void gs_step_core(GsState& s, GsCache& cache, double&
         storage = SB2_CK_STORAGE(cache);
         sca = SB2_CK_SCA(cache);
     } else {
-        gs_calc_snow_state(alpha, sdc_scale, y0, acc_melt, lwc, p.max_water, temp_swe, storage, sca, SB2_CK_LGKEY(cache), SB2_CK_LGVAL(cache));  // cold: memo hit
+        gs_calc_snow_state(alpha, sdc_scale, y0, acc_melt, lwc, p.inv_max_water, temp_swe, storage, sca, SB2_CK_LGKEY(cache), SB2_CK_LGVAL(cache));  // cold: memo hit
         gs_cache_store(cache, alpha, sdc_scale, acc_melt, lwc, temp_swe, storage, sca);
     }
     const double start_storage_value = storage;
@@ -459,15 +474,15 @@ __device__ __forceinline__ void gs_step_core(GsState& s, GsCache& cache, double&
         else {
             const double alpha_prev = alpha;
             const double sdc_scale_prev = sdc_scale;
-            const double sdc_snow = GS_DIV(snow, 1.0 - y0);
-            alpha = GS_DIV(sdc_melt_mean * alpha + GS_DIV(sdc_snow, snow_cv * snow_cv), sdc_snow + sdc_melt_mean);
+            const double sdc_snow = div_by(snow, p.inv_one_minus_y0);
+            alpha = GS_DIV(sdc_melt_mean * alpha + div_by(sdc_snow, inv_cv2), sdc_snow + sdc_melt_mean);
             sdc_melt_mean += sdc_snow;
             sdc_scale = GS_DIV(sdc_melt_mean, alpha);
             if (lwc > 0.0 && sdc_snow > 0.01 * sdc_melt_mean) {
-                double z1 = GS_DIV(lwc, p.max_water);
+                double z1 = div_by(lwc, p.inv_max_water);
                 z1 = gs_corr_lwc(z1, alpha_prev, sdc_scale_prev > 0.0 ? sdc_scale_prev : sdc_scale, alpha, sdc_scale);
                 lwc = z1 * p.max_water;
-                gs_calc_snow_state(alpha, sdc_scale, y0, acc_melt, lwc, p.max_water, temp_swe, storage, sca, SB2_CK_LGKEY(cache), SB2_CK_LGVAL(cache));
+                gs_calc_snow_state(alpha, sdc_scale, y0, acc_melt, lwc, p.inv_max_water, temp_swe, storage, sca, SB2_CK_LGKEY(cache), SB2_CK_LGVAL(cache));
             }
         }
         lwc += rain;
@@ -479,11 +494,11 @@ __device__ __forceinline__ void gs_step_core(GsState& s, GsCache& cache, double&
             sdc_melt_mean -= potential_melt;
             lwc += potential_melt;
             alpha = dmax(0.1, GS_DIV(sdc_melt_mean, sdc_scale));
-            if (alpha > GS_DIV(1.0, snow_cv * snow_cv)) alpha = GS_DIV(1.0, snow_cv * snow_cv);
+            if (alpha > inv_cv2.y) alpha = inv_cv2.y;  // 1.0 / (snow_cv * snow_cv)
             sdc_scale = GS_DIV(sdc_melt_mean, alpha);
         }
     } else {  // :452-470
-        temp_swe += div_pos(snow, 1.0 - y0);  // y0 < 1
+        temp_swe += div_by(snow, p.inv_one_minus_y0);
         if (temp_swe > 0.0) {
             const double melt = dmin(temp_swe, potential_melt);
             temp_swe -= melt;
@@ -512,8 +527,8 @@ __device__ __forceinline__ void gs_step_core(GsState& s, GsCache& cache, double&
         storage = SB2_CK_STORAGE(cache);
         sca = SB2_CK_SCA(cache);
     } else {
-        if (FLAT) gs_calc_snow_state_hot(alpha, sdc_scale, y0, acc_melt, lwc, p.max_water, temp_swe, storage, sca, SB2_CK_LGKEY(cache), SB2_CK_LGVAL(cache));
-        else gs_calc_snow_state(alpha, sdc_scale, y0, acc_melt, lwc, p.max_water, temp_swe, storage, sca, SB2_CK_LGKEY(cache), SB2_CK_LGVAL(cache));
+        if (FLAT) gs_calc_snow_state_hot(alpha, sdc_scale, y0, acc_melt, lwc, p.inv_max_water, temp_swe, storage, sca, SB2_CK_LGKEY(cache), SB2_CK_LGVAL(cache));
+        else gs_calc_snow_state(alpha, sdc_scale, y0, acc_melt, lwc, p.inv_max_water, temp_swe, storage, sca, SB2_CK_LGKEY(cache), SB2_CK_LGVAL(cache));
         gs_cache_store(cache, alpha, sdc_scale, acc_melt, lwc, temp_swe, storage, sca);
     }
 
@@ -530,7 +545,7 @@ __device__ __forceinline__ void gs_step_core(GsState& s, GsCache& cache, double&
     s.temp_swe = temp_swe;
     r_sca = sca;
     r_storage = storage;
-    r_outflow = div_pos(outflow * 3600000000.0, dt_us);
+    r_outflow = div_by(outflow * 3600000000.0, k.inv_dt_us);
 }
 
 // ---- priestley_taylor, core/priestley_taylor.h:75-103 -------------------------------------------------
@@ -677,23 +692,29 @@ __device__ __forceinline__ bool kirchner_step(double c1, double c2, double c3, d
 }
 
 // Dormand-Prince tableau as odeint writes it (value_type(n)/value_type(d)); same expressions as in kirchner_step
-__constant__ double kDopri[27] = {
-    1.0 / 5.0,
-    3.0 / 40.0, 9.0 / 40.0,
-    44.0 / 45.0, -56.0 / 15.0, 32.0 / 9.0,
-    19372.0 / 6561.0, -25360.0 / 2187.0, 64448.0 / 6561.0, -212.0 / 729.0,
-    9017.0 / 3168.0, -355.0 / 33.0, 46732.0 / 5247.0, 49.0 / 176.0, -5103.0 / 18656.0,
-    35.0 / 384.0, 500.0 / 1113.0, 125.0 / 192.0, -2187.0 / 6784.0, 11.0 / 84.0,
-    35.0 / 384.0 - 5179.0 / 57600.0, 500.0 / 1113.0 - 7571.0 / 16695.0, 125.0 / 192.0 - 393.0 / 640.0,
-    -2187.0 / 6784.0 - (-92097.0 / 339200.0), 11.0 / 84.0 - 187.0 / 2100.0, -1.0 / 40.0,
-    1.e-30};  // [26]: the threshold of kirchner.h:197
+#define SB2_DOPRI_TABLEAU { \
+    1.0 / 5.0, \
+    3.0 / 40.0, 9.0 / 40.0, \
+    44.0 / 45.0, -56.0 / 15.0, 32.0 / 9.0, \
+    19372.0 / 6561.0, -25360.0 / 2187.0, 64448.0 / 6561.0, -212.0 / 729.0, \
+    9017.0 / 3168.0, -355.0 / 33.0, 46732.0 / 5247.0, 49.0 / 176.0, -5103.0 / 18656.0, \
+    35.0 / 384.0, 500.0 / 1113.0, 125.0 / 192.0, -2187.0 / 6784.0, 11.0 / 84.0, \
+    35.0 / 384.0 - 5179.0 / 57600.0, 500.0 / 1113.0 - 7571.0 / 16695.0, 125.0 / 192.0 - 393.0 / 640.0, \
+    -2187.0 / 6784.0 - (-92097.0 / 339200.0), 11.0 / 84.0 - 187.0 / 2100.0, -1.0 / 40.0, \
+    1.e-30}  /* [26]: the threshold of kirchner.h:197 */
+__constant__ double kDopri[27] = SB2_DOPRI_TABLEAU;
+static const double kDopri_host[27] = SB2_DOPRI_TABLEAU;
+// dtb[k] = dt * tableau[k], k < 26: what the first try of every model step multiplies the slopes with (dt = t1 for all lanes then)
+inline void fill_dopri_products(double dt_hours, double* dtb) {
+    for (int k = 0; k < 26; ++k) dtb[k] = dt_hours * kDopri_host[k];
+}
 
 // The same step, warp-synchronous: all 32 lanes call it together and iterate until every lane has reached t1.  Each pass of the
 // loop is one try_step of every lane that is still running (finished lanes recompute their last try and discard it), so the
 // Runge-Kutta stages and their 14 exponentials sit in uniform control flow -- no per-lane loop, no call -- and each lane still
 // follows exactly the accept / reject sequence of kirchner_step above (bit-identical; tests/test_gpu_units.py).
 __device__ __forceinline__ double kirchner_rhs_flat(double c1, double c2, double c3, double pe, double x) {
-    // both exponentials through one range test, so that the two polynomials (four independent fma chains) interleave
+    // both exponentials through one range test, so that the two polynomials interleave
     const double a = c1 + c2 * x + c3 * x * x;
     int ea, ex_;
     const double va = sb_exp_core<true>(a, ea), vx = sb_exp_core<true>(-x, ex_);
@@ -703,77 +724,91 @@ __device__ __forceinline__ double kirchner_rhs_flat(double c1, double c2, double
     const double h = g * (pe * ex - 1.0);
     return g >= kDopri[26] ? h : 0.0;
 }
-__device__ __forceinline__ bool kirchner_step_warp(double c1, double c2, double c3, double t1, double& q, double& q_avg, double p, double e) {
+// One try_step of the controlled stepper from (x, dxdt) with step dt: the seven stages, the error estimate's numerator and denominator.
+// UDT: dt is the same for every lane and its products with the tableau come from `dtb` (host-evaluated dt * b, the same IEEE products the
+// lane would form: (dt * b21) * dxdt is how `dt * b21 * dxdt` parses) -- the first try of every model step, i.e. > 99.9 % of all tries;
+// 26 fp64 multiplications less per step, and the products sit in the constant bank.
+template <bool UDT>
+__device__ __forceinline__ void kirchner_try(const double* __restrict__ dtb, double dt, double c1, double c2, double c3, double pe, double x, double dxdt,
+                                             double& x_new, double& dxdt_new, double& k3, double& k4, double& k5, double& k6, double& err_num,
+                                             double& err_den) {
     const double eps_abs = 1.0e-7, eps_rel = 1.0e-8;
+#define SB2_DTB(k) (UDT ? dtb[k] : dt * kDopri[k])
+    double xt = 1.0 * x + SB2_DTB(0) * dxdt;
+    const double k2 = kirchner_rhs_flat(c1, c2, c3, pe, xt);
+    xt = 1.0 * x + SB2_DTB(1) * dxdt + SB2_DTB(2) * k2;
+    k3 = kirchner_rhs_flat(c1, c2, c3, pe, xt);
+    xt = 1.0 * x + SB2_DTB(3) * dxdt + SB2_DTB(4) * k2 + SB2_DTB(5) * k3;
+    k4 = kirchner_rhs_flat(c1, c2, c3, pe, xt);
+    xt = 1.0 * x + SB2_DTB(6) * dxdt + SB2_DTB(7) * k2 + SB2_DTB(8) * k3 + SB2_DTB(9) * k4;
+    k5 = kirchner_rhs_flat(c1, c2, c3, pe, xt);
+    xt = 1.0 * x + SB2_DTB(10) * dxdt + SB2_DTB(11) * k2 + SB2_DTB(12) * k3 + SB2_DTB(13) * k4 + SB2_DTB(14) * k5;
+    k6 = kirchner_rhs_flat(c1, c2, c3, pe, xt);
+    x_new = 1.0 * x + SB2_DTB(15) * dxdt + SB2_DTB(16) * k3 + SB2_DTB(17) * k4 + SB2_DTB(18) * k5 + SB2_DTB(19) * k6;
+    dxdt_new = kirchner_rhs_flat(c1, c2, c3, pe, x_new);
+    const double x_err = SB2_DTB(20) * dxdt + SB2_DTB(21) * k3 + SB2_DTB(22) * k4 + SB2_DTB(23) * k5 + SB2_DTB(24) * k6 + SB2_DTB(25) * dxdt_new;
+#undef SB2_DTB
+    err_num = fabs(x_err);
+    err_den = eps_abs + eps_rel * (1.0 * fabs(x) + (1.0 * dt) * fabs(dxdt));
+}
+// UDT = true: t1 is the same for all lanes of the launch and dtb = t1 * tableau (PtgskRunArgs::dtb / HbvRunArgs::dtb)
+template <bool UDT>
+__device__ __forceinline__ bool kirchner_step_warp(const double* __restrict__ dtb, double c1, double c2, double c3, double t1, double& q, double& q_avg,
+                                                   double p, double e) {
     if (q < 0.00001) q = 0.00001;
     double x = sb_log_inl<true>(q);
     double t = 0.0, dt = t1;
     const double pe = p - e;
     double dxdt = kirchner_rhs_flat(c1, c2, c3, pe, x);
     double area = 0.0, f_a = q, t_a = 0.0;
-
-    // the tableau comes from constant memory (kDopri): a literal costs two uniform moves per use, a constant half a uniform load
-    const double b21 = kDopri[0];
-    const double b31 = kDopri[1], b32 = kDopri[2];
-    const double b41 = kDopri[3], b42 = kDopri[4], b43 = kDopri[5];
-    const double b51 = kDopri[6], b52 = kDopri[7], b53 = kDopri[8], b54 = kDopri[9];
-    const double b61 = kDopri[10], b62 = kDopri[11], b63 = kDopri[12], b64 = kDopri[13], b65 = kDopri[14];
-    const double c1_ = kDopri[15], c3_ = kDopri[16], c4_ = kDopri[17], c5_ = kDopri[18], c6_ = kDopri[19];
-    const double dc1 = kDopri[20], dc3 = kDopri[21], dc4 = kDopri[22], dc5 = kDopri[23], dc6 = kDopri[24], dc7 = kDopri[25];
-
     int fails = 0;
     bool failed = false;
     bool running = t < t1;
-    while (__any_sync(0xffffffffu, running)) {
-        double xt = 1.0 * x + dt * b21 * dxdt;
-        const double k2 = kirchner_rhs_flat(c1, c2, c3, pe, xt);
-        xt = 1.0 * x + dt * b31 * dxdt + dt * b32 * k2;
-        const double k3 = kirchner_rhs_flat(c1, c2, c3, pe, xt);
-        xt = 1.0 * x + dt * b41 * dxdt + dt * b42 * k2 + dt * b43 * k3;
-        const double k4 = kirchner_rhs_flat(c1, c2, c3, pe, xt);
-        xt = 1.0 * x + dt * b51 * dxdt + dt * b52 * k2 + dt * b53 * k3 + dt * b54 * k4;
-        const double k5 = kirchner_rhs_flat(c1, c2, c3, pe, xt);
-        xt = 1.0 * x + dt * b61 * dxdt + dt * b62 * k2 + dt * b63 * k3 + dt * b64 * k4 + dt * b65 * k5;
-        const double k6 = kirchner_rhs_flat(c1, c2, c3, pe, xt);
-        const double x_new = 1.0 * x + dt * c1_ * dxdt + dt * c3_ * k3 + dt * c4_ * k4 + dt * c5_ * k5 + dt * c6_ * k6;
-        const double dxdt_new = kirchner_rhs_flat(c1, c2, c3, pe, x_new);
-        const double x_err = dt * dc1 * dxdt + dt * dc3 * k3 + dt * dc4 * k4 + dt * dc5 * k5 + dt * dc6 * k6 + dt * dc7 * dxdt_new;
-        const double err_num = fabs(x_err), err_den = eps_abs + eps_rel * (1.0 * fabs(x) + (1.0 * dt) * fabs(dxdt));
-        if (running) {
-            const double t_new = t + dt;
-            if (err_num < 0.75 * err_den && !(t_new < t1)) {
-                // accepted and at (or beyond) t1 without needing err itself, see kirchner_step
-                if (!(t == 0.0 && t_new == t1 && fabs(dxdt_new) < inf_()))
-                    x = kirchner_calc_state(x, t_new - t, (t1 - t) / (t_new - t), dxdt, k3, k4, k5, k6, dxdt_new);
-                else
-                    x = x_new;
-                running = false;
-            } else {
-                const double err = err_num / err_den;
-                if (err > 1.0) {
-                    dt *= dmax(9.0 / 10.0 * sb_pow<true>(err, -1.0 / (4 - 1)), 1.0 / 5.0);
-                    if (++fails >= 500) { failed = true; running = false; }
-                } else {
-                    fails = 0;
-                    if (t_new < t1) {
-                        if (err < 0.5) dt *= 9.0 / 10.0 * sb_pow<true>(dmax(0.00032, err), -1.0 / 5);
-                        t = t_new;
-                        x = x_new;
-                        dxdt = dxdt_new;
-                        const double fq = sb_exp<true>(x);
-                        area += 0.5 * (f_a + fq) * (t - t_a);
-                        f_a = fq;
-                        t_a = t;
-                    } else {
-                        if (!(t == 0.0 && t_new == t1 && fabs(dxdt_new) < inf_()))
-                            x = kirchner_calc_state(x, t_new - t, (t1 - t) / (t_new - t), dxdt, k3, k4, k5, k6, dxdt_new);
-                        else
-                            x = x_new;
-                        running = false;
-                    }
-                }
-            }
+    // what the controller does with one try (controlled_runge_kutta::try_step + dense_output::do_step)
+    auto control = [&](double x_new, double dxdt_new, double k3, double k4, double k5, double k6, double err_num, double err_den) {
+        if (!running) return;
+        const double t_new = t + dt;
+        if (err_num < 0.75 * err_den && !(t_new < t1)) {
+            // accepted and at (or beyond) t1 without needing err itself, see kirchner_step
+            if (!(t == 0.0 && t_new == t1 && fabs(dxdt_new) < inf_()))
+                x = kirchner_calc_state(x, t_new - t, (t1 - t) / (t_new - t), dxdt, k3, k4, k5, k6, dxdt_new);
+            else
+                x = x_new;
+            running = false;
+            return;
         }
+        const double err = err_num / err_den;
+        if (err > 1.0) {
+            dt *= dmax(9.0 / 10.0 * sb_pow<true>(err, -1.0 / (4 - 1)), 1.0 / 5.0);
+            if (++fails >= 500) { failed = true; running = false; }
+            return;
+        }
+        fails = 0;
+        if (t_new < t1) {
+            if (err < 0.5) dt *= 9.0 / 10.0 * sb_pow<true>(dmax(0.00032, err), -1.0 / 5);
+            t = t_new;
+            x = x_new;
+            dxdt = dxdt_new;
+            const double fq = sb_exp<true>(x);
+            area += 0.5 * (f_a + fq) * (t - t_a);
+            f_a = fq;
+            t_a = t;
+        } else {
+            if (!(t == 0.0 && t_new == t1 && fabs(dxdt_new) < inf_()))
+                x = kirchner_calc_state(x, t_new - t, (t1 - t) / (t_new - t), dxdt, k3, k4, k5, k6, dxdt_new);
+            else
+                x = x_new;
+            running = false;
+        }
+    };
+    double x_new, dxdt_new, k3, k4, k5, k6, err_num, err_den;
+    if (UDT) {  // the first try: dt = t1 on every lane
+        kirchner_try<true>(dtb, dt, c1, c2, c3, pe, x, dxdt, x_new, dxdt_new, k3, k4, k5, k6, err_num, err_den);
+        control(x_new, dxdt_new, k3, k4, k5, k6, err_num, err_den);
+    }
+    while (__any_sync(0xffffffffu, running)) {
+        kirchner_try<false>(nullptr, dt, c1, c2, c3, pe, x, dxdt, x_new, dxdt_new, k3, k4, k5, k6, err_num, err_den);
+        control(x_new, dxdt_new, k3, k4, k5, k6, err_num, err_den);
     }
     q = sb_exp_flat<true>(x);
     area += 0.5 * (f_a + q) * (t1 - t_a);
@@ -826,17 +861,18 @@ __device__ __forceinline__ void prefetch_l1(const double* p) { asm volatile("pre
 
 // no minimum-blocks bound: left to itself the compiler settles on 72 registers (28 resident warps); (128, 1) lets it take 94 and costs
 // 2.4 ms per year, (128, 8..10) = 64..48 registers measured no gain (tools/build_variants.py A8..A10)
+template <bool UPAR>
 #ifdef SB2_MINBLOCKS_A
-__global__ void __launch_bounds__(SB2_BLOCK_A, SB2_MINBLOCKS_A) ptgsk_forcing_terms_kernel(const PtgskRunArgs a) {
+__global__ void __launch_bounds__(SB2_BLOCK_A, SB2_MINBLOCKS_A) ptgsk_forcing_terms_kernel(const __grid_constant__ PtgskRunArgs a) {
 #else
-__global__ void __launch_bounds__(SB2_BLOCK_A) ptgsk_forcing_terms_kernel(const PtgskRunArgs a) {
+__global__ void __launch_bounds__(SB2_BLOCK_A) ptgsk_forcing_terms_kernel(const __grid_constant__ PtgskRunArgs a) {
 #endif
     sb_math_stage_tables();
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= a.n_cells) return;
     if (a.active != nullptr && a.active[c] == 0) return;
     const int ens = blockIdx.z;  // parameter-set ensemble member (calibration), as in ptgsk_run_kernel
-    const PtgskParam& p = (a.ens_params != nullptr && a.pset[c] == 0) ? a.ens_params[ens] : a.params[a.pset[c]];
+    const PtgskParam& p = UPAR ? a.par0 : ((a.ens_params != nullptr && a.pset[c] == 0) ? a.ens_params[ens] : a.params[a.pset[c]]);
     const double pt_albedo = p.pt_albedo, pt_alpha = p.pt_alpha;
     const int64_t n = a.n_cells;
     double* __restrict__ s_pot = a.scr[SCR_POT] + (int64_t)ens * a.ens_scr_stride;
@@ -857,8 +893,9 @@ __global__ void __launch_bounds__(SB2_BLOCK_A) ptgsk_forcing_terms_kernel(const 
 }
 
 // COLLECT bits used here: 2 snow sca/swe, 4 snow_outflow, 8 state series (the eight gamma_snow fields)
-template <int COLLECT>
-__global__ void __launch_bounds__(SB2_BLOCK_B, SB2_MINBLOCKS_B) ptgsk_snow_kernel(const PtgskRunArgs a) {
+// UPAR: every cell uses the region parameter set and there is no ensemble -- parameters are read from the kernel's constant bank (a.par0)
+template <int COLLECT, bool UPAR>
+__global__ void __launch_bounds__(SB2_BLOCK_B, SB2_MINBLOCKS_B) ptgsk_snow_kernel(const __grid_constant__ PtgskRunArgs a) {
     sb_math_stage_tables();
     const int ens = blockIdx.y;
     // time split by ticket, as in ptgsk_response_kernel (1.76 waves of whole-window blocks otherwise); the memo starts empty in
@@ -885,7 +922,7 @@ __global__ void __launch_bounds__(SB2_BLOCK_B, SB2_MINBLOCKS_B) ptgsk_snow_kerne
     const int64_t c = group * blockDim.x + threadIdx.x;
     const bool live = c < a.n_cells && (a.active == nullptr || a.active[c] != 0);
     if (live) {
-    const PtgskParam& p = (a.ens_params != nullptr && a.pset[c] == 0) ? a.ens_params[ens] : a.params[a.pset[c]];
+    const PtgskParam& p = UPAR ? a.par0 : ((a.ens_params != nullptr && a.pset[c] == 0) ? a.ens_params[ens] : a.params[a.pset[c]]);
     const int64_t n = a.n_cells;
     const double* __restrict__ s_lw = a.scr[SCR_LW] + (int64_t)ens * a.ens_scr_stride;
     const double* __restrict__ s_tadd = a.scr[SCR_TADD] + (int64_t)ens * a.ens_scr_stride;
@@ -894,6 +931,10 @@ __global__ void __launch_bounds__(SB2_BLOCK_B, SB2_MINBLOCKS_B) ptgsk_snow_kerne
     const double altitude = a.z[c], cell_area_m2 = a.area[c], forest_fraction = a.forest[c];
     const double snow_storage_fraction = 1.0 - a.lake[c] - a.reservoir[c];
     const bool iso = p.calculate_iso_pot_energy != 0;
+    // the cell's effective coefficient of variation (gamma_snow.h:327), squared, as a divisor: the same every step
+    const double snow_cv = p.snow_cv + forest_fraction * p.snow_cv_forest_factor + altitude * p.snow_cv_altitude_factor;
+    const InvDivisor inv_cv2 = make_inv_divisor(snow_cv * snow_cv);
+    const GsStepConst gk{a.inv_dt_seconds, a.inv_dt_us};
     double* __restrict__ state = a.state + (int64_t)ens * a.ens_state_stride;
     GsState gs;
     // __ldcg: the state may have been written by the previous time slice on another SM a moment ago -- read it from L2, never from
@@ -931,8 +972,8 @@ __global__ void __launch_bounds__(SB2_BLOCK_B, SB2_MINBLOCKS_B) ptgsk_snow_kerne
         double wind = 0.0, rel_hum = 0.0;
         if (iso) { wind = a.f[3][o]; rel_hum = a.f[4][o]; }
         double sca, storage, outflow;
-        gs_step_core<(SB2_SNOW_FLAT != 0)>(gs, cache, sca, storage, outflow, p, a.day_of_year[step], a.sec_of_year[step], a.dt_seconds, a.dt_us, a.bb0, temp, rad, prec,
-                           lw, tadd, wind, rel_hum, forest_fraction, altitude);
+        gs_step_core<(SB2_SNOW_FLAT != 0)>(gs, cache, sca, storage, outflow, p, a.day_of_year[step], a.sec_of_year[step], a.dt_seconds, a.dt_us, gk, a.bb0, temp, rad,
+                                           prec, lw, tadd, wind, rel_hum, inv_cv2);
         s_outflow[o] = outflow;
         s_sca[o] = sca;
         if (COLLECT & 2) { a.resp[2][orow] = sca; a.resp[3][orow] = storage * snow_storage_fraction; }
@@ -961,8 +1002,8 @@ __global__ void __launch_bounds__(SB2_BLOCK_B, SB2_MINBLOCKS_B) ptgsk_snow_kerne
 }
 
 // COLLECT bits used here: 1 avg_discharge+charge, 4 glacier_melt/ae/pe, 8 state series (kirchner discharge)
-template <int COLLECT>
-__global__ void __launch_bounds__(SB2_BLOCK_C, SB2_MINBLOCKS_C) ptgsk_response_kernel(const PtgskRunArgs a) {
+template <int COLLECT, bool UPAR>
+__global__ void __launch_bounds__(SB2_BLOCK_C, SB2_MINBLOCKS_C) ptgsk_response_kernel(const __grid_constant__ PtgskRunArgs a) {
     sb_math_stage_tables();
     const int ens = blockIdx.y;
     // Time split.  A block steps one group of blockDim cells; with ~115 registers 2 500 of the 3 125 one-warp blocks of a 100 000-cell
@@ -995,7 +1036,7 @@ __global__ void __launch_bounds__(SB2_BLOCK_C, SB2_MINBLOCKS_C) ptgsk_response_k
     const int64_t cc = in_range ? c : a.n_cells - 1;  // out-of-range lanes shadow the last cell, never store
     const bool active = in_range && (a.active == nullptr || a.active[cc] != 0);
     const unsigned lane = threadIdx.x & 31u;
-    const PtgskParam& p = (a.ens_params != nullptr && a.pset[cc] == 0) ? a.ens_params[ens] : a.params[a.pset[cc]];
+    const PtgskParam& p = UPAR ? a.par0 : ((a.ens_params != nullptr && a.pset[cc] == 0) ? a.ens_params[ens] : a.params[a.pset[cc]]);
     double* __restrict__ state = a.state + (int64_t)ens * a.ens_state_stride;
     double* __restrict__ partial = a.partial != nullptr ? a.partial + (int64_t)ens * a.ens_partial_stride : nullptr;
     const double* __restrict__ s_pot = a.scr[SCR_POT] + (int64_t)ens * a.ens_scr_stride;
@@ -1004,7 +1045,7 @@ __global__ void __launch_bounds__(SB2_BLOCK_C, SB2_MINBLOCKS_C) ptgsk_response_k
     // Per-cell constants of the step (run_pt_gs_k prologue, pt_gs_k.h:347-357) live in shared memory, one column per thread: each is
     // read once or twice per step, and twelve doubles less in registers is one more resident warp per scheduler for the ODE solver.
 #if SB2_RESP_SMEM_CONST
-    __shared__ double cst[12][SB2_BLOCK_C];
+    __shared__ double cst[13][SB2_BLOCK_C];
 #define SB2_CST(k) (((volatile double*)cst[k])[threadIdx.x])
     {
         const double area = a.area[cc], gf = a.glacier[cc], lake = a.lake[cc], reservoir = a.reservoir[cc];
@@ -1022,7 +1063,9 @@ __global__ void __launch_bounds__(SB2_BLOCK_C, SB2_MINBLOCKS_C) ptgsk_response_k
         cst[9][threadIdx.x] = p.ae_scale_factor;
         cst[10][threadIdx.x] = p.gm_dtf;
         cst[11][threadIdx.x] = p.p_corr_scale_factor;
+        cst[12][threadIdx.x] = p.inv_ae_scale.y;
     }
+    const unsigned ae_e_lo = p.inv_ae_scale.e_lo;
     __syncwarp();
 #define cell_area_m2 SB2_CST(0)
 #define glacier_fraction SB2_CST(1)
@@ -1076,6 +1119,11 @@ __global__ void __launch_bounds__(SB2_BLOCK_C, SB2_MINBLOCKS_C) ptgsk_response_k
         }
         const int64_t step = a.first_step + i;
         const int64_t orow = (step - a.out_first_step) * n + cc;
+#if SB2_RESP_SMEM_CONST
+        const InvDivisor inv_ae{ae_scale_factor, SB2_CST(12), ae_e_lo};
+#else
+        const InvDivisor inv_ae = p.inv_ae_scale;
+#endif
         double out_q = 0.0, out_charge = 0.0;
         {   // every lane steps (the Kirchner solver is warp-synchronous); lanes without an active cell run on benign inputs, store nothing
             if ((COLLECT & 8) && active) a.st[0][orow] = mmh_to_m3s(kq, cell_area_m2);
@@ -1084,11 +1132,11 @@ __global__ void __launch_bounds__(SB2_BLOCK_C, SB2_MINBLOCKS_C) ptgsk_response_k
             const double gm_melt_m3s =
                 (glacier_area_m2 <= sca_m2 || temp <= 0.0) ? 0.0 : gm_dtf * temp * (glacier_area_m2 - sca_m2) * (0.001 / 86400.0);
             // actual_evapotranspiration::calculate_step, actual_evapotranspiration.h:56-62
-            const double ae = pot * (1.0 - sb_exp_flat<true>(-kq * 3.0 / ae_scale_factor)) * (1.0 - dmax(sca, glacier_fraction));
+            const double ae = pot * (1.0 - sb_exp_flat<true>(div_by(-kq * 3.0, inv_ae))) * (1.0 - dmax(sca, glacier_fraction));
             const double gm_mmh = div_pos(gm_melt_m3s, (1 / (3600.0 * 1000.0)) * cell_area_m2);  // m3s_to_mmh; mostly 0 / x (no melt)
             double q_avg, kq_new = active ? kq : 1.0;
             const double k_in = outflow * snow_storage_fraction + prec * kirchner_routed_prec + gm_routed * gm_mmh;
-            if (!kirchner_step_warp(c1, c2, c3, a.dt_hours, kq_new, q_avg, active ? k_in : 0.0, active ? ae : 0.0)) {
+            if (!kirchner_step_warp<true>(a.dtb, c1, c2, c3, a.dt_hours, kq_new, q_avg, active ? k_in : 0.0, active ? ae : 0.0)) {
                 failed = true;
                 q_avg = nan("");
             }

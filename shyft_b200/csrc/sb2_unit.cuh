@@ -8,7 +8,11 @@ namespace sb2 {
 
 enum { UNIT_EXP = 0, UNIT_LOG, UNIT_POW, UNIT_LGAMMA, UNIT_GAMMA_P, UNIT_CORR_LWC, UNIT_CALC_SNOW_STATE, UNIT_KIRCHNER_STEP,
        // the forms the production kernels use: branch-free exp/log/pow, the in-place snow state, the warp-synchronous Kirchner step
-       UNIT_EXP_FLAT, UNIT_LOG_FLAT, UNIT_POW_FLAT, UNIT_CALC_SNOW_STATE_HOT, UNIT_KIRCHNER_STEP_WARP, UNIT_GAMMA_P_PAIR, UNIT_N };
+       UNIT_EXP_FLAT, UNIT_LOG_FLAT, UNIT_POW_FLAT, UNIT_CALC_SNOW_STATE_HOT, UNIT_KIRCHNER_STEP_WARP, UNIT_GAMMA_P_PAIR,
+       // a / d through the reciprocal of a step-invariant divisor (div_by) and as the IEEE division; the Kirchner step with the host-evaluated dt * tableau
+       UNIT_DIV_BY, UNIT_KIRCHNER_STEP_WARP_UDT, UNIT_N };
+
+__constant__ double kUnitDtb[26];  // 1.0 * tableau, uploaded by sb2_unit_eval
 
 __global__ void unit_eval_kernel(int fn, int64_t n, const double* __restrict__ in, int n_in, double* __restrict__ out, int n_out) {
     sb_math_stage_tables();  // the step-kernel forms below read the tables from shared memory, the plain ones from global memory
@@ -27,7 +31,7 @@ __global__ void unit_eval_kernel(int fn, int64_t n, const double* __restrict__ i
         case UNIT_CORR_LWC: o[0] = gs_corr_lwc(a[0], a[1], a[2], a[3], a[4]); break;
         case UNIT_CALC_SNOW_STATE: {
             double lg_key = nan_(), lg_val = 0.0;
-            gs_calc_snow_state(a[0], a[1], a[2], a[3], a[4], a[5], a[6], o[0], o[1], lg_key, lg_val);
+            gs_calc_snow_state(a[0], a[1], a[2], a[3], a[4], make_inv_divisor(a[5]), a[6], o[0], o[1], lg_key, lg_val);
             break;
         }
         case UNIT_KIRCHNER_STEP: {
@@ -41,12 +45,12 @@ __global__ void unit_eval_kernel(int fn, int64_t n, const double* __restrict__ i
         case UNIT_POW_FLAT: o[0] = sb_pow_flat<true>(a[0], a[1]); break;
         case UNIT_CALC_SNOW_STATE_HOT: {
             double lg_key = nan_(), lg_val = 0.0;
-            gs_calc_snow_state_hot(a[0], a[1], a[2], a[3], a[4], a[5], a[6], o[0], o[1], lg_key, lg_val);
+            gs_calc_snow_state_hot(a[0], a[1], a[2], a[3], a[4], make_inv_divisor(a[5]), a[6], o[0], o[1], lg_key, lg_val);
             break;
         }
         case UNIT_KIRCHNER_STEP_WARP: {
             double q = a[4], q_avg = 0.0;
-            const bool ok = kirchner_step_warp(a[0], a[1], a[2], a[3], q, q_avg, a[5], a[6]);
+            const bool ok = kirchner_step_warp<false>(nullptr, a[0], a[1], a[2], a[3], q, q_avg, a[5], a[6]);
             o[0] = q; o[1] = q_avg; o[2] = ok ? 1.0 : 0.0;
             break;
         }
@@ -56,6 +60,13 @@ __global__ void unit_eval_kernel(int fn, int64_t n, const double* __restrict__ i
             double P1 = 0.0, P2 = 0.0;
             gamma_p_pair_inl(a[0], a[1], a[1] > 0.0, pre1, a[2], a[3], a[3] > 0.0, pre2, P1, P2);
             o[0] = P1; o[1] = P2;
+            break;
+        }
+        case UNIT_DIV_BY: o[0] = div_by(a[0], make_inv_divisor(a[1])); o[1] = a[0] / a[1]; break;
+        case UNIT_KIRCHNER_STEP_WARP_UDT: {  // t1 = 1 hour on every lane, products from the launch's constant table (filled by the host)
+            double q = a[4], q_avg = 0.0;
+            const bool ok = kirchner_step_warp<true>(kUnitDtb, a[0], a[1], a[2], 1.0, q, q_avg, a[5], a[6]);
+            o[0] = q; o[1] = q_avg; o[2] = ok ? 1.0 : 0.0;
             break;
         }
         default: break;

@@ -113,3 +113,43 @@ def test_kirchner_step_bit_identity_and_known_behaviour(capi, oracle):
         out = capi.unit_eval("kirchner_step", row)
         row[0, 4] = out[0, 0]
     assert abs(out[0, 0] - 10.0) < 1e-3 and abs(out[0, 1] - 10.0) < 1e-3
+
+
+def test_division_by_a_step_invariant_divisor_is_the_ieee_quotient(capi):
+    """div_by (sb2_math.cuh): a / d through the once-divided reciprocal and two fused corrections -- Markstein's theorem makes it the
+    correctly rounded quotient; the out-of-range numerators and divisors take the IEEE division.  Bit for bit against a / d on the
+    device and on the host."""
+    rng = np.random.default_rng(23)
+    n = 2_000_000
+    a = rng.standard_normal(n) * np.exp(rng.uniform(-40, 40, n))
+    d = np.exp(rng.uniform(-12, 24, n))
+    # the divisors of the step kernels, zero / tiny / huge / non-finite numerators, divisors with all-ones and all-zeros mantissas
+    d[:9] = [3600000000.0, 3600.0, 333660.0, 5.0, 0.96, 0.1, 0.16, 1.5, 0.4 * 0.4]
+    a[:64:7] = 0.0
+    a[1:64:7] = -0.0
+    a[100:110] = [np.inf, -np.inf, np.nan, 5e-324, 1e-310, 1e-250, 1e250, 1.7e308, -1e-300, 2.0**-823]
+    d[200:300] = np.nextafter(2.0 ** rng.integers(-20, 20, 100).astype(np.float64), 0.0)
+    d[300:400] = 2.0 ** rng.integers(-20, 20, 100).astype(np.float64)
+    d[400:410] = [0.0, np.inf, np.nan, 1e-300, 1e300, -3.0, -0.5, 2.0**-200, 2.0**199, 5e-324]
+    got = capi.unit_eval("div_by", np.stack([a, d], axis=1))
+    with np.errstate(all="ignore"):
+        want = a / d
+    assert _bits_equal(got[:, 1], want)          # the device's own IEEE division
+    assert _bits_equal(got[:, 0], want)          # div_by
+
+
+def test_kirchner_first_try_with_host_evaluated_products_is_bit_identical(capi, oracle):
+    """kirchner_step_warp<true>: the first try of a step multiplies the slopes with dt * tableau products evaluated on the host (the
+    production kernels' form) -- same bits as the per-lane products, with 1..n sub-step lanes mixed in a warp"""
+    rng = np.random.default_rng(19)
+    n = 20000 - 5
+    q = np.exp(rng.uniform(np.log(1e-6), np.log(60.0), n))
+    p = rng.exponential(2.0, n) * (rng.random(n) < 0.5)
+    p[::50] *= 40.0                                  # cloudbursts: rejected first tries, several sub-steps
+    e = rng.uniform(0, 0.3, n)
+    rows = np.stack([np.full(n, -2.439), np.full(n, 0.966), np.full(n, -0.10), np.full(n, 1.0), q, p, e], axis=1)
+    got = capi.unit_eval("kirchner_step_warp_udt", rows)
+    assert np.all(got[:, 2] == 1.0)
+    want = np.array([oracle.kirchner_step(r[4], r[5], r[6])[:2] for r in rows])
+    assert _bits_equal(got[:, :2], want)
+    assert _bits_equal(capi.unit_eval("kirchner_step_warp", rows)[:, :2], want)
