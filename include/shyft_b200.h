@@ -109,6 +109,14 @@ int sb2_has_catchment_parameter(const sb2_model* m, int64_t cid);               
 int sb2_set_catchment_calculation_filter(sb2_model* m, const int64_t* cids, int n);     /* :715-729; n == 0 clears */
 int sb2_set_states(sb2_model* m, const double* states, int64_t n_cells);                /* :802-809, [cell][state_size] */
 int sb2_get_states(const sb2_model* m, double* states, int64_t n_cells);                /* :784-787 */
+/* Flat state layouts ([cell][state_size], the order of the reference's state classes):
+ *   pt_gs_k   9: gs.albedo, gs.lwc, gs.surface_heat, gs.alpha, gs.sdc_melt_mean, gs.acc_melt, gs.iso_pot_energy, gs.temp_swe, kirchner.q
+ *   pt_hs_k  13: snow.swe, snow.sca, snow.sp[0..4], snow.sw[0..4], kirchner.q
+ *   hbv_stack 15: snow.swe, snow.sca, snow.sp[0..4], snow.sw[0..4], soil.sm, tank.uz, tank.lz
+ * hbv_snow::state::distribute(parameter, false) (core/hbv_snow.h:114-118; called first thing by pt_hs_k::run :230 and run_hbv_stack :312):
+ * rows whose ten snow bins are all zero -- the flat spelling of HbvSnowState(swe, sca) with empty bin vectors -- get sp / sw from swe, sca
+ * and the cell's hs parameters (hbv_snow_common.h:44-67); other rows are left as they are.  Host side, in place, before sb2_set_states. */
+int sb2_hbv_distribute_snow(const sb2_model* m, double* states, int64_t n_cells);
 int sb2_set_initial_state(sb2_model* m, const double* states, int64_t n_cells);         /* the public member initial_state, :313 */
 int sb2_get_initial_state(const sb2_model* m, double* states, int64_t n_cells);
 int sb2_revert_to_initial_state(sb2_model* m);                                          /* :814-818 */

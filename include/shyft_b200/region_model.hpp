@@ -82,7 +82,11 @@ class region_model {
     void set_catchment_calculation_filter(const std::vector<int64_t>& cids) { ck(sb2_set_catchment_calculation_filter(h_, cids.data(), int(cids.size()))); }  // :715-729
 
     // states: vector<state_t> flattened [cell][state_size]
-    void set_states(const std::vector<double>& states) { ck(sb2_set_states(h_, states.data(), int64_t(states.size()) / sb2_state_size(h_))); }  // :802-809
+    void set_states(const std::vector<double>& states) {                                                                                       // :802-809
+        const size_t ss = size_t(sb2_state_size(h_));
+        if (states.size() % ss != 0) throw std::runtime_error("set_states: the flattened state vector is not a whole number of cell states");
+        ck(sb2_set_states(h_, states.data(), int64_t(states.size() / ss)));  // a wrong cell count is the reference's "Length of the state vector ..." error
+    }
     void get_states(std::vector<double>& states) const { states.resize(size() * size_t(sb2_state_size(h_))); ck(sb2_get_states(h_, states.data(), int64_t(size()))); }
     void revert_to_initial_state() { ck(sb2_revert_to_initial_state(h_)); }                                                                   // :814-818
     void adjust_q(double q_scale, const std::vector<int64_t>& cids) { ck(sb2_adjust_q(h_, q_scale, cids.data(), int(cids.size()))); }          // :831-837
@@ -99,6 +103,7 @@ class region_model {
     std::vector<int64_t> apply_state(const std::vector<sb2_cell_state_id>& ids, const std::vector<double>& states, const std::vector<int64_t>& cids) {
         std::vector<int64_t> missing(ids.size() + 1);
         int64_t n = 0;
+        if (states.size() != ids.size() * size_t(sb2_state_size(h_))) throw std::runtime_error("apply_state: states must be [ids][state_size]");
         ck(sb2_apply_state(h_, int64_t(ids.size()), ids.data(), states.data(), cids.data(), int(cids.size()), missing.data(), &n));
         missing.resize(size_t(n));
         return missing;
@@ -116,6 +121,9 @@ class region_model {
     bool interpolate(const interpolation_parameter& ip, const region_environment& env, bool best_effort = true) {                                   // :397-527
         for (int v = 0; v < SB2_N_FORCING; ++v) {
             const geo_point_sources& s = env.of(v);
+            // the C ABI takes no element counts: a mis-shaped vector would be over-read during the upload
+            if (s.xyz.size() % 3 != 0) throw std::runtime_error("interpolate: source xyz must be [n_sources][3]");
+            if (s.values.size() != time_axis.n * s.size()) throw std::runtime_error("interpolate: source values must be [n_steps][n_sources]");
             ck(sb2_set_sources(h_, v, int64_t(s.size()), s.size() ? s.xyz.data() : nullptr, s.size() ? s.values.data() : nullptr));
         }
         int ok = 0;
@@ -126,6 +134,8 @@ class region_model {
     // a variable's series on their own point axis (any resolution), projected onto the model axis on the device (:426-438)
     void set_sources_on_axis(int var, const std::vector<double>& xyz, const std::vector<int64_t>& t_us, int64_t t_end_us,
                              const std::vector<double>& values /* [points][sources] */, int point_interpretation) {
+        if (xyz.size() % 3 != 0 || values.size() != t_us.size() * (xyz.size() / 3))
+            throw std::runtime_error("set_sources_on_axis: xyz must be [n_sources][3] and values [n_points][n_sources]");
         ck(sb2_set_sources_on_axis(h_, var, int64_t(xyz.size() / 3), xyz.data(), int64_t(t_us.size()), t_us.data(), t_end_us, values.data(),
                                    point_interpretation));
     }
@@ -169,7 +179,10 @@ class region_model {
         return v;
     }
     std::vector<double> river_output_flow_m3s(int64_t rid) { std::vector<double> v(time_axis.n); ck(sb2_river_flows(h_, rid, 0, int64_t(time_axis.n), nullptr, nullptr, v.data())); return v; }  // :926-933
-    void set_river_network(const std::vector<double>& rivers6) { ck(sb2_set_river_network(h_, int64_t(rivers6.size() / 6), rivers6.data())); }
+    void set_river_network(const std::vector<double>& rivers6) {
+        if (rivers6.size() % 6 != 0) throw std::runtime_error("set_river_network: rivers must be [n][6]");
+        ck(sb2_set_river_network(h_, int64_t(rivers6.size() / 6), rivers6.data()));
+    }
 
   private:
     template <class F>

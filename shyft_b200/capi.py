@@ -74,7 +74,7 @@ EXPORTS = """sb2_interpolation_parameter_default sb2_model_create sb2_model_dest
 sb2_number_of_catchments sb2_catchment_ids sb2_cell_catchment_ix sb2_parameter_size sb2_state_size sb2_set_region_parameter
 sb2_get_region_parameter sb2_set_catchment_parameter sb2_get_catchment_parameter sb2_remove_catchment_parameter
 sb2_has_catchment_parameter sb2_set_catchment_calculation_filter sb2_set_states sb2_get_states sb2_set_initial_state
-sb2_get_initial_state sb2_revert_to_initial_state sb2_adjust_q sb2_adjust_state_to_target_flow sb2_extract_state sb2_apply_state sb2_set_collector_mode sb2_initialize_cell_environment
+sb2_hbv_distribute_snow sb2_get_initial_state sb2_revert_to_initial_state sb2_adjust_q sb2_adjust_state_to_target_flow sb2_extract_state sb2_apply_state sb2_set_collector_mode sb2_initialize_cell_environment
 sb2_set_cell_forcing sb2_get_cell_forcing sb2_set_sources sb2_set_sources_on_axis sb2_set_sources_on_axes sb2_get_sources_on_model_axis sb2_interpolate sb2_is_cell_env_ts_ok sb2_run_cells sb2_run_windowed
 sb2_get_response sb2_get_state_series sb2_catchment_discharges sb2_catchment_charges sb2_statistics_series sb2_statistics_cells
 sb2_statistics_geo sb2_set_river_network sb2_river_flows

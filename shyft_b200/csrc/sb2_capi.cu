@@ -533,7 +533,6 @@ void check_device_errors(sb2_model* m) {
     if (flag) {
         CUDA_OK(cudaMemsetAsync(m->d_error_flag.p, 0, sizeof(int), m->stream));
         if (flag & ERR_KIRCHNER_STEP) throw Error("Max number of iterations exceeded (500). A new step size was not found.");
-        if (flag & ERR_MASS_BALANCE) throw Error("Mass balance violation!!!!");
         if (flag & ERR_HBV_NEGATIVE_OUTFLOW) throw Error("hbv_snow: Negative outflow");
         throw Error("device error flag " + std::to_string(flag));
     }
@@ -1309,7 +1308,11 @@ int sb2_get_catchment_parameter(const sb2_model* m, int64_t cid, double* p, int 
 }
 int sb2_remove_catchment_parameter(sb2_model* m, int64_t cid) {
     return guarded(m, [&] {
-        if (m->catch_param.erase(cid)) m->param_dirty = true;
+        if (m->catch_param.erase(cid)) {
+            m->param_dirty = true;
+            m->route.reset();  // the cells' unit hydrographs carry the removed override's routing velocity / alpha / beta
+            m->rlocal_valid = m->rnet_valid = false;
+        }
     });
 }
 int sb2_has_catchment_parameter(const sb2_model* m, int64_t cid) { return m && m->catch_param.count(cid) ? 1 : 0; }
@@ -1339,6 +1342,48 @@ int sb2_set_states(sb2_model* m, const double* states, int64_t n_cells) {
             m->d_initial_state.upload(soa, m->stream);
             CUDA_OK(cudaStreamSynchronize(m->stream));
             m->has_initial = true;
+        }
+    });
+}
+// hbv_snow::state::distribute(parameter, force = false) (core/hbv_snow.h:114-118 over hbv_snow_common.h:44-67), which pt_hs_k::run and
+// run_hbv_stack call first (core/pt_hs_k.h:230, core/hbv_stack.h:312): a state given as (swe, sca) with EMPTY bin vectors -- the usual
+// HbvSnowState(swe, sca) -- gets its bins from swe and sca.  The flat state of this ABI always carries the 5 + 5 bins, so "empty" is spelled
+// "all ten bins zero": such rows are distributed here (host side, before set_states); rows with any non-zero bin are left alone, exactly as
+// a state whose vectors already have the parameter's size.  states: [cell][state_size] in place, n_cells rows in the model's cell order.
+int sb2_hbv_distribute_snow(const sb2_model* cm, double* states, int64_t n_cells) {
+    return guarded_c(cm, [&] {
+        sb2_model* m = const_cast<sb2_model*>(cm);
+        if (m->stack == SB2_PT_GS_K) throw Error("distribute_snow: the pt_gs_k state has no snow bins");
+        if (n_cells != m->n) throw Error("Length of the state vector must equal number of cells");
+        const int lw_ix = m->stack == SB2_PT_HS_K ? 4 : 8;  // hs.lw in parameter::get order
+        for (int64_t i = 0; i < m->n; ++i) {
+            double* st = states + i * m->n_state;
+            double *swe = st, *sca = st + 1, *sp = st + 2, *sw = st + 2 + HBV_NB;
+            bool empty = true;
+            for (int k = 0; k < 2 * HBV_NB; ++k) empty = empty && sp[k] == 0.0;
+            if (!empty) continue;
+            auto f = m->catch_param.find(m->geo[i].catchment_id);
+            const std::vector<double>& pv = f != m->catch_param.end() ? f->second : m->region_param;
+            const HbvParam p = make_hbv_param(m->stack == SB2_HBV_STACK, pv.data());
+            const double lw = pv[lw_ix];
+            if (*swe <= 1.0e-3 || *sca <= 1.0e-3) { *swe = *sca = 0.0; continue; }
+            for (int k = 0; k < HBV_NB; ++k) sp[k] = *sca < p.I[k] ? 0.0 : p.s[k] * *swe;
+            // integrate(sp, intervals, n, 0.0, sca, true), hbv_snow_common.h:14-43 with a = x[0]
+            double area = 0.0, f_l = sp[0], x_l = 0.0;
+            for (int left = 0; left < HBV_NB - 1; ++left) {
+                if (*sca >= p.I[left + 1]) {
+                    area += 0.5 * (f_l + sp[left + 1]) * (p.I[left + 1] - x_l);
+                    x_l = p.I[left + 1];
+                    f_l = sp[left + 1];
+                } else {
+                    area += 0.5 * f_l * (*sca - x_l);
+                    break;
+                }
+            }
+            if (area < *swe) {
+                const double corr1 = *swe / area * lw, corr2 = *swe / area * (1.0 - lw);
+                for (int k = 0; k < HBV_NB; ++k) { sw[k] = corr1 * sp[k]; sp[k] *= corr2; }
+            }
         }
     });
 }
@@ -1487,7 +1532,7 @@ int sb2_initialize_cell_environment(sb2_model* m, int64_t t0_us, int64_t dt_us, 
         if (dt_us <= 0 || n < 0) throw Error("initialize_cell_environment: invalid time axis");
         const bool same_dt = dt_us == m->dt;
         m->t0 = t0_us; m->dt = dt_us; m->T = n;
-        if (!same_dt) m->param_dirty = true;  // the albedo decay steps depend on dt
+        if (!same_dt) { m->param_dirty = true; m->route.reset(); }  // the albedo decay steps and the unit hydrographs depend on dt
         std::vector<int32_t> doy(n), soy(n);
         m->h_prior_gradient.resize(n);
         for (int64_t i = 0; i < n; ++i) {
@@ -1510,6 +1555,23 @@ int sb2_initialize_cell_environment(sb2_model* m, int64_t t0_us, int64_t dt_us, 
         m->forcing_rows = 0; m->forcing_first = 0;
         free_series(m);
         m->ran_steps = 0;
+        // everything that was laid out on the PREVIOUS axis goes with it: the station series ([T_old][n_src] -- interpolating them over a
+        // longer or shifted axis would read past their end or pair them with the wrong times), the interpolation plans and kriging
+        // operators built on them, the cached point times of the axis, and the calibration targets (aligned against the old t0 / dt).
+        // interpolate / run_windowed then see unset sources (forcing stays NaN, as for a variable without sources) and
+        // calculate_goal_function asks for targets again.
+        for (int v = 0; v < SB2_N_FORCING; ++v) {
+            Source& src = m->src[v];
+            src.n_src = 0;
+            src.xyz.clear(); src.h_values.clear();
+            src.d_xyz.release(); src.d_values.release();
+            src.has_nonfinite = false;
+            m->idw[v].valid = false; m->idw[v].dense_valid = false;
+        }
+        m->btk_cache.clear();
+        m->d_axis_t.release();
+        m->targets.clear();
+        m->rlocal_valid = m->rnet_valid = false;
         CUDA_OK(cudaStreamSynchronize(m->stream));
     });
 }
@@ -1860,9 +1922,16 @@ int sb2_run_windowed(sb2_model* m, const sb2_interpolation_parameter* ip, int st
                 double* row0 = m->d_qhist.p + size_t(H) * m->n;
                 CUDA_OK(cudaMemcpyAsync(row0, m->d_resp[SB2_R_AVG_DISCHARGE].p, size_t(wn) * m->n * sizeof(double), cudaMemcpyDeviceToDevice, m->stream));
                 routing_local_inflow(*m->route, row0, m->n, wn, H, w0, m->T, m->d_rlocal.p, m->stream, &m->launches);
-                if (H > 0)  // the tail of this window becomes the history of the next (wn >= H for every window but possibly the last)
-                    CUDA_OK(cudaMemcpyAsync(m->d_qhist.p, m->d_qhist.p + size_t(wn) * m->n, size_t(H) * m->n * sizeof(double), cudaMemcpyDeviceToDevice,
-                                            m->stream));
+                // the last H rows of [history ; window] become the history of the next window: rows [wn, wn + H) -> [0, H).  With wn < H
+                // (window_steps below the longest unit hydrograph, or a short window) the two ranges overlap, which cudaMemcpy does not
+                // allow: moved in ascending pieces of at most wn rows, each piece's source lying wholly behind its destination.
+                if (H > 0 && w0 + wn < first + count) {
+                    for (int64_t r = 0; r < H; r += wn) {
+                        const int64_t rows = std::min<int64_t>(wn, H - r);
+                        CUDA_OK(cudaMemcpyAsync(m->d_qhist.p + size_t(r) * m->n, m->d_qhist.p + size_t(r + wn) * m->n, size_t(rows) * m->n * sizeof(double),
+                                                cudaMemcpyDeviceToDevice, m->stream));
+                    }
+                }
             }
             CUDA_OK(cudaEventRecord(m->ev[3], m->stream));
             CUDA_OK(cudaEventSynchronize(m->ev[3]));

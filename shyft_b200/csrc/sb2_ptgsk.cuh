@@ -47,7 +47,9 @@ struct PtgskParam {
     InvDivisor inv_snowfall_reset_depth, inv_one_minus_y0, inv_max_water, inv_ae_scale;
 };
 
-enum : int { ERR_KIRCHNER_STEP = 1, ERR_MASS_BALANCE = 2 };
+// device error bits.  gamma_snow's "Mass balance violation" (gamma_snow.h:310-311) has none: with snow, rain = prec, 0 or 0, prec the tested
+// |snow + rain - prec| is 0, or NaN for a non-finite prec, and neither exceeds 1e-8 -- the throw is unreachable.
+enum : int { ERR_KIRCHNER_STEP = 1 };
 
 struct PtgskRunArgs {
     int64_t n_cells;
@@ -728,12 +730,12 @@ __device__ __forceinline__ double kirchner_rhs_flat(double c1, double c2, double
 // UDT: dt is the same for every lane and its products with the tableau come from `dtb` (host-evaluated dt * b, the same IEEE products the
 // lane would form: (dt * b21) * dxdt is how `dt * b21 * dxdt` parses) -- the first try of every model step, i.e. > 99.9 % of all tries;
 // 26 fp64 multiplications less per step, and the products sit in the constant bank.
-template <bool UDT>
-__device__ __forceinline__ void kirchner_try(const double* __restrict__ dtb, double dt, double c1, double c2, double c3, double pe, double x, double dxdt,
+template <bool UDT, class ARGS>
+__device__ __forceinline__ void kirchner_try(const ARGS& ka, double dt, double c1, double c2, double c3, double pe, double x, double dxdt,
                                              double& x_new, double& dxdt_new, double& k3, double& k4, double& k5, double& k6, double& err_num,
                                              double& err_den) {
     const double eps_abs = 1.0e-7, eps_rel = 1.0e-8;
-#define SB2_DTB(k) (UDT ? dtb[k] : dt * kDopri[k])
+#define SB2_DTB(k) (UDT ? ka.dtb[k] : dt * kDopri[k])
     double xt = 1.0 * x + SB2_DTB(0) * dxdt;
     const double k2 = kirchner_rhs_flat(c1, c2, c3, pe, xt);
     xt = 1.0 * x + SB2_DTB(1) * dxdt + SB2_DTB(2) * k2;
@@ -751,9 +753,10 @@ __device__ __forceinline__ void kirchner_try(const double* __restrict__ dtb, dou
     err_num = fabs(x_err);
     err_den = eps_abs + eps_rel * (1.0 * fabs(x) + (1.0 * dt) * fabs(dxdt));
 }
-// UDT = true: t1 is the same for all lanes of the launch and dtb = t1 * tableau (PtgskRunArgs::dtb / HbvRunArgs::dtb)
-template <bool UDT>
-__device__ __forceinline__ bool kirchner_step_warp(const double* __restrict__ dtb, double c1, double c2, double c3, double t1, double& q, double& q_avg,
+// UDT = true: t1 is the same for all lanes of the launch and ka.dtb = t1 * tableau (PtgskRunArgs::dtb / HbvRunArgs::dtb: the kernel's
+// __grid_constant__ argument, read in place from the constant bank -- a pointer to it would cost an address conversion per use)
+template <bool UDT, class ARGS>
+__device__ __forceinline__ bool kirchner_step_warp(const ARGS& ka, double c1, double c2, double c3, double t1, double& q, double& q_avg,
                                                    double p, double e) {
     if (q < 0.00001) q = 0.00001;
     double x = sb_log_inl<true>(q);
@@ -803,11 +806,11 @@ __device__ __forceinline__ bool kirchner_step_warp(const double* __restrict__ dt
     };
     double x_new, dxdt_new, k3, k4, k5, k6, err_num, err_den;
     if (UDT) {  // the first try: dt = t1 on every lane
-        kirchner_try<true>(dtb, dt, c1, c2, c3, pe, x, dxdt, x_new, dxdt_new, k3, k4, k5, k6, err_num, err_den);
+        kirchner_try<true>(ka, dt, c1, c2, c3, pe, x, dxdt, x_new, dxdt_new, k3, k4, k5, k6, err_num, err_den);
         control(x_new, dxdt_new, k3, k4, k5, k6, err_num, err_den);
     }
     while (__any_sync(0xffffffffu, running)) {
-        kirchner_try<false>(nullptr, dt, c1, c2, c3, pe, x, dxdt, x_new, dxdt_new, k3, k4, k5, k6, err_num, err_den);
+        kirchner_try<false>(ka, dt, c1, c2, c3, pe, x, dxdt, x_new, dxdt_new, k3, k4, k5, k6, err_num, err_den);
         control(x_new, dxdt_new, k3, k4, k5, k6, err_num, err_den);
     }
     q = sb_exp_flat<true>(x);
@@ -1136,7 +1139,7 @@ __global__ void __launch_bounds__(SB2_BLOCK_C, SB2_MINBLOCKS_C) ptgsk_response_k
             const double gm_mmh = div_pos(gm_melt_m3s, (1 / (3600.0 * 1000.0)) * cell_area_m2);  // m3s_to_mmh; mostly 0 / x (no melt)
             double q_avg, kq_new = active ? kq : 1.0;
             const double k_in = outflow * snow_storage_fraction + prec * kirchner_routed_prec + gm_routed * gm_mmh;
-            if (!kirchner_step_warp<true>(a.dtb, c1, c2, c3, a.dt_hours, kq_new, q_avg, active ? k_in : 0.0, active ? ae : 0.0)) {
+            if (!kirchner_step_warp<true>(a, c1, c2, c3, a.dt_hours, kq_new, q_avg, active ? k_in : 0.0, active ? ae : 0.0)) {
                 failed = true;
                 q_avg = nan("");
             }

@@ -13,6 +13,7 @@ enum { UNIT_EXP = 0, UNIT_LOG, UNIT_POW, UNIT_LGAMMA, UNIT_GAMMA_P, UNIT_CORR_LW
        UNIT_DIV_BY, UNIT_KIRCHNER_STEP_WARP_UDT, UNIT_N };
 
 __constant__ double kUnitDtb[26];  // 1.0 * tableau, uploaded by sb2_unit_eval
+struct UnitDtb { struct { __device__ double operator[](int k) const { return kUnitDtb[k]; } } dtb; };
 
 __global__ void unit_eval_kernel(int fn, int64_t n, const double* __restrict__ in, int n_in, double* __restrict__ out, int n_out) {
     sb_math_stage_tables();  // the step-kernel forms below read the tables from shared memory, the plain ones from global memory
@@ -50,7 +51,7 @@ __global__ void unit_eval_kernel(int fn, int64_t n, const double* __restrict__ i
         }
         case UNIT_KIRCHNER_STEP_WARP: {
             double q = a[4], q_avg = 0.0;
-            const bool ok = kirchner_step_warp<false>(nullptr, a[0], a[1], a[2], a[3], q, q_avg, a[5], a[6]);
+            const bool ok = kirchner_step_warp<false>(UnitDtb{}, a[0], a[1], a[2], a[3], q, q_avg, a[5], a[6]);
             o[0] = q; o[1] = q_avg; o[2] = ok ? 1.0 : 0.0;
             break;
         }
@@ -65,7 +66,7 @@ __global__ void unit_eval_kernel(int fn, int64_t n, const double* __restrict__ i
         case UNIT_DIV_BY: o[0] = div_by(a[0], make_inv_divisor(a[1])); o[1] = a[0] / a[1]; break;
         case UNIT_KIRCHNER_STEP_WARP_UDT: {  // t1 = 1 hour on every lane, products from the launch's constant table (filled by the host)
             double q = a[4], q_avg = 0.0;
-            const bool ok = kirchner_step_warp<true>(kUnitDtb, a[0], a[1], a[2], 1.0, q, q_avg, a[5], a[6]);
+            const bool ok = kirchner_step_warp<true>(UnitDtb{}, a[0], a[1], a[2], 1.0, q, q_avg, a[5], a[6]);
             o[0] = q; o[1] = q_avg; o[2] = ok ? 1.0 : 0.0;
             break;
         }

@@ -231,11 +231,23 @@ class RegionModel:
     # -- state ---------------------------------------------------------------------------------------------------------
     def set_states(self, states):
         s = f64(states)
-        if s.ndim != 2 or s.shape[1] != self.state_size:
-            if s.shape[0] != self.size():
-                raise RuntimeError("Length of the state vector must equal number of cells")
+        if s.ndim != 2:
+            raise RuntimeError("states must be [cell][state_size]")
+        if s.shape[0] != self.size():
+            raise RuntimeError("Length of the state vector must equal number of cells")   # core/region_model.h:803-804
+        if s.shape[1] != self.state_size:
             raise RuntimeError("state rows must have state_size values")
         self._ck(self._L.sb2_set_states(self._h, dptr(s), C.c_int64(s.shape[0])))
+
+    def distribute_snow(self, states):
+        """hbv_snow::state::distribute(parameter, force=False) for a flat state array: rows whose ten snow bins are all zero (the
+        flat spelling of HbvSnowState(swe, sca)) get sp / sw from swe and sca, as pt_hs_k::run / run_hbv_stack do first thing
+        (core/pt_hs_k.h:230, core/hbv_stack.h:312, core/hbv_snow_common.h:44-67).  -> a new [cell][state_size] array for set_states."""
+        s = f64(states).copy()
+        if s.shape != (self.size(), self.state_size):
+            raise RuntimeError("states must be [cell][state_size]")
+        self._ck(self._L.sb2_hbv_distribute_snow(self._h, dptr(s), C.c_int64(s.shape[0])))
+        return s
 
     def get_states(self, out=None):
         """-> [cell][state_size]; `out` = a caller-owned C-contiguous float64 array of that shape to fill instead (e.g. pinned host memory)"""
@@ -260,6 +272,8 @@ class RegionModel:
     @initial_state.setter
     def initial_state(self, states):
         s = f64(states)
+        if s.shape != (self.size(), self.state_size):
+            raise RuntimeError("initial_state must be [cell][state_size]")
         self._ck(self._L.sb2_set_initial_state(self._h, dptr(s), C.c_int64(s.shape[0])))
 
     def revert_to_initial_state(self):
@@ -296,6 +310,8 @@ class RegionModel:
 
     def set_cell_forcing(self, name, values, layout=capi.TIME_MAJOR):
         v = f64(values)
+        if v.shape != ((self.time_axis.n, self.size()) if layout == capi.TIME_MAJOR else (self.size(), self.time_axis.n)):
+            raise RuntimeError(f"{name}: cell forcing must be [n_steps][cell] (TIME_MAJOR) or [cell][n_steps] (CELL_MAJOR)")
         self._ck(self._L.sb2_set_cell_forcing(self._h, C.c_int(FORCING_NAMES.index(name)), dptr(v), C.c_int(layout)))
 
     def cell_forcing(self, name, start_step=0, n_steps=None, layout=capi.TIME_MAJOR):
@@ -325,6 +341,8 @@ class RegionModel:
                                                          src.point_fx.ctypes.data_as(C.POINTER(C.c_int32))))
                 continue
             xyz, values = f64(src[0]), f64(src[1])
+            if xyz.ndim != 2 or xyz.shape[1] != 3:
+                raise RuntimeError(f"{name}: source positions must be [n_sources][3]")
             if values.shape != (self.time_axis.n, xyz.shape[0]):
                 raise RuntimeError(f"{name}: source values must be [n_steps][n_sources]")
             self._ck(self._L.sb2_set_sources(self._h, C.c_int(vi), C.c_int64(xyz.shape[0]), dptr(xyz), dptr(values)))

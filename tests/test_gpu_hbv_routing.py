@@ -181,3 +181,34 @@ def test_reference_python_hbv_model_run(sb, oracle):
     want = oracle.hbv_stack_run_cells(g, HBV_DEFAULT, f, s0, fx["t0"] * 10**6, 3600 * 10**6)
     assert_parity(m.response("avg_discharge"), want["avg_discharge"], "hbv python fixture discharge")
     assert want["avg_discharge"][0].sum() >= 32.0
+
+
+@pytest.mark.parametrize("stack", [1, 2])
+def test_snow_state_given_as_swe_and_sca_is_distributed_like_the_reference(sb, oracle, stack):
+    """HbvSnowState(swe, sca) with empty bins: pt_hs_k::run / run_hbv_stack call state.snow.distribute(parameter, false) first
+    (core/pt_hs_k.h:230, core/hbv_stack.h:312; hbv_snow_common.h:44-67).  model.distribute_snow is that call for the flat state."""
+    cls, par = (sb.PTHSKModel, PTHSK_DEFAULT) if stack == 1 else (sb.HbvStackModel, HBV_DEFAULT)
+    m, geo, ta, st0, f = _setup(sb, cls, par, stack, n=64, T=300)
+    rng = np.random.default_rng(3)
+    s = st0.copy()
+    s[:, 0] = rng.uniform(0.0, 300.0, 64)      # swe
+    s[:, 1] = rng.uniform(0.0, 1.0, 64)        # sca
+    s[:4, 0] = [0.0, 5e-4, 50.0, 50.0]         # no pack / below the 1e-3 thresholds
+    s[:4, 1] = [0.5, 0.5, 0.0, 5e-4]
+    s[10, 2:12] = 7.0                          # bins given: left alone
+    d = m.distribute_snow(s)
+    lw = par[4] if stack == 1 else par[8]
+    for i in range(64):
+        if i == 10:
+            assert np.array_equal(d[i], s[i])
+            continue
+        sp, sw, swe, sca = oracle.hbv_snow_distribute(s[i, 0], s[i, 1], [1.0] * 5, [0, 0.25, 0.5, 0.75, 1.0], lw=lw)
+        assert np.array_equal(d[i, 2:7], sp) and np.array_equal(d[i, 7:12], sw) and d[i, 0] == swe and d[i, 1] == sca, i
+    assert np.all(d[:4, :2] == 0.0)
+    # and the run from the distributed state equals the oracle's run from it
+    m.set_states(d)
+    m.run_cells()
+    run = oracle.pthsk_run_cells if stack == 1 else oracle.hbv_stack_run_cells
+    want = run(geo_matrix(geo), par, f, d, ta.start * 10**6, ta.delta_t * 10**6)
+    assert_parity(m.response("snow_swe"), want["snow_swe"], "snow_swe from a distributed state")
+    assert_parity(m.response("avg_discharge"), want["avg_discharge"], "discharge from a distributed state")

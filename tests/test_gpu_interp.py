@@ -225,3 +225,32 @@ def test_every_station_on_its_own_axis(sb, oracle):
     assert np.array_equal(np.isnan(a), np.isnan(b)) and np.allclose(a[~np.isnan(a)], b[~np.isnan(b)], rtol=1e-12, atol=0)
     with pytest.raises(RuntimeError, match="strictly increasing"):
         m._set_sources(sb.RegionEnvironment(temperature=sb.GeoPointSourceVector([(xyz[0], [t0, t0], [1.0, 2.0], t0 + 10, "average")])))
+
+
+def test_a_new_time_axis_drops_everything_laid_out_on_the_old_one():
+    """initialize_cell_environment (core/region_model.h:359-364) with another axis: the station series, interpolation plans and calibration
+    targets of the previous axis are gone -- a windowed run without new sources sees unset sources (NaN forcing), never the old buffers
+    read past their end."""
+    import shyft_b200 as sb
+    from shyft_b200 import synthetic
+    geo, ta, env = synthetic.make_region(200, 96, 9, config_index=5)
+    m = sb.PTGSKOptModel(geo)
+    ip = sb.InterpolationParameter()
+    assert m.run_interpolation(ip, ta, env)
+    m.set_states(synthetic.default_state(0, 200))
+    m.run_cells()
+    assert np.all(np.isfinite(m.catchment_discharges()))
+    longer = sb.TimeAxis(ta.start + 7 * 3600, 3600, 4 * 96)          # same dt, other start, four times the length
+    m.initialize_cell_environment(longer)
+    with pytest.raises(RuntimeError):
+        m.sources_on_model_axis("temperature")                       # no sources on this axis
+    try:
+        m.run_windowed(ip, window_steps=128)
+    except RuntimeError:
+        pass                                                         # NaN forcing may be reported by the Kirchner stepper
+    assert np.all(np.isnan(m.cell_forcing("temperature", 3 * 96, 96)))
+    # with sources of the new axis everything works again
+    geo2, ta2, env2 = synthetic.make_region(200, 4 * 96, 9, config_index=5, start=longer.start)
+    m.revert_to_initial_state()
+    m.run_windowed(ip, env=env2, window_steps=128)
+    assert np.all(np.isfinite(m.catchment_discharges()))
