@@ -20,6 +20,7 @@
 #include "sb2_ptgsk.cuh"
 #include "sb2_hbv.cuh"
 #include "sb2_routing.cuh"
+#include <nvtx3/nvToolsExt.h>  // header-only; ranges are no-ops unless a profiler is attached
 #include "sb2_unit.cuh"
 #include "sb2_goal.cuh"
 #include "sb2_stats.cuh"
@@ -469,8 +470,10 @@ void launch_step_range(sb2_model* m, int64_t first, int64_t n_steps, bool collec
             // UPAR kernels: no catchment override in use -> every cell reads the region parameter set from the constant bank
             const bool upar = m->catch_param.empty();
             const dim3 ga((unsigned)grid_for(n, SB2_BLOCK_A), (unsigned)grid_for(chunk, SB2_STEPS_A));
+            nvtxRangePushA("A forcing_terms");
             if (upar) ptgsk_forcing_terms_kernel<true><<<ga, SB2_BLOCK_A, SB2_MTAB_BYTES, m->stream>>>(a);
             else ptgsk_forcing_terms_kernel<false><<<ga, SB2_BLOCK_A, SB2_MTAB_BYTES, m->stream>>>(a);
+            nvtxRangePop();
             const int gb = grid_for(n, SB2_BLOCK_B), gc = grid_for(n, SB2_BLOCK_C);
             // snow and response kernels in slices of SB2_UNIT_STEPS steps handed out by ticket (see the kernels); counters zeroed per launch
             const bool split = use_time_split(gb);
@@ -478,19 +481,23 @@ void launch_step_range(sb2_model* m, int64_t first, int64_t n_steps, bool collec
             m->d_tickets.ensure(size_t(1 + std::max(gb, gc)));
             a.unit_steps = split ? SB2_UNIT_STEPS : 0; a.tickets = m->d_tickets.p; a.progress = m->d_tickets.p + 1;
             CUDA_OK(cudaMemsetAsync(m->d_tickets.p, 0, size_t(1 + gb) * sizeof(int), m->stream));
+            nvtxRangePushA("B snow");
             switch (m->collect_bits & 14) {
 #define SB2_CASE(B) case B: if (upar) ptgsk_snow_kernel<B, true><<<gb * n_slices, SB2_BLOCK_B, SB2_MTAB_BYTES, m->stream>>>(a); \
                             else ptgsk_snow_kernel<B, false><<<gb * n_slices, SB2_BLOCK_B, SB2_MTAB_BYTES, m->stream>>>(a); break;
                 SB2_CASE(0) SB2_CASE(2) SB2_CASE(4) SB2_CASE(6) SB2_CASE(8) SB2_CASE(10) SB2_CASE(12) SB2_CASE(14)
 #undef SB2_CASE
             }
+            nvtxRangePop();
             CUDA_OK(cudaMemsetAsync(m->d_tickets.p, 0, size_t(1 + gc) * sizeof(int), m->stream));
+            nvtxRangePushA("C response");
             switch (m->collect_bits & 13) {
 #define SB2_CASE(B) case B: if (upar) ptgsk_response_kernel<B, true><<<gc * n_slices, SB2_BLOCK_C, SB2_MTAB_BYTES, m->stream>>>(a); \
                             else ptgsk_response_kernel<B, false><<<gc * n_slices, SB2_BLOCK_C, SB2_MTAB_BYTES, m->stream>>>(a); break;
                 SB2_CASE(0) SB2_CASE(1) SB2_CASE(4) SB2_CASE(5) SB2_CASE(8) SB2_CASE(9) SB2_CASE(12) SB2_CASE(13)
 #undef SB2_CASE
             }
+            nvtxRangePop();
             m->launches += 2;
         } else {
             HbvRunArgs a{};
@@ -518,6 +525,7 @@ void launch_step_range(sb2_model* m, int64_t first, int64_t n_steps, bool collec
             else hbv_run_kernel<true><<<g * n_slices, block, SB2_MTAB_BYTES, m->stream>>>(a);
         }
         CUDA_OK(cudaGetLastError());
+        NvtxRange nv_reduce("catchment_reduce");
         const int64_t total = int64_t(chunk) * m->n_catch();
         catchment_reduce_kernel<<<grid_for(total, 256), 256, 0, m->stream>>>(m->d_partial.p, m->n_slots, m->d_cat_ptr.p, m->d_cat_slots.p,
                                                                               int(m->n_catch()), chunk, m->d_cq.p, m->d_cc.p, s0, 0, 0);
@@ -808,6 +816,7 @@ void interpolate_variable(sb2_model* m, int var, int64_t first, int64_t n_steps,
 }
 
 bool interpolate_range(sb2_model* m, int64_t first, int64_t n_steps, int best_effort) {
+    NvtxRange nv("interpolate");
     sync_filter(m);
     bool all_ok = true;
     for (int var = 0; var < SB2_N_FORCING; ++var) {
@@ -855,6 +864,16 @@ void copy_out_2d(sb2_model* m, const double* d_src /* [rows][n] */, int64_t rows
     }
     CUDA_OK(cudaStreamSynchronize(m->stream));
 }
+
+// NVTX ranges around the phases of the ABI calls (nsys / ncu --nvtx timelines): interpolate, window i, forcing_terms / snow / response,
+// catchment_reduce, routing
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    explicit NvtxRange(const std::string& name) { nvtxRangePushA(name.c_str()); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 void time_begin(sb2_model* m, int which) { CUDA_OK(cudaEventRecord(m->ev[which], m->stream)); }
 float time_end(sb2_model* m, int a, int b) {
@@ -1904,6 +1923,7 @@ int sb2_run_windowed(sb2_model* m, const sb2_interpolation_parameter* ip, int st
         m->rlocal_valid = m->rnet_valid = false;
         for (int64_t w0 = first; w0 < first + count; w0 += W) {
             const int64_t wn = std::min<int64_t>(W, first + count - w0);
+            NvtxRange nv_window("window " + std::to_string((w0 - first) / W));
             // the window buffers are reused: forcing rows [w0, w0+W), series rows likewise
             if (m->forcing_rows != W || !m->d_forcing[0].p) {
                 for (auto& f : m->d_forcing) f.resize(size_t(W) * m->n);
@@ -1919,6 +1939,7 @@ int sb2_run_windowed(sb2_model* m, const sb2_interpolation_parameter* ip, int st
             CUDA_OK(cudaEventRecord(m->ev[2], m->stream));
             launch_step_range(m, w0, wn, true);
             if (route) {
+                NvtxRange nv_route("routing local inflow");
                 double* row0 = m->d_qhist.p + size_t(H) * m->n;
                 CUDA_OK(cudaMemcpyAsync(row0, m->d_resp[SB2_R_AVG_DISCHARGE].p, size_t(wn) * m->n * sizeof(double), cudaMemcpyDeviceToDevice, m->stream));
                 routing_local_inflow(*m->route, row0, m->n, wn, H, w0, m->T, m->d_rlocal.p, m->stream, &m->launches);
@@ -2315,6 +2336,7 @@ int sb2_device_catchment_charges(sb2_model* m, void** dptr, int64_t* n_steps, in
     return guarded(m, [&] { *dptr = m->d_cc.p; *n_steps = m->T; *n_catchments = m->n_catch(); });
 }
 int64_t sb2_kernel_launches(const sb2_model* m) { return m ? m->launches : -1; }
+int sb2_step_chunk_steps(const sb2_model* m) { return m ? m->partial_steps : -1; }
 int sb2_last_run_kernel_ms(const sb2_model* m, float* step_ms, float* interp_ms) {
     return guarded_c(m, [&] {
         if (step_ms) *step_ms = m->last_step_ms;

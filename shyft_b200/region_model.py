@@ -448,6 +448,10 @@ class RegionModel:
     def kernel_launches(self):
         return int(self._L.sb2_kernel_launches(self._h))
 
+    def step_chunk_steps(self):
+        """steps one launch of the step kernels covers (a forcing window is stepped in chunks of this many steps)"""
+        return int(self._L.sb2_step_chunk_steps(self._h))
+
     def last_run_kernel_ms(self):
         a, b = C.c_float(0), C.c_float(0)
         self._ck(self._L.sb2_last_run_kernel_ms(self._h, C.byref(a), C.byref(b)))
