@@ -125,6 +125,16 @@ struct DevArray {  // library-owned device buffer
     void upload(const std::vector<T>& h, cudaStream_t s) { upload(h.data(), h.size(), s); }
 };
 
+// NVTX ranges around the phases of the ABI calls (nsys / ncu --nvtx timelines): interpolate, window i, forcing_terms / snow / response,
+// catchment_reduce, routing
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    explicit NvtxRange(const std::string& name) { nvtxRangePushA(name.c_str()); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+
 struct Source {  // one region_environment variable: geo-located series on the model axis (api/api.h:137-168)
     int64_t n_src = 0;
     std::vector<double> xyz;       // [src][3]
@@ -864,16 +874,6 @@ void copy_out_2d(sb2_model* m, const double* d_src /* [rows][n] */, int64_t rows
     }
     CUDA_OK(cudaStreamSynchronize(m->stream));
 }
-
-// NVTX ranges around the phases of the ABI calls (nsys / ncu --nvtx timelines): interpolate, window i, forcing_terms / snow / response,
-// catchment_reduce, routing
-struct NvtxRange {
-    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
-    explicit NvtxRange(const std::string& name) { nvtxRangePushA(name.c_str()); }
-    ~NvtxRange() { nvtxRangePop(); }
-    NvtxRange(const NvtxRange&) = delete;
-    NvtxRange& operator=(const NvtxRange&) = delete;
-};
 
 void time_begin(sb2_model* m, int which) { CUDA_OK(cudaEventRecord(m->ev[which], m->stream)); }
 float time_end(sb2_model* m, int a, int b) {
