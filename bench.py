@@ -112,7 +112,8 @@ def build_workload(args, rank, world):
     n_steps = int(round(args.years * 8760))
     n_total = args.cells * world
     # the whole region is generated identically on every rank; each rank keeps its shard (cells are independent)
-    geo, ta, env = synthetic.make_region(n_total, n_steps, args.stations, config_index=1)
+    # catchments of 1 000 cells; at N > 1 of 1 500 cells, so that catchments straddle the shard boundaries and the all-reduce has real sums to form
+    geo, ta, env = synthetic.make_region(n_total, n_steps, args.stations, config_index=1, cells_per_catchment=1000 if world == 1 else 1500)
     from shyft_b200.sharding import partition_cells
     b, e = partition_cells(n_total, world, rank)
     return geo, geo[b:e], ta, env, synthetic.default_state(0, e - b)

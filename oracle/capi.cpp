@@ -42,6 +42,7 @@ extern "C" {
 
 const char* sho_last_error() { return g_err.c_str(); }
 int sho_hardware_concurrency() { return int(std::thread::hardware_concurrency()); }
+void sho_set_gamma_policy(int mode) { special::g_gamma_policy = mode; }  // tools/gamma_policy_sensitivity.py; 0 = full double (the oracle proper)
 #ifdef SHO_COUNT
 void sho_cost_buffer(unsigned char* buf) { dm::g_cost_cursor = buf; }
 void sho_counters(long long* out, int reset) {  // tools/cost_model.py

@@ -114,7 +114,21 @@ inline double m3s_to_mmh(double m3s, double area_m2) { return m3s / (mmh_to_m3s_
 // ---------------------------------------------------------------------------
 namespace special {
 
-inline double lgamma_(double a) { return dm::lgamma(a); }  // boost::math::lgamma, gamma_snow.h:199-201 (full double, deterministic: sho_detmath.hpp)
+// Sensitivity switch (tools/gamma_policy_sensitivity.py only; 0 everywhere else).  The reference evaluates gamma_p / lgamma under boost
+// policies digits10<5> (a >= 2) and digits10<10> (a < 2), core/gamma_snow.h:189-201: 18 and 35 binary digits, i.e. series and continued
+// fractions stop at 2^-17 / 2^-34 relative.  With g_gamma_policy = 1 the restatement below stops at those epsilons and rounds lgamma to
+// that many digits -- not boost's arithmetic (which cannot be reproduced offline), but an error of the size boost's has, which is what
+// bounds how far the full-double oracle can be from real Shyft in this branch.
+inline int g_gamma_policy = 0;
+inline double policy_eps(double a) { return a < 2.0 ? 5.8207660913467407e-11 /* 2^-34 */ : 7.62939453125e-06 /* 2^-17 */; }
+inline double lgamma_(double a) {  // boost::math::lgamma, gamma_snow.h:199-201 (full double, deterministic: sho_detmath.hpp)
+    const double v = dm::lgamma(a);
+    if (!g_gamma_policy || v == 0.0 || !std::isfinite(v)) return v;
+    const int bits = a < 2.0 ? 35 : 18;
+    int e;
+    const double m = std::frexp(v, &e);
+    return std::ldexp(std::nearbyint(std::ldexp(m, bits)), e - bits);
+}
 
 // common prefix x^a e^-x / Gamma(a); the same expression order gamma_snow.h:245,254 uses
 inline double gamma_prefix(double a, double x) { return dm::exp(a * dm::log(x) - x - lgamma_(a)); }
@@ -132,7 +146,7 @@ inline double gamma_prefix(double a, double x) { return dm::exp(a * dm::log(x) -
 inline double gamma_p(double a, double x) {
     if (!(x > 0.0)) return 0.0;
     if (std::isinf(x)) return 1.0;
-    const double eps = 1.0e-16;
+    const double eps = g_gamma_policy ? policy_eps(a) : 1.0e-16;
     const double small = 3.0549363634996047e-151;  // 2^-500
     const double pre = gamma_prefix(a, x);
     if (x < a + 1.0) {

@@ -54,10 +54,5 @@ def test_all_reduced_catchment_series_equal_the_single_gpu_run(tmp_path, world):
     assert np.all(np.isfinite(q1)) and q1.max() > 0.0
     assert_parity(red["q"], q1, f"all-reduced catchment discharge, {world} ranks", rtol=1e-12)
     assert_parity(red["c"], c1, f"all-reduced catchment charge, {world} ranks", rtol=1e-12, atol_frac=1e-12)
-    # catchments that lie wholly inside one shard are bit-identical (nothing is re-associated)
-    from shyft_b200 import sharding
-    cix, _ = sharding.global_catchment_index(geo["catchment_id"])
-    for k in range(q1.shape[1]):
-        owners = {r for r in range(world) if np.any(cix[slice(*sharding.partition_cells(geo.shape[0], world, r))] == k)}
-        if len(owners) == 1:
-            assert np.array_equal(red["q"][:, k], q1[:, k]), k
+    # (not bit-identical even for a catchment that lies wholly inside one shard: the deterministic segmented reduction groups a catchment's
+    # cells by warp, and a shard's warps start at another cell than the whole region's)
