@@ -267,6 +267,9 @@ int sb2_set_idw_dense(sb2_model* m, int on);
 int sb2_set_stream(sb2_model* m, void* cuda_stream);           /* launch on this stream (default: the legacy default stream) */
 int sb2_device_catchment_discharges(sb2_model* m, void** dptr, int64_t* n_steps, int64_t* n_catchments); /* [T][n_catch] fp64 in HBM */
 int sb2_device_catchment_charges(sb2_model* m, void** dptr, int64_t* n_steps, int64_t* n_catchments);
+/* diagnostic: with SB2_GUARD=1 in the environment every device buffer carries 4 KB red zones; -> number of buffers whose zones were
+ * overwritten so far (0 = no out-of-bounds write seen), the first finding as text */
+int64_t sb2_check_guards(char* message, int message_size);
 int64_t sb2_kernel_launches(const sb2_model* m);               /* launches of this library's kernels since creation */
 int sb2_step_chunk_steps(const sb2_model* m);                  /* steps one launch of the step kernels covers (0 before the first run) */
 int sb2_last_run_kernel_ms(const sb2_model* m, float* step_ms, float* interp_ms); /* CUDA-event time of the last run's kernels */

@@ -78,7 +78,7 @@ sb2_hbv_distribute_snow sb2_get_initial_state sb2_revert_to_initial_state sb2_ad
 sb2_set_cell_forcing sb2_get_cell_forcing sb2_set_sources sb2_set_sources_on_axis sb2_set_sources_on_axes sb2_get_sources_on_model_axis sb2_interpolate sb2_is_cell_env_ts_ok sb2_run_cells sb2_run_windowed
 sb2_get_response sb2_get_state_series sb2_catchment_discharges sb2_catchment_charges sb2_statistics_series sb2_statistics_cells
 sb2_statistics_geo sb2_set_river_network sb2_river_flows
-sb2_set_targets sb2_calculate_goal_function sb2_calculate_goal_function_batch sb2_unit_eval sb2_host_eval sb2_set_idw_dense sb2_set_stream sb2_device_catchment_discharges sb2_device_catchment_charges sb2_step_chunk_steps sb2_kernel_launches sb2_last_run_kernel_ms""".split()
+sb2_set_targets sb2_calculate_goal_function sb2_calculate_goal_function_batch sb2_unit_eval sb2_host_eval sb2_set_idw_dense sb2_set_stream sb2_device_catchment_discharges sb2_device_catchment_charges sb2_step_chunk_steps sb2_check_guards sb2_kernel_launches sb2_last_run_kernel_ms""".split()
 
 _LIB = None
 
@@ -124,6 +124,14 @@ UNIT_FUNCTIONS = dict(exp=(0, 1, 1), log=(1, 1, 1), pow=(2, 2, 1), lgamma=(3, 1,
                       # the forms the production kernels use (sb2_unit.cuh)
                       exp_flat=(8, 1, 1), log_flat=(9, 1, 1), pow_flat=(10, 2, 1), calc_snow_state_hot=(11, 7, 2), kirchner_step_warp=(12, 7, 3),
                       gamma_p_pair=(13, 4, 2), div_by=(14, 2, 2), kirchner_step_warp_udt=(15, 7, 3))
+
+
+def check_guards():
+    """-> (violations, first finding): the red zones of every live device buffer (SB2_GUARD=1), see sb2_check_guards"""
+    buf = C.create_string_buffer(256)
+    L = lib()
+    L.sb2_check_guards.restype = C.c_int64
+    return int(L.sb2_check_guards(buf, C.c_int(256))), buf.value.decode()
 
 
 def host_eval(fn, inputs, n_out):

@@ -84,6 +84,56 @@ struct DevicePool {
     }
 };
 
+// Red zones (diagnostic, SB2_GUARD=1 in the environment): compute-sanitizer is not available on every GPU pool, so the library can check
+// itself for out-of-bounds WRITES -- every device buffer is then allocated with 4 KB of 0xA5 bytes in front of and behind it (the pool is
+// bypassed), and sb2_check_guards() / every release verifies that the zones are intact.  tests/test_gpu_guards.py runs the multi-wave
+// time-sliced step kernels, the TMA-staged interpolation, routing and the goal kernels this way.
+struct GuardZones {
+    static constexpr size_t Z = 4096;
+    std::mutex mu;
+    std::map<void*, size_t> live;  // user pointer -> user bytes
+    int64_t violations = 0;
+    std::string first;
+    static GuardZones& get() { static GuardZones g; return g; }
+    static bool on() { const char* e = std::getenv("SB2_GUARD"); return e && e[0] == '1'; }
+    void* alloc(size_t bytes) {
+        unsigned char* raw = nullptr;
+        if (cudaMalloc((void**)&raw, bytes + 2 * Z) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        cudaMemset(raw, 0xA5, Z);
+        cudaMemset(raw + Z + bytes, 0xA5, Z);
+        std::lock_guard<std::mutex> g(mu);
+        live[raw + Z] = bytes;
+        return raw + Z;
+    }
+    bool owns(void* p) { std::lock_guard<std::mutex> g(mu); return live.count(p) != 0; }
+    void check_one(void* p, size_t bytes) {  // mu held
+        std::vector<unsigned char> h(2 * Z);
+        cudaDeviceSynchronize();
+        cudaMemcpy(h.data(), (unsigned char*)p - Z, Z, cudaMemcpyDeviceToHost);
+        cudaMemcpy(h.data() + Z, (unsigned char*)p + bytes, Z, cudaMemcpyDeviceToHost);
+        for (size_t i = 0; i < 2 * Z; ++i)
+            if (h[i] != 0xA5) {
+                ++violations;
+                if (first.empty())
+                    first = "red zone of a " + std::to_string(bytes) + "-byte device buffer overwritten " +
+                            (i < Z ? std::to_string(Z - i) + " bytes before its start" : std::to_string(i - Z) + " bytes behind its end");
+                break;
+            }
+    }
+    void free(void* p) {
+        std::lock_guard<std::mutex> g(mu);
+        auto f = live.find(p);
+        check_one(p, f->second);
+        live.erase(f);
+        cudaFree((unsigned char*)p - Z);
+    }
+    int64_t check_all() {
+        std::lock_guard<std::mutex> g(mu);
+        for (auto& kv : live) check_one(kv.first, kv.second);
+        return violations;
+    }
+};
+
 template <class T>
 struct DevArray {  // library-owned device buffer
     T* p = nullptr;
@@ -93,13 +143,17 @@ struct DevArray {  // library-owned device buffer
     DevArray& operator=(const DevArray&) = delete;
     ~DevArray() { release(); }
     void release() {
-        if (p && !DevicePool::get().park(p, n * sizeof(T))) cudaFree(p);
+        if (p && GuardZones::get().owns(p)) GuardZones::get().free(p);
+        else if (p && !DevicePool::get().park(p, n * sizeof(T))) cudaFree(p);
         p = nullptr; n = 0;
     }
     void resize(size_t count) {
         if (count == n) return;
         release();
-        if (count) {
+        if (count && GuardZones::on()) {
+            p = static_cast<T*>(GuardZones::get().alloc(count * sizeof(T)));
+            if (!p) throw Error("device allocation of " + std::to_string(count * sizeof(T)) + " bytes (+ red zones) failed");
+        } else if (count) {
             p = static_cast<T*>(DevicePool::get().take(count * sizeof(T)));
             if (!p) {
                 cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
@@ -2334,6 +2388,14 @@ int sb2_device_catchment_discharges(sb2_model* m, void** dptr, int64_t* n_steps,
 }
 int sb2_device_catchment_charges(sb2_model* m, void** dptr, int64_t* n_steps, int64_t* n_catchments) {
     return guarded(m, [&] { *dptr = m->d_cc.p; *n_steps = m->T; *n_catchments = m->n_catch(); });
+}
+int64_t sb2_check_guards(char* message, int message_size) {
+    const int64_t v = GuardZones::get().check_all();
+    if (message && message_size > 0) {
+        std::lock_guard<std::mutex> g(GuardZones::get().mu);
+        std::snprintf(message, size_t(message_size), "%s", GuardZones::get().first.c_str());
+    }
+    return v;
 }
 int64_t sb2_kernel_launches(const sb2_model* m) { return m ? m->launches : -1; }
 int sb2_step_chunk_steps(const sb2_model* m) { return m ? m->partial_steps : -1; }
