@@ -8,5 +8,5 @@ from .capi import (COLLECT_ALL, COLLECT_DISCHARGE, COLLECT_NONE, COLLECT_SNOW, C
                    InterpolationParameter)
 from .region_model import (GeoPointSources, GeoPointSourceVector, HbvModel, HbvOptModel, HbvStackModel, HbvStackOptModel, PTGSKModel, PTGSKOptModel, PTHSKModel, PTHSKOptModel,  # noqa: F401
                            RegionEnvironment, RegionModel, TimeAxis, geo_cell_data_vector)
-from .calibration import Optimizer, TargetSpecification  # noqa: F401,E402
+from .calibration import Optimizer, TargetSpecification, calendar_period_points  # noqa: F401,E402
 from .state_io import StateIoHandler, StateWithIdVector, cell_state_id_of  # noqa: F401,E402

@@ -18,6 +18,27 @@ DISCHARGE, SNOW_COVERED_AREA, SNOW_WATER_EQUIVALENT, ROUTED_DISCHARGE, CELL_CHAR
 USEC = 1000000
 
 
+def calendar_period_points(start, unit, n):
+    """n + 1 boundaries [s] of n calendar periods (unit: 'day', 'week', 'month', 'quarter', 'year') from `start` [s since epoch], UTC calendar:
+    a calendar_dt target axis (core/time_axis.h calendar_dt; month / year steps of core/utctime_utilities.cpp:151-228) spelled as the point
+    axis `TargetSpecification(time_points=...)` takes.  The day of month is clipped to the target month's length."""
+    if unit in ("day", "week"):
+        return [int(start) + i * (86400 if unit == "day" else 7 * 86400) for i in range(n + 1)]
+    months = {"month": 1, "quarter": 3, "year": 12}[unit]
+    t0 = np.datetime64(int(start), "s")
+    day0 = t0.astype("datetime64[D]")
+    tod = int((t0 - day0) / np.timedelta64(1, "s"))
+    m0 = day0.astype("datetime64[M]")
+    dom = int((day0 - m0) / np.timedelta64(1, "D"))
+    out = []
+    for i in range(n + 1):
+        m = m0 + np.timedelta64(i * months, "M")
+        length = int(((m + np.timedelta64(1, "M")).astype("datetime64[D]") - m.astype("datetime64[D]")) / np.timedelta64(1, "D"))
+        d = m.astype("datetime64[D]") + np.timedelta64(min(dom, length - 1), "D")
+        out.append(int(d.astype("datetime64[s]").astype(np.int64)) + tod)
+    return out
+
+
 class TargetSpecification:
     """target_specification<PS> (:242-329): observed series on its own fixed axis + what it is compared with."""
 

@@ -572,6 +572,10 @@ void launch_step_range(sb2_model* m, int64_t first, int64_t n_steps, bool collec
             a.n_steps = chunk; a.first_step = s0;
             a.dt_seconds = dt_seconds; a.dt_hours = dt_seconds / 3600.0; a.dt_us = double(m->dt);
             fill_dopri_products(a.dt_hours, a.dtb);
+            a.inv_dt_hours = make_inv_divisor(a.dt_hours);
+            a.step_in_days = dt_seconds / 86400.0;
+            a.par0 = make_hbv_param(m->stack == SB2_HBV_STACK, m->region_param.data());
+            const bool upar = m->catch_param.empty();
             for (int r = 0; r < 9; ++r) a.resp[r] = m->d_resp[r].p;
             for (int s = 0; s < n_state_series(m); ++s) a.st[s] = m->d_st[s].p;
             a.out_first_step = m->out_first;
@@ -585,8 +589,13 @@ void launch_step_range(sb2_model* m, int64_t first, int64_t n_steps, bool collec
             m->d_tickets.ensure(size_t(1 + g));
             a.unit_steps = split ? SB2_HBV_UNIT_STEPS : 0; a.tickets = m->d_tickets.p; a.progress = m->d_tickets.p + 1;
             if (split) CUDA_OK(cudaMemsetAsync(m->d_tickets.p, 0, size_t(1 + g) * sizeof(int), m->stream));
-            if (m->stack == SB2_PT_HS_K) hbv_run_kernel<false><<<g * n_slices, block, SB2_MTAB_BYTES, m->stream>>>(a);
-            else hbv_run_kernel<true><<<g * n_slices, block, SB2_MTAB_BYTES, m->stream>>>(a);
+            if (m->stack == SB2_PT_HS_K) {
+                if (upar) hbv_run_kernel<false, true><<<g * n_slices, block, SB2_MTAB_BYTES, m->stream>>>(a);
+                else hbv_run_kernel<false, false><<<g * n_slices, block, SB2_MTAB_BYTES, m->stream>>>(a);
+            } else {
+                if (upar) hbv_run_kernel<true, true><<<g * n_slices, block, SB2_MTAB_BYTES, m->stream>>>(a);
+                else hbv_run_kernel<true, false><<<g * n_slices, block, SB2_MTAB_BYTES, m->stream>>>(a);
+            }
         }
         CUDA_OK(cudaGetLastError());
         NvtxRange nv_reduce("catchment_reduce");

@@ -33,6 +33,7 @@ struct HbvParam {
     double p_corr_scale_factor;
     double pt_albedo, pt_alpha;
     double reservoir_direct_response_fraction;
+    InvDivisor inv_lp, inv_fc, inv_ae_scale;  // parameter-only divisors with their reciprocals (div_by, sb2_math.cuh)
 };
 
 // host: parameter vectors in the order of pt_hs_k::parameter::set (core/pt_hs_k.h:66-88) / hbv_stack::parameter::set (core/hbv_stack.h:73-99)
@@ -55,6 +56,9 @@ inline HbvParam make_hbv_param(bool hbv_stack, const double* v) {
     double mean = 0.0;
     for (int i = 0; i < HBV_NB - 1; ++i) mean += 0.5 * (1.0 + 1.0) * (I[i + 1] - I[i]);
     for (int i = 0; i < HBV_NB; ++i) { p.I[i] = I[i]; p.s[i] = 1.0 / mean; }
+    p.inv_lp = make_inv_divisor(p.lp);
+    p.inv_fc = make_inv_divisor(p.fc);
+    p.inv_ae_scale = make_inv_divisor(p.ae_scale_factor);
     return p;
 }
 
@@ -82,6 +86,9 @@ struct HbvRunArgs {
     int64_t first_step;
     double dt_seconds, dt_hours, dt_us;
     double dtb[26];              // dt_hours * Dormand-Prince tableau (kirchner_try<true>, sb2_ptgsk.cuh)
+    InvDivisor inv_dt_hours;     // the step length in hours as a divisor (hbv_snow's outflow, hbv_snow.h:209,272)
+    double step_in_days;         // dt_seconds / 86400 (hbv_snow.h:199), host-evaluated
+    HbvParam par0;               // the region parameter set by value
     double* __restrict__ resp[9];
     double* __restrict__ st[5 + 2 * HBV_NB];  // state series, ids of include/shyft_b200.h (the per-bin sp / sw series last)
     int64_t out_first_step;
@@ -118,14 +125,14 @@ __device__ __forceinline__ double hbv_integrate0(const double (&f)[HBV_NB], cons
 }
 
 // hbv_snow::calculator::step, core/hbv_snow.h:195-275.  Returns false on "Negative outflow".
+// dt_hours = dt_seconds / 3600 and step_in_days = dt_seconds / 86400 (:199-200) come host-evaluated; inv_dt_hours divides by dt_hours
 __device__ __forceinline__ bool hbv_snow_step(double (&sp)[HBV_NB], double (&sw)[HBV_NB], double& s_swe, double& s_sca, double& outflow,
-                                              const HbvParam& p, double dt_seconds, double prec_mm_h, double temp) {
+                                              const HbvParam& p, double dt_hours, double step_in_days, const InvDivisor& inv_dt_hours, double prec_mm_h,
+                                              double temp) {
     double swe = s_swe, sca = s_sca;
     double I[HBV_NB];
 #pragma unroll
     for (int i = 0; i < HBV_NB; ++i) I[i] = p.I[i];
-    const double step_in_days = dt_seconds / 86400.0;
-    const double dt_hours = dt_seconds / 3600.0;
     const double prec = prec_mm_h * dt_hours;
     const double total_water = prec + swe;
     double snow, rain;
@@ -133,7 +140,7 @@ __device__ __forceinline__ bool hbv_snow_step(double (&sp)[HBV_NB], double (&sw)
     else { snow = 0.0; rain = prec; }
     swe += snow + sca * rain;
     if (swe < 0.1) {
-        outflow = div_pos(total_water, dt_hours);
+        outflow = div_by(total_water, inv_dt_hours);
 #pragma unroll
         for (int i = 0; i < HBV_NB; ++i) sp[i] = sw[i] = 0.0;
         s_swe = 0.0;
@@ -228,7 +235,7 @@ __device__ __forceinline__ bool hbv_snow_step(double (&sp)[HBV_NB], double (&sw)
         if (total_water - swe < -1.0e-6) ok = false;
         else swe = total_water;
     }
-    outflow = div_pos(total_water - swe, dt_hours);
+    outflow = div_by(total_water - swe, inv_dt_hours);
     s_swe = swe;
     s_sca = sca;
     return ok;
@@ -244,7 +251,8 @@ __device__ __forceinline__ bool hbv_snow_step(double (&sp)[HBV_NB], double (&sw)
 #ifndef SB2_HBV_MINBLOCKS_S
 #define SB2_HBV_MINBLOCKS_S 5   // hbv_stack (soil + tank)
 #endif
-template <bool HBV_STACK>
+// UPAR: no catchment override in use -- every cell reads the region parameter set (a.par0) from the kernel's constant bank
+template <bool HBV_STACK, bool UPAR>
 __global__ void __launch_bounds__(128, (HBV_STACK ? SB2_HBV_MINBLOCKS_S : SB2_HBV_MINBLOCKS_K)) hbv_run_kernel(const __grid_constant__ HbvRunArgs a) {
     constexpr int NS = HBV_STACK ? 5 + 2 * HBV_NB : 3 + 2 * HBV_NB;
     sb_math_stage_tables();  // exp / log tables of the shared math spec into this block's shared memory (sb2_math.cuh)
@@ -278,7 +286,7 @@ __global__ void __launch_bounds__(128, (HBV_STACK ? SB2_HBV_MINBLOCKS_S : SB2_HB
     const unsigned lane = threadIdx.x & 31u;
     const int64_t n = a.n_cells;
 
-    const HbvParam& p = a.params[a.pset[cc]];
+    const HbvParam& p = UPAR ? a.par0 : a.params[a.pset[cc]];
     const double cell_area_m2 = a.area[cc], glacier_fraction = a.glacier[cc], lake = a.lake[cc], reservoir = a.reservoir[cc];
     const double gm_direct = p.gm_direct_response;
     const double gm_routed = 1 - gm_direct;
@@ -316,8 +324,21 @@ __global__ void __launch_bounds__(128, (HBV_STACK ? SB2_HBV_MINBLOCKS_S : SB2_HB
     };
 
     bool failed_snow = false, failed_k = false;
+    // the next step's forcing is loaded one step ahead into registers and SB2_PREFETCH_AHEAD steps ahead into L1 (as the pt_gs_k kernels do):
+    // the step consumes one 8-byte value per array, so without it every step waits for DRAM
+    const int64_t o_first = (int64_t)i_begin * n + cc;
+    double f_t = a.f[0][o_first], f_p = a.f[1][o_first], f_r = a.f[2][o_first], f_h = a.f[4][o_first];
     for (int i = i_begin; i < i_end; ++i) {
         const int64_t o = (int64_t)i * n + cc;
+        const double temp = f_t, rad = f_r, rel_hum = f_h, prec_raw = f_p;
+        if (i + 1 < i_end) {
+            const int64_t o1 = o + n;
+            f_t = a.f[0][o1]; f_p = a.f[1][o1]; f_r = a.f[2][o1]; f_h = a.f[4][o1];
+        }
+        if (SB2_PREFETCH_AHEAD > 1 && i + SB2_PREFETCH_AHEAD < a.n_steps) {
+            const int64_t o2 = o + SB2_PREFETCH_AHEAD * n;
+            prefetch_l1(a.f[0] + o2); prefetch_l1(a.f[1] + o2); prefetch_l1(a.f[2] + o2); prefetch_l1(a.f[4] + o2);
+        }
         const int64_t step = a.first_step + i;
         const int64_t orow = (step - a.out_first_step) * n + cc;
         double out_q = 0.0, out_charge = 0.0;
@@ -325,20 +346,19 @@ __global__ void __launch_bounds__(128, (HBV_STACK ? SB2_HBV_MINBLOCKS_S : SB2_HB
         // lanes without an active cell on benign inputs
         double prec = 0.0, snow_outflow = 0.0, gm_melt_m3s = 0.0, pot = 0.0, gm_mmh = 0.0, ae = 0.0, total_discharge = 0.0, soil_outflow = 0.0;
         if (active) {
-            const double temp = a.f[0][o], rad = a.f[2][o], rel_hum = a.f[4][o];
-            prec = a.f[1][o] * p.p_corr_scale_factor;
+            prec = prec_raw * p.p_corr_scale_factor;
             if (a.collect & 8) collect_state(orow);
-            if (!hbv_snow_step(sp, sw, swe, sca, snow_outflow, p, a.dt_seconds, prec, temp)) failed_snow = true;
+            if (!hbv_snow_step(sp, sw, swe, sca, snow_outflow, p, a.dt_hours, a.step_in_days, a.inv_dt_hours, prec, temp)) failed_snow = true;
             const double sca_m2 = cell_area_m2 * sca;
             gm_melt_m3s = (glacier_area_m2 <= sca_m2 || temp <= 0.0) ? 0.0 : p.gm_dtf * temp * (glacier_area_m2 - sca_m2) * (0.001 / 86400.0);
             pot = pt_potential_evapotranspiration<true>(p.pt_albedo, p.pt_alpha, temp, rad, rel_hum) * 3600.0;
             gm_mmh = div_pos(gm_melt_m3s, (1 / (3600.0 * 1000.0)) * cell_area_m2);  // m3s_to_mmh; mostly 0 / x (no melt)
             if (HBV_STACK) {
                 const double snow_fraction = dmax(sca, glacier_fraction);
-                ae = (1.0 - snow_fraction) * (x0 < p.lp ? pot * (x0 / p.lp) : pot);  // hbv_actual_evapotranspiration.h:32-38
+                ae = (1.0 - snow_fraction) * (x0 < p.lp ? pot * div_by(x0, p.inv_lp) : pot);  // hbv_actual_evapotranspiration.h:32-38
                 {  // hbv_soil::step, hbv_soil.h:59-64
                     const double t = x0 + snow_outflow;
-                    const double of = snow_outflow * sb_pow<true>(t / p.fc, p.beta);
+                    const double of = snow_outflow * sb_pow<true>(div_by(t, p.inv_fc), p.beta);
                     soil_outflow = of > t ? t : of;
                     x0 = dmax(0.0, x0 + snow_outflow - soil_outflow - ae);
                 }
@@ -355,7 +375,7 @@ __global__ void __launch_bounds__(128, (HBV_STACK ? SB2_HBV_MINBLOCKS_S : SB2_HB
                 }
                 total_discharge = dmax(0.0, prec - ae) * direct_response_fraction + gm_direct * gm_mmh + tank_outflow * land_fraction;
             } else {
-                ae = pot * (1.0 - sb_exp_flat<true>(-x0 * 3.0 / p.ae_scale_factor)) * (1.0 - dmax(sca, glacier_fraction));
+                ae = pot * (1.0 - sb_exp_flat<true>(div_by(-x0 * 3.0, p.inv_ae_scale))) * (1.0 - dmax(sca, glacier_fraction));
             }
         }
         if (!HBV_STACK) {

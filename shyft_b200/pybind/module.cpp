@@ -118,6 +118,46 @@ void bind_model(py::module_& m, const char* name, int collect_bits, const char* 
              py::arg("scope") = int(SB2_SCOPE_CATCHMENT_IX));
 }
 
+// model_calibrator<RegionModel>(optimizer_name) of api/boostpython/expose.h:472-731: the optimizer class of one model type under the
+// reference's member names.  keep_alive ties the model's lifetime to the optimizer that holds a reference to it.
+template <int STACK>
+void bind_optimizer(py::module_& m, const char* name) {
+    using O = sb::optimizer<STACK>;
+    using M = sb::region_model<STACK>;
+    using P = std::vector<double>;
+    py::class_<O>(m, name, "optimizer<region_model, parameter, ts> (core/model_calibration.h:404-900): goal-function entry on the device, search drivers on the host")
+        .def(py::init<M&, const std::vector<sb::target_specification>&, const P&, const P&>(), py::arg("model"), py::arg("targets"), py::arg("p_min"),
+             py::arg("p_max"), py::keep_alive<1, 2>())
+        .def(py::init<M&>(), py::arg("model"), py::keep_alive<1, 2>())
+        .def("set_target_specification", &O::set_target_specification, py::arg("target_specification"), py::arg("parameter_lower_bound"),
+             py::arg("parameter_upper_bound"))
+        .def("set_parameter_ranges", &O::set_parameter_ranges, py::arg("p_min"), py::arg("p_max"))
+        .def("set_verbose_level", &O::set_verbose_level, py::arg("level"))
+        .def("reset_states", &O::reset_states)
+        .def("calculate_goal_function", &O::calculate_goal_function, py::arg("full_vector_of_parameters"))
+        .def("calculate_goal_function_batch",
+             [](O& self, const darray& P) {
+                 if (P.ndim() != 2) throw std::runtime_error("calculate_goal_function_batch: parameters must be [n_sets][parameter_size]");
+                 std::vector<std::vector<double>> sets(size_t(P.shape(0)), std::vector<double>(size_t(P.shape(1))));
+                 for (py::ssize_t k = 0; k < P.shape(0); ++k) std::memcpy(sets[size_t(k)].data(), P.data(k, 0), size_t(P.shape(1)) * sizeof(double));
+                 return self.calculate_goal_function_batch(sets);
+             },
+             py::arg("parameter_sets"), "a whole population in one device pass; equals calling calculate_goal_function once per set")
+        .def("optimize", &O::optimize, py::arg("p"), py::arg("max_n_evaluations"), py::arg("tr_start"), py::arg("tr_stop"))
+        .def("optimize_dream", &O::optimize_dream, py::arg("p"), py::arg("max_n_evaluations"))
+        .def("optimize_sceua", &O::optimize_sceua, py::arg("p"), py::arg("max_n_evaluations"), py::arg("x_eps"), py::arg("y_eps"))
+        .def("parameter_active", &O::active_parameter, py::arg("i"))
+        .def_property_readonly("trace_size", &O::trace_size)
+        .def_readonly("trace_goal_function_values", &O::goal_fn_trace)
+        .def("trace_goal_function_value", &O::trace_goal_function_value, py::arg("i"))
+        .def("trace_parameter", &O::trace_parameter, py::arg("i"))
+        .def_readonly("target_specification", &O::targets)
+        .def_readonly("parameter_lower_bound", &O::parameter_lower_bound)
+        .def_readonly("parameter_upper_bound", &O::parameter_upper_bound)
+        .def_readonly("n_single_calls", &O::n_single_calls)
+        .def_readonly("n_batch_calls", &O::n_batch_calls);
+}
+
 }  // namespace
 
 PYBIND11_MODULE(_shyft_b200_cpp, m) {
@@ -137,6 +177,48 @@ PYBIND11_MODULE(_shyft_b200_cpp, m) {
           py::arg("geo_cell_data_vector"), py::arg("region_parameter"), py::arg("device") = 0);
     m.def("HbvOptModel", [opt](const py::array& geo, const std::vector<double>& p, int device) { return make_model<SB2_HBV_STACK>(geo, p, device, opt); },
           py::arg("geo_cell_data_vector"), py::arg("region_parameter"), py::arg("device") = 0);
+    // TargetSpecificationPts / TargetSpecificationVector (api/boostpython/api_target_specification.cpp:50-61); the vector is a Python list
+    py::class_<sb::target_specification>(m, "TargetSpecificationPts", "target_specification<pts_t> (core/model_calibration.h:242-329)")
+        .def(py::init([](const std::vector<double>& values, int64_t t0_us, int64_t dt_us, const std::vector<int64_t>& cids, double scale_factor, int calc_mode,
+                         double s_r, double s_a, double s_b, int catchment_property, int64_t river_id, const std::string& uid,
+                         const std::vector<int64_t>& period_points_us) {
+                 sb::target_specification t;
+                 t.values = values; t.t0_us = t0_us; t.dt_us = dt_us; t.catchment_indexes = cids; t.scale_factor = scale_factor; t.calc_mode = calc_mode;
+                 t.s_r = s_r; t.s_a = s_a; t.s_b = s_b; t.catchment_property = catchment_property; t.river_id = river_id; t.uid = uid;
+                 t.period_points_us = period_points_us;
+                 return t;
+             }),
+             py::arg("values"), py::arg("t0_us"), py::arg("dt_us"), py::arg("catchment_indexes") = std::vector<int64_t>{}, py::arg("scale_factor") = 1.0,
+             py::arg("calc_mode") = int(sb::NASH_SUTCLIFFE), py::arg("s_r") = 1.0, py::arg("s_a") = 1.0, py::arg("s_b") = 1.0,
+             py::arg("catchment_property") = int(sb::DISCHARGE), py::arg("river_id") = 0, py::arg("uid") = std::string(),
+             py::arg("period_points_us") = std::vector<int64_t>{})
+        .def_readwrite("values", &sb::target_specification::values)
+        .def_readwrite("catchment_indexes", &sb::target_specification::catchment_indexes)
+        .def_readwrite("scale_factor", &sb::target_specification::scale_factor)
+        .def_readwrite("calc_mode", &sb::target_specification::calc_mode)
+        .def_readwrite("catchment_property", &sb::target_specification::catchment_property)
+        .def_readwrite("s_r", &sb::target_specification::s_r)
+        .def_readwrite("s_a", &sb::target_specification::s_a)
+        .def_readwrite("s_b", &sb::target_specification::s_b)
+        .def_readwrite("river_id", &sb::target_specification::river_id)
+        .def_readwrite("uid", &sb::target_specification::uid)
+        .def_readwrite("period_points_us", &sb::target_specification::period_points_us);
+    m.def("calendar_period_points",
+          [](int64_t t0_us, const std::string& unit, size_t n) {
+              const sb::calendar_unit u = unit == "day" ? sb::CAL_DAY : unit == "week" ? sb::CAL_WEEK : unit == "month" ? sb::CAL_MONTH
+                                          : unit == "quarter" ? sb::CAL_QUARTER : unit == "year" ? sb::CAL_YEAR : sb::calendar_unit(-1);
+              if (int(u) < 0) throw std::runtime_error("calendar_period_points: unit must be day, week, month, quarter or year");
+              return sb::calendar_period_points(t0_us, u, n);
+          },
+          py::arg("t0_us"), py::arg("unit"), py::arg("n"),
+          "n + 1 boundaries of n calendar periods from t0 (UTC): a calendar_dt target axis as the point axis period_points_us takes");
+    bind_optimizer<SB2_PT_GS_K>(m, "PTGSKOptimizer");
+    bind_optimizer<SB2_PT_HS_K>(m, "PTHSKOptimizer");
+    bind_optimizer<SB2_HBV_STACK>(m, "HbvOptimizer");
+    m.attr("NASH_SUTCLIFFE") = int(sb::NASH_SUTCLIFFE); m.attr("KLING_GUPTA") = int(sb::KLING_GUPTA); m.attr("ABS_DIFF") = int(sb::ABS_DIFF);
+    m.attr("RMSE") = int(sb::RMSE); m.attr("DISCHARGE") = int(sb::DISCHARGE); m.attr("SNOW_COVERED_AREA") = int(sb::SNOW_COVERED_AREA);
+    m.attr("SNOW_WATER_EQUIVALENT") = int(sb::SNOW_WATER_EQUIVALENT); m.attr("ROUTED_DISCHARGE") = int(sb::ROUTED_DISCHARGE);
+    m.attr("CELL_CHARGE") = int(sb::CELL_CHARGE);
     m.attr("STAT_FORCING") = int(SB2_STAT_FORCING); m.attr("STAT_RESPONSE") = int(SB2_STAT_RESPONSE); m.attr("STAT_STATE") = int(SB2_STAT_STATE);
     m.attr("STAT_SUM") = int(SB2_STAT_SUM); m.attr("STAT_AREA_AVERAGE") = int(SB2_STAT_AREA_AVERAGE);
     m.attr("R_AVG_DISCHARGE") = int(SB2_R_AVG_DISCHARGE); m.attr("R_CHARGE_M3S") = int(SB2_R_CHARGE_M3S);

@@ -71,3 +71,83 @@ def test_reference_fixture_through_the_module_equals_the_ctypes_mirror(cpp):
         a.run_cells(0, 10**6, 1)
     o = cpp.PTGSKOptModel(geo, list(fx["par"]))
     assert o.size() == 20
+
+
+def test_calendar_axes_expand_to_period_points(cpp):
+    """calendar_dt target axes (month / quarter / year steps, core/utctime_utilities.cpp:151-228) spelled as point axes: the C++ shim's
+    calendar arithmetic against numpy's datetime64 months, and against the Python mirror's helper"""
+    import calendar as pycal
+
+    import shyft_b200 as sb
+    t0 = pycal.timegm((2015, 1, 31, 6, 0, 0))            # the 31st: clipped to the month's length on the way
+    pts = cpp.calendar_period_points(t0 * 10**6, "month", 14)
+    want = [pycal.timegm((2015 + (m // 12), m % 12 + 1, min(31, pycal.monthrange(2015 + m // 12, m % 12 + 1)[1]), 6, 0, 0)) for m in range(15)]
+    assert pts == [w * 10**6 for w in want]
+    assert [p // 10**6 for p in pts] == sb.calendar_period_points(t0, "month", 14)
+    y = cpp.calendar_period_points(pycal.timegm((2012, 2, 29, 0, 0, 0)) * 10**6, "year", 4)
+    assert [p // 10**6 for p in y] == [pycal.timegm((2012 + k, 2, 29 if (2012 + k) % 4 == 0 else 28, 0, 0, 0)) for k in range(5)]
+    assert [p // 10**6 for p in y] == sb.calendar_period_points(pycal.timegm((2012, 2, 29, 0, 0, 0)), "year", 4)
+    q = cpp.calendar_period_points(pycal.timegm((1969, 11, 15, 0, 0, 0)) * 10**6, "quarter", 2)   # across the epoch
+    assert [p // 10**6 for p in q] == [pycal.timegm((1969, 11, 15, 0, 0, 0)), pycal.timegm((1970, 2, 15, 0, 0, 0)), pycal.timegm((1970, 5, 15, 0, 0, 0))]
+    assert cpp.calendar_period_points(0, "day", 3) == [0, 86400 * 10**6, 2 * 86400 * 10**6, 3 * 86400 * 10**6]
+    with pytest.raises(RuntimeError, match="unit"):
+        cpp.calendar_period_points(0, "fortnight", 1)
+    for name in ("TargetSpecificationPts", "PTGSKOptimizer", "PTHSKOptimizer", "HbvOptimizer"):
+        assert hasattr(cpp, name), name
+    for method in ("set_target_specification", "set_parameter_ranges", "set_verbose_level", "reset_states", "calculate_goal_function", "optimize",
+                   "optimize_dream", "optimize_sceua", "parameter_active", "trace_goal_function_value", "trace_parameter", "calculate_goal_function_batch"):
+        assert hasattr(cpp.PTGSKOptimizer, method), method   # model_calibrator<RegionModel>, api/boostpython/expose.h:472-731
+
+
+@pytest.mark.gpu
+def test_optimizer_through_the_module(cpp, oracle):
+    """PTGSKOptimizer (api/boostpython/expose.h:472-731): goal function, traces, parameter ranges; a population driver hands every generation
+    to the device in one batch, and the batch equals one-at-a-time evaluation; a monthly calendar axis as target axis"""
+    import shyft_b200 as sb
+    from shyft_b200 import synthetic
+    n, T = 240, 24 * 90
+    geo, ta, env = synthetic.make_region(n, T, 9, config_index=4, cells_per_catchment=80, start=1425168000)   # 2015-03-01
+    envd = {k: getattr(env, k) for k in sb.capi.FORCING_NAMES}
+    m = cpp.PTGSKOptModel(geo, list(PTGSK_DEFAULT))
+    assert m.run_interpolation(ta.start * 10**6, 3600 * 10**6, T, envd)
+    m.set_states(synthetic.default_state(0, n))
+    m.run_cells()
+    q = m.catchment_discharges()                      # [catchment][step]
+    obs_daily = (q[0] + q[1]).reshape(-1, 24).mean(axis=1)
+    t_daily = cpp.TargetSpecificationPts(list(obs_daily), ta.start * 10**6, 86400 * 10**6, [1, 2], 1.0, cpp.NASH_SUTCLIFFE)
+    lo, hi = list(PTGSK_DEFAULT), list(PTGSK_DEFAULT)
+    lo[0], hi[0] = -3.0, -2.0       # kirchner.c1
+    lo[4], hi[4] = -1.5, 1.0        # gs.tx
+    opt = cpp.PTGSKOptimizer(m, [t_daily], lo, hi)
+    assert [i for i in range(31) if opt.parameter_active(i)] == [0, 4]
+    assert opt.calculate_goal_function(list(PTGSK_DEFAULT)) == pytest.approx(0.0, abs=1e-9)      # the twin reproduces itself
+    rng = np.random.default_rng(2)
+    P = np.tile(PTGSK_DEFAULT, (6, 1))
+    P[:, 0] = rng.uniform(-3.0, -2.0, 6)
+    P[:, 4] = rng.uniform(-1.5, 1.0, 6)
+    g_batch = opt.calculate_goal_function_batch(P)
+    g_single = [opt.calculate_goal_function(list(p)) for p in P]
+    assert g_batch == g_single                         # bit-identical: members are grid layers of the same kernels
+    assert opt.trace_size == 1 + 6 + 6 and opt.trace_goal_function_value(1) == g_batch[0] and opt.trace_parameter(1) == list(P[0])
+    # a differential-evolution generation = ONE device batch (8 chains: the initial population + 3 generations = 4 batches, 32 evaluations)
+    start = list(PTGSK_DEFAULT)
+    start[0], start[4] = -2.9, 0.8
+    b0, s0, n0 = opt.n_batch_calls, opt.n_single_calls, opt.trace_size
+    best = opt.optimize_dream(start, 32)
+    assert opt.n_batch_calls - b0 == 4 and opt.n_single_calls == s0 and opt.trace_size - n0 == 32
+    assert opt.calculate_goal_function(best) <= opt.calculate_goal_function(start)
+    best2 = opt.optimize_sceua(start, 60, 1e-4, 1e-7)
+    assert opt.calculate_goal_function(best2) <= opt.calculate_goal_function(start)
+    best3 = opt.optimize(start, 40, 0.1, 1e-4)
+    assert opt.calculate_goal_function(best3) <= opt.calculate_goal_function(start)
+    assert all(lo[i] - 1e-12 <= best3[i] <= hi[i] + 1e-12 for i in range(31))
+    # monthly target periods (a calendar_dt axis) as a point axis: March, April, May 2015 (until the model axis ends)
+    pts = cpp.calendar_period_points(ta.start * 10**6, "month", 3)
+    end_us = (ta.start + T * 3600) * 10**6
+    pts[-1] = min(pts[-1], end_us)
+    hours = [(pts[i] // 10**6 - ta.start) // 3600 for i in range(4)]
+    obs_monthly = [float((q[0] + q[1])[hours[i]:hours[i + 1]].mean()) for i in range(3)]
+    t_monthly = cpp.TargetSpecificationPts(obs_monthly, 0, 0, [1, 2], 1.0, cpp.RMSE, period_points_us=pts)
+    opt.set_target_specification([t_monthly], lo, hi)
+    assert opt.calculate_goal_function(list(PTGSK_DEFAULT)) == pytest.approx(0.0, abs=1e-9)
+    assert opt.calculate_goal_function(start) > 1e-6
