@@ -123,7 +123,7 @@ UNIT_FUNCTIONS = dict(exp=(0, 1, 1), log=(1, 1, 1), pow=(2, 2, 1), lgamma=(3, 1,
                       kirchner_step=(7, 7, 3),
                       # the forms the production kernels use (sb2_unit.cuh)
                       exp_flat=(8, 1, 1), log_flat=(9, 1, 1), pow_flat=(10, 2, 1), calc_snow_state_hot=(11, 7, 2), kirchner_step_warp=(12, 7, 3),
-                      gamma_p_pair=(13, 4, 2), div_by=(14, 2, 2), kirchner_step_warp_udt=(15, 7, 3))
+                      gamma_p_pair=(13, 4, 2), div_by=(14, 2, 2), kirchner_step_warp_udt=(15, 7, 3), corr_lwc_warp=(16, 6, 1))
 
 
 def check_guards():

@@ -2316,7 +2316,7 @@ int sb2_calculate_goal_function_batch(sb2_model* m, int64_t n_sets, const double
 // ---- diagnostics ---------------------------------------------------------------------------------------------------------------
 int sb2_unit_eval(int device, int fn, int64_t n, const double* in, int n_in, double* out, int n_out) {
     try {
-        static const int need_in[UNIT_N] = {1, 1, 2, 1, 2, 5, 7, 7, 1, 1, 2, 7, 7, 4, 2, 7}, need_out[UNIT_N] = {1, 1, 1, 1, 1, 1, 2, 3, 1, 1, 1, 2, 3, 2, 2, 3};
+        static const int need_in[UNIT_N] = {1, 1, 2, 1, 2, 5, 7, 7, 1, 1, 2, 7, 7, 4, 2, 7, 6}, need_out[UNIT_N] = {1, 1, 1, 1, 1, 1, 2, 3, 1, 1, 1, 2, 3, 2, 2, 3, 1};
         if (fn < 0 || fn >= UNIT_N) throw Error("unknown unit function");
         if (n_in < need_in[fn] || n_out < need_out[fn]) throw Error("unit function: too few input or output columns");
         CUDA_OK(cudaSetDevice(device));

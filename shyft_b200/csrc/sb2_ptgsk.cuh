@@ -238,6 +238,133 @@ __device__ __noinline__ double gs_corr_lwc(double z1, double a1, double b1, doub
     return x;
 }
 
+// The same search, warp-cooperative ("lane borrowing").  A Brent search occupies the one to four lanes of a warp whose cell gets fresh
+// snow onto a wet pack, for ~10 objective evaluations of TWO incomplete gammas each, P(a, x) and P(a + 1, x), while the other lanes idle
+// (ncu r01: 17 of 32 lanes live inside gamma_p_with_prefix).  Here all 32 lanes enter together; every lane that needs a search (a
+// "client") is paired with a lane that does not (its "helper"); the client evaluates P(a, x), the helper P(a + 1, x) -- the same function on
+// the same arguments as the client would have called it, so the same bits -- at the same time, and hands the value back by shuffle.
+// lgamma(a) / lgamma(a + 1) and the two incomplete gammas of Q1 are shared the same way.  More than 16 clients in a warp are served in
+// rounds of 16.  The Brent logic is that of gs_corr_lwc, operation for operation (tests/test_gpu_units.py compares both with the oracle,
+// with every client count from 0 to 32).  Every lane of the warp must call; returns corr_lwc for lanes with need, z1 otherwise.
+// MEASURED AND NOT USED by the snow kernel (round 2, profiles/README.md): the search itself halves, but making gs_step_core warp-collective
+// around it (every lane walks every step, one warp vote per step, the step's locals live across the collective call: 292 B of spills
+// instead of 32) cost more than it saved -- step kernels 168.0 -> 184.9 ms per two simulated years.  Kept as a tested device function.
+__device__ __forceinline__ double gs_pair_p(bool working, double a_mine, double lg_mine, double b, double z) {
+    // gamma_p(a_mine, z / b, lg_mine): 0 unless x > 0, 1 at x = inf (sb2_math.cuh)
+    double P = 0.0;
+    if (working) {
+        const double x = z / b;
+        if (x == inf_()) P = 1.0;
+        else if (x > 0.0) P = gamma_p_with_prefix(a_mine, x, sb_exp<true>(a_mine * sb_log<true>(x) - x - lg_mine));
+    }
+    return P;
+}
+__device__ __noinline__ double gs_corr_lwc_warp(bool need, double z1, double a1, double b1, double a2, double b2) {
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt = (1u << lane) - 1u;
+    unsigned pending = __ballot_sync(FULL, need);
+    double result = z1;
+    const double tolerance = 0.00048828125;  // ldexp(1.0, 1 - 12)
+    const double golden = (double)0.3819660f;
+    while (pending != 0u) {
+        // this round's clients: the first 16 pending lanes; helpers: the first n_clients lanes that are not clients of this round
+        const bool mine = (pending >> lane) & 1u;
+        const bool client = mine && __popc(pending & lt) < 16;
+        const unsigned cmask = __ballot_sync(FULL, client);
+        const int n_clients = __popc(cmask);
+        const int h_rank = __popc(~cmask & lt);
+        const bool helper = !client && h_rank < n_clients;
+        const bool working = client || helper;
+        // partner lane: the k-th helper serves the k-th client
+        int partner = int(lane);
+        if (client) partner = int(__fns(~cmask, 0, __popc(cmask & lt) + 1));
+        if (helper) partner = int(__fns(cmask, 0, h_rank + 1));
+        const int src = client ? int(lane) : partner;  // whose problem this lane works on
+        const double pz1 = __shfl_sync(FULL, z1, src), pa1 = __shfl_sync(FULL, a1, src), pb1 = __shfl_sync(FULL, b1, src);
+        const double pa2 = __shfl_sync(FULL, a2, src), pb2 = __shfl_sync(FULL, b2, src);
+        const double add = client ? 0.0 : 1.0;  // the client takes P(a, .), the helper P(a + 1, .)
+        // Q1 = calc_q(a1, b1, z1) = a1 b1 P(a1 + 1, z1 / b1) + z1 (1 - P(a1, z1 / b1))
+        const double a1m = pa1 + add, a2m = pa2 + add;
+        double lg1 = 0.0, lg2 = 0.0;
+        if (working) { lg1 = sb_lgamma<true>(a1m); lg2 = sb_lgamma<true>(a2m); }
+        const double q_mine = gs_pair_p(working, a1m, lg1, pb1, pz1);
+        const double q_other = __shfl_sync(FULL, q_mine, partner);
+        const double Q1 = pa1 * pb1 * q_other + pz1 * (1.0 - q_mine);  // meaningful on clients
+        // Brent: boost brent_find_minima(f, 0, z1, bits = 12, 60 iterations), state on the client
+        double bmin = 0.0, bmax = pz1;
+        double x = bmax, w = bmax, v = bmax, u = 0.0, delta = 0.0, delta2 = 0.0, fv = 0.0, fw = 0.0, fx = 0.0;
+        int count = 60;
+        bool first = true;
+        bool iterating = client;
+        double z_eval = x;
+        while (__any_sync(FULL, iterating)) {
+            const double zz = __shfl_sync(FULL, z_eval, src);
+            const int src_iterating = __shfl_sync(FULL, int(iterating), src);  // every lane shuffles: no short-circuit around a warp-wide shuffle
+            const bool busy = working && src_iterating != 0;
+            const double p_mine = gs_pair_p(busy, a2m, lg2, pb2, zz);
+            const double p_other = __shfl_sync(FULL, p_mine, partner);
+            if (iterating) {
+                const double d = (pa2 * pb2 * p_other + zz * (1.0 - p_mine)) - Q1;
+                const double fval = d * d;
+                if (first) {
+                    fw = fv = fx = fval;
+                    first = false;
+                } else {
+                    const double fu = fval;
+                    if (fu <= fx) {
+                        if (u >= x) bmin = x; else bmax = x;
+                        v = w; w = x; x = u;
+                        fv = fw; fw = fx; fx = fu;
+                    } else {
+                        if (u < x) bmin = u; else bmax = u;
+                        if ((fu <= fw) || (w == x)) {
+                            v = w; w = u; fv = fw; fw = fu;
+                        } else if ((fu <= fv) || (v == x) || (v == w)) {
+                            v = u; fv = fu;
+                        }
+                    }
+                    if (--count == 0) iterating = false;
+                }
+                if (iterating) {
+                    const double mid = (bmin + bmax) / 2;
+                    const double fract1 = tolerance * fabs(x) + tolerance / 4;
+                    const double fract2 = 2 * fract1;
+                    if (fabs(x - mid) <= (fract2 - (bmax - bmin) / 2)) iterating = false;
+                    else {
+                        if (fabs(delta2) > fract1) {
+                            double r = (x - w) * (fx - fv);
+                            double q = (x - v) * (fx - fw);
+                            double pp = (x - v) * q - (x - w) * r;
+                            q = 2 * (q - r);
+                            if (q > 0) pp = -pp;
+                            q = fabs(q);
+                            const double td = delta2;
+                            delta2 = delta;
+                            if ((fabs(pp) >= fabs(q * td / 2)) || (pp <= q * (bmin - x)) || (pp >= q * (bmax - x))) {
+                                delta2 = (x >= mid) ? bmin - x : bmax - x;
+                                delta = golden * delta2;
+                            } else {
+                                delta = pp / q;
+                                u = x + delta;
+                                if (((u - bmin) < fract2) || ((bmax - u) < fract2)) delta = (mid - x) < 0 ? -fabs(fract1) : fabs(fract1);
+                            }
+                        } else {
+                            delta2 = (x >= mid) ? bmin - x : bmax - x;
+                            delta = golden * delta2;
+                        }
+                        u = (fabs(delta) >= fract1) ? (x + delta) : (delta > 0 ? (x + fabs(fract1)) : (x - fabs(fract1)));
+                        z_eval = u;
+                    }
+                }
+            }
+        }
+        if (client) result = x;
+        pending &= ~cmask;
+    }
+    return result;
+}
+
 // calc_snow_state, gamma_snow.h:230-260
 // `lg_key`/`lg_val` memoise lgamma(shape): the shape (alpha) changes on few steps, and equal bits in give equal bits out
 __device__ __forceinline__ void gs_calc_snow_state_impl(double shape, double scale, double y0, double lambda, double lwd, const InvDivisor& inv_mwf,

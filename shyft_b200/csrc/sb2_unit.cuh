@@ -10,7 +10,9 @@ enum { UNIT_EXP = 0, UNIT_LOG, UNIT_POW, UNIT_LGAMMA, UNIT_GAMMA_P, UNIT_CORR_LW
        // the forms the production kernels use: branch-free exp/log/pow, the in-place snow state, the warp-synchronous Kirchner step
        UNIT_EXP_FLAT, UNIT_LOG_FLAT, UNIT_POW_FLAT, UNIT_CALC_SNOW_STATE_HOT, UNIT_KIRCHNER_STEP_WARP, UNIT_GAMMA_P_PAIR,
        // a / d through the reciprocal of a step-invariant divisor (div_by) and as the IEEE division; the Kirchner step with the host-evaluated dt * tableau
-       UNIT_DIV_BY, UNIT_KIRCHNER_STEP_WARP_UDT, UNIT_N };
+       UNIT_DIV_BY, UNIT_KIRCHNER_STEP_WARP_UDT,
+       // corr_lwc searched warp-cooperatively (gs_corr_lwc_warp): in z1 a1 b1 a2 b2 need(0/1) -> z
+       UNIT_CORR_LWC_WARP, UNIT_N };
 
 __constant__ double kUnitDtb[26];  // 1.0 * tableau, uploaded by sb2_unit_eval
 struct UnitDtb { struct { __device__ double operator[](int k) const { return kUnitDtb[k]; } } dtb; };
@@ -70,6 +72,7 @@ __global__ void unit_eval_kernel(int fn, int64_t n, const double* __restrict__ i
             o[0] = q; o[1] = q_avg; o[2] = ok ? 1.0 : 0.0;
             break;
         }
+        case UNIT_CORR_LWC_WARP: o[0] = gs_corr_lwc_warp(in_range && a[5] != 0.0, a[0], a[1], a[2], a[3], a[4]); break;  // fn is launch-uniform: all lanes call
         default: break;
     }
     if (in_range)

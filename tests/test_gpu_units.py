@@ -153,3 +153,26 @@ def test_kirchner_first_try_with_host_evaluated_products_is_bit_identical(capi, 
     want = np.array([oracle.kirchner_step(r[4], r[5], r[6])[:2] for r in rows])
     assert _bits_equal(got[:, :2], want)
     assert _bits_equal(capi.unit_eval("kirchner_step_warp", rows)[:, :2], want)
+
+
+@pytest.mark.timeout(180)
+def test_warp_cooperative_corr_lwc_is_bit_identical(capi, oracle):
+    """gs_corr_lwc_warp (lane borrowing): the lanes of a warp that need a search are paired with lanes that do not, P(a, x) and P(a + 1, x) of
+    every objective evaluation run side by side.  Same bits as the per-lane search and as the oracle, for every client count 0..32 per warp
+    (more than 16 clients are served in rounds)."""
+    rng = np.random.default_rng(29)
+    n = 33 * 32 * 3
+    a1 = rng.uniform(2.0, 6.25, n)
+    b1 = rng.uniform(0.05, 8.0, n)
+    z1 = rng.uniform(0.01, 1.0, n) * a1 * b1 * 2
+    a2 = np.minimum(6.25, a1 * rng.uniform(0.9, 1.2, n))
+    b2 = b1 * rng.uniform(1.0, 1.5, n)
+    need = np.zeros(n)
+    for w in range(n // 32):                     # warp w: (w mod 33) clients at random lanes
+        k = w % 33
+        need[32 * w + rng.permutation(32)[:k]] = 1.0
+    got = capi.unit_eval("corr_lwc_warp", np.stack([z1, a1, b1, a2, b2, need], axis=1))[:, 0]
+    want = np.array([oracle.gs_corr_lwc(z1[i], a1[i], b1[i], 0.0, a2[i], b2[i])[0] if need[i] else z1[i] for i in range(n)])
+    assert _bits_equal(got, want)
+    sel = need == 1.0
+    assert _bits_equal(capi.unit_eval("corr_lwc", np.stack([z1, a1, b1, a2, b2], axis=1)[sel])[:, 0], want[sel])
