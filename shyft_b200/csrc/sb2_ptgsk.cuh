@@ -952,6 +952,12 @@ __device__ __forceinline__ void prefetch_l1(const double* p) { asm volatile("pre
 #ifndef SB2_PREFETCH_AHEAD
 #define SB2_PREFETCH_AHEAD 4
 #endif
+#ifndef SB2_REG_PREFETCH_B
+#define SB2_REG_PREFETCH_B 1   // snow kernel: next step's forcing loaded one step ahead into registers (0: at the point of use, L1 prefetch only)
+#endif
+#ifndef SB2_REG_PREFETCH_C
+#define SB2_REG_PREFETCH_C 1   // response kernel: likewise
+#endif
 
 // ---- the phase pipeline (the production path of run_cells) ----------------------------------------------------------
 // The stack of one step is a chain  forcing -> snow -> response  with no feedback from the Kirchner response into the snow
@@ -1077,9 +1083,12 @@ __global__ void __launch_bounds__(SB2_BLOCK_B, SB2_MINBLOCKS_B) ptgsk_snow_kerne
     const int64_t o0 = (int64_t)i_begin * n + c;
     double f_t = a.f[0][o0], f_p = a.f[1][o0], f_r = a.f[2][o0], f_lw = s_lw[o0], f_ta = s_tadd[o0];
     for (int i = i_begin; i < i_end; ++i) {
-        const double temp = f_t, prec = f_p * p.p_corr_scale_factor, rad = f_r, lw = f_lw, tadd = f_ta;
         const int64_t o = (int64_t)i * n + c;
-        if (i + 1 < i_end) {
+#if !SB2_REG_PREFETCH_B
+        f_t = a.f[0][o]; f_p = a.f[1][o]; f_r = a.f[2][o]; f_lw = s_lw[o]; f_ta = s_tadd[o];
+#endif
+        const double temp = f_t, prec = f_p * p.p_corr_scale_factor, rad = f_r, lw = f_lw, tadd = f_ta;
+        if (SB2_REG_PREFETCH_B && i + 1 < i_end) {
             const int64_t o1 = o + n;
             f_t = a.f[0][o1]; f_p = a.f[1][o1]; f_r = a.f[2][o1]; f_lw = s_lw[o1]; f_ta = s_tadd[o1];
         }
@@ -1237,8 +1246,11 @@ __global__ void __launch_bounds__(SB2_BLOCK_C, SB2_MINBLOCKS_C) ptgsk_response_k
     double f_t = a.f[0][o0], f_p = a.f[1][o0], f_pot = s_pot[o0], f_out = s_outflow[o0], f_sca = s_sca[o0];
     bool failed = false;
     for (int i = i_begin; i < i_end; ++i) {
+#if !SB2_REG_PREFETCH_C
+        { const int64_t oc = (int64_t)i * n + cc; f_t = a.f[0][oc]; f_p = a.f[1][oc]; f_pot = s_pot[oc]; f_out = s_outflow[oc]; f_sca = s_sca[oc]; }
+#endif
         const double temp = f_t, prec = f_p * p_corr, pot = f_pot, outflow = f_out, sca = f_sca;
-        if (i + 1 < i_end) {
+        if (SB2_REG_PREFETCH_C && i + 1 < i_end) {
             const int64_t o1 = (int64_t)(i + 1) * n + cc;
             f_t = a.f[0][o1]; f_p = a.f[1][o1]; f_pot = s_pot[o1]; f_out = s_outflow[o1]; f_sca = s_sca[o1];
         }
