@@ -144,14 +144,22 @@ def oracle_pass(O, gm, ta, env, window, cores, n_steps=None):
         t0_us = (ta.start + w0 * ta.delta_t) * 10**6
         a = time.perf_counter()
         f = {}
-        for name in FORCING:
+
+        def one(name):
             xyz, vals = getattr(env, name)
             vals = O.average_accessor_same_axis(vals[w0:w0 + wn], dt_us)
-            if name == "temperature":
+            if name == "temperature":   # btk_interpolation: one thread (core/bayesian_kriging.h:280-402 has no threading of its own)
                 f[name] = O.btk_run(xyz, vals, gm[:, :3], t0_us, dt_us)
-            else:
+            else:                       # idw::run_interpolation splits the cells over ncore threads (core/inverse_distance.h:503-560)
                 f[name] = O.idw_run(name, xyz, vals, gm[:, :3], O.idw_par(max_members=20 if name == "precipitation" else 10), dst_slope=gm[:, 5],
                                     ncore=cores)
+        # the five variables are interpolated by five concurrent tasks, as region_model::interpolate launches them (core/region_model.h:456-523);
+        # the oracle's C functions release the GIL
+        tasks = [threading.Thread(target=one, args=(name,)) for name in FORCING]
+        for t in tasks:
+            t.start()
+        for t in tasks:
+            t.join()
         b = time.perf_counter()
         st = O.ptgsk_run_cells(gm, PTGSK_DEFAULT, f, st, t0_us, dt_us, collect_response=False, ncore=cores)["state"]
         c = time.perf_counter()
