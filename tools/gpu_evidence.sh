@@ -14,7 +14,7 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:ptgs
    python bench.py --years 1 --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/${TAG}_ncu_pipeline.log 2>&1; echo "ncu pipeline rc $?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:dense_apply --launch-skip 10 --launch-count 5 -f -o gpurun_out/${TAG}_dense_apply \
    python bench.py --years 1 --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/${TAG}_ncu_dense.log 2>&1; echo "ncu dense rc $?"
-SB2_C3_YEARS=0.06 SB2_C3_WINDOW=256 timeout 900 ncu --set full --clock-control none --import-source on -k regex:hbv_run_kernel --launch-skip 2 --launch-count 1 -f \
+SB2_C3_YEARS=0.06 SB2_C3_WINDOW=256 timeout 900 ncu --set full --clock-control none --import-source on -k regex:hbv_run_kernel --launch-skip 7 --launch-count 4 -f \
    -o gpurun_out/${TAG}_hbv python tools/bench_configs.py 3 > gpurun_out/${TAG}_ncu_hbv.log 2>&1; echo "ncu hbv rc $?"
 SB2_C3_YEARS=1 timeout 900 python tools/bench_configs.py 3 > gpurun_out/${TAG}_bench_configs_c3.jsonl 2> gpurun_out/${TAG}_bench_configs_c3.err; echo "c3 rc $?"; cat gpurun_out/${TAG}_bench_configs_c3.jsonl
 SB2_C5_SETS=128 timeout 900 python tools/bench_configs.py 5 > gpurun_out/${TAG}_bench_configs_c5.jsonl 2> gpurun_out/${TAG}_bench_configs_c5.err; echo "c5 rc $?"; cat gpurun_out/${TAG}_bench_configs_c5.jsonl
