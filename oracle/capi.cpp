@@ -9,6 +9,7 @@
 #include "sho_detmath.hpp"
 #include "sho_core.hpp"
 #include "sho_hbv.hpp"
+#include "sho_skaugen.hpp"
 #include "sho_pt_gs_k.hpp"
 #include "sho_region.hpp"
 #include "sho_ts.hpp"
@@ -201,6 +202,43 @@ int sho_hbv_stack_run_cells(int64_t n_cells, const double* geo, int64_t n_sets, 
         s.pack(state + ci * n_state, size_t(n_state));
     });
     SHO_END
+}
+// pt_ss_k region run: state [n_cells][8] = snow.nu, alpha, sca, swe, free_water, residual, num_units, kirchner.q; sts = SS_N nullable
+// state series ([n_axis + 1][cells]), resp = HR_N nullable response series
+int sho_ptssk_run_cells(int64_t n_cells, const double* geo, int64_t n_sets, const double* params, int n_param, const int32_t* pset_of_cell,
+                        int64_t t0_us, int64_t dt_us, int64_t n_axis, int start_step, int n_steps, const double* f_temp, const double* f_prec,
+                        const double* f_rad, const double* f_wind, const double* f_rh, int64_t f_tstride, int64_t f_cstride, double* state,
+                        double** resp, double** sts, int64_t o_tstride, int64_t o_cstride, int ncore) {
+    SHO_TRY
+    auto cells = make_cells(n_cells, geo);
+    std::vector<pt_ss_k::parameter> ps(n_sets);
+    for (int64_t k = 0; k < n_sets; ++k) ps[k].set(params + k * n_param, size_t(n_param));
+    fixed_dt ta{t0_us, dt_us, size_t(n_axis)};
+    parallel_run(size_t(n_cells), ncore, [&](size_t ci) {
+        const auto& p = ps[pset_of_cell ? pset_of_cell[ci] : 0];
+        pt_ss_k::state s;
+        s.unpack(state + ci * 8);
+        pt_ss_k::cell_forcing f{f_temp + ci * f_cstride, f_prec + ci * f_cstride, f_wind + ci * f_cstride, f_rh + ci * f_cstride,
+                                f_rad + ci * f_cstride, f_tstride};
+        pt_ss_k::run(cells[ci], p, ta, start_step, n_steps, f, s, resp, sts, o_tstride, o_cstride, ci);
+        s.pack(state + ci * 8);
+    });
+    SHO_END
+}
+// skaugen::calculator::step (core/skaugen.h:150-339): par8 = alpha_0 d_range unit_size max_water_fraction tx cx ts cfr;
+// state7 = nu alpha sca swe free_water residual num_units (in place); out3 = outflow sca swe
+int sho_skaugen_step(const double* par8, double* state7, int64_t dt_us, double temp, double prec, double* out3) {
+    SHO_TRY
+    skaugen::parameter p{par8[0], par8[1], par8[2], par8[3], par8[4], par8[5], par8[6], par8[7]};
+    skaugen::state s{state7[0], state7[1], state7[2], state7[3], state7[4], state7[5], (unsigned long)state7[6]};
+    skaugen::response r;
+    skaugen::step(dt_us, p, temp, prec, s, r);
+    state7[0] = s.nu; state7[1] = s.alpha; state7[2] = s.sca; state7[3] = s.swe; state7[4] = s.free_water; state7[5] = s.residual; state7[6] = double(s.num_units);
+    out3[0] = r.outflow; out3[1] = r.sca; out3[2] = r.swe;
+    SHO_END
+}
+double sho_skaugen_sca_rel_red(double u, double n, double unit_size, double nu_a, double alpha) {
+    try { return skaugen::statistics::sca_rel_red((unsigned long)u, (unsigned long)n, unit_size, nu_a, alpha); } catch (...) { return std::nan(""); }
 }
 // hbv unit steps for known-answer tests
 int sho_hbv_snow_step(const double* s_q /*n*/, const double* intervals /*n*/, int n, const double* par5 /*tx cx ts lw cfr*/, double* sp, double* sw,

@@ -36,7 +36,7 @@ def geo_matrix(geo_records):
 
 def build(force=False):
     so = os.path.join(_HERE, "libsho_oracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("capi.cpp", "sho_detmath.hpp", "sho_math_tables.inc", "sho_core.hpp", "sho_pt_gs_k.hpp", "sho_hbv.hpp", "sho_region.hpp", "sho_ts.hpp")]
+    srcs = [os.path.join(_HERE, f) for f in ("capi.cpp", "sho_detmath.hpp", "sho_math_tables.inc", "sho_core.hpp", "sho_pt_gs_k.hpp", "sho_hbv.hpp", "sho_skaugen.hpp", "sho_region.hpp", "sho_ts.hpp")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "libsho_oracle.so"], stdout=subprocess.DEVNULL)
     return so
@@ -53,7 +53,7 @@ def lib():
         for name in ("sho_gamma_p", "sho_gamma_quantile", "sho_pt_potential_evapotranspiration", "sho_ae_calculate_step",
                      "sho_glacier_melt_step", "sho_gs_corr_lwc", "sho_gs_calc_q", "sho_hbv_soil_step", "sho_hbv_tank_step",
                      "sho_hbv_ae_step", "sho_btk_prior_gradient", "sho_nash_sutcliffe", "sho_rmse", "sho_kling_gupta", "sho_abs_diff_sum",
-                     "sho_average_value"):
+                     "sho_average_value", "sho_skaugen_sca_rel_red"):
             getattr(L, name).restype = C.c_double
     return _LIB
 
@@ -245,6 +245,46 @@ def pthsk_run_cells(geo, params, forcing, state, t0_us, dt_us, start_step=0, n_s
 def hbv_stack_run_cells(geo, params, forcing, state, t0_us, dt_us, start_step=0, n_steps=0, pset_of_cell=None, ncore=1):
     """state [n][5+2*nb] = swe, sca, sp[nb], sw[nb], soil.sm, tank.uz, tank.lz"""
     return _hs_run(lib().sho_hbv_stack_run_cells, 22, geo, params, forcing, state, t0_us, dt_us, start_step, n_steps, pset_of_cell, ncore)
+
+
+PTSSK_STATES = ("kirchner_discharge", "snow_swe", "snow_sca", "snow_alpha", "snow_nu", "snow_lwc", "snow_residual")
+SKAUGEN_DEFAULT = (40.77, 113.0, 0.1, 0.1, 0.16, 2.5, 0.14, 0.01)   # alpha_0 d_range unit_size max_water_fraction tx cx ts cfr (skaugen.h:92-99)
+
+
+def ptssk_run_cells(geo, params, forcing, state, t0_us, dt_us, start_step=0, n_steps=0, pset_of_cell=None, collect_state=False, ncore=1):
+    """Reference-equivalent pt_ss_k run_cells (core/pt_ss_k.h:195-293).  state [n][8] = snow.nu, alpha, sca, swe, free_water, residual,
+    num_units, kirchner.q.  -> dict(state, <response series [T][n]>, <state series [T+1][n]> when collect_state)"""
+    geo = _f64(geo)
+    n = geo.shape[0]
+    params = _f64(params).reshape(-1, 21)
+    f = [_f64(forcing[k]) for k in ("temperature", "precipitation", "radiation", "wind_speed", "rel_hum")]
+    T = f[0].shape[0]
+    st = _f64(state).reshape(n, 8).copy()
+    resp = [np.full((T, n), np.nan) for _ in HS_RESPONSES]
+    sts = [np.full((T + 1, n), np.nan) if collect_state else None for _ in PTSSK_STATES]
+    ps = np.ascontiguousarray(pset_of_cell, dtype=np.int32) if pset_of_cell is not None else None
+    _check(lib().sho_ptssk_run_cells(C.c_int64(n), _d(geo), C.c_int64(params.shape[0]), _d(params), C.c_int(21), ps.ctypes.data_as(c_i32p) if ps is not None else None,
+                                     C.c_int64(t0_us), C.c_int64(dt_us), C.c_int64(T), C.c_int(start_step), C.c_int(n_steps),
+                                     _d(f[0]), _d(f[1]), _d(f[2]), _d(f[3]), _d(f[4]), C.c_int64(n), C.c_int64(1), _d(st),
+                                     _ptrs(resp), _ptrs(sts) if collect_state else None, C.c_int64(n), C.c_int64(1), C.c_int(ncore)))
+    out = dict(zip(HS_RESPONSES, resp))
+    out.pop("soil_outflow")
+    out["state"] = st
+    if collect_state:   # state series share names with response series (snow_swe, snow_sca): keyed "state_<name>"
+        out.update({"state_" + k: v for k, v in zip(PTSSK_STATES, sts)})
+    return out
+
+
+def skaugen_step(state7, temp, prec, dt_us=3600 * 10**6, par=SKAUGEN_DEFAULT):
+    """skaugen::calculator::step -> (new state [nu, alpha, sca, swe, free_water, residual, num_units], (outflow, sca, swe))"""
+    s = _f64(state7).copy()
+    out = np.zeros(3)
+    _check(lib().sho_skaugen_step(_d(_f64(par)), _d(s), C.c_int64(dt_us), C.c_double(temp), C.c_double(prec), _d(out)))
+    return s, out
+
+
+def skaugen_sca_rel_red(u, n, nu_a, alpha, unit_size=0.1):
+    return float(lib().sho_skaugen_sca_rel_red(C.c_double(u), C.c_double(n), C.c_double(unit_size), C.c_double(nu_a), C.c_double(alpha)))
 
 
 def hbv_snow_step(sp, sw, swe, sca, prec, temp, dt_us=3600 * 10**6, s=None, intervals=None, tx=0.0, cx=1.0, ts=0.0, lw=0.1, cfr=0.5):

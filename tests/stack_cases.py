@@ -1,4 +1,4 @@
-"""The reference's stack-level known-answer cases (test/pt_gs_k_test.cpp:174-354, test/pt_hs_k_test.cpp:93-153), restated once and
+"""The reference's stack-level known-answer cases (test/pt_gs_k_test.cpp:174-354, test/pt_hs_k_test.cpp:93-153, test/pt_ss_k_test.cpp:118-168), restated once and
 driven through a `run(stack, geo [1][12], params, forcing dict of [T][1], state [1][k], t0_us, T) -> dict` callable, so that the
 CPU oracle (tests/test_oracle_stack_known_answers.py) and the CUDA path through the C ABI (tests/test_gpu_stack_known_answers.py)
 are held to the same asserts."""
@@ -7,7 +7,7 @@ import calendar as pycal
 import numpy as np
 import pytest
 
-from fixtures import PTGSK_DEFAULT, PTHSK_DEFAULT
+from fixtures import PTGSK_DEFAULT, PTHSK_DEFAULT, PTSSK_DEFAULT
 
 T0 = pycal.timegm((2014, 8, 1, 0, 0, 0)) * 10**6
 AREA = 1000.0 * 1000.0
@@ -145,3 +145,27 @@ def pthsk_lake_reservoir_response(run):
         assert out["state_snow_swe"][1, 0] == pytest.approx(0.0, abs=1e-4)
         assert out["state_snow_swe"][2, 0] == approx(1.5, 1e-4)
     assert out["avg_discharge"][n - 1, 0] == approx(0.2 * 3.0 * MMH_TO_M3S * (1.0 - 0.3) + 0.3 * 3.0 * MMH_TO_M3S, 0.01)
+
+
+def ptssk_lake_reservoir_response(run):
+    """pt_ss_k_lake_reservoir_response (test/pt_ss_k_test.cpp:118-168): the same story with the Skaugen routine; the state collector's
+    snow_swe (instant, over the cell) is 0 / 0 / 1.5 / 3.0 at the first four points"""
+    n = 50
+    geo = geo_cell(lake=0.2, reservoir=0.3)
+    f = forcing(n, -15.0, 3.0, first_prec=0.0)
+    st = np.array([[4.077, 40.77, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0]])   # skaugen::state() + kirchner q = 1
+    par = PTSSK_DEFAULT.copy()
+    par[20] = 0.0
+    out = run(3, geo, par, f, st, T0, n)
+    assert out["avg_discharge"][0, 0] == approx(0.266, 0.01)
+    assert out["avg_discharge"][n - 1, 0] == approx(0.5 * 3.0 * MMH_TO_M3S, 0.01)
+    par[20] = 1.0
+    out = run(3, geo, par, f, st, T0, n)
+    assert out["avg_discharge"][0, 0] == approx(0.266 * 0.7, 0.01)
+    assert out["avg_discharge"][1, 0] == approx(0.266 + 0.3 * 0.5 * 3.0 * MMH_TO_M3S, 0.05)
+    assert out["state_snow_swe"][0, 0] == approx(0.0, 0.001)
+    assert out["state_snow_swe"][1, 0] == approx(0.0, 0.001)
+    assert out["state_snow_swe"][2, 0] == approx(1.5, 0.001)
+    assert out["state_snow_swe"][3, 0] == approx(3.0, 0.001)
+    assert out["avg_discharge"][n - 1, 0] == approx(0.2 * 3.0 * MMH_TO_M3S * (1.0 - 0.3) + 0.3 * 3.0 * MMH_TO_M3S, 0.01)
+    assert np.all(np.isfinite(out["snow_swe"])) and np.all(out["snow_swe"] >= 0.0)   # test_call_stack's assert

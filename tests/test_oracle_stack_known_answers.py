@@ -10,6 +10,8 @@ import stack_cases as sc
 @pytest.fixture(scope="module")
 def run(oracle):
     def f(stack, geo, par, forcing, state, t0_us, T):
+        if stack == 3:
+            return oracle.ptssk_run_cells(geo, par, forcing, state, t0_us, 3600 * 10**6, collect_state=True)
         fn = oracle.ptgsk_run_cells if stack == 0 else oracle.pthsk_run_cells
         return fn(geo, par, forcing, state, t0_us, 3600 * 10**6)
     return f
@@ -27,6 +29,49 @@ def test_pt_gs_k_lake_reservoir_response(run):
 
 def test_pt_hs_k_lake_reservoir_response(run):
     sc.pthsk_lake_reservoir_response(run)
+
+
+def test_pt_ss_k_lake_reservoir_response(run):
+    sc.ptssk_lake_reservoir_response(run)
+
+
+def test_skaugen_known_answers(oracle):
+    """test/skaugen_test.cpp:9-281: accumulation, melt with mass balance, liquid water, the melt-down regression"""
+    alpha_0, unit = 40.77, 0.1
+    s0 = np.array([alpha_0 * unit, alpha_0, 0.0, 0.0, 0.0, 0.0, 0.0])
+    s = s0.copy()
+    for _ in range(10):                                   # test_accumulation: ten hours of 10 mm/h at -10 degC
+        s, r = oracle.skaugen_step(s, -10.0, 10.0)
+    assert s[3] * s[2] == pytest.approx(100.0, abs=1e-6) and s[2] == pytest.approx(1.0, abs=1e-6) and s[0] < alpha_0 * unit
+    day = 24 * 3600 * 10**6
+    s = s0.copy()
+    for _ in range(10):                                   # test_melt: ten days of 10 mm/day, then +10 degC
+        s, r = oracle.skaugen_step(s, -10.0, 10.0 / 24.0, dt_us=day)
+    total_water = s[3] * s[2]
+    s, r = oracle.skaugen_step(s, 10.0, 0.0, dt_us=day)
+    agg = r[0] * 24.0
+    assert s[2] * (s[3] + s[4]) < total_water
+    assert r[0] * 24.0 + s[4] >= 1.0
+    assert r[0] * 24.0 + s[2] * (s[4] + s[3]) == pytest.approx(total_water, abs=1e-6)
+    for _ in range(100):
+        s, r = oracle.skaugen_step(s, 10.0, 0.0, dt_us=day)
+        agg += r[0] * 24.0
+    assert s[2] == pytest.approx(0.0, abs=1e-6) and s[3] == pytest.approx(0.0, abs=1e-6)
+    assert agg == pytest.approx(total_water, abs=1e-10)
+    assert s[1] == pytest.approx(alpha_0, abs=1e-6) and s[0] == pytest.approx(alpha_0 * unit, abs=1e-6)
+    s = s0.copy()
+    for _ in range(10):                                   # test_lwc
+        s, r = oracle.skaugen_step(s, -10.0, 10.0 / 24.0, dt_us=day)
+    assert s[4] == pytest.approx(0.0, abs=1e-6)
+    s, r = oracle.skaugen_step(s, 10.0, 0.0, dt_us=day)
+    assert s[4] <= s[3] * 0.1
+    for _ in range(5):
+        s, r = oracle.skaugen_step(s, 2.0, 0.0, dt_us=day)
+    assert s[4] == pytest.approx(s[3] * 0.1, abs=1e-6)
+    # skaugen_meltdown: the state of 2017-07-17T22:00 must step without throwing
+    s = np.array([0.012785227731289801, 0.127852277312898, 0.005033599471562574, 32.1, 3.21, 0.0, 321.0])
+    s, r = oracle.skaugen_step(s, 4.891358376624782, 0.0010356738461072955, dt_us=3 * 3600 * 10**6)
+    assert s[3] == 0.0 and s[2] == 0.0 and np.isfinite(r[0])
 
 
 @pytest.mark.parametrize("s,sca_after", [([1.0, 1.0, 1.0, 0.0, 0.0], 0.75), ([1.0, 1.0, 1.0, 1.0, 1.0], 1.0), ([1.0, 0.0, 0.0, 0.0, 0.0], 0.25)])
