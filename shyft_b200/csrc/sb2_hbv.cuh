@@ -65,6 +65,7 @@ inline HbvParam make_hbv_param(bool hbv_stack, const double* v) {
 // default-constructed cell state per stack, flat ABI order
 inline std::vector<double> default_state(int stack) {
     if (stack == 0) return {0.4, 0.1, 30000.0, 1.26, 0.0, 0.0, 0.0, 0.0, 0.1};  // gamma_snow::state (gamma_snow.h:101-116) + kirchner.q (kirchner.h:124-126)
+    if (stack == 3) return {4.077, 40.77, 0.0, 0.0, 0.0, 0.0, 0.0, 0.1};         // skaugen::state (skaugen.h:121-124) + kirchner.q
     std::vector<double> s(stack == 1 ? 3 + 2 * HBV_NB : 5 + 2 * HBV_NB, 0.0);   // swe, sca, sp[], sw[] = 0
     if (stack == 1) s[2 + 2 * HBV_NB] = 0.1;                                     // kirchner.q
     else { s[2 + 2 * HBV_NB] = 0.0; s[3 + 2 * HBV_NB] = 20.0; s[4 + 2 * HBV_NB] = 10.0; }  // soil.sm = 0 (hbv_soil.h:28), tank uz/lz (hbv_tank.h:32)

@@ -2,7 +2,7 @@
 // (deterministic math, incomplete gamma, Brent's lwc correction, snow state, one Kirchner step) with the oracle, the way
 // the reference unit-tests its methods (test/gamma_snow_test.cpp, test/kirchner_test.cpp).
 #pragma once
-#include "sb2_ptgsk.cuh"
+#include "sb2_ptssk.cuh"
 
 namespace sb2 {
 
@@ -12,7 +12,10 @@ enum { UNIT_EXP = 0, UNIT_LOG, UNIT_POW, UNIT_LGAMMA, UNIT_GAMMA_P, UNIT_CORR_LW
        // a / d through the reciprocal of a step-invariant divisor (div_by) and as the IEEE division; the Kirchner step with the host-evaluated dt * tableau
        UNIT_DIV_BY, UNIT_KIRCHNER_STEP_WARP_UDT,
        // corr_lwc searched warp-cooperatively (gs_corr_lwc_warp): in z1 a1 b1 a2 b2 need(0/1) -> z
-       UNIT_CORR_LWC_WARP, UNIT_N };
+       UNIT_CORR_LWC_WARP,
+       // skaugen::calculator::step: in par8 (alpha_0 d_range unit_size max_water_fraction tx cx ts cfr), state7, dt_hours, temp, prec -> state7, outflow, sca, swe, bad
+       // skaugen::statistics::sca_rel_red: in u n nu_a alpha -> value, bad
+       UNIT_SKAUGEN_STEP, UNIT_SCA_REL_RED, UNIT_N };
 
 __constant__ double kUnitDtb[26];  // 1.0 * tableau, uploaded by sb2_unit_eval
 struct UnitDtb { struct { __device__ double operator[](int k) const { return kUnitDtb[k]; } } dtb; };
@@ -23,7 +26,7 @@ __global__ void unit_eval_kernel(int fn, int64_t n, const double* __restrict__ i
     const bool in_range = i0 < n;
     const int64_t i = in_range ? i0 : n - 1;  // lanes past the end shadow the last element (warp-synchronous functions need all 32 lanes)
     const double* a = in + i * n_in;
-    double ob[4] = {0.0, 0.0, 0.0, 0.0};
+    double ob[12] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     double* o = ob;
     switch (fn) {
         case UNIT_EXP: o[0] = sb_exp(a[0]); break;
@@ -73,10 +76,27 @@ __global__ void unit_eval_kernel(int fn, int64_t n, const double* __restrict__ i
             break;
         }
         case UNIT_CORR_LWC_WARP: o[0] = gs_corr_lwc_warp(in_range && a[5] != 0.0, a[0], a[1], a[2], a[3], a[4]); break;  // fn is launch-uniform: all lanes call
+        case UNIT_SKAUGEN_STEP: {
+            SskParam p{};
+            p.alpha_0 = a[0]; p.d_range = a[1]; p.unit_size = a[2]; p.max_water_fraction = a[3]; p.tx = a[4]; p.cx = a[5]; p.ts = a[6]; p.cfr = a[7];
+            SsState s{a[8], a[9], a[10], a[11], a[12], a[13], (unsigned long long)a[14]};
+            const double dt_hours = a[15];
+            bool bad = false;
+            ss_step(p, dt_hours, dt_hours * 3600.0 / 86400.0, make_inv_divisor(dt_hours), a[16], a[17], s, o[7], o[8], o[9], bad);
+            o[0] = s.nu; o[1] = s.alpha; o[2] = s.sca; o[3] = s.swe; o[4] = s.free_water; o[5] = s.residual; o[6] = double(s.num_units);
+            o[10] = bad ? 1.0 : 0.0;
+            break;
+        }
+        case UNIT_SCA_REL_RED: {
+            bool bad = false;
+            o[0] = ss_sca_rel_red((unsigned long long)a[0], (unsigned long long)a[1], a[2], a[3], bad);
+            o[1] = bad ? 1.0 : 0.0;
+            break;
+        }
         default: break;
     }
     if (in_range)
-        for (int k = 0; k < n_out && k < 4; ++k) out[i * n_out + k] = ob[k];
+        for (int k = 0; k < n_out && k < 12; ++k) out[i * n_out + k] = ob[k];
 }
 
 }  // namespace sb2

@@ -77,6 +77,8 @@ def default_state(stack, n_cells, q0=0.8):
     """state_t{} defaults with kirchner.q = q0 mm/h."""
     if stack == 0:
         s = np.tile(np.array([0.4, 0.1, 30000.0, 1.26, 0.0, 0.0, 0.0, 0.0, q0]), (n_cells, 1))
+    elif stack == 3:
+        s = np.tile(np.array([4.077, 40.77, 0.0, 0.0, 0.0, 0.0, 0.0, q0]), (n_cells, 1))   # skaugen::state() + kirchner.q
     elif stack == 1:
         s = np.zeros((n_cells, 13))
         s[:, 12] = q0
