@@ -67,7 +67,6 @@ def test_skaugen_step_sequences_are_bit_identical(sb, oracle):
                 assert _bits_equal(got[c, :7], s1) and _bits_equal(got[c, 7:10], r), (i, c, got[c], s1, r)
             st_o[c] = s1
         st = got[:, :7].copy()
-    assert st_o[:, 3].max() == 0.0 or True
     assert bad_seen < n_cells * n_steps * 0.01
 
 
@@ -148,6 +147,7 @@ def test_pt_ss_k_through_the_pybind_module_and_statistics(sb):
     b = sb.PTSSKModel(geo, PTSSK_DEFAULT)
     b.run_interpolation(sb.InterpolationParameter(), ta, env)
     b.set_states(synthetic.default_state(3, n))
+    b.set_state_collection(-1, True)
     b.run_cells()
     assert np.array_equal(a.catchment_discharges()[0], b.catchment_discharges()[:, 0])
     assert np.array_equal(b.statistics.discharge([1]), b.response("avg_discharge")[:, :32].sum(axis=1)) or \
