@@ -19,7 +19,7 @@ import pytest
 
 from e2e_cases import oracle_forcing, region_slice, run_device_windows
 from e2e_census import Census
-from fixtures import HBV_DEFAULT, PTGSK_DEFAULT, PTHSK_DEFAULT, geo_matrix
+from fixtures import HBV_DEFAULT, PTGSK_DEFAULT, PTHSK_DEFAULT, PTSSK_DEFAULT, geo_matrix
 from parity import assert_parity
 
 pytestmark = pytest.mark.gpu
@@ -86,15 +86,16 @@ def test_config2_slice_pt_gs_k_windowed_dense_interpolation_census(sb, oracle):
     assert np.array_equal(m.catchment_discharges(), cq_chunked)
 
 
-@pytest.mark.parametrize("stack", ["pt_hs_k", "hbv_stack"])
+@pytest.mark.parametrize("stack", ["pt_hs_k", "hbv_stack", "pt_ss_k"])
 def test_config3_slice_hbv_windowed_with_routing_census(sb, oracle, stack):
     """BASELINE configs[2] shape: 1 024 cells cut out of the 400 000-cell grid x 1 year from November, river network routing."""
     from shyft_b200 import synthetic
     T, W = 8760, 1024
     geo, ta, env = region_slice(400000, T, 64, 64, config_index=2, with_routing=True, start=1414800000)
     n = geo.shape[0]
-    cls, par, sid, run = ((sb.PTHSKModel, PTHSK_DEFAULT, 1, oracle.pthsk_run_cells) if stack == "pt_hs_k"
-                          else (sb.HbvStackModel, HBV_DEFAULT, 2, oracle.hbv_stack_run_cells))
+    cls, par, sid, run = {"pt_hs_k": (sb.PTHSKModel, PTHSK_DEFAULT, 1, oracle.pthsk_run_cells),
+                          "hbv_stack": (sb.HbvStackModel, HBV_DEFAULT, 2, oracle.hbv_stack_run_cells),
+                          "pt_ss_k": (sb.PTSSKModel, PTSSK_DEFAULT, 3, oracle.ptssk_run_cells)}[stack]
     st0 = synthetic.default_state(sid, n)
     gm, f = oracle_forcing(oracle, geo, ta, env, btk_temperature=True)
     want = run(gm, par, f, st0, ta.start * 10**6, ta.delta_t * 10**6, ncore=16)
@@ -110,7 +111,7 @@ def test_config3_slice_hbv_windowed_with_routing_census(sb, oracle, stack):
     def on_window(w0, got, fg):
         q_dev[w0:w0 + got["avg_discharge"].shape[0]] = got["avg_discharge"]
         cs.add_window(w0, got, fg)
-    if stack == "pt_hs_k":
+    if stack != "hbv_stack":
         want.pop("soil_outflow", None)   # hbv_stack only
     run_device_windows(m, ip, T, W, [k for k in want if want[k].shape == (T, n)], (), on_window)
     c = cs.result()
@@ -132,7 +133,7 @@ def test_config3_slice_hbv_windowed_with_routing_census(sb, oracle, stack):
     m.set_river_network(rivers)
     m.revert_to_initial_state()
     m.run_windowed(ip, window_steps=W)
-    uhg = np.tile(par[13:16] if stack == "pt_hs_k" else par[17:20], (n, 1))
+    uhg = np.tile({"pt_hs_k": par[13:16], "hbv_stack": par[17:20], "pt_ss_k": par[16:19]}[stack], (n, 1))
     for rid in (cids[0], cids[3], cids[-1]):
         local, up, out = oracle.river_flows(rivers, int(rid), q_dev, gm[:, 10].astype(np.int64), gm[:, 11], uhg, ta.delta_t * 10**6)
         assert_parity(m.river_local_inflow_m3s(int(rid)), local, f"river {rid} local inflow", rtol=1e-9)
