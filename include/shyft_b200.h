@@ -21,8 +21,8 @@ extern "C" {
 
 typedef struct sb2_model sb2_model;
 
-/* method stacks (core/pt_gs_k.h, core/pt_hs_k.h, core/hbv_stack.h, core/pt_ss_k.h) */
-enum { SB2_PT_GS_K = 0, SB2_PT_HS_K = 1, SB2_HBV_STACK = 2, SB2_PT_SS_K = 3 };
+/* method stacks (core/pt_gs_k.h, core/pt_hs_k.h, core/hbv_stack.h, core/pt_ss_k.h, core/pt_hps_k.h) */
+enum { SB2_PT_GS_K = 0, SB2_PT_HS_K = 1, SB2_HBV_STACK = 2, SB2_PT_SS_K = 3, SB2_PT_HPS_K = 4 };
 /* forcing variables, the members of cell.env_ts (core/cell_model.h:47-56) */
 enum { SB2_TEMPERATURE = 0, SB2_PRECIPITATION = 1, SB2_RADIATION = 2, SB2_WIND_SPEED = 3, SB2_REL_HUM = 4, SB2_N_FORCING = 5 };
 /* host array layouts for [time x cell] data */
@@ -44,10 +44,13 @@ enum { SB2_R_AVG_DISCHARGE = 0, SB2_R_CHARGE_M3S, SB2_R_SNOW_SCA, SB2_R_SNOW_SWE
  * hbv_stack: 0 snow_swe, 1 snow_sca, 2 soil_moisture, 3 tank_uz, 4 tank_lz, 5..9 sp[0..4], 10..14 sw[0..4]
  * (core/hbv_stack_cell_model.h:148-213); sp / sw = the snow pack and its liquid water per quantile bin (five bins);
  * pt_ss_k: 0 kirchner_discharge, 1 snow_swe, 2 snow_sca, 3 snow_alpha, 4 snow_nu, 5 snow_lwc, 6 snow_residual
- * (core/pt_ss_k_cell_model.h:148-199). */
+ * (core/pt_ss_k_cell_model.h:148-199);
+ * pt_hps_k: 0 kirchner_discharge, 1 snow_sca, 2 snow_swe, 3 surface_heat, 4..8 sp[0..4], 9..13 sw[0..4], 14..18 albedo[0..4],
+ * 19..23 iso_pot_energy[0..4] (core/pt_hps_k_cell_model.h:150-230). */
 enum { SB2_S_KIRCHNER_DISCHARGE = 0, SB2_S_GS_ALBEDO, SB2_S_GS_LWC, SB2_S_GS_SURFACE_HEAT, SB2_S_GS_ALPHA, SB2_S_GS_SDC_MELT_MEAN,
-       SB2_S_GS_ACC_MELT, SB2_S_GS_ISO_POT_ENERGY, SB2_S_GS_TEMP_SWE, SB2_N_STATE_SERIES = 15 };
-enum { SB2_S_PTHSK_SP0 = 3, SB2_S_PTHSK_SW0 = 8, SB2_S_HBV_SP0 = 5, SB2_S_HBV_SW0 = 10 };
+       SB2_S_GS_ACC_MELT, SB2_S_GS_ISO_POT_ENERGY, SB2_S_GS_TEMP_SWE, SB2_N_STATE_SERIES = 24 };
+enum { SB2_S_PTHSK_SP0 = 3, SB2_S_PTHSK_SW0 = 8, SB2_S_HBV_SP0 = 5, SB2_S_HBV_SW0 = 10, SB2_S_PTHPSK_SP0 = 4, SB2_S_PTHPSK_SW0 = 9,
+       SB2_S_PTHPSK_ALBEDO0 = 14, SB2_S_PTHPSK_ISO0 = 19 };
 
 /* geo_cell_data (core/geo_cell_data.h:107-138) flattened; one per cell, in the caller's cell order */
 typedef struct sb2_geo_cell {
@@ -116,6 +119,7 @@ int sb2_get_states(const sb2_model* m, double* states, int64_t n_cells);        
  *   pt_hs_k  13: snow.swe, snow.sca, snow.sp[0..4], snow.sw[0..4], kirchner.q
  *   hbv_stack 15: snow.swe, snow.sca, snow.sp[0..4], snow.sw[0..4], soil.sm, tank.uz, tank.lz
  *   pt_ss_k   8: snow.nu, snow.alpha, snow.sca, snow.swe, snow.free_water, snow.residual, snow.num_units, kirchner.q
+ *   pt_hps_k 24: hps.sp[0..4], hps.sw[0..4], hps.albedo[0..4], hps.iso_pot_energy[0..4], hps.surface_heat, hps.swe, hps.sca, kirchner.q
  * hbv_snow::state::distribute(parameter, false) (core/hbv_snow.h:114-118; called first thing by pt_hs_k::run :230 and run_hbv_stack :312):
  * rows whose ten snow bins are all zero -- the flat spelling of HbvSnowState(swe, sca) with empty bin vectors -- get sp / sw from swe, sca
  * and the cell's hs parameters (hbv_snow_common.h:44-67); other rows are left as they are.  Host side, in place, before sb2_set_states. */

@@ -527,5 +527,6 @@ using pt_gs_k_region_model = region_model<SB2_PT_GS_K>;
 using pt_hs_k_region_model = region_model<SB2_PT_HS_K>;
 using hbv_stack_region_model = region_model<SB2_HBV_STACK>;
 using pt_ss_k_region_model = region_model<SB2_PT_SS_K>;
+using pt_hps_k_region_model = region_model<SB2_PT_HPS_K>;
 
 }  // namespace shyft_b200

@@ -10,6 +10,7 @@
 #include "sho_core.hpp"
 #include "sho_hbv.hpp"
 #include "sho_skaugen.hpp"
+#include "sho_hps.hpp"
 #include "sho_pt_gs_k.hpp"
 #include "sho_region.hpp"
 #include "sho_ts.hpp"
@@ -239,6 +240,51 @@ int sho_skaugen_step(const double* par8, double* state7, int64_t dt_us, double t
 }
 double sho_skaugen_sca_rel_red(double u, double n, double unit_size, double nu_a, double alpha) {
     try { return skaugen::statistics::sca_rel_red((unsigned long)u, (unsigned long)n, unit_size, nu_a, alpha); } catch (...) { return std::nan(""); }
+}
+// pt_hps_k region run: state [n_cells][4*nb + 4] = sp[nb], sw[nb], albedo[nb], iso_pot_energy[nb], surface_heat, swe, sca, kirchner.q
+int sho_pthpsk_run_cells(int64_t n_cells, const double* geo, int64_t n_sets, const double* params, int n_param, const int32_t* pset_of_cell,
+                         int64_t t0_us, int64_t dt_us, int64_t n_axis, int start_step, int n_steps, const double* f_temp, const double* f_prec,
+                         const double* f_rad, const double* f_wind, const double* f_rh, int64_t f_tstride, int64_t f_cstride, double* state,
+                         int n_state, double** resp, int64_t o_tstride, int64_t o_cstride, int ncore) {
+    SHO_TRY
+    auto cells = make_cells(n_cells, geo);
+    std::vector<pt_hps_k::parameter> ps(n_sets);
+    for (int64_t k = 0; k < n_sets; ++k) ps[k].set(params + k * n_param, size_t(n_param));
+    fixed_dt ta{t0_us, dt_us, size_t(n_axis)};
+    parallel_run(size_t(n_cells), ncore, [&](size_t ci) {
+        const auto& p = ps[pset_of_cell ? pset_of_cell[ci] : 0];
+        pt_hps_k::state s;
+        s.unpack(state + ci * n_state, size_t(n_state));
+        pt_hps_k::cell_forcing f{f_temp + ci * f_cstride, f_prec + ci * f_cstride, f_wind + ci * f_cstride, f_rh + ci * f_cstride,
+                                 f_rad + ci * f_cstride, f_tstride};
+        pt_hps_k::run(cells[ci], p, ta, start_step, n_steps, f, s, resp, o_tstride, o_cstride, ci);
+        s.pack(state + ci * n_state, size_t(n_state));
+    });
+    SHO_END
+}
+// hbv_physical_snow::calculator::step (core/hbv_physical_snow.h:266-529) with the explicit parameter(s, intervals) constructor (normalised);
+// par11 = tx lw cfr wind_scale wind_const surface_magnitude max_albedo min_albedo fast_albedo_decay_rate slow_albedo_decay_rate snowfall_reset_depth;
+// state = sp[n], sw[n], albedo[n], iso_pot_energy[n], surface_heat, swe, sca in place (distribute = 1: state.distribute(p) first);
+// forcing5 = T rad prec wind_speed rel_hum; out3 = outflow sca storage
+int sho_hps_step(const double* s_q, const double* intervals, int n, const double* par11, int iso, int distribute, double* state, int64_t dt_us,
+                 const double* forcing5, double* out3) {
+    SHO_TRY
+    hbv_physical_snow::parameter p(std::vector<double>(s_q, s_q + n), std::vector<double>(intervals, intervals + n));
+    p.tx = par11[0]; p.lw = par11[1]; p.cfr = par11[2]; p.wind_scale = par11[3]; p.wind_const = par11[4]; p.surface_magnitude = par11[5];
+    p.max_albedo = par11[6]; p.min_albedo = par11[7]; p.fast_albedo_decay_rate = par11[8]; p.slow_albedo_decay_rate = par11[9];
+    p.snowfall_reset_depth = par11[10]; p.calculate_iso_pot_energy = iso != 0;
+    hbv_physical_snow::state s;
+    s.sp.assign(state, state + n); s.sw.assign(state + n, state + 2 * n); s.albedo.assign(state + 2 * n, state + 3 * n);
+    s.iso_pot_energy.assign(state + 3 * n, state + 4 * n);
+    s.surface_heat = state[4 * n]; s.swe = state[4 * n + 1]; s.sca = state[4 * n + 2];
+    if (distribute) s.distribute(p);
+    hbv_physical_snow::response r;
+    hbv_physical_snow::calculator c(p);
+    c.step(s, r, 0, dt_us, forcing5[0], forcing5[1], forcing5[2], forcing5[3], forcing5[4]);
+    for (int i = 0; i < n; ++i) { state[i] = s.sp[i]; state[n + i] = s.sw[i]; state[2 * n + i] = s.albedo[i]; state[3 * n + i] = s.iso_pot_energy[i]; }
+    state[4 * n] = s.surface_heat; state[4 * n + 1] = s.swe; state[4 * n + 2] = s.sca;
+    out3[0] = r.outflow; out3[1] = r.sca; out3[2] = r.storage;
+    SHO_END
 }
 // hbv unit steps for known-answer tests
 int sho_hbv_snow_step(const double* s_q /*n*/, const double* intervals /*n*/, int n, const double* par5 /*tx cx ts lw cfr*/, double* sp, double* sw,

@@ -36,7 +36,7 @@ def geo_matrix(geo_records):
 
 def build(force=False):
     so = os.path.join(_HERE, "libsho_oracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("capi.cpp", "sho_detmath.hpp", "sho_math_tables.inc", "sho_core.hpp", "sho_pt_gs_k.hpp", "sho_hbv.hpp", "sho_skaugen.hpp", "sho_region.hpp", "sho_ts.hpp")]
+    srcs = [os.path.join(_HERE, f) for f in ("capi.cpp", "sho_detmath.hpp", "sho_math_tables.inc", "sho_core.hpp", "sho_pt_gs_k.hpp", "sho_hbv.hpp", "sho_skaugen.hpp", "sho_hps.hpp", "sho_region.hpp", "sho_ts.hpp")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "libsho_oracle.so"], stdout=subprocess.DEVNULL)
     return so
@@ -285,6 +285,27 @@ def skaugen_step(state7, temp, prec, dt_us=3600 * 10**6, par=SKAUGEN_DEFAULT):
 
 def skaugen_sca_rel_red(u, n, nu_a, alpha, unit_size=0.1):
     return float(lib().sho_skaugen_sca_rel_red(C.c_double(u), C.c_double(n), C.c_double(unit_size), C.c_double(nu_a), C.c_double(alpha)))
+
+
+HPS_DEFAULT = (0.0, 0.1, 0.5, 2.0, 1.0, 30.0, 0.9, 0.6, 5.0, 5.0, 5.0)   # tx lw cfr wind_scale wind_const surface_magnitude max/min albedo fast/slow decay reset_depth
+
+
+def pthpsk_run_cells(geo, params, forcing, state, t0_us, dt_us, start_step=0, n_steps=0, pset_of_cell=None, ncore=1):
+    """Reference-equivalent pt_hps_k run_cells (core/pt_hps_k.h:201-303).  state [n][24] = sp[5], sw[5], albedo[5], iso_pot_energy[5],
+    surface_heat, swe, sca, kirchner.q"""
+    out = _hs_run(lib().sho_pthpsk_run_cells, 24, geo, params, forcing, state, t0_us, dt_us, start_step, n_steps, pset_of_cell, ncore)
+    out.pop("soil_outflow")
+    return out
+
+
+def hps_step(state, T, rad, prec, wind_speed, rel_hum, dt_us=3600 * 10**6, s=(1.0,) * 5, intervals=(0.0, 0.25, 0.5, 0.75, 1.0), par=HPS_DEFAULT, iso=False,
+             distribute=False):
+    """hbv_physical_snow::calculator::step on state [sp.., sw.., albedo.., iso.., surface_heat, swe, sca] -> (state, (outflow, sca, storage))"""
+    st = _f64(state).copy()
+    out = np.zeros(3)
+    _check(lib().sho_hps_step(_d(_f64(s)), _d(_f64(intervals)), C.c_int(len(s)), _d(_f64(par)), C.c_int(int(iso)), C.c_int(int(distribute)), _d(st),
+                              C.c_int64(dt_us), _d(_f64([T, rad, prec, wind_speed, rel_hum])), _d(out)))
+    return st, out
 
 
 def hbv_snow_step(sp, sw, swe, sca, prec, temp, dt_us=3600 * 10**6, s=None, intervals=None, tx=0.0, cx=1.0, ts=0.0, lw=0.1, cfr=0.5):

@@ -14,7 +14,7 @@ c_dp = C.POINTER(C.c_double)
 c_i64p = C.POINTER(C.c_int64)
 
 # enums of include/shyft_b200.h
-PT_GS_K, PT_HS_K, HBV_STACK, PT_SS_K = 0, 1, 2, 3
+PT_GS_K, PT_HS_K, HBV_STACK, PT_SS_K, PT_HPS_K = 0, 1, 2, 3, 4
 TEMPERATURE, PRECIPITATION, RADIATION, WIND_SPEED, REL_HUM = 0, 1, 2, 3, 4
 FORCING_NAMES = ("temperature", "precipitation", "radiation", "wind_speed", "rel_hum")
 TIME_MAJOR, CELL_MAJOR = 0, 1
@@ -25,6 +25,8 @@ STATE_SERIES_NAMES = {
               "gs_temp_swe"),
     PT_HS_K: ("kirchner_discharge", "snow_sca", "snow_swe") + tuple(f"snow_sp_{i}" for i in range(5)) + tuple(f"snow_sw_{i}" for i in range(5)),
     PT_SS_K: ("kirchner_discharge", "snow_swe", "snow_sca", "snow_alpha", "snow_nu", "snow_lwc", "snow_residual"),
+    PT_HPS_K: ("kirchner_discharge", "snow_sca", "snow_swe", "snow_surface_heat") + tuple(f"snow_sp_{i}" for i in range(5))
+    + tuple(f"snow_sw_{i}" for i in range(5)) + tuple(f"snow_albedo_{i}" for i in range(5)) + tuple(f"snow_iso_pot_energy_{i}" for i in range(5)),
     HBV_STACK: ("snow_swe", "snow_sca", "soil_moisture", "tank_uz", "tank_lz") + tuple(f"snow_sp_{i}" for i in range(5))
     + tuple(f"snow_sw_{i}" for i in range(5)),
 }
@@ -124,7 +126,8 @@ UNIT_FUNCTIONS = dict(exp=(0, 1, 1), log=(1, 1, 1), pow=(2, 2, 1), lgamma=(3, 1,
                       kirchner_step=(7, 7, 3),
                       # the forms the production kernels use (sb2_unit.cuh)
                       exp_flat=(8, 1, 1), log_flat=(9, 1, 1), pow_flat=(10, 2, 1), calc_snow_state_hot=(11, 7, 2), kirchner_step_warp=(12, 7, 3),
-                      gamma_p_pair=(13, 4, 2), div_by=(14, 2, 2), kirchner_step_warp_udt=(15, 7, 3), corr_lwc_warp=(16, 6, 1), skaugen_step=(17, 18, 11), sca_rel_red=(18, 4, 2))
+                      gamma_p_pair=(13, 4, 2), div_by=(14, 2, 2), kirchner_step_warp_udt=(15, 7, 3), corr_lwc_warp=(16, 6, 1), skaugen_step=(17, 18, 11), sca_rel_red=(18, 4, 2),
+                      hps_step=(19, 41, 27))
 
 
 def check_guards():

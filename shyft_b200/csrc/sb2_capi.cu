@@ -20,6 +20,7 @@
 #include "sb2_ptgsk.cuh"
 #include "sb2_hbv.cuh"
 #include "sb2_ptssk.cuh"
+#include "sb2_pthpsk.cuh"
 #include "sb2_routing.cuh"
 #include <nvtx3/nvToolsExt.h>  // header-only; ranges are no-ops unless a profiler is attached
 #include "sb2_unit.cuh"
@@ -217,9 +218,9 @@ struct BtkOps {  // operators of one valid-station subset
     DevArray<int32_t> valid_idx;
 };
 
-const int kParamSize[4] = {31, 18, 22, 21};
+const int kParamSize[5] = {31, 18, 22, 21, 24};
 const int kSnowBins = 5;
-const int kStateSize[4] = {9, 3 + 2 * kSnowBins, 5 + 2 * kSnowBins, 8};
+const int kStateSize[5] = {9, 3 + 2 * kSnowBins, 5 + 2 * kSnowBins, 8, 4 + 4 * kSnowBins};
 
 inline int grid_for(int64_t n, int block) { return int((n + block - 1) / block); }
 
@@ -257,6 +258,7 @@ struct sb2_model {
     DevArray<PtgskParam> d_ptgsk_params;
     DevArray<HbvParam> d_hbv_params;
     DevArray<SskParam> d_ssk_params;
+    DevArray<HpsParam> d_hps_params;
     // state [n_state][n] + the initial-state snapshot (region_model.h:313,593-594)
     DevArray<double> d_state, d_initial_state;
     bool has_initial = false;
@@ -381,6 +383,8 @@ std::vector<double> default_parameter(int stack) {
                 0.04,   100.0, 0.0,  6.0, 1.0,  7.0, 0.0, 221.0, 0.0, 1.0};
     if (stack == SB2_PT_SS_K)  // pt_ss_k::parameter::get order (core/pt_ss_k.h:90-117); skaugen::parameter defaults (core/skaugen.h:92-99)
         return {-2.439, 0.966, -0.10, 1.5, 40.77, 113.0, 0.1, 0.1, 0.16, 2.5, 0.14, 0.01, 1.0, 0.2, 1.26, 6.0, 1.0, 7.0, 0.0, 0.0, 1.0};
+    if (stack == SB2_PT_HPS_K)  // pt_hps_k::parameter::get order (core/pt_hps_k.h:93-120); hbv_physical_snow::parameter defaults (:40-92)
+        return {-2.439, 0.966, -0.10, 1.5, 0.1, 0.0, 0.5, 2.0, 1.0, 30.0, 0.9, 0.6, 5.0, 5.0, 5.0, 0.0, 6.0, 1.0, 0.2, 1.26, 1.0, 7.0, 0.0, 1.0};
     if (stack == SB2_PT_HS_K)  // pt_hs_k::parameter::get order (core/pt_hs_k.h:108-131)
         return {-2.439, 0.966, -0.10, 1.5, 0.1, 0.0, 1.0, 0.0, 0.5, 6.0, 1.0, 0.2, 1.26, 1.0, 7.0, 0.0, 0.0, 1.0};
     // hbv_stack::parameter::get order (core/hbv_stack.h:127-155)
@@ -407,6 +411,10 @@ void sync_parameters(sb2_model* m) {
         std::vector<SskParam> tab;
         for (auto* s : sets) tab.push_back(make_ssk_param(s->data()));
         m->d_ssk_params.upload(tab, m->stream);
+    } else if (m->stack == SB2_PT_HPS_K) {
+        std::vector<HpsParam> tab;
+        for (auto* s : sets) tab.push_back(make_hps_param(s->data(), m->dt > 0 ? m->dt : 3600000000LL));
+        m->d_hps_params.upload(tab, m->stream);
     } else {
         std::vector<HbvParam> tab;
         for (auto* s : sets) tab.push_back(make_hbv_param(m->stack == SB2_HBV_STACK, s->data()));
@@ -463,6 +471,7 @@ bool wants_response(const sb2_model* m, int r) {
     return (bits & 4) && m->stack == SB2_HBV_STACK;  // soil_outflow
 }
 int n_state_series(const sb2_model* m) {
+    if (m->stack == SB2_PT_HPS_K) return 4 + 4 * kSnowBins;
     return m->stack == SB2_PT_GS_K ? 9 : (m->stack == SB2_PT_SS_K ? 7 : (m->stack == SB2_PT_HS_K ? 3 + 2 * kSnowBins : 5 + 2 * kSnowBins));
 }
 
@@ -597,6 +606,30 @@ void launch_step_range(sb2_model* m, int64_t first, int64_t n_steps, bool collec
             a.unit_steps = split ? SB2_HBV_UNIT_STEPS : 0; a.tickets = m->d_tickets.p; a.progress = m->d_tickets.p + 1;
             if (split) CUDA_OK(cudaMemsetAsync(m->d_tickets.p, 0, size_t(1 + g) * sizeof(int), m->stream));
             ptssk_run_kernel<<<g * n_slices, block, SB2_MTAB_BYTES, m->stream>>>(a);
+        } else if (m->stack == SB2_PT_HPS_K) {
+            HpsRunArgs a{};
+            a.n_cells = n;
+            a.area = m->d_area.p; a.glacier = m->d_glacier.p; a.lake = m->d_lake.p; a.reservoir = m->d_reservoir.p;
+            a.pset = m->d_pset.p; a.active = m->d_active.p; a.params = m->d_hps_params.p; a.state = m->d_state.p;
+            for (int v = 0; v < 5; ++v) a.f[v] = m->d_forcing[v].p + (s0 - m->forcing_first) * n;
+            a.n_steps = chunk; a.first_step = s0;
+            a.dt_seconds = dt_seconds; a.dt_hours = dt_seconds / 3600.0; a.dt_us = double(m->dt);
+            a.bb0 = 0.98 * 5.670373e-8 * sb_pow4(273.15);  // calculator::BB0 (hbv_physical_snow.h:208)
+            fill_dopri_products(a.dt_hours, a.dtb);
+            a.inv_dt_seconds = make_inv_divisor(dt_seconds);
+            for (int r = 0; r < 8; ++r) a.resp[r] = m->d_resp[r].p;
+            for (int s = 0; s < 4 + 4 * kSnowBins; ++s) a.st[s] = m->d_st[s].p;
+            a.out_first_step = m->out_first;
+            a.collect_end_state = (last && collect_end_state) ? 1 : 0;
+            a.slot = m->d_slot.p; a.partial = m->d_partial.p; a.n_slots = m->n_slots; a.error_flag = m->d_error_flag.p;
+            a.collect = m->collect_bits & 15;
+            const int g = grid_for(n, block);
+            const bool split = use_time_split(g) && SB2_HBV_UNIT_STEPS > 0;
+            const int n_slices = split ? grid_for(chunk, SB2_HBV_UNIT_STEPS) : 1;
+            m->d_tickets.ensure(size_t(1 + g));
+            a.unit_steps = split ? SB2_HBV_UNIT_STEPS : 0; a.tickets = m->d_tickets.p; a.progress = m->d_tickets.p + 1;
+            if (split) CUDA_OK(cudaMemsetAsync(m->d_tickets.p, 0, size_t(1 + g) * sizeof(int), m->stream));
+            pthpsk_run_kernel<<<g * n_slices, block, SB2_MTAB_BYTES, m->stream>>>(a);
         } else {
             HbvRunArgs a{};
             a.n_cells = n;
@@ -986,7 +1019,7 @@ void ensure_routing_plan(sb2_model* m) {
     if (m->route) return;
     if (m->rivers.empty()) throw Error("routing: the river network is empty");
     // routing velocity/alpha/beta live in the cell's parameter set (pt_gs_k.h:102-104, pt_hs_k.h:81-83, hbv_stack.h:93-95)
-    const int off = m->stack == SB2_PT_GS_K ? 25 : (m->stack == SB2_PT_HS_K ? 13 : (m->stack == SB2_PT_SS_K ? 16 : 17));
+    const int off = m->stack == SB2_PT_GS_K ? 25 : (m->stack == SB2_PT_HS_K ? 13 : (m->stack == SB2_PT_SS_K ? 16 : (m->stack == SB2_PT_HPS_K ? 20 : 17)));
     std::vector<double> cell_routing(size_t(m->n) * 5);
     for (int64_t i = 0; i < m->n; ++i) {
         auto f = m->catch_param.find(m->geo[i].catchment_id);
@@ -1250,6 +1283,8 @@ const double* stat_ae_scale(sb2_model* m, int kind, DevArray<double>& buf) {
         stat_cell_ae_scale_kernel<<<grid_for(m->n, 256), 256, 0, m->stream>>>(m->n, m->d_pset.p, m->d_ptgsk_params.p, buf.p);
     else if (m->stack == SB2_PT_SS_K)
         stat_cell_ae_scale_ssk_kernel<<<grid_for(m->n, 256), 256, 0, m->stream>>>(m->n, m->d_pset.p, m->d_ssk_params.p, buf.p);
+    else if (m->stack == SB2_PT_HPS_K)
+        stat_cell_ae_scale_hps_kernel<<<grid_for(m->n, 256), 256, 0, m->stream>>>(m->n, m->d_pset.p, m->d_hps_params.p, buf.p);
     else
         stat_cell_ae_scale_hbv_kernel<<<grid_for(m->n, 256), 256, 0, m->stream>>>(m->n, m->d_pset.p, m->d_hbv_params.p, buf.p);
     CUDA_OK(cudaGetLastError());
@@ -1313,7 +1348,7 @@ int sb2_model_create(int stack, int64_t n_cells, const sb2_geo_cell* cells, int 
     std::unique_ptr<sb2_model> m;
     try {
         if (!out) throw Error("null output pointer");
-        if (stack < 0 || stack > 3) throw Error("unknown method stack");
+        if (stack < 0 || stack > 4) throw Error("unknown method stack");
         if (n_cells <= 0 || !cells) throw Error("region_model needs at least one cell");
         int count = 0;
         cudaError_t e = cudaGetDeviceCount(&count);
@@ -1473,6 +1508,7 @@ int sb2_hbv_distribute_snow(const sb2_model* cm, double* states, int64_t n_cells
     return guarded_c(cm, [&] {
         sb2_model* m = const_cast<sb2_model*>(cm);
         if (m->stack == SB2_PT_GS_K || m->stack == SB2_PT_SS_K) throw Error("distribute_snow: this stack's state has no snow bins");
+        if (m->stack == SB2_PT_HPS_K) throw Error("distribute_snow: a pt_hps_k state carries its bins (and their albedo / iso_pot_energy) explicitly");
         if (n_cells != m->n) throw Error("Length of the state vector must equal number of cells");
         const int lw_ix = m->stack == SB2_PT_HS_K ? 4 : 8;  // hs.lw in parameter::get order
         for (int64_t i = 0; i < m->n; ++i) {
@@ -2353,7 +2389,7 @@ int sb2_calculate_goal_function_batch(sb2_model* m, int64_t n_sets, const double
 // ---- diagnostics ---------------------------------------------------------------------------------------------------------------
 int sb2_unit_eval(int device, int fn, int64_t n, const double* in, int n_in, double* out, int n_out) {
     try {
-        static const int need_in[UNIT_N] = {1, 1, 2, 1, 2, 5, 7, 7, 1, 1, 2, 7, 7, 4, 2, 7, 6, 18, 4}, need_out[UNIT_N] = {1, 1, 1, 1, 1, 1, 2, 3, 1, 1, 1, 2, 3, 2, 2, 3, 1, 11, 2};
+        static const int need_in[UNIT_N] = {1, 1, 2, 1, 2, 5, 7, 7, 1, 1, 2, 7, 7, 4, 2, 7, 6, 18, 4, 41}, need_out[UNIT_N] = {1, 1, 1, 1, 1, 1, 2, 3, 1, 1, 1, 2, 3, 2, 2, 3, 1, 11, 2, 27};
         if (fn < 0 || fn >= UNIT_N) throw Error("unknown unit function");
         if (n_in < need_in[fn] || n_out < need_out[fn]) throw Error("unit function: too few input or output columns");
         CUDA_OK(cudaSetDevice(device));

@@ -71,5 +71,10 @@ __global__ void stat_cell_ae_scale_ssk_kernel(int64_t n_cells, const int32_t* __
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c < n_cells) out[c] = params[pset[c]].ae_scale_factor;
 }
+__global__ void stat_cell_ae_scale_hps_kernel(int64_t n_cells, const int32_t* __restrict__ pset, const HpsParam* __restrict__ params,
+                                              double* __restrict__ out) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n_cells) out[c] = params[pset[c]].ae_scale_factor;
+}
 
 }  // namespace sb2

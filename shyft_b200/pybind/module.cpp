@@ -171,12 +171,15 @@ PYBIND11_MODULE(_shyft_b200_cpp, m) {
     bind_model<SB2_PT_HS_K>(m, "PTHSKModel", all, "region_model<pt_hs_k::cell_complete_response_t>");
     bind_model<SB2_HBV_STACK>(m, "HbvModel", all, "region_model<hbv_stack::cell_complete_response_t>");
     bind_model<SB2_PT_SS_K>(m, "PTSSKModel", all, "region_model<pt_ss_k::cell_complete_response_t>");
+    bind_model<SB2_PT_HPS_K>(m, "PTHPSKModel", all, "region_model<pt_hps_k::cell_complete_response_t>");
     // the *OptModel types are the same C++ classes with the discharge collector only (cell_discharge_response_t): factory functions
     m.def("PTGSKOptModel", [opt](const py::array& geo, const std::vector<double>& p, int device) { return make_model<SB2_PT_GS_K>(geo, p, device, opt); },
           py::arg("geo_cell_data_vector"), py::arg("region_parameter"), py::arg("device") = 0);
     m.def("PTHSKOptModel", [opt](const py::array& geo, const std::vector<double>& p, int device) { return make_model<SB2_PT_HS_K>(geo, p, device, opt); },
           py::arg("geo_cell_data_vector"), py::arg("region_parameter"), py::arg("device") = 0);
     m.def("PTSSKOptModel", [opt](const py::array& geo, const std::vector<double>& p, int device) { return make_model<SB2_PT_SS_K>(geo, p, device, opt); },
+          py::arg("geo_cell_data_vector"), py::arg("region_parameter"), py::arg("device") = 0);
+    m.def("PTHPSKOptModel", [opt](const py::array& geo, const std::vector<double>& p, int device) { return make_model<SB2_PT_HPS_K>(geo, p, device, opt); },
           py::arg("geo_cell_data_vector"), py::arg("region_parameter"), py::arg("device") = 0);
     m.def("HbvOptModel", [opt](const py::array& geo, const std::vector<double>& p, int device) { return make_model<SB2_HBV_STACK>(geo, p, device, opt); },
           py::arg("geo_cell_data_vector"), py::arg("region_parameter"), py::arg("device") = 0);
@@ -219,6 +222,7 @@ PYBIND11_MODULE(_shyft_b200_cpp, m) {
     bind_optimizer<SB2_PT_HS_K>(m, "PTHSKOptimizer");
     bind_optimizer<SB2_HBV_STACK>(m, "HbvOptimizer");
     bind_optimizer<SB2_PT_SS_K>(m, "PTSSKOptimizer");
+    bind_optimizer<SB2_PT_HPS_K>(m, "PTHPSKOptimizer");
     m.attr("NASH_SUTCLIFFE") = int(sb::NASH_SUTCLIFFE); m.attr("KLING_GUPTA") = int(sb::KLING_GUPTA); m.attr("ABS_DIFF") = int(sb::ABS_DIFF);
     m.attr("RMSE") = int(sb::RMSE); m.attr("DISCHARGE") = int(sb::DISCHARGE); m.attr("SNOW_COVERED_AREA") = int(sb::SNOW_COVERED_AREA);
     m.attr("SNOW_WATER_EQUIVALENT") = int(sb::SNOW_WATER_EQUIVALENT); m.attr("ROUTED_DISCHARGE") = int(sb::ROUTED_DISCHARGE);

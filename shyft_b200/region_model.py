@@ -12,7 +12,7 @@ import ctypes as C
 import numpy as np
 
 from . import capi
-from .capi import (COLLECT_ALL, COLLECT_DISCHARGE, COLLECT_NONE, COLLECT_SNOW, COLLECT_STATE, FORCING_NAMES, GEO_DTYPE, HBV_STACK, PT_GS_K, PT_HS_K, PT_SS_K,
+from .capi import (COLLECT_ALL, COLLECT_DISCHARGE, COLLECT_NONE, COLLECT_SNOW, COLLECT_STATE, FORCING_NAMES, GEO_DTYPE, HBV_STACK, PT_GS_K, PT_HPS_K, PT_HS_K, PT_SS_K,
                    RESPONSE_NAMES, STATE_SERIES_NAMES, InterpolationParameter, dptr, f64)
 
 # parameter vector names, order of parameter::get_name (core/pt_gs_k.h:156-193, core/pt_hs_k.h:133-146, core/hbv_stack.h:136-167)
@@ -29,6 +29,10 @@ PARAMETER_NAMES = {
     PT_SS_K: ("kirchner.c1", "kirchner.c2", "kirchner.c3", "ae.ae_scale_factor", "ss.alpha_0", "ss.d_range", "ss.unit_size", "ss.max_water_fraction",
               "ss.tx", "ss.cx", "ss.ts", "ss.cfr", "p_corr.scale_factor", "pt.albedo", "pt.alpha", "gm.dtf", "routing.velocity", "routing.alpha",
               "routing.beta", "gm.direct_response", "msp.reservoir_direct_response_fraction"),
+    PT_HPS_K: ("kirchner.c1", "kirchner.c2", "kirchner.c3", "ae.ae_scale_factor", "hps.lw", "hps.tx", "hps.cfr", "hps.wind_scale", "hps.wind_const",
+               "hps.surface_magnitude", "hps.max_albedo", "hps.min_albedo", "hps.fast_albedo_decay_rate", "hps.slow_albedo_decay_rate",
+               "hps.snowfall_reset_depth", "hps.calculate_iso_pot_energy", "gm.dtf", "p_corr.scale_factor", "pt.albedo", "pt.alpha",
+               "routing.velocity", "routing.alpha", "routing.beta", "msp.reservoir_direct_response_fraction"),
     HBV_STACK: ("soil.fc", "soil.beta", "ae.lp", "tank.uz1", "tank.kuz2", "tank.kuz1", "tank.perc", "tank.klz", "hs.lw", "hs.tx", "hs.cx", "hs.ts",
                 "hs.cfr", "p_corr.scale_factor", "pt.albedo", "pt.alpha", "gm.dtf", "routing.velocity", "routing.alpha", "routing.beta",
                 "gm.direct_response", "msp.reservoir_direct_response_fraction"),
@@ -511,6 +515,19 @@ class PTSSKModel(RegionModel):
 
 class PTSSKOptModel(RegionModel):
     stack = PT_SS_K
+    default_collect = COLLECT_DISCHARGE
+
+
+class PTHPSKModel(RegionModel):
+    """PTHPSKModel (shyft/api/pt_hps_k/__init__.py): Priestley-Taylor, hbv_physical_snow, actual evapotranspiration, Kirchner"""
+    stack = PT_HPS_K
+    priestley_taylor_response = property(lambda self: _stats().PriestleyTaylorResponseStatistics(self))
+    actual_evaptranspiration_response = property(lambda self: _stats().ActualEvapotranspirationResponseStatistics(self))
+    kirchner_state = property(lambda self: _stats().KirchnerStateStatistics(self))
+
+
+class PTHPSKOptModel(RegionModel):
+    stack = PT_HPS_K
     default_collect = COLLECT_DISCHARGE
 
 

@@ -79,6 +79,8 @@ def default_state(stack, n_cells, q0=0.8):
         s = np.tile(np.array([0.4, 0.1, 30000.0, 1.26, 0.0, 0.0, 0.0, 0.0, q0]), (n_cells, 1))
     elif stack == 3:
         s = np.tile(np.array([4.077, 40.77, 0.0, 0.0, 0.0, 0.0, 0.0, q0]), (n_cells, 1))   # skaugen::state() + kirchner.q
+    elif stack == 4:   # hbv_physical_snow::state() after distribute() (core/hbv_physical_snow.h:132-189) + kirchner.q
+        s = np.tile(np.array([0.0] * 10 + [0.4] * 5 + [0.0] * 5 + [30000.0, 0.0, 0.0, q0]), (n_cells, 1))
     elif stack == 1:
         s = np.zeros((n_cells, 13))
         s[:, 12] = q0

@@ -10,6 +10,10 @@ PTHSK_DEFAULT = np.array([-2.439, 0.966, -0.10, 1.5, 0.1, 0.0, 1.0, 0.0, 0.5, 6.
 # pt_ss_k::parameter::get order (core/pt_ss_k.h:90-117): kirchner c1 c2 c3, ae scale, ss alpha_0 d_range unit_size max_water_fraction tx cx ts cfr,
 # p_corr, pt albedo alpha, gm.dtf, routing velocity alpha beta, gm.direct_response, msp.reservoir_direct_response_fraction
 PTSSK_DEFAULT = np.array([-2.439, 0.966, -0.10, 1.5, 40.77, 113.0, 0.1, 0.1, 0.16, 2.5, 0.14, 0.01, 1.0, 0.2, 1.26, 6.0, 1.0, 7.0, 0.0, 0.0, 1.0])
+# pt_hps_k::parameter::get order (core/pt_hps_k.h:93-120): kirchner c1 c2 c3, ae scale, hps lw tx cfr wind_scale wind_const surface_magnitude max_albedo
+# min_albedo fast_albedo_decay_rate slow_albedo_decay_rate snowfall_reset_depth calculate_iso_pot_energy, gm.dtf, p_corr, pt albedo alpha, routing
+# velocity alpha beta, msp.reservoir_direct_response_fraction
+PTHPSK_DEFAULT = np.array([-2.439, 0.966, -0.10, 1.5, 0.1, 0.0, 0.5, 2.0, 1.0, 30.0, 0.9, 0.6, 5.0, 5.0, 5.0, 0.0, 6.0, 1.0, 0.2, 1.26, 1.0, 7.0, 0.0, 1.0])
 HBV_DEFAULT = np.array([300.0, 2.0, 150.0, 25.0, 0.5, 0.3, 0.8, 0.02, 0.1, 0.0, 1.0, 0.0, 0.5, 1.0, 0.2, 1.26, 6.0, 1.0, 7.0, 0.0, 0.0, 1.0])
 FORCING = ("temperature", "precipitation", "radiation", "wind_speed", "rel_hum")
 GEO_COLS = ("x", "y", "z", "area", "catchment_id", "radiation_slope_factor", "glacier", "lake", "reservoir", "forest", "routing_id", "routing_distance")

@@ -1,4 +1,5 @@
-"""The reference's stack-level known-answer cases (test/pt_gs_k_test.cpp:174-354, test/pt_hs_k_test.cpp:93-153, test/pt_ss_k_test.cpp:118-168), restated once and
+"""The reference's stack-level known-answer cases (test/pt_gs_k_test.cpp:174-354, test/pt_hs_k_test.cpp:93-153, test/pt_ss_k_test.cpp:118-168,
+test/pt_hps_k_test.cpp:43-156), restated once and
 driven through a `run(stack, geo [1][12], params, forcing dict of [T][1], state [1][k], t0_us, T) -> dict` callable, so that the
 CPU oracle (tests/test_oracle_stack_known_answers.py) and the CUDA path through the C ABI (tests/test_gpu_stack_known_answers.py)
 are held to the same asserts."""
@@ -7,7 +8,7 @@ import calendar as pycal
 import numpy as np
 import pytest
 
-from fixtures import PTGSK_DEFAULT, PTHSK_DEFAULT, PTSSK_DEFAULT
+from fixtures import PTGSK_DEFAULT, PTHPSK_DEFAULT, PTHSK_DEFAULT, PTSSK_DEFAULT
 
 T0 = pycal.timegm((2014, 8, 1, 0, 0, 0)) * 10**6
 AREA = 1000.0 * 1000.0
@@ -167,5 +168,39 @@ def ptssk_lake_reservoir_response(run):
     assert out["state_snow_swe"][1, 0] == approx(0.0, 0.001)
     assert out["state_snow_swe"][2, 0] == approx(1.5, 0.001)
     assert out["state_snow_swe"][3, 0] == approx(3.0, 0.001)
+    assert out["avg_discharge"][n - 1, 0] == approx(0.2 * 3.0 * MMH_TO_M3S * (1.0 - 0.3) + 0.3 * 3.0 * MMH_TO_M3S, 0.01)
+    assert np.all(np.isfinite(out["snow_swe"])) and np.all(out["snow_swe"] >= 0.0)   # test_call_stack's assert
+
+
+def hps_state(swe=0.0, sca=0.0, q=1.0, albedo=0.4, iso=0.0, surface_heat=30000.0, sp=None, sw=None):
+    """hbv_physical_snow::state flat: sp[5], sw[5], albedo[5], iso_pot_energy[5], surface_heat, swe, sca + kirchner.q"""
+    sp = [0.0] * 5 if sp is None else list(sp)
+    sw = [0.0] * 5 if sw is None else list(sw)
+    return np.array([sp + sw + [albedo] * 5 + [iso] * 5 + [surface_heat, swe, sca, q]])
+
+
+def pthpsk_lake_reservoir_response(run):
+    """pt_hps_k_lake_reservoir_response (test/pt_hps_k_test.cpp:97-156): the same story with hbv_physical_snow; the response swe (stair) is
+    0 / 1.5 / 3.0, the state collector's (instant) 0 / 0 / 1.5"""
+    n = 50
+    geo = geo_cell(lake=0.2, reservoir=0.3)
+    f = forcing(n, -15.0, 3.0, first_prec=0.0)
+    st = hps_state()
+    par = PTHPSK_DEFAULT.copy()
+    par[23] = 0.0
+    out = run(4, geo, par, f, st, T0, n)
+    assert out["avg_discharge"][0, 0] == approx(0.266, 0.01)
+    assert out["avg_discharge"][n - 1, 0] == approx(0.5 * 3.0 * MMH_TO_M3S, 0.01)
+    par[23] = 1.0
+    out = run(4, geo, par, f, st, T0, n)
+    assert out["avg_discharge"][0, 0] == approx(0.266 * 0.7, 0.01)
+    assert out["avg_discharge"][1, 0] == approx(0.266 + 0.3 * 0.5 * 3.0 * MMH_TO_M3S, 0.05)
+    if "state_snow_swe" in out:
+        assert out["state_snow_swe"][0, 0] == pytest.approx(0.0, abs=1e-4)
+        assert out["state_snow_swe"][1, 0] == pytest.approx(0.0, abs=1e-4)
+        assert out["state_snow_swe"][2, 0] == approx(1.5, 1e-4)
+    assert out["snow_swe"][0, 0] == pytest.approx(0.0, abs=1e-4)
+    assert out["snow_swe"][1, 0] == approx(1.5, 1e-4)
+    assert out["snow_swe"][2, 0] == approx(3.0, 1e-4)
     assert out["avg_discharge"][n - 1, 0] == approx(0.2 * 3.0 * MMH_TO_M3S * (1.0 - 0.3) + 0.3 * 3.0 * MMH_TO_M3S, 0.01)
     assert np.all(np.isfinite(out["snow_swe"])) and np.all(out["snow_swe"] >= 0.0)   # test_call_stack's assert

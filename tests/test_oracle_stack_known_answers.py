@@ -10,6 +10,8 @@ import stack_cases as sc
 @pytest.fixture(scope="module")
 def run(oracle):
     def f(stack, geo, par, forcing, state, t0_us, T):
+        if stack == 4:
+            return oracle.pthpsk_run_cells(geo, par, forcing, state, t0_us, 3600 * 10**6)
         if stack == 3:
             return oracle.ptssk_run_cells(geo, par, forcing, state, t0_us, 3600 * 10**6, collect_state=True)
         fn = oracle.ptgsk_run_cells if stack == 0 else oracle.pthsk_run_cells
@@ -33,6 +35,35 @@ def test_pt_hs_k_lake_reservoir_response(run):
 
 def test_pt_ss_k_lake_reservoir_response(run):
     sc.ptssk_lake_reservoir_response(run)
+
+
+def test_pt_hps_k_lake_reservoir_response(run):
+    sc.pthpsk_lake_reservoir_response(run)
+
+
+def test_pt_hps_k_call_stack(oracle):
+    """test/pt_hps_k_test.cpp:43-95: three days from HbvPhysicalSnowState(albedo 0.4, iso 0, surface_heat 30000, swe 10, sca 0.5), q = 5; the state's
+    empty bin vectors are filled by distribute() at the top of run() -- here through the oracle's hbv_snow distribute"""
+    T = 72
+    sp, sw, swe, sca = oracle.hbv_snow_distribute(10.0, 0.5, [1.0] * 5, [0.0, 0.25, 0.5, 0.75, 1.0], lw=0.1)
+    st = sc.hps_state(swe=swe, sca=sca, q=5.0, sp=sp, sw=sw)
+    h = np.arange(T)
+    f = dict(temperature=(-5.0 + 10.0 * np.sin(2 * np.pi * h / 24.0))[:, None], precipitation=np.where(h % 7 == 0, 3.0, 0.0)[:, None].astype(float),
+             radiation=np.maximum(0.0, 300.0 * np.sin(2 * np.pi * (h - 6) / 24.0))[:, None], wind_speed=np.full((T, 1), 2.0), rel_hum=np.full((T, 1), 0.7))
+    out = oracle.pthpsk_run_cells(sc.geo_cell(), sc.PTHPSK_DEFAULT, f, st, sc.T0, 3600 * 10**6)
+    assert np.all(np.isfinite(out["snow_swe"])) and np.all(out["snow_swe"] >= 0.0)
+    assert np.all(np.isfinite(out["avg_discharge"])) and out["state"].shape == (1, 24)
+
+
+@pytest.mark.parametrize("T,prec,swe,sca,rain_no_snow", [(1.0, 0.04, 0.05, 1.0, False), (-1.0, 0.15, 0.2, 0.6, False), (0.0, 0.15, 0.2, 0.6, False),
+                                                         (0.0, 0.15, 0.0, 0.0, True), (3.0, 0.0, 10.0, 0.5, False)])
+def test_hbv_physical_snow_mass_balance(oracle, T, prec, swe, sca, rain_no_snow):
+    """test/hbv_physical_snow_test.cpp:29-176: snow pack reset, build-up (and at T = tx), rain without snow, melt without precipitation"""
+    st = np.array([0.0] * 10 + [0.6] * 5 + [1752.56396484375] * 5 + [0.0, swe, sca])
+    s1, r = oracle.hps_step(st, T, 10.0, prec, 2.0, 0.70, distribute=True)
+    assert s1[21] + r[0] == pytest.approx(prec + swe, abs=1e-8)
+    if rain_no_snow:
+        assert s1[22] == pytest.approx(0.0, abs=1e-8) and s1[21] == pytest.approx(0.0, abs=1e-8)
 
 
 def test_skaugen_known_answers(oracle):
