@@ -19,7 +19,7 @@ import pytest
 
 from e2e_cases import oracle_forcing, region_slice, run_device_windows
 from e2e_census import Census
-from fixtures import HBV_DEFAULT, PTGSK_DEFAULT, PTHSK_DEFAULT, PTSSK_DEFAULT, geo_matrix
+from fixtures import HBV_DEFAULT, PTGSK_DEFAULT, PTHPSK_DEFAULT, PTHSK_DEFAULT, PTSSK_DEFAULT, geo_matrix
 from parity import assert_parity
 
 pytestmark = pytest.mark.gpu
@@ -86,7 +86,7 @@ def test_config2_slice_pt_gs_k_windowed_dense_interpolation_census(sb, oracle):
     assert np.array_equal(m.catchment_discharges(), cq_chunked)
 
 
-@pytest.mark.parametrize("stack", ["pt_hs_k", "hbv_stack", "pt_ss_k"])
+@pytest.mark.parametrize("stack", ["pt_hs_k", "hbv_stack", "pt_ss_k", "pt_hps_k"])
 def test_config3_slice_hbv_windowed_with_routing_census(sb, oracle, stack):
     """BASELINE configs[2] shape: 1 024 cells cut out of the 400 000-cell grid x 1 year from November, river network routing."""
     from shyft_b200 import synthetic
@@ -95,7 +95,8 @@ def test_config3_slice_hbv_windowed_with_routing_census(sb, oracle, stack):
     n = geo.shape[0]
     cls, par, sid, run = {"pt_hs_k": (sb.PTHSKModel, PTHSK_DEFAULT, 1, oracle.pthsk_run_cells),
                           "hbv_stack": (sb.HbvStackModel, HBV_DEFAULT, 2, oracle.hbv_stack_run_cells),
-                          "pt_ss_k": (sb.PTSSKModel, PTSSK_DEFAULT, 3, oracle.ptssk_run_cells)}[stack]
+                          "pt_ss_k": (sb.PTSSKModel, PTSSK_DEFAULT, 3, oracle.ptssk_run_cells),
+                          "pt_hps_k": (sb.PTHPSKModel, PTHPSK_DEFAULT, 4, oracle.pthpsk_run_cells)}[stack]
     st0 = synthetic.default_state(sid, n)
     gm, f = oracle_forcing(oracle, geo, ta, env, btk_temperature=True)
     want = run(gm, par, f, st0, ta.start * 10**6, ta.delta_t * 10**6, ncore=16)
@@ -133,7 +134,7 @@ def test_config3_slice_hbv_windowed_with_routing_census(sb, oracle, stack):
     m.set_river_network(rivers)
     m.revert_to_initial_state()
     m.run_windowed(ip, window_steps=W)
-    uhg = np.tile({"pt_hs_k": par[13:16], "hbv_stack": par[17:20], "pt_ss_k": par[16:19]}[stack], (n, 1))
+    uhg = np.tile({"pt_hs_k": par[13:16], "hbv_stack": par[17:20], "pt_ss_k": par[16:19], "pt_hps_k": par[20:23]}[stack], (n, 1))
     for rid in (cids[0], cids[3], cids[-1]):
         local, up, out = oracle.river_flows(rivers, int(rid), q_dev, gm[:, 10].astype(np.int64), gm[:, 11], uhg, ta.delta_t * 10**6)
         assert_parity(m.river_local_inflow_m3s(int(rid)), local, f"river {rid} local inflow", rtol=1e-9)
