@@ -264,7 +264,7 @@ struct sb2_model {
     bool has_initial = false;
     // time axis
     int64_t t0 = 0, dt = 0, T = 0;
-    DevArray<int32_t> d_doy, d_soy;
+    DevArray<int2> d_doy_soy;  // [T] (calendar day of year, seconds since the start of the year) of each period start, UTC
     std::vector<double> h_prior_gradient;
     DevArray<double> d_prior_gradient;
     // forcing [rows][n] per variable; rows cover steps [forcing_first, forcing_first + forcing_rows)
@@ -538,7 +538,7 @@ void launch_step_range(sb2_model* m, int64_t first, int64_t n_steps, bool collec
             a.dt_seconds = dt_seconds; a.dt_hours = dt_seconds / 3600.0; a.dt_us = double(m->dt);
             a.bb0 = 0.98 * 5.670373e-8 * sb_pow4(273.15);
             fill_step_constants(m, a);
-            a.day_of_year = m->d_doy.p; a.sec_of_year = m->d_soy.p;
+            a.day_sec_of_year = m->d_doy_soy.p;
             for (int r = 0; r < 8; ++r) a.resp[r] = m->d_resp[r].p;
             for (int s = 0; s < 9; ++s) a.st[s] = m->d_st[s].p;
             a.out_first_step = m->out_first;
@@ -1211,7 +1211,7 @@ void goal_batch_ptgsk(sb2_model* m, int64_t n_sets, const double* P, double* goa
             a.dt_seconds = dt_seconds; a.dt_hours = dt_seconds / 3600.0; a.dt_us = double(m->dt);
             a.bb0 = 0.98 * 5.670373e-8 * sb_pow4(273.15);
             fill_step_constants(m, a);
-            a.day_of_year = m->d_doy.p; a.sec_of_year = m->d_soy.p;
+            a.day_sec_of_year = m->d_doy_soy.p;
             a.out_first_step = 0; a.collect_end_state = 0;
             a.slot = m->d_slot.p; a.partial = d_partial.p; a.n_slots = m->n_slots; a.error_flag = m->d_error_flag.p;
             a.ens_params = d_par.p; a.ens_state_stride = int64_t(state_sz); a.ens_partial_stride = ps * m->n_slots * 2;
@@ -1688,16 +1688,14 @@ int sb2_initialize_cell_environment(sb2_model* m, int64_t t0_us, int64_t dt_us, 
         const bool same_dt = dt_us == m->dt;
         m->t0 = t0_us; m->dt = dt_us; m->T = n;
         if (!same_dt) { m->param_dirty = true; m->route.reset(); }  // the albedo decay steps and the unit hydrographs depend on dt
-        std::vector<int32_t> doy(n), soy(n);
+        std::vector<int2> doy_soy(n);
         m->h_prior_gradient.resize(n);
         for (int64_t i = 0; i < n; ++i) {
             const int64_t t = t0_us + i * dt_us;
-            doy[i] = host::day_of_year(t);
-            soy[i] = int32_t(host::seconds_of_year(t));
+            doy_soy[i] = make_int2(host::day_of_year(t), int32_t(host::seconds_of_year(t)));
             m->h_prior_gradient[i] = host::btk_prior_gradient(t, dt_us);
         }
-        m->d_doy.upload(doy, m->stream);
-        m->d_soy.upload(soy, m->stream);
+        m->d_doy_soy.upload(doy_soy, m->stream);
         m->d_prior_gradient.upload(m->h_prior_gradient, m->stream);
         m->d_cq.resize(size_t(n) * m->n_catch());
         m->d_cc.resize(size_t(n) * m->n_catch());

@@ -78,8 +78,8 @@ struct PtgskRunArgs {
     // the region parameter set (params[0]) by value: with no catchment overrides and no ensemble every cell reads its parameters from
     // the kernel's constant bank (UPAR kernels) instead of through a pointer the step's stores might alias
     PtgskParam par0;
-    const int32_t* __restrict__ day_of_year;   // [T] calendar::day_of_year(period.start), UTC
-    const int32_t* __restrict__ sec_of_year;   // [T] (period.start - trim(period.start, YEAR)) in seconds
+    // [T] x = calendar::day_of_year(period.start), y = (period.start - trim(period.start, YEAR)) in seconds, UTC: one 8-byte load per step
+    const int2* __restrict__ day_sec_of_year;
     // collected series: element (absolute step - out_first_step, cell) at r[s][...*n_cells + c]; null = not collected
     double* __restrict__ resp[8];
     double* __restrict__ st[9];
@@ -1007,7 +1007,7 @@ __global__ void __launch_bounds__(SB2_BLOCK_A) ptgsk_forcing_terms_kernel(const 
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= a.n_cells) return;
     if (a.active != nullptr && a.active[c] == 0) return;
-    const int ens = blockIdx.z;  // parameter-set ensemble member (calibration), as in ptgsk_run_kernel
+    const int ens = UPAR ? 0 : blockIdx.z;  // parameter-set ensemble member (calibration); UPAR launches have none
     const PtgskParam& p = UPAR ? a.par0 : ((a.ens_params != nullptr && a.pset[c] == 0) ? a.ens_params[ens] : a.params[a.pset[c]]);
     const double pt_albedo = p.pt_albedo, pt_alpha = p.pt_alpha;
     const int64_t n = a.n_cells;
@@ -1016,9 +1016,9 @@ __global__ void __launch_bounds__(SB2_BLOCK_A) ptgsk_forcing_terms_kernel(const 
     double* __restrict__ s_tadd = a.scr[SCR_TADD] + (int64_t)ens * a.ens_scr_stride;
     const int i0 = blockIdx.y * SB2_STEPS_A;
     const int i1 = min(i0 + SB2_STEPS_A, a.n_steps);
+    int64_t o = (int64_t)i0 * n + c;
 #pragma unroll 2
-    for (int i = i0; i < i1; ++i) {
-        const int64_t o = (int64_t)i * n + c;
+    for (int i = i0; i < i1; ++i, o += n) {
         const double temp = a.f[0][o], rad = a.f[2][o], wind = a.f[3][o], rel_hum = a.f[4][o];
         double lw, tadd;
         gs_energy_terms<true>(p, a.bb0, temp, wind, rel_hum, lw, tadd);
@@ -1033,7 +1033,7 @@ __global__ void __launch_bounds__(SB2_BLOCK_A) ptgsk_forcing_terms_kernel(const 
 template <int COLLECT, bool UPAR>
 __global__ void __launch_bounds__(SB2_BLOCK_B, SB2_MINBLOCKS_B) ptgsk_snow_kernel(const __grid_constant__ PtgskRunArgs a) {
     sb_math_stage_tables();
-    const int ens = blockIdx.y;
+    const int ens = UPAR ? 0 : blockIdx.y;  // UPAR launches have no ensemble: the member offsets fold away
     // time split by ticket, as in ptgsk_response_kernel (1.76 waves of whole-window blocks otherwise); the memo starts empty in
     // every slice, which costs one snow-state evaluation per cell and slice
     int64_t group = blockIdx.x;
@@ -1080,10 +1080,12 @@ __global__ void __launch_bounds__(SB2_BLOCK_B, SB2_MINBLOCKS_B) ptgsk_snow_kerne
     gs.iso_pot_energy = __ldcg(state + 6 * n + c); gs.temp_swe = __ldcg(state + 7 * n + c);
     GsCache cache;
     gs_cache_clear(cache);
-    const int64_t o0 = (int64_t)i_begin * n + c;
-    double f_t = a.f[0][o0], f_p = a.f[1][o0], f_r = a.f[2][o0], f_lw = s_lw[o0], f_ta = s_tadd[o0];
-    for (int i = i_begin; i < i_end; ++i) {
-        const int64_t o = (int64_t)i * n + c;
+    // o: running element offset of (step i, cell c) in every [step][cell] array of the chunk -- bumped by n per step instead of
+    // multiplied out (the 64-bit i * n + c per array access was a sixth of this kernel's instructions)
+    int64_t o = (int64_t)i_begin * n + c;
+    const int64_t out_shift = (a.first_step - a.out_first_step) * n;  // collected series: row of step i = local row + this (uniform)
+    double f_t = a.f[0][o], f_p = a.f[1][o], f_r = a.f[2][o], f_lw = s_lw[o], f_ta = s_tadd[o];
+    for (int i = i_begin; i < i_end; ++i, o += n) {
 #if !SB2_REG_PREFETCH_B
         f_t = a.f[0][o]; f_p = a.f[1][o]; f_r = a.f[2][o]; f_lw = s_lw[o]; f_ta = s_tadd[o];
 #endif
@@ -1097,7 +1099,7 @@ __global__ void __launch_bounds__(SB2_BLOCK_B, SB2_MINBLOCKS_B) ptgsk_snow_kerne
             prefetch_l1(a.f[0] + o2); prefetch_l1(a.f[1] + o2); prefetch_l1(a.f[2] + o2); prefetch_l1(s_lw + o2); prefetch_l1(s_tadd + o2);
         }
         const int64_t step = a.first_step + i;
-        const int64_t orow = (step - a.out_first_step) * n + c;
+        const int64_t orow = o + out_shift;  // (step - a.out_first_step) * n + c
         if (COLLECT & 8) {  // state at the beginning of the period, scale_snow applied (pt_gs_k.h:213-218,367)
             a.st[1][orow] = gs.albedo;
             a.st[2][orow] = gs.lwc * snow_storage_fraction;
@@ -1111,7 +1113,8 @@ __global__ void __launch_bounds__(SB2_BLOCK_B, SB2_MINBLOCKS_B) ptgsk_snow_kerne
         double wind = 0.0, rel_hum = 0.0;
         if (iso) { wind = a.f[3][o]; rel_hum = a.f[4][o]; }
         double sca, storage, outflow;
-        gs_step_core<(SB2_SNOW_FLAT != 0)>(gs, cache, sca, storage, outflow, p, a.day_of_year[step], a.sec_of_year[step], a.dt_seconds, a.dt_us, gk, a.bb0, temp, rad,
+        const int2 ds = a.day_sec_of_year[step];
+        gs_step_core<(SB2_SNOW_FLAT != 0)>(gs, cache, sca, storage, outflow, p, ds.x, ds.y, a.dt_seconds, a.dt_us, gk, a.bb0, temp, rad,
                                            prec, lw, tadd, wind, rel_hum, inv_cv2);
         s_outflow[o] = outflow;
         s_sca[o] = sca;
@@ -1144,7 +1147,7 @@ __global__ void __launch_bounds__(SB2_BLOCK_B, SB2_MINBLOCKS_B) ptgsk_snow_kerne
 template <int COLLECT, bool UPAR>
 __global__ void __launch_bounds__(SB2_BLOCK_C, SB2_MINBLOCKS_C) ptgsk_response_kernel(const __grid_constant__ PtgskRunArgs a) {
     sb_math_stage_tables();
-    const int ens = blockIdx.y;
+    const int ens = UPAR ? 0 : blockIdx.y;  // UPAR launches have no ensemble
     // Time split.  A block steps one group of blockDim cells; with ~115 registers 2 500 of the 3 125 one-warp blocks of a 100 000-cell
     // shard are resident, so a launch of whole-window blocks runs as 1.25 waves -- the second wave leaves three quarters of the
     // machine idle for as long as the first took.  The window is therefore cut into units of unit_steps steps: blocks take tickets
@@ -1242,25 +1245,26 @@ __global__ void __launch_bounds__(SB2_BLOCK_C, SB2_MINBLOCKS_C) ptgsk_response_k
         const int prev = __shfl_up_sync(0xffffffffu, my_slot, 1);
         head = in_range && (lane == 0 || prev != my_slot);
     }
-    const int64_t o0 = (int64_t)i_begin * n + cc;
-    double f_t = a.f[0][o0], f_p = a.f[1][o0], f_pot = s_pot[o0], f_out = s_outflow[o0], f_sca = s_sca[o0];
+    int64_t o = (int64_t)i_begin * n + cc;  // running element offset of (step i, cell), bumped by n per step (see ptgsk_snow_kernel)
+    int64_t po = ((int64_t)i_begin * a.n_slots + (my_slot < 0 ? 0 : my_slot)) * 2;  // likewise into partial[step][slot][2]
+    const int64_t out_shift = (a.first_step - a.out_first_step) * n;
+    double f_t = a.f[0][o], f_p = a.f[1][o], f_pot = s_pot[o], f_out = s_outflow[o], f_sca = s_sca[o];
     bool failed = false;
-    for (int i = i_begin; i < i_end; ++i) {
+    for (int i = i_begin; i < i_end; ++i, o += n) {
 #if !SB2_REG_PREFETCH_C
-        { const int64_t oc = (int64_t)i * n + cc; f_t = a.f[0][oc]; f_p = a.f[1][oc]; f_pot = s_pot[oc]; f_out = s_outflow[oc]; f_sca = s_sca[oc]; }
+        f_t = a.f[0][o]; f_p = a.f[1][o]; f_pot = s_pot[o]; f_out = s_outflow[o]; f_sca = s_sca[o];
 #endif
         const double temp = f_t, prec = f_p * p_corr, pot = f_pot, outflow = f_out, sca = f_sca;
         if (SB2_REG_PREFETCH_C && i + 1 < i_end) {
-            const int64_t o1 = (int64_t)(i + 1) * n + cc;
+            const int64_t o1 = o + n;
             f_t = a.f[0][o1]; f_p = a.f[1][o1]; f_pot = s_pot[o1]; f_out = s_outflow[o1]; f_sca = s_sca[o1];
         }
         if (SB2_PREFETCH_AHEAD > 1 && i + SB2_PREFETCH_AHEAD < a.n_steps) {  // may reach into the next slice: same cells, same arrays
-            const int64_t o2 = (int64_t)(i + SB2_PREFETCH_AHEAD) * n + cc;
+            const int64_t o2 = o + SB2_PREFETCH_AHEAD * n;
             prefetch_l1(a.f[0] + o2); prefetch_l1(a.f[1] + o2); prefetch_l1(s_pot + o2); prefetch_l1(s_outflow + o2);
             prefetch_l1(s_sca + o2);
         }
-        const int64_t step = a.first_step + i;
-        const int64_t orow = (step - a.out_first_step) * n + cc;
+        const int64_t orow = o + out_shift;  // (a.first_step + i - a.out_first_step) * n + cc
 #if SB2_RESP_SMEM_CONST
         const InvDivisor inv_ae{ae_scale_factor, SB2_CST(12), ae_e_lo};
 #else
@@ -1307,10 +1311,11 @@ __global__ void __launch_bounds__(SB2_BLOCK_C, SB2_MINBLOCKS_C) ptgsk_response_k
                 if (lane + off < 32 && os == my_slot) { v0 += o0; v1 += o1; }
             }
             if (head) {
-                double* dst = partial + ((int64_t)i * a.n_slots + my_slot) * 2;
+                double* dst = partial + po;  // ((int64_t)i * a.n_slots + my_slot) * 2
                 dst[0] = v0;
                 dst[1] = v1;
             }
+            po += 2 * a.n_slots;
         }
     }
     if (active) {
