@@ -327,10 +327,11 @@ __global__ void __launch_bounds__(128, (HBV_STACK ? SB2_HBV_MINBLOCKS_S : SB2_HB
     bool failed_snow = false, failed_k = false;
     // the next step's forcing is loaded one step ahead into registers and SB2_PREFETCH_AHEAD steps ahead into L1 (as the pt_gs_k kernels do):
     // the step consumes one 8-byte value per array, so without it every step waits for DRAM
-    const int64_t o_first = (int64_t)i_begin * n + cc;
-    double f_t = a.f[0][o_first], f_p = a.f[1][o_first], f_r = a.f[2][o_first], f_h = a.f[4][o_first];
-    for (int i = i_begin; i < i_end; ++i) {
-        const int64_t o = (int64_t)i * n + cc;
+    int64_t o = (int64_t)i_begin * n + cc;  // running element offset of (step i, cell), bumped by n per step (see ptgsk_snow_kernel)
+    const int64_t out_shift = (a.first_step - a.out_first_step) * n;
+    int64_t po = ((int64_t)i_begin * a.n_slots + (my_slot < 0 ? 0 : my_slot)) * 2;  // likewise into partial[step][slot][2]
+    double f_t = a.f[0][o], f_p = a.f[1][o], f_r = a.f[2][o], f_h = a.f[4][o];
+    for (int i = i_begin; i < i_end; ++i, o += n) {
         const double temp = f_t, rad = f_r, rel_hum = f_h, prec_raw = f_p;
         if (i + 1 < i_end) {
             const int64_t o1 = o + n;
@@ -340,8 +341,7 @@ __global__ void __launch_bounds__(128, (HBV_STACK ? SB2_HBV_MINBLOCKS_S : SB2_HB
             const int64_t o2 = o + SB2_PREFETCH_AHEAD * n;
             prefetch_l1(a.f[0] + o2); prefetch_l1(a.f[1] + o2); prefetch_l1(a.f[2] + o2); prefetch_l1(a.f[4] + o2);
         }
-        const int64_t step = a.first_step + i;
-        const int64_t orow = (step - a.out_first_step) * n + cc;
+        const int64_t orow = o + out_shift;  // (step - a.out_first_step) * n + cc
         double out_q = 0.0, out_charge = 0.0;
         // pt_hs_k: the Kirchner solver is warp-synchronous (kirchner_step_warp), so the step is split around it: every lane calls it,
         // lanes without an active cell on benign inputs
@@ -420,10 +420,11 @@ __global__ void __launch_bounds__(128, (HBV_STACK ? SB2_HBV_MINBLOCKS_S : SB2_HB
                 if (lane + off < 32 && os == my_slot) { v0 += o0; v1 += o1; }
             }
             if (head) {
-                double* dst = a.partial + ((int64_t)i * a.n_slots + my_slot) * 2;
+                double* dst = a.partial + po;  // ((int64_t)i * a.n_slots + my_slot) * 2
                 dst[0] = v0;
                 dst[1] = v1;
             }
+            po += 2 * a.n_slots;
         }
     }
     if (active) {

@@ -525,7 +525,8 @@ struct GsStepConst { InvDivisor inv_dt_seconds, inv_dt_us; };
 template <bool FLAT = false>
 __device__ __forceinline__ void gs_step_core(GsState& s, GsCache& cache, double& r_sca, double& r_storage, double& r_outflow, const PtgskParam& p, int doy,
                                              int sec_of_year, double dt_seconds, double dt_us, const GsStepConst& k, double BB0, double T, double rad,
-                                             double prec_mm_h, double lw, double tadd, double wind_speed, double rel_hum, const InvDivisor& inv_cv2) {
+                                             double prec_mm_h, double lw, double tadd, const double* __restrict__ f_wind_speed, const double* __restrict__ f_rel_hum,
+                                             int64_t f_offset, const InvDivisor& inv_cv2) {
     const double tol = 1.0e-10;
     const double melt_heat = 333660.0, water_heat = 4180.0, ice_heat = 2050.0;
     double sdc_melt_mean = s.sdc_melt_mean;
@@ -569,7 +570,8 @@ __device__ __forceinline__ void gs_step_core(GsState& s, GsCache& cache, double&
     if (T > 0.0 && snow < tol) effect += div_by(rain * T * water_heat, k.inv_dt_seconds);
     if (T <= 0.0 && rain < tol) effect += div_by(snow * T * ice_heat, k.inv_dt_seconds);
 
-    if (p.calculate_iso_pot_energy) {
+    if (p.calculate_iso_pot_energy) {  // the only use of wind speed and relative humidity in this kernel: loaded here, under the branch
+        const double wind_speed = f_wind_speed[f_offset], rel_hum = f_rel_hum[f_offset];
         const double turb = p.wind_scale * wind_speed + p.wind_const;
         const double iso_effect = effect - BB0 + turb * (T + 1.7 * (gs_vapour_pressure(T, rel_hum) - 6.12));
         iso_pot_energy += div_by(iso_effect * dt_seconds, k_melt_heat);
@@ -1066,7 +1068,6 @@ __global__ void __launch_bounds__(SB2_BLOCK_B, SB2_MINBLOCKS_B) ptgsk_snow_kerne
     double* __restrict__ s_sca = a.scr[SCR_SCA] + (int64_t)ens * a.ens_scr_stride;
     const double altitude = a.z[c], cell_area_m2 = a.area[c], forest_fraction = a.forest[c];
     const double snow_storage_fraction = 1.0 - a.lake[c] - a.reservoir[c];
-    const bool iso = p.calculate_iso_pot_energy != 0;
     // the cell's effective coefficient of variation (gamma_snow.h:327), squared, as a divisor: the same every step
     const double snow_cv = p.snow_cv + forest_fraction * p.snow_cv_forest_factor + altitude * p.snow_cv_altitude_factor;
     const InvDivisor inv_cv2 = make_inv_divisor(snow_cv * snow_cv);
@@ -1084,6 +1085,7 @@ __global__ void __launch_bounds__(SB2_BLOCK_B, SB2_MINBLOCKS_B) ptgsk_snow_kerne
     // multiplied out (the 64-bit i * n + c per array access was a sixth of this kernel's instructions)
     int64_t o = (int64_t)i_begin * n + c;
     const int64_t out_shift = (a.first_step - a.out_first_step) * n;  // collected series: row of step i = local row + this (uniform)
+    const int2* __restrict__ ds_row = a.day_sec_of_year + a.first_step;
     double f_t = a.f[0][o], f_p = a.f[1][o], f_r = a.f[2][o], f_lw = s_lw[o], f_ta = s_tadd[o];
     for (int i = i_begin; i < i_end; ++i, o += n) {
 #if !SB2_REG_PREFETCH_B
@@ -1098,7 +1100,6 @@ __global__ void __launch_bounds__(SB2_BLOCK_B, SB2_MINBLOCKS_B) ptgsk_snow_kerne
             const int64_t o2 = o + SB2_PREFETCH_AHEAD * n;
             prefetch_l1(a.f[0] + o2); prefetch_l1(a.f[1] + o2); prefetch_l1(a.f[2] + o2); prefetch_l1(s_lw + o2); prefetch_l1(s_tadd + o2);
         }
-        const int64_t step = a.first_step + i;
         const int64_t orow = o + out_shift;  // (step - a.out_first_step) * n + c
         if (COLLECT & 8) {  // state at the beginning of the period, scale_snow applied (pt_gs_k.h:213-218,367)
             a.st[1][orow] = gs.albedo;
@@ -1110,12 +1111,10 @@ __global__ void __launch_bounds__(SB2_BLOCK_B, SB2_MINBLOCKS_B) ptgsk_snow_kerne
             a.st[7][orow] = gs.iso_pot_energy;
             a.st[8][orow] = gs.temp_swe * snow_storage_fraction;
         }
-        double wind = 0.0, rel_hum = 0.0;
-        if (iso) { wind = a.f[3][o]; rel_hum = a.f[4][o]; }
         double sca, storage, outflow;
-        const int2 ds = a.day_sec_of_year[step];
+        const int2 ds = ds_row[i];
         gs_step_core<(SB2_SNOW_FLAT != 0)>(gs, cache, sca, storage, outflow, p, ds.x, ds.y, a.dt_seconds, a.dt_us, gk, a.bb0, temp, rad,
-                                           prec, lw, tadd, wind, rel_hum, inv_cv2);
+                                           prec, lw, tadd, a.f[3], a.f[4], o, inv_cv2);
         s_outflow[o] = outflow;
         s_sca[o] = sca;
         if (COLLECT & 2) { a.resp[2][orow] = sca; a.resp[3][orow] = storage * snow_storage_fraction; }
