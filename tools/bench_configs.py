@@ -34,7 +34,8 @@ if 3 in which:  # pt_hs_k and hbv_stack, 400k cells x 5 years hourly, river rout
     T = int(8760 * years)
     geo, ta, env = synthetic.make_region(n, T, 64, config_index=2, with_routing=True)
     rivers = synthetic.river_chain(n // 1000, depth=8)
-    for name, cls, sid, nbytes in (("pt_hs_k", sb.PTHSKOptModel, 1, 56), ("hbv_stack", sb.HbvStackOptModel, 2, 56), ("pt_ss_k", sb.PTSSKOptModel, 3, 56)):
+    for name, cls, sid, nbytes in (("pt_hs_k", sb.PTHSKOptModel, 1, 56), ("hbv_stack", sb.HbvStackOptModel, 2, 56), ("pt_ss_k", sb.PTSSKOptModel, 3, 56),
+                                   ("pt_hps_k", sb.PTHPSKOptModel, 4, 56)):
         m = cls(geo)
         m.initialize_cell_environment(ta)
         m._set_sources(env)

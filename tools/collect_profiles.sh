@@ -12,5 +12,5 @@ for f in gpurun_out/${TAG}_hbv*.ncu-rep; do b=$(basename $f .ncu-rep); python to
 cp gpurun_out/${TAG}_bench_configs_c3.jsonl profiles/bench_configs_${R}_c3.jsonl
 cp gpurun_out/${TAG}_bench_configs_c5.jsonl profiles/bench_configs_${R}_c5.jsonl
 cp gpurun_out/${TAG}_pytest.log profiles/pytest_gpu_${R}.log
-for s in pt_gs_k pt_hs_k hbv_stack; do [ -f gpurun_out/e2e_census_$s.json ] && cp gpurun_out/e2e_census_$s.json profiles/e2e_census_${R}_$s.json; done
+for s in pt_gs_k pt_hs_k hbv_stack pt_ss_k pt_hps_k; do [ -f gpurun_out/e2e_census_$s.json ] && cp gpurun_out/e2e_census_$s.json profiles/e2e_census_${R}_$s.json; done
 ls profiles | grep ${R}
