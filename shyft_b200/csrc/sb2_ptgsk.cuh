@@ -844,39 +844,50 @@ inline void fill_dopri_products(double dt_hours, double* dtb) {
 // loop is one try_step of every lane that is still running (finished lanes recompute their last try and discard it), so the
 // Runge-Kutta stages and their 14 exponentials sit in uniform control flow -- no per-lane loop, no call -- and each lane still
 // follows exactly the accept / reject sequence of kirchner_step above (bit-identical; tests/test_gpu_units.py).
-__device__ __forceinline__ double kirchner_rhs_flat(double c1, double c2, double c3, double pe, double x) {
+// DEFER: an argument outside the fast range of exp only raises `out_of_range` (the caller then repeats the whole try with DEFER = false):
+// the seven stages of a try are then straight-line code without a call, and the polynomial and tableau constants can stay where they are
+// between the stages instead of being fetched again after every (never taken) call site
+template <bool DEFER = false>
+__device__ __forceinline__ double kirchner_rhs_flat(double c1, double c2, double c3, double pe, double x, bool& out_of_range) {
     // both exponentials through one range test, so that the two polynomials interleave
     const double a = c1 + c2 * x + c3 * x * x;
     int ea, ex_;
     const double va = sb_exp_core<true>(a, ea), vx = sb_exp_core<true>(-x, ex_);
     double g = sb_scale2(va, ea);
     double ex = sb_scale2(vx, ex_);
-    if (!(fabs(a) < 690.0 && fabs(x) < 690.0)) { g = sb_exp_slow(a); ex = sb_exp_slow(-x); }
+    if (!(fabs(a) < 690.0 && fabs(x) < 690.0)) {
+        if (DEFER) out_of_range = true;
+        else { g = sb_exp_slow(a); ex = sb_exp_slow(-x); }
+    }
     const double h = g * (pe * ex - 1.0);
     return g >= kDopri[26] ? h : 0.0;
+}
+__device__ __forceinline__ double kirchner_rhs_flat(double c1, double c2, double c3, double pe, double x) {
+    bool unused = false;
+    return kirchner_rhs_flat<false>(c1, c2, c3, pe, x, unused);
 }
 // One try_step of the controlled stepper from (x, dxdt) with step dt: the seven stages, the error estimate's numerator and denominator.
 // UDT: dt is the same for every lane and its products with the tableau come from `dtb` (host-evaluated dt * b, the same IEEE products the
 // lane would form: (dt * b21) * dxdt is how `dt * b21 * dxdt` parses) -- the first try of every model step, i.e. > 99.9 % of all tries;
 // 26 fp64 multiplications less per step, and the products sit in the constant bank.
-template <bool UDT, class ARGS>
+template <bool UDT, bool DEFER, class ARGS>
 __device__ __forceinline__ void kirchner_try(const ARGS& ka, double dt, double c1, double c2, double c3, double pe, double x, double dxdt,
                                              double& x_new, double& dxdt_new, double& k3, double& k4, double& k5, double& k6, double& err_num,
-                                             double& err_den) {
+                                             double& err_den, bool& out_of_range) {
     const double eps_abs = 1.0e-7, eps_rel = 1.0e-8;
 #define SB2_DTB(k) (UDT ? ka.dtb[k] : dt * kDopri[k])
     double xt = 1.0 * x + SB2_DTB(0) * dxdt;
-    const double k2 = kirchner_rhs_flat(c1, c2, c3, pe, xt);
+    const double k2 = kirchner_rhs_flat<DEFER>(c1, c2, c3, pe, xt, out_of_range);
     xt = 1.0 * x + SB2_DTB(1) * dxdt + SB2_DTB(2) * k2;
-    k3 = kirchner_rhs_flat(c1, c2, c3, pe, xt);
+    k3 = kirchner_rhs_flat<DEFER>(c1, c2, c3, pe, xt, out_of_range);
     xt = 1.0 * x + SB2_DTB(3) * dxdt + SB2_DTB(4) * k2 + SB2_DTB(5) * k3;
-    k4 = kirchner_rhs_flat(c1, c2, c3, pe, xt);
+    k4 = kirchner_rhs_flat<DEFER>(c1, c2, c3, pe, xt, out_of_range);
     xt = 1.0 * x + SB2_DTB(6) * dxdt + SB2_DTB(7) * k2 + SB2_DTB(8) * k3 + SB2_DTB(9) * k4;
-    k5 = kirchner_rhs_flat(c1, c2, c3, pe, xt);
+    k5 = kirchner_rhs_flat<DEFER>(c1, c2, c3, pe, xt, out_of_range);
     xt = 1.0 * x + SB2_DTB(10) * dxdt + SB2_DTB(11) * k2 + SB2_DTB(12) * k3 + SB2_DTB(13) * k4 + SB2_DTB(14) * k5;
-    k6 = kirchner_rhs_flat(c1, c2, c3, pe, xt);
+    k6 = kirchner_rhs_flat<DEFER>(c1, c2, c3, pe, xt, out_of_range);
     x_new = 1.0 * x + SB2_DTB(15) * dxdt + SB2_DTB(16) * k3 + SB2_DTB(17) * k4 + SB2_DTB(18) * k5 + SB2_DTB(19) * k6;
-    dxdt_new = kirchner_rhs_flat(c1, c2, c3, pe, x_new);
+    dxdt_new = kirchner_rhs_flat<DEFER>(c1, c2, c3, pe, x_new, out_of_range);
     const double x_err = SB2_DTB(20) * dxdt + SB2_DTB(21) * k3 + SB2_DTB(22) * k4 + SB2_DTB(23) * k5 + SB2_DTB(24) * k6 + SB2_DTB(25) * dxdt_new;
 #undef SB2_DTB
     err_num = fabs(x_err);
@@ -934,12 +945,15 @@ __device__ __forceinline__ bool kirchner_step_warp(const ARGS& ka, double c1, do
         }
     };
     double x_new, dxdt_new, k3, k4, k5, k6, err_num, err_den;
+    bool out_of_range = false;
     if (UDT) {  // the first try: dt = t1 on every lane
-        kirchner_try<true>(ka, dt, c1, c2, c3, pe, x, dxdt, x_new, dxdt_new, k3, k4, k5, k6, err_num, err_den);
-        control(x_new, dxdt_new, k3, k4, k5, k6, err_num, err_den);
+        kirchner_try<true, true>(ka, dt, c1, c2, c3, pe, x, dxdt, x_new, dxdt_new, k3, k4, k5, k6, err_num, err_den, out_of_range);
+        // an argument out of the fast range on any lane: nothing is taken from this try, and the loop below repeats it (dt = t1 still, so
+        // the same products) with the full-range exp -- the same bits on the lanes that were in range
+        if (!__any_sync(0xffffffffu, out_of_range)) control(x_new, dxdt_new, k3, k4, k5, k6, err_num, err_den);
     }
     while (__any_sync(0xffffffffu, running)) {
-        kirchner_try<false>(ka, dt, c1, c2, c3, pe, x, dxdt, x_new, dxdt_new, k3, k4, k5, k6, err_num, err_den);
+        kirchner_try<false, false>(ka, dt, c1, c2, c3, pe, x, dxdt, x_new, dxdt_new, k3, k4, k5, k6, err_num, err_den, out_of_range);
         control(x_new, dxdt_new, k3, k4, k5, k6, err_num, err_den);
     }
     q = sb_exp_flat<true>(x);

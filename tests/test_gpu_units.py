@@ -155,6 +155,27 @@ def test_kirchner_first_try_with_host_evaluated_products_is_bit_identical(capi, 
     assert _bits_equal(capi.unit_eval("kirchner_step_warp", rows)[:, :2], want)
 
 
+def test_kirchner_first_try_out_of_the_fast_exp_range(capi, oracle):
+    """The first try defers arguments outside exp's fast range (|.| >= 690) to a repeat of the whole try with the full-range exp: warps that
+    mix such lanes (c1 around -700: g(q) underflows, the response is frozen) with ordinary ones give the oracle's bits on every lane.
+    (Only the underflow side: an overflowing g sends the reference's own controller into millions of sub-steps.)"""
+    rng = np.random.default_rng(23)
+    n = 32 * 32
+    q = np.exp(rng.uniform(np.log(1e-6), np.log(60.0), n))
+    p = rng.exponential(2.0, n) * (rng.random(n) < 0.5)
+    e = rng.uniform(0, 0.3, n)
+    c = np.tile(np.array([-2.439, 0.966, -0.10]), (n, 1))
+    wild = rng.random(n) < 0.2
+    wild[:32] = False                                # one warp without any, the rest mixed
+    c[wild] = np.stack([rng.uniform(-760, -690, wild.sum()), rng.uniform(-1, 1, wild.sum()), rng.uniform(-0.2, 0.2, wild.sum())], axis=1)
+    rows = np.concatenate([c, np.ones((n, 1)), q[:, None], p[:, None], e[:, None]], axis=1)
+    got = capi.unit_eval("kirchner_step_warp_udt", rows)
+    want = np.array([oracle.kirchner_step(q[i], p[i], e[i], c=tuple(c[i]))[:2] for i in range(n)])
+    assert wild.sum() > 100 and np.all(got[:, 2] == 1.0)
+    assert _bits_equal(got[:, :2], want)
+    assert _bits_equal(capi.unit_eval("kirchner_step_warp", rows)[:, :2], want)
+
+
 @pytest.mark.timeout(180)
 def test_warp_cooperative_corr_lwc_is_bit_identical(capi, oracle):
     """gs_corr_lwc_warp (lane borrowing): the lanes of a warp that need a search are paired with lanes that do not, P(a, x) and P(a + 1, x) of
