@@ -485,21 +485,33 @@ __device__ __forceinline__ void gs_reset_snow_pack(double& sca, double& lwc, dou
 // The addends of the energy balance that depend on the forcing (and parameters) only, gamma_snow.h:345-392: the long-wave term
 // and the turbulent / surface-emission term.  Evaluated per step inside the fused kernel, or for a whole window by
 // ptgsk_forcing_terms_kernel (no state involved); each is one addend of `effect`, so the sum keeps the reference's order.
+// The literals of the forcing-only formulas (vapour pressure, energy terms, Priestley-Taylor) as a __constant__ table: sm_100a has no
+// 64-bit immediate, so a double literal with a non-zero low word costs two UMOV per use (55 of the forcing-terms kernel's 420 instructions
+// per step, ncu), an entry of this table one LDCU.  The same literal text as the reference, hence the same bits.
+enum : int { K_VP_A = 0, K_VP_B, K_VP_C, K_VP_D, K_VP_E, K_VP_F, K_VP_G, K_VP_H, K_LW, K_LW_EXP, K_SST_A, K_SST_B, K_TURB_A, K_TURB_B, K_TURB_C,
+             K_SURF_A, K_SURF_B, K_KELVIN, K_PT_CK1, K_PT_PSYCR, K_PT_BOLZ, K_PT_CK2_NEG, K_PT_CK2_POS, K_PT_CK3_NEG, K_PT_CK3_POS, K_PT_EATM_A,
+             K_PT_EATM_EXP, K_PT_EATM_B, K_PT_EMIS, K_PHYS_N };
+__constant__ double kPhysC[K_PHYS_N] = {33.864, 7.38e-3, 0.8072, 1.9e-5, 1.8, 1.316e-3, 9.72e-3, 4.2e-5, 0.98 * 5.670373e-8, 6.87e-2, 1.16, 2.09, 1.7, 6.12, 6.132,
+                                        0.103, 0.186, 273.15, 0.610780, 0.066, 0.0000000567, 17.84362, 17.08085, 245.425, 234.175, 1.24,
+                                        0.143, 0.85, 0.98};
+#define SB2_K(name) kPhysC[name]
 __device__ __forceinline__ double gs_vapour_pressure(double T, double rel_hum) {
-    double vapour_pressure = 33.864 * (sb_pow8(7.38e-3 * T + 0.8072) - 1.9e-5 * fabs(1.8 * T + 48.0) + 1.316e-3) * rel_hum;
-    if (T < 0.0) vapour_pressure *= 1.0 + 9.72e-3 * T + 4.2e-5 * T * T;
+    // 33.864 * (pow(7.38e-3 * T + 0.8072, 8) - 1.9e-5 * fabs(1.8 * T + 48.0) + 1.316e-3) * rel_hum; T < 0: *= 1.0 + 9.72e-3 * T + 4.2e-5 * T * T
+    double vapour_pressure = SB2_K(K_VP_A) * (sb_pow8(SB2_K(K_VP_B) * T + SB2_K(K_VP_C)) - SB2_K(K_VP_D) * fabs(SB2_K(K_VP_E) * T + 48.0) + SB2_K(K_VP_F)) * rel_hum;
+    if (T < 0.0) vapour_pressure *= 1.0 + SB2_K(K_VP_G) * T + SB2_K(K_VP_H) * T * T;
     return vapour_pressure;
 }
 template <bool FLAT = false>
 __device__ __forceinline__ void gs_energy_terms(const PtgskParam& p, double BB0, double T, double wind_speed, double rel_hum, double& lw, double& tadd) {
-    const double tol = 1.0e-10, sigma = 5.670373e-8;
-    const double T_k = T + 273.15;
+    const double tol = 1.0e-10;
+    // the reference's literals through kPhysC (the exponents of pow stay literals: its exact cases fold away at compile time): 273.15; 0.98 * sigma, 6.87e-2; 1.16, 2.09; 1.7, 6.12; 6.132, 0.103, 0.186
+    const double T_k = T + SB2_K(K_KELVIN);
     const double turb = p.wind_scale * wind_speed + p.wind_const;
     const double vapour_pressure = gs_vapour_pressure(T, rel_hum);
-    lw = 0.98 * sigma * (FLAT ? sb_pow_flat<true>(vapour_pressure / T_k, 6.87e-2) : sb_pow<true>(vapour_pressure / T_k, 6.87e-2)) * sb_pow4(T_k);
-    const double sst = dmin(0.0, 1.16 * T - 2.09);
-    if (sst > -tol) tadd = turb * (T + 1.7 * (vapour_pressure - 6.12)) - BB0;
-    else tadd = turb * (T - sst + 1.7 * (vapour_pressure - 6.132 * (FLAT ? sb_exp_flat<true>(0.103 * T - 0.186) : sb_exp<true>(0.103 * T - 0.186)))) - 0.98 * sigma * sb_pow4(sst + 273.15);
+    lw = SB2_K(K_LW) * (FLAT ? sb_pow_flat<true>(vapour_pressure / T_k, 6.87e-2) : sb_pow<true>(vapour_pressure / T_k, 6.87e-2)) * sb_pow4(T_k);
+    const double sst = dmin(0.0, SB2_K(K_SST_A) * T - SB2_K(K_SST_B));
+    if (sst > -tol) tadd = turb * (T + SB2_K(K_TURB_A) * (vapour_pressure - SB2_K(K_TURB_B))) - BB0;
+    else tadd = turb * (T - sst + SB2_K(K_TURB_A) * (vapour_pressure - SB2_K(K_TURB_C) * (FLAT ? sb_exp_flat<true>(SB2_K(K_SURF_A) * T - SB2_K(K_SURF_B)) : sb_exp<true>(SB2_K(K_SURF_A) * T - SB2_K(K_SURF_B))))) - SB2_K(K_LW) * sb_pow4(sst + SB2_K(K_KELVIN));
 }
 
 // Division sites of the step body: in line (default) or through one shared out-of-line copy (SB2_GS_DIV_CALL=1, a smaller per-step code
@@ -683,17 +695,19 @@ __device__ __forceinline__ void gs_step_core(GsState& s, GsCache& cache, double&
 template <bool FLAT = false>
 __device__ __forceinline__ double pt_potential_evapotranspiration(double land_albedo, double alpha, double temperature, double global_radiation,
                                                                   double rhumidity) {
-    const double ck1 = 0.610780, psycr = 0.066, bolz = 0.0000000567;
+    // ck1 = 0.610780, psycr = 0.066, bolz = 0.0000000567; ck2 = 17.84362 / 17.08085 and ck3 = 245.425 / 234.175 below / above freezing (kPhysC)
+    const double ck1 = SB2_K(K_PT_CK1), psycr = SB2_K(K_PT_PSYCR), bolz = SB2_K(K_PT_BOLZ);
     const bool neg = temperature < 0;
-    const double ck2 = neg ? 17.84362 : 17.08085;
-    const double ck3 = neg ? 245.425 : 234.175;
+    const double ck2 = neg ? SB2_K(K_PT_CK2_NEG) : SB2_K(K_PT_CK2_POS);
+    const double ck3 = neg ? SB2_K(K_PT_CK3_NEG) : SB2_K(K_PT_CK3_POS);
     const double ctt_inv = 1 / (ck3 + temperature);
     const double sat_pressure = ck1 * (FLAT ? sb_exp_flat<true>(ck2 * temperature * ctt_inv) : sb_exp<true>(ck2 * temperature * ctt_inv));
     const double delta = sat_pressure * ck2 * ck3 * ctt_inv * ctt_inv;
     const double vapour_pressure = sat_pressure * rhumidity;
-    const double k_temp = temperature + 273.15;
-    const double e_atm = 1.24 * (FLAT ? sb_pow_flat<true>(10 * vapour_pressure / k_temp, 0.143) : sb_pow<true>(10 * vapour_pressure / k_temp, 0.143)) * (0.85 + 0.5 * rhumidity);
-    const double net_radiation = bolz * sb_pow4(k_temp) * (e_atm - 0.98) + global_radiation * (1.0 - land_albedo);
+    const double k_temp = temperature + SB2_K(K_KELVIN);
+    // 1.24 * pow(10 * vapour_pressure / k_temp, 0.143) * (0.85 + 0.5 * rhumidity);  ... (e_atm - 0.98)
+    const double e_atm = SB2_K(K_PT_EATM_A) * (FLAT ? sb_pow_flat<true>(10 * vapour_pressure / k_temp, 0.143) : sb_pow<true>(10 * vapour_pressure / k_temp, 0.143)) * (SB2_K(K_PT_EATM_B) + 0.5 * rhumidity);
+    const double net_radiation = bolz * sb_pow4(k_temp) * (e_atm - SB2_K(K_PT_EMIS)) + global_radiation * (1.0 - land_albedo);
     const double epot = alpha * delta * net_radiation / (delta + psycr);
     if (epot < 0.0) return 0.0;
     return epot / (2500780 - 2361 * temperature);

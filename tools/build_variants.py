@@ -26,6 +26,7 @@ VARIANTS = {
     "A8": ["-DSB2_MINBLOCKS_A=8"], "A9": ["-DSB2_MINBLOCKS_A=9"], "A10": ["-DSB2_MINBLOCKS_A=10"], "As4": ["-DSB2_STEPS_A=4"], "As16": ["-DSB2_STEPS_A=16"],
     "hbvus0": ["-DSB2_HBV_UNIT_STEPS=0"], "hbvus32": ["-DSB2_HBV_UNIT_STEPS=32"], "hbvus128": ["-DSB2_HBV_UNIT_STEPS=128"],
     "lwcpair": ["-DSB2_LWC_PAIR=1"],
+    "norpB": ["-DSB2_REG_PREFETCH_B=0"], "norpC": ["-DSB2_REG_PREFETCH_C=0"], "norpBC": ["-DSB2_REG_PREFETCH_B=0", "-DSB2_REG_PREFETCH_C=0"],
     "pf0": ["-DSB2_PREFETCH_AHEAD=0"], "pf2": ["-DSB2_PREFETCH_AHEAD=2"], "pf8": ["-DSB2_PREFETCH_AHEAD=8"],
 }
 out_dir = os.path.join(_build.ROOT, "build")
