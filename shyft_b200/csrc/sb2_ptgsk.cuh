@@ -139,8 +139,18 @@ __device__ __forceinline__ void gs_cache_store(GsCache& c, double alpha, double 
     SB2_CK_STORAGE(c) = storage; SB2_CK_SCA(c) = sca;
 }
 
-__device__ __forceinline__ double mmh_to_m3s(double mmh, double area) { return area * mmh * (1 / (3600.0 * 1000.0)); }
-__device__ __forceinline__ double m3s_to_mmh(double m3s, double area) { return m3s / ((1 / (3600.0 * 1000.0)) * area); }
+// The literals of the step formulas (vapour pressure, energy terms, Priestley-Taylor, unit conversions, tolerances) as a __constant__ table: sm_100a has no
+// 64-bit immediate, so a double literal with a non-zero low word costs two UMOV per use (55 of the forcing-terms kernel's 420 instructions
+// per step, ncu), an entry of this table one LDCU.  The same literal text as the reference, hence the same bits.
+enum : int { K_VP_A = 0, K_VP_B, K_VP_C, K_VP_D, K_VP_E, K_VP_F, K_VP_G, K_VP_H, K_LW, K_LW_EXP, K_SST_A, K_SST_B, K_TURB_A, K_TURB_B, K_TURB_C,
+             K_SURF_A, K_SURF_B, K_KELVIN, K_PT_CK1, K_PT_PSYCR, K_PT_BOLZ, K_PT_CK2_NEG, K_PT_CK2_POS, K_PT_CK3_NEG, K_PT_CK3_POS, K_PT_EATM_A,
+             K_PT_EATM_EXP, K_PT_EATM_B, K_PT_EMIS, K_MMH_M3S, K_TOL, K_EPS_ABS, K_EPS_REL, K_Q_MIN, K_GM, K_PHYS_N };
+__constant__ double kPhysC[K_PHYS_N] = {33.864, 7.38e-3, 0.8072, 1.9e-5, 1.8, 1.316e-3, 9.72e-3, 4.2e-5, 0.98 * 5.670373e-8, 6.87e-2, 1.16, 2.09, 1.7, 6.12, 6.132,
+                                        0.103, 0.186, 273.15, 0.610780, 0.066, 0.0000000567, 17.84362, 17.08085, 245.425, 234.175, 1.24,
+                                        0.143, 0.85, 0.98, 1 / (3600.0 * 1000.0), 1.0e-10, 1.0e-7, 1.0e-8, 0.00001, 0.001 / 86400.0};
+#define SB2_K(name) kPhysC[name]
+__device__ __forceinline__ double mmh_to_m3s(double mmh, double area) { return area * mmh * SB2_K(K_MMH_M3S); }  // 1 / (3600.0 * 1000.0)
+__device__ __forceinline__ double m3s_to_mmh(double m3s, double area) { return m3s / (SB2_K(K_MMH_M3S) * area); }
 
 // ---- gamma_snow ---------------------------------------------------------------------------------
 // calc_q, gamma_snow.h:209-212
@@ -485,16 +495,6 @@ __device__ __forceinline__ void gs_reset_snow_pack(double& sca, double& lwc, dou
 // The addends of the energy balance that depend on the forcing (and parameters) only, gamma_snow.h:345-392: the long-wave term
 // and the turbulent / surface-emission term.  Evaluated per step inside the fused kernel, or for a whole window by
 // ptgsk_forcing_terms_kernel (no state involved); each is one addend of `effect`, so the sum keeps the reference's order.
-// The literals of the forcing-only formulas (vapour pressure, energy terms, Priestley-Taylor) as a __constant__ table: sm_100a has no
-// 64-bit immediate, so a double literal with a non-zero low word costs two UMOV per use (55 of the forcing-terms kernel's 420 instructions
-// per step, ncu), an entry of this table one LDCU.  The same literal text as the reference, hence the same bits.
-enum : int { K_VP_A = 0, K_VP_B, K_VP_C, K_VP_D, K_VP_E, K_VP_F, K_VP_G, K_VP_H, K_LW, K_LW_EXP, K_SST_A, K_SST_B, K_TURB_A, K_TURB_B, K_TURB_C,
-             K_SURF_A, K_SURF_B, K_KELVIN, K_PT_CK1, K_PT_PSYCR, K_PT_BOLZ, K_PT_CK2_NEG, K_PT_CK2_POS, K_PT_CK3_NEG, K_PT_CK3_POS, K_PT_EATM_A,
-             K_PT_EATM_EXP, K_PT_EATM_B, K_PT_EMIS, K_PHYS_N };
-__constant__ double kPhysC[K_PHYS_N] = {33.864, 7.38e-3, 0.8072, 1.9e-5, 1.8, 1.316e-3, 9.72e-3, 4.2e-5, 0.98 * 5.670373e-8, 6.87e-2, 1.16, 2.09, 1.7, 6.12, 6.132,
-                                        0.103, 0.186, 273.15, 0.610780, 0.066, 0.0000000567, 17.84362, 17.08085, 245.425, 234.175, 1.24,
-                                        0.143, 0.85, 0.98};
-#define SB2_K(name) kPhysC[name]
 __device__ __forceinline__ double gs_vapour_pressure(double T, double rel_hum) {
     // 33.864 * (pow(7.38e-3 * T + 0.8072, 8) - 1.9e-5 * fabs(1.8 * T + 48.0) + 1.316e-3) * rel_hum; T < 0: *= 1.0 + 9.72e-3 * T + 4.2e-5 * T * T
     double vapour_pressure = SB2_K(K_VP_A) * (sb_pow8(SB2_K(K_VP_B) * T + SB2_K(K_VP_C)) - SB2_K(K_VP_D) * fabs(SB2_K(K_VP_E) * T + 48.0) + SB2_K(K_VP_F)) * rel_hum;
@@ -503,7 +503,7 @@ __device__ __forceinline__ double gs_vapour_pressure(double T, double rel_hum) {
 }
 template <bool FLAT = false>
 __device__ __forceinline__ void gs_energy_terms(const PtgskParam& p, double BB0, double T, double wind_speed, double rel_hum, double& lw, double& tadd) {
-    const double tol = 1.0e-10;
+    const double tol = SB2_K(K_TOL);  // 1.0e-10
     // the reference's literals through kPhysC (the exponents of pow stay literals: its exact cases fold away at compile time): 273.15; 0.98 * sigma, 6.87e-2; 1.16, 2.09; 1.7, 6.12; 6.132, 0.103, 0.186
     const double T_k = T + SB2_K(K_KELVIN);
     const double turb = p.wind_scale * wind_speed + p.wind_const;
@@ -539,7 +539,7 @@ __device__ __forceinline__ void gs_step_core(GsState& s, GsCache& cache, double&
                                              int sec_of_year, double dt_seconds, double dt_us, const GsStepConst& k, double BB0, double T, double rad,
                                              double prec_mm_h, double lw, double tadd, const double* __restrict__ f_wind_speed, const double* __restrict__ f_rel_hum,
                                              int64_t f_offset, const InvDivisor& inv_cv2) {
-    const double tol = 1.0e-10;
+    const double tol = SB2_K(K_TOL);  // 1.0e-10
     const double melt_heat = 333660.0, water_heat = 4180.0, ice_heat = 2050.0;
     double sdc_melt_mean = s.sdc_melt_mean;
     double acc_melt = s.acc_melt;
@@ -765,8 +765,8 @@ __device__ __noinline__ double kirchner_calc_state(double x_old, double dtl, dou
 // (abs 1e-7, rel 1e-8): same accept/reject sequence, same step-size updates, same continuous extension.
 template <bool INL = false>
 __device__ __forceinline__ bool kirchner_step(double c1, double c2, double c3, double t1, double& q, double& q_avg, double p, double e) {
-    const double eps_abs = 1.0e-7, eps_rel = 1.0e-8;
-    if (q < 0.00001) q = 0.00001;
+    const double eps_abs = SB2_K(K_EPS_ABS), eps_rel = SB2_K(K_EPS_REL);  // 1.0e-7, 1.0e-8
+    if (q < SB2_K(K_Q_MIN)) q = SB2_K(K_Q_MIN);  // 0.00001
     double x = INL ? sb_log_inl<true>(q) : sb_log<true>(q);
     double t = 0.0, dt = t1;
     const KirchnerRhs<INL> rhs{c1, c2, c3, p - e};
@@ -888,7 +888,7 @@ template <bool UDT, bool DEFER, class ARGS>
 __device__ __forceinline__ void kirchner_try(const ARGS& ka, double dt, double c1, double c2, double c3, double pe, double x, double dxdt,
                                              double& x_new, double& dxdt_new, double& k3, double& k4, double& k5, double& k6, double& err_num,
                                              double& err_den, bool& out_of_range) {
-    const double eps_abs = 1.0e-7, eps_rel = 1.0e-8;
+    const double eps_abs = SB2_K(K_EPS_ABS), eps_rel = SB2_K(K_EPS_REL);  // 1.0e-7, 1.0e-8
 #define SB2_DTB(k) (UDT ? ka.dtb[k] : dt * kDopri[k])
     double xt = 1.0 * x + SB2_DTB(0) * dxdt;
     const double k2 = kirchner_rhs_flat<DEFER>(c1, c2, c3, pe, xt, out_of_range);
@@ -912,7 +912,7 @@ __device__ __forceinline__ void kirchner_try(const ARGS& ka, double dt, double c
 template <bool UDT, class ARGS>
 __device__ __forceinline__ bool kirchner_step_warp(const ARGS& ka, double c1, double c2, double c3, double t1, double& q, double& q_avg,
                                                    double p, double e) {
-    if (q < 0.00001) q = 0.00001;
+    if (q < SB2_K(K_Q_MIN)) q = SB2_K(K_Q_MIN);  // 0.00001
     double x = sb_log_inl<true>(q);
     double t = 0.0, dt = t1;
     const double pe = p - e;
@@ -1303,10 +1303,10 @@ __global__ void __launch_bounds__(SB2_BLOCK_C, SB2_MINBLOCKS_C) ptgsk_response_k
             // glacier_melt::step, glacier_melt.h:47-52
             const double sca_m2 = cell_area_m2 * sca;
             const double gm_melt_m3s =
-                (glacier_area_m2 <= sca_m2 || temp <= 0.0) ? 0.0 : gm_dtf * temp * (glacier_area_m2 - sca_m2) * (0.001 / 86400.0);
+                (glacier_area_m2 <= sca_m2 || temp <= 0.0) ? 0.0 : gm_dtf * temp * (glacier_area_m2 - sca_m2) * SB2_K(K_GM);  // 0.001 / 86400.0
             // actual_evapotranspiration::calculate_step, actual_evapotranspiration.h:56-62
             const double ae = pot * (1.0 - sb_exp_flat<true>(div_by(-kq * 3.0, inv_ae))) * (1.0 - dmax(sca, glacier_fraction));
-            const double gm_mmh = div_pos(gm_melt_m3s, (1 / (3600.0 * 1000.0)) * cell_area_m2);  // m3s_to_mmh; mostly 0 / x (no melt)
+            const double gm_mmh = div_pos(gm_melt_m3s, SB2_K(K_MMH_M3S) * cell_area_m2);  // m3s_to_mmh; mostly 0 / x (no melt)
             double q_avg, kq_new = active ? kq : 1.0;
             const double k_in = outflow * snow_storage_fraction + prec * kirchner_routed_prec + gm_routed * gm_mmh;
             if (!kirchner_step_warp<true>(a, c1, c2, c3, a.dt_hours, kq_new, q_avg, active ? k_in : 0.0, active ? ae : 0.0)) {

@@ -362,9 +362,9 @@ __global__ void __launch_bounds__(128, 4) pthpsk_run_kernel(const __grid_constan
             if (a.collect & 8) collect_state(orow);
             if (!hps_step(hs, snow_outflow, r_sca, r_storage, p, a.dt_seconds, a.dt_us, a.bb0, a.inv_dt_seconds, temp, rad, prec, wind, rel_hum)) failed_snow = true;
             const double sca_m2 = cell_area_m2 * hs.sca;
-            gm_melt_m3s = (glacier_area_m2 <= sca_m2 || temp <= 0.0) ? 0.0 : p.gm_dtf * temp * (glacier_area_m2 - sca_m2) * (0.001 / 86400.0);
+            gm_melt_m3s = (glacier_area_m2 <= sca_m2 || temp <= 0.0) ? 0.0 : p.gm_dtf * temp * (glacier_area_m2 - sca_m2) * SB2_K(K_GM);  // 0.001 / 86400.0
             pot = pt_potential_evapotranspiration<true>(p.pt_albedo, p.pt_alpha, temp, rad, rel_hum) * 3600.0;
-            gm_mmh = div_pos(gm_melt_m3s, (1 / (3600.0 * 1000.0)) * cell_area_m2);
+            gm_mmh = div_pos(gm_melt_m3s, SB2_K(K_MMH_M3S) * cell_area_m2);
             ae = pot * (1.0 - sb_exp_flat<true>(div_by(-kq * 3.0, p.inv_ae_scale))) * (1.0 - dmax(hs.sca, glacier_fraction));
         }
         double q_avg, kq_new = active ? kq : 1.0;

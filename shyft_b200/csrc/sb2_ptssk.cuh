@@ -431,9 +431,9 @@ __global__ void __launch_bounds__(128, 4) ptssk_run_kernel(const __grid_constant
             ss_step(p, a.dt_hours, a.step_in_days, a.inv_dt_hours, temp, prec, ss, snow_outflow, r_sca, r_swe, bad);
             failed_snow = failed_snow || bad;
             const double sca_m2 = cell_area_m2 * ss.sca;
-            gm_melt_m3s = (glacier_area_m2 <= sca_m2 || temp <= 0.0) ? 0.0 : p.gm_dtf * temp * (glacier_area_m2 - sca_m2) * (0.001 / 86400.0);
+            gm_melt_m3s = (glacier_area_m2 <= sca_m2 || temp <= 0.0) ? 0.0 : p.gm_dtf * temp * (glacier_area_m2 - sca_m2) * SB2_K(K_GM);  // 0.001 / 86400.0
             pot = pt_potential_evapotranspiration<true>(p.pt_albedo, p.pt_alpha, temp, rad, rel_hum) * 3600.0;
-            gm_mmh = div_pos(gm_melt_m3s, (1 / (3600.0 * 1000.0)) * cell_area_m2);
+            gm_mmh = div_pos(gm_melt_m3s, SB2_K(K_MMH_M3S) * cell_area_m2);
             ae = pot * (1.0 - sb_exp_flat<true>(div_by(-kq * 3.0, p.inv_ae_scale))) * (1.0 - dmax(ss.sca, glacier_fraction));
         }
         double q_avg, kq_new = active ? kq : 1.0;
