@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--cells", type=int, default=0, help="cells per GPU (default: 100 000 on one GPU = configs[1]; 1 000 000 / N on N GPUs = configs[3])")
     ap.add_argument("--years", type=float, default=10.0)
     ap.add_argument("--stations", type=int, default=64)
-    ap.add_argument("--window", type=int, default=2048, help="time steps per forcing window (measured: 512 -> 7.68, 1024 -> 7.90, 2048 -> 7.96 G cell-steps/s)")
+    ap.add_argument("--window", type=int, default=4096, help="time steps per forcing window (round 2, with one launch set per window: 2048 -> 9.54, 4096 -> 9.62 G cell-steps/s)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU work of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle legs (cpu_baseline and config.parity_check)")
     a = ap.parse_args()
@@ -55,7 +55,7 @@ def parse():
     a.cells_given = a.cells > 0
     if not a.cells_given:
         a.cells = 100000 if world == 1 else 1000000 // world
-    # window buffers: keep cells x window at what 100 000 cells x 2 048 steps take (16 GB of forcing + series per GPU)
+    # window buffers: keep cells x window at what 100 000 cells x 4 096 steps take (33 GB of forcing + series and 16 GB of scratch per GPU)
     a.window = max(256, min(a.window, (a.window * 100000 // a.cells) // 64 * 64))
     return a
 

@@ -1025,8 +1025,12 @@ __device__ __forceinline__ void prefetch_l1(const double* p) { asm volatile("pre
 #define SB2_MINBLOCKS_C 16
 #endif
 
-// no minimum-blocks bound: left to itself the compiler settles on 72 registers (28 resident warps); (128, 1) lets it take 94 and costs
-// 2.4 ms per year, (128, 8..10) = 64..48 registers measured no gain (tools/build_variants.py A8..A10)
+// (128, 10): 48 registers, no stack.  Round 1's version settled on 72 registers without a bound; with the running offsets and the constant
+// table of round 2 the unbounded build takes 40 registers and 8 bytes of stack -- 8, 9, 10 blocks and no bound all measure the same
+// (tools/build_variants.py A8..A10), (128, 1) = 94 registers costs 2.4 ms per year
+#ifndef SB2_MINBLOCKS_A
+#define SB2_MINBLOCKS_A 10
+#endif
 template <bool UPAR>
 #ifdef SB2_MINBLOCKS_A
 __global__ void __launch_bounds__(SB2_BLOCK_A, SB2_MINBLOCKS_A) ptgsk_forcing_terms_kernel(const __grid_constant__ PtgskRunArgs a) {

@@ -6,7 +6,7 @@ cp gpurun_out/${TAG}_bench_reference_arm.json profiles/bench_${R}_reference_arm.
 cp gpurun_out/${TAG}_launches.csv profiles/launches_${R}.csv
 python tools/launch_summary.py gpurun_out/${TAG}_launches.csv > profiles/launches_${R}_summary.txt
 python tools/ncu_summary.py gpurun_out/${TAG}_pipeline.ncu-rep profiles/ncu_pipeline_${R}_shipped.txt
-python tools/ncu_pipeline_json.py gpurun_out/${TAG}_pipeline.ncu-rep 100000 1024 profiles/ncu_pipeline_${R}_shipped.json
+python tools/ncu_pipeline_json.py gpurun_out/${TAG}_pipeline.ncu-rep 100000 4096 profiles/ncu_pipeline_${R}_shipped.json
 python tools/ncu_summary.py gpurun_out/${TAG}_dense_apply.ncu-rep profiles/ncu_dense_apply_${R}.txt
 for f in gpurun_out/${TAG}_hbv*.ncu-rep; do b=$(basename $f .ncu-rep); python tools/ncu_summary.py $f profiles/ncu_${b#${TAG}_}_${R}.txt; done
 cp gpurun_out/${TAG}_bench_configs_c3.jsonl profiles/bench_configs_${R}_c3.jsonl

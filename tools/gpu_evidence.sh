@@ -15,7 +15,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --c
    python bench.py --years 1 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/${TAG}_ncu_launch.log 2>&1; echo "ncu launches rc $?"
 fi
 if [[ $PART == *b* ]]; then
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:ptgsk_ --launch-skip 6 --launch-count 3 -f -o gpurun_out/${TAG}_pipeline \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:ptgsk_ --launch-skip 3 --launch-count 3 -f -o gpurun_out/${TAG}_pipeline \
    python bench.py --years 1 --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/${TAG}_ncu_pipeline.log 2>&1; echo "ncu pipeline rc $?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:dense_apply --launch-skip 10 --launch-count 3 -f -o gpurun_out/${TAG}_dense_apply \
    python bench.py --years 1 --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/${TAG}_ncu_dense.log 2>&1; echo "ncu dense rc $?"
