@@ -45,13 +45,13 @@ struct Error : std::runtime_error { using std::runtime_error::runtime_error; };
 
 thread_local std::string g_create_error;
 
-// Freed device buffers of >= 1 MB are parked (per device, by size, up to 12 GB) and handed back to the next allocation of the same
+// Freed device buffers of >= 1 MB are parked (per device, by size, up to 40 % of the device memory) and handed back to the next allocation of the same
 // size: re-initialising a model's environment drops and re-creates GB-sized windows, and cudaFree / cudaMalloc of those cost
 // ~150 ms per run_interpolation + run_cells cycle (bench.py e2e leg).  A failed cudaMalloc empties the pool and retries.
 struct DevicePool {
     std::mutex mu;
     std::map<std::pair<int, size_t>, std::vector<void*>> parked;
-    size_t parked_bytes = 0;
+    size_t parked_bytes = 0, limit = 0;
     static DevicePool& get() { static DevicePool p; return p; }
     void* take(size_t bytes) {
         int dev = 0;
@@ -70,7 +70,11 @@ struct DevicePool {
         cudaGetDevice(&dev);
         cudaDeviceSynchronize();  // what cudaFree would do: nothing in flight may still touch the buffer when another stream takes it
         std::lock_guard<std::mutex> g(mu);
-        if (parked_bytes + bytes > (12ULL << 30)) return false;
+        if (limit == 0) {  // 40 % of the device's memory (72 GB on a B200: the window buffers and scratch of a 4 096-step window are 50 GB)
+            size_t free_b = 0, total_b = 0;
+            limit = (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b > 0) ? total_b / 5 * 2 : (12ULL << 30);
+        }
+        if (parked_bytes + bytes > limit) return false;
         parked[{dev, bytes}].push_back(p);
         parked_bytes += bytes;
         return true;
