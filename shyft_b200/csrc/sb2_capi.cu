@@ -536,7 +536,7 @@ void launch_step_range(sb2_model* m, int64_t first, int64_t n_steps, bool collec
     // chunks of equal length (a whole number of time slices each) rather than full ones and a remainder
     const int64_t n_chunks = std::max<int64_t>(1, (n_steps + m->partial_steps - 1) / m->partial_steps);
     int64_t even = (n_steps + n_chunks - 1) / n_chunks;
-    even = std::min<int64_t>(m->partial_steps, (even + 63) / 64 * 64);
+    even = std::min<int64_t>(m->partial_steps, (even + 127) / 128 * 128);
     for (int64_t done = 0; done < n_steps; done += even) {
         const int chunk = int(std::min<int64_t>(even, n_steps - done));
         const int64_t s0 = first + done;
