@@ -86,7 +86,7 @@ struct HpsRunArgs {
 struct HpsState { double sp[HBV_NB], sw[HBV_NB], albedo[HBV_NB], iso[HBV_NB], surface_heat, swe, sca; };
 
 // hbv_physical_snow::calculator::step (:266-529).  Returns false on "Negative outflow".
-__device__ __noinline__ bool hps_step(HpsState& s, double& r_outflow, double& r_sca, double& r_storage, const HpsParam& p, double dt_seconds, double dt_us,
+__device__ __forceinline__ bool hps_step(HpsState& s, double& r_outflow, double& r_sca, double& r_storage, const HpsParam& p, double dt_seconds, double dt_us,
                                       double BB0, const InvDivisor& inv_dt_seconds, double T, double rad, double prec_mm_h, double wind_speed,
                                       double rel_hum) {
     const double tol = 1.0e-10;
@@ -274,7 +274,10 @@ __device__ __noinline__ bool hps_step(HpsState& s, double& r_outflow, double& r_
     return ok;
 }
 
-__global__ void __launch_bounds__(128, 4) pthpsk_run_kernel(const __grid_constant__ HpsRunArgs a) {
+#ifndef SB2_HPS_MINBLOCKS
+#define SB2_HPS_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(128, SB2_HPS_MINBLOCKS) pthpsk_run_kernel(const __grid_constant__ HpsRunArgs a) {
     sb_math_stage_tables();
     int64_t group = blockIdx.x;
     int i_begin = 0, i_end = a.n_steps, slice = 0;
