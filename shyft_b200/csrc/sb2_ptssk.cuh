@@ -224,7 +224,7 @@ __device__ __noinline__ void ss_compute_shape_vars(double alpha_0, double d_rang
 struct SsState { double nu, alpha, sca, swe, free_water, residual; unsigned long long num_units; };
 
 // calculator::step, skaugen.h:150-339 -> outflow [mm/h], response sca and swe (over the cell); `bad` where the reference would throw
-__device__ __noinline__ void ss_step(const SskParam& p, double dt_hours, double step_in_days, const InvDivisor& inv_dt_hours, double T, double prec_mm_h,
+__device__ __forceinline__ void ss_step(const SskParam& p, double dt_hours, double step_in_days, const InvDivisor& inv_dt_hours, double T, double prec_mm_h,
                                      SsState& s, double& r_outflow, double& r_sca, double& r_swe, bool& bad) {
     const double snow_tol = 1.0e-10;
     const double unit_size = p.unit_size;
