@@ -1119,11 +1119,14 @@ __global__ void __launch_bounds__(SB2_BLOCK_B, SB2_MINBLOCKS_B) ptgsk_snow_kerne
     const int64_t out_shift = (a.first_step - a.out_first_step) * n;  // collected series: row of step i = local row + this (uniform)
     const int2* __restrict__ ds_row = a.day_sec_of_year + a.first_step;
     double f_t = a.f[0][o], f_p = a.f[1][o], f_r = a.f[2][o], f_lw = s_lw[o], f_ta = s_tadd[o];
+    int2 f_ds = ds_row[i_begin];  // day / second of year: the step starts with a test on it, so it travels one step ahead like the forcing
     for (int i = i_begin; i < i_end; ++i, o += n) {
 #if !SB2_REG_PREFETCH_B
         f_t = a.f[0][o]; f_p = a.f[1][o]; f_r = a.f[2][o]; f_lw = s_lw[o]; f_ta = s_tadd[o];
 #endif
         const double temp = f_t, prec = f_p * p.p_corr_scale_factor, rad = f_r, lw = f_lw, tadd = f_ta;
+        const int2 ds = f_ds;
+        if (i + 1 < i_end) f_ds = ds_row[i + 1];
         if (SB2_REG_PREFETCH_B && i + 1 < i_end) {
             const int64_t o1 = o + n;
             f_t = a.f[0][o1]; f_p = a.f[1][o1]; f_r = a.f[2][o1]; f_lw = s_lw[o1]; f_ta = s_tadd[o1];
@@ -1144,7 +1147,6 @@ __global__ void __launch_bounds__(SB2_BLOCK_B, SB2_MINBLOCKS_B) ptgsk_snow_kerne
             a.st[8][orow] = gs.temp_swe * snow_storage_fraction;
         }
         double sca, storage, outflow;
-        const int2 ds = ds_row[i];
         gs_step_core<(SB2_SNOW_FLAT != 0)>(gs, cache, sca, storage, outflow, p, ds.x, ds.y, a.dt_seconds, a.dt_us, gk, a.bb0, temp, rad,
                                            prec, lw, tadd, a.f[3], a.f[4], o, inv_cv2);
         s_outflow[o] = outflow;
