@@ -1025,11 +1025,11 @@ __device__ __forceinline__ void prefetch_l1(const double* p) { asm volatile("pre
 #define SB2_MINBLOCKS_C 16
 #endif
 
-// (128, 10): 48 registers, no stack.  Round 1's version settled on 72 registers without a bound; with the running offsets and the constant
-// table of round 2 the unbounded build takes 40 registers and 8 bytes of stack -- 8, 9, 10 blocks and no bound all measure the same
-// (tools/build_variants.py A8..A10), (128, 1) = 94 registers costs 2.4 ms per year
+// (128, 8): 63 registers, no stack, with the next step's inputs held in registers (SB2_REG_PREFETCH_A; at (128, 10) = 48 registers the
+// prefetch spills and costs 1.5 %).  Without the prefetch 8, 9, 10 blocks and no bound all measure the same (tools/build_variants.py A8..A10),
+// (128, 1) = 94 registers costs 2.4 ms per year.
 #ifndef SB2_MINBLOCKS_A
-#define SB2_MINBLOCKS_A 10
+#define SB2_MINBLOCKS_A 8
 #endif
 template <bool UPAR>
 #ifdef SB2_MINBLOCKS_A
@@ -1051,9 +1051,18 @@ __global__ void __launch_bounds__(SB2_BLOCK_A) ptgsk_forcing_terms_kernel(const 
     const int i0 = blockIdx.y * SB2_STEPS_A;
     const int i1 = min(i0 + SB2_STEPS_A, a.n_steps);
     int64_t o = (int64_t)i0 * n + c;
+#ifndef SB2_REG_PREFETCH_A
+#define SB2_REG_PREFETCH_A 1   // the next step's four inputs loaded before this step is evaluated (0: at the point of use)
+#endif
+    double f_t = a.f[0][o], f_r = a.f[2][o], f_w = a.f[3][o], f_h = a.f[4][o];
 #pragma unroll 2
     for (int i = i0; i < i1; ++i, o += n) {
+#if SB2_REG_PREFETCH_A
+        const double temp = f_t, rad = f_r, wind = f_w, rel_hum = f_h;
+        if (i + 1 < i1) { const int64_t o1 = o + n; f_t = a.f[0][o1]; f_r = a.f[2][o1]; f_w = a.f[3][o1]; f_h = a.f[4][o1]; }
+#else
         const double temp = a.f[0][o], rad = a.f[2][o], wind = a.f[3][o], rel_hum = a.f[4][o];
+#endif
         double lw, tadd;
         gs_energy_terms<true>(p, a.bb0, temp, wind, rel_hum, lw, tadd);
         s_pot[o] = pt_potential_evapotranspiration<true>(pt_albedo, pt_alpha, temp, rad, rel_hum) * 3600.0;

@@ -27,6 +27,7 @@ VARIANTS = {
     "hbvus0": ["-DSB2_HBV_UNIT_STEPS=0"], "hbvus32": ["-DSB2_HBV_UNIT_STEPS=32"], "hbvus128": ["-DSB2_HBV_UNIT_STEPS=128"],
     "lwcpair": ["-DSB2_LWC_PAIR=1"],
     "norpB": ["-DSB2_REG_PREFETCH_B=0"], "norpC": ["-DSB2_REG_PREFETCH_C=0"], "norpBC": ["-DSB2_REG_PREFETCH_B=0", "-DSB2_REG_PREFETCH_C=0"],
+    "rpA8": ["-DSB2_MINBLOCKS_A=8"], "norpA": ["-DSB2_REG_PREFETCH_A=0"],
     "hps2": ["-DSB2_HPS_MINBLOCKS=2"], "hps3": ["-DSB2_HPS_MINBLOCKS=3"],
     "pf0": ["-DSB2_PREFETCH_AHEAD=0"], "pf2": ["-DSB2_PREFETCH_AHEAD=2"], "pf8": ["-DSB2_PREFETCH_AHEAD=8"],
 }
