@@ -1229,7 +1229,7 @@ __global__ void __launch_bounds__(SB2_BLOCK_C, SB2_MINBLOCKS_C) ptgsk_response_k
     // Per-cell constants of the step (run_pt_gs_k prologue, pt_gs_k.h:347-357) live in shared memory, one column per thread: each is
     // read once or twice per step, and twelve doubles less in registers is one more resident warp per scheduler for the ODE solver.
 #if SB2_RESP_SMEM_CONST
-    __shared__ double cst[13][SB2_BLOCK_C];
+    __shared__ double cst[14][SB2_BLOCK_C];
 #define SB2_CST(k) (((volatile double*)cst[k])[threadIdx.x])
     {
         const double area = a.area[cc], gf = a.glacier[cc], lake = a.lake[cc], reservoir = a.reservoir[cc];
@@ -1248,8 +1248,10 @@ __global__ void __launch_bounds__(SB2_BLOCK_C, SB2_MINBLOCKS_C) ptgsk_response_k
         cst[10][threadIdx.x] = p.gm_dtf;
         cst[11][threadIdx.x] = p.p_corr_scale_factor;
         cst[12][threadIdx.x] = p.inv_ae_scale.y;
+        cst[13][threadIdx.x] = 1.0 / (SB2_K(K_MMH_M3S) * area);  // m3s_to_mmh divides by this per-cell constant every step: div_by
     }
     const unsigned ae_e_lo = p.inv_ae_scale.e_lo;
+    const unsigned mmh_e_lo = make_inv_divisor(SB2_K(K_MMH_M3S) * a.area[cc]).e_lo;
     __syncwarp();
 #define cell_area_m2 SB2_CST(0)
 #define glacier_fraction SB2_CST(1)
@@ -1321,7 +1323,12 @@ __global__ void __launch_bounds__(SB2_BLOCK_C, SB2_MINBLOCKS_C) ptgsk_response_k
                 (glacier_area_m2 <= sca_m2 || temp <= 0.0) ? 0.0 : gm_dtf * temp * (glacier_area_m2 - sca_m2) * SB2_K(K_GM);  // 0.001 / 86400.0
             // actual_evapotranspiration::calculate_step, actual_evapotranspiration.h:56-62
             const double ae = pot * (1.0 - sb_exp_flat<true>(div_by(-kq * 3.0, inv_ae))) * (1.0 - dmax(sca, glacier_fraction));
+#if SB2_RESP_SMEM_CONST
+            // m3s_to_mmh: the divisor is a per-cell constant, its reciprocal sits with the other per-cell constants (mostly 0 / x: no melt)
+            const double gm_mmh = div_by(gm_melt_m3s, InvDivisor{SB2_K(K_MMH_M3S) * cell_area_m2, SB2_CST(13), mmh_e_lo});
+#else
             const double gm_mmh = div_pos(gm_melt_m3s, SB2_K(K_MMH_M3S) * cell_area_m2);  // m3s_to_mmh; mostly 0 / x (no melt)
+#endif
             double q_avg, kq_new = active ? kq : 1.0;
             const double k_in = outflow * snow_storage_fraction + prec * kirchner_routed_prec + gm_routed * gm_mmh;
             if (!kirchner_step_warp<true>(a, c1, c2, c3, a.dt_hours, kq_new, q_avg, active ? k_in : 0.0, active ? ae : 0.0)) {
