@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, GPU pass (script reused per build: pass the tag as $1): parity tests, the default bench line, the launch list and one ncu --set full capture of the three step kernels
-# (a winter window of the shipped configuration: 2 048-step windows stepped in chunks of 1 024)
+# (superseded by tools/gpu_evidence.sh; kept for the round-1 profile names it produced)
 TAG=${1:-r02x}
 set -x
 mkdir -p gpurun_out
