@@ -112,3 +112,46 @@ def test_hbv_snow_sca_at_snowpack_buildup(oracle, s, sca_after):
     sp, sw, swe, sca = oracle.hbv_snow_distribute(10.0, 0.15, s, iv)
     sp, sw, swe, sca, out = oracle.hbv_snow_step(sp, sw, swe, sca, 0.15, -1.0, s=s, intervals=iv)
     assert sca == pytest.approx(sca_after, abs=1e-8)
+
+
+def test_pt_hps_k_oracle_properties(oracle):
+    """Properties of the restated stack that hold by construction of the reference's code (core/pt_hps_k.h:201-303, hbv_physical_snow.h:266-529):
+    a run in chunks carries its state exactly; iso_pot_energy is a diagnostic (switching it on changes that state and nothing else); without
+    precipitation and without a pack the snow routine passes nothing on; water is conserved over the snow routine step by step"""
+    T = 24 * 20
+    h = np.arange(T)
+    rng = np.random.default_rng(5)
+    f = dict(temperature=(-6.0 + 9.0 * np.sin(2 * np.pi * h / (24.0 * 9)) + rng.normal(0, 1.0, T))[:, None],
+             precipitation=(rng.exponential(1.2, T) * (rng.random(T) < 0.25))[:, None],
+             radiation=np.maximum(0.0, 250.0 * np.sin(2 * np.pi * (h - 6) / 24.0))[:, None], wind_speed=np.full((T, 1), 2.5), rel_hum=np.full((T, 1), 0.75))
+    geo = sc.geo_cell(lake=0.1, reservoir=0.1, glacier=0.05)
+    st0 = sc.hps_state(q=0.5)
+    par = sc.PTHPSK_DEFAULT.copy()
+    dt = 3600 * 10**6
+    one = oracle.pthpsk_run_cells(geo, par, f, st0, sc.T0, dt)
+    assert np.nanmax(one["snow_swe"]) > 1.0
+    # chunked = one shot
+    st, q = st0.copy(), []
+    for k in range(0, T, 96):
+        part = oracle.pthpsk_run_cells(geo, par, f, st, sc.T0, dt, start_step=k, n_steps=min(96, T - k))
+        st = part["state"]
+        q.append(part["avg_discharge"][k:k + 96])
+    assert np.array_equal(np.concatenate(q), one["avg_discharge"]) and np.array_equal(st, one["state"])
+    # iso_pot_energy: a diagnostic
+    par_iso = par.copy()
+    par_iso[15] = 1.0
+    iso = oracle.pthpsk_run_cells(geo, par_iso, f, st0, sc.T0, dt)
+    assert np.array_equal(iso["avg_discharge"], one["avg_discharge"]) and np.array_equal(iso["snow_swe"], one["snow_swe"])
+    assert np.any(iso["state"][0, 15:20] != 0.0) and np.all(one["state"][0, 15:20] == 0.0)
+    assert np.array_equal(np.delete(iso["state"], np.s_[15:20], axis=1), np.delete(one["state"], np.s_[15:20], axis=1))
+    # dry and bare: nothing leaves the snow routine
+    f_dry = {k: v.copy() for k, v in f.items()}
+    f_dry["precipitation"][:] = 0.0
+    dry = oracle.pthpsk_run_cells(geo, par, f_dry, st0, sc.T0, dt)
+    assert np.all(dry["snow_outflow"] == 0.0) and np.all(dry["snow_swe"] == 0.0) and np.all(dry["snow_sca"] == 0.0)
+    # water balance of the snow routine, step by step: swe_before + prec = swe_after + outflow (response swe and outflow both scaled by the
+    # snow storage fraction 0.8; mm per 1 h step)
+    frac = 0.8
+    swe = np.concatenate([[0.0], one["snow_swe"][:, 0]]) / frac
+    bal = swe[:-1] + f["precipitation"][:, 0] * par[17] - swe[1:] - one["snow_outflow"][:, 0] / frac
+    assert np.max(np.abs(bal)) < 1e-8
