@@ -155,3 +155,30 @@ def test_pt_hps_k_oracle_properties(oracle):
     swe = np.concatenate([[0.0], one["snow_swe"][:, 0]]) / frac
     bal = swe[:-1] + f["precipitation"][:, 0] * par[17] - swe[1:] - one["snow_outflow"][:, 0] / frac
     assert np.max(np.abs(bal)) < 1e-8
+
+
+def test_pt_ss_k_oracle_properties(oracle):
+    """pt_ss_k restated (core/pt_ss_k.h:195-293): a run in chunks carries its state exactly (num_units travels as a double in the flat state);
+    without precipitation and without a pack the Skaugen routine passes nothing on"""
+    T = 24 * 20
+    h = np.arange(T)
+    rng = np.random.default_rng(6)
+    f = dict(temperature=(-6.0 + 9.0 * np.sin(2 * np.pi * h / (24.0 * 9)) + rng.normal(0, 1.0, T))[:, None],
+             precipitation=(rng.exponential(1.2, T) * (rng.random(T) < 0.25))[:, None],
+             radiation=np.maximum(0.0, 250.0 * np.sin(2 * np.pi * (h - 6) / 24.0))[:, None], wind_speed=np.full((T, 1), 2.5), rel_hum=np.full((T, 1), 0.75))
+    geo = sc.geo_cell(lake=0.1, reservoir=0.1, glacier=0.05)
+    st0 = np.array([[4.077, 40.77, 0.0, 0.0, 0.0, 0.0, 0.0, 0.5]])
+    par = sc.PTSSK_DEFAULT.copy()
+    dt = 3600 * 10**6
+    one = oracle.ptssk_run_cells(geo, par, f, st0, sc.T0, dt)
+    assert np.nanmax(one["snow_swe"]) > 1.0
+    st, q = st0.copy(), []
+    for k in range(0, T, 96):
+        part = oracle.ptssk_run_cells(geo, par, f, st, sc.T0, dt, start_step=k, n_steps=min(96, T - k))
+        st = part["state"]
+        q.append(part["avg_discharge"][k:k + 96])
+    assert np.array_equal(np.concatenate(q), one["avg_discharge"]) and np.array_equal(st, one["state"])
+    f_dry = {k: v.copy() for k, v in f.items()}
+    f_dry["precipitation"][:] = 0.0
+    dry = oracle.ptssk_run_cells(geo, par, f_dry, st0, sc.T0, dt)
+    assert np.all(dry["snow_outflow"] == 0.0) and np.all(dry["snow_swe"] == 0.0) and np.all(dry["snow_sca"] == 0.0)
